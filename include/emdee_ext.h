@@ -1,0 +1,63 @@
+/*
+ * emdee_ext.h -- extensions that the reference API has no slot for.
+ *
+ * The reference (atoms-ufrj/EmDee) keeps its neighbor lists private (src/EmDeeData.f90:129) and is a
+ * single-process OpenMP library (no device, no ranks). These entry points exist so that
+ *   (1) parity tests can compare neighbor-list CONTENTS as pair sets (north_star: "bit-exact as
+ *       sorted pair sets") -- they read what src/neighbor_lists.f90:199-300 would have produced;
+ *   (2) a benchmark can ask which kernels ran and how long they took on the device;
+ *   (3) a multi-process launcher (one rank per GPU) can tell the library its rank layout.
+ * None of them is needed by a client that only uses emdee.h.
+ */
+#ifndef EMDEE_EXT_H
+#define EMDEE_EXT_H
+
+#include "emdee.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Number of unordered neighbor pairs currently held (pairs with r^2 < (Rc+skin)^2 at the last
+   rebuild, after exclusion / same-body / non-interacting-type filtering). */
+long long EmDeeX_pair_count( tEmDee md );
+
+/* Writes the pair list as 0-based atom indices, pairs[2*k] < pairs[2*k+1], in unspecified order.
+   `capacity` is the number of pairs the buffer can hold; returns the number written. */
+long long EmDeeX_download_pairs( tEmDee md, int* pairs, long long capacity );
+
+/* Release every host and device resource owned by the system (the reference has no destructor). */
+void EmDeeX_finalize( tEmDee* md );
+
+/* Implementation tag: "oracle-cpu" for the CPU restatement, "b200-cuda" for the product. */
+const char* EmDeeX_backend( void );
+
+#ifndef EMDEE_ORACLE_BUILD
+/* ---- product-only: device statistics -------------------------------------------------------- */
+
+typedef struct {
+  long long launches;         /* kernels of this library launched since EmDee_system */
+  long long force_launches;   /* launches of the pair-force kernel */
+  double    force_ms;         /* accumulated device time of the pair-force kernel (CUDA events) */
+  long long build_launches;   /* launches of the list-build kernel */
+  double    build_ms;         /* accumulated device time of the list-build kernel */
+  long long list_entries;     /* neighbor entries held by the device list (full list: 2 per pair) */
+  long long interacting;      /* entries with r^2 < Rc^2 at the last force evaluation (if counted) */
+  int       cells_per_dim;    /* M of the last rebuild */
+  int       device;           /* CUDA device ordinal */
+} tEmDeeXStats;
+
+void EmDeeX_stats( tEmDee md, tEmDeeXStats* out );
+
+/* Enable per-kernel CUDA-event timing of the force and build kernels (adds a sync per call). */
+void EmDeeX_set_kernel_timing( tEmDee md, int enabled );
+
+/* Block until all queued device work of this system has finished. */
+void EmDeeX_synchronize( tEmDee md );
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* EMDEE_EXT_H */

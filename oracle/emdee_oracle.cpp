@@ -1,0 +1,1763 @@
+// =================================================================================================
+// emdee_oracle.cpp -- TEST INFRASTRUCTURE. NOT PART OF THE PRODUCT.
+//
+// CPU (C++17 + OpenMP) restatement of the nonbonded hot path of atoms-ufrj/EmDee ("15 Oct 2018"):
+// the cell-list Verlet neighbor-list build and the pairwise force/energy/virial loop, behind the
+// same C ABI (include/emdee.h). The reference is Fortran 2008 and no Fortran compiler exists in the
+// build image, so the reference itself cannot be compiled (oracle/_ref is therefore absent); this
+// file follows the reference sources function by function and every function cites the file:line
+// it restates (paths relative to the reference tree).
+//
+// Who may use it: tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs -- as the checker or as the CPU baseline, never as the thing shipped. The product library
+// (emdee_b200/lib/libemdee.so) neither links nor calls anything in this directory.
+//
+// Parity pins (tests/test_oracle_pins.py): the reference's own live known-answer tests
+//   test/test_pair_lj_cut.f90:46, test/test_pair_lj_sf.f90:46 (100-step NVE, 800-atom NIST LJ),
+//   test/test_pair_lj_smoothed.f90:46 (valid for skin = 1.0),
+// NIST SRSW reference energies for the LJ sample, and the survey's independent O(N^2) probes.
+// Coulomb models, soft-core and rigid-body totals are NOT pinned by any reference test
+// ("parity unpinned" for those rows; self-consistency checks only).
+//
+// Two builds (oracle/Makefile): strict (-O2 -ffp-contract=off, defines bit-level truth for list
+// membership) and fast (-Ofast -march=native -fopenmp, mirrors reference Makefile:13,21; used for
+// CPU timing only).
+// =================================================================================================
+
+#define EMDEE_ORACLE_BUILD 1
+#include "../include/emdee.h"
+#include "../include/emdee_ext.h"
+
+#include <omp.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static_assert(sizeof(tEmDee) == 240, "tEmDee must match the reference layout (240 bytes)");
+static_assert(offsetof(tEmDee, Energy) == 40 && offsetof(tEmDee, Kinetic) == 104, "layout");
+static_assert(offsetof(tEmDee, Virial) == 192 && offsetof(tEmDee, Data) == 216, "layout");
+static_assert(offsetof(tEmDee, Options) == 224, "layout");
+
+namespace {
+
+// ---- src/global.f90:51-64 ----------------------------------------------------------------------
+[[noreturn]] void error(const char* task, const std::string& msg) {
+  std::fprintf(stderr, "Error in %s: %s.\n", task, msg.c_str());
+  std::fflush(stderr);
+  std::exit(1);
+}
+void warning(const std::string& msg) { std::fprintf(stderr, "WARNING: %s.\n", msg.c_str()); }
+
+// src/EmDeeData.f90:31-34
+constexpr int extra = 2000;
+constexpr int ndiv = 2;
+constexpr int nbcells = 62;
+
+// src/neighbor_lists.f90:26-35 -- half shell of the 5x5x5 stencil, as (x,y,z) triples
+constexpr int nb[nbcells][3] = {
+    {0, 0, 1},   {0, 1, 0},   {1, 0, 0},   {-1, 0, 1},  {-1, 1, 0},  {0, -1, 1},  {0, 1, 1},
+    {1, 0, 1},   {1, 1, 0},   {-1, -1, 1}, {-1, 1, 1},  {1, -1, 1},  {1, 1, 1},   {0, 0, 2},
+    {0, 2, 0},   {2, 0, 0},   {-2, 0, 1},  {-2, 1, 0},  {-1, 0, 2},  {-1, 2, 0},  {0, -2, 1},
+    {0, -1, 2},  {0, 1, 2},   {0, 2, 1},   {1, 0, 2},   {1, 2, 0},   {2, 0, 1},   {2, 1, 0},
+    {-2, -1, 1}, {-2, 1, 1},  {-1, -2, 1}, {-1, -1, 2}, {-1, 1, 2},  {-1, 2, 1},  {1, -2, 1},
+    {1, -1, 2},  {1, 1, 2},   {1, 2, 1},   {2, -1, 1},  {2, 1, 1},   {-2, 0, 2},  {-2, 2, 0},
+    {0, -2, 2},  {0, 2, 2},   {2, 0, 2},   {2, 2, 0},   {-2, -2, 1}, {-2, -1, 2}, {-2, 1, 2},
+    {-2, 2, 1},  {-1, -2, 2}, {-1, 2, 2},  {1, -2, 2},  {1, 2, 2},   {2, -2, 1},  {2, -1, 2},
+    {2, 1, 2},   {2, 2, 1},   {-2, -2, 2}, {-2, 2, 2},  {2, -2, 2},  {2, 2, 2}};
+
+// ---- models -------------------------------------------------------------------------------------
+// src/modelClass_nonbonded.f90:27-33
+enum Modifier { NONE = 0, SHIFTED, SHIFTED_FORCE, SMOOTHED, SHIFTED_SMOOTHED, SQUARE_SMOOTHED,
+                SHIFTED_SQUARE_SMOOTHED };
+
+enum Kind {
+  PAIR_NONE, PAIR_LJ_CUT, PAIR_SOFTCORE_CUT,
+  COUL_NONE, COUL_CUT, COUL_SF, COUL_DAMPED, COUL_LONG, COUL_DAMPED_SMOOTHED,
+  COUL_DAMPED_SQUARE_SMOOTHED, COUL_SQUARE_SMOOTHED, COUL_SHIFTED_SQUARE_SMOOTHED,
+  BOND_NONE, BOND_HARMONIC, ANGLE_NONE, ANGLE_HARMONIC, DIHEDRAL_NONE, KSPACE_EWALD
+};
+inline bool is_pair(Kind k) { return k <= PAIR_SOFTCORE_CUT; }
+inline bool is_coul(Kind k) { return k >= COUL_NONE && k <= COUL_SHIFTED_SQUARE_SMOOTHED; }
+inline bool is_nonbonded(Kind k) { return is_pair(k) || is_coul(k); }
+
+constexpr uint64_t MODEL_MAGIC = 0x4d4f44454c4f5243ull;
+
+// One flat record holds the union of the fields of the reference's model class hierarchy:
+// cModel (src/modelClass.f90:25-30), cNonBondedModel (src/modelClass_nonbonded.f90:36-50),
+// cCoulModel (src/modelClass_coul.f90:28-37) and the concrete models. Sharing one set of
+// (eshift, fshift, Rm, factor) between a Coulomb model and the modifier machinery is deliberate:
+// the reference does the same through inheritance, and results depend on it (see Q1 in DESIGN.md).
+struct Model {
+  uint64_t magic = MODEL_MAGIC;
+  Kind kind = PAIR_NONE;
+  const char* name = "none";
+  // cNonBondedModel
+  int modifier = NONE;
+  double eshift = 0, fshift = 0, skin = 0, Rm = 0, RmSq = 0, factor = 0, Rm2fac = 0;
+  // cCoulModel
+  bool shifted = false, shifted_force = false, requires_kspace = false;
+  double alpha = 0;
+  // pair_lj_cut / pair_softcore_cut
+  double epsilon = 0, sigma = 0, lambda = 0;
+  double eps4 = 0, eps24 = 0, sigsq = 0;
+  double prefactor = 0, prefactor6 = 0, invSigSq = 0, shift = 0;
+  // coulomb models
+  double damp = 0, skinWidth = 0, beta = 0, Rm2 = 0, invRm = 0;
+  // bonded / kspace (kept only so that handles can be created and validated)
+  double p1 = 0, p2 = 0, accuracy = 0;
+};
+
+constexpr double Pi = 3.14159265358979323846;
+
+// uerfc: src/math.f90:35-40, 685-691 (Abramowitz-Stegun 7.1.26 times a supplied exp(-x^2))
+inline double uerfc(double x, double expmx2) {
+  constexpr double a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027,
+                   a5 = 1.061405429, p = 0.327591100;
+  double t = 1.0 / (1.0 + p * x);
+  return t * (a1 + t * (a2 + t * (a3 + t * (a4 + t * a5)))) * expmx2;
+}
+
+// quintic switch shared by the smoothed Coulomb models and apply_modifier
+inline void switch_GW(double u, double c, double& G, double& WGu) {
+  double u2 = u * u;
+  double u3 = u * u2;
+  G = 1.0 + u3 * (15.0 * u - 6.0 * u2 - 10.0);
+  WGu = c * u2 * (2.0 * u - u2 - 1.0);   // caller multiplies by (factor * r) or (factor * r2)
+}
+
+// ---- model bodies: *_compute / *_energy / *_virial of each model file ----------------------------
+// MODE: 0 = compute (E and W), 1 = energy only, 2 = virial only.
+template <int MODE>
+inline void model_eval(const Model& m, double& Eij, double& Wij, double invR, double invR2) {
+  switch (m.kind) {
+    case PAIR_NONE:   // src/modelClass_pair.f90:165-190
+      if (MODE != 2) Eij = 0.0;
+      if (MODE != 1) Wij = 0.0;
+      break;
+    case COUL_NONE:   // src/modelClass_coul.f90:150-177 (coul_none_virial leaves Wij untouched)
+      if (MODE == 0) { Eij = 0.0; Wij = 0.0; }
+      if (MODE == 1) Eij = 0.0;
+      break;
+    case PAIR_LJ_CUT: {   // src/pair_lj_cut.f90:73-118
+      double sr2 = m.sigsq * invR2;
+      double sr6 = sr2 * sr2 * sr2;
+      double sr12 = sr6 * sr6;
+      if (MODE != 2) Eij = m.eps4 * (sr12 - sr6);
+      if (MODE != 1) Wij = m.eps24 * (sr12 + sr12 - sr6);
+      break;
+    }
+    case PAIR_SOFTCORE_CUT: {   // src/pair_softcore_cut.f90:86-135
+      double rsig2 = m.invSigSq / invR2;
+      double rsig6 = rsig2 * rsig2 * rsig2;
+      double sinv = 1.0 / (rsig6 + m.shift);
+      double sinvSq = sinv * sinv;
+      double sinvCb = sinv * sinvSq;
+      if (MODE != 2) Eij = m.prefactor * (sinvSq - sinv);
+      if (MODE != 1) Wij = m.prefactor6 * rsig6 * (sinvCb + sinvCb - sinvSq);
+      break;
+    }
+    case COUL_CUT:   // src/coul_cut.f90:62-94
+      if (MODE != 2) Eij = invR;
+      if (MODE != 1) Wij = invR;
+      break;
+    case COUL_SF: {   // src/coul_sf.f90:61-94
+      double rFc = m.fshift / invR;
+      if (MODE != 2) Eij = invR + m.eshift + rFc;
+      if (MODE != 1) Wij = invR - rFc;
+      break;
+    }
+    case COUL_DAMPED:   // src/coul_damped.f90:71-114
+    case COUL_LONG: {   // src/coul_long.f90:80-123
+      double x = m.alpha / invR;
+      double expmx2 = std::exp(-x * x);
+      double E = uerfc(x, expmx2) * invR;
+      if (MODE != 2) Eij = E;
+      if (MODE != 1) Wij = E + m.beta * expmx2;
+      break;
+    }
+    case COUL_DAMPED_SMOOTHED: {   // src/coul_damped_smoothed.f90:92-166
+      double r = 1.0 / invR;
+      double x = m.alpha * r;
+      double expmx2 = std::exp(-x * x);
+      double E = uerfc(x, expmx2) * invR;
+      double W = E + m.beta * expmx2;
+      if (r > m.Rm) {
+        double u = m.factor * (r - m.Rm);
+        double G, WG;
+        switch_GW(u, -30.0, G, WG);
+        WG = WG * m.factor * r;
+        W = W * G + E * WG;
+        E = E * G;
+      }
+      if (MODE != 2) Eij = E;
+      if (MODE != 1) Wij = W;
+      break;
+    }
+    case COUL_DAMPED_SQUARE_SMOOTHED: {   // src/coul_damped_square_smoothed.f90:91-165
+      double x = m.alpha / invR;
+      double expmx2 = std::exp(-x * x);
+      double E = uerfc(x, expmx2) * invR;
+      double W = E + m.beta * expmx2;
+      if (invR < m.invRm) {
+        double r2 = 1.0 / invR2;
+        double u = m.factor * (r2 - m.Rm2);
+        double G, WG;
+        switch_GW(u, -60.0, G, WG);
+        WG = WG * m.factor * r2;
+        W = W * G + E * WG;
+        E = E * G;
+      }
+      if (MODE != 2) Eij = E;
+      if (MODE != 1) Wij = W;
+      break;
+    }
+    case COUL_SQUARE_SMOOTHED: {   // src/coul_square_smoothed.f90:83-151
+      double W = invR, E = invR;
+      if (invR < m.invRm) {
+        double r2 = 1.0 / invR2;
+        double u = m.factor * (r2 - m.Rm2);
+        double G, WG;
+        switch_GW(u, -60.0, G, WG);
+        WG = WG * m.factor * r2;
+        if (MODE == 2) W = W * (G + WG);       // coul_square_smoothed_virial, line 148
+        else W = W * G + E * WG;
+        E = E * G;
+      }
+      if (MODE != 2) Eij = E;
+      if (MODE != 1) Wij = W;
+      break;
+    }
+    case COUL_SHIFTED_SQUARE_SMOOTHED: {   // src/coul_shifted_square_smoothed.f90:86-154
+      double W = invR;
+      double E = W + m.eshift;
+      if (invR < m.invRm) {
+        double r2 = 1.0 / invR2;
+        double u = m.factor * (r2 - m.Rm2);
+        double G, WG;
+        switch_GW(u, -60.0, G, WG);
+        WG = WG * m.factor * r2;
+        if (MODE == 2) W = W * G + (W + m.eshift) * WG;   // ..._virial, line 151
+        else W = W * G + E * WG;
+        E = E * G;
+      }
+      if (MODE != 2) Eij = E;
+      if (MODE != 1) Wij = W;
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// src/apply_modifier.f90:1-60
+template <bool COMPUTE>
+inline void apply_modifier(const Model& m, double& Eij, double& Wij, double invR, double invR2) {
+  switch (m.modifier) {
+    case SHIFTED:
+      if (COMPUTE) Eij = Eij + m.eshift;
+      break;
+    case SHIFTED_FORCE: {
+      double rFc = m.fshift / invR;
+      Wij = Wij - rFc;
+      if (COMPUTE) Eij = Eij + m.eshift + rFc;
+      break;
+    }
+    case SMOOTHED:
+    case SHIFTED_SMOOTHED:
+    case SQUARE_SMOOTHED:
+    case SHIFTED_SQUARE_SMOOTHED: {
+      const bool square = (m.modifier == SQUARE_SMOOTHED || m.modifier == SHIFTED_SQUARE_SMOOTHED);
+      if (COMPUTE) Eij = Eij + m.eshift;
+      double r2fac = square ? m.factor / invR2 : m.factor / invR;
+      if (r2fac > m.Rm2fac) {
+        if (!COMPUTE) {
+          double dummy = 0.0;
+          model_eval<1>(m, Eij, dummy, invR, invR2);
+          Eij = Eij + m.eshift;
+        }
+        double u = r2fac - m.Rm2fac;
+        double G, WG;
+        switch_GW(u, square ? -60.0 : -30.0, G, WG);
+        WG = WG * r2fac;
+        Wij = Wij * G + Eij * WG;
+        Eij = Eij * G;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// src/modelClass_nonbonded.f90:245-296
+void modifier_setup(Model& m, double cutoff) {
+  double Ec = 0, Wc = 0, Es = 0, Ws = 0;
+  m.fshift = 0.0;
+  m.eshift = 0.0;
+  m.Rm = cutoff - m.skin;
+  m.RmSq = m.Rm * m.Rm;
+  bool shifting = m.modifier == SHIFTED || m.modifier == SHIFTED_FORCE ||
+                  m.modifier == SHIFTED_SMOOTHED || m.modifier == SHIFTED_SQUARE_SMOOTHED;
+  if (shifting) model_eval<0>(m, Ec, Wc, 1.0 / cutoff, 1.0 / (cutoff * cutoff));
+  switch (m.modifier) {
+    case SHIFTED:
+      m.eshift = -Ec;
+      break;
+    case SHIFTED_FORCE:
+      m.eshift = -(Ec + Wc);
+      m.fshift = Wc / cutoff;
+      break;
+    case SMOOTHED:
+    case SHIFTED_SMOOTHED:
+      if (shifting) {
+        model_eval<0>(m, Es, Ws, 1.0 / m.Rm, 1.0 / m.RmSq);
+        m.eshift = -0.5 * (Es + Ec);
+      }
+      m.factor = 1.0 / (cutoff - m.Rm);
+      m.Rm2fac = m.factor * m.Rm;
+      break;
+    case SQUARE_SMOOTHED:
+    case SHIFTED_SQUARE_SMOOTHED:
+      if (shifting) {
+        model_eval<0>(m, Es, Ws, 1.0 / m.Rm, 1.0 / m.RmSq);
+        m.eshift = -0.5 * (Es + Ec);
+      }
+      m.factor = 1.0 / (cutoff * cutoff - m.RmSq);
+      m.Rm2fac = m.factor * m.RmSq;
+      break;
+    default:
+      break;
+  }
+}
+
+// *_apply_cutoff of the smoothed Coulomb models
+void apply_cutoff(Model& m, double Rc) {
+  switch (m.kind) {
+    case COUL_DAMPED_SMOOTHED:   // src/coul_damped_smoothed.f90:76-85
+      m.Rm = Rc - m.skinWidth;
+      m.Rm2 = m.Rm * m.Rm;
+      m.invRm = 1.0 / m.Rm;
+      m.factor = 1.0 / (Rc - m.Rm);
+      break;
+    case COUL_DAMPED_SQUARE_SMOOTHED:    // src/coul_damped_square_smoothed.f90:76-84
+    case COUL_SQUARE_SMOOTHED:           // src/coul_square_smoothed.f90:69-76
+    case COUL_SHIFTED_SQUARE_SMOOTHED:   // src/coul_shifted_square_smoothed.f90:72-79
+      m.Rm2 = (Rc - m.skinWidth) * (Rc - m.skinWidth);
+      m.invRm = 1.0 / (Rc - m.skinWidth);
+      m.factor = 1.0 / (Rc * Rc - m.Rm2);
+      break;
+    default:   // src/modelClass_coul.f90:97-101
+      break;
+  }
+}
+
+// src/modelClass_coul.f90:62-93
+void cutoff_setup(Model& m, double cutoff) {
+  m.fshift = 0.0;
+  m.eshift = 0.0;
+  if (m.shifted || m.shifted_force) {
+    double invR = 1.0 / cutoff;
+    double invR2 = invR * invR;
+    double E = 0, W = 0;
+    model_eval<0>(m, E, W, invR, invR2);
+    if (m.shifted_force) {
+      m.fshift = W / cutoff;
+      m.eshift = -(E + W);
+    } else {
+      m.fshift = 0.0;
+      m.eshift = -E;
+    }
+  }
+  apply_cutoff(m, cutoff);
+}
+
+// model setup routines
+void setup_lj(Model& m, double epsilon, double sigma) {   // src/pair_lj_cut.f90:52-69
+  m.kind = PAIR_LJ_CUT;
+  m.name = "lj_cut";
+  m.epsilon = epsilon;
+  m.sigma = sigma;
+  m.eps4 = 4.0 * epsilon;
+  m.eps24 = 24.0 * epsilon;
+  m.sigsq = sigma * sigma;
+}
+void setup_softcore(Model& m, double epsilon, double sigma, double lambda) {   // src/pair_softcore_cut.f90:58-82
+  m.kind = PAIR_SOFTCORE_CUT;
+  m.name = "softcore_cut";
+  m.epsilon = epsilon;
+  m.sigma = sigma;
+  m.lambda = lambda;
+  if (lambda < 0.0 || lambda > 1.0) error("pair_softcore_cut setup", "out-of-range parameter lambda");
+  m.prefactor = 4.0 * epsilon * lambda;          // lambda**exponent_n, exponent_n = 1
+  m.prefactor6 = 6.0 * m.prefactor;
+  m.invSigSq = 1.0 / (sigma * sigma);
+  m.shift = 0.5 * (1.0 - lambda);                // alpha*(1-lambda)**exponent_p, alpha = 1/2
+}
+
+// *_mix: returns true and fills `mixed` when a rule exists (src/pair_lj_cut.f90:122-138,
+// src/pair_softcore_cut.f90:139-163, src/modelClass_pair.f90:194-200)
+bool model_mix(const Model& self, const Model& other, Model& mixed) {
+  mixed = Model();
+  switch (self.kind) {
+    case PAIR_NONE:
+      mixed.kind = PAIR_NONE;
+      mixed.name = "none";
+      return true;
+    case PAIR_LJ_CUT:
+      if (other.kind == PAIR_LJ_CUT) {
+        setup_lj(mixed, std::sqrt(self.epsilon * other.epsilon), 0.5 * (self.sigma + other.sigma));
+        return true;
+      }
+      return false;
+    case PAIR_SOFTCORE_CUT:
+      if (other.kind == PAIR_SOFTCORE_CUT) {
+        setup_softcore(mixed, std::sqrt(self.epsilon * other.epsilon), 0.5 * (self.sigma + other.sigma),
+                       self.lambda * other.lambda);
+        return true;
+      }
+      if (other.kind == PAIR_LJ_CUT) {
+        setup_softcore(mixed, std::sqrt(self.epsilon * other.epsilon), 0.5 * (self.sigma + other.sigma),
+                       self.lambda);
+        return true;
+      }
+      return false;
+    default:
+      return false;
+  }
+}
+
+// src/modelClass_pair.f90:66-74
+struct PairContainer {
+  Model model;
+  bool coulomb = false;
+  double kCoul = 0.0;
+};
+
+// src/modelClass_pair.f90:120-140
+PairContainer container_mix(const PairContainer& a, const PairContainer& b) {
+  PairContainer c;
+  if (!model_mix(b.model, a.model, c.model)) {
+    if (!model_mix(a.model, b.model, c.model)) {
+      c.model = Model();
+      warning(std::string("no mixing rule found for models ") + a.model.name + " and " + b.model.name);
+    }
+  }
+  c.coulomb = a.coulomb && b.coulomb;
+  if (c.coulomb) c.kCoul = std::sqrt(a.kCoul * b.kCoul);
+  return c;
+}
+
+// ---- lists (src/lists.f90:26-99) ----------------------------------------------------------------
+struct List {
+  int nitems = 0, nobjects = 0, count = 0;
+  std::vector<int> first, middle, last, item;
+  std::vector<double> value;
+  bool has_value = false;
+  void allocate(int nitems_, int nobjects_, bool middle_ = false, bool value_ = false) {
+    nobjects = nobjects_;
+    nitems = nitems_;
+    count = 0;
+    first.assign(nobjects, 1);
+    last.assign(nobjects, 0);
+    item.assign(nitems, 0);
+    if (middle_) middle.assign(nobjects, 0);
+    has_value = value_;
+    if (value_) value.assign(nitems, 0.0);
+  }
+  void resize(int size) {
+    item.resize(size);
+    if (has_value) value.resize(size);
+    nitems = size;
+  }
+};
+
+// ---- RNG: KISS + ziggurat normal (src/math.f90:42-177) -------------------------------------------
+struct Kiss {
+  bool seeding_required = true;
+  int32_t kn[128];
+  double wn[128], fn[128];
+  uint32_t x, y, z, w;   // unsigned storage, two's-complement wraparound like gfortran's integer(4)
+  static uint32_t m(uint32_t k, int n) { return k ^ (n >= 0 ? (k << n) : (k >> (-n))); }
+  void init(int32_t seed) {   // src/math.f90:150-163
+    x = m(m(m((uint32_t)seed, 13), -17), 5);
+    y = m(m(m(x, 13), -17), 5);
+    z = m(m(m(y, 13), -17), 5);
+    w = m(m(m(z, 13), -17), 5);
+  }
+  int32_t i32() {   // src/math.f90:167-177
+    x = 69069u * x + 1327217885u;
+    y ^= (y << 13);
+    y ^= (y >> 17);
+    y ^= (y << 5);
+    z = 18000u * (z & 65535u) + (z >> 16);
+    w = 30903u * (w & 65535u) + (w >> 16);
+    return (int32_t)(x + y + (z << 16) + w);
+  }
+  void setup(int32_t seed) {   // src/math.f90:80-105
+    const double m1 = 2147483648.0;
+    init(seed);
+    seeding_required = false;
+    double dn = 3.442619855899, tn = 3.442619855899, vn = 0.00991256303526217;
+    double q = vn * std::exp(0.5 * dn * dn);
+    kn[0] = (int32_t)((dn / q) * m1);
+    kn[1] = 0;
+    wn[0] = q / m1;
+    wn[127] = dn / m1;
+    fn[0] = 1.0;
+    fn[127] = std::exp(-0.5 * dn * dn);
+    for (int i = 126; i >= 1; --i) {
+      dn = std::sqrt(-2.0 * std::log(vn / dn + std::exp(-0.5 * dn * dn)));
+      kn[i + 1] = (int32_t)((dn / tn) * m1);
+      tn = dn;
+      fn[i] = std::exp(-0.5 * dn * dn);
+      wn[i] = dn / m1;
+    }
+  }
+  static int32_t iabs(int32_t v) { return v < 0 ? (int32_t)(0u - (uint32_t)v) : v; }
+  double normal() {   // src/math.f90:109-146
+    const double r = 3.442620, s = 0.2328306e-9;
+    int32_t hz = i32();
+    int32_t iz = hz & 127;
+    if (iabs(hz) < kn[iz]) return hz * wn[iz];
+    for (;;) {
+      if (iz == 0) {
+        double xx, yy;
+        do {
+          xx = -0.2904764 * std::log(s * i32() + 0.5);
+          yy = -std::log(s * i32() + 0.5);
+        } while (!(yy + yy >= xx * xx));
+        double rnor = r + xx;
+        if (hz <= 0) rnor = -rnor;
+        return rnor;
+      }
+      double xx = hz * wn[iz];
+      if (fn[iz] + (s * i32() + 0.5) * (fn[iz - 1] - fn[iz]) < std::exp(-0.5 * xx * xx)) return xx;
+      hz = i32();
+      iz = hz & 127;
+      if (iabs(hz) < kn[iz]) return hz * wn[iz];
+    }
+  }
+};
+
+// src/math.f90:230-237
+inline double phi(double x) {
+  if (std::fabs(x) > 1e-4) return (1.0 - std::exp(-x)) / x;
+  return 1.0 + 0.5 * x * ((1.0 / 3.0) * x * (1.0 - 0.25 * x) - 1.0);
+}
+
+// src/math.f90:642-657
+double inverse_of_x_plus_ln_x(double y) {
+  const double tol = 1.0e-12;
+  double x = (y > 0.5671432904097839) ? y - std::log(y) : std::exp(y);
+  double x0 = x + 1.0;
+  while (std::fabs(x - x0) > tol * x0) {
+    x0 = x;
+    x = x * (y + 1.0 - std::log(x)) / (x + 1.0);
+  }
+  return x;
+}
+
+// ---- rigid bodies: only what the hot path reads (src/ArBee.f90:29-106) ---------------------------
+struct Body {
+  int NP = 0;
+  int dof = 6;
+  double mass = 0, invMass = 0;
+  double rcm[3] = {0, 0, 0};
+  std::vector<int> index;        // 0-based atom indices
+  std::vector<double> M;         // masses
+  std::vector<double> delta;     // 3*NP, space-frame positions relative to rcm
+};
+
+// ---- system state (src/EmDeeData.f90:66-151) -----------------------------------------------------
+struct Cell { int neighbor[nbcells]; };
+
+struct System {
+  int natoms = 0, mcells = 0, ncells = 0, maxcells = 0, maxatoms = 0, maxpairs = 0, ntypes = 1;
+  int nbodies = 0, nfree = 0, nthreads = 1, threadAtoms = 0, threadFreeAtoms = 0, threadBodies = 0;
+  int nlayers = 1, layer = 1;
+  bool hasL = false, hasR = false;
+  double Lbox = 0;
+  double Rc = 0, skin = 0, RcSq = 0, xRc = 0, xRcSq = 0, skinSq = 0, InRc = 0, InRcSq = 0, xInRcSq = 0;
+  double totalMass = 0, startTime = 0;
+  bool initialized = false;
+  Kiss random;
+  List cellAtom, threadCell, excluded;
+  std::vector<int> atomType, atomCell, atomBody, free_, atomsInCell;
+  std::vector<double> R, P, charge, mass, invMass, R0;
+  std::vector<char> charged;
+  std::vector<Body> body;
+  std::vector<Cell> cell;
+  std::vector<List> neighbor;
+  std::vector<PairContainer> pair;   // (ntypes, ntypes, nlayers)
+  std::vector<Model> coul;           // (nlayers)
+  Model kspace;
+  std::vector<char> multilayer, overridable, interact, pairs_exist;
+  std::vector<char> bonded, useInRc, forcesUpToDate;
+  std::vector<double> layerF;        // (3, N, nlayers)
+  std::vector<tEnergy> layerEnergy;
+  std::vector<tVirial> layerVirial;
+  bool multilayer_coulomb = false, kspace_active = false;
+
+  PairContainer& pr(int i, int j, int l) { return pair[(size_t)(l - 1) * ntypes * ntypes + (size_t)(j - 1) * ntypes + (i - 1)]; }
+  char& tt(std::vector<char>& a, int i, int j) { return a[(size_t)(j - 1) * ntypes + (i - 1)]; }
+  double* F() { return layerF.data() + (size_t)(layer - 1) * 3 * natoms; }
+  double layerRc(int l) const { return useInRc[l - 1] ? InRc : Rc; }
+};
+
+System* sys(const tEmDee& md) { return static_cast<System*>(md.Data); }
+
+std::string option_string(const char* option) {   // src/global.f90:120-128
+  std::string s;
+  for (int i = 0; i < 256 && option[i] != '\0'; ++i) s.push_back(option[i]);
+  return s;
+}
+
+bool ranged(std::initializer_list<int> idx, int imax) {   // src/global.f90:68-78
+  for (int i : idx)
+    if (!(i > 0 && i <= imax)) return false;
+  return true;
+}
+
+Model* as_model(void* handle) {
+  if (handle == nullptr) return nullptr;
+  Model* m = static_cast<Model*>(handle);
+  if (m->magic != MODEL_MAGIC) return nullptr;
+  return m;
+}
+void* deliver(const Model& m) { return new Model(m); }   // src/modelClass.f90:51-60 (never freed)
+
+// src/EmDeeData.f90:268-351
+void allocate_rigid_bodies(System& me, const int* bodies) {
+  const int N = me.natoms;
+  me.atomBody.assign(N, 0);
+  if (bodies != nullptr) {
+    // clean_body_indices (310-349): bodies with a single atom or id <= 0 become free atoms;
+    // the others are renumbered 1..nbodies in order of first appearance.
+    std::vector<int> index(N, 0), saved, amount, first;
+    for (int i = 0; i < N; ++i) {
+      int ibody = bodies[i];
+      if (ibody > 0) {
+        int j = -1;
+        for (size_t k = 0; k < saved.size(); ++k)
+          if (saved[k] == ibody) { j = (int)k; break; }
+        if (j < 0) {
+          saved.push_back(ibody);
+          amount.push_back(1);
+          first.push_back(i);
+          index[i] = 0;
+        } else {
+          amount[j] += 1;
+          index[i] = j + 1;
+          index[first[j]] = j + 1;
+        }
+      }
+    }
+    int nb_ = 0;
+    std::vector<int> renum(saved.size(), 0);
+    for (size_t j = 0; j < saved.size(); ++j)
+      if (amount[j] > 1) renum[j] = ++nb_;
+    for (int i = 0; i < N; ++i)
+      if (index[i] > 0) index[i] = renum[index[i] - 1];
+    me.atomBody = index;
+    me.nbodies = nb_;
+    me.free_.clear();
+    for (int i = 0; i < N; ++i)
+      if (me.atomBody[i] == 0) me.free_.push_back(i);
+    me.nfree = (int)me.free_.size();
+    me.body.assign(me.nbodies, Body());
+    for (int i = 0; i < N; ++i) {
+      int b = me.atomBody[i];
+      if (b > 0) {
+        me.body[b - 1].index.push_back(i);
+        me.body[b - 1].M.push_back(me.mass[i]);
+      }
+    }
+    for (auto& b : me.body) {   // tBody_setup, src/ArBee.f90:78-93
+      b.NP = (int)b.index.size();
+      b.mass = 0.0;
+      for (double mm : b.M) b.mass += mm;
+      b.invMass = 1.0 / b.mass;
+      b.delta.assign(3 * b.NP, 0.0);
+    }
+    int k = me.nbodies;
+    for (int j = 0; j < N; ++j)
+      if (me.atomBody[j] == 0) me.atomBody[j] = ++k;
+  } else {
+    me.nbodies = 0;
+    me.free_.resize(N);
+    for (int i = 0; i < N; ++i) {
+      me.free_[i] = i;
+      me.atomBody[i] = i + 1;
+    }
+    me.nfree = N;
+    me.body.clear();
+  }
+  me.threadFreeAtoms = (me.nfree + me.nthreads - 1) / me.nthreads;
+  me.threadBodies = (me.nbodies + me.nthreads - 1) / me.nthreads;
+}
+
+// src/EmDeeData.f90:420-439 + tBody_update (src/ArBee.f90:97-106; inertia/quaternion parts belong to
+// the rigid-body integrator and are outside the hot path)
+void update_rigid_bodies(System& me) {
+  const double L = me.Lbox, invL = 1.0 / L;
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+  for (int j = 0; j < me.nbodies; ++j) {
+    Body& b = me.body[j];
+    std::vector<double> R(3 * b.NP);
+    for (int i = 0; i < b.NP; ++i)
+      for (int x = 0; x < 3; ++x) R[3 * i + x] = me.R[3 * (size_t)b.index[i] + x];
+    for (int i = 1; i < b.NP; ++i)
+      for (int x = 0; x < 3; ++x) R[3 * i + x] = R[3 * i + x] - L * std::round(invL * (R[3 * i + x] - R[x]));
+    for (int x = 0; x < 3; ++x) {
+      double s = 0.0;
+      for (int i = 0; i < b.NP; ++i) s += b.M[i] * R[3 * i + x];
+      b.rcm[x] = s * b.invMass;
+    }
+    for (int i = 0; i < b.NP; ++i)
+      for (int x = 0; x < 3; ++x) b.delta[3 * i + x] = R[3 * i + x] - b.rcm[x];
+    for (int i = 0; i < b.NP; ++i)
+      for (int x = 0; x < 3; ++x) me.R[3 * (size_t)b.index[i] + x] = R[3 * i + x];
+  }
+}
+
+// src/EmDeeData.f90:193-223
+void check_actual_interactions(System& me) {
+  const int nt = me.ntypes;
+  std::vector<char> inter((size_t)nt * nt * me.nlayers, 0);
+  std::vector<char> neutral(nt, 1);
+  for (int i = 1; i <= nt; ++i) {
+    int cnt = 0;
+    for (int a = 0; a < me.natoms; ++a)
+      if (me.atomType[a] == i && me.charged[a]) ++cnt;
+    neutral[i - 1] = (cnt == 0);
+    for (int j = 1; j <= i; ++j) {
+      bool any = false;
+      for (int k = 1; k <= me.nlayers; ++k) {
+        PairContainer& p = me.pr(i, j, k);
+        bool no_pair = p.model.kind == PAIR_NONE;
+        bool no_coul = me.coul[k - 1].kind == COUL_NONE || !p.coulomb;
+        bool coul_only = no_pair && !no_coul;
+        bool inert = (no_pair && no_coul) || (coul_only && neutral[i - 1] && neutral[j - 1]);
+        inter[(size_t)(k - 1) * nt * nt + (size_t)(j - 1) * nt + (i - 1)] = !inert;
+        inter[(size_t)(k - 1) * nt * nt + (size_t)(i - 1) * nt + (j - 1)] = !inert;
+        any = any || !inert;
+      }
+      me.tt(me.interact, i, j) = any;
+      me.tt(me.interact, j, i) = any;
+    }
+  }
+  for (int k = 1; k <= me.nlayers; ++k) {
+    bool any = false;
+    // the reference's local `interact(i,j,k)` is only filled for j <= i; `any` over it is the same
+    for (size_t q = 0; q < (size_t)nt * nt; ++q) any = any || inter[(size_t)(k - 1) * nt * nt + q];
+    me.pairs_exist[k - 1] = any;
+  }
+}
+
+// src/EmDeeData.f90:227-264
+void set_pair_type(System& me, int itype, int jtype, int layer, const Model& model, double kCoul) {
+  const double cutoff = me.layerRc(layer);
+  if (!is_pair(model.kind)) error("pair model setup", "a valid pair model must be provided");
+  if (itype == jtype) {
+    PairContainer& ii = me.pr(itype, itype, layer);
+    ii.model = model;   // pairContainer = modelContainer copies the model only (modelClass_pair.f90:101-116)
+    ii.coulomb = kCoul != 0.0;
+    if (ii.coulomb) ii.kCoul = kCoul;
+    modifier_setup(ii.model, cutoff);
+    for (int ktype = 1; ktype <= me.ntypes; ++ktype) {
+      if (ktype != itype && me.tt(me.overridable, itype, ktype)) {
+        PairContainer mixed = container_mix(me.pr(ktype, ktype, layer), me.pr(itype, itype, layer));
+        modifier_setup(mixed.model, cutoff);
+        me.pr(itype, ktype, layer) = mixed;
+        me.pr(ktype, itype, layer) = mixed;
+      }
+    }
+  } else {
+    PairContainer& ij = me.pr(itype, jtype, layer);
+    ij.model = model;
+    ij.coulomb = kCoul != 0.0;
+    if (ij.coulomb) ij.kCoul = kCoul;
+    modifier_setup(ij.model, cutoff);
+    me.pr(jtype, itype, layer) = ij;
+  }
+}
+
+// src/EmDeeData.f90:359-416
+void perform_initialization(System& me, int& DoF, int& RotDoF) {
+  const char* task = "system initialization";
+  update_rigid_bodies(me);
+  int bodyDoF = 0;
+  for (auto& b : me.body) bodyDoF += b.dof;
+  RotDoF = bodyDoF - 3 * me.nbodies;
+  DoF = 3 * me.nfree + bodyDoF - 3;
+  check_actual_interactions(me);
+  bool any_required = false;
+  double kspaceRc = 0.0;
+  bool first = true;
+  for (int l = 1; l <= me.nlayers; ++l) {
+    if (me.coul[l - 1].requires_kspace) {
+      any_required = true;
+      if (first) { kspaceRc = me.layerRc(l); first = false; }
+      else if (me.layerRc(l) != kspaceRc)
+        error(task, "all layers with ewald-like coulomb models must have the same cutoff");
+    }
+  }
+  if (any_required != me.kspace_active) {
+    if (me.kspace_active) me.kspace_active = false;
+    else error(task, "a kspace solver is required, but has not been defined");
+  }
+  if (me.kspace_active) {
+    // cKspaceModel_initialize -> kspace_ewald_set_parameters (src/kspace_ewald.f90:82-99): only the
+    // Ewald splitting parameter feeds the real-space hot path. The reciprocal-space sum itself
+    // (src/kspace_ewald.f90:188-314) is outside the hot-path scope and is NOT evaluated.
+    double s = std::sqrt(inverse_of_x_plus_ln_x(-std::log(me.kspace.accuracy)));
+    double alpha = s / kspaceRc;
+    std::printf("KSPACE PARAMETERS: alpha = %10.5f and kmax = %10.5f\n", alpha, 2.0 * alpha * s);
+    warning("reciprocal-space Ewald terms are outside the hot-path scope and are not evaluated");
+    for (int l = 1; l <= me.nlayers; ++l) {
+      Model& c = me.coul[l - 1];
+      if (c.requires_kspace) {   // coul_long_kspace_setup, src/coul_long.f90:66-73
+        c.alpha = alpha;
+        c.beta = 2.0 * alpha / std::sqrt(Pi);
+      }
+    }
+  }
+  me.initialized = true;
+}
+
+// src/neighbor_lists.f90:41-59
+double maximum_approach_sq(int N, const double* R, const double* R0) {
+  auto dsq = [&](int i) {
+    double a = R[3 * (size_t)i] - R0[3 * (size_t)i], b = R[3 * (size_t)i + 1] - R0[3 * (size_t)i + 1],
+           c = R[3 * (size_t)i + 2] - R0[3 * (size_t)i + 2];
+    return a * a + b * b + c * c;
+  };
+  double maximum = dsq(0);
+  double next = maximum;
+  for (int i = 1; i < N; ++i) {
+    double deltaSq = dsq(i);
+    if (deltaSq > maximum) {
+      next = maximum;
+      maximum = deltaSq;
+    }
+  }
+  return maximum + 2 * std::sqrt(maximum * next) + next;
+}
+
+inline int ipbc(int x, int M) { return x < 0 ? x + M : (x >= M ? x - M : x); }
+
+// src/neighbor_lists.f90:63-171
+void distribute_atoms(System& me, int M, const double* Rs) {
+  const int MM = M * M;
+  const int T = me.nthreads;
+  bool make_cells = M != me.mcells;
+  int cells_per_thread = 0;
+  if (make_cells) {
+    me.mcells = M;
+    me.ncells = M * MM;
+    if (me.ncells > me.maxcells) {
+      me.cell.assign(me.ncells, Cell());
+      me.cellAtom.first.assign(me.ncells, 1);
+      me.cellAtom.last.assign(me.ncells, 0);
+      me.atomsInCell.assign(me.ncells, 0);
+      me.threadCell.allocate(0, T);
+      me.maxcells = me.ncells;
+    }
+    cells_per_thread = (me.ncells + T - 1) / T;
+  }
+  std::vector<int> maxNatoms(T, 0), threadNatoms(T, 0);
+  std::vector<int> next(me.natoms, 0);
+#pragma omp parallel num_threads(T)
+  {
+    const int thread = omp_get_thread_num() + 1;
+    int first, last;
+    if (make_cells) {
+      first = (thread - 1) * cells_per_thread + 1;
+      last = std::min(thread * cells_per_thread, me.ncells);
+      for (int icell = first; icell <= last; ++icell) {
+        int k = icell - 1;
+        int iz = k / MM;
+        int j = k - iz * MM;
+        int iy = j / M;
+        int ix = j - iy * M;
+        for (int q = 0; q < nbcells; ++q)
+          me.cell[icell - 1].neighbor[q] =
+              1 + ipbc(ix + nb[q][0], M) + ipbc(iy + nb[q][1], M) * M + ipbc(iz + nb[q][2], M) * MM;
+      }
+      me.threadCell.first[thread - 1] = first;
+      me.threadCell.last[thread - 1] = last;
+    } else {
+      first = me.threadCell.first[thread - 1];
+      last = me.threadCell.last[thread - 1];
+    }
+    const int a1 = (thread - 1) * me.threadAtoms + 1, aN = std::min(thread * me.threadAtoms, me.natoms);
+    for (int i = a1; i <= aN; ++i) {
+      int ic[3];
+      for (int x = 0; x < 3; ++x) {
+        double r = Rs[3 * (size_t)(i - 1) + x];
+        ic[x] = (int)(M * (r - std::floor(r)));
+        if (ic[x] >= M) ic[x] = M - 1;   // Q5: result-neutral clamp (the reference would index out of range)
+      }
+      me.atomCell[i - 1] = 1 + ic[0] + M * ic[1] + MM * ic[2];
+    }
+#pragma omp barrier
+    std::vector<int> head(std::max(last - first + 1, 0), 0);
+    for (int c = first; c <= last; ++c) me.atomsInCell[c - 1] = 0;
+    for (int i = 1; i <= me.natoms; ++i) {
+      int icell = me.atomCell[i - 1];
+      if (icell >= first && icell <= last) {
+        next[i - 1] = head[icell - first];
+        head[icell - first] = i;
+        me.atomsInCell[icell - 1] += 1;
+      }
+    }
+    int s = 0;
+    for (int c = first; c <= last; ++c) s += me.atomsInCell[c - 1];
+    threadNatoms[thread - 1] = s;
+#pragma omp barrier
+    int mx = 0;
+    int k = 0;
+    for (int t = 0; t < thread - 1; ++t) k += threadNatoms[t];
+    for (int icell = first; icell <= last; ++icell) {
+      me.cellAtom.first[icell - 1] = k + 1;
+      int i = head[icell - first];
+      while (i != 0) {
+        k += 1;
+        me.cellAtom.item[k - 1] = i;
+        i = next[i - 1];
+      }
+      me.cellAtom.last[icell - 1] = k;
+      if (me.atomsInCell[icell - 1] > mx) mx = me.atomsInCell[icell - 1];
+    }
+    maxNatoms[thread - 1] = mx;
+  }
+  me.maxatoms = *std::max_element(maxNatoms.begin(), maxNatoms.end());
+  me.maxpairs = (me.maxatoms * ((2 * nbcells + 1) * me.maxatoms - 1)) / 2;
+}
+
+inline double pbc(double x) { return x - std::round(x); }   // x - anint(x)
+
+// src/neighbor_lists.f90:199-300
+void build_neighbor_lists(System& me, int thread, const double* Rs) {
+  const double invL2 = 1.0 / (me.Lbox * me.Lbox);
+  const double xRc2 = me.xRcSq * invL2;
+  const double xInRc2 = me.xInRcSq * invL2;
+  std::vector<char> include(me.natoms, 1);
+  std::vector<int> atom((size_t)(nbcells + 1) * std::max(me.maxatoms, 1));
+  std::vector<double> Ratom;
+  int npairs = 0;
+  List& neighbor = me.neighbor[thread - 1];
+  const std::vector<int>& c1 = me.cellAtom.first;
+  const std::vector<int>& cN = me.cellAtom.last;
+  const int nt = me.ntypes;
+  for (int icell = me.threadCell.first[thread - 1]; icell <= me.threadCell.last[thread - 1]; ++icell) {
+    const int* neigh = me.cell[icell - 1].neighbor;
+    int nlocal = me.atomsInCell[icell - 1];
+    int ntotal = 0;
+    for (int k = c1[icell - 1]; k <= cN[icell - 1]; ++k) atom[ntotal++] = me.cellAtom.item[k - 1];
+    for (int q = 0; q < nbcells; ++q)
+      for (int k = c1[neigh[q] - 1]; k <= cN[neigh[q] - 1]; ++k) atom[ntotal++] = me.cellAtom.item[k - 1];
+    if (neighbor.nitems < npairs + nlocal * ntotal) neighbor.resize(npairs + nlocal * ntotal + extra);
+    Ratom.resize(3 * (size_t)ntotal);
+    for (int q = 0; q < ntotal; ++q)
+      for (int x = 0; x < 3; ++x) Ratom[3 * (size_t)q + x] = Rs[3 * (size_t)(atom[q] - 1) + x];
+    for (int k = 0; k < nlocal; ++k) {
+      int i = atom[k];
+      int first = npairs + 1;
+      neighbor.first[i - 1] = first;
+      int* item = neighbor.item.data() + (first - 1);
+      double* value = neighbor.value.data() + (first - 1);
+      int ipairs = 0, middle = 0;
+      int itype = me.atomType[i - 1];
+      int ibody = me.atomBody[i - 1];
+      const int x1 = me.excluded.first[i - 1], xN = me.excluded.last[i - 1];
+      for (int q = x1; q <= xN; ++q) include[me.excluded.item[q - 1] - 1] = 0;
+      for (int m = k + 1; m < ntotal; ++m) {
+        double dx = pbc(Ratom[3 * (size_t)k] - Ratom[3 * (size_t)m]);
+        double dy = pbc(Ratom[3 * (size_t)k + 1] - Ratom[3 * (size_t)m + 1]);
+        double dz = pbc(Ratom[3 * (size_t)k + 2] - Ratom[3 * (size_t)m + 2]);
+        double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 < xRc2) {
+          int j = atom[m];
+          if (include[j - 1]) {
+            if (me.atomBody[j - 1] != ibody) {
+              if (me.interact[(size_t)(itype - 1) * nt + (me.atomType[j - 1] - 1)]) {
+                // insert_neighbor (283-298): keep the atom's neighbors sorted by r2 ascending
+                int q;
+                for (q = ipairs; q >= 1; --q) {
+                  if (value[q - 1] < r2) break;
+                  value[q] = value[q - 1];
+                  item[q] = item[q - 1];
+                }
+                value[q] = r2;
+                item[q] = j;
+                ipairs += 1;
+                if (r2 < xInRc2) middle += 1;
+              }
+            }
+          }
+        }
+      }
+      for (int q = x1; q <= xN; ++q) include[me.excluded.item[q - 1] - 1] = 1;
+      neighbor.middle[i - 1] = npairs + middle;
+      npairs += ipairs;
+      neighbor.last[i - 1] = npairs;
+    }
+  }
+  neighbor.count = npairs;
+}
+
+// src/neighbor_lists.f90:175-195
+void handle_neighbor_lists(System& me, int& builds, double& time, const double* Rs) {
+  time -= omp_get_wtime();
+  if (maximum_approach_sq(me.natoms, me.R.data(), me.R0.data()) > me.skinSq) {
+    int M = (int)std::floor(ndiv * me.Lbox / me.xRc);
+    distribute_atoms(me, std::max(M, 2 * ndiv + 1), Rs);
+    me.R0 = me.R;
+    builds += 1;
+#pragma omp parallel num_threads(me.nthreads)
+    build_neighbor_lists(me, omp_get_thread_num() + 1, Rs);
+  }
+  time += omp_get_wtime();
+}
+
+// src/EmDeeData.f90:644-685 wrapping src/compute.f90:20-100
+template <bool COMPUTE>
+void compute_pairs(System& me, int thread, const double* Rs, double* F, double& Epair, double& Ecoul,
+                   double& Wpair, double& Wcoul) {
+  const int N = me.natoms;
+  std::fill(F, F + 3 * (size_t)N, 0.0);
+  Wpair = 0.0;
+  Wcoul = 0.0;
+  Epair = 0.0;
+  // NOTE: Ecoul is intent(out) in the reference but only ever accumulated; the caller zeroes E(:).
+  if (!me.pairs_exist[me.layer - 1]) return;
+  const double L2 = me.Lbox * me.Lbox;
+  const double invL2 = 1.0 / L2;
+  double Rc2;
+  const std::vector<int>* upper;
+  List& neighbor = me.neighbor[thread - 1];
+  if (me.useInRc[me.layer - 1]) {
+    Rc2 = me.InRcSq * invL2;
+    upper = &neighbor.middle;
+  } else {
+    Rc2 = me.RcSq * invL2;
+    upper = &neighbor.last;
+  }
+  const int tfirst = me.threadCell.first[thread - 1], tlast = me.threadCell.last[thread - 1];
+  if (tlast < tfirst) return;
+  const int firstAtom = me.cellAtom.first[tfirst - 1];
+  const int lastAtom = me.cellAtom.last[tlast - 1];
+  const Model& coul = me.coul[me.layer - 1];
+  for (int k = firstAtom; k <= lastAtom; ++k) {
+    const int i = me.cellAtom.item[k - 1];
+    const int itype = me.atomType[i - 1];
+    const double Qi = me.charge[i - 1];
+    const bool icharged = me.charged[i - 1];
+    const double Ri[3] = {Rs[3 * (size_t)(i - 1)], Rs[3 * (size_t)(i - 1) + 1], Rs[3 * (size_t)(i - 1) + 2]};
+    double Fi[3] = {0.0, 0.0, 0.0};
+    for (int m = neighbor.first[i - 1]; m <= (*upper)[i - 1]; ++m) {
+      const int j = neighbor.item[m - 1];
+      const double Rij[3] = {pbc(Ri[0] - Rs[3 * (size_t)(j - 1)]), pbc(Ri[1] - Rs[3 * (size_t)(j - 1) + 1]),
+                             pbc(Ri[2] - Rs[3 * (size_t)(j - 1) + 2])};
+      const double r2 = Rij[0] * Rij[0] + Rij[1] * Rij[1] + Rij[2] * Rij[2];
+      if (r2 < Rc2) {
+        const double invR2 = invL2 / r2;
+        const double invR = std::sqrt(invR2);
+        const int jtype = me.atomType[j - 1];
+        const bool ijcharged = icharged && me.charged[j - 1];
+        const PairContainer& pair = me.pr(jtype, itype, me.layer);
+        double Eij = 0.0, Wij = 0.0;
+        model_eval<COMPUTE ? 0 : 2>(pair.model, Eij, Wij, invR, invR2);
+        apply_modifier<COMPUTE>(pair.model, Eij, Wij, invR, invR2);
+        if (COMPUTE) Epair = Epair + Eij;
+        Wpair = Wpair + Wij;
+        double Wsum = Wij;
+        if (ijcharged && pair.coulomb) {
+          model_eval<COMPUTE ? 0 : 2>(coul, Eij, Wij, invR, invR2);   // Q4: coul_none leaves Wij in virial mode
+          apply_modifier<COMPUTE>(coul, Eij, Wij, invR, invR2);
+          const double QiQj = pair.kCoul * Qi * me.charge[j - 1];
+          if (COMPUTE) Ecoul = Ecoul + QiQj * Eij;
+          Wij = QiQj * Wij;
+          Wcoul = Wcoul + Wij;
+          Wsum = Wsum + Wij;
+        }
+        const double s = Wsum * invR2;
+        for (int x = 0; x < 3; ++x) {
+          const double Fij = s * Rij[x];
+          Fi[x] = Fi[x] + Fij;
+          F[3 * (size_t)(j - 1) + x] = F[3 * (size_t)(j - 1) + x] - Fij;
+        }
+      }
+    }
+    for (int x = 0; x < 3; ++x) F[3 * (size_t)(i - 1) + x] = F[3 * (size_t)(i - 1) + x] + Fi[x];
+  }
+  for (size_t q = 0; q < 3 * (size_t)N; ++q) F[q] = me.Lbox * F[q];
+}
+
+// src/EmDeeData.f90:926-953
+double rigid_body_virial(System& me) {
+  std::vector<double> W(me.nthreads, 0.0);
+#pragma omp parallel num_threads(me.nthreads)
+  {
+    const int thread = omp_get_thread_num() + 1;
+    double w = 0.0;
+    const double* F = me.F();
+    for (int i = (thread - 1) * me.threadBodies + 1; i <= std::min(thread * me.threadBodies, me.nbodies); ++i) {
+      const Body& b = me.body[i - 1];
+      double s = 0.0;
+      for (int a = 0; a < b.NP; ++a)
+        for (int x = 0; x < 3; ++x) s += F[3 * (size_t)b.index[a] + x] * b.delta[3 * a + x];
+      w = w + s;
+    }
+    W[thread - 1] = w;
+  }
+  double tot = 0.0;
+  for (double w : W) tot += w;
+  return -tot;
+}
+
+void invalidate(System& me, tEmDee* md) {
+  std::fill(me.forcesUpToDate.begin(), me.forcesUpToDate.end(), 0);
+  for (auto& e : me.layerEnergy) e.UpToDate = false;
+  md->Energy.UpToDate = false;
+}
+
+[[noreturn]] void out_of_scope(const char* task) {
+  error(task, "this entry point is outside the nonbonded hot-path scope of the oracle");
+}
+
+}  // namespace
+
+// =================================================================================================
+//                                     C   A B I
+// =================================================================================================
+extern "C" {
+
+const char* EmDeeX_backend(void) { return "oracle-cpu"; }
+
+// src/EmDeeCode.f90:69-208
+tEmDee EmDee_system(int threads, int layers, double rc, double skin, int N, int* types, double* masses,
+                    int* bodies) {
+  if (std::getenv("EMDEE_QUIET") == nullptr) std::printf("EmDee (version: %11s)\n", "15 Oct 2018");
+  System* me = new System();
+  me->nthreads = threads;
+  me->nlayers = layers;
+  me->Rc = rc;
+  me->skin = skin;
+  me->RcSq = rc * rc;
+  me->xRc = rc + skin;
+  me->xRcSq = me->xRc * me->xRc;
+  me->InRc = me->Rc;
+  me->InRcSq = me->RcSq;
+  me->xInRcSq = me->xRcSq;
+  me->skinSq = skin * skin;
+  me->natoms = N;
+  me->threadAtoms = (N + threads - 1) / threads;
+  me->kspace_active = false;
+  if (types != nullptr) {
+    if (*std::min_element(types, types + N) != 1) error("system setup", "wrong specification of atom types");
+    me->ntypes = *std::max_element(types, types + N);
+    me->atomType.assign(types, types + N);
+  } else {
+    me->ntypes = 1;
+    me->atomType.assign(N, 1);
+  }
+  if (masses != nullptr) {
+    me->mass.resize(N);
+    me->invMass.resize(N);
+    me->totalMass = 0.0;
+    for (int i = 0; i < N; ++i) {
+      me->mass[i] = masses[me->atomType[i] - 1];
+      me->invMass[i] = 1.0 / masses[me->atomType[i] - 1];
+      me->totalMass += masses[me->atomType[i] - 1];
+    }
+  } else {
+    me->mass.assign(N, 1.0);
+    me->invMass.assign(N, 1.0);
+    me->totalMass = (double)N;
+  }
+  me->startTime = omp_get_wtime();
+  me->P.assign(3 * (size_t)N, 0.0);
+  me->R0.assign(3 * (size_t)N, 0.0);
+  me->charge.assign(N, 0.0);
+  me->charged.assign(N, 0);
+  me->atomCell.assign(N, 0);
+  allocate_rigid_bodies(*me, bodies);
+  me->cellAtom.allocate(N, 0);
+  me->neighbor.resize(threads);
+  for (auto& l : me->neighbor) l.allocate(extra, N, true, true);
+  me->excluded.allocate(extra, N);
+  me->pair.assign((size_t)me->ntypes * me->ntypes * layers, PairContainer());
+  me->multilayer.assign((size_t)me->ntypes * me->ntypes, 0);
+  me->overridable.assign((size_t)me->ntypes * me->ntypes, 1);
+  me->interact.assign((size_t)me->ntypes * me->ntypes, 0);
+  Model noCoul;
+  noCoul.kind = COUL_NONE;
+  me->multilayer_coulomb = false;
+  me->coul.assign(layers, noCoul);
+  me->pairs_exist.assign(layers, 0);
+  me->useInRc.assign(layers, 0);
+  me->bonded.assign(layers, 1);
+  me->forcesUpToDate.assign(layers, 0);
+  me->layerF.assign(3 * (size_t)N * layers, 0.0);
+  me->layer = 1;
+  me->initialized = false;
+
+  tEmDee md;
+  std::memset(&md, 0, sizeof(md));
+  md.Builds = 0;
+  md.Energy.UpToDate = false;
+  me->layerEnergy.assign(layers, md.Energy);
+  me->layerVirial.assign(layers, md.Virial);
+  md.DoF = 3 * (N - 1);
+  md.RotDoF = 0;
+  md.Data = me;
+  md.Options.Translate = true;
+  md.Options.Rotate = true;
+  md.Options.RotationMode = 0;
+  md.Options.AutoBodyUpdate = true;
+  md.Options.Compute = true;
+  return md;
+}
+
+// src/EmDeeCode.f90:212-235
+void* EmDee_memory_address(tEmDee md, const char* option) {
+  System* me = sys(md);
+  std::string item = option_string(option);
+  if (item == "coordinates") return me->R.data();
+  if (item == "momenta") return me->P.data();
+  if (item == "forces") return me->F();
+  if (item == "layerForces") return me->layerF.data();
+  error("memory address retrieving", "invalid option " + item);
+}
+
+void EmDee_share_phase_space(tEmDee, tEmDee*) { out_of_scope("phase space sharing"); }
+
+// src/EmDeeCode.f90:273-305
+void EmDee_layer_based_parameters(tEmDee md, double InternalRc, int* Apply, int* Bonded) {
+  const char* task = "layer-based parameter setting";
+  System* me = sys(md);
+  if (me->initialized) error(task, "system has already been initialized");
+  bool any = false;
+  for (int l = 0; l < me->nlayers; ++l) {
+    me->useInRc[l] = Apply[l] != 0;
+    any = any || me->useInRc[l];
+  }
+  if (any && (InternalRc <= 0.0 || InternalRc > me->Rc)) error(task, "invalid internal cutoff specification");
+  me->InRc = InternalRc;
+  me->InRcSq = InternalRc * InternalRc;
+  me->xInRcSq = (InternalRc + me->skin) * (InternalRc + me->skin);
+  for (int l = 0; l < me->nlayers; ++l) me->bonded[l] = Bonded[l] != 0;
+  for (int l = 1; l <= me->nlayers; ++l) cutoff_setup(me->coul[l - 1], me->layerRc(l));
+}
+
+// src/EmDeeCode.f90:309-359
+void EmDee_set_pair_model(tEmDee md, int itype, int jtype, void* model, double kCoul) {
+  const char* task = "pair model setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  if (!ranged({itype, jtype}, me->ntypes)) error(task, "provided type index is out of range");
+  Model* m = as_model(model);
+  if (m == nullptr || !is_pair(m->kind)) error(task, "a valid pair model must be provided");
+  for (int layer = 1; layer <= me->nlayers; ++layer) set_pair_type(*me, itype, jtype, layer, *m, kCoul);
+  me->tt(me->multilayer, itype, jtype) = 0;
+  me->tt(me->multilayer, jtype, itype) = 0;
+  if (itype == jtype) {
+    for (int k = 1; k <= me->ntypes; ++k)
+      if (k != itype && me->tt(me->overridable, itype, k)) {
+        me->tt(me->multilayer, itype, k) = me->tt(me->multilayer, k, k);
+        me->tt(me->multilayer, k, itype) = me->tt(me->multilayer, k, k);
+      }
+  } else {
+    me->tt(me->overridable, itype, jtype) = 0;
+    me->tt(me->overridable, jtype, itype) = 0;
+  }
+}
+
+// src/EmDeeCode.f90:363-412
+void EmDee_set_pair_multimodel(tEmDee md, int itype, int jtype, void* model[], double kCoul[]) {
+  const char* task = "pair multimodel setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  if (!ranged({itype, jtype}, me->ntypes)) error(task, "provided type index is out of range");
+  for (int layer = 1; layer <= me->nlayers; ++layer) {
+    Model* m = as_model(model[layer - 1]);
+    if (m == nullptr) error(task, std::to_string(me->nlayers) + " valid pair models must be provided");
+    if (!is_pair(m->kind)) error(task, "a valid pair model must be provided");
+    set_pair_type(*me, itype, jtype, layer, *m, kCoul[layer - 1]);
+  }
+  me->tt(me->multilayer, itype, jtype) = 1;
+  me->tt(me->multilayer, jtype, itype) = 1;
+  if (itype == jtype) {
+    for (int k = 1; k <= me->ntypes; ++k)
+      if (k != itype && me->tt(me->overridable, itype, k)) {
+        me->tt(me->multilayer, itype, k) = 1;
+        me->tt(me->multilayer, k, itype) = 1;
+      }
+  } else {
+    me->tt(me->overridable, itype, jtype) = 0;
+    me->tt(me->overridable, jtype, itype) = 0;
+  }
+}
+
+// src/EmDeeCode.f90:416-444 (only the Ewald accuracy is kept; see perform_initialization)
+void EmDee_set_kspace_model(tEmDee md, void* model) {
+  const char* task = "kspace model setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  Model* m = as_model(model);
+  if (m == nullptr || m->kind != KSPACE_EWALD) error(task, "a valid kspace model must be provided");
+  me->kspace = *m;
+  me->kspace_active = true;
+}
+
+// src/EmDeeCode.f90:448-482
+void EmDee_set_coul_model(tEmDee md, void* model) {
+  const char* task = "coulomb model setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  Model* m = as_model(model);
+  if (m == nullptr || !is_coul(m->kind)) error(task, "a valid coulomb model must be provided");
+  for (int layer = 1; layer <= me->nlayers; ++layer) {
+    double layerRc = me->layerRc(layer);
+    me->coul[layer - 1] = *m;
+    cutoff_setup(me->coul[layer - 1], layerRc);
+    modifier_setup(me->coul[layer - 1], layerRc);   // zeroes eshift/fshift again and resets Rm: Q1
+  }
+  me->multilayer_coulomb = false;
+}
+
+// src/EmDeeCode.f90:486-520
+void EmDee_set_coul_multimodel(tEmDee md, void* model[]) {
+  const char* task = "coulomb multimodel setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  for (int layer = 1; layer <= me->nlayers; ++layer) {
+    double layerRc = me->layerRc(layer);
+    Model* m = as_model(model[layer - 1]);
+    if (m == nullptr) error(task, std::to_string(me->nlayers) + " valid coulomb models must be provided");
+    if (!is_coul(m->kind)) error(task, "a valid coulomb model must be provided");
+    me->coul[layer - 1] = *m;
+    cutoff_setup(me->coul[layer - 1], layerRc);
+    modifier_setup(me->coul[layer - 1], layerRc);
+  }
+  me->multilayer_coulomb = true;
+}
+
+// src/EmDeeCode.f90:524-570. The reference keeps, per atom, a sorted duplicate-free CSR row.
+void EmDee_ignore_pair(tEmDee md, int i, int j) {
+  System* me = sys(md);
+  if (i == j || !ranged({i, j}, me->natoms)) return;
+  List& ex = me->excluded;
+  int n = ex.count;
+  if (n + 2 > ex.nitems) ex.resize(n + extra);   // reference resizes when n == nitems; same effect, no overrun
+  auto add_item = [&](int a, int b) {
+    int start = ex.first[a - 1];
+    int end = ex.last[a - 1];
+    int pos;   // 1-based insertion position
+    if (end < start) pos = end + 1;
+    else if (b > ex.item[end - 1]) pos = end + 1;
+    else {
+      while (b > ex.item[start - 1]) start += 1;
+      if (b == ex.item[start - 1]) return;
+      pos = start;
+    }
+    for (int q = n; q >= pos; --q) ex.item[q] = ex.item[q - 1];
+    ex.item[pos - 1] = b;
+    for (int q = a; q < me->natoms; ++q) ex.first[q] += 1;
+    for (int q = a - 1; q < me->natoms; ++q) ex.last[q] += 1;
+    n += 1;
+  };
+  add_item(i, j);
+  add_item(j, i);
+  ex.count = n;
+}
+
+void EmDee_add_bond(tEmDee, int, int, void*) { out_of_scope("add_bond"); }
+void EmDee_add_angle(tEmDee, int, int, int, void*) { out_of_scope("add_angle"); }
+void EmDee_add_dihedral(tEmDee, int, int, int, int, void*) { out_of_scope("add_dihedral"); }
+
+void EmDee_compute_forces(tEmDee* md);
+
+// src/EmDeeCode.f90:659-801
+void EmDee_download(tEmDee md, const char* option, double* address) {
+  System* me = sys(md);
+  std::string item = option_string(option);
+  if (address == nullptr) error("download", "provided address is invalid");
+  const size_t n3 = 3 * (size_t)me->natoms;
+  if (item == "box") {
+    *address = me->Lbox;
+  } else if (item == "coordinates") {
+    if (!me->hasR) error("download", "coordinates have not been allocated");
+    std::copy(me->R.begin(), me->R.end(), address);
+  } else if (item == "momenta") {
+    if (me->nbodies != 0) out_of_scope("download (momenta of rigid bodies)");
+    std::copy(me->P.begin(), me->P.end(), address);
+  } else if (item == "forces") {
+    if (!me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(&md);
+    std::copy(me->F(), me->F() + n3, address);
+  } else if (item == "centersOfMass") {
+    for (int b = 0; b < me->nbodies; ++b)
+      for (int x = 0; x < 3; ++x) address[3 * (size_t)b + x] = me->body[b].rcm[x];
+    for (int f = 0; f < me->nfree; ++f)
+      for (int x = 0; x < 3; ++x) address[3 * (size_t)(me->nbodies + f) + x] = me->R[3 * (size_t)me->free_[f] + x];
+  } else if (item == "quaternions" || item == "quatmom" || item == "quattau" || item == "angmom" ||
+             item == "bodycoord" || item == "bodymom" || item == "bodyforces" || item == "torques" ||
+             item == "inertia") {
+    out_of_scope("download (rigid-body dynamics)");
+  } else {
+    error("download", "invalid option");
+  }
+}
+
+// src/EmDeeCode.f90:929-946
+void EmDee_switch_model_layer(tEmDee* md, int layer) {
+  System* me = sys(*md);
+  if (layer != me->layer) {
+    if (layer < 1 || layer > me->nlayers) error("model layer switch", "selected layer is out of range");
+    me->layer = layer;
+    md->Energy = me->layerEnergy[layer - 1];
+    md->Virial = me->layerVirial[layer - 1];
+  }
+}
+
+// src/EmDeeCode.f90:805-925
+void EmDee_upload(tEmDee* md, const char* option, double* address) {
+  System* me = sys(*md);
+  std::string item = option_string(option);
+  if (address == nullptr) error("upload", "provided address is invalid");
+  auto initialize_system = [&]() {   // 916-923
+    perform_initialization(*me, md->DoF, md->RotDoF);
+    for (int layer = me->nlayers; layer >= 1; --layer) {
+      EmDee_switch_model_layer(md, layer);
+      EmDee_compute_forces(md);
+    }
+  };
+  const size_t n3 = 3 * (size_t)me->natoms;
+  if (item == "box") {
+    me->hasL = true;
+    me->Lbox = *address;
+    if (me->initialized) invalidate(*me, md);
+    else if (me->hasR) initialize_system();
+  } else if (item == "coordinates") {
+    if (!me->hasR) { me->R.assign(n3, 0.0); me->hasR = true; }
+    std::copy(address, address + n3, me->R.begin());
+    if (me->initialized) {
+      invalidate(*me, md);
+      if (md->Options.AutoBodyUpdate) update_rigid_bodies(*me);
+    } else if (me->hasL) {
+      initialize_system();
+    }
+  } else if (item == "momenta") {
+    if (!me->initialized) error("upload", "box and coordinates have not been defined");
+    if (me->nbodies != 0) out_of_scope("upload (momenta of rigid bodies)");
+    // assign_momenta, src/EmDeeData.f90:157-189 (free atoms)
+    double twoKEt[3] = {0, 0, 0};
+    for (int f = 0; f < me->nfree; ++f) {
+      int i = me->free_[f];
+      for (int x = 0; x < 3; ++x) {
+        me->P[3 * (size_t)i + x] = address[3 * (size_t)i + x];
+        twoKEt[x] += me->invMass[i] * address[3 * (size_t)i + x] * address[3 * (size_t)i + x];
+      }
+    }
+    for (int x = 0; x < 3; ++x) { md->Kinetic.RotPart[x] = 0.0; md->Kinetic.TransPart[x] = 0.5 * twoKEt[x]; }
+    md->Kinetic.Rotational = 0.0;
+    md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] +
+                        md->Kinetic.Rotational;
+    md->Kinetic.ShadowKinetic = md->Kinetic.Total;
+    md->Kinetic.ShadowRotational = md->Kinetic.Rotational;
+    md->Kinetic.UpToDate = true;
+  } else if (item == "forces") {
+    if (!me->initialized) error("upload", "box and coordinates have not been defined");
+    std::copy(address, address + n3, me->F());
+  } else if (item == "charges") {
+    if (me->initialized) error("upload", "cannot set charges after box and coordinates initialization");
+    for (int i = 0; i < me->natoms; ++i) {
+      me->charge[i] = address[i];
+      me->charged[i] = std::fabs(address[i]) > 2.220446049250313e-16;   // epsilon(one)
+    }
+    invalidate(*me, md);
+  } else {
+    error("upload", "invalid option");
+  }
+}
+
+// src/EmDeeCode.f90:950-1020 (free atoms; rigid-body momenta need the ArBee integrator)
+void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {
+  System* me = sys(*md);
+  if (me->random.seeding_required) me->random.setup(seed);
+  if (me->nbodies != 0) out_of_scope("random_momenta (rigid bodies)");
+  double twoKEt[3] = {0, 0, 0};
+  Kiss& rng = me->random;
+  for (int f = 0; f < me->nfree; ++f) {
+    int i = me->free_[f];
+    double s = std::sqrt(me->mass[i] * kT);
+    for (int x = 0; x < 3; ++x) me->P[3 * (size_t)i + x] = s * rng.normal();
+    for (int x = 0; x < 3; ++x) twoKEt[x] += me->invMass[i] * me->P[3 * (size_t)i + x] * me->P[3 * (size_t)i + x];
+  }
+  if (adjust) {   // adjust_momenta, 994-1018
+    double vcm[3];
+    for (int x = 0; x < 3; ++x) {
+      double s = 0.0;
+      for (int f = 0; f < me->nfree; ++f) s += me->P[3 * (size_t)me->free_[f] + x];
+      vcm[x] = s / me->totalMass;
+    }
+    for (int x = 0; x < 3; ++x) twoKEt[x] = 0.0;
+    for (int f = 0; f < me->nfree; ++f) {
+      int i = me->free_[f];
+      for (int x = 0; x < 3; ++x) {
+        me->P[3 * (size_t)i + x] = me->P[3 * (size_t)i + x] - me->mass[i] * vcm[x];
+        twoKEt[x] += me->invMass[i] * me->P[3 * (size_t)i + x] * me->P[3 * (size_t)i + x];
+      }
+    }
+    double factor = std::sqrt((3 * me->nfree - 3) * kT / (twoKEt[0] + twoKEt[1] + twoKEt[2]));
+    for (int f = 0; f < me->nfree; ++f) {
+      int i = me->free_[f];
+      for (int x = 0; x < 3; ++x) me->P[3 * (size_t)i + x] = factor * me->P[3 * (size_t)i + x];
+    }
+    for (int x = 0; x < 3; ++x) twoKEt[x] = factor * factor * twoKEt[x];
+  }
+  for (int x = 0; x < 3; ++x) { md->Kinetic.RotPart[x] = 0.0; md->Kinetic.TransPart[x] = 0.5 * twoKEt[x]; }
+  md->Kinetic.Rotational = 0.0;
+  md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] +
+                      md->Kinetic.Rotational;
+  md->Kinetic.ShadowKinetic = md->Kinetic.Total;
+  md->Kinetic.ShadowRotational = md->Kinetic.Rotational;
+  md->Kinetic.UpToDate = true;
+}
+
+// src/EmDeeCode.f90:1024-1065 with boost / kinetic_energies (src/EmDeeData.f90:864-922), free atoms
+void EmDee_boost(tEmDee* md, double lambda, double alpha, double dt) {
+  System* me = sys(*md);
+  double CF = phi(alpha * dt) * dt;
+  double CP = 1.0 - alpha * CF;
+  CF = lambda * CF;
+  if (lambda != 0.0 && !me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(md);
+  if (me->nbodies != 0) out_of_scope("boost (rigid bodies)");
+  const int T = me->nthreads;
+  std::vector<double> twoKEt(3 * (size_t)T, 0.0);
+  const double* F = me->F();
+  const bool compute = md->Options.Compute, translate = md->Options.Translate;
+#pragma omp parallel num_threads(T)
+  {
+    const int thread = omp_get_thread_num() + 1;
+    const int f1 = (thread - 1) * me->threadFreeAtoms + 1, fN = std::min(thread * me->threadFreeAtoms, me->nfree);
+    if (translate)
+      for (int f = f1; f <= fN; ++f) {
+        int j = me->free_[f - 1];
+        for (int x = 0; x < 3; ++x) me->P[3 * (size_t)j + x] = CP * me->P[3 * (size_t)j + x] + CF * F[3 * (size_t)j + x];
+      }
+    if (compute && translate) {
+      double k[3] = {0, 0, 0};
+      for (int f = f1; f <= fN; ++f) {
+        int j = me->free_[f - 1];
+        for (int x = 0; x < 3; ++x) k[x] = k[x] + me->invMass[j] * me->P[3 * (size_t)j + x] * me->P[3 * (size_t)j + x];
+      }
+      for (int x = 0; x < 3; ++x) twoKEt[3 * (size_t)(thread - 1) + x] = k[x];
+    }
+  }
+  if (compute) {
+    if (translate)
+      for (int x = 0; x < 3; ++x) {
+        double s = 0.0;
+        for (int t = 0; t < T; ++t) s += twoKEt[3 * (size_t)t + x];
+        md->Kinetic.TransPart[x] = 0.5 * s;
+      }
+    if (md->Options.Rotate) {
+      for (int x = 0; x < 3; ++x) md->Kinetic.RotPart[x] = 0.0;
+      md->Kinetic.Rotational = 0.0;
+    }
+    md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] +
+                        md->Kinetic.Rotational;
+  }
+  md->Kinetic.UpToDate = compute;
+}
+
+// src/EmDeeCode.f90:1069-1103 with move (src/EmDeeData.f90:823-860), free atoms
+void EmDee_displace(tEmDee* md, double lambda, double alpha, double dt) {
+  System* me = sys(*md);
+  md->Time.Motion -= omp_get_wtime();
+  double CR, CP;
+  if (alpha != 0.0) {
+    CP = phi(alpha * dt) * dt;
+    CR = 1.0 - alpha * CP;
+    me->Lbox = CR * me->Lbox;
+  } else {
+    CP = dt;
+    CR = 1.0;
+  }
+  CP = lambda * CP;
+  if (me->nbodies != 0) out_of_scope("displace (rigid bodies)");
+  if (md->Options.Translate) {
+#pragma omp parallel for num_threads(me->nthreads) schedule(static)
+    for (int f = 0; f < me->nfree; ++f) {
+      int j = me->free_[f];
+      for (int x = 0; x < 3; ++x)
+        me->R[3 * (size_t)j + x] = CR * me->R[3 * (size_t)j + x] + CP * me->P[3 * (size_t)j + x] * me->invMass[j];
+    }
+  }
+  invalidate(*me, md);
+  md->Time.Motion += omp_get_wtime();
+}
+
+void EmDee_verlet_step(tEmDee*, double) { out_of_scope("verlet_step"); }
+
+// src/EmDeeCode.f90:1215-1277
+void EmDee_compute_forces(tEmDee* md) {
+  System* me = sys(*md);
+  const int N = me->natoms, T = me->nthreads;
+  enum { pair = 0, coul = 1, long_ = 2, bond = 3, angle = 4 };
+  std::vector<double> Rs(3 * (size_t)N), Fs(3 * (size_t)N * T);
+  for (size_t q = 0; q < 3 * (size_t)N; ++q) Rs[q] = me->R[q] / me->Lbox;
+
+  handle_neighbor_lists(*me, md->Builds, md->Time.Neighbor, Rs.data());
+
+  md->Time.Pair -= omp_get_wtime();
+  const bool compute = md->Options.Compute;
+  double E[5] = {0, 0, 0, 0, 0}, W[5] = {0, 0, 0, 0, 0};
+  std::vector<double> Et(4 * (size_t)T, 0.0);
+#pragma omp parallel num_threads(T)
+  {
+    const int thread = omp_get_thread_num() + 1;
+    double* F = Fs.data() + 3 * (size_t)N * (thread - 1);
+    double Ep = 0, Ec = 0, Wp = 0, Wc = 0;
+    if (compute) compute_pairs<true>(*me, thread, Rs.data(), F, Ep, Ec, Wp, Wc);
+    else compute_pairs<false>(*me, thread, Rs.data(), F, Ep, Ec, Wp, Wc);
+    Et[4 * (size_t)(thread - 1) + 0] = Ep;
+    Et[4 * (size_t)(thread - 1) + 1] = Ec;
+    Et[4 * (size_t)(thread - 1) + 2] = Wp;
+    Et[4 * (size_t)(thread - 1) + 3] = Wc;
+  }
+  for (int t = 0; t < T; ++t) {   // reduction(+:E,W)
+    E[pair] += Et[4 * (size_t)t + 0];
+    E[coul] += Et[4 * (size_t)t + 1];
+    W[pair] += Et[4 * (size_t)t + 2];
+    W[coul] += Et[4 * (size_t)t + 3];
+  }
+  double* Fm = me->F();   // me%F = sum(Fs,3)
+#pragma omp parallel for num_threads(T) schedule(static)
+  for (long long q = 0; q < 3LL * N; ++q) {
+    double s = 0.0;
+    for (int t = 0; t < T; ++t) s += Fs[(size_t)t * 3 * N + q];
+    Fm[q] = s;
+  }
+  if (me->coul[me->layer - 1].requires_kspace) {
+    // compute_kspace (src/EmDeeData.f90:689-700) is outside the hot-path scope: E(long) stays zero.
+    W[long_] = E[coul] + E[long_] - W[coul];
+  }
+  md->Virial.Total = W[0] + W[1] + W[2] + W[3] + W[4];
+  if (me->nbodies != 0) {
+    md->Virial.Body = rigid_body_virial(*me);
+    md->Virial.Total = md->Virial.Total + md->Virial.Body;
+  }
+  if (compute) {
+    md->Energy.Dispersion = E[pair];
+    md->Energy.Coulomb = E[coul] + E[long_];
+    md->Energy.Bond = E[bond];
+    md->Energy.Angle = E[angle];
+    md->Energy.Potential = E[0] + E[1] + E[2] + E[3] + E[4];
+    md->Energy.ShadowPotential = md->Energy.Potential;
+  }
+  md->Energy.UpToDate = compute;
+  me->forcesUpToDate[me->layer - 1] = 1;
+  me->layerEnergy[me->layer - 1] = md->Energy;
+  me->layerVirial[me->layer - 1] = md->Virial;
+  double time = omp_get_wtime();
+  md->Time.Pair += time;
+  md->Time.Total = time - me->startTime;
+}
+
+void EmDee_rdf(tEmDee, int, double, int, int*, int*, double*) { out_of_scope("radial distribution calculation"); }
+
+// ---- modifiers (src/modelClass_nonbonded.f90:83-241) ---------------------------------------------
+static void* wrap_modifier(void* model, int modifier, double skin, bool has_skin, const char* task) {
+  Model* m = as_model(model);
+  if (m == nullptr || !is_nonbonded(m->kind)) error(task, "a valid pair model must be provided");
+  Model n = *m;
+  n.modifier = modifier;
+  if (has_skin) n.skin = skin;
+  return deliver(n);
+}
+void* EmDee_shifted(void* model) { return wrap_modifier(model, SHIFTED, 0, false, "shifted potential assignment"); }
+void* EmDee_shifted_force(void* model) { return wrap_modifier(model, SHIFTED_FORCE, 0, false, "shifted-force potential assignment"); }
+void* EmDee_smoothed(void* model, double skin) { return wrap_modifier(model, SMOOTHED, skin, true, "smoothed potential assignment"); }
+void* EmDee_shifted_smoothed(void* model, double skin) { return wrap_modifier(model, SHIFTED_SMOOTHED, skin, true, "shifted-smoothed potential assignment"); }
+void* EmDee_square_smoothed(void* model, double skin) { return wrap_modifier(model, SQUARE_SMOOTHED, skin, true, "square-smoothed potential assignment"); }
+void* EmDee_shifted_square_smoothed(void* model, double skin) { return wrap_modifier(model, SHIFTED_SQUARE_SMOOTHED, skin, true, "shifted-square-smoothed potential assignment"); }
+
+// ---- constructors --------------------------------------------------------------------------------
+static void* make(Kind k, const char* name) { Model m; m.kind = k; m.name = name; return deliver(m); }
+void* EmDee_pair_none(void) { return make(PAIR_NONE, "none"); }
+void* EmDee_coul_none(void) { return make(COUL_NONE, "none"); }
+void* EmDee_bond_none(void) { return make(BOND_NONE, "none"); }
+void* EmDee_angle_none(void) { return make(ANGLE_NONE, "none"); }
+void* EmDee_dihedral_none(void) { return make(DIHEDRAL_NONE, "none"); }
+void* EmDee_pair_lj_cut(double epsilon, double sigma) { Model m; setup_lj(m, epsilon, sigma); return deliver(m); }
+void* EmDee_pair_softcore_cut(double epsilon, double sigma, double lambda) { Model m; setup_softcore(m, epsilon, sigma, lambda); return deliver(m); }
+void* EmDee_coul_cut(void) { return make(COUL_CUT, "cut"); }
+void* EmDee_coul_sf(void) { Model m; m.kind = COUL_SF; m.name = "sf"; m.shifted_force = true; return deliver(m); }
+void* EmDee_coul_damped(double damp) {   // src/coul_damped.f90:50-64
+  Model m; m.kind = COUL_DAMPED; m.name = "damped"; m.damp = damp; m.alpha = damp; m.beta = 2.0 * m.alpha / std::sqrt(Pi);
+  return deliver(m);
+}
+void* EmDee_coul_long(void) { Model m; m.kind = COUL_LONG; m.name = "long"; m.requires_kspace = true; return deliver(m); }
+void* EmDee_coul_damped_smoothed(double damp, double skinWidth) {   // src/coul_damped_smoothed.f90:54-72
+  Model m; m.kind = COUL_DAMPED_SMOOTHED; m.name = "damped_openmm_smoothed"; m.damp = damp; m.skinWidth = skinWidth;
+  m.alpha = damp; m.beta = 2.0 * m.alpha / std::sqrt(Pi);
+  return deliver(m);
+}
+void* EmDee_coul_damped_square_smoothed(double damp, double skinWidth) {   // src/coul_damped_square_smoothed.f90:54-72
+  Model m; m.kind = COUL_DAMPED_SQUARE_SMOOTHED; m.name = "damped_smoothed"; m.damp = damp; m.skinWidth = skinWidth;
+  m.alpha = damp; m.beta = 2.0 * m.alpha / std::sqrt(Pi);
+  return deliver(m);
+}
+void* EmDee_coul_square_smoothed(double skinWidth) { Model m; m.kind = COUL_SQUARE_SMOOTHED; m.name = "smoothed"; m.skinWidth = skinWidth; return deliver(m); }
+void* EmDee_coul_shifted_square_smoothed(double skinWidth) {
+  Model m; m.kind = COUL_SHIFTED_SQUARE_SMOOTHED; m.name = "shifted_smoothed"; m.skinWidth = skinWidth; m.shifted = true;
+  return deliver(m);
+}
+void* EmDee_bond_harmonic(double k, double r0) { Model m; m.kind = BOND_HARMONIC; m.name = "harmonic"; m.p1 = k; m.p2 = r0; return deliver(m); }
+void* EmDee_angle_harmonic(double k, double theta0) { Model m; m.kind = ANGLE_HARMONIC; m.name = "harmonic"; m.p1 = k; m.p2 = theta0; return deliver(m); }
+void* EmDee_kspace_ewald(double accuracy) { Model m; m.kind = KSPACE_EWALD; m.name = "ewald"; m.accuracy = accuracy; return deliver(m); }
+
+// ---- extensions (include/emdee_ext.h) ------------------------------------------------------------
+long long EmDeeX_pair_count(tEmDee md) {
+  System* me = sys(md);
+  long long n = 0;
+  for (auto& l : me->neighbor) n += l.count;
+  return n;
+}
+
+long long EmDeeX_download_pairs(tEmDee md, int* pairs, long long capacity) {
+  System* me = sys(md);
+  long long n = 0;
+  for (int t = 0; t < me->nthreads; ++t) {
+    List& nl = me->neighbor[t];
+    const int tfirst = me->threadCell.first[t], tlast = me->threadCell.last[t];
+    if (tlast < tfirst) continue;
+    for (int k = me->cellAtom.first[tfirst - 1]; k <= me->cellAtom.last[tlast - 1]; ++k) {
+      int i = me->cellAtom.item[k - 1];
+      for (int m = nl.first[i - 1]; m <= nl.last[i - 1]; ++m) {
+        if (n >= capacity) return n;
+        int j = nl.item[m - 1];
+        pairs[2 * n] = std::min(i, j) - 1;
+        pairs[2 * n + 1] = std::max(i, j) - 1;
+        ++n;
+      }
+    }
+  }
+  return n;
+}
+
+void EmDeeX_finalize(tEmDee* md) {
+  delete sys(*md);
+  md->Data = nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""SPC/E single-point values of the CPU oracle against the survey's independent O(N^2) numpy probes
+(NOT reference output -- the reference's SPC/E tests carry no expected values, so
+these rows are "parity unpinned" by the reference and pinned only by two independent restatements
+agreeing). Values in kcal/mol (x mvv2e), NIST SPC/E sample, 2250 atoms, 750 rigid waters.
+"""
+import pytest
+
+import common as cm
+
+DISP = 957.9773289867705
+ROWS = {
+    # name: (factory, re-run cutoff_setup through EmDee_layer_based_parameters?, Coulomb E, Virial%Body, Virial%Total)
+    "coul_sf literal (Q1: shifts zeroed by modifier_setup)":
+        (lambda l: l.EmDee_coul_sf(), False, -28686.256823039643, -18718.386631384867, -23779.17571552381),
+    "shifted_force(coul_cut)":
+        (lambda l: l.EmDee_shifted_force(l.EmDee_coul_cut()), False, -6826.749756368041, -18108.414766379356, -1944.2104162198348),
+    "coul_sf after layer_based_parameters":
+        (lambda l: l.EmDee_coul_sf(), True, -6826.749756368041, -18108.414766379356, -1944.2104162198348),
+    "coul_damped_square_smoothed(0.2,1.0)":
+        (lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0), False, -6856.821617251877, -18279.392679472843, -3783.053650262019),
+    "coul_damped_smoothed(0.2,1.0) after layer_based_parameters":
+        (lambda l: l.EmDee_coul_damped_smoothed(0.2, 1.0), True, -6854.440663505941, -18277.973792886394, -3700.865208564038),
+}
+
+
+def _build(lib, factory, relayer, threads=2):
+    orig = cm.api.System.upload
+    state = {"done": not relayer}
+
+    def patched(self, option, array):
+        if not state["done"]:
+            self.layer_based_parameters(10.0, [0], [1])
+            state["done"] = True
+        return orig(self, option, array)
+
+    cm.api.System.upload = patched
+    try:
+        return cm.spce_sample_system(lib, factory, threads=threads)
+    finally:
+        cm.api.System.upload = orig
+
+
+@pytest.mark.parametrize("name", list(ROWS))
+def test_spce_single_point(name):
+    factory, relayer, ecoul, wbody, wtot = ROWS[name]
+    s, c = _build(cm.oracle(), factory, relayer)
+    m = c["mvv2e"]
+    assert abs(m * s.md.Energy.Dispersion - DISP) < 1e-7
+    assert abs(m * s.md.Energy.Coulomb - ecoul) < 1e-6
+    assert abs(m * s.md.Virial.Body - wbody) < 1e-6
+    assert abs(m * s.md.Virial.Total - wtot) < 1e-6
+    assert s.md.DoF == 6 * 750 - 3 and s.md.RotDoF == 3 * 750
+    s.finalize()
+
+
+def test_coul_damped_smoothed_literal_loses_its_switch():
+    """Q1b (found while restating): EmDee_set_coul_model runs cutoff_setup (Rm = Rc - skinWidth) and then
+    modifier_setup, which overwrites the inherited Rm with Rc - skin = Rc (reference
+    src/modelClass_nonbonded.f90:257). coul_damped_smoothed tests `r > model%Rm`
+    (src/coul_damped_smoothed.f90:104), so as set through the plain setter it never switches and
+    evaluates exactly like coul_damped."""
+    lib = cm.oracle()
+    s1, c = cm.spce_sample_system(lib, lambda l: l.EmDee_coul_damped_smoothed(0.2, 1.0))
+    s2, _ = cm.spce_sample_system(lib, lambda l: l.EmDee_coul_damped(0.2))
+    assert s1.md.Energy.Coulomb == s2.md.Energy.Coulomb
+    assert s1.md.Virial.Total == s2.md.Virial.Total
+    s1.finalize()
+    s2.finalize()
+
+
+def test_spce_replica_scaling():
+    """Cutoff models: energies of an n^3 periodic replica are exactly n^3 times the single box (to rounding)."""
+    lib = cm.oracle()
+    f = lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0)
+    s1, c1 = cm.spce_sample_system(lib, f, replicas=1)
+    s2, c2 = cm.spce_sample_system(lib, f, replicas=2, threads=4)
+    for a, b in [(s1.md.Energy.Potential, s2.md.Energy.Potential), (s1.md.Virial.Total, s2.md.Virial.Total),
+                 (s1.md.Energy.Coulomb, s2.md.Energy.Coulomb)]:
+        assert cm.rel(b, 8 * a) < 1e-11
+    assert lib.EmDeeX_pair_count(s2.md) == 8 * lib.EmDeeX_pair_count(s1.md)
+    s1.finalize()
+    s2.finalize()
