@@ -81,7 +81,14 @@ def spce_sample_system(lib, coul_factory, threads=2, replicas=1, pair_factory=No
     """reference test/test_coul_*.f90:36-50: SPC/E water, LJ-sf on O, pair_none on H, rigid bodies."""
     c = load_fixture("NIST_spce_sample")
     n = replicas
-    R0, L0 = c["R"], c["L"]
+    R0, L0 = c["R"].copy(), c["L"]
+    if n > 1:
+        # make molecules whole (minimum image w.r.t. their first atom) so that replicas tile exactly
+        first_of = {}
+        for a, m in enumerate(c["molecule"]):
+            first_of.setdefault(m, a)
+        ref = R0[[first_of[m] for m in c["molecule"]]]
+        R0 = R0 - L0 * np.round((R0 - ref) / L0)
     shifts = np.array([[i, j, k] for i in range(n) for j in range(n) for k in range(n)], dtype=float) * L0
     R = (R0[None, :, :] + shifts[:, None, :]).reshape(-1, 3)
     nmol0 = int(c["molecule"].max())
