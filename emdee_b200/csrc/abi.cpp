@@ -1,0 +1,1058 @@
+// abi.cpp -- the drop-in boundary: every `bind(C)` entry point of the reference library
+// (src/EmDeeCode.f90, generated src/models.f90) re-hosted in C++ on top of the CUDA engine.
+//
+// What lives here: the reference's host-side semantics for the nonbonded path -- model objects and
+// the order-dependent setup rules (set_pair_type + mixing + modifier_setup, cutoff_setup; reference
+// src/EmDeeData.f90:193-264, src/modelClass_nonbonded.f90:245-296, src/modelClass_coul.f90:62-93,
+// src/modelClass_pair.f90:120-140), lazy initialisation and up-to-date flags (src/EmDeeCode.f90:805-946),
+// the error convention (src/global.f90:51-56). What does NOT live here: any arithmetic over atoms --
+// that is all in engine.cu, on the device. There is no CPU fallback.
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
+#include <string>
+#include <vector>
+
+#include "../../include/emdee.h"
+#include "../../include/emdee_ext.h"
+#include "engine.h"
+
+static_assert(sizeof(tEmDee) == 240, "tEmDee must be 240 bytes (reference src/EmDeeCode.f90:51-61)");
+static_assert(offsetof(tEmDee, Data) == 216 && offsetof(tEmDee, Options) == 224, "tEmDee layout");
+
+namespace {
+
+using emdee::Engine;
+using nb::DevModel;
+
+[[noreturn]] void error(const char* task, const std::string& msg) {   // src/global.f90:51-56
+  std::fprintf(stderr, "Error in %s: %s.\n", task, msg.c_str());
+  std::fflush(stderr);
+  std::exit(1);
+}
+void warning(const std::string& msg) { std::fprintf(stderr, "WARNING: %s.\n", msg.c_str()); }   // :60-64
+
+[[noreturn]] void unsupported(const char* task) {
+  error(task, "not available in the B200 hot-path build (outside the nonbonded neighbor-list/pair-force scope)");
+}
+
+double now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- model handles ------------------------------------------------------------------------------
+enum Family { F_PAIR, F_COUL, F_BOND, F_ANGLE, F_DIHEDRAL, F_KSPACE };
+constexpr uint64_t HANDLE_TAG = 0x456d446565423230ull;   // "EmDeeB20"
+
+struct HostModel {
+  uint64_t tag = HANDLE_TAG;
+  Family family = F_PAIR;
+  const char* name = "none";
+  DevModel dev{};            // what the kernels see
+  // host-only state of the reference's class hierarchy
+  double skin = 0.0;         // cNonBondedModel%skin (modifier smoothing width)
+  double RmSq = 0.0;
+  bool shifted = false, shifted_force = false, requires_kspace = false;   // cCoulModel flags
+  double epsilon = 0.0, sigma = 0.0, lambda = 0.0;                        // raw pair parameters (for mixing)
+  double skinWidth = 0.0;                                                  // smoothed Coulomb models
+  double accuracy = 0.0;                                                   // kspace_ewald
+  bool is_long = false;                                                    // coul_long (kind shares K_COUL_DAMPED)
+};
+
+HostModel blank(Family fam, int kind, const char* name) {
+  HostModel m;
+  m.family = fam;
+  m.name = name;
+  std::memset(&m.dev, 0, sizeof(m.dev));
+  m.dev.kind = kind;
+  m.dev.modifier = nb::M_NONE;
+  return m;
+}
+
+HostModel* handle(void* p) {
+  if (p == nullptr) return nullptr;
+  HostModel* m = static_cast<HostModel*>(p);
+  return m->tag == HANDLE_TAG ? m : nullptr;
+}
+void* deliver(const HostModel& m) { return new HostModel(m); }   // never freed, like src/modelClass.f90:51-60
+
+void eval(const HostModel& m, double invR, double invR2, double& E, double& W) {
+  nb::eval_kind<nb::K_DYNAMIC>(m.dev, invR, invR2, E, W);
+}
+
+HostModel make_lj(double epsilon, double sigma) {   // src/pair_lj_cut.f90:52-69
+  HostModel m = blank(F_PAIR, nb::K_PAIR_LJ_CUT, "lj_cut");
+  m.epsilon = epsilon;
+  m.sigma = sigma;
+  m.dev.a = 4.0 * epsilon;
+  m.dev.b = 24.0 * epsilon;
+  m.dev.c = sigma * sigma;
+  return m;
+}
+HostModel make_softcore(double epsilon, double sigma, double lambda) {   // src/pair_softcore_cut.f90:58-82
+  HostModel m = blank(F_PAIR, nb::K_PAIR_SOFTCORE_CUT, "softcore_cut");
+  m.epsilon = epsilon;
+  m.sigma = sigma;
+  m.lambda = lambda;
+  if (lambda < 0.0 || lambda > 1.0) error("pair_softcore_cut setup", "out-of-range parameter lambda");
+  m.dev.a = 4.0 * epsilon * lambda;
+  m.dev.b = 6.0 * m.dev.a;
+  m.dev.c = 1.0 / (sigma * sigma);
+  m.dev.d = 0.5 * (1.0 - lambda);
+  return m;
+}
+
+// src/modelClass_nonbonded.f90:245-296
+void modifier_setup(HostModel& m, double cutoff) {
+  DevModel& d = m.dev;
+  d.fshift = 0.0;
+  d.eshift = 0.0;
+  d.Rm = cutoff - m.skin;
+  m.RmSq = d.Rm * d.Rm;
+  const int mod = d.modifier;
+  const bool shifting = mod == nb::M_SHIFTED || mod == nb::M_SHIFTED_FORCE || mod == nb::M_SHIFTED_SMOOTHED ||
+                        mod == nb::M_SHIFTED_SQUARE_SMOOTHED;
+  double Ec = 0, Wc = 0, Es = 0, Ws = 0;
+  if (shifting) eval(m, 1.0 / cutoff, 1.0 / (cutoff * cutoff), Ec, Wc);
+  if (mod == nb::M_SHIFTED) {
+    d.eshift = -Ec;
+  } else if (mod == nb::M_SHIFTED_FORCE) {
+    d.eshift = -(Ec + Wc);
+    d.fshift = Wc / cutoff;
+  } else if (mod == nb::M_SMOOTHED || mod == nb::M_SHIFTED_SMOOTHED) {
+    if (shifting) {
+      eval(m, 1.0 / d.Rm, 1.0 / m.RmSq, Es, Ws);
+      d.eshift = -0.5 * (Es + Ec);
+    }
+    d.factor = 1.0 / (cutoff - d.Rm);
+    d.Rm2fac = d.factor * d.Rm;
+  } else if (mod == nb::M_SQUARE_SMOOTHED || mod == nb::M_SHIFTED_SQUARE_SMOOTHED) {
+    if (shifting) {
+      eval(m, 1.0 / d.Rm, 1.0 / m.RmSq, Es, Ws);
+      d.eshift = -0.5 * (Es + Ec);
+    }
+    d.factor = 1.0 / (cutoff * cutoff - m.RmSq);
+    d.Rm2fac = d.factor * m.RmSq;
+  }
+}
+
+// src/modelClass_coul.f90:62-93 + the *_apply_cutoff overrides of the smoothed Coulomb models
+void cutoff_setup(HostModel& m, double cutoff) {
+  DevModel& d = m.dev;
+  d.fshift = 0.0;
+  d.eshift = 0.0;
+  if (m.shifted || m.shifted_force) {
+    double invR = 1.0 / cutoff, E = 0, W = 0;
+    eval(m, invR, invR * invR, E, W);
+    if (m.shifted_force) {
+      d.fshift = W / cutoff;
+      d.eshift = -(E + W);
+    } else {
+      d.fshift = 0.0;
+      d.eshift = -E;
+    }
+  }
+  switch (d.kind) {
+    case nb::K_COUL_DAMPED_SMOOTHED:   // src/coul_damped_smoothed.f90:76-85
+      d.Rm = cutoff - m.skinWidth;
+      d.c = d.Rm * d.Rm;
+      d.d = 1.0 / d.Rm;
+      d.factor = 1.0 / (cutoff - d.Rm);
+      break;
+    case nb::K_COUL_DAMPED_SQUARE_SMOOTHED:    // src/coul_damped_square_smoothed.f90:76-84
+    case nb::K_COUL_SQUARE_SMOOTHED:           // src/coul_square_smoothed.f90:69-76
+    case nb::K_COUL_SHIFTED_SQUARE_SMOOTHED:   // src/coul_shifted_square_smoothed.f90:72-79
+      d.c = (cutoff - m.skinWidth) * (cutoff - m.skinWidth);
+      d.d = 1.0 / (cutoff - m.skinWidth);
+      d.factor = 1.0 / (cutoff * cutoff - d.c);
+      break;
+    default:
+      break;
+  }
+}
+
+// mixing rules: src/pair_lj_cut.f90:122-138, src/pair_softcore_cut.f90:139-163, src/modelClass_pair.f90:194-200
+bool mix_rule(const HostModel& self, const HostModel& other, HostModel& out) {
+  const double eps = std::sqrt(self.epsilon * other.epsilon), sig = 0.5 * (self.sigma + other.sigma);
+  switch (self.dev.kind) {
+    case nb::K_PAIR_NONE:
+      out = blank(F_PAIR, nb::K_PAIR_NONE, "none");
+      return true;
+    case nb::K_PAIR_LJ_CUT:
+      if (other.dev.kind != nb::K_PAIR_LJ_CUT) return false;
+      out = make_lj(eps, sig);
+      return true;
+    case nb::K_PAIR_SOFTCORE_CUT:
+      if (other.dev.kind == nb::K_PAIR_SOFTCORE_CUT) out = make_softcore(eps, sig, self.lambda * other.lambda);
+      else if (other.dev.kind == nb::K_PAIR_LJ_CUT) out = make_softcore(eps, sig, self.lambda);
+      else return false;
+      return true;
+    default:
+      return false;
+  }
+}
+
+struct PairSlot {   // reference pairContainer
+  HostModel model = blank(F_PAIR, nb::K_PAIR_NONE, "none");
+  bool coulomb = false;
+  double kCoul = 0.0;
+};
+
+PairSlot mix_slots(const PairSlot& a, const PairSlot& b) {   // src/modelClass_pair.f90:120-140
+  PairSlot c;
+  if (!mix_rule(b.model, a.model, c.model) && !mix_rule(a.model, b.model, c.model)) {
+    c.model = blank(F_PAIR, nb::K_PAIR_NONE, "none");
+    warning(std::string("no mixing rule found for models ") + a.model.name + " and " + b.model.name);
+  }
+  c.coulomb = a.coulomb && b.coulomb;
+  if (c.coulomb) c.kCoul = std::sqrt(a.kCoul * b.kCoul);
+  return c;
+}
+
+// ---- KISS + ziggurat (src/math.f90:42-177): needed by EmDee_random_momenta --------------------------
+struct Rng {
+  bool seeding_required = true;
+  int32_t kn[128];
+  double wn[128], fn[128];
+  uint32_t x = 0, y = 0, z = 0, w = 0;
+  static uint32_t mixbits(uint32_t k, int n) { return k ^ (n > 0 ? k << n : k >> -n); }
+  static uint32_t scramble(uint32_t v) { return mixbits(mixbits(mixbits(v, 13), -17), 5); }
+  void seed(int32_t s) {
+    x = scramble((uint32_t)s);
+    y = scramble(x);
+    z = scramble(y);
+    w = scramble(z);
+    seeding_required = false;
+    const double m1 = 2147483648.0, vn = 0.00991256303526217;
+    double dn = 3.442619855899, tn = dn;
+    const double q = vn * std::exp(0.5 * dn * dn);
+    kn[0] = (int32_t)((dn / q) * m1);
+    kn[1] = 0;
+    wn[0] = q / m1;
+    wn[127] = dn / m1;
+    fn[0] = 1.0;
+    fn[127] = std::exp(-0.5 * dn * dn);
+    for (int i = 126; i >= 1; --i) {
+      dn = std::sqrt(-2.0 * std::log(vn / dn + std::exp(-0.5 * dn * dn)));
+      kn[i + 1] = (int32_t)((dn / tn) * m1);
+      tn = dn;
+      fn[i] = std::exp(-0.5 * dn * dn);
+      wn[i] = dn / m1;
+    }
+  }
+  int32_t next_i32() {
+    x = 69069u * x + 1327217885u;
+    y ^= y << 13;
+    y ^= y >> 17;
+    y ^= y << 5;
+    z = 18000u * (z & 65535u) + (z >> 16);
+    w = 30903u * (w & 65535u) + (w >> 16);
+    return (int32_t)(x + y + (z << 16) + w);
+  }
+  static bool inside(int32_t hz, int32_t bound) {   // abs(hz) < bound with 32-bit wraparound abs
+    int32_t a = hz < 0 ? (int32_t)(0u - (uint32_t)hz) : hz;
+    return a < bound;
+  }
+  double uni() { return 0.2328306e-9 * next_i32() + 0.5; }
+  double normal() {
+    int32_t hz = next_i32();
+    int iz = hz & 127;
+    if (inside(hz, kn[iz])) return hz * wn[iz];
+    for (;;) {
+      if (iz == 0) {
+        double a, b;
+        do {
+          a = -0.2904764 * std::log(uni());
+          b = -std::log(uni());
+        } while (b + b < a * a);
+        return hz <= 0 ? -(3.442620 + a) : 3.442620 + a;
+      }
+      const double v = hz * wn[iz];
+      if (fn[iz] + uni() * (fn[iz - 1] - fn[iz]) < std::exp(-0.5 * v * v)) return v;
+      hz = next_i32();
+      iz = hz & 127;
+      if (inside(hz, kn[iz])) return hz * wn[iz];
+    }
+  }
+};
+
+double phi(double x) {   // src/math.f90:230-237
+  return std::fabs(x) > 1e-4 ? (1.0 - std::exp(-x)) / x : 1.0 + 0.5 * x * ((1.0 / 3.0) * x * (1.0 - 0.25 * x) - 1.0);
+}
+
+double inverse_of_x_plus_ln_x(double y) {   // src/math.f90:642-657
+  double x = y > 0.5671432904097839 ? y - std::log(y) : std::exp(y);
+  double x0 = x + 1.0;
+  while (std::fabs(x - x0) > 1.0e-12 * x0) {
+    x0 = x;
+    x = x * (y + 1.0 - std::log(x)) / (x + 1.0);
+  }
+  return x;
+}
+
+// ---- system -------------------------------------------------------------------------------------
+struct RigidBody {   // the part of reference tBody (src/ArBee.f90:29-106) the hot path reads
+  std::vector<int> atoms;   // 0-based
+  std::vector<double> m;
+  double mass = 0.0;
+};
+
+struct System {
+  int N = 0, ntypes = 1, nlayers = 1, layer = 1, threads = 1;
+  double Rc = 0, skin = 0, InRc = 0, Lbox = 0, totalMass = 0, startTime = 0;
+  bool hasL = false, hasR = false, initialized = false, kspace_active = false;
+  std::vector<int> type;                 // 1-based type of each atom
+  std::vector<double> mass, invMass, charge;
+  std::vector<char> charged;
+  std::vector<int> atomBody, freeAtoms;
+  std::vector<RigidBody> bodies;
+  std::vector<double> hostR;             // host copy, kept only when rigid bodies exist
+  std::vector<std::vector<int>> excluded;   // per atom, sorted unique 1-based partners
+  bool exclusions_dirty = true;
+  std::vector<PairSlot> pair;            // (ntypes, ntypes, nlayers)
+  std::vector<HostModel> coul;           // per layer
+  HostModel kspace = blank(F_KSPACE, 0, "ewald");
+  std::vector<char> overridable, multilayer, interact, pairs_exist, useInRc, bonded, forcesUpToDate;
+  std::vector<tEnergy> layerEnergy;
+  std::vector<tVirial> layerVirial;
+  Rng random;
+  Engine* engine = nullptr;
+
+  PairSlot& slot(int i, int j, int l) { return pair[((size_t)(l - 1) * ntypes + (j - 1)) * ntypes + (i - 1)]; }
+  char& flag(std::vector<char>& a, int i, int j) { return a[(size_t)(j - 1) * ntypes + (i - 1)]; }
+  double layerRc(int l) const { return useInRc[l - 1] ? InRc : Rc; }
+  int nbodies() const { return (int)bodies.size(); }
+};
+
+System* sys(const tEmDee& md) { return static_cast<System*>(md.Data); }
+
+std::string opt(const char* s) {   // src/global.f90:120-128
+  size_t n = 0;
+  while (n < 256 && s[n] != '\0') ++n;
+  return std::string(s, n);
+}
+bool ranged(std::initializer_list<int> v, int imax) {
+  for (int i : v)
+    if (i <= 0 || i > imax) return false;
+  return true;
+}
+
+// src/EmDeeData.f90:227-264
+void set_pair_type(System& me, int itype, int jtype, int layer, const HostModel& model, double kCoul) {
+  const double cutoff = me.layerRc(layer);
+  auto assign = [&](PairSlot& s) {
+    s.model = model;            // container assignment copies the model only
+    s.coulomb = kCoul != 0.0;
+    if (s.coulomb) s.kCoul = kCoul;
+    modifier_setup(s.model, cutoff);
+  };
+  if (itype == jtype) {
+    assign(me.slot(itype, itype, layer));
+    for (int k = 1; k <= me.ntypes; ++k) {
+      if (k == itype || !me.flag(me.overridable, itype, k)) continue;
+      PairSlot mixed = mix_slots(me.slot(k, k, layer), me.slot(itype, itype, layer));
+      modifier_setup(mixed.model, cutoff);
+      me.slot(itype, k, layer) = mixed;
+      me.slot(k, itype, layer) = mixed;
+    }
+  } else {
+    assign(me.slot(itype, jtype, layer));
+    me.slot(jtype, itype, layer) = me.slot(itype, jtype, layer);
+  }
+}
+
+// src/EmDeeData.f90:268-351 (allocate_rigid_bodies + clean_body_indices)
+void setup_bodies(System& me, const int* bodies) {
+  const int N = me.N;
+  me.atomBody.assign(N, 0);
+  me.bodies.clear();
+  me.freeAtoms.clear();
+  if (bodies == nullptr) {
+    for (int i = 0; i < N; ++i) {
+      me.atomBody[i] = i + 1;
+      me.freeAtoms.push_back(i);
+    }
+    return;
+  }
+  // ids that occur more than once become bodies, numbered by first appearance
+  std::vector<int> ids, count, firstAtom, which(N, -1);
+  for (int i = 0; i < N; ++i) {
+    if (bodies[i] <= 0) continue;
+    int k = -1;
+    for (size_t q = 0; q < ids.size(); ++q)
+      if (ids[q] == bodies[i]) { k = (int)q; break; }
+    if (k < 0) {
+      ids.push_back(bodies[i]);
+      count.push_back(1);
+      firstAtom.push_back(i);
+      k = (int)ids.size() - 1;
+    } else {
+      count[k] += 1;
+    }
+    which[i] = k;
+  }
+  std::vector<int> bodyIndex(ids.size(), 0);
+  int nb_ = 0;
+  for (size_t k = 0; k < ids.size(); ++k)
+    if (count[k] > 1) bodyIndex[k] = ++nb_;
+  me.bodies.resize(nb_);
+  for (int i = 0; i < N; ++i) {
+    int b = which[i] >= 0 ? bodyIndex[which[i]] : 0;
+    me.atomBody[i] = b;
+    if (b > 0) {
+      me.bodies[b - 1].atoms.push_back(i);
+      me.bodies[b - 1].m.push_back(me.mass[i]);
+      me.bodies[b - 1].mass += me.mass[i];
+    } else {
+      me.freeAtoms.push_back(i);
+    }
+  }
+  int next = nb_;
+  for (int i = 0; i < N; ++i)
+    if (me.atomBody[i] == 0) me.atomBody[i] = ++next;
+}
+
+// src/EmDeeData.f90:420-439 + src/ArBee.f90:97-106: make each body whole w.r.t. its first atom, then
+// delta = r - r_cm. Runs on the host copy of an uploaded configuration, before it is sent to HBM.
+void update_rigid_bodies(System& me, std::vector<double>& delta) {
+  const double L = me.Lbox, invL = 1.0 / L;
+  delta.assign(3 * (size_t)me.N, 0.0);
+  for (const RigidBody& b : me.bodies) {
+    const int first = b.atoms[0];
+    double rcm[3] = {0, 0, 0};
+    for (size_t k = 0; k < b.atoms.size(); ++k) {
+      const int a = b.atoms[k];
+      for (int x = 0; x < 3; ++x) {
+        double& r = me.hostR[3 * (size_t)a + x];
+        if (k > 0) r = r - L * std::round(invL * (r - me.hostR[3 * (size_t)first + x]));
+        rcm[x] += b.m[k] * r;
+      }
+    }
+    for (int x = 0; x < 3; ++x) rcm[x] *= 1.0 / b.mass;
+    for (int a : b.atoms)
+      for (int x = 0; x < 3; ++x) delta[3 * (size_t)a + x] = me.hostR[3 * (size_t)a + x] - rcm[x];
+  }
+}
+
+// src/EmDeeData.f90:193-223
+void check_actual_interactions(System& me) {
+  const int nt = me.ntypes;
+  std::vector<char> neutral(nt, 1);
+  for (int a = 0; a < me.N; ++a)
+    if (me.charged[a]) neutral[me.type[a] - 1] = 0;
+  std::fill(me.pairs_exist.begin(), me.pairs_exist.end(), 0);
+  for (int i = 1; i <= nt; ++i)
+    for (int j = 1; j <= i; ++j) {
+      bool any = false;
+      for (int k = 1; k <= me.nlayers; ++k) {
+        const PairSlot& p = me.slot(i, j, k);
+        const bool no_pair = p.model.dev.kind == nb::K_PAIR_NONE;
+        const bool no_coul = me.coul[k - 1].dev.kind == nb::K_COUL_NONE || !p.coulomb;
+        const bool inert = (no_pair && no_coul) || (no_pair && !no_coul && neutral[i - 1] && neutral[j - 1]);
+        if (!inert) {
+          any = true;
+          me.pairs_exist[k - 1] = 1;
+        }
+      }
+      me.flag(me.interact, i, j) = any;
+      me.flag(me.interact, j, i) = any;
+    }
+}
+
+void push_tables(System& me) {
+  std::vector<char> inter0((size_t)me.ntypes * me.ntypes);
+  for (int i = 0; i < me.ntypes; ++i)
+    for (int j = 0; j < me.ntypes; ++j) inter0[(size_t)i * me.ntypes + j] = me.flag(me.interact, i + 1, j + 1);
+  me.engine->set_interact(inter0);
+  for (int l = 1; l <= me.nlayers; ++l) {
+    emdee::LayerTable t;
+    t.pair.resize((size_t)me.ntypes * me.ntypes);
+    for (int i = 1; i <= me.ntypes; ++i)
+      for (int j = 1; j <= me.ntypes; ++j) {
+        const PairSlot& s = me.slot(i, j, l);
+        emdee::PairEntry e;
+        e.model = s.model.dev;
+        e.kCoul = s.kCoul;
+        e.coulomb = s.coulomb ? 1 : 0;
+        e.pad = 0;
+        t.pair[(size_t)(i - 1) * me.ntypes + (j - 1)] = e;
+      }
+    t.coul = me.coul[l - 1].dev;
+    t.pairs_exist = me.pairs_exist[l - 1];
+    t.useInRc = me.useInRc[l - 1];
+    me.engine->set_layer(l - 1, t);
+  }
+}
+
+void push_exclusions(System& me) {
+  std::vector<int> first(me.N), last(me.N), item;
+  for (int i = 0; i < me.N; ++i) {
+    first[i] = (int)item.size() + 1;
+    item.insert(item.end(), me.excluded[i].begin(), me.excluded[i].end());
+    last[i] = (int)item.size();
+  }
+  me.engine->set_exclusions(first, last, item);
+  me.exclusions_dirty = false;
+}
+
+// src/EmDeeData.f90:359-416
+void perform_initialization(System& me, tEmDee* md) {
+  const char* task = "system initialization";
+  if (me.nbodies() != 0) {
+    std::vector<double> delta;
+    update_rigid_bodies(me, delta);
+    me.engine->upload_coordinates(me.hostR.data());
+    me.engine->upload_body_delta(delta.data());
+  }
+  const int bodyDoF = 6 * me.nbodies();
+  md->RotDoF = bodyDoF - 3 * me.nbodies();
+  md->DoF = 3 * (int)me.freeAtoms.size() + bodyDoF - 3;
+  check_actual_interactions(me);
+  bool required = false;
+  double kspaceRc = 0.0;
+  for (int l = 1; l <= me.nlayers; ++l)
+    if (me.coul[l - 1].requires_kspace) {
+      if (!required) kspaceRc = me.layerRc(l);
+      else if (me.layerRc(l) != kspaceRc)
+        error(task, "all layers with ewald-like coulomb models must have the same cutoff");
+      required = true;
+    }
+  if (required != me.kspace_active) {
+    if (me.kspace_active) me.kspace_active = false;
+    else error(task, "a kspace solver is required, but has not been defined");
+  }
+  if (me.kspace_active) {
+    // src/kspace_ewald.f90:82-99: only the splitting parameter feeds the real-space pair loop. The
+    // reciprocal-space sum (src/kspace_ewald.f90:188-314) is outside this build's scope.
+    const double s = std::sqrt(inverse_of_x_plus_ln_x(-std::log(me.kspace.accuracy)));
+    const double alpha = s / kspaceRc;
+    std::printf("KSPACE PARAMETERS: alpha = %10.5f and kmax = %10.5f\n", alpha, 2.0 * alpha * s);
+    warning("reciprocal-space Ewald terms are outside the hot-path scope and are not evaluated");
+    for (HostModel& c : me.coul)
+      if (c.requires_kspace) {   // src/coul_long.f90:66-73
+        c.dev.a = alpha;
+        c.dev.b = 2.0 * alpha / std::sqrt(3.14159265358979323846);
+      }
+  }
+  me.engine->set_charges(me.charge.data());
+  push_tables(me);
+  push_exclusions(me);
+  me.initialized = true;
+}
+
+void invalidate(System& me, tEmDee* md) {
+  std::fill(me.forcesUpToDate.begin(), me.forcesUpToDate.end(), 0);
+  for (tEnergy& e : me.layerEnergy) e.UpToDate = false;
+  md->Energy.UpToDate = false;
+}
+
+void set_kinetic(tEmDee* md, const double twoKE[3]) {
+  for (int x = 0; x < 3; ++x) {
+    md->Kinetic.TransPart[x] = 0.5 * twoKE[x];
+    md->Kinetic.RotPart[x] = 0.0;
+  }
+  md->Kinetic.Rotational = 0.0;
+  md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] + md->Kinetic.Rotational;
+  md->Kinetic.ShadowKinetic = md->Kinetic.Total;
+  md->Kinetic.ShadowRotational = md->Kinetic.Rotational;
+  md->Kinetic.UpToDate = true;
+}
+
+void* with_modifier(void* model, int modifier, double skin, bool set_skin, const char* task) {
+  HostModel* m = handle(model);
+  if (m == nullptr || (m->family != F_PAIR && m->family != F_COUL)) error(task, "a valid pair model must be provided");
+  HostModel n = *m;
+  n.dev.modifier = modifier;
+  if (set_skin) n.skin = skin;
+  return deliver(n);
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* EmDeeX_backend(void) { return "b200-cuda"; }
+
+tEmDee EmDee_system(int threads, int layers, double rc, double skin, int N, int* types, double* masses,
+                    int* bodies) {
+  if (std::getenv("EMDEE_QUIET") == nullptr) std::printf("EmDee (version: %11s)\n", "15 Oct 2018");
+  System* me = new System();
+  me->threads = threads;   // host threads: kept for ABI compatibility, the device parallelises the work
+  me->nlayers = layers;
+  me->Rc = rc;
+  me->skin = skin;
+  me->InRc = rc;
+  me->N = N;
+  if (types != nullptr) {
+    int lo = types[0], hi = types[0];
+    for (int i = 1; i < N; ++i) {
+      lo = types[i] < lo ? types[i] : lo;
+      hi = types[i] > hi ? types[i] : hi;
+    }
+    if (lo != 1) error("system setup", "wrong specification of atom types");
+    me->ntypes = hi;
+    me->type.assign(types, types + N);
+  } else {
+    me->ntypes = 1;
+    me->type.assign(N, 1);
+  }
+  me->mass.assign(N, 1.0);
+  me->invMass.assign(N, 1.0);
+  me->totalMass = (double)N;
+  if (masses != nullptr) {
+    me->totalMass = 0.0;
+    for (int i = 0; i < N; ++i) {
+      me->mass[i] = masses[me->type[i] - 1];
+      me->invMass[i] = 1.0 / masses[me->type[i] - 1];
+      me->totalMass += me->mass[i];
+    }
+  }
+  me->startTime = now();
+  me->charge.assign(N, 0.0);
+  me->charged.assign(N, 0);
+  setup_bodies(*me, bodies);
+  me->excluded.assign(N, {});
+  const size_t nt2 = (size_t)me->ntypes * me->ntypes;
+  me->pair.assign(nt2 * layers, PairSlot());
+  me->coul.assign(layers, blank(F_COUL, nb::K_COUL_NONE, "none"));
+  me->overridable.assign(nt2, 1);
+  me->multilayer.assign(nt2, 0);
+  me->interact.assign(nt2, 0);
+  me->pairs_exist.assign(layers, 0);
+  me->useInRc.assign(layers, 0);
+  me->bonded.assign(layers, 1);
+  me->forcesUpToDate.assign(layers, 0);
+  me->engine = new Engine(N, me->ntypes, layers, rc, skin, me->type.data(), me->mass.data(), me->invMass.data(),
+                          me->atomBody.data(), me->nbodies());
+
+  tEmDee md;
+  std::memset(&md, 0, sizeof(md));
+  me->layerEnergy.assign(layers, md.Energy);
+  me->layerVirial.assign(layers, md.Virial);
+  md.DoF = 3 * (N - 1);
+  md.Data = me;
+  md.Options.Translate = true;
+  md.Options.Rotate = true;
+  md.Options.RotationMode = 0;
+  md.Options.AutoBodyUpdate = true;
+  md.Options.Compute = true;
+  return md;
+}
+
+void* EmDee_memory_address(tEmDee, const char*) {
+  // The reference hands out raw pointers into its host arrays (src/EmDeeCode.f90:212-235); here the
+  // state lives in HBM. Use EmDee_upload / EmDee_download.
+  unsupported("memory address retrieving");
+}
+void EmDee_share_phase_space(tEmDee, tEmDee*) { unsupported("phase space sharing"); }
+
+void EmDee_layer_based_parameters(tEmDee md, double InternalRc, int* Apply, int* Bonded) {
+  const char* task = "layer-based parameter setting";
+  System* me = sys(md);
+  if (me->initialized) error(task, "system has already been initialized");
+  bool any = false;
+  for (int l = 0; l < me->nlayers; ++l) {
+    me->useInRc[l] = Apply[l] != 0;
+    any = any || me->useInRc[l];
+  }
+  if (any && (InternalRc <= 0.0 || InternalRc > me->Rc)) error(task, "invalid internal cutoff specification");
+  me->InRc = InternalRc;
+  me->engine->set_inner_cutoff(InternalRc);
+  for (int l = 0; l < me->nlayers; ++l) me->bonded[l] = Bonded[l] != 0;
+  for (int l = 1; l <= me->nlayers; ++l) cutoff_setup(me->coul[l - 1], me->layerRc(l));   // cutoff_setup ONLY (Q1)
+}
+
+static void after_pair_setting(System* me, int itype, int jtype, char multi) {
+  me->flag(me->multilayer, itype, jtype) = multi;
+  me->flag(me->multilayer, jtype, itype) = multi;
+  if (itype == jtype) {
+    for (int k = 1; k <= me->ntypes; ++k)
+      if (k != itype && me->flag(me->overridable, itype, k)) {
+        char v = multi ? 1 : me->flag(me->multilayer, k, k);
+        me->flag(me->multilayer, itype, k) = v;
+        me->flag(me->multilayer, k, itype) = v;
+      }
+  } else {
+    me->flag(me->overridable, itype, jtype) = 0;
+    me->flag(me->overridable, jtype, itype) = 0;
+  }
+}
+
+void EmDee_set_pair_model(tEmDee md, int itype, int jtype, void* model, double kCoul) {
+  const char* task = "pair model setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  if (!ranged({itype, jtype}, me->ntypes)) error(task, "provided type index is out of range");
+  HostModel* m = handle(model);
+  if (m == nullptr || m->family != F_PAIR) error(task, "a valid pair model must be provided");
+  for (int layer = 1; layer <= me->nlayers; ++layer) set_pair_type(*me, itype, jtype, layer, *m, kCoul);
+  after_pair_setting(me, itype, jtype, 0);
+}
+
+void EmDee_set_pair_multimodel(tEmDee md, int itype, int jtype, void* model[], double kCoul[]) {
+  const char* task = "pair multimodel setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  if (!ranged({itype, jtype}, me->ntypes)) error(task, "provided type index is out of range");
+  for (int layer = 1; layer <= me->nlayers; ++layer) {
+    HostModel* m = handle(model[layer - 1]);
+    if (m == nullptr) error(task, std::to_string(me->nlayers) + " valid pair models must be provided");
+    if (m->family != F_PAIR) error(task, "a valid pair model must be provided");
+    set_pair_type(*me, itype, jtype, layer, *m, kCoul[layer - 1]);
+  }
+  after_pair_setting(me, itype, jtype, 1);
+}
+
+void EmDee_set_kspace_model(tEmDee md, void* model) {
+  const char* task = "kspace model setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  HostModel* m = handle(model);
+  if (m == nullptr || m->family != F_KSPACE) error(task, "a valid kspace model must be provided");
+  me->kspace = *m;
+  me->kspace_active = true;
+}
+
+static void set_coul_layer(System* me, int layer, const HostModel& m) {
+  const double cutoff = me->layerRc(layer);
+  me->coul[layer - 1] = m;
+  cutoff_setup(me->coul[layer - 1], cutoff);
+  modifier_setup(me->coul[layer - 1], cutoff);   // literal call order of src/EmDeeCode.f90:474-475 (Q1, Q1b)
+}
+
+void EmDee_set_coul_model(tEmDee md, void* model) {
+  const char* task = "coulomb model setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  HostModel* m = handle(model);
+  if (m == nullptr || m->family != F_COUL) error(task, "a valid coulomb model must be provided");
+  for (int layer = 1; layer <= me->nlayers; ++layer) set_coul_layer(me, layer, *m);
+}
+
+void EmDee_set_coul_multimodel(tEmDee md, void* model[]) {
+  const char* task = "coulomb multimodel setup";
+  System* me = sys(md);
+  if (me->initialized) error(task, "cannot set model after coordinates have been defined");
+  for (int layer = 1; layer <= me->nlayers; ++layer) {
+    HostModel* m = handle(model[layer - 1]);
+    if (m == nullptr) error(task, std::to_string(me->nlayers) + " valid coulomb models must be provided");
+    if (m->family != F_COUL) error(task, "a valid coulomb model must be provided");
+    set_coul_layer(me, layer, *m);
+  }
+}
+
+void EmDee_ignore_pair(tEmDee md, int i, int j) {   // src/EmDeeCode.f90:524-570
+  System* me = sys(md);
+  if (i == j || !ranged({i, j}, me->N)) return;
+  auto insert = [&](int a, int b) {
+    std::vector<int>& row = me->excluded[a - 1];
+    size_t pos = 0;
+    while (pos < row.size() && row[pos] < b) ++pos;
+    if (pos < row.size() && row[pos] == b) return;
+    row.insert(row.begin() + pos, b);
+    me->exclusions_dirty = true;
+  };
+  insert(i, j);
+  insert(j, i);
+}
+
+void EmDee_add_bond(tEmDee, int, int, void*) { unsupported("add_bond"); }
+void EmDee_add_angle(tEmDee, int, int, int, void*) { unsupported("add_angle"); }
+void EmDee_add_dihedral(tEmDee, int, int, int, int, void*) { unsupported("add_dihedral"); }
+
+void EmDee_compute_forces(tEmDee* md);
+
+void EmDee_download(tEmDee md, const char* option, double* address) {
+  System* me = sys(md);
+  const std::string item = opt(option);
+  if (address == nullptr) error("download", "provided address is invalid");
+  if (item == "box") {
+    *address = me->Lbox;
+  } else if (item == "coordinates") {
+    if (!me->hasR) error("download", "coordinates have not been allocated");
+    me->engine->download_coordinates(address);
+  } else if (item == "momenta") {
+    if (me->nbodies() != 0) unsupported("download (momenta of rigid bodies)");
+    me->engine->download_momenta(address);
+  } else if (item == "forces") {
+    if (!me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(&md);
+    me->engine->download_forces(me->layer - 1, address);
+  } else if (item == "centersOfMass" || item == "quaternions" || item == "quatmom" || item == "quattau" ||
+             item == "angmom" || item == "bodycoord" || item == "bodymom" || item == "bodyforces" ||
+             item == "torques" || item == "inertia") {
+    unsupported("download (rigid-body properties)");
+  } else {
+    error("download", "invalid option");
+  }
+}
+
+void EmDee_switch_model_layer(tEmDee* md, int layer) {   // src/EmDeeCode.f90:929-946
+  System* me = sys(*md);
+  if (layer == me->layer) return;
+  if (layer < 1 || layer > me->nlayers) error("model layer switch", "selected layer is out of range");
+  me->layer = layer;
+  md->Energy = me->layerEnergy[layer - 1];
+  md->Virial = me->layerVirial[layer - 1];
+}
+
+void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/EmDeeCode.f90:805-925
+  System* me = sys(*md);
+  const std::string item = opt(option);
+  if (address == nullptr) error("upload", "provided address is invalid");
+  auto initialize_system = [&]() {
+    perform_initialization(*me, md);
+    for (int layer = me->nlayers; layer >= 1; --layer) {
+      EmDee_switch_model_layer(md, layer);
+      EmDee_compute_forces(md);
+    }
+  };
+  if (item == "box") {
+    me->hasL = true;
+    me->Lbox = *address;
+    if (me->initialized) invalidate(*me, md);
+    else if (me->hasR) initialize_system();
+  } else if (item == "coordinates") {
+    me->hasR = true;
+    if (me->nbodies() != 0) {
+      me->hostR.assign(address, address + 3 * (size_t)me->N);
+      if (me->initialized) {
+        invalidate(*me, md);
+        if (md->Options.AutoBodyUpdate) {
+          std::vector<double> delta;
+          update_rigid_bodies(*me, delta);
+          me->engine->upload_body_delta(delta.data());
+        }
+        me->engine->upload_coordinates(me->hostR.data());
+      } else if (me->hasL) {
+        initialize_system();   // uploads the body-updated coordinates itself
+      }
+    } else {
+      me->engine->upload_coordinates(address);
+      if (me->initialized) invalidate(*me, md);
+      else if (me->hasL) initialize_system();
+    }
+  } else if (item == "momenta") {
+    if (!me->initialized) error("upload", "box and coordinates have not been defined");
+    if (me->nbodies() != 0) unsupported("upload (momenta of rigid bodies)");
+    me->engine->upload_momenta(address);
+    double twoKE[3] = {0, 0, 0};
+    for (int i = 0; i < me->N; ++i)
+      for (int x = 0; x < 3; ++x) twoKE[x] += me->invMass[i] * address[3 * (size_t)i + x] * address[3 * (size_t)i + x];
+    set_kinetic(md, twoKE);
+  } else if (item == "forces") {
+    if (!me->initialized) error("upload", "box and coordinates have not been defined");
+    me->engine->upload_forces(me->layer - 1, address);
+  } else if (item == "charges") {
+    if (me->initialized) error("upload", "cannot set charges after box and coordinates initialization");
+    for (int i = 0; i < me->N; ++i) {
+      me->charge[i] = address[i];
+      me->charged[i] = std::fabs(address[i]) > 2.220446049250313e-16;
+    }
+    invalidate(*me, md);
+  } else {
+    error("upload", "invalid option");
+  }
+}
+
+void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {   // src/EmDeeCode.f90:950-1020
+  System* me = sys(*md);
+  if (me->random.seeding_required) me->random.seed(seed);
+  if (me->nbodies() != 0) unsupported("random_momenta (rigid bodies)");
+  std::vector<double> P(3 * (size_t)me->N, 0.0);
+  double twoKE[3] = {0, 0, 0};
+  for (int i : me->freeAtoms) {
+    const double s = std::sqrt(me->mass[i] * kT);
+    for (int x = 0; x < 3; ++x) P[3 * (size_t)i + x] = s * me->random.normal();
+    for (int x = 0; x < 3; ++x) twoKE[x] += me->invMass[i] * P[3 * (size_t)i + x] * P[3 * (size_t)i + x];
+  }
+  if (adjust) {
+    double vcm[3] = {0, 0, 0};
+    for (int x = 0; x < 3; ++x) {
+      for (int i : me->freeAtoms) vcm[x] += P[3 * (size_t)i + x];
+      vcm[x] /= me->totalMass;
+      twoKE[x] = 0.0;
+    }
+    for (int i : me->freeAtoms)
+      for (int x = 0; x < 3; ++x) {
+        P[3 * (size_t)i + x] -= me->mass[i] * vcm[x];
+        twoKE[x] += me->invMass[i] * P[3 * (size_t)i + x] * P[3 * (size_t)i + x];
+      }
+    const double factor = std::sqrt((3 * (int)me->freeAtoms.size() - 3) * kT / (twoKE[0] + twoKE[1] + twoKE[2]));
+    for (double& p : P) p *= factor;
+    for (int x = 0; x < 3; ++x) twoKE[x] *= factor * factor;
+  }
+  me->engine->upload_momenta(P.data());
+  set_kinetic(md, twoKE);
+}
+
+void EmDee_boost(tEmDee* md, double lambda, double alpha, double dt) {   // src/EmDeeCode.f90:1024-1065
+  System* me = sys(*md);
+  double CF = phi(alpha * dt) * dt;
+  const double CP = 1.0 - alpha * CF;
+  CF = lambda * CF;
+  if (lambda != 0.0 && !me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(md);
+  if (me->nbodies() != 0) unsupported("boost (rigid bodies)");
+  const bool compute = md->Options.Compute;
+  emdee::KineticScalars ke;
+  if (md->Options.Translate) me->engine->boost(me->layer - 1, CP, CF, compute, ke);
+  if (compute) {
+    if (md->Options.Translate)
+      for (int x = 0; x < 3; ++x) md->Kinetic.TransPart[x] = 0.5 * ke.twoKE[x];
+    if (md->Options.Rotate) {
+      for (int x = 0; x < 3; ++x) md->Kinetic.RotPart[x] = 0.0;
+      md->Kinetic.Rotational = 0.0;
+    }
+    md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] + md->Kinetic.Rotational;
+  }
+  md->Kinetic.UpToDate = compute;
+}
+
+void EmDee_displace(tEmDee* md, double lambda, double alpha, double dt) {   // src/EmDeeCode.f90:1069-1103
+  System* me = sys(*md);
+  const double t0 = now();
+  double CR = 1.0, CP = dt;
+  if (alpha != 0.0) {
+    CP = phi(alpha * dt) * dt;
+    CR = 1.0 - alpha * CP;
+    me->Lbox = CR * me->Lbox;
+  }
+  CP = lambda * CP;
+  if (me->nbodies() != 0) unsupported("displace (rigid bodies)");
+  if (md->Options.Translate) me->engine->displace(CR, CP);
+  invalidate(*me, md);
+  md->Time.Motion += now() - t0;
+}
+
+void EmDee_verlet_step(tEmDee*, double) { unsupported("verlet_step"); }
+
+void EmDee_compute_forces(tEmDee* md) {   // src/EmDeeCode.f90:1215-1277
+  System* me = sys(*md);
+  if (!me->initialized) error("force computation", "box and coordinates have not been defined");
+  if (me->exclusions_dirty) push_exclusions(*me);
+  const bool compute = md->Options.Compute;
+  emdee::ForceScalars r;
+  double tn = 0.0;
+  const double t0 = now();
+  const bool rebuilt = me->engine->compute_forces(me->layer - 1, compute, me->Lbox, r, tn);
+  if (rebuilt) md->Builds += 1;
+  md->Time.Neighbor += tn;
+  double Wlong = 0.0;
+  if (me->coul[me->layer - 1].requires_kspace) Wlong = r.Ecoul - r.Wcoul;   // W(long) = E(coul) + E(long) - W(coul), E(long) not evaluated
+  md->Virial.Total = r.Wpair + r.Wcoul + Wlong;
+  if (me->nbodies() != 0) {
+    md->Virial.Body = r.Wbody;
+    md->Virial.Total = md->Virial.Total + md->Virial.Body;
+  }
+  if (compute) {
+    md->Energy.Dispersion = r.Epair;
+    md->Energy.Coulomb = r.Ecoul;
+    md->Energy.Bond = 0.0;
+    md->Energy.Angle = 0.0;
+    md->Energy.Potential = r.Epair + r.Ecoul;
+    md->Energy.ShadowPotential = md->Energy.Potential;
+  }
+  md->Energy.UpToDate = compute;
+  me->forcesUpToDate[me->layer - 1] = 1;
+  me->layerEnergy[me->layer - 1] = md->Energy;
+  me->layerVirial[me->layer - 1] = md->Virial;
+  const double t1 = now();
+  md->Time.Pair += (t1 - t0) - tn;
+  md->Time.Total = t1 - me->startTime;
+}
+
+void EmDee_rdf(tEmDee, int, double, int, int*, int*, double*) { unsupported("radial distribution calculation"); }
+
+void* EmDee_shifted(void* m) { return with_modifier(m, nb::M_SHIFTED, 0, false, "shifted potential assignment"); }
+void* EmDee_shifted_force(void* m) { return with_modifier(m, nb::M_SHIFTED_FORCE, 0, false, "shifted-force potential assignment"); }
+void* EmDee_smoothed(void* m, double skin) { return with_modifier(m, nb::M_SMOOTHED, skin, true, "smoothed potential assignment"); }
+void* EmDee_shifted_smoothed(void* m, double skin) { return with_modifier(m, nb::M_SHIFTED_SMOOTHED, skin, true, "shifted-smoothed potential assignment"); }
+void* EmDee_square_smoothed(void* m, double skin) { return with_modifier(m, nb::M_SQUARE_SMOOTHED, skin, true, "square-smoothed potential assignment"); }
+void* EmDee_shifted_square_smoothed(void* m, double skin) { return with_modifier(m, nb::M_SHIFTED_SQUARE_SMOOTHED, skin, true, "shifted-square-smoothed potential assignment"); }
+
+void* EmDee_pair_none(void) { return deliver(blank(F_PAIR, nb::K_PAIR_NONE, "none")); }
+void* EmDee_coul_none(void) { return deliver(blank(F_COUL, nb::K_COUL_NONE, "none")); }
+void* EmDee_bond_none(void) { return deliver(blank(F_BOND, 0, "none")); }
+void* EmDee_angle_none(void) { return deliver(blank(F_ANGLE, 0, "none")); }
+void* EmDee_dihedral_none(void) { return deliver(blank(F_DIHEDRAL, 0, "none")); }
+void* EmDee_pair_lj_cut(double epsilon, double sigma) { return deliver(make_lj(epsilon, sigma)); }
+void* EmDee_pair_softcore_cut(double epsilon, double sigma, double lambda) { return deliver(make_softcore(epsilon, sigma, lambda)); }
+void* EmDee_coul_cut(void) { return deliver(blank(F_COUL, nb::K_COUL_CUT, "cut")); }
+void* EmDee_coul_sf(void) {
+  HostModel m = blank(F_COUL, nb::K_COUL_SF, "sf");
+  m.shifted_force = true;
+  return deliver(m);
+}
+static HostModel damped_family(int kind, const char* name, double damp, double skinWidth) {
+  HostModel m = blank(F_COUL, kind, name);
+  m.skinWidth = skinWidth;
+  m.dev.a = damp;                                            // alpha
+  m.dev.b = 2.0 * damp / std::sqrt(3.14159265358979323846);  // beta
+  return m;
+}
+void* EmDee_coul_damped(double damp) { return deliver(damped_family(nb::K_COUL_DAMPED, "damped", damp, 0.0)); }
+void* EmDee_coul_long(void) {
+  HostModel m = blank(F_COUL, nb::K_COUL_DAMPED, "long");
+  m.requires_kspace = true;
+  m.is_long = true;
+  return deliver(m);
+}
+void* EmDee_coul_damped_smoothed(double damp, double skinWidth) {
+  return deliver(damped_family(nb::K_COUL_DAMPED_SMOOTHED, "damped_openmm_smoothed", damp, skinWidth));
+}
+void* EmDee_coul_damped_square_smoothed(double damp, double skinWidth) {
+  return deliver(damped_family(nb::K_COUL_DAMPED_SQUARE_SMOOTHED, "damped_smoothed", damp, skinWidth));
+}
+void* EmDee_coul_square_smoothed(double skinWidth) {
+  HostModel m = blank(F_COUL, nb::K_COUL_SQUARE_SMOOTHED, "smoothed");
+  m.skinWidth = skinWidth;
+  return deliver(m);
+}
+void* EmDee_coul_shifted_square_smoothed(double skinWidth) {
+  HostModel m = blank(F_COUL, nb::K_COUL_SHIFTED_SQUARE_SMOOTHED, "shifted_smoothed");
+  m.skinWidth = skinWidth;
+  m.shifted = true;
+  return deliver(m);
+}
+void* EmDee_bond_harmonic(double, double) { return deliver(blank(F_BOND, 1, "harmonic")); }
+void* EmDee_angle_harmonic(double, double) { return deliver(blank(F_ANGLE, 1, "harmonic")); }
+void* EmDee_kspace_ewald(double accuracy) {
+  HostModel m = blank(F_KSPACE, 1, "ewald");
+  m.accuracy = accuracy;
+  return deliver(m);
+}
+
+// ---- extensions -----------------------------------------------------------------------------------
+long long EmDeeX_pair_count(tEmDee md) { return sys(md)->engine->pair_count(); }
+long long EmDeeX_download_pairs(tEmDee md, int* pairs, long long capacity) {
+  return sys(md)->engine->download_pairs(pairs, capacity);
+}
+void EmDeeX_finalize(tEmDee* md) {
+  System* me = sys(*md);
+  if (me == nullptr) return;
+  delete me->engine;
+  delete me;
+  md->Data = nullptr;
+}
+void EmDeeX_stats(tEmDee md, tEmDeeXStats* out) {
+  System* me = sys(md);
+  if (me->initialized) me->engine->update_list_stats(me->layer - 1, me->Lbox);
+  emdee::EngineStats s = me->engine->stats();
+  out->launches = s.launches;
+  out->force_launches = s.force_launches;
+  out->force_ms = s.force_ms;
+  out->build_launches = s.build_launches;
+  out->build_ms = s.build_ms;
+  out->list_entries = s.list_entries;
+  out->interacting = s.interacting;
+  out->cells_per_dim = s.cells_per_dim;
+  out->device = s.device;
+}
+void EmDeeX_set_kernel_timing(tEmDee md, int enabled) { sys(md)->engine->set_kernel_timing(enabled != 0); }
+void EmDeeX_synchronize(tEmDee md) { sys(md)->engine->synchronize(); }
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// engine.h -- device-resident state and the CUDA hot path behind the EmDee C ABI.
+//
+// The host shim (abi.cpp) owns model semantics (setup order, mixing, modifiers: reference
+// src/EmDeeData.f90:193-264, src/modelClass_*.f90) and hands the engine flat POD tables; the engine
+// owns everything that lives in HBM and every kernel (engine.cu). No reference type appears here.
+#pragma once
+
+#include <vector>
+
+#include "nb_math.h"
+
+namespace emdee {
+
+// One (itype, jtype) cell of a layer's interaction table (reference pairContainer,
+// src/modelClass_pair.f90:66-74, after set_pair_type / mixing / modifier_setup).
+struct PairEntry {
+  nb::DevModel model;
+  double kCoul;
+  int coulomb;   // pair%coulomb
+  int pad;
+};
+
+struct LayerTable {
+  std::vector<PairEntry> pair;   // ntypes*ntypes, index = itype*ntypes + jtype (0-based, symmetric)
+  nb::DevModel coul;             // me%coul(layer)%model
+  bool pairs_exist = false;      // me%pairs_exist(layer)
+  bool useInRc = false;          // me%useInRc(layer)
+};
+
+struct ForceScalars {
+  double Epair = 0, Ecoul = 0, Wpair = 0, Wcoul = 0, Wbody = 0;
+};
+
+struct KineticScalars {
+  double twoKE[3] = {0, 0, 0};   // sum over free atoms of p^2/m per dimension
+};
+
+struct EngineStats {
+  long long launches = 0, force_launches = 0, build_launches = 0;
+  double force_ms = 0, build_ms = 0;
+  long long list_entries = 0, interacting = 0;
+  int cells_per_dim = 0, device = 0;
+};
+
+class Engine {
+ public:
+  Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, const int* atomType1,
+         const double* mass, const double* invMass, const int* atomBody, int nbodies);
+  ~Engine();
+
+  // ---- setup-time state --------------------------------------------------------------------
+  void set_inner_cutoff(double InRc);                                    // EmDee_layer_based_parameters
+  void set_exclusions(const std::vector<int>& first, const std::vector<int>& last,
+                      const std::vector<int>& item);                     // 1-based CSR, reference layout
+  void set_charges(const double* q);
+  void set_interact(const std::vector<char>& interact);                  // ntypes*ntypes
+  void set_layer(int layer0, const LayerTable& t);
+
+  // ---- transfers (host pointers; pinned or pageable) ---------------------------------------
+  void upload_coordinates(const double* R);
+  void upload_body_delta(const double* delta);                           // (3,N), zero for free atoms
+  void upload_momenta(const double* P);
+  void upload_forces(int layer0, const double* F);
+  void download_coordinates(double* R);
+  void download_momenta(double* P);
+  void download_forces(int layer0, double* F);
+
+  // ---- hot path ----------------------------------------------------------------------------
+  // Neighbor-list maintenance (reference handle_neighbor_lists) + pair loop (compute_pairs).
+  // Returns true if the list was rebuilt.
+  bool compute_forces(int layer0, bool compute, double Lbox, ForceScalars& out, double& neighbor_seconds);
+
+  // ---- device-resident dynamics for free atoms (reference boost / move / kinetic_energies) --
+  void boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke);
+  void displace(double CR, double CP);
+
+  // ---- extensions --------------------------------------------------------------------------
+  long long pair_count();
+  void update_list_stats(int layer0, double Lbox);   // fills list_entries / interacting
+  long long download_pairs(int* pairs, long long capacity);
+  void set_kernel_timing(bool on) { timing_ = on; }
+  void synchronize();
+  EngineStats stats() const { return stats_; }
+
+ private:
+  struct Impl;
+  Impl* d_;
+  bool timing_ = false;
+  EngineStats stats_;
+};
+
+}  // namespace emdee

@@ -1,0 +1,94 @@
+"""CPU-side checks of the drop-in boundary: the CUDA library loads, exports every symbol that
+include/emdee.h and include/emdee_ext.h declare, mirrors the reference's struct layout, and refuses to
+run without a GPU (no CPU fallback). No compute call is made here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+import common as cm
+
+INCLUDE = os.path.join(cm.ROOT, "include")
+
+
+def declared_symbols(header):
+    text = open(os.path.join(INCLUDE, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(EmDeeX?_\w+)\s*\(", text)))
+
+
+def test_headers_declare_the_reference_symbol_set():
+    names = declared_symbols("emdee.h")
+    assert len(names) == 46, names                      # 33 hand-written + 13 generated
+    assert set(names) == set(cm.api.ABI)
+
+
+@pytest.mark.parametrize("path", [cm.api.PRODUCT_LIB, cm.ORACLE_STRICT])
+def test_library_exports_every_declared_symbol(path):
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build()
+    dll = C.CDLL(path, mode=os.RTLD_NOW | os.RTLD_LOCAL)
+    for name in declared_symbols("emdee.h"):
+        assert hasattr(dll, name), f"{os.path.basename(path)} lacks {name}"
+    ext = declared_symbols("emdee_ext.h")
+    product_only = {"EmDeeX_stats", "EmDeeX_set_kernel_timing", "EmDeeX_synchronize"}
+    for name in ext:
+        if path == cm.ORACLE_STRICT and name in product_only:
+            continue
+        assert hasattr(dll, name), f"{os.path.basename(path)} lacks {name}"
+
+
+def test_struct_layout_matches_reference_implementation():
+    # reference src/EmDeeCode.f90:36-61, src/EmDeeData.f90:40-64 (x86-64 SysV): see SURVEY.md section 8(b)
+    t = cm.api.tEmDee
+    assert C.sizeof(t) == 240
+    off = {f[0]: getattr(t, f[0]).offset for f in t._fields_}
+    assert off == {"Builds": 0, "Time": 8, "Energy": 40, "Kinetic": 104, "Virial": 192, "DoF": 208,
+                   "RotDoF": 212, "Data": 216, "Options": 224}
+    o = cm.api.tOpts
+    assert (o.Translate.offset, o.Rotate.offset, o.RotationMode.offset, o.AutoBodyUpdate.offset,
+            o.Compute.offset) == (0, 1, 4, 8, 9)
+    assert cm.api.tEnergy.UpToDate.offset == 56 and cm.api.tKinetic.UpToDate.offset == 80
+
+
+def test_backend_tags():
+    assert cm.product().backend == "b200-cuda"
+    assert cm.oracle().backend == "oracle-cpu"
+
+
+def test_model_constructors_and_modifiers_work_without_a_device():
+    lib = cm.product()
+    lj = lib.EmDee_pair_lj_cut(1.0, 1.0)
+    assert lj and lib.EmDee_shifted_force(lj) and lib.EmDee_smoothed(lj, 0.5)
+    assert lib.EmDee_coul_damped_smoothed(0.2, 1.0) and lib.EmDee_kspace_ewald(1e-4)
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_product_fails_loudly_without_a_gpu():
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import common as cm; "
+            "cm.product().system(1, 1, 2.5, 0.3, 10, None, None, None)") % (cm.ROOT, os.path.join(cm.ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "no CUDA device is available" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_error_convention_matches_reference():
+    """reference src/global.f90:51-56: 'Error in <task>: <msg>.' on stderr and exit status 1."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import common as cm; "
+            "lib = cm.oracle(); s = lib.system(1, 1, 2.5, 0.3, 10, None, None, None); "
+            "s.set_pair_model(1, 2, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0)") % (cm.ROOT, os.path.join(cm.ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "Error in pair model setup: provided type index is out of range." in r.stderr
