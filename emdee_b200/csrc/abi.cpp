@@ -1054,5 +1054,6 @@ void EmDeeX_stats(tEmDee md, tEmDeeXStats* out) {
 }
 void EmDeeX_set_kernel_timing(tEmDee md, int enabled) { sys(md)->engine->set_kernel_timing(enabled != 0); }
 void EmDeeX_synchronize(tEmDee md) { sys(md)->engine->synchronize(); }
+double EmDeeX_measure_fp64_tflops(void) { return emdee::measure_fp64_fma_tflops(); }
 
 }  // extern "C"

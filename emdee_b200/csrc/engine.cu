@@ -1011,3 +1011,47 @@ long long Engine::download_pairs(int* pairs, long long capacity) {
 }
 
 }  // namespace emdee
+
+// ---- FP64 issue-rate microbenchmark (roofline denominator that MEASURED_PEAKS.json does not carry) ----
+namespace emdee {
+namespace {
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;   // keep the chain alive
+}
+}  // namespace
+
+double measure_fp64_fma_tflops() {
+  int dev = 0, sms = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  const int iters = 1 << 14, grid = sms * 8, tpb = 256;
+  k_dfma_peak<<<grid, tpb>>>(d, iters, 1.0);   // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_CHECK(cudaEventRecord(e0));
+    k_dfma_peak<<<grid, tpb>>>(d, iters, 1.0 + rep);
+    CUDA_CHECK(cudaEventRecord(e1));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 8.0 * (double)iters * grid * tpb / (ms * 1e-3) / 1e12;
+    best = tf > best ? tf : best;
+  }
+  CUDA_CHECK(cudaFree(d));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}
+}  // namespace emdee

@@ -89,4 +89,7 @@ class Engine {
   EngineStats stats_;
 };
 
+// DFMA microbenchmark on the current device: sustained FP64 FMA throughput in TFLOP/s.
+double measure_fp64_fma_tflops();
+
 }  // namespace emdee

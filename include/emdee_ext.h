@@ -54,6 +54,10 @@ void EmDeeX_set_kernel_timing( tEmDee md, int enabled );
 
 /* Block until all queued device work of this system has finished. */
 void EmDeeX_synchronize( tEmDee md );
+
+/* DFMA microbenchmark on the current device: measured FP64 FMA throughput in TFLOP/s (the FP64
+   roofline denominator; MEASURED_PEAKS.json carries only HBM and bf16 figures). */
+double EmDeeX_measure_fp64_tflops( void );
 #endif
 
 #ifdef __cplusplus

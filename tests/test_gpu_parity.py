@@ -214,11 +214,12 @@ def _two_type_system(lib, coul=None, layers=1, multimodel=False, inner=None):
     else:
         s.set_pair_model(1, 1, a, 1.0)
         s.set_pair_model(2, 2, b, 1.0)   # (1,2) is auto-mixed: softcore x lj rule, modifier dropped (Q3b)
-    if coul is not None:
+    cmodel = coul(lib) if coul is not None else None
+    if cmodel is not None:
         if multimodel:
-            s.set_coul_multimodel([coul(lib), lib.EmDee_coul_cut()][:layers])
+            s.set_coul_multimodel([cmodel, lib.EmDee_coul_cut()][:layers])
         else:
-            s.set_coul_model(coul(lib))
+            s.set_coul_model(cmodel)
     for i in range(1, N):
         for j in range(i + 1, min(i + 4, N + 1)):
             s.ignore_pair(i, j)
