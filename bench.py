@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s of EmDee's nonbonded hot path (neighbor-list maintenance + pair
+forces/energy/virial) on the synthetic LJ box BASELINE.json names, through the C ABI.
+
+  python bench.py --gpus N --steps K --warmup W            product (CUDA, emdee_b200/lib/libemdee.so)
+  python bench.py --impl reference --gpus N --steps K ...  the reference ALGORITHM on host cores
+                                                           (CPU oracle port: the Fortran reference cannot
+                                                           be built in this image)
+
+A "step" is one velocity-Verlet step of the reference's own test loop (reference
+test/common/contained.f90:63-72): EmDee_boost, EmDee_displace, EmDee_boost -- i.e. exactly one
+EmDee_compute_forces (rebuild check, list rebuild when triggered, forces + energy + virial with
+Options.Compute = true) plus the two tiny momentum/position updates that produce the next configuration.
+
+  value : atoms x steps / time with the state RESIDENT in HBM (only the scalars come back each call)
+  e2e   : same metric with HOST buffers: each step uploads that step's coordinates from pinned host
+          memory (EmDee_upload), runs EmDee_compute_forces and downloads the forces (EmDee_download)
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("EMDEE_QUIET", "1")
+
+from emdee_b200 import api  # noqa: E402
+
+METRIC = "atom-steps/s (forces+nlist)"
+UNIT = "atom-steps/s"
+
+# workload: BASELINE.json configs[3] -- synthetic LJ fluid, rho* = 0.8442, Rc = 2.5 sigma, energy +
+# virial every step; skin and dt follow SURVEY.md section 8(d) (LAMMPS in.lj convention).
+RHO, RC, SKIN, DT, TSTAR = 0.8442, 2.5, 0.3, 0.005, 1.44
+NCELL_DEFAULT = 63   # fcc 63^3 x 4 = 1 000 188 atoms
+
+
+def make_workload(ncell, seed=86245):
+    N = 4 * ncell ** 3
+    L = (N / RHO) ** (1.0 / 3.0)
+    a = L / ncell
+    base = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) + 0.25
+    g = np.arange(ncell)
+    cells = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+    R = ((cells[:, None, :] + base[None, :, :]) * a).reshape(-1, 3)
+    rng = np.random.default_rng(seed)
+    R = R + rng.uniform(-0.05, 0.05, size=R.shape)
+    P = np.random.default_rng(seed + 1).normal(0.0, np.sqrt(TSTAR), size=R.shape)
+    P -= P.mean(axis=0)
+    return np.ascontiguousarray(R), np.ascontiguousarray(P), L
+
+
+def build_system(lib, R, P, L, threads):
+    s = lib.system(threads, 1, RC, SKIN, R.shape[0], None, None, None)
+    s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0)
+    s.upload("box", np.array([L]))
+    s.upload("coordinates", R)
+    s.upload("momenta", P)
+    s.md.Options.Compute = True
+    return s
+
+
+def md_step(s):
+    s.boost(1.0, 0.0, 0.5 * DT)
+    s.displace(1.0, 0.0, DT)
+    s.boost(1.0, 0.0, 0.5 * DT)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, nme in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_lib():
+    """The CPU restatement of the reference algorithm, -Ofast build (test infrastructure; used here only as
+    the timed CPU baseline / reference arm)."""
+    path = os.path.join(ROOT, "oracle", "_build", "libemdee_oracle_fast.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return api.EmDeeLib(path)
+
+
+def cpu_run(ncell, steps, warmup, threads):
+    """Times the reference algorithm (oracle port) on `threads` host cores: same workload, same step."""
+    lib = oracle_lib()
+    R, P, L = make_workload(ncell)
+    s = build_system(lib, R, P, L, threads)
+    for _ in range(warmup):
+        md_step(s)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        md_step(s)
+    dt = time.perf_counter() - t0
+    N = R.shape[0]
+    out = {"value": N * steps / dt, "seconds": dt, "steps": steps, "N": N, "builds": int(s.md.Builds),
+           "U": s.md.Energy.Potential}
+    s.finalize()
+    return out
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = int(os.environ.get("EMDEE_CPU_THREADS", cores))
+    ncell = args.ncell
+    N = 4 * ncell ** 3
+    # bounded sample: the same 1M-atom box, a few steps (each costs ~0.2-1 s on a multicore host)
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 3))
+    r = cpu_run(ncell, steps, warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(ncell, N, 1, "host cores (no GPU)"),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} velocity-Verlet steps of the {N}-atom LJ box after {warmup} warm-up "
+                                   f"({r['builds']} list builds); reference algorithm restated in C++/OpenMP "
+                                   f"(-Ofast), the Fortran reference cannot be built in this image"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(ncell, N, world, where):
+    return {"workload": f"synthetic LJ fluid, fcc {ncell}^3 x 4 = {N} atoms per GPU, rho*=0.8442, Rc=2.5, skin=0.3, "
+                        f"pair_lj_cut(1,1), T*=1.44, dt=0.005, energy+virial every step (BASELINE.json configs[3])",
+            "atoms_per_gpu": N, "atoms_total": N * world, "rc": RC, "skin": SKIN, "dt": DT,
+            "parallelism": where,
+            "l2_policy": "inputs larger than L2: the neighbor list streamed every step (>300 MB at 1M atoms) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="fcc cells per dimension (atoms = 4*ncell^3)")
+    ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    os.environ["EMDEE_DEVICE"] = str(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = api.load()
+    W = max(args.warmup, 3)
+    K = args.steps
+    ncell = args.ncell
+    # Multi-GPU: independent replicas of the per-GPU box, one per rank (weak scaling). The spatial slab
+    # decomposition with halo exchange is the next row (multi-GPU); no collective is invented here.
+    R, P, L = make_workload(ncell, seed=86245 + 17 * rank)
+    N = R.shape[0]
+    s = build_system(lib, R, P, L, 1)
+    s.set_kernel_timing(True)
+
+    # ---- resident arm ---------------------------------------------------------------------------
+    for _ in range(W):
+        md_step(s)
+    st0 = s.stats()
+    builds0 = s.md.Builds
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(K):
+            md_step(s)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    st1 = s.stats()
+    builds = s.md.Builds - builds0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = N * world * K / (dev_ms_max * 1e-3)
+
+    force_launches = st1.force_launches - st0.force_launches
+    force_ms = (st1.force_ms - st0.force_ms) / max(force_launches, 1)
+    build_launches = st1.build_launches - st0.build_launches
+    build_ms = (st1.build_ms - st0.build_ms) / max(build_launches, 1)
+    launches = st1.launches - st0.launches
+    C_half = st1.list_entries / 2.0 / N          # neighbor-list entries per atom (half-list count, as SURVEY 8(d))
+    P_half = st1.interacting / 2.0 / N           # entries with r < Rc per atom
+
+    # ---- e2e arm: host buffers in the timed region -------------------------------------------------
+    nframes = 24
+    frames = torch.empty((nframes, N, 3), dtype=torch.float64).pin_memory()
+    fout = torch.empty((N, 3), dtype=torch.float64).pin_memory()
+    fr = frames.numpy()
+    for k in range(nframes):
+        md_step(s)
+        fr[k] = s.download("coordinates")
+    order = list(range(nframes)) + list(range(nframes - 2, 0, -1))   # ping-pong: displacements evolve like a trajectory
+    e2eK = min(K, 50)
+    import ctypes as C
+    fptr = C.c_void_p(fout.data_ptr())
+
+    def e2e_step(k):
+        frame = frames[order[k % len(order)]]
+        lib.EmDee_upload(C.byref(s.md), b"coordinates", C.c_void_p(frame.data_ptr()))
+        lib.EmDee_compute_forces(C.byref(s.md))
+        lib.EmDee_download(s.md, b"forces", fptr)
+
+    for k in range(3):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for k in range(e2eK):
+        e2e_step(3 + k)
+    ev1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = N * world * e2eK / float(t.item())
+
+    # ---- rooflines for the dominant kernel (pair forces) -------------------------------------------
+    hbm_peak, peak_src = measured_peaks()
+    bytes_per_atom = 56.0 + 4.0 * C_half                     # 24 r + 24 F + 8 offsets + 4*C list
+    flops_per_atom = 15.0 * C_half + 22.0 * P_half + 6.0
+    ach_gbs = bytes_per_atom * N / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
+    fp64_peak = lib.EmDeeX_measure_fp64_tflops() if rank == 0 else None
+    ach_tf = flops_per_atom * N / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r = cpu_run(ncell, args.cpu_steps, 1, cores)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_steps} velocity-Verlet steps of the same {N}-atom box after 1 warm-up, "
+                                  f"{r['seconds']:.1f} s; reference algorithm restated in C++/OpenMP (-Ofast)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(ncell, N, world, "single GPU" if world == 1 else
+                                      f"{world} independent replicas, one per GPU (no data-path collective)"),
+            "timing": {"device_ms_total": dev_ms_max, "wall_s": wall, "list_builds_in_timed_region": int(builds),
+                       "force_kernel_ms": force_ms, "build_kernel_ms": build_ms,
+                       "force_kernel_share_of_step": force_ms / (dev_ms_max / K) if K else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 24 * N + 40,
+                    "steps": e2eK, "what": "EmDee_upload(coordinates, pinned host) + EmDee_compute_forces + "
+                                           "EmDee_download(forces, pinned host) per step, wall clock, max over ranks"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_pair_forces", "achieved": ach_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "traffic": None,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_atom": bytes_per_atom, "list_entries_per_atom_half": C_half,
+                         "interacting_per_atom_half": P_half,
+                         "note": "FP64-issue-bound kernel: see roofline_fp64; HBM fraction reported because "
+                                 "MEASURED_PEAKS.json carries only HBM and bf16 peaks"},
+            "roofline_fp64": {"bound": "fp64", "kernel": "k_pair_forces", "achieved": ach_tf, "peak": fp64_peak,
+                              "unit": "TFLOP/s", "frac": (ach_tf / fp64_peak) if (ach_tf and fp64_peak) else None,
+                              "algorithmic_flops_per_atom": flops_per_atom,
+                              "peak_source": "DFMA microbenchmark run in this process (EmDeeX_measure_fp64_tflops)"},
+            "clocks": clocks.summary(),
+            "state": {"U": s.md.Energy.Potential, "W": s.md.Virial.Total, "K": s.md.Kinetic.Total,
+                      "builds_total": int(s.md.Builds)},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    s.finalize()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -998,7 +998,6 @@ long long Engine::download_pairs(int* pairs, long long capacity) {
   if (pairs != nullptr && capacity > 0) dp.ensure(2 * (size_t)capacity);
   CUDA_CHECK(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned long long), s.stream));
   k_export_pairs<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, s.nbr.p, s.nbrCount.p, s.sMeta.p, dp.p, capacity, s.counter.p);
-  stats_.launches += 1;
   unsigned long long n = 0;
   CUDA_CHECK(cudaMemcpyAsync(&n, s.counter.p, sizeof(n), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
