@@ -2,21 +2,22 @@
 // list build, pair force/energy/virial kernels, device-resident velocity-Verlet pieces.
 //
 // Reference loops replaced (paths relative to the reference tree):
-//   k_displacement_check  <- src/neighbor_lists.f90:41-59,184      (maximum_approach_sq + trigger)
-//   k_bin / k_fill / k_place <- src/neighbor_lists.f90:63-171       (distribute_atoms)
-//   k_build_list          <- src/neighbor_lists.f90:199-300         (build_neighbor_lists)
-//   k_refresh_positions   <- src/EmDeeCode.f90:1228                 (Rs = R/L)
-//   k_pair_forces         <- src/compute.f90:20-100 + src/apply_modifier.f90 + model bodies,
-//                            src/EmDeeData.f90:644-685, src/EmDeeCode.f90:1247 (sum of thread forces),
-//                            src/EmDeeData.f90:926-953 (rigid_body_virial, fused in the epilogue)
-//   k_boost / k_displace  <- src/EmDeeData.f90:823-922 (free atoms)
+//   k_displacement_check, k_displace (fused check)  <- src/neighbor_lists.f90:41-59,184
+//   k_bin / k_fill / k_place                        <- src/neighbor_lists.f90:63-171   (distribute_atoms)
+//   k_build_list                                    <- src/neighbor_lists.f90:199-300  (build_neighbor_lists)
+//   k_refresh_positions                             <- src/EmDeeCode.f90:1228          (Rs = R/L)
+//   k_pair_forces   <- src/compute.f90:20-100 + src/apply_modifier.f90 + model bodies,
+//                      src/EmDeeData.f90:644-685, src/EmDeeCode.f90:1236-1247 (reductions),
+//                      src/EmDeeData.f90:926-953 (rigid_body_virial, fused in the epilogue)
+//   k_boost / k_displace                            <- src/EmDeeData.f90:823-922 (free atoms)
 //
 // Design: atoms are sorted by cell of an EXTENDED grid (M+4)^3 that carries explicit
 // periodic ghost images in a 2-cell shell, so the force kernel needs no minimum-image arithmetic; the
 // Verlet list is a FULL list (both directions of every pair) stored as 32-lane tiles (ELL-in-tile,
 // coalesced 128-byte rows), so every atom's force is finished inside one thread: no atomics, no
 // scatter, deterministic summation order. List MEMBERSHIP is decided with the reference's exact
-// arithmetic (un-fused IEEE operations on unwrapped scaled coordinates), so pair sets are bit-identical.
+// arithmetic (un-fused IEEE operations on unwrapped scaled coordinates), so pair sets are bit-identical;
+// an FP32 pre-test with a rigorous error band only short-cuts candidates far from the cutoff sphere.
 #include "engine.h"
 
 #include <cuda_runtime.h>
@@ -24,6 +25,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,13 +71,60 @@ constexpr int TPB = 128;           // threads per block for per-atom / per-entry
 constexpr int TILE = 32;           // list tile = one warp of consecutive sorted entries
 constexpr int MAX_SMEM_TYPES = 16; // interaction table staged in shared memory up to this many types
 constexpr double MAGIC_RINT = 6755399441055744.0;   // 1.5 * 2^52: (x + M) - M == rint(x) for |x| < 2^51
+constexpr double DEPS = 2.220446049250313e-16;      // epsilon(1d0): charged = |q| > epsilon
 
 inline int nblocks(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+
+// ------------------------------------------------------------------------------------------------
+// Grid-wide finish without a second launch: every block publishes WIDTH partial sums, takes a ticket,
+// and the block drawing the last ticket folds all partials in a FIXED order (thread t sums blocks
+// t, t+T, ...; then a fixed shared-memory tree), so the result never depends on which block is last.
+// ------------------------------------------------------------------------------------------------
+template <int WIDTH>
+__device__ __forceinline__ void grid_finish(const double (&mine)[WIDTH], double* __restrict__ partial,
+                                            unsigned int* __restrict__ ticket, double* __restrict__ out,
+                                            double scale_first4) {
+  __shared__ double fin[TPB][WIDTH];
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < WIDTH; ++q) partial[(size_t)blockIdx.x * WIDTH + q] = mine[q];
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double acc[WIDTH];
+#pragma unroll
+  for (int q = 0; q < WIDTH; ++q) acc[q] = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += TPB) {
+#pragma unroll
+    for (int q = 0; q < WIDTH; ++q) acc[q] += __ldcg(&partial[(size_t)b * WIDTH + q]);
+  }
+#pragma unroll
+  for (int q = 0; q < WIDTH; ++q) fin[threadIdx.x][q] = acc[q];
+  __syncthreads();
+  for (int off = TPB / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+#pragma unroll
+      for (int q = 0; q < WIDTH; ++q) fin[threadIdx.x][q] += fin[threadIdx.x + off][q];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < WIDTH; ++q) out[q] = fin[0][q] * ((q < 4) ? scale_first4 : 1.0);
+    *ticket = 0u;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // K0: rebuild trigger. Ordered reduction reproducing the sequential scan of maximum_approach_sq:
 // state (m, n): m = running maximum, n = value `next` holds. combine(A then B) =
 //   B.m > A.m ? (B.m, max(A.m, B.n)) : A.     Atom 0 contributes (d0, d0), atom i>0 (d_i, -inf).
+// The criterion is evaluated where the coordinates change (k_displace) or, after an upload, by
+// k_displacement_check; either way the last block folds the per-block states IN BLOCK ORDER.
 // ------------------------------------------------------------------------------------------------
 struct MaxNext {
   double m, n;
@@ -89,12 +138,27 @@ __device__ __forceinline__ MaxNext mn_combine(MaxNext a, MaxNext b) {
   }
   return a;
 }
-constexpr int CHK_ITEMS = 8;   // consecutive atoms per thread
+__device__ __forceinline__ MaxNext mn_identity() {
+  MaxNext s;
+  s.m = -1.0 / 0.0;
+  s.n = -1.0 / 0.0;
+  return s;
+}
+__device__ __forceinline__ MaxNext mn_atom(const double* __restrict__ R, const double* __restrict__ R0, long long i) {
+  double dx = __dsub_rn(R[3 * i], R0[3 * i]);
+  double dy = __dsub_rn(R[3 * i + 1], R0[3 * i + 1]);
+  double dz = __dsub_rn(R[3 * i + 2], R0[3 * i + 2]);
+  double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  MaxNext e;
+  e.m = d;
+  e.n = (i == 0) ? d : -1.0 / 0.0;
+  return e;
+}
 
+// ordered reduction over the block (thread order = atom order); result valid in thread 0
 __device__ __forceinline__ MaxNext block_ordered_reduce(MaxNext s) {
   __shared__ MaxNext warp_state[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ordered tree inside the warp: lane L absorbs lane L+off (its right-hand neighbour segment)
   for (int off = 1; off < 32; off <<= 1) {
     MaxNext o;
     o.m = __shfl_down_sync(0xffffffffu, s.m, off);
@@ -108,49 +172,51 @@ __device__ __forceinline__ MaxNext block_ordered_reduce(MaxNext s) {
     const int nw = (blockDim.x + 31) >> 5;
     for (int w = 1; w < nw; ++w) r = mn_combine(r, warp_state[w]);
   }
-  return r;   // valid in thread 0
+  __syncthreads();
+  return r;
+}
+
+// publish this block's state; the last block folds all block states in block order and writes
+// maximum + 2*sqrt(maximum*next) + next (reference neighbor_lists.f90:57)
+__device__ __forceinline__ void check_finish(MaxNext mine, MaxNext* __restrict__ partial,
+                                             unsigned int* __restrict__ ticket, double* __restrict__ result) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = mine;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int nparts = gridDim.x;
+  const int per = (nparts + blockDim.x - 1) / blockDim.x;
+  MaxNext s = mn_identity();
+  for (int q = 0; q < per; ++q) {
+    int i = threadIdx.x * per + q;
+    if (i < nparts) {
+      MaxNext p;
+      p.m = __ldcg(&partial[i].m);
+      p.n = __ldcg(&partial[i].n);
+      s = mn_combine(s, p);
+    }
+  }
+  s = block_ordered_reduce(s);
+  if (threadIdx.x == 0) {
+    result[0] = __dadd_rn(__dadd_rn(s.m, __dmul_rn(2.0, __dsqrt_rn(__dmul_rn(s.m, s.n)))), s.n);
+    *ticket = 0u;
+  }
 }
 
 __global__ void __launch_bounds__(TPB) k_displacement_check(const double* __restrict__ R,
                                                             const double* __restrict__ R0, int N,
-                                                            MaxNext* __restrict__ partial) {
-  const double NEG_INF = -1.0 / 0.0;
-  long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * CHK_ITEMS;
-  MaxNext s;
-  s.m = NEG_INF;
-  s.n = NEG_INF;
-  for (int q = 0; q < CHK_ITEMS; ++q) {
-    long long i = first + q;
-    if (i < N) {
-      double dx = __dsub_rn(R[3 * i], R0[3 * i]);
-      double dy = __dsub_rn(R[3 * i + 1], R0[3 * i + 1]);
-      double dz = __dsub_rn(R[3 * i + 2], R0[3 * i + 2]);
-      double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      MaxNext e;
-      e.m = d;
-      e.n = (i == 0) ? d : NEG_INF;
-      s = mn_combine(s, e);
-    }
-  }
-  s = block_ordered_reduce(s);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-
-__global__ void __launch_bounds__(256) k_displacement_final(const MaxNext* __restrict__ partial, int nparts,
+                                                            MaxNext* __restrict__ partial,
+                                                            unsigned int* __restrict__ ticket,
                                                             double* __restrict__ result) {
-  const double NEG_INF = -1.0 / 0.0;
-  // each thread folds a contiguous range of block partials, then an ordered block reduction
-  int per = (nparts + blockDim.x - 1) / blockDim.x;
-  MaxNext s;
-  s.m = NEG_INF;
-  s.n = NEG_INF;
-  for (int q = 0; q < per; ++q) {
-    int i = threadIdx.x * per + q;
-    if (i < nparts) s = mn_combine(s, partial[i]);
-  }
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  MaxNext s = (i < N) ? mn_atom(R, R0, i) : mn_identity();
   s = block_ordered_reduce(s);
-  if (threadIdx.x == 0)
-    result[0] = __dadd_rn(__dadd_rn(s.m, __dmul_rn(2.0, __dsqrt_rn(__dmul_rn(s.m, s.n)))), s.n);
+  check_finish(s, partial, ticket, result);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -161,8 +227,8 @@ struct GridDesc {
   int Mx;   // extended cells per dimension = M + 4
 };
 
-// enumerate the images of an atom in real cell coordinate c (one dimension): s in {0} U {+1 if c<=1}
-// U {-1 if c>=M-2}; at most two because M >= 5.
+// images of an atom whose real cell coordinate is c (one dimension): s in {0} U {+1 if c<=1} U
+// {-1 if c>=M-2}; at most two because M >= 5.
 __device__ __forceinline__ int image_shifts(int c, int M, int s[2]) {
   s[0] = 0;
   if (c <= 1) {
@@ -227,54 +293,76 @@ __global__ void __launch_bounds__(TPB) k_fill(int N, GridDesc g, const int* __re
 
 // Deterministic order inside a cell: ascending atom index (rank by counting), then materialise the
 // per-entry arrays the list build and the force kernel read.
-__global__ void __launch_bounds__(TPB) k_place(int Next, const int* __restrict__ slotAtom,
-                                               const int* __restrict__ slotImg, const int* __restrict__ slotCell,
-                                               const int* __restrict__ cellStart, const int* __restrict__ atomFloor,
-                                               const double* __restrict__ Rs, const int* __restrict__ atomType,
-                                               const int* __restrict__ atomBody, int4* __restrict__ sMeta,
-                                               int* __restrict__ sCell, unsigned char* __restrict__ sGhost,
-                                               int* __restrict__ sType, int* __restrict__ sBody,
-                                               double* __restrict__ sRs, int* __restrict__ nbrCount) {
+struct PlaceArgs {
+  int Next;
+  const int* slotAtom;
+  const int* slotImg;
+  const int* slotCell;
+  const int* cellStart;
+  const int* atomFloor;
+  const double* Rs;
+  const int* atomType;
+  const int* atomBody;
+  int4* sMeta;            // {atom, sx, sy, sz}: position = R/L + (sx,sy,sz)
+  int* sCell;
+  unsigned char* sGhost;
+  int* sType;
+  int* sBody;
+  double4* sRs;           // unwrapped scaled coordinates of the underlying atom (exact membership test)
+  float4* sPosF;          // ghost-shifted scaled position rounded to FP32 (pre-test only)
+  int* nbrCount;
+};
+
+__global__ void __launch_bounds__(TPB) k_place(PlaceArgs a) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Next) return;
-  int cell = slotCell[t];
-  int a = slotAtom[t];
-  int lo = cellStart[cell], hi = cellStart[cell + 1];
+  if (t >= a.Next) return;
+  int cell = a.slotCell[t];
+  int at = a.slotAtom[t];
+  int lo = a.cellStart[cell], hi = a.cellStart[cell + 1];
   int rank = 0;
-  for (int u = lo; u < hi; ++u) rank += (slotAtom[u] < a);
+  for (int u = lo; u < hi; ++u) rank += (a.slotAtom[u] < at);
   int e = lo + rank;
-  int img = slotImg[t];
-  int sx = (img & 3) - 1, sy = ((img >> 2) & 3) - 1, sz = ((img >> 4) & 3) - 1;
-  sMeta[e] = make_int4(a, sx - atomFloor[3 * (size_t)a], sy - atomFloor[3 * (size_t)a + 1],
-                       sz - atomFloor[3 * (size_t)a + 2]);
-  sCell[e] = cell;
-  sGhost[e] = (img != (1 | (1 << 2) | (1 << 4)));
-  sType[e] = atomType[a];
-  sBody[e] = atomBody[a];
-  sRs[3 * (size_t)e] = Rs[3 * (size_t)a];
-  sRs[3 * (size_t)e + 1] = Rs[3 * (size_t)a + 1];
-  sRs[3 * (size_t)e + 2] = Rs[3 * (size_t)a + 2];
-  nbrCount[e] = 0;
+  int img = a.slotImg[t];
+  int sx = (img & 3) - 1 - a.atomFloor[3 * (size_t)at];
+  int sy = ((img >> 2) & 3) - 1 - a.atomFloor[3 * (size_t)at + 1];
+  int sz = ((img >> 4) & 3) - 1 - a.atomFloor[3 * (size_t)at + 2];
+  a.sMeta[e] = make_int4(at, sx, sy, sz);
+  a.sCell[e] = cell;
+  a.sGhost[e] = (img != (1 | (1 << 2) | (1 << 4)));
+  a.sType[e] = a.atomType[at];
+  a.sBody[e] = a.atomBody[at];
+  double x = a.Rs[3 * (size_t)at], y = a.Rs[3 * (size_t)at + 1], z = a.Rs[3 * (size_t)at + 2];
+  a.sRs[e] = make_double4(x, y, z, 0.0);
+  a.sPosF[e] = make_float4((float)(x + (double)sx), (float)(y + (double)sy), (float)(z + (double)sz), 0.0f);
+  a.nbrCount[e] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4: Verlet list build. One thread per real entry; candidates = the 5x5x5 block of extended cells
-// around the entry's cell (25 contiguous x-runs). Membership test is the reference's, bit for bit:
+// around the entry's cell, walked as 25 contiguous x-runs that are first clipped against the cutoff
+// sphere (a run, or its ends, that cannot hold a neighbor is skipped). Membership is the reference's,
+// bit for bit:
 //   d = Rs_i - Rs_j (unwrapped scaled), d -= anint(d), r2 = (dx^2 + dy^2) + dz^2, r2 < xRc^2/L^2
-// with every operation individually rounded (no FMA contraction). rint replaces anint: they differ
-// only at |d| = k + 1/2 exactly, where (d - round(d))^2 is the same number.
+// with every operation individually rounded (no FMA contraction; rint replaces anint: they differ only
+// at |d| = k + 1/2 exactly, where (d - round(d))^2 is the same number). An FP32 pre-test on the
+// ghost-shifted positions decides candidates whose FP32 r^2 lies outside [xRc2 - band, xRc2 + band];
+// `band` bounds the FP32 error rigorously (host: build_band), so only the thin shell is re-tested in FP64
+// and the accepted set is exactly the reference's.
 // ------------------------------------------------------------------------------------------------
 struct BuildArgs {
   int Next, cap, nt;
   GridDesc g;
-  double xRc2s;   // xRcSq * invL2
+  double xRc2s;          // xRcSq * invL2
+  double xRcs;           // sqrt of it, padded (run clipping only; conservative)
+  float r2_accept, r2_reject;   // FP32 pre-test thresholds: < accept => in, > reject => out
   const int* cellStart;
   const int4* sMeta;
   const int* sCell;
   const unsigned char* sGhost;
   const int* sType;
   const int* sBody;
-  const double* sRs;
+  const double4* sRs;
+  const float4* sPosF;
   const int* exFirst;   // CSR over atoms (0-based rows), items = 0-based atom ids ascending
   const int* exItem;
   const unsigned char* interact;   // nt*nt
@@ -290,41 +378,66 @@ __device__ __forceinline__ double strict_pbc_sq(double a, double b) {
   return __dmul_rn(d, d);
 }
 
-__global__ void __launch_bounds__(TPB) k_build_list(BuildArgs a) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ BuildArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
   const int lane = threadIdx.x & 31;
   if (e < a.Next && !a.sGhost[e]) {
-    const size_t base = ((size_t)(e >> 5) * a.cap) * TILE + lane;
+    int* out = a.nbr + ((size_t)(e >> 5) * a.cap) * TILE + lane;
     const int atom_i = a.sMeta[e].x;
     const int type_i = a.sType[e], body_i = a.sBody[e];
-    const double xi = a.sRs[3 * (size_t)e], yi = a.sRs[3 * (size_t)e + 1], zi = a.sRs[3 * (size_t)e + 2];
+    const double4 ri = a.sRs[e];
+    const float4 pf = a.sPosF[e];
     const int x0 = a.exFirst[atom_i], x1 = a.exFirst[atom_i + 1];
     const int cell = a.sCell[e];
     const int Mx = a.g.Mx;
     const int ez = cell / (Mx * Mx), ey = (cell - ez * Mx * Mx) / Mx, ex = cell - Mx * (ey + Mx * ez);
-    for (int dz = -2; dz <= 2; ++dz)
+    // geometry for run clipping, in scaled units: extended cell c spans [(c-2)/M, (c-1)/M)
+    const float w = 1.0f / (float)a.g.M;
+    const float slack = 1.0e-5f * w + 4.0e-7f;   // covers FP32 rounding of the clip arithmetic and positions
+    const float rc = (float)a.xRcs + slack;
+    const float rc2 = rc * rc;
+    for (int dz = -2; dz <= 2; ++dz) {
+      const float zlo = (float)(ez + dz - 2) * w, zhi = zlo + w;
+      const float gz = fmaxf(0.0f, fmaxf(zlo - pf.z, pf.z - zhi) - slack);
       for (int dy = -2; dy <= 2; ++dy) {
+        const float ylo = (float)(ey + dy - 2) * w, yhi = ylo + w;
+        const float gy = fmaxf(0.0f, fmaxf(ylo - pf.y, pf.y - yhi) - slack);
+        const float rem = rc2 - gz * gz - gy * gy;
+        if (rem <= 0.0f) continue;
+        const float hx = sqrtf(rem) + slack;
+        int cl = (int)floorf((pf.x - hx) * (float)a.g.M) + 2;   // `slack` (inside hx) exceeds the FP32 rounding here
+        int ch = (int)floorf((pf.x + hx) * (float)a.g.M) + 2;
+        cl = max(cl, ex - 2);
+        ch = min(ch, ex + 2);
         const int row = Mx * ((ey + dy) + Mx * (ez + dz));
-        const int f0 = a.cellStart[row + ex - 2], f1 = a.cellStart[row + ex + 3];
+        const int f0 = a.cellStart[row + cl], f1 = a.cellStart[row + ch + 1];
         for (int f = f0; f < f1; ++f) {
-          double r2 = __dadd_rn(__dadd_rn(strict_pbc_sq(xi, a.sRs[3 * (size_t)f]),
-                                          strict_pbc_sq(yi, a.sRs[3 * (size_t)f + 1])),
-                                strict_pbc_sq(zi, a.sRs[3 * (size_t)f + 2]));
-          if (r2 < a.xRc2s && f != e) {
+          const float4 qf = __ldg(&a.sPosF[f]);
+          const float dxf = pf.x - qf.x, dyf = pf.y - qf.y, dzf = pf.z - qf.z;
+          const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
+          if (r2f > a.r2_reject) continue;
+          if (f == e) continue;
+          if (r2f >= a.r2_accept) {   // inside the FP32 uncertainty band: decide exactly
+            const double4 rj = a.sRs[f];
+            const double r2 = __dadd_rn(__dadd_rn(strict_pbc_sq(ri.x, rj.x), strict_pbc_sq(ri.y, rj.y)),
+                                        strict_pbc_sq(ri.z, rj.z));
+            if (!(r2 < a.xRc2s)) continue;
+          }
+          bool ok = (a.sBody[f] != body_i) && a.interact[type_i * a.nt + a.sType[f]];
+          if (ok && x0 < x1) {
             const int atom_j = a.sMeta[f].x;
-            bool ok = (a.sBody[f] != body_i) && a.interact[type_i * a.nt + a.sType[f]];
             for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
-            if (ok) {
-              if (cnt < a.cap) a.nbr[base + (size_t)cnt * TILE] = f;
-              ++cnt;
-            }
+          }
+          if (ok) {
+            if (cnt < a.cap) out[(size_t)cnt * TILE] = f;
+            ++cnt;
           }
         }
       }
+    }
     a.nbrCount[e] = min(cnt, a.cap);
   }
-  // warp max of counts -> one atomicMax per warp
   int mx = cnt;
   for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
   if (lane == 0 && mx > 0) {
@@ -364,30 +477,32 @@ struct ForceArgs {
   const int4* sMeta;
   const unsigned char* sGhost;
   const int* sType;
-  const double* delta;     // (3,N) body-frame offsets for the rigid-body virial, or nullptr
+  const double* delta;     // (3,N) offsets from the body centre of mass (rigid-body virial), or nullptr
   const PairEntry* tab;    // nt*nt (device)
   PairEntry single;        // the only entry when nt == 1
   nb::DevModel coul;
   int q4_quirk;            // virial-only + coul_none: Wij keeps the pair value (reference make_virial_compute.sh:24-29)
   double* F;               // (3,N) output, original atom order
   double* partial;         // gridDim.x * 5
+  unsigned int* ticket;
+  double* out;             // 5 scalars: Epair, Ecoul, Wpair, Wcoul, Wbody
 };
 
+// reciprocal to full double precision from the 20-bit hardware seed: cubic (two-term) refinement,
+// relative error ~ e0^3 < 2^-57
 __device__ __forceinline__ double fast_rcp(double a) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
   double e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  return x;
+  double t = fma(e, e, e);
+  return fma(x, t, x);
 }
 
+// one 32-byte gather = one 256-bit load = one sector (LDG.E.256 on sm_100a)
 __device__ __forceinline__ double4 ld_pos(const double4* p) {
-  // 2 x 16-byte read-only loads (one 32-byte sector)
-  const double2* q = reinterpret_cast<const double2*>(p);
-  double2 a = __ldg(q), b = __ldg(q + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
 }
 
 template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE>
@@ -403,67 +518,106 @@ __global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ For
     __syncthreads();
     tab = st;
   }
+  // plain single-type Lennard-Jones: sums are accumulated unscaled and the constants applied once
+  constexpr bool LJ_FAST = SINGLE && PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   double Ep = 0.0, Ec = 0.0, Wp = 0.0, Wc = 0.0, Wb = 0.0;
-  const int cnt = (e < a.Next) ? a.nbrCount[e] : 0;   // ghosts hold 0
   const bool has_coul = (CK == nb::K_DYNAMIC) ? true : (CK != nb::K_COUL_NONE);
   if (e < a.Next) {
+    const int cnt = a.nbrCount[e];   // ghosts hold 0
     const double4 pi = a.pos[e];
     const int itype = SINGLE ? 0 : a.sType[e];
-    const bool icharged = fabs(pi.w) > 2.220446049250313e-16;
+    const bool icharged = fabs(pi.w) > DEPS;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const int* nb_ptr = a.nbr + ((size_t)(e >> 5) * a.cap) * TILE + lane;
-#pragma unroll 2
-    for (int k = 0; k < cnt; ++k) {
-      const int f = nb_ptr[(size_t)k * TILE];
-      const double4 pj = ld_pos(a.pos + f);
+    const double c1 = a.single.model.c * a.invL2;   // LJ_FAST: sr2 = sigsq * invL2 / r2
+
+    auto interact = [&](const double4& pj, int f) {
       const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
       const double r2 = dx * dx + dy * dy + dz * dz;
       if (r2 < a.Rc2s) {
-        double invR, invR2;
-        if (NEED_INVR) {
-          invR = rsqrt(r2) * a.invL;
-          invR2 = invR * invR;
+        if (LJ_FAST) {
+          const double rinv = fast_rcp(r2);
+          const double sr2 = c1 * rinv;
+          const double sr6 = sr2 * sr2 * sr2;
+          const double sr12 = sr6 * sr6;
+          if (COMPUTE) Ep += sr12 - sr6;
+          const double w = fma(2.0, sr12, -sr6);
+          Wp += w;
+          const double s = w * rinv;
+          fx = fma(s, dx, fx);
+          fy = fma(s, dy, fy);
+          fz = fma(s, dz, fz);
         } else {
-          invR2 = fast_rcp(r2) * a.invL2;
-          invR = 0.0;
-        }
-        const PairEntry& pe = SINGLE ? a.single : tab[itype * a.nt + a.sType[f]];
-        double E, W;
-        nb::eval_kind<PK>(pe.model, invR, invR2, E, W);
-        nb::eval_modifier<PM>(pe.model, invR, invR2, E, W);
-        if (COMPUTE) Ep += E;
-        Wp += W;
-        double Wsum = W;
-        if (has_coul) {
-          if (icharged && fabs(pj.w) > 2.220446049250313e-16 && pe.coulomb) {
-            double Eq, Wq;
-            if (!COMPUTE && a.q4_quirk) {
-              Eq = 0.0;
-              Wq = W;
-            } else {
-              nb::eval_kind<CK>(a.coul, invR, invR2, Eq, Wq);
-              nb::eval_modifier<CM>(a.coul, invR, invR2, Eq, Wq);
-            }
-            const double QiQj = pe.kCoul * pi.w * pj.w;
-            if (COMPUTE) Ec += QiQj * Eq;
-            Wq = QiQj * Wq;
-            Wc += Wq;
-            Wsum += Wq;
+          double invR, invR2;
+          if (NEED_INVR) {
+            invR = rsqrt(r2) * a.invL;
+            invR2 = invR * invR;
+          } else {
+            invR2 = fast_rcp(r2) * a.invL2;
+            invR = 0.0;
           }
+          const PairEntry& pe = SINGLE ? a.single : tab[itype * a.nt + a.sType[f]];
+          double E, W;
+          nb::eval_kind<PK>(pe.model, invR, invR2, E, W);
+          nb::eval_modifier<PM>(pe.model, invR, invR2, E, W);
+          if (COMPUTE) Ep += E;
+          Wp += W;
+          double Wsum = W;
+          if (has_coul) {
+            if (icharged && fabs(pj.w) > DEPS && pe.coulomb) {
+              double Eq, Wq;
+              if (!COMPUTE && a.q4_quirk) {
+                Eq = 0.0;
+                Wq = W;
+              } else {
+                nb::eval_kind<CK>(a.coul, invR, invR2, Eq, Wq);
+                nb::eval_modifier<CM>(a.coul, invR, invR2, Eq, Wq);
+              }
+              const double QiQj = pe.kCoul * pi.w * pj.w;
+              if (COMPUTE) Ec += QiQj * Eq;
+              Wq = QiQj * Wq;
+              Wc += Wq;
+              Wsum += Wq;
+            }
+          }
+          const double s = Wsum * invR2;
+          fx = fma(s, dx, fx);
+          fy = fma(s, dy, fy);
+          fz = fma(s, dz, fz);
         }
-        const double s = Wsum * invR2;
-        fx += s * dx;
-        fy += s * dy;
-        fz += s * dz;
       }
+    };
+
+    int k = 0;
+    for (; k + 2 <= cnt; k += 2) {   // two gathers in flight before either is consumed
+      const int f0 = nb_ptr[(size_t)k * TILE];
+      const int f1 = nb_ptr[(size_t)(k + 1) * TILE];
+      const double4 p0 = ld_pos(a.pos + f0);
+      const double4 p1 = ld_pos(a.pos + f1);
+      interact(p0, f0);
+      interact(p1, f1);
     }
+    if (k < cnt) {
+      const int f0 = nb_ptr[(size_t)k * TILE];
+      interact(ld_pos(a.pos + f0), f0);
+    }
+
     if (!a.sGhost[e]) {   // ghost images hold no list (count 0) and own no force slot
       const int atom = a.sMeta[e].x;
-      fx *= a.L;
-      fy *= a.L;
-      fz *= a.L;
+      if (LJ_FAST) {
+        const double fs = a.single.model.b * a.invL2 * a.L;   // eps24 * invL2 * L
+        fx *= fs;
+        fy *= fs;
+        fz *= fs;
+        Ep *= a.single.model.a;   // eps4
+        Wp *= a.single.model.b;   // eps24
+      } else {
+        fx *= a.L;
+        fy *= a.L;
+        fz *= a.L;
+      }
       a.F[3 * (size_t)atom] = fx;
       a.F[3 * (size_t)atom + 1] = fy;
       a.F[3 * (size_t)atom + 2] = fz;
@@ -480,29 +634,13 @@ __global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ For
     if (lane == 0) red[threadIdx.x >> 5][q] = x;
   }
   __syncthreads();
-  if (threadIdx.x < 5) {
-    double s = 0.0;
-    for (int w = 0; w < TPB / 32; ++w) s += red[w][threadIdx.x];
-    a.partial[(size_t)blockIdx.x * 5 + threadIdx.x] = s;
+  double mine[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+      for (int w = 0; w < TPB / 32; ++w) mine[q] += red[w][q];
   }
-}
-
-// final fixed-order reduction of per-block partials; pair sums are halved (full list counts i-j and j-i)
-__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ partial, int nparts, int width,
-                                                         double half_mask_scale, double* __restrict__ out) {
-  __shared__ double sm[256];
-  for (int q = 0; q < width; ++q) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[(size_t)i * width + q];
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-      if (threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[q] = sm[0] * ((q < 4) ? half_mask_scale : 1.0);
-    __syncthreads();
-  }
+  grid_finish<5>(mine, a.partial, a.ticket, a.out, 0.5);   // pair sums halved: the full list holds i-j and j-i
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -510,7 +648,8 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, double* __restrict__ P,
                                                const double* __restrict__ F, const double* __restrict__ invMass,
-                                               int want_ke, double* __restrict__ partial) {
+                                               int want_ke, double* __restrict__ partial,
+                                               unsigned int* __restrict__ ticket, double* __restrict__ out) {
   __shared__ double red[TPB / 32][3];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double k[3] = {0.0, 0.0, 0.0};
@@ -532,21 +671,31 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
     if (lane == 0) red[threadIdx.x >> 5][x] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 3) {
-    double s = 0.0;
-    for (int w = 0; w < TPB / 32; ++w) s += red[w][threadIdx.x];
-    partial[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+  double mine[3] = {0.0, 0.0, 0.0};
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+      for (int w = 0; w < TPB / 32; ++w) mine[x] += red[w][x];
   }
+  grid_finish<3>(mine, partial, ticket, out, 1.0);
 }
 
+// R = CR*R + CP*P/m, fused with the rebuild criterion on the NEW coordinates (|R - R0|^2 ordered scan)
 __global__ void __launch_bounds__(TPB) k_displace(int N, double CR, double CP, double* __restrict__ R,
-                                                  const double* __restrict__ P, const double* __restrict__ invMass) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  double im = invMass[i];
+                                                  const double* __restrict__ P, const double* __restrict__ invMass,
+                                                  const double* __restrict__ R0, MaxNext* __restrict__ partial,
+                                                  unsigned int* __restrict__ ticket, double* __restrict__ result) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  MaxNext s = mn_identity();
+  if (i < N) {
+    double im = invMass[i];
 #pragma unroll
-  for (int x = 0; x < 3; ++x)
-    R[3 * (size_t)i + x] = __dadd_rn(__dmul_rn(CR, R[3 * (size_t)i + x]), __dmul_rn(__dmul_rn(CP, P[3 * (size_t)i + x]), im));
+    for (int x = 0; x < 3; ++x)
+      R[3 * i + x] = __dadd_rn(__dmul_rn(CR, R[3 * i + x]), __dmul_rn(__dmul_rn(CP, P[3 * i + x]), im));
+    s = mn_atom(R, R0, i);
+  }
+  s = block_ordered_reduce(s);
+  check_finish(s, partial, ticket, result);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,6 +743,18 @@ __global__ void __launch_bounds__(TPB) k_count_interacting(int Next, int cap, do
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
 }
 
+// ---- FP64 issue-rate microbenchmark (roofline denominator that MEASURED_PEAKS.json does not carry) ----
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;   // keep the chain alive
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -615,8 +776,9 @@ struct Engine::Impl {
   // rebuild artifacts
   GridDesc grid{0, 0};
   int Next = 0, cap = 0;
-  double Lbuild = 0;
-  DBuf<double> Rs, sRs;
+  DBuf<double> Rs;
+  DBuf<double4> sRs;
+  DBuf<float4> sPosF;
   DBuf<int> atomCell, atomFloor, cellCount, cellStart, cellFill, slotAtom, slotImg, slotCell;
   DBuf<int4> sMeta;
   DBuf<int> sCell, sType, sBody, nbr, nbrCount, flags;
@@ -629,9 +791,11 @@ struct Engine::Impl {
   // reductions
   DBuf<MaxNext> chkPartial;
   DBuf<double> partial, scalars;
+  DBuf<unsigned int> tickets;      // [0] force kernel, [1] boost, [2] displacement check
   DBuf<unsigned long long> counter;
-  double* h_scalars = nullptr;   // pinned
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double* h_scalars = nullptr;     // pinned: [0..4] force scalars, [8] rebuild criterion, [10..12] kinetic
+  bool check_cached = false;       // h_scalars[8] (after check_event) holds the criterion for the current R
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, check_event = nullptr;
 };
 
 Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, const int* atomType1,
@@ -686,9 +850,14 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.flags.ensure(4);
   s.scalars.ensure(16);
   s.counter.ensure(2);
+  s.tickets.ensure(4);
+  CUDA_CHECK(cudaMemset(s.tickets.p, 0, 4 * sizeof(unsigned int)));
+  s.chkPartial.ensure(nblocks(natoms));
+  s.partial.ensure((size_t)nblocks(natoms) * 5);
   CUDA_CHECK(cudaMallocHost(&s.h_scalars, 16 * sizeof(double)));
   CUDA_CHECK(cudaEventCreate(&s.ev0));
   CUDA_CHECK(cudaEventCreate(&s.ev1));
+  CUDA_CHECK(cudaEventCreateWithFlags(&s.check_event, cudaEventDisableTiming));
   stats_.device = s.device;
 }
 
@@ -699,14 +868,15 @@ Engine::~Engine() {
   s.delta.release(); s.type.release(); s.body.release(); s.exFirst.release(); s.exItem.release();
   s.interact.release();
   for (auto& t : s.tabs) t.release();
-  s.Rs.release(); s.sRs.release(); s.atomCell.release(); s.atomFloor.release(); s.cellCount.release();
-  s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release(); s.slotCell.release();
-  s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
+  s.Rs.release(); s.sRs.release(); s.sPosF.release(); s.atomCell.release(); s.atomFloor.release();
+  s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
+  s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
-  s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release();
+  s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release(); s.tickets.release();
   if (s.h_scalars) cudaFreeHost(s.h_scalars);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
+  if (s.check_event) cudaEventDestroy(s.check_event);
   delete d_;
 }
 
@@ -724,7 +894,6 @@ void Engine::set_exclusions(const std::vector<int>& first, const std::vector<int
   CUDA_CHECK(cudaMemcpy(s.exFirst.p, f0.data(), (s.N + 1) * sizeof(int), cudaMemcpyHostToDevice));
   s.exItem.ensure(it.size() + 1);
   if (!it.empty()) CUDA_CHECK(cudaMemcpy(s.exItem.p, it.data(), it.size() * sizeof(int), cudaMemcpyHostToDevice));
-  s.list_valid = false;
 }
 
 void Engine::set_charges(const double* q) {
@@ -732,7 +901,7 @@ void Engine::set_charges(const double* q) {
   CUDA_CHECK(cudaMemcpy(s.q.p, q, s.N * sizeof(double), cudaMemcpyHostToDevice));
   s.any_charged = false;
   for (int i = 0; i < s.N; ++i)
-    if (std::fabs(q[i]) > 2.220446049250313e-16) { s.any_charged = true; break; }
+    if (std::fabs(q[i]) > DEPS) { s.any_charged = true; break; }
 }
 
 void Engine::set_interact(const std::vector<char>& interact) {
@@ -751,6 +920,7 @@ void Engine::upload_coordinates(const double* R) {
   CUDA_CHECK(cudaMemcpyAsync(s.R.p, R, 3 * (size_t)s.N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
   s.has_R = true;
+  s.check_cached = false;
 }
 void Engine::upload_body_delta(const double* delta) {
   Impl& s = *d_;
@@ -784,6 +954,23 @@ void launch_force(const ForceArgs& a, bool compute, int grid, size_t smem, cudaS
   else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false><<<grid, TPB, smem, st>>>(a);
 }
 
+// FP32 pre-test band (see k_build_list). Positions are ghost-shifted scaled coordinates, |p| <= pmax.
+// Rounding p to FP32 moves each coordinate by <= 2^-24*pmax; the FP32 difference adds <= 2^-24*|d|.
+// So every component of the FP32 separation is within delta of the true one, and
+//   |r2_f - r2| <= 2*sqrt(3)*r*delta + 3*delta^2 + (FP32 rounding of 3 products and 2 sums) ~ 6*2^-24*r2.
+// Evaluated at r = sqrt(xRc2s) (+ band) and doubled. The reference's own r2 differs from the
+// ghost-shifted one by O(1e-16), far inside the band.
+void build_band(double xRc2s, int M, float& accept, float& reject) {
+  const double u = std::ldexp(1.0, -24);
+  const double pmax = 1.0 + 2.0 / M + 1e-6;
+  const double dmax = 3.0 / M;
+  const double delta = 2.0 * u * pmax + u * dmax;
+  const double r = std::sqrt(xRc2s) * 1.01;
+  const double band = 2.0 * (2.0 * std::sqrt(3.0) * r * delta + 3.0 * delta * delta + 8.0 * u * xRc2s * 1.03);
+  accept = std::nextafterf((float)(xRc2s - band), -1.0f);
+  reject = std::nextafterf((float)(xRc2s + band), 2.0f);
+}
+
 }  // namespace
 
 bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars& out, double& neighbor_seconds) {
@@ -793,13 +980,17 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   auto t_start = std::chrono::steady_clock::now();
 
   // ---- K0: rebuild trigger (reference handle_neighbor_lists) -----------------------------------
-  const int chkBlocks = nblocks(((long long)N + CHK_ITEMS - 1) / CHK_ITEMS);
-  s.chkPartial.ensure(chkBlocks);
-  k_displacement_check<<<chkBlocks, TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p);
-  k_displacement_final<<<1, 256, 0, s.stream>>>(s.chkPartial.p, chkBlocks, s.scalars.p + 8);
-  stats_.launches += 2;
-  CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  if (s.check_cached) {
+    CUDA_CHECK(cudaEventSynchronize(s.check_event));   // evaluated by k_displace when the atoms moved
+  } else {
+    k_displacement_check<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p, s.tickets.p + 2,
+                                                           s.scalars.p + 8);
+    stats_.launches += 1;
+    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
+    CUDA_CHECK(cudaEventSynchronize(s.check_event));
+    s.check_cached = true;   // stays valid until the coordinates or R0 change
+  }
   const bool rebuild = s.h_scalars[8] > s.skinSq;
 
   const double invL2 = 1.0 / (Lbox * Lbox);
@@ -840,14 +1031,18 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     s.sGhost.ensure(Next, 1.1);
     s.sType.ensure(Next, 1.1);
     s.sBody.ensure(Next, 1.1);
-    s.sRs.ensure(3 * (size_t)Next, 1.1);
+    s.sRs.ensure(Next, 1.1);
+    s.sPosF.ensure(Next, 1.1);
     s.nbrCount.ensure(Next, 1.1);
     s.pos.ensure(Next, 1.1);
     k_fill<<<nblocks(N), TPB, 0, s.stream>>>(N, s.grid, s.atomCell.p, s.cellStart.p, s.cellFill.p, s.slotAtom.p,
                                              s.slotImg.p, s.slotCell.p);
-    k_place<<<nblocks(Next), TPB, 0, s.stream>>>(Next, s.slotAtom.p, s.slotImg.p, s.slotCell.p, s.cellStart.p,
-                                                 s.atomFloor.p, s.Rs.p, s.type.p, s.body.p, s.sMeta.p, s.sCell.p,
-                                                 s.sGhost.p, s.sType.p, s.sBody.p, s.sRs.p, s.nbrCount.p);
+    PlaceArgs pa;
+    pa.Next = Next; pa.slotAtom = s.slotAtom.p; pa.slotImg = s.slotImg.p; pa.slotCell = s.slotCell.p;
+    pa.cellStart = s.cellStart.p; pa.atomFloor = s.atomFloor.p; pa.Rs = s.Rs.p; pa.atomType = s.type.p;
+    pa.atomBody = s.body.p; pa.sMeta = s.sMeta.p; pa.sCell = s.sCell.p; pa.sGhost = s.sGhost.p; pa.sType = s.sType.p;
+    pa.sBody = s.sBody.p; pa.sRs = s.sRs.p; pa.sPosF = s.sPosF.p; pa.nbrCount = s.nbrCount.p;
+    k_place<<<nblocks(Next), TPB, 0, s.stream>>>(pa);
     stats_.launches += 4;
     // capacity guess from the mean density; grown on overflow
     if (s.cap == 0) {
@@ -861,9 +1056,11 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       BuildArgs b;
       b.Next = Next; b.cap = s.cap; b.nt = s.nt; b.g = s.grid;
       b.xRc2s = s.xRcSq * invL2;
+      b.xRcs = std::sqrt(b.xRc2s) * (1.0 + 1e-9);
+      build_band(b.xRc2s, M, b.r2_accept, b.r2_reject);
       b.cellStart = s.cellStart.p; b.sMeta = s.sMeta.p; b.sCell = s.sCell.p; b.sGhost = s.sGhost.p;
-      b.sType = s.sType.p; b.sBody = s.sBody.p; b.sRs = s.sRs.p; b.exFirst = s.exFirst.p; b.exItem = s.exItem.p;
-      b.interact = s.interact.p; b.nbr = s.nbr.p; b.nbrCount = s.nbrCount.p; b.flags = s.flags.p;
+      b.sType = s.sType.p; b.sBody = s.sBody.p; b.sRs = s.sRs.p; b.sPosF = s.sPosF.p; b.exFirst = s.exFirst.p;
+      b.exItem = s.exItem.p; b.interact = s.interact.p; b.nbr = s.nbr.p; b.nbrCount = s.nbrCount.p; b.flags = s.flags.p;
       if (timing_) CUDA_CHECK(cudaEventRecord(s.ev0, s.stream));
       k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
       if (timing_) CUDA_CHECK(cudaEventRecord(s.ev1, s.stream));
@@ -881,7 +1078,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       s.cap = (int)(hflags[0] * 1.15) + 8;   // overflow: regrow to the observed maximum and redo
     }
     CUDA_CHECK(cudaMemcpyAsync(s.R0.p, s.R.p, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
-    s.Lbuild = Lbox;
+    s.h_scalars[8] = 0.0;   // R0 = R: the criterion for the current coordinates is now zero displacement
     s.list_valid = true;
     stats_.cells_per_dim = M;
   }
@@ -903,12 +1100,13 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   a.Next = Next; a.cap = s.cap; a.nt = s.nt;
   a.Rc2s = (lt.useInRc ? s.InRcSq : s.RcSq) * invL2;
   a.L = Lbox; a.invL = 1.0 / Lbox; a.invL2 = invL2;
-  a.pos = s.pos.p; a.nbr = s.nbr.p; a.nbrCount = s.nbrCount.p; a.sMeta = s.sMeta.p; a.sGhost = s.sGhost.p; a.sType = s.sType.p;
+  a.pos = s.pos.p; a.nbr = s.nbr.p; a.nbrCount = s.nbrCount.p; a.sMeta = s.sMeta.p; a.sGhost = s.sGhost.p;
+  a.sType = s.sType.p;
   a.delta = (s.has_delta && s.nbodies != 0) ? s.delta.p : nullptr;
   a.tab = s.tabs[layer0].p;
   a.single = lt.pair[0];
   a.coul = lt.coul;
-  a.F = Fl; a.partial = s.partial.p;
+  a.F = Fl; a.partial = s.partial.p; a.ticket = s.tickets.p; a.out = s.scalars.p;
 
   // classify the layer for kernel selection
   bool uniform = true;
@@ -933,8 +1131,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   else
     launch_force<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, compute, grid, smem_dyn, s.stream);
   if (timing_) CUDA_CHECK(cudaEventRecord(s.ev1, s.stream));
-  k_reduce_partials<<<1, 256, 0, s.stream>>>(s.partial.p, grid, 5, 0.5, s.scalars.p);
-  stats_.launches += 3;
+  stats_.launches += 2;
   stats_.force_launches += 1;
   CUDA_CHECK(cudaMemcpyAsync(s.h_scalars, s.scalars.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -955,13 +1152,10 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
 void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke) {
   Impl& s = *d_;
   const int grid = nblocks(s.N);
-  s.partial.ensure((size_t)grid * 5);
   k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, s.F.p + (size_t)layer0 * 3 * s.N, s.invMass.p,
-                                      want_kinetic ? 1 : 0, s.partial.p);
+                                      want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10);
   stats_.launches += 1;
   if (want_kinetic) {
-    k_reduce_partials<<<1, 256, 0, s.stream>>>(s.partial.p, grid, 3, 1.0, s.scalars.p + 10);
-    stats_.launches += 1;
     CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.h_scalars[10 + x];
@@ -970,8 +1164,12 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
 
 void Engine::displace(double CR, double CP) {
   Impl& s = *d_;
-  k_displace<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p);
+  k_displace<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, s.R0.p, s.chkPartial.p,
+                                                 s.tickets.p + 2, s.scalars.p + 8);
   stats_.launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
+  s.check_cached = true;
 }
 
 long long Engine::pair_count() { return download_pairs(nullptr, 0); }
@@ -1009,23 +1207,6 @@ long long Engine::download_pairs(int* pairs, long long capacity) {
   return pairs == nullptr ? (long long)n : got;
 }
 
-}  // namespace emdee
-
-// ---- FP64 issue-rate microbenchmark (roofline denominator that MEASURED_PEAKS.json does not carry) ----
-namespace emdee {
-namespace {
-__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
-  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-  const double m = 1.0000001, c = 1e-9;
-  for (int i = 0; i < iters; ++i) {
-    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-  }
-  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-  if (s == 123.456) out[0] = s;   // keep the chain alive
-}
-}  // namespace
-
 double measure_fp64_fma_tflops() {
   int dev = 0, sms = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -1053,4 +1234,5 @@ double measure_fp64_fma_tflops() {
   cudaEventDestroy(e1);
   return best;
 }
+
 }  // namespace emdee

