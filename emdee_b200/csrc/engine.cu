@@ -795,6 +795,9 @@ struct Engine::Impl {
   DBuf<unsigned long long> counter;
   double* h_scalars = nullptr;     // pinned: [0..4] force scalars, [8] rebuild criterion, [10..12] kinetic
   bool check_cached = false;       // h_scalars[8] (after check_event) holds the criterion for the current R
+  // host-side phase timers (printed by the destructor when EMDEE_PROFILE is set)
+  double t_check = 0, t_rebuild = 0, t_force = 0, t_boost = 0, t_displace = 0;
+  long long n_force = 0, n_boost = 0, n_displace = 0, n_rebuild = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, check_event = nullptr;
 };
 
@@ -861,9 +864,18 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   stats_.device = s.device;
 }
 
+static inline double wall_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 Engine::~Engine() {
   Impl& s = *d_;
   cudaDeviceSynchronize();
+  if (std::getenv("EMDEE_PROFILE") != nullptr)
+    std::fprintf(stderr, "[emdee profile] host ms per call: check %.3f (n=%lld) rebuild %.3f (n=%lld) force %.3f boost %.3f (n=%lld) displace %.3f (n=%lld)\n",
+                 1e3 * s.t_check / std::max(1LL, s.n_force), s.n_force, 1e3 * s.t_rebuild / std::max(1LL, s.n_rebuild), s.n_rebuild,
+                 1e3 * s.t_force / std::max(1LL, s.n_force), 1e3 * s.t_boost / std::max(1LL, s.n_boost), s.n_boost,
+                 1e3 * s.t_displace / std::max(1LL, s.n_displace), s.n_displace);
   s.R.release(); s.P.release(); s.R0.release(); s.F.release(); s.q.release(); s.invMass.release();
   s.delta.release(); s.type.release(); s.body.release(); s.exFirst.release(); s.exItem.release();
   s.interact.release();
@@ -979,6 +991,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   const LayerTable& lt = s.layers[layer0];
   auto t_start = std::chrono::steady_clock::now();
 
+  const double tp0 = wall_now();
   // ---- K0: rebuild trigger (reference handle_neighbor_lists) -----------------------------------
   if (s.check_cached) {
     CUDA_CHECK(cudaEventSynchronize(s.check_event));   // evaluated by k_displace when the atoms moved
@@ -992,6 +1005,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     s.check_cached = true;   // stays valid until the coordinates or R0 change
   }
   const bool rebuild = s.h_scalars[8] > s.skinSq;
+  const double tp1 = wall_now();
+  s.t_check += tp1 - tp0;
 
   const double invL2 = 1.0 / (Lbox * Lbox);
   if (rebuild) {
@@ -1051,7 +1066,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     }
     const long long ntiles = ((long long)Next + TILE - 1) / TILE;
     for (;;) {
-      s.nbr.ensure((size_t)ntiles * s.cap * TILE);
+      s.nbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
       CUDA_CHECK(cudaMemsetAsync(s.flags.p, 0, 4 * sizeof(int), s.stream));
       BuildArgs b;
       b.Next = Next; b.cap = s.cap; b.nt = s.nt; b.g = s.grid;
@@ -1083,6 +1098,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     stats_.cells_per_dim = M;
   }
   neighbor_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  const double tp2 = wall_now();
+  if (rebuild) { s.t_rebuild += tp2 - tp1; s.n_rebuild += 1; }
 
   // ---- pair loop -------------------------------------------------------------------------------
   double* Fl = s.F.p + (size_t)layer0 * 3 * N;
@@ -1141,6 +1158,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
     stats_.force_ms += ms;
   }
+  s.t_force += wall_now() - tp2;
+  s.n_force += 1;
   out.Epair = s.h_scalars[0];
   out.Ecoul = s.h_scalars[1];
   out.Wpair = s.h_scalars[2];
@@ -1151,6 +1170,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
 
 void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke) {
   Impl& s = *d_;
+  const double tp0 = wall_now();
   const int grid = nblocks(s.N);
   k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, s.F.p + (size_t)layer0 * 3 * s.N, s.invMass.p,
                                       want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10);
@@ -1160,16 +1180,21 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.h_scalars[10 + x];
   }
+  s.t_boost += wall_now() - tp0;
+  s.n_boost += 1;
 }
 
 void Engine::displace(double CR, double CP) {
   Impl& s = *d_;
+  const double tp0 = wall_now();
   k_displace<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, s.R0.p, s.chkPartial.p,
                                                  s.tickets.p + 2, s.scalars.p + 8);
   stats_.launches += 1;
   CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
   s.check_cached = true;
+  s.t_displace += wall_now() - tp0;
+  s.n_displace += 1;
 }
 
 long long Engine::pair_count() { return download_pairs(nullptr, 0); }
