@@ -95,15 +95,18 @@ __device__ __forceinline__ void grid_finish(const double (&mine)[WIDTH], double*
   __syncthreads();
   if (!last) return;
   __threadfence();
-  double acc[WIDTH];
+  const bool worker = threadIdx.x < TPB;   // blocks may be larger than TPB; the fold always uses TPB threads
+  if (worker) {
+    double acc[WIDTH];
 #pragma unroll
-  for (int q = 0; q < WIDTH; ++q) acc[q] = 0.0;
-  for (unsigned int b = threadIdx.x; b < gridDim.x; b += TPB) {
+    for (int q = 0; q < WIDTH; ++q) acc[q] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += TPB) {
 #pragma unroll
-    for (int q = 0; q < WIDTH; ++q) acc[q] += __ldcg(&partial[(size_t)b * WIDTH + q]);
+      for (int q = 0; q < WIDTH; ++q) acc[q] += __ldcg(&partial[(size_t)b * WIDTH + q]);
+    }
+#pragma unroll
+    for (int q = 0; q < WIDTH; ++q) fin[threadIdx.x][q] = acc[q];
   }
-#pragma unroll
-  for (int q = 0; q < WIDTH; ++q) fin[threadIdx.x][q] = acc[q];
   __syncthreads();
   for (int off = TPB / 2; off > 0; off >>= 1) {
     if ((int)threadIdx.x < off) {
@@ -505,127 +508,102 @@ __device__ __forceinline__ double4 ld_pos(const double4* p) {
   return v;
 }
 
-template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE>
-__global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ ForceArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double red[TPB / 32][5];
-  const PairEntry* tab = a.tab;
-  if (!SINGLE && a.nt <= MAX_SMEM_TYPES) {
-    PairEntry* st = reinterpret_cast<PairEntry*>(smem_raw);
-    const int words = a.nt * a.nt * (int)(sizeof(PairEntry) / sizeof(int));
-    for (int w = threadIdx.x; w < words; w += blockDim.x)
-      reinterpret_cast<int*>(st)[w] = reinterpret_cast<const int*>(a.tab)[w];
-    __syncthreads();
-    tab = st;
-  }
-  // plain single-type Lennard-Jones: sums are accumulated unscaled and the constants applied once
-  constexpr bool LJ_FAST = SINGLE && PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  double Ep = 0.0, Ec = 0.0, Wp = 0.0, Wc = 0.0, Wb = 0.0;
-  const bool has_coul = (CK == nb::K_DYNAMIC) ? true : (CK != nb::K_COUL_NONE);
-  if (e < a.Next) {
-    const int cnt = a.nbrCount[e];   // ghosts hold 0
-    const double4 pi = a.pos[e];
-    const int itype = SINGLE ? 0 : a.sType[e];
-    const bool icharged = fabs(pi.w) > DEPS;
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    const int* nb_ptr = a.nbr + ((size_t)(e >> 5) * a.cap) * TILE + lane;
-    const double c1 = a.single.model.c * a.invL2;   // LJ_FAST: sr2 = sigsq * invL2 / r2
+struct PairAcc {
+  double fx = 0.0, fy = 0.0, fz = 0.0, Ep = 0.0, Ec = 0.0, Wp = 0.0, Wc = 0.0;
+};
 
-    auto interact = [&](const double4& pj, int f) {
-      const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      const double r2 = dx * dx + dy * dy + dz * dz;
-      if (r2 < a.Rc2s) {
-        if (LJ_FAST) {
-          const double rinv = fast_rcp(r2);
-          const double sr2 = c1 * rinv;
-          const double sr6 = sr2 * sr2 * sr2;
-          const double sr12 = sr6 * sr6;
-          if (COMPUTE) Ep += sr12 - sr6;
-          const double w = fma(2.0, sr12, -sr6);
-          Wp += w;
-          const double s = w * rinv;
-          fx = fma(s, dx, fx);
-          fy = fma(s, dy, fy);
-          fz = fma(s, dz, fz);
-        } else {
-          double invR, invR2;
-          if (NEED_INVR) {
-            invR = rsqrt(r2) * a.invL;
-            invR2 = invR * invR;
+// One neighbor of atom i (position pi, type itype): cutoff test, pair model + modifier, optional Coulomb
+// model + modifier, force accumulation (reference compute.f90:44-93). `f` is the neighbor's sorted entry,
+// only used to look its type up when the system has several types.
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE>
+__device__ __forceinline__ void pair_term(const ForceArgs& a, const PairEntry* tab, const double4& pi, int itype,
+                                          bool icharged, double c1, const double4& pj, int f, PairAcc& s) {
+  constexpr bool LJ_FAST = SINGLE && PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
+  const bool has_coul = (CK == nb::K_DYNAMIC) ? true : (CK != nb::K_COUL_NONE);
+  const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+  const double r2 = dx * dx + dy * dy + dz * dz;
+  if (r2 < a.Rc2s) {
+    if (LJ_FAST) {
+      // plain single-type Lennard-Jones: unscaled sums, constants applied once per atom (lj_fast_scale)
+      const double rinv = fast_rcp(r2);
+      const double sr2 = c1 * rinv;
+      const double sr6 = sr2 * sr2 * sr2;
+      const double sr12 = sr6 * sr6;
+      if (COMPUTE) s.Ep += sr12 - sr6;
+      const double w = fma(2.0, sr12, -sr6);
+      s.Wp += w;
+      const double t = w * rinv;
+      s.fx = fma(t, dx, s.fx);
+      s.fy = fma(t, dy, s.fy);
+      s.fz = fma(t, dz, s.fz);
+    } else {
+      double invR, invR2;
+      if (NEED_INVR) {
+        invR = rsqrt(r2) * a.invL;
+        invR2 = invR * invR;
+      } else {
+        invR2 = fast_rcp(r2) * a.invL2;
+        invR = 0.0;
+      }
+      const PairEntry& pe = SINGLE ? a.single : tab[itype * a.nt + a.sType[f]];
+      double E, W;
+      nb::eval_kind<PK>(pe.model, invR, invR2, E, W);
+      nb::eval_modifier<PM>(pe.model, invR, invR2, E, W);
+      if (COMPUTE) s.Ep += E;
+      s.Wp += W;
+      double Wsum = W;
+      if (has_coul) {
+        if (icharged && fabs(pj.w) > DEPS && pe.coulomb) {
+          double Eq, Wq;
+          if (!COMPUTE && a.q4_quirk) {
+            Eq = 0.0;
+            Wq = W;
           } else {
-            invR2 = fast_rcp(r2) * a.invL2;
-            invR = 0.0;
+            nb::eval_kind<CK>(a.coul, invR, invR2, Eq, Wq);
+            nb::eval_modifier<CM>(a.coul, invR, invR2, Eq, Wq);
           }
-          const PairEntry& pe = SINGLE ? a.single : tab[itype * a.nt + a.sType[f]];
-          double E, W;
-          nb::eval_kind<PK>(pe.model, invR, invR2, E, W);
-          nb::eval_modifier<PM>(pe.model, invR, invR2, E, W);
-          if (COMPUTE) Ep += E;
-          Wp += W;
-          double Wsum = W;
-          if (has_coul) {
-            if (icharged && fabs(pj.w) > DEPS && pe.coulomb) {
-              double Eq, Wq;
-              if (!COMPUTE && a.q4_quirk) {
-                Eq = 0.0;
-                Wq = W;
-              } else {
-                nb::eval_kind<CK>(a.coul, invR, invR2, Eq, Wq);
-                nb::eval_modifier<CM>(a.coul, invR, invR2, Eq, Wq);
-              }
-              const double QiQj = pe.kCoul * pi.w * pj.w;
-              if (COMPUTE) Ec += QiQj * Eq;
-              Wq = QiQj * Wq;
-              Wc += Wq;
-              Wsum += Wq;
-            }
-          }
-          const double s = Wsum * invR2;
-          fx = fma(s, dx, fx);
-          fy = fma(s, dy, fy);
-          fz = fma(s, dz, fz);
+          const double QiQj = pe.kCoul * pi.w * pj.w;
+          if (COMPUTE) s.Ec += QiQj * Eq;
+          Wq = QiQj * Wq;
+          s.Wc += Wq;
+          Wsum += Wq;
         }
       }
-    };
-
-    int k = 0;
-    for (; k + 2 <= cnt; k += 2) {   // two gathers in flight before either is consumed
-      const int f0 = nb_ptr[(size_t)k * TILE];
-      const int f1 = nb_ptr[(size_t)(k + 1) * TILE];
-      const double4 p0 = ld_pos(a.pos + f0);
-      const double4 p1 = ld_pos(a.pos + f1);
-      interact(p0, f0);
-      interact(p1, f1);
-    }
-    if (k < cnt) {
-      const int f0 = nb_ptr[(size_t)k * TILE];
-      interact(ld_pos(a.pos + f0), f0);
-    }
-
-    if (!a.sGhost[e]) {   // ghost images hold no list (count 0) and own no force slot
-      const int atom = a.sMeta[e].x;
-      if (LJ_FAST) {
-        const double fs = a.single.model.b * a.invL2 * a.L;   // eps24 * invL2 * L
-        fx *= fs;
-        fy *= fs;
-        fz *= fs;
-        Ep *= a.single.model.a;   // eps4
-        Wp *= a.single.model.b;   // eps24
-      } else {
-        fx *= a.L;
-        fy *= a.L;
-        fz *= a.L;
-      }
-      a.F[3 * (size_t)atom] = fx;
-      a.F[3 * (size_t)atom + 1] = fy;
-      a.F[3 * (size_t)atom + 2] = fz;
-      if (a.delta != nullptr)
-        Wb = -(fx * a.delta[3 * (size_t)atom] + fy * a.delta[3 * (size_t)atom + 1] + fz * a.delta[3 * (size_t)atom + 2]);
+      const double t = Wsum * invR2;
+      s.fx = fma(t, dx, s.fx);
+      s.fy = fma(t, dy, s.fy);
+      s.fz = fma(t, dz, s.fz);
     }
   }
-  // block reduction of the five scalars (deterministic: fixed shuffle tree + fixed warp order)
+}
+
+// final per-atom scaling (F = L * sum, reference compute.f90:99) and store; returns the body-virial term
+template <bool LJ_FAST>
+__device__ __forceinline__ double finish_atom(const ForceArgs& a, int atom, PairAcc& s) {
+  if (LJ_FAST) {
+    const double fs = a.single.model.b * a.invL2 * a.L;   // eps24 * invL2 * L
+    s.fx *= fs;
+    s.fy *= fs;
+    s.fz *= fs;
+    s.Ep *= a.single.model.a;   // eps4
+    s.Wp *= a.single.model.b;   // eps24
+  } else {
+    s.fx *= a.L;
+    s.fy *= a.L;
+    s.fz *= a.L;
+  }
+  a.F[3 * (size_t)atom] = s.fx;
+  a.F[3 * (size_t)atom + 1] = s.fy;
+  a.F[3 * (size_t)atom + 2] = s.fz;
+  if (a.delta != nullptr)
+    return -(s.fx * a.delta[3 * (size_t)atom] + s.fy * a.delta[3 * (size_t)atom + 1] + s.fz * a.delta[3 * (size_t)atom + 2]);
+  return 0.0;
+}
+
+// block reduction of the five scalars (fixed shuffle tree + fixed warp order) followed by the grid finish
+__device__ __forceinline__ void reduce_scalars(const ForceArgs& a, double Ep, double Ec, double Wp, double Wc, double Wb) {
+  __shared__ double red[32][5];
+  const int lane = threadIdx.x & 31;
   double v[5] = {Ep, Ec, Wp, Wc, Wb};
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
@@ -636,11 +614,362 @@ __global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ For
   __syncthreads();
   double mine[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int q = 0; q < 5; ++q)
-      for (int w = 0; w < TPB / 32; ++w) mine[q] += red[w][q];
+      for (int w = 0; w < nw; ++w) mine[q] += red[w][q];
   }
   grid_finish<5>(mine, a.partial, a.ticket, a.out, 0.5);   // pair sums halved: the full list holds i-j and j-i
+}
+
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE>
+__global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ ForceArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PairEntry* tab = a.tab;
+  if (!SINGLE && a.nt <= MAX_SMEM_TYPES) {
+    PairEntry* st = reinterpret_cast<PairEntry*>(smem_raw);
+    const int words = a.nt * a.nt * (int)(sizeof(PairEntry) / sizeof(int));
+    for (int w = threadIdx.x; w < words; w += blockDim.x)
+      reinterpret_cast<int*>(st)[w] = reinterpret_cast<const int*>(a.tab)[w];
+    __syncthreads();
+    tab = st;
+  }
+  constexpr bool LJ_FAST = SINGLE && PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  PairAcc s;
+  double Wb = 0.0;
+  if (e < a.Next) {
+    const int cnt = a.nbrCount[e];   // ghosts hold 0
+    const double4 pi = a.pos[e];
+    const int itype = SINGLE ? 0 : a.sType[e];
+    const bool icharged = fabs(pi.w) > DEPS;
+    const int* nb_ptr = a.nbr + ((size_t)(e >> 5) * a.cap) * TILE + lane;
+    const double c1 = a.single.model.c * a.invL2;   // LJ_FAST: sr2 = sigsq * invL2 / r2
+    int k = 0;
+    for (; k + 2 <= cnt; k += 2) {   // two gathers in flight before either is consumed
+      const int f0 = nb_ptr[(size_t)k * TILE];
+      const int f1 = nb_ptr[(size_t)(k + 1) * TILE];
+      const double4 p0 = ld_pos(a.pos + f0);
+      const double4 p1 = ld_pos(a.pos + f1);
+      pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p0, f0, s);
+      pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p1, f1, s);
+    }
+    if (k < cnt) {
+      const int f0 = nb_ptr[(size_t)k * TILE];
+      pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, ld_pos(a.pos + f0), f0, s);
+    }
+    if (!a.sGhost[e]) Wb = finish_atom<LJ_FAST>(a, a.sMeta[e].x, s);   // ghosts: no list (count 0), no force slot
+  }
+  reduce_scalars(a, s.Ep, s.Ec, s.Wp, s.Wc, Wb);
+}
+
+// ================================================================================================
+// Brick path (single-type systems whose cell occupancy fits): the real cells are tiled by bricks of
+// about b^3 cells; one CTA owns a brick, stages the positions of the brick plus its 2-cell halo in
+// shared memory with bulk asynchronous copies (cp.async.bulk -> UBLKCP, completion on an mbarrier: the
+// TMA path, one copy per contiguous x-run of cells), and gathers neighbors from shared memory through
+// 16-bit brick-local indices. Versus the global path: a divergent gather costs shared-memory bank
+// conflicts instead of one LSU wavefront per 32-byte sector, and the list is half the bytes.
+// ================================================================================================
+constexpr int BRICK_MAX_SEG = 144;    // (b+4)^2 staged x-runs, b <= 8
+constexpr int BRICK_MAX_ROWS = 64;    // b^2 owned x-runs
+constexpr int BRICK_TPB = 640;        // upper bound of the brick kernels' block size
+constexpr int BRICK_SMAX = 3328;      // staged entries per brick (x 32 B = 104 KB of shared memory)
+
+struct BrickGrid {
+  int M, Mx;
+  int nbx, nby, nbz;   // bricks per dimension; brick i covers real cells [floor(i*M/nb), floor((i+1)*M/nb))
+};
+
+struct BrickDesc {
+  int nseg, nrows, S, B;           // staged runs, owned runs, staged entries, owned (real) entries
+  int segG[BRICK_MAX_SEG];         // first global sorted entry of each staged run
+  int segL[BRICK_MAX_SEG + 1];     // prefix sum of run lengths = local index of each run's first entry
+  int rowG[BRICK_MAX_ROWS];        // first global entry of each owned run
+  int rowL[BRICK_MAX_ROWS];        // its local (staged) index
+  int rowT[BRICK_MAX_ROWS + 1];    // prefix sum of owned-run lengths = first owned-atom ordinal of the run
+};
+
+__device__ __forceinline__ void brick_range(int i, int nb, int M, int& c0, int& c1) {
+  c0 = 2 + (int)(((long long)i * M) / nb);
+  c1 = 2 + (int)(((long long)(i + 1) * M) / nb);
+}
+
+__global__ void __launch_bounds__(TPB) k_brick_setup(BrickGrid g, const int* __restrict__ cellStart,
+                                                     BrickDesc* __restrict__ desc, int* __restrict__ flags) {
+  __shared__ int len[BRICK_MAX_SEG];
+  __shared__ int rlen[BRICK_MAX_ROWS];
+  const int brick = blockIdx.x;
+  const int ix = brick % g.nbx, iy = (brick / g.nbx) % g.nby, iz = brick / (g.nbx * g.nby);
+  int x0, x1, y0, y1, z0, z1;
+  brick_range(ix, g.nbx, g.M, x0, x1);
+  brick_range(iy, g.nby, g.M, y0, y1);
+  brick_range(iz, g.nbz, g.M, z0, z1);
+  const int nys = (y1 - y0) + 4, nzs = (z1 - z0) + 4, nseg = nys * nzs;
+  const int nyr = (y1 - y0), nzr = (z1 - z0), nrows = nyr * nzr;
+  BrickDesc& d = desc[brick];
+  for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
+    const int y = y0 - 2 + (s % nys), z = z0 - 2 + (s / nys);
+    const int row = g.Mx * (y + g.Mx * z);
+    const int a = cellStart[row + x0 - 2], b = cellStart[row + x1 + 2];
+    d.segG[s] = a;
+    len[s] = b - a;
+  }
+  for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+    const int y = y0 + (r % nyr), z = z0 + (r / nyr);
+    const int row = g.Mx * (y + g.Mx * z);
+    const int a = cellStart[row + x0], b = cellStart[row + x1];
+    d.rowG[r] = a;
+    rlen[r] = b - a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int s = 0; s < nseg; ++s) {
+      d.segL[s] = acc;
+      acc += len[s];
+    }
+    d.segL[nseg] = acc;
+    d.S = acc;
+    d.nseg = nseg;
+    int t = 0;
+    for (int r = 0; r < nrows; ++r) {
+      d.rowT[r] = t;
+      t += rlen[r];
+      // local index of the owned run = local start of its staged run + offset of x0 inside that run
+      const int sy = (r % nyr) + 2, sz = (r / nyr) + 2, sidx = sy + nys * sz;
+      d.rowL[r] = d.segL[sidx] + (d.rowG[r] - d.segG[sidx]);
+    }
+    d.rowT[nrows] = t;
+    d.B = t;
+    d.nrows = nrows;
+    atomicMax(&flags[2], acc);
+    atomicMax(&flags[3], t);
+  }
+}
+
+// ---- mbarrier + bulk-copy helpers -------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned int phase) {
+  unsigned int ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+// stage `elem_bytes`-sized records of all runs of a brick into shared memory (one bulk copy per run)
+__device__ __forceinline__ void brick_stage(const BrickDesc& d, const int* sSegG, const int* sSegL, const void* src,
+                                            void* dst, int elem_bytes, unsigned long long* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned int)d.S * (unsigned int)elem_bytes);
+  for (int s = threadIdx.x; s < d.nseg; s += blockDim.x) {
+    const int n = sSegL[s + 1] - sSegL[s];
+    if (n > 0)
+      bulk_g2s(reinterpret_cast<char*>(dst) + (size_t)sSegL[s] * elem_bytes,
+               reinterpret_cast<const char*>(src) + (size_t)sSegG[s] * elem_bytes, (unsigned int)n * elem_bytes, bar);
+  }
+  while (!mbar_try_wait(bar, 0u)) {
+  }
+}
+
+// owned-atom ordinal b -> (global sorted entry, local staged index)
+__device__ __forceinline__ void brick_locate(const int* sRowT, const int* sRowG, const int* sRowL, int nrows, int b,
+                                             int& e, int& li) {
+  int lo = 0, hi = nrows - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (sRowT[mid] <= b) lo = mid;
+    else hi = mid - 1;
+  }
+  const int off = b - sRowT[lo];
+  e = sRowG[lo] + off;
+  li = sRowL[lo] + off;
+}
+
+struct BrickArgs {
+  BrickGrid g;
+  const BrickDesc* desc;
+  unsigned short* nbr16;   // [brick][slot][Bmax]
+  int cap, Bmax;
+};
+
+// ---- list build, brick version ----------------------------------------------------------------------
+__global__ void __launch_bounds__(BRICK_TPB) k_build_list_brick(const __grid_constant__ BuildArgs a,
+                                                                const __grid_constant__ BrickArgs k) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int sSegG[BRICK_MAX_SEG], sSegL[BRICK_MAX_SEG + 1];
+  __shared__ int sRowG[BRICK_MAX_ROWS], sRowL[BRICK_MAX_ROWS], sRowT[BRICK_MAX_ROWS + 1];
+  __shared__ __align__(8) unsigned long long bar;
+  float4* sPos = reinterpret_cast<float4*>(smem_raw);
+  const int brick = blockIdx.x;
+  const BrickDesc& d = k.desc[brick];
+  const int nseg = d.nseg, nrows = d.nrows, B = d.B;
+  for (int s = threadIdx.x; s <= nseg; s += blockDim.x) {
+    sSegL[s] = d.segL[s];
+    if (s < nseg) sSegG[s] = d.segG[s];
+  }
+  for (int r = threadIdx.x; r <= nrows; r += blockDim.x) {
+    sRowT[r] = d.rowT[r];
+    if (r < nrows) {
+      sRowG[r] = d.rowG[r];
+      sRowL[r] = d.rowL[r];
+    }
+  }
+  __syncthreads();
+  brick_stage(d, sSegG, sSegL, a.sPosF, sPos, (int)sizeof(float4), &bar);
+
+  const int ix = brick % k.g.nbx, iy = (brick / k.g.nbx) % k.g.nby, iz = brick / (k.g.nbx * k.g.nby);
+  int bx0, bx1, by0, by1, bz0, bz1;
+  brick_range(ix, k.g.nbx, k.g.M, bx0, bx1);
+  brick_range(iy, k.g.nby, k.g.M, by0, by1);
+  brick_range(iz, k.g.nbz, k.g.M, bz0, bz1);
+  const int nys = (by1 - by0) + 4;
+  const int Mx = a.g.Mx;
+  const float w = 1.0f / (float)a.g.M;
+  const float slack = 1.0e-5f * w + 4.0e-7f;
+  const float rc = (float)a.xRcs + slack;
+  const float rc2 = rc * rc;
+  int mxcnt = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int e, li;
+    brick_locate(sRowT, sRowG, sRowL, nrows, b, e, li);
+    unsigned short* out = k.nbr16 + ((size_t)brick * k.cap) * k.Bmax + b;
+    const int atom_i = a.sMeta[e].x;
+    const int body_i = a.sBody[e];
+    const double4 ri = a.sRs[e];
+    const float4 pf = sPos[li];
+    const int x0 = a.exFirst[atom_i], x1 = a.exFirst[atom_i + 1];
+    const int cell = a.sCell[e];
+    const int ez = cell / (Mx * Mx), ey = (cell - ez * Mx * Mx) / Mx, ex = cell - Mx * (ey + Mx * ez);
+    int cnt = 0;
+    for (int dz = -2; dz <= 2; ++dz) {
+      const float zlo = (float)(ez + dz - 2) * w, zhi = zlo + w;
+      const float gz = fmaxf(0.0f, fmaxf(zlo - pf.z, pf.z - zhi) - slack);
+      for (int dy = -2; dy <= 2; ++dy) {
+        const float ylo = (float)(ey + dy - 2) * w, yhi = ylo + w;
+        const float gy = fmaxf(0.0f, fmaxf(ylo - pf.y, pf.y - yhi) - slack);
+        const float rem = rc2 - gz * gz - gy * gy;
+        if (rem <= 0.0f) continue;
+        const float hx = sqrtf(rem) + slack;
+        int cl = (int)floorf((pf.x - hx) * (float)a.g.M) + 2;
+        int ch = (int)floorf((pf.x + hx) * (float)a.g.M) + 2;
+        cl = max(cl, ex - 2);
+        ch = min(ch, ex + 2);
+        const int row = Mx * ((ey + dy) + Mx * (ez + dz));
+        const int f0 = a.cellStart[row + cl], f1 = a.cellStart[row + ch + 1];
+        const int sidx = (ey + dy - (by0 - 2)) + nys * (ez + dz - (bz0 - 2));
+        const int toLocal = sSegL[sidx] - sSegG[sidx];
+        for (int f = f0; f < f1; ++f) {
+          const float4 qf = sPos[f + toLocal];
+          const float dxf = pf.x - qf.x, dyf = pf.y - qf.y, dzf = pf.z - qf.z;
+          const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
+          if (r2f > a.r2_reject) continue;
+          if (f == e) continue;
+          if (r2f >= a.r2_accept) {
+            const double4 rj = a.sRs[f];
+            const double r2 = __dadd_rn(__dadd_rn(strict_pbc_sq(ri.x, rj.x), strict_pbc_sq(ri.y, rj.y)),
+                                        strict_pbc_sq(ri.z, rj.z));
+            if (!(r2 < a.xRc2s)) continue;
+          }
+          bool ok = (a.sBody[f] != body_i) && a.interact[0];
+          if (ok && x0 < x1) {
+            const int atom_j = a.sMeta[f].x;
+            for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
+          }
+          if (ok) {
+            if (cnt < k.cap) out[(size_t)cnt * k.Bmax] = (unsigned short)(f + toLocal);
+            ++cnt;
+          }
+        }
+      }
+    }
+    a.nbrCount[e] = min(cnt, k.cap);
+    mxcnt = max(mxcnt, cnt);
+  }
+  for (int off = 16; off > 0; off >>= 1) mxcnt = max(mxcnt, __shfl_xor_sync(0xffffffffu, mxcnt, off));
+  if ((threadIdx.x & 31) == 0 && mxcnt > 0) {
+    atomicMax(&a.flags[0], mxcnt);
+    if (mxcnt > k.cap) a.flags[1] = 1;
+  }
+}
+
+// ---- pair forces, brick version -----------------------------------------------------------------------
+template <int PK, int PM, int CK, int CM, bool NEED_INVR, bool COMPUTE>
+__global__ void __launch_bounds__(BRICK_TPB, (PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE) ? 2 : 1)
+    k_pair_forces_brick(const __grid_constant__ ForceArgs a,
+                                                                 const __grid_constant__ BrickArgs k) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int sSegG[BRICK_MAX_SEG], sSegL[BRICK_MAX_SEG + 1];
+  __shared__ int sRowG[BRICK_MAX_ROWS], sRowL[BRICK_MAX_ROWS], sRowT[BRICK_MAX_ROWS + 1];
+  __shared__ __align__(8) unsigned long long bar;
+  double4* sPos = reinterpret_cast<double4*>(smem_raw);
+  constexpr bool LJ_FAST = PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
+  const int brick = blockIdx.x;
+  const BrickDesc& d = k.desc[brick];
+  const int nseg = d.nseg, nrows = d.nrows, B = d.B;
+  for (int s = threadIdx.x; s <= nseg; s += blockDim.x) {
+    sSegL[s] = d.segL[s];
+    if (s < nseg) sSegG[s] = d.segG[s];
+  }
+  for (int r = threadIdx.x; r <= nrows; r += blockDim.x) {
+    sRowT[r] = d.rowT[r];
+    if (r < nrows) {
+      sRowG[r] = d.rowG[r];
+      sRowL[r] = d.rowL[r];
+    }
+  }
+  __syncthreads();
+  brick_stage(d, sSegG, sSegL, a.pos, sPos, (int)sizeof(double4), &bar);
+
+  double Ep = 0.0, Ec = 0.0, Wp = 0.0, Wc = 0.0, Wb = 0.0;
+  const double c1 = a.single.model.c * a.invL2;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int e, li;
+    brick_locate(sRowT, sRowG, sRowL, nrows, b, e, li);
+    const int cnt = a.nbrCount[e];
+    const double4 pi = sPos[li];
+    const bool icharged = fabs(pi.w) > DEPS;
+    const unsigned short* nb_ptr = k.nbr16 + ((size_t)brick * k.cap) * k.Bmax + b;
+    PairAcc s;
+    int q = 0;
+    for (; q + 2 <= cnt; q += 2) {
+      const int l0 = nb_ptr[(size_t)q * k.Bmax];
+      const int l1 = nb_ptr[(size_t)(q + 1) * k.Bmax];
+      const double4 p0 = sPos[l0];
+      const double4 p1 = sPos[l1];
+      pair_term<PK, PM, CK, CM, true, NEED_INVR, COMPUTE>(a, nullptr, pi, 0, icharged, c1, p0, 0, s);
+      pair_term<PK, PM, CK, CM, true, NEED_INVR, COMPUTE>(a, nullptr, pi, 0, icharged, c1, p1, 0, s);
+    }
+    if (q < cnt) {
+      const double4 p0 = sPos[nb_ptr[(size_t)q * k.Bmax]];
+      pair_term<PK, PM, CK, CM, true, NEED_INVR, COMPUTE>(a, nullptr, pi, 0, icharged, c1, p0, 0, s);
+    }
+    Wb += finish_atom<LJ_FAST>(a, a.sMeta[e].x, s);
+    Ep += s.Ep;
+    Ec += s.Ec;
+    Wp += s.Wp;
+    Wc += s.Wc;
+  }
+  reduce_scalars(a, Ep, Ec, Wp, Wc, Wb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -743,6 +1072,58 @@ __global__ void __launch_bounds__(TPB) k_count_interacting(int Next, int cap, do
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
 }
 
+// brick-local staged index -> global sorted entry
+__device__ __forceinline__ int brick_to_global(const BrickDesc& d, int lf) {
+  int lo = 0, hi = d.nseg - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (d.segL[mid] <= lf) lo = mid;
+    else hi = mid - 1;
+  }
+  return d.segG[lo] + (lf - d.segL[lo]);
+}
+
+// mode 0: export pairs (ai < aj); mode 1: count entries with r^2 < Rc2s
+__global__ void __launch_bounds__(TPB) k_brick_list_walk(BrickArgs k, int mode, const int* __restrict__ nbrCount,
+                                                         const int4* __restrict__ sMeta, const double4* __restrict__ pos,
+                                                         double Rc2s, int* __restrict__ pairs, long long capacity,
+                                                         unsigned long long* __restrict__ counter) {
+  const int brick = blockIdx.x;
+  const BrickDesc& d = k.desc[brick];
+  unsigned long long n = 0;
+  for (int b = threadIdx.x; b < d.B; b += blockDim.x) {
+    int lo = 0, hi = d.nrows - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (d.rowT[mid] <= b) lo = mid;
+      else hi = mid - 1;
+    }
+    const int e = d.rowG[lo] + (b - d.rowT[lo]);
+    const int cnt = nbrCount[e];
+    const int ai = sMeta[e].x;
+    const double4 pi = pos[e];
+    const unsigned short* p = k.nbr16 + ((size_t)brick * k.cap) * k.Bmax + b;
+    for (int q = 0; q < cnt; ++q) {
+      const int f = brick_to_global(d, p[(size_t)q * k.Bmax]);
+      if (mode == 0) {
+        const int aj = sMeta[f].x;
+        if (ai < aj) {
+          unsigned long long slot = atomicAdd(counter, 1ull);
+          if (pairs != nullptr && (long long)slot < capacity) {
+            pairs[2 * slot] = ai;
+            pairs[2 * slot + 1] = aj;
+          }
+        }
+      } else {
+        const double4 pj = pos[f];
+        const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        if (dx * dx + dy * dy + dz * dz < Rc2s) ++n;
+      }
+    }
+  }
+  if (mode == 1 && n) atomicAdd(counter, n);
+}
+
 // ---- FP64 issue-rate microbenchmark (roofline denominator that MEASURED_PEAKS.json does not carry) ----
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -787,6 +1168,13 @@ struct Engine::Impl {
   DBuf<unsigned char> scanTmp;
   size_t scanTmpBytes = 0;
   bool list_valid = false;
+
+  // brick path (single-type systems): per-brick descriptors and the 16-bit brick-local list
+  bool use_bricks = false;
+  BrickGrid bgrid{0, 0, 0, 0, 0};
+  int nbricks = 0, Bmax = 0, brick_threads = 0;
+  DBuf<BrickDesc> bdesc;
+  DBuf<unsigned short> nbr16;
 
   // reductions
   DBuf<MaxNext> chkPartial;
@@ -884,6 +1272,7 @@ Engine::~Engine() {
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
+  s.bdesc.release(); s.nbr16.release();
   s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release(); s.tickets.release();
   if (s.h_scalars) cudaFreeHost(s.h_scalars);
   if (s.ev0) cudaEventDestroy(s.ev0);
@@ -964,6 +1353,35 @@ template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR>
 void launch_force(const ForceArgs& a, bool compute, int grid, size_t smem, cudaStream_t st) {
   if (compute) k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, true><<<grid, TPB, smem, st>>>(a);
   else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false><<<grid, TPB, smem, st>>>(a);
+}
+
+template <int PK, int PM, int CK, int CM, bool NEED_INVR>
+void launch_force_brick(const ForceArgs& a, const BrickArgs& k, bool compute, int grid, int threads, size_t smem,
+                        cudaStream_t st) {
+  if (compute) k_pair_forces_brick<PK, PM, CK, CM, NEED_INVR, true><<<grid, threads, smem, st>>>(a, k);
+  else k_pair_forces_brick<PK, PM, CK, CM, NEED_INVR, false><<<grid, threads, smem, st>>>(a, k);
+}
+
+template <class K>
+void allow_big_smem(K kernel, size_t bytes) {
+  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+void configure_brick_kernels() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  using namespace nb;
+  const size_t fb = (size_t)BRICK_SMAX * sizeof(double4), bb = (size_t)BRICK_SMAX * sizeof(float4);
+  allow_big_smem(k_build_list_brick, bb);
+  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, false, true>, fb);
+  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, false, false>, fb);
+  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true>, fb);
+  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, false>, fb);
+  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>, fb);
+  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, false>, fb);
+  allow_big_smem(k_pair_forces_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true, true>, fb);
+  allow_big_smem(k_pair_forces_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true, false>, fb);
 }
 
 // FP32 pre-test band (see k_build_list). Positions are ghost-shifted scaled coordinates, |p| <= pmax.
@@ -1064,26 +1482,65 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       double nbar = (double)N / (Lbox * Lbox * Lbox) * (4.0 / 3.0) * 3.14159265358979323846 * s.xRc * s.xRcSq;
       s.cap = std::max(16, (int)(1.35 * nbar) + 16);
     }
+    // ---- brick decomposition (single-type systems): largest brick whose staged halo fits shared memory ----
+    s.use_bricks = false;
+    if (s.nt == 1 && std::getenv("EMDEE_BRICKS") != nullptr) {   // opt-in: measured slower than the global path
+      configure_brick_kernels();
+      const double per_cell = (double)Next / (double)ncell;
+      for (int b = 6; b >= 2 && !s.use_bricks; --b) {
+        if ((b + 4.0) * (b + 4.0) * (b + 4.0) * per_cell > 1.02 * BRICK_SMAX) continue;
+        BrickGrid bg;
+        bg.M = M;
+        bg.Mx = M + 4;
+        bg.nbx = bg.nby = bg.nbz = (M + b - 1) / b;
+        const int nbricks = bg.nbx * bg.nby * bg.nbz;
+        s.bdesc.ensure(nbricks, 1.0);
+        CUDA_CHECK(cudaMemsetAsync(s.flags.p, 0, 4 * sizeof(int), s.stream));
+        k_brick_setup<<<nbricks, TPB, 0, s.stream>>>(bg, s.cellStart.p, s.bdesc.p, s.flags.p);
+        stats_.launches += 1;
+        int hf[4];
+        CUDA_CHECK(cudaMemcpyAsync(hf, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        if (hf[2] <= BRICK_SMAX && hf[2] < 65536) {
+          s.use_bricks = true;
+          s.bgrid = bg;
+          s.nbricks = nbricks;
+          s.Bmax = ((hf[3] + 31) / 32) * 32;
+          s.brick_threads = std::max(TPB, std::min(BRICK_TPB, s.Bmax));   // >= TPB: grid_finish folds with TPB threads
+        }
+      }
+    }
+    BuildArgs b;
+    b.Next = Next; b.nt = s.nt; b.g = s.grid;
+    b.xRc2s = s.xRcSq * invL2;
+    b.xRcs = std::sqrt(b.xRc2s) * (1.0 + 1e-9);
+    build_band(b.xRc2s, M, b.r2_accept, b.r2_reject);
+    b.cellStart = s.cellStart.p; b.sMeta = s.sMeta.p; b.sCell = s.sCell.p; b.sGhost = s.sGhost.p;
+    b.sType = s.sType.p; b.sBody = s.sBody.p; b.sRs = s.sRs.p; b.sPosF = s.sPosF.p; b.exFirst = s.exFirst.p;
+    b.exItem = s.exItem.p; b.interact = s.interact.p; b.nbrCount = s.nbrCount.p; b.flags = s.flags.p;
     const long long ntiles = ((long long)Next + TILE - 1) / TILE;
     for (;;) {
-      s.nbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
       CUDA_CHECK(cudaMemsetAsync(s.flags.p, 0, 4 * sizeof(int), s.stream));
-      BuildArgs b;
-      b.Next = Next; b.cap = s.cap; b.nt = s.nt; b.g = s.grid;
-      b.xRc2s = s.xRcSq * invL2;
-      b.xRcs = std::sqrt(b.xRc2s) * (1.0 + 1e-9);
-      build_band(b.xRc2s, M, b.r2_accept, b.r2_reject);
-      b.cellStart = s.cellStart.p; b.sMeta = s.sMeta.p; b.sCell = s.sCell.p; b.sGhost = s.sGhost.p;
-      b.sType = s.sType.p; b.sBody = s.sBody.p; b.sRs = s.sRs.p; b.sPosF = s.sPosF.p; b.exFirst = s.exFirst.p;
-      b.exItem = s.exItem.p; b.interact = s.interact.p; b.nbr = s.nbr.p; b.nbrCount = s.nbrCount.p; b.flags = s.flags.p;
+      b.cap = s.cap;
       if (timing_) CUDA_CHECK(cudaEventRecord(s.ev0, s.stream));
-      k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      if (s.use_bricks) {
+        s.nbr16.ensure((size_t)s.nbricks * s.cap * s.Bmax, 1.1);
+        b.nbr = nullptr;
+        BrickArgs k;
+        k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
+        k_build_list_brick<<<s.nbricks, s.brick_threads, (size_t)BRICK_SMAX * sizeof(float4), s.stream>>>(b, k);
+      } else {
+        s.nbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
+        b.nbr = s.nbr.p;
+        k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      }
       if (timing_) CUDA_CHECK(cudaEventRecord(s.ev1, s.stream));
       stats_.launches += 1;
       stats_.build_launches += 1;
       int hflags[4];
       CUDA_CHECK(cudaMemcpyAsync(hflags, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
       CUDA_CHECK(cudaStreamSynchronize(s.stream));
+      CUDA_CHECK(cudaGetLastError());
       if (timing_) {
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
@@ -1139,11 +1596,25 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
 
   if (timing_) CUDA_CHECK(cudaEventRecord(s.ev0, s.stream));
   using namespace nb;
-  if (s.nt == 1 && uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_NONE && !a.q4_quirk)
+  const bool lj_plain = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_NONE && !a.q4_quirk;
+  const bool lj_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_SHIFTED_FORCE && ck == K_COUL_NONE && !a.q4_quirk;
+  const bool lj_coul_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_SF && cm == M_NONE;
+  if (s.use_bricks) {
+    BrickArgs k;
+    k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
+    const int bgrid = s.nbricks, bt = s.brick_threads;
+    s.partial.ensure((size_t)bgrid * 5);
+    a.partial = s.partial.p;
+    const size_t sm = (size_t)BRICK_SMAX * sizeof(double4);
+    if (lj_plain) launch_force_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, false>(a, k, compute, bgrid, bt, sm, s.stream);
+    else if (lj_sf) launch_force_brick<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true>(a, k, compute, bgrid, bt, sm, s.stream);
+    else if (lj_coul_sf) launch_force_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true>(a, k, compute, bgrid, bt, sm, s.stream);
+    else launch_force_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true>(a, k, compute, bgrid, bt, sm, s.stream);
+  } else if (s.nt == 1 && lj_plain)
     launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false>(a, compute, grid, 0, s.stream);
-  else if (s.nt == 1 && uniform && pk == K_PAIR_LJ_CUT && pm == M_SHIFTED_FORCE && ck == K_COUL_NONE && !a.q4_quirk)
+  else if (s.nt == 1 && lj_sf)
     launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true>(a, compute, grid, 0, s.stream);
-  else if (s.nt == 1 && uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_SF && cm == M_NONE)
+  else if (s.nt == 1 && lj_coul_sf)
     launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>(a, compute, grid, 0, s.stream);
   else
     launch_force<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, compute, grid, smem_dyn, s.stream);
@@ -1207,7 +1678,13 @@ void Engine::update_list_stats(int layer0, double Lbox) {
   const double Rc2s = (s.layers[layer0].useInRc ? s.InRcSq : s.RcSq) * invL2;
   CUDA_CHECK(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned long long), s.stream));
   k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
-  k_count_interacting<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, Rc2s, s.pos.p, s.nbr.p, s.nbrCount.p, s.counter.p);
+  if (s.use_bricks) {
+    BrickArgs k;
+    k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
+    k_brick_list_walk<<<s.nbricks, TPB, 0, s.stream>>>(k, 1, s.nbrCount.p, s.sMeta.p, s.pos.p, Rc2s, nullptr, 0, s.counter.p);
+  } else {
+    k_count_interacting<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, Rc2s, s.pos.p, s.nbr.p, s.nbrCount.p, s.counter.p);
+  }
   unsigned long long n = 0;
   CUDA_CHECK(cudaMemcpyAsync(&n, s.counter.p, sizeof(n), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -1220,7 +1697,13 @@ long long Engine::download_pairs(int* pairs, long long capacity) {
   DBuf<int> dp;
   if (pairs != nullptr && capacity > 0) dp.ensure(2 * (size_t)capacity);
   CUDA_CHECK(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned long long), s.stream));
-  k_export_pairs<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, s.nbr.p, s.nbrCount.p, s.sMeta.p, dp.p, capacity, s.counter.p);
+  if (s.use_bricks) {
+    BrickArgs k;
+    k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
+    k_brick_list_walk<<<s.nbricks, TPB, 0, s.stream>>>(k, 0, s.nbrCount.p, s.sMeta.p, s.pos.p, 0.0, dp.p, capacity, s.counter.p);
+  } else {
+    k_export_pairs<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, s.nbr.p, s.nbrCount.p, s.sMeta.p, dp.p, capacity, s.counter.p);
+  }
   unsigned long long n = 0;
   CUDA_CHECK(cudaMemcpyAsync(&n, s.counter.p, sizeof(n), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));

@@ -347,3 +347,20 @@ def test_kernels_actually_ran():
     assert st.list_entries == 2 * s.pairs().shape[0]
     assert st.cells_per_dim == 6
     s.finalize()
+
+
+def test_brick_path_opt_in(monkeypatch):
+    """EMDEE_BRICKS=1 selects the shared-memory (cp.async.bulk staged, 16-bit local index) kernels for
+    single-type systems; same parity bars. (Kept opt-in: measured slower than the global-gather path.)"""
+    monkeypatch.setenv("EMDEE_BRICKS", "1")
+    for variant in ("lj_cut", "lj_shifted_force", "softcore_0.7"):
+        sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS[variant])[0])
+        assert_state_parity(sp, so)
+        sp.finalize(), so.finalize()
+    outs = []
+    for lib in (cm.product(), cm.oracle()):
+        s, c = cm.lj_sample_system(lib, _lj)
+        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
+        outs.append(cm.run_nve(s, c, 100))
+        s.finalize()
+    assert np.abs(outs[0] - cm.kats()["lj_cut"]).max() < KTOL
