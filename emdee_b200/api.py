@@ -126,6 +126,9 @@ ABI_EXT_PRODUCT = {
     "EmDeeX_set_kernel_timing": (None, [tEmDee, C.c_int]),
     "EmDeeX_synchronize": (None, [tEmDee]),
     "EmDeeX_measure_fp64_tflops": (C.c_double, []),
+    "EmDeeX_comm_unique_id": (None, [C.c_char_p]),
+    "EmDeeX_comm_init": (None, [tEmDee, C.c_int, C.c_int, C.c_char_p]),
+    "EmDeeX_slab_range": (None, [C.c_int, C.c_int, C.c_int, _ip, _ip]),
 }
 
 

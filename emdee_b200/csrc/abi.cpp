@@ -1055,5 +1055,13 @@ void EmDeeX_stats(tEmDee md, tEmDeeXStats* out) {
 void EmDeeX_set_kernel_timing(tEmDee md, int enabled) { sys(md)->engine->set_kernel_timing(enabled != 0); }
 void EmDeeX_synchronize(tEmDee md) { sys(md)->engine->synchronize(); }
 double EmDeeX_measure_fp64_tflops(void) { return emdee::measure_fp64_fma_tflops(); }
+void EmDeeX_comm_unique_id(char* out128) { emdee::comm_unique_id(out128); }
+void EmDeeX_comm_init(tEmDee md, int rank, int world, const char* unique_id) {
+  System* me = sys(md);
+  if (me->initialized) error("multi-GPU setup", "EmDeeX_comm_init must be called before box and coordinates are uploaded");
+  if (rank < 0 || rank >= world) error("multi-GPU setup", "rank is out of range");
+  me->engine->comm_init(rank, world, unique_id);
+}
+void EmDeeX_slab_range(int M, int rank, int world, int* z0, int* z1) { emdee::slab_range(M, rank, world, *z0, *z1); }
 
 }  // extern "C"

@@ -22,6 +22,10 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <chrono>
@@ -226,12 +230,15 @@ __global__ void __launch_bounds__(TPB) k_displacement_check(const double* __rest
 // K1-K3: binning into the extended grid (real cells [2, M+2) per dimension + 2-cell ghost shell).
 // ------------------------------------------------------------------------------------------------
 struct GridDesc {
-  int M;    // real cells per dimension (reference: max(floor(2L/xRc), 5))
-  int Mx;   // extended cells per dimension = M + 4
+  int M;     // real cells per dimension of the WHOLE box (reference: max(floor(2L/xRc), 5))
+  int Mx;    // extended cells per dimension in x and y = M + 4
+  int z0;    // first global cell layer owned by this rank (0 on a single GPU)
+  int nzl;   // number of owned layers (M on a single GPU)
+  int Mz;    // extended layers in z = nzl + 4 (two halo layers each side: periodic images or neighbor ranks' atoms)
 };
 
-// images of an atom whose real cell coordinate is c (one dimension): s in {0} U {+1 if c<=1} U
-// {-1 if c>=M-2}; at most two because M >= 5.
+// images of an atom whose real cell coordinate is c (x or y): s in {0} U {+1 if c<=1} U {-1 if c>=M-2};
+// at most two because M >= 5.
 __device__ __forceinline__ int image_shifts(int c, int M, int s[2]) {
   s[0] = 0;
   if (c <= 1) {
@@ -245,9 +252,25 @@ __device__ __forceinline__ int image_shifts(int c, int M, int s[2]) {
   return 1;
 }
 
+// z direction, slab aware: the atom in global layer cz appears at local layer cz - z0 + 2 + s*M for every
+// s in {-1,0,1} that lands inside [0, Mz). On a single GPU (z0 = 0, Mz = M + 4) this is image_shifts().
+__device__ __forceinline__ int image_shifts_z(int cz, const GridDesc& g, int s[3], int lz[3]) {
+  int n = 0;
+  for (int t = -1; t <= 1; ++t) {
+    const int l = cz - g.z0 + 2 + t * g.M;
+    if (l >= 0 && l < g.Mz) {
+      s[n] = t;
+      lz[n] = l;
+      ++n;
+    }
+  }
+  return n;
+}
+
 __global__ void __launch_bounds__(TPB) k_bin(const double* __restrict__ R, int N, double L, GridDesc g,
                                              double* __restrict__ Rs, int* __restrict__ atomCell,
-                                             int* __restrict__ atomFloor, int* __restrict__ cellCount) {
+                                             int* __restrict__ atomFloor, unsigned char* __restrict__ owned,
+                                             int* __restrict__ cellCount) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   int c[3];
@@ -262,13 +285,14 @@ __global__ void __launch_bounds__(TPB) k_bin(const double* __restrict__ R, int N
     atomFloor[3 * (size_t)i + x] = (int)fl;
   }
   atomCell[i] = c[0] | (c[1] << 10) | (c[2] << 20);
-  int sx[2], sy[2], sz[2];
-  int nx = image_shifts(c[0], g.M, sx), ny = image_shifts(c[1], g.M, sy), nz = image_shifts(c[2], g.M, sz);
+  owned[i] = (c[2] >= g.z0 && c[2] < g.z0 + g.nzl);
+  int sx[2], sy[2], sz[3], lz[3];
+  int nx = image_shifts(c[0], g.M, sx), ny = image_shifts(c[1], g.M, sy), nz = image_shifts_z(c[2], g, sz, lz);
   for (int a = 0; a < nz; ++a)
     for (int b = 0; b < ny; ++b)
       for (int d = 0; d < nx; ++d) {
-        int ex = c[0] + 2 + sx[d] * g.M, ey = c[1] + 2 + sy[b] * g.M, ez = c[2] + 2 + sz[a] * g.M;
-        atomicAdd(&cellCount[ex + g.Mx * (ey + g.Mx * ez)], 1);
+        int ex = c[0] + 2 + sx[d] * g.M, ey = c[1] + 2 + sy[b] * g.M;
+        atomicAdd(&cellCount[ex + g.Mx * (ey + g.Mx * lz[a])], 1);
       }
 }
 
@@ -280,13 +304,13 @@ __global__ void __launch_bounds__(TPB) k_fill(int N, GridDesc g, const int* __re
   if (i >= N) return;
   int pc = atomCell[i];
   int c[3] = {pc & 1023, (pc >> 10) & 1023, (pc >> 20) & 1023};
-  int sx[2], sy[2], sz[2];
-  int nx = image_shifts(c[0], g.M, sx), ny = image_shifts(c[1], g.M, sy), nz = image_shifts(c[2], g.M, sz);
+  int sx[2], sy[2], sz[3], lz[3];
+  int nx = image_shifts(c[0], g.M, sx), ny = image_shifts(c[1], g.M, sy), nz = image_shifts_z(c[2], g, sz, lz);
   for (int a = 0; a < nz; ++a)
     for (int b = 0; b < ny; ++b)
       for (int d = 0; d < nx; ++d) {
-        int ex = c[0] + 2 + sx[d] * g.M, ey = c[1] + 2 + sy[b] * g.M, ez = c[2] + 2 + sz[a] * g.M;
-        int cell = ex + g.Mx * (ey + g.Mx * ez);
+        int ex = c[0] + 2 + sx[d] * g.M, ey = c[1] + 2 + sy[b] * g.M;
+        int cell = ex + g.Mx * (ey + g.Mx * lz[a]);
         int slot = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
         slotAtom[slot] = i;
         slotImg[slot] = (sx[d] + 1) | ((sy[b] + 1) << 2) | ((sz[a] + 1) << 4);
@@ -306,6 +330,7 @@ struct PlaceArgs {
   const double* Rs;
   const int* atomType;
   const int* atomBody;
+  const unsigned char* owned;
   int4* sMeta;            // {atom, sx, sy, sz}: position = R/L + (sx,sy,sz)
   int* sCell;
   unsigned char* sGhost;
@@ -331,7 +356,7 @@ __global__ void __launch_bounds__(TPB) k_place(PlaceArgs a) {
   int sz = ((img >> 4) & 3) - 1 - a.atomFloor[3 * (size_t)at + 2];
   a.sMeta[e] = make_int4(at, sx, sy, sz);
   a.sCell[e] = cell;
-  a.sGhost[e] = (img != (1 | (1 << 2) | (1 << 4)));
+  a.sGhost[e] = (img != (1 | (1 << 2) | (1 << 4))) || !a.owned[at];   // real = central image of an atom this rank owns
   a.sType[e] = a.atomType[at];
   a.sBody[e] = a.atomBody[at];
   double x = a.Rs[3 * (size_t)at], y = a.Rs[3 * (size_t)at + 1], z = a.Rs[3 * (size_t)at + 2];
@@ -401,7 +426,7 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
     const float rc = (float)a.xRcs + slack;
     const float rc2 = rc * rc;
     for (int dz = -2; dz <= 2; ++dz) {
-      const float zlo = (float)(ez + dz - 2) * w, zhi = zlo + w;
+      const float zlo = (float)(ez + dz - 2 + a.g.z0) * w, zhi = zlo + w;   // local layer -> global coordinate
       const float gz = fmaxf(0.0f, fmaxf(zlo - pf.z, pf.z - zhi) - slack);
       for (int dy = -2; dy <= 2; ++dy) {
         const float ylo = (float)(ey + dy - 2) * w, yhi = ylo + w;
@@ -815,7 +840,7 @@ struct BrickArgs {
 // ---- list build, brick version ----------------------------------------------------------------------
 __global__ void __launch_bounds__(BRICK_TPB) k_build_list_brick(const __grid_constant__ BuildArgs a,
                                                                 const __grid_constant__ BrickArgs k) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sSegG[BRICK_MAX_SEG], sSegL[BRICK_MAX_SEG + 1];
   __shared__ int sRowG[BRICK_MAX_ROWS], sRowL[BRICK_MAX_ROWS], sRowT[BRICK_MAX_ROWS + 1];
   __shared__ __align__(8) unsigned long long bar;
@@ -862,7 +887,7 @@ __global__ void __launch_bounds__(BRICK_TPB) k_build_list_brick(const __grid_con
     const int ez = cell / (Mx * Mx), ey = (cell - ez * Mx * Mx) / Mx, ex = cell - Mx * (ey + Mx * ez);
     int cnt = 0;
     for (int dz = -2; dz <= 2; ++dz) {
-      const float zlo = (float)(ez + dz - 2) * w, zhi = zlo + w;
+      const float zlo = (float)(ez + dz - 2 + a.g.z0) * w, zhi = zlo + w;   // local layer -> global coordinate
       const float gz = fmaxf(0.0f, fmaxf(zlo - pf.z, pf.z - zhi) - slack);
       for (int dy = -2; dy <= 2; ++dy) {
         const float ylo = (float)(ey + dy - 2) * w, yhi = ylo + w;
@@ -917,7 +942,7 @@ template <int PK, int PM, int CK, int CM, bool NEED_INVR, bool COMPUTE>
 __global__ void __launch_bounds__(BRICK_TPB, (PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE) ? 2 : 1)
     k_pair_forces_brick(const __grid_constant__ ForceArgs a,
                                                                  const __grid_constant__ BrickArgs k) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sSegG[BRICK_MAX_SEG], sSegL[BRICK_MAX_SEG + 1];
   __shared__ int sRowG[BRICK_MAX_ROWS], sRowL[BRICK_MAX_ROWS], sRowT[BRICK_MAX_ROWS + 1];
   __shared__ __align__(8) unsigned long long bar;
@@ -977,12 +1002,13 @@ __global__ void __launch_bounds__(BRICK_TPB, (PK == nb::K_PAIR_LJ_CUT && PM == n
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, double* __restrict__ P,
                                                const double* __restrict__ F, const double* __restrict__ invMass,
-                                               int want_ke, double* __restrict__ partial,
-                                               unsigned int* __restrict__ ticket, double* __restrict__ out) {
+                                               const unsigned char* __restrict__ owned, int want_ke,
+                                               double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                               double* __restrict__ out) {
   __shared__ double red[TPB / 32][3];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double k[3] = {0.0, 0.0, 0.0};
-  if (i < N) {
+  if (i < N && (owned == nullptr || owned[i])) {   // multi-GPU: each rank integrates the atoms it owns
     double im = invMass[i];
 #pragma unroll
     for (int x = 0; x < 3; ++x) {
@@ -1009,22 +1035,144 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
   grid_finish<3>(mine, partial, ticket, out, 1.0);
 }
 
-// R = CR*R + CP*P/m, fused with the rebuild criterion on the NEW coordinates (|R - R0|^2 ordered scan)
+// R = CR*R + CP*P/m, fused with the rebuild criterion on the NEW coordinates (|R - R0|^2 ordered scan).
+// Multi-GPU: only owned atoms move here and the criterion is evaluated by the distributed kernels below
+// (partial == nullptr skips the fused scan).
 __global__ void __launch_bounds__(TPB) k_displace(int N, double CR, double CP, double* __restrict__ R,
                                                   const double* __restrict__ P, const double* __restrict__ invMass,
+                                                  const unsigned char* __restrict__ owned,
                                                   const double* __restrict__ R0, MaxNext* __restrict__ partial,
                                                   unsigned int* __restrict__ ticket, double* __restrict__ result) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   MaxNext s = mn_identity();
-  if (i < N) {
+  if (i < N && (owned == nullptr || owned[i])) {
     double im = invMass[i];
+    double r[3];
 #pragma unroll
-    for (int x = 0; x < 3; ++x)
-      R[3 * i + x] = __dadd_rn(__dmul_rn(CR, R[3 * i + x]), __dmul_rn(__dmul_rn(CP, P[3 * i + x]), im));
-    s = mn_atom(R, R0, i);
+    for (int x = 0; x < 3; ++x) {
+      r[x] = __dadd_rn(__dmul_rn(CR, R[3 * i + x]), __dmul_rn(__dmul_rn(CP, P[3 * i + x]), im));
+      R[3 * i + x] = r[x];
+    }
+    if (partial != nullptr) {
+      double dx = __dsub_rn(r[0], R0[3 * i]), dy = __dsub_rn(r[1], R0[3 * i + 1]), dz = __dsub_rn(r[2], R0[3 * i + 2]);
+      s.m = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      s.n = (i == 0) ? s.m : -1.0 / 0.0;
+    }
   }
+  if (partial == nullptr) return;
   s = block_ordered_reduce(s);
   check_finish(s, partial, ticket, result);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU pieces (one rank per GPU, z-slab decomposition; collectives are issued by the host).
+// ------------------------------------------------------------------------------------------------
+// Rebuild criterion over the atoms this rank owns. The reference's sequential scan equals
+//   maximum = max_i d_i, i* = first index attaining it, next = (i* == 0) ? maximum : max_{i < i*} d_i,
+// so it is evaluated in two phases: (1) per-rank (max, first index) -> all-gather -> global (maximum, i*);
+// (2) only when the decision is not already implied by maximum (maximum <= value <= 4*maximum):
+// per-rank max over owned i < i* -> all-reduce(max).
+struct MaxIdx {
+  double m;
+  long long i;
+};
+__device__ __forceinline__ MaxIdx mi_better(MaxIdx a, MaxIdx b) { return (b.m > a.m || (b.m == a.m && b.i < a.i)) ? b : a; }
+
+__global__ void __launch_bounds__(TPB) k_check_dist(const double* __restrict__ R, const double* __restrict__ R0,
+                                                    const unsigned char* __restrict__ owned, int N, long long below,
+                                                    MaxIdx* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                                    MaxIdx* __restrict__ result) {
+  __shared__ MaxIdx sm[TPB];
+  __shared__ bool last;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  MaxIdx v;
+  v.m = -1.0 / 0.0;
+  v.i = 0x7fffffffffffffffLL;
+  if (i < N && owned[i] && i < below) {
+    MaxNext d = mn_atom(R, R0, i);
+    v.m = d.m;
+    v.i = i;
+  }
+  sm[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = TPB / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sm[threadIdx.x] = mi_better(sm[threadIdx.x], sm[threadIdx.x + off]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sm[0];
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  MaxIdx acc;
+  acc.m = -1.0 / 0.0;
+  acc.i = 0x7fffffffffffffffLL;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += TPB) {
+    MaxIdx p;
+    p.m = __ldcg(&partial[b].m);
+    p.i = __ldcg(&partial[b].i);
+    acc = mi_better(acc, p);
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = TPB / 2; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sm[threadIdx.x] = mi_better(sm[threadIdx.x], sm[threadIdx.x + off]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    result[0] = sm[0];
+    *ticket = 0u;
+  }
+}
+
+// dst = owned ? src : 0 (three doubles per atom): the summand of the all-reduce that rebuilds a full array
+__global__ void __launch_bounds__(TPB) k_mask_owned(int N, const unsigned char* __restrict__ owned,
+                                                    const double* __restrict__ src, double* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const bool o = owned[i];
+#pragma unroll
+  for (int x = 0; x < 3; ++x) dst[3 * (size_t)i + x] = o ? src[3 * (size_t)i + x] : 0.0;
+}
+
+// halo bookkeeping: which owned atoms sit in my top / bottom two layers (to send), which foreign atoms sit
+// in the two layers above / below my slab (to receive). Lists are compacted in ascending atom order, so
+// a sender's list and the matching receiver's list are identical without exchanging indices.
+__global__ void __launch_bounds__(TPB) k_halo_flags(int N, GridDesc g, const int* __restrict__ atomCell,
+                                                    unsigned char* __restrict__ fl) {   // 4 flag arrays of N
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int cz = (atomCell[i] >> 20) & 1023;
+  const int z1 = g.z0 + g.nzl;
+  const bool own = cz >= g.z0 && cz < z1;
+  const int up0 = z1 % g.M, up1 = (z1 + 1) % g.M;
+  const int dn0 = (g.z0 - 2 + g.M) % g.M, dn1 = (g.z0 - 1 + g.M) % g.M;
+  fl[i] = own && cz >= z1 - 2;                          // send up
+  fl[(size_t)N + i] = own && cz < g.z0 + 2;             // send down
+  fl[2 * (size_t)N + i] = !own && (cz == dn0 || cz == dn1);   // receive from below
+  fl[3 * (size_t)N + i] = !own && (cz == up0 || cz == up1);   // receive from above
+}
+
+__global__ void __launch_bounds__(TPB) k_pack3(int n, const int* __restrict__ list, const double* __restrict__ X,
+                                               double* __restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int a = list[k];
+  buf[3 * (size_t)k] = X[3 * (size_t)a];
+  buf[3 * (size_t)k + 1] = X[3 * (size_t)a + 1];
+  buf[3 * (size_t)k + 2] = X[3 * (size_t)a + 2];
+}
+__global__ void __launch_bounds__(TPB) k_unpack3(int n, const int* __restrict__ list, const double* __restrict__ buf,
+                                                 double* __restrict__ X) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int a = list[k];
+  X[3 * (size_t)a] = buf[3 * (size_t)k];
+  X[3 * (size_t)a + 1] = buf[3 * (size_t)k + 1];
+  X[3 * (size_t)a + 2] = buf[3 * (size_t)k + 2];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1155,7 +1303,7 @@ struct Engine::Impl {
   std::vector<DBuf<PairEntry>> tabs;
 
   // rebuild artifacts
-  GridDesc grid{0, 0};
+  GridDesc grid{0, 0, 0, 0, 0};
   int Next = 0, cap = 0;
   DBuf<double> Rs;
   DBuf<double4> sRs;
@@ -1176,6 +1324,21 @@ struct Engine::Impl {
   DBuf<BrickDesc> bdesc;
   DBuf<unsigned short> nbr16;
 
+  // multi-GPU (one rank per GPU, z-slabs): NCCL is loaded lazily, only when EmDeeX_comm_init is called
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  DBuf<unsigned char> owned;       // per atom: this rank integrates it and computes its force
+  bool owned_valid = false;        // false until the first distributed rebuild (all ranks hold full arrays)
+  bool halo_fresh = true;          // halo positions are current (false after displace)
+  DBuf<double> scratch3;           // 3N doubles: masked copies for the all-reduce that rebuilds full arrays
+  DBuf<unsigned char> haloFlags;   // 4N
+  DBuf<int> haloList[4];           // send up, send down, receive from below, receive from above
+  int haloCount[4] = {0, 0, 0, 0};
+  DBuf<double> haloBuf[4];
+  DBuf<int> selCount;
+  DBuf<MaxIdx> miPartial, miResult;
+  MaxIdx* h_mi = nullptr;          // pinned, world entries
+
   // reductions
   DBuf<MaxNext> chkPartial;
   DBuf<double> partial, scalars;
@@ -1188,6 +1351,58 @@ struct Engine::Impl {
   long long n_force = 0, n_boost = 0, n_displace = 0, n_rebuild = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, check_event = nullptr;
 };
+
+// ---- NCCL, loaded lazily (a single-GPU client never needs libnccl) ------------------------------------
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.handle == nullptr) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (api.handle == nullptr) fatal("multi-GPU setup", "libnccl.so.2 could not be loaded");
+    auto sym = [&](const char* n) {
+      void* p = dlsym(api.handle, n);
+      if (p == nullptr) fatal("multi-GPU setup", "a required NCCL symbol is missing");
+      return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  }
+  return api;
+}
+#define NCCL_CHECK(call)                                                                              \
+  do {                                                                                                \
+    ncclResult_t r__ = (call);                                                                        \
+    if (r__ != ncclSuccess) {                                                                         \
+      std::fprintf(stderr, "Error in NCCL: %s (%s:%d).\n", nccl().GetErrorString(r__), __FILE__, __LINE__); \
+      std::exit(1);                                                                                   \
+    }                                                                                                 \
+  } while (0)
+}  // namespace
 
 Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, const int* atomType1,
                const double* mass, const double* invMass, const int* atomBody, int nbodies) {
@@ -1273,6 +1488,10 @@ Engine::~Engine() {
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
   s.bdesc.release(); s.nbr16.release();
+  s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
+  for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
+  if (s.h_mi) cudaFreeHost(s.h_mi);
+  if (s.comm) nccl().CommDestroy(s.comm);
   s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release(); s.tickets.release();
   if (s.h_scalars) cudaFreeHost(s.h_scalars);
   if (s.ev0) cudaEventDestroy(s.ev0);
@@ -1280,6 +1499,120 @@ Engine::~Engine() {
   if (s.check_event) cudaEventDestroy(s.check_event);
   delete d_;
 }
+
+void slab_range(int M, int rank, int world, int& z0, int& z1) {
+  z0 = (int)(((long long)rank * M) / world);
+  z1 = (int)(((long long)(rank + 1) * M) / world);
+}
+
+void comm_unique_id(void* out128) {
+  ncclUniqueId id;
+  NCCL_CHECK(nccl().GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+}
+
+void Engine::comm_init(int rank, int world, const void* unique_id) {
+  Impl& s = *d_;
+  if (world <= 1) return;
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, sizeof(id));
+  CUDA_CHECK(cudaSetDevice(s.device));
+  NCCL_CHECK(nccl().CommInitRank(&s.comm, world, id, rank));
+  s.rank = rank;
+  s.world = world;
+  CUDA_CHECK(cudaMallocHost(&s.h_mi, (size_t)world * sizeof(MaxIdx)));
+  s.miResult.ensure(world + 1);
+  s.miPartial.ensure(nblocks(s.N));
+  s.scratch3.ensure(3 * (size_t)s.N);
+  s.check_cached = false;
+}
+
+namespace {
+
+// X (3N doubles, valid for the atoms each rank owns) -> full array on every rank:
+// all-reduce(sum) of the owned parts (every atom is owned by exactly one rank, so the sum is exact)
+void gather_full(Engine::Impl& s, double* X) {
+  if (s.world <= 1 || !s.owned_valid) return;
+  k_mask_owned<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, s.owned.p, X, s.scratch3.p);
+  NCCL_CHECK(nccl().AllReduce(s.scratch3.p, X, 3 * (size_t)s.N, ncclDouble, ncclSum, s.comm, s.stream));
+}
+
+// per-rebuild: compact the four halo lists (ascending atom index) from the cell layers
+void build_halo_lists(Engine::Impl& s) {
+  const int N = s.N;
+  s.haloFlags.ensure(4 * (size_t)N);
+  s.selCount.ensure(4);
+  k_halo_flags<<<nblocks(N), TPB, 0, s.stream>>>(N, s.grid, s.atomCell.p, s.haloFlags.p);
+  cub::CountingInputIterator<int> ids(0);
+  size_t need = 0;
+  cub::DeviceSelect::Flagged(nullptr, need, ids, s.haloFlags.p, (int*)nullptr, s.selCount.p, N, s.stream);
+  if (need > s.scanTmpBytes) {
+    s.scanTmp.ensure(need);
+    s.scanTmpBytes = need;
+  }
+  for (int k = 0; k < 4; ++k) {
+    s.haloList[k].ensure(N / 2 + 64);   // a halo is two layers out of >= 4 per rank; grown below if ever exceeded
+    if (s.haloList[k].n < (size_t)N) s.haloList[k].ensure(N);
+    cub::DeviceSelect::Flagged(s.scanTmp.p, need, ids, s.haloFlags.p + (size_t)k * N, s.haloList[k].p, s.selCount.p + k, N,
+                               s.stream);
+  }
+  int h[4];
+  CUDA_CHECK(cudaMemcpyAsync(h, s.selCount.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  for (int k = 0; k < 4; ++k) {
+    s.haloCount[k] = h[k];
+    s.haloBuf[k].ensure(3 * (size_t)h[k] + 8, 1.2);
+  }
+}
+
+// per step: ghost positions of the two layers above and below the slab (no reverse exchange: full list)
+void halo_exchange(Engine::Impl& s) {
+  if (s.world <= 1 || !s.owned_valid || s.halo_fresh) return;
+  const int up = (s.rank + 1) % s.world, dn = (s.rank + s.world - 1) % s.world;
+  for (int k = 0; k < 2; ++k)
+    if (s.haloCount[k] > 0)
+      k_pack3<<<nblocks(s.haloCount[k]), TPB, 0, s.stream>>>(s.haloCount[k], s.haloList[k].p, s.R.p, s.haloBuf[k].p);
+  NCCL_CHECK(nccl().GroupStart());
+  NCCL_CHECK(nccl().Send(s.haloBuf[0].p, 3 * (size_t)s.haloCount[0], ncclDouble, up, s.comm, s.stream));
+  NCCL_CHECK(nccl().Send(s.haloBuf[1].p, 3 * (size_t)s.haloCount[1], ncclDouble, dn, s.comm, s.stream));
+  NCCL_CHECK(nccl().Recv(s.haloBuf[2].p, 3 * (size_t)s.haloCount[2], ncclDouble, dn, s.comm, s.stream));
+  NCCL_CHECK(nccl().Recv(s.haloBuf[3].p, 3 * (size_t)s.haloCount[3], ncclDouble, up, s.comm, s.stream));
+  NCCL_CHECK(nccl().GroupEnd());
+  for (int k = 2; k < 4; ++k)
+    if (s.haloCount[k] > 0)
+      k_unpack3<<<nblocks(s.haloCount[k]), TPB, 0, s.stream>>>(s.haloCount[k], s.haloList[k].p, s.haloBuf[k].p, s.R.p);
+  s.halo_fresh = true;
+}
+
+// distributed rebuild decision: identical on every rank (all inputs are all-gathered / all-reduced)
+bool rebuild_needed_dist(Engine::Impl& s) {
+  const int N = s.N;
+  const long long all = 0x7fffffffffffffffLL;
+  k_check_dist<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, s.owned.p, N, all, s.miPartial.p, s.tickets.p + 2,
+                                                 s.miResult.p + s.world);
+  NCCL_CHECK(nccl().AllGather(s.miResult.p + s.world, s.miResult.p, sizeof(MaxIdx), ncclChar, s.comm, s.stream));
+  CUDA_CHECK(cudaMemcpyAsync(s.h_mi, s.miResult.p, (size_t)s.world * sizeof(MaxIdx), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  MaxIdx g = s.h_mi[0];
+  for (int r = 1; r < s.world; ++r)
+    if (s.h_mi[r].m > g.m || (s.h_mi[r].m == g.m && s.h_mi[r].i < g.i)) g = s.h_mi[r];
+  if (g.m > s.skinSq) return true;            // value >= maximum
+  if (4.0 * g.m <= s.skinSq) return false;    // value <= 4*maximum
+  double next = g.m;                          // i* == 0: `next` still holds the first atom's value
+  if (g.i > 0) {
+    k_check_dist<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, s.owned.p, N, g.i, s.miPartial.p, s.tickets.p + 2,
+                                                   s.miResult.p + s.world);
+    NCCL_CHECK(nccl().AllGather(s.miResult.p + s.world, s.miResult.p, sizeof(MaxIdx), ncclChar, s.comm, s.stream));
+    CUDA_CHECK(cudaMemcpyAsync(s.h_mi, s.miResult.p, (size_t)s.world * sizeof(MaxIdx), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    next = s.h_mi[0].m;
+    for (int r = 1; r < s.world; ++r) next = std::max(next, s.h_mi[r].m);
+  }
+  const double value = g.m + 2 * std::sqrt(g.m * next) + next;   // reference neighbor_lists.f90:57
+  return value > s.skinSq;
+}
+
+}  // namespace
 
 void Engine::set_inner_cutoff(double InRc) { d_->InRcSq = InRc * InRc; }
 
@@ -1322,6 +1655,7 @@ void Engine::upload_coordinates(const double* R) {
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
   s.has_R = true;
   s.check_cached = false;
+  s.halo_fresh = true;   // every rank uploads the full array
 }
 void Engine::upload_body_delta(const double* delta) {
   Impl& s = *d_;
@@ -1336,12 +1670,16 @@ void Engine::upload_forces(int layer0, const double* F) {
   CUDA_CHECK(cudaMemcpy(d_->F.p + (size_t)layer0 * 3 * d_->N, F, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
 }
 void Engine::download_coordinates(double* R) {
+  gather_full(*d_, d_->R.p);   // multi-GPU: collective, every rank must call
+  d_->halo_fresh = true;
   CUDA_CHECK(cudaMemcpy(R, d_->R.p, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::download_momenta(double* P) {
+  gather_full(*d_, d_->P.p);
   CUDA_CHECK(cudaMemcpy(P, d_->P.p, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::download_forces(int layer0, double* F) {
+  gather_full(*d_, d_->F.p + (size_t)layer0 * 3 * d_->N);
   CUDA_CHECK(cudaMemcpy(F, d_->F.p + (size_t)layer0 * 3 * d_->N, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
@@ -1411,18 +1749,25 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
 
   const double tp0 = wall_now();
   // ---- K0: rebuild trigger (reference handle_neighbor_lists) -----------------------------------
-  if (s.check_cached) {
-    CUDA_CHECK(cudaEventSynchronize(s.check_event));   // evaluated by k_displace when the atoms moved
-  } else {
-    k_displacement_check<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p, s.tickets.p + 2,
-                                                           s.scalars.p + 8);
+  bool rebuild;
+  if (s.world > 1 && s.owned_valid) {
+    halo_exchange(s);
+    rebuild = rebuild_needed_dist(s);
     stats_.launches += 1;
-    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
-    CUDA_CHECK(cudaEventSynchronize(s.check_event));
-    s.check_cached = true;   // stays valid until the coordinates or R0 change
+  } else {
+    if (s.check_cached) {
+      CUDA_CHECK(cudaEventSynchronize(s.check_event));   // evaluated by k_displace when the atoms moved
+    } else {
+      k_displacement_check<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p, s.tickets.p + 2,
+                                                             s.scalars.p + 8);
+      stats_.launches += 1;
+      CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+      CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
+      CUDA_CHECK(cudaEventSynchronize(s.check_event));
+      s.check_cached = true;   // stays valid until the coordinates or R0 change
+    }
+    rebuild = s.h_scalars[8] > s.skinSq;
   }
-  const bool rebuild = s.h_scalars[8] > s.skinSq;
   const double tp1 = wall_now();
   s.t_check += tp1 - tp0;
 
@@ -1435,7 +1780,21 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     if (M > 1019) fatal("neighbor list handling", "more than 1019 cells per dimension are not supported");
     s.grid.M = M;
     s.grid.Mx = M + 4;
-    const long long ncell = (long long)s.grid.Mx * s.grid.Mx * s.grid.Mx;
+    s.grid.z0 = 0;
+    s.grid.nzl = M;
+    if (s.world > 1) {
+      // every rank needs the current positions (and momenta: ownership may change) of all atoms to re-bin
+      gather_full(s, s.R.p);
+      gather_full(s, s.P.p);
+      int z0, z1;
+      slab_range(M, s.rank, s.world, z0, z1);
+      if (z1 - z0 < 2) fatal("neighbor list handling", "fewer than two cell layers per GPU: use fewer GPUs for this box");
+      s.grid.z0 = z0;
+      s.grid.nzl = z1 - z0;
+    }
+    s.grid.Mz = s.grid.nzl + 4;
+    s.owned.ensure(N);
+    const long long ncell = (long long)s.grid.Mx * s.grid.Mx * s.grid.Mz;
     s.Rs.ensure(3 * (size_t)N);
     s.atomCell.ensure(N);
     s.atomFloor.ensure(3 * (size_t)N);
@@ -1444,7 +1803,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     s.cellFill.ensure(ncell + 1);
     CUDA_CHECK(cudaMemsetAsync(s.cellCount.p, 0, (ncell + 1) * sizeof(int), s.stream));
     CUDA_CHECK(cudaMemsetAsync(s.cellFill.p, 0, (ncell + 1) * sizeof(int), s.stream));
-    k_bin<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, N, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p, s.cellCount.p);
+    k_bin<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, N, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p, s.owned.p, s.cellCount.p);
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, s.cellCount.p, s.cellStart.p, (int)(ncell + 1), s.stream);
     if (need > s.scanTmpBytes) {
@@ -1473,7 +1832,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     PlaceArgs pa;
     pa.Next = Next; pa.slotAtom = s.slotAtom.p; pa.slotImg = s.slotImg.p; pa.slotCell = s.slotCell.p;
     pa.cellStart = s.cellStart.p; pa.atomFloor = s.atomFloor.p; pa.Rs = s.Rs.p; pa.atomType = s.type.p;
-    pa.atomBody = s.body.p; pa.sMeta = s.sMeta.p; pa.sCell = s.sCell.p; pa.sGhost = s.sGhost.p; pa.sType = s.sType.p;
+    pa.atomBody = s.body.p; pa.owned = s.owned.p; pa.sMeta = s.sMeta.p; pa.sCell = s.sCell.p; pa.sGhost = s.sGhost.p; pa.sType = s.sType.p;
     pa.sBody = s.sBody.p; pa.sRs = s.sRs.p; pa.sPosF = s.sPosF.p; pa.nbrCount = s.nbrCount.p;
     k_place<<<nblocks(Next), TPB, 0, s.stream>>>(pa);
     stats_.launches += 4;
@@ -1484,7 +1843,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     }
     // ---- brick decomposition (single-type systems): largest brick whose staged halo fits shared memory ----
     s.use_bricks = false;
-    if (s.nt == 1 && std::getenv("EMDEE_BRICKS") != nullptr) {   // opt-in: measured slower than the global path
+    if (s.nt == 1 && s.world == 1 && std::getenv("EMDEE_BRICKS") != nullptr) {   // opt-in: measured slower than the global path
       configure_brick_kernels();
       const double per_cell = (double)Next / (double)ncell;
       for (int b = 6; b >= 2 && !s.use_bricks; --b) {
@@ -1548,6 +1907,11 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       }
       if (!hflags[1]) break;
       s.cap = (int)(hflags[0] * 1.15) + 8;   // overflow: regrow to the observed maximum and redo
+    }
+    if (s.world > 1) {
+      build_halo_lists(s);
+      s.owned_valid = true;
+      s.halo_fresh = true;   // gather_full just made every position current
     }
     CUDA_CHECK(cudaMemcpyAsync(s.R0.p, s.R.p, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
     s.h_scalars[8] = 0.0;   // R0 = R: the criterion for the current coordinates is now zero displacement
@@ -1621,6 +1985,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   if (timing_) CUDA_CHECK(cudaEventRecord(s.ev1, s.stream));
   stats_.launches += 2;
   stats_.force_launches += 1;
+  if (s.world > 1) NCCL_CHECK(nccl().AllReduce(s.scalars.p, s.scalars.p, 5, ncclDouble, ncclSum, s.comm, s.stream));
   CUDA_CHECK(cudaMemcpyAsync(s.h_scalars, s.scalars.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
   CUDA_CHECK(cudaGetLastError());
@@ -1643,10 +2008,13 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
   Impl& s = *d_;
   const double tp0 = wall_now();
   const int grid = nblocks(s.N);
-  k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, s.F.p + (size_t)layer0 * 3 * s.N, s.invMass.p,
+  const unsigned char* owned = (s.world > 1 && s.owned_valid) ? s.owned.p : nullptr;
+  k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, s.F.p + (size_t)layer0 * 3 * s.N, s.invMass.p, owned,
                                       want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10);
   stats_.launches += 1;
   if (want_kinetic) {
+    if (owned != nullptr)
+      NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
     CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.h_scalars[10 + x];
@@ -1658,12 +2026,20 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
 void Engine::displace(double CR, double CP) {
   Impl& s = *d_;
   const double tp0 = wall_now();
-  k_displace<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, s.R0.p, s.chkPartial.p,
-                                                 s.tickets.p + 2, s.scalars.p + 8);
-  stats_.launches += 1;
-  CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-  CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
-  s.check_cached = true;
+  if (s.world > 1 && s.owned_valid) {
+    k_displace<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, s.owned.p, s.R0.p, nullptr,
+                                                   s.tickets.p + 2, s.scalars.p + 8);
+    stats_.launches += 1;
+    s.halo_fresh = false;
+    s.check_cached = false;
+  } else {
+    k_displace<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p, s.chkPartial.p,
+                                                   s.tickets.p + 2, s.scalars.p + 8);
+    stats_.launches += 1;
+    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
+    s.check_cached = true;
+  }
   s.t_displace += wall_now() - tp0;
   s.n_displace += 1;
 }

@@ -82,12 +82,21 @@ class Engine {
   void synchronize();
   EngineStats stats() const { return stats_; }
 
- private:
+  // ---- multi-GPU: one rank per GPU, z-slab decomposition (NCCL) ---------------------------------
+  void comm_init(int rank, int world, const void* nccl_unique_id);
+
   struct Impl;
+
+ private:
   Impl* d_;
   bool timing_ = false;
   EngineStats stats_;
 };
+
+// rank's cell layers [z0, z1) out of M (host helper, no device work)
+void slab_range(int M, int rank, int world, int& z0, int& z1);
+// 128-byte NCCL unique id (rank 0 creates it, the launcher broadcasts it)
+void comm_unique_id(void* out128);
 
 // DFMA microbenchmark on the current device: sustained FP64 FMA throughput in TFLOP/s.
 double measure_fp64_fma_tflops();

@@ -58,6 +58,19 @@ void EmDeeX_synchronize( tEmDee md );
 /* DFMA microbenchmark on the current device: measured FP64 FMA throughput in TFLOP/s (the FP64
    roofline denominator; MEASURED_PEAKS.json carries only HBM and bf16 figures). */
 double EmDeeX_measure_fp64_tflops( void );
+
+/* ---- product-only: multi-GPU (one process per GPU, z-slab decomposition over NCCL) -------------
+   Every rank creates the SAME system with the same calls and the same full-size arrays (SPMD). Rank 0
+   obtains a 128-byte NCCL id, the launcher broadcasts it (e.g. torch.distributed), and every rank calls
+   EmDeeX_comm_init before the first box/coordinates upload. From then on each rank integrates and
+   computes forces for the atoms in its cell layers [z0, z1) of the reference's M x M x M grid; ghost
+   positions of the two layers above/below come from the neighbor ranks every step (no reverse force
+   exchange: the list is full), energies/virial are all-reduced, EmDee_download is a collective that
+   reassembles the full array on every rank. */
+void EmDeeX_comm_unique_id( char* out128 );
+void EmDeeX_comm_init( tEmDee md, int rank, int world, const char* unique_id );
+/* cell layers [z0, z1) owned by `rank` out of M (pure host arithmetic) */
+void EmDeeX_slab_range( int M, int rank, int world, int* z0, int* z1 );
 #endif
 
 #ifdef __cplusplus

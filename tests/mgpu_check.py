@@ -1,0 +1,118 @@
+"""Run under torchrun with one rank per GPU (tests/test_multi_gpu.py launches it): the slab-decomposed CUDA path
+must give the single-process oracle's results -- pair sets bit-exact (union over ranks), forces, energies,
+virial, rebuild counts -- on a static configuration and along a short trajectory."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("EMDEE_QUIET", "1")
+
+import common as cm  # noqa: E402
+from emdee_b200 import dist as edist  # noqa: E402
+
+
+def build_lj(lib, comm, ncell=14, charged=False):
+    R, L = cm.fcc_lj_box(ncell, rho=0.8442, jitter=0.06, seed=5)
+    N = R.shape[0]
+    s = lib.system(2, 1, 2.5, 0.3, N, None, None, None)
+    if comm:
+        edist.init_comm(lib, s)
+    s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 1.0 if charged else 0.0)
+    if charged:
+        s.set_coul_model(lib.EmDee_shifted_force(lib.EmDee_coul_cut()))
+        q = np.where(np.arange(N) % 2 == 0, 0.5, -0.5)
+        s.upload("charges", q)
+    s.upload("box", np.array([L]))
+    s.upload("coordinates", R)
+    return s
+
+
+def build_spce(lib, comm):
+    def pre(lib_, s_):
+        if comm:
+            edist.init_comm(lib_, s_)
+    # spce_sample_system creates the system and sets models before any upload; hook the comm in between
+    orig = cm.api.System.set_pair_model
+    state = {"done": False}
+
+    def patched(self, *a, **k):
+        if not state["done"]:
+            pre(self.lib, self)
+            state["done"] = True
+        return orig(self, *a, **k)
+
+    cm.api.System.set_pair_model = patched
+    try:
+        s, c = cm.spce_sample_system(lib, lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0), replicas=2)
+    finally:
+        cm.api.System.set_pair_model = orig
+    return s
+
+
+def compare(tag, sp, so, rank, ftol=1e-10, stol=1e-12):
+    F = sp.download("forces")          # collective on the product side
+    pairs = edist.gather_pairs(sp.pairs())
+    if rank == 0:
+        assert np.array_equal(pairs, so.pairs()), f"{tag}: pair sets differ ({pairs.shape} vs {so.pairs().shape})"
+        err = cm.rel_force_error(F, so.download("forces"))
+        assert err <= ftol, f"{tag}: force error {err:.3e}"
+        sc = max(abs(so.md.Energy.Potential), abs(so.md.Energy.Coulomb), abs(so.md.Virial.Total))
+        for a, b, nm in [(sp.md.Energy.Potential, so.md.Energy.Potential, "U"), (sp.md.Energy.Coulomb, so.md.Energy.Coulomb, "Ucoul"),
+                         (sp.md.Virial.Total, so.md.Virial.Total, "W"), (sp.md.Virial.Body, so.md.Virial.Body, "Wbody")]:
+            assert abs(a - b) <= stol * sc, f"{tag}: {nm} {a!r} vs {b!r}"
+        print(f"[mgpu] {tag}: ok  pairs={pairs.shape[0]} force_err={err:.2e} U={sp.md.Energy.Potential:.6f}", flush=True)
+
+
+def main():
+    rank, world, local = edist.env_rank_world()
+    torch.cuda.set_device(local)
+    os.environ["EMDEE_DEVICE"] = str(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = cm.product()
+    orc = cm.oracle() if rank == 0 else None
+
+    for charged in (False, True):
+        sp = build_lj(lib, True, charged=charged)
+        so = build_lj(orc, False, charged=charged) if rank == 0 else None
+        compare(f"lj charged={charged} static", sp, so, rank)
+        sp.random_momenta(1.3, True, 777)
+        if rank == 0:
+            so.random_momenta(1.3, True, 777)
+        for step in range(40):
+            for s in ([sp, so] if rank == 0 else [sp]):
+                s.md.Options.Compute = (step % 8 == 7)
+                s.boost(1.0, 0.0, 0.0025)
+                s.displace(1.0, 0.0, 0.005)
+                s.boost(1.0, 0.0, 0.0025)
+        b = torch.tensor([sp.md.Builds], device="cuda")
+        dist.all_reduce(b, op=dist.ReduceOp.MAX)
+        assert int(b.item()) == sp.md.Builds
+        if rank == 0:
+            assert sp.md.Builds == so.md.Builds and sp.md.Builds > 2, (sp.md.Builds, so.md.Builds)
+            assert abs(sp.md.Kinetic.Total - so.md.Kinetic.Total) <= 1e-10 * abs(so.md.Kinetic.Total)
+        compare(f"lj charged={charged} after 40 steps ({sp.md.Builds} builds)", sp, so, rank, ftol=1e-8, stol=1e-10)
+        Rp = sp.download("coordinates")
+        if rank == 0:
+            assert np.abs(Rp - so.download("coordinates")).max() < 1e-10
+        sp.finalize()
+        if rank == 0:
+            so.finalize()
+
+    sp = build_spce(lib, True)
+    so = build_spce(orc, False) if rank == 0 else None
+    compare("spce 2x2x2 replicas (rigid bodies, body virial)", sp, so, rank)
+    sp.finalize()
+    dist.barrier()
+    if rank == 0:
+        print("[mgpu] ALL OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
