@@ -59,8 +59,10 @@ def make_workload(ncell, seed=86245):
     return np.ascontiguousarray(R), np.ascontiguousarray(P), L
 
 
-def build_system(lib, R, P, L, threads):
+def build_system(lib, R, P, L, threads, before_upload=None):
     s = lib.system(threads, 1, RC, SKIN, R.shape[0], None, None, None)
+    if before_upload is not None:
+        before_upload(s)          # multi-GPU: hand the system its communicator before any upload
     s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0)
     s.upload("box", np.array([L]))
     s.upload("coordinates", R)
@@ -164,10 +166,10 @@ def reference_arm(args, rank, world):
         return
     cores = os.cpu_count() or 1
     threads = int(os.environ.get("EMDEE_CPU_THREADS", cores))
-    ncell = args.ncell
+    ncell = args.ncell if world == 1 else int(round(args.ncell * world ** (1.0 / 3.0)))
     N = 4 * ncell ** 3
-    # bounded sample: the same 1M-atom box, a few steps (each costs ~0.2-1 s on a multicore host)
-    steps = max(1, min(args.steps, 20))
+    # bounded sample: the same box as the product arm at this N, a few steps (~0.2-1 s each per million atoms)
+    steps = max(1, min(args.steps, 20 if world == 1 else max(2, 20 // world)))
     warmup = max(1, min(args.warmup, 3))
     r = cpu_run(ncell, steps, warmup, threads)
     line = {
@@ -186,9 +188,9 @@ def reference_arm(args, rank, world):
 
 
 def workload_config(ncell, N, world, where):
-    return {"workload": f"synthetic LJ fluid, fcc {ncell}^3 x 4 = {N} atoms per GPU, rho*=0.8442, Rc=2.5, skin=0.3, "
+    return {"workload": f"synthetic LJ fluid, fcc {ncell}^3 x 4 = {N} atoms in one cubic box, rho*=0.8442, Rc=2.5, skin=0.3, "
                         f"pair_lj_cut(1,1), T*=1.44, dt=0.005, energy+virial every step (BASELINE.json configs[3])",
-            "atoms_per_gpu": N, "atoms_total": N * world, "rc": RC, "skin": SKIN, "dt": DT,
+            "atoms_per_gpu": N // world, "atoms_total": N, "rc": RC, "skin": SKIN, "dt": DT,
             "parallelism": where,
             "l2_policy": "inputs larger than L2: the neighbor list streamed every step (>300 MB at 1M atoms) exceeds the 126 MB L2"}
 
@@ -228,14 +230,16 @@ def main():
         torch.cuda.synchronize()
 
     lib = api.load()
+    from emdee_b200 import dist as edist
     W = max(args.warmup, 3)
     K = args.steps
-    ncell = args.ncell
-    # Multi-GPU: independent replicas of the per-GPU box, one per rank (weak scaling). The spatial slab
-    # decomposition with halo exchange is the next row (multi-GPU); no collective is invented here.
-    R, P, L = make_workload(ncell, seed=86245 + 17 * rank)
-    N = R.shape[0]
-    s = build_system(lib, R, P, L, 1)
+    # Multi-GPU (weak scaling): ONE box of about world x 1M atoms (the reference only knows cubic boxes), cut
+    # into z-slabs of cell layers, one per rank; ghost positions are exchanged every step over NCCL, energies
+    # all-reduced, rebuilds re-bin after an all-reduce of the owned coordinates.
+    ncell = args.ncell if world == 1 else int(round(args.ncell * world ** (1.0 / 3.0)))
+    R, P, L = make_workload(ncell)
+    N = R.shape[0]                      # atoms of the whole job
+    s = build_system(lib, R, P, L, 1, before_upload=(lambda sy: edist.init_comm(lib, sy)) if world > 1 else None)
     s.set_kernel_timing(True)
 
     # ---- resident arm ---------------------------------------------------------------------------
@@ -260,15 +264,16 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
-    value = N * world * K / (dev_ms_max * 1e-3)
+    value = N * K / (dev_ms_max * 1e-3)
 
     force_launches = st1.force_launches - st0.force_launches
     force_ms = (st1.force_ms - st0.force_ms) / max(force_launches, 1)
     build_launches = st1.build_launches - st0.build_launches
     build_ms = (st1.build_ms - st0.build_ms) / max(build_launches, 1)
     launches = st1.launches - st0.launches
-    C_half = st1.list_entries / 2.0 / N          # neighbor-list entries per atom (half-list count, as SURVEY 8(d))
-    P_half = st1.interacting / 2.0 / N           # entries with r < Rc per atom
+    n_local = N / world                          # atoms per rank (list statistics below are rank 0's)
+    C_half = st1.list_entries / 2.0 / n_local    # neighbor-list entries per atom (half-list count, as SURVEY 8(d))
+    P_half = st1.interacting / 2.0 / n_local     # entries with r < Rc per atom
 
     # ---- e2e arm: host buffers in the timed region -------------------------------------------------
     nframes = 24
@@ -302,15 +307,15 @@ def main():
     t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = N * world * e2eK / float(t.item())
+    e2e_value = N * e2eK / float(t.item())
 
     # ---- rooflines for the dominant kernel (pair forces) -------------------------------------------
     hbm_peak, peak_src = measured_peaks()
     bytes_per_atom = 56.0 + 4.0 * C_half                     # 24 r + 24 F + 8 offsets + 4*C list
     flops_per_atom = 15.0 * C_half + 22.0 * P_half + 6.0
-    ach_gbs = bytes_per_atom * N / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
+    ach_gbs = bytes_per_atom * n_local / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
     fp64_peak = lib.EmDeeX_measure_fp64_tflops() if rank == 0 else None
-    ach_tf = flops_per_atom * N / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
+    ach_tf = flops_per_atom * n_local / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -326,11 +331,12 @@ def main():
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(ncell, N, world, "single GPU" if world == 1 else
-                                      f"{world} independent replicas, one per GPU (no data-path collective)"),
+                                      f"z-slab decomposition over {world} GPUs (NCCL halo of ghost positions per step, "
+                                      f"all-reduced energies, no reverse force exchange)"),
             "timing": {"device_ms_total": dev_ms_max, "wall_s": wall, "list_builds_in_timed_region": int(builds),
                        "force_kernel_ms": force_ms, "build_kernel_ms": build_ms,
                        "force_kernel_share_of_step": force_ms / (dev_ms_max / K) if K else None},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 24 * N + 40,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 24 * N + 40,   # per rank (SPMD: every rank moves the full arrays)
                     "steps": e2eK, "what": "EmDee_upload(coordinates, pinned host) + EmDee_compute_forces + "
                                            "EmDee_download(forces, pinned host) per step, wall clock, max over ranks"},
             "gpu_launches": int(launches),
