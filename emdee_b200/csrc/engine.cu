@@ -699,6 +699,112 @@ __global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ For
 }
 
 // ================================================================================================
+// Duo path: one thread owns TWO consecutive sorted entries (same or adjacent cell) and walks the UNION of
+// their neighbor rows, so a neighbor that both atoms see is gathered once. The LSU data path (one
+// wavefront per distinct 32-byte sector of a divergent gather) is what binds the force kernel; the union
+// of two neighboring atoms' lists is ~1.3 lists instead of 2, i.e. ~1/3 fewer gathers for the same pair
+// arithmetic. Rows produced by k_build_list are ascending in the sorted entry index, so the union is a
+// sorted merge (k_merge_duos, once per rebuild). Union entry = neighbor index | bit30 (first atom sees it)
+// | bit31 (second atom sees it).
+// ================================================================================================
+constexpr unsigned int DUO_IDX = 0x3fffffffu, DUO_B0 = 0x40000000u, DUO_B1 = 0x80000000u;
+
+__global__ void __launch_bounds__(TPB) k_merge_duos(int Next, int cap, int cap2, const int* __restrict__ nbr,
+                                                    const int* __restrict__ nbrCount, unsigned int* __restrict__ duoNbr,
+                                                    int* __restrict__ duoCount, int* __restrict__ flags) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e0 = 2 * d, e1 = 2 * d + 1;
+  int cnt = 0;
+  if (e0 < Next) {
+    const int c0 = nbrCount[e0], c1 = (e1 < Next) ? nbrCount[e1] : 0;
+    const int* r0 = nbr + ((size_t)(e0 >> 5) * cap) * TILE + (e0 & 31);
+    const int* r1 = nbr + ((size_t)(e1 >> 5) * cap) * TILE + (e1 & 31);
+    unsigned int* out = duoNbr + ((size_t)(d >> 5) * cap2) * TILE + (d & 31);
+    int k0 = 0, k1 = 0;
+    int a = (k0 < c0) ? r0[0] : 0x7fffffff, b = (k1 < c1) ? r1[0] : 0x7fffffff;
+    while (k0 < c0 || k1 < c1) {
+      const int f = min(a, b);
+      unsigned int v = (unsigned int)f;
+      if (a == f) {
+        v |= DUO_B0;
+        ++k0;
+        a = (k0 < c0) ? r0[(size_t)k0 * TILE] : 0x7fffffff;
+      }
+      if (b == f) {
+        v |= DUO_B1;
+        ++k1;
+        b = (k1 < c1) ? r1[(size_t)k1 * TILE] : 0x7fffffff;
+      }
+      if (cnt < cap2) out[(size_t)cnt * TILE] = v;
+      ++cnt;
+    }
+    duoCount[d] = min(cnt, cap2);
+  }
+  int mx = cnt;
+  for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0 && mx > 0) {
+    atomicMax(&flags[2], mx);
+    if (mx > cap2) flags[3] = 1;
+  }
+}
+
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE>
+__global__ void __launch_bounds__(TPB) k_pair_forces_duo(const __grid_constant__ ForceArgs a, int cap2,
+                                                         const unsigned int* __restrict__ duoNbr,
+                                                         const int* __restrict__ duoCount) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PairEntry* tab = a.tab;
+  if (!SINGLE && a.nt <= MAX_SMEM_TYPES) {
+    PairEntry* st = reinterpret_cast<PairEntry*>(smem_raw);
+    const int words = a.nt * a.nt * (int)(sizeof(PairEntry) / sizeof(int));
+    for (int w = threadIdx.x; w < words; w += blockDim.x)
+      reinterpret_cast<int*>(st)[w] = reinterpret_cast<const int*>(a.tab)[w];
+    __syncthreads();
+    tab = st;
+  }
+  constexpr bool LJ_FAST = SINGLE && PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e0 = 2 * d, e1 = 2 * d + 1;
+  PairAcc s0, s1;
+  double Wb = 0.0;
+  if (e0 < a.Next) {
+    const bool has1 = e1 < a.Next;
+    const int cnt = duoCount[d];
+    const double4 p0 = a.pos[e0];
+    const double4 p1 = has1 ? a.pos[e1] : p0;
+    const int t0 = SINGLE ? 0 : a.sType[e0];
+    const int t1 = (SINGLE || !has1) ? 0 : a.sType[e1];
+    const bool q0 = fabs(p0.w) > DEPS, q1 = fabs(p1.w) > DEPS;
+    const unsigned int* row = duoNbr + ((size_t)(d >> 5) * cap2) * TILE + (d & 31);
+    const double c1 = a.single.model.c * a.invL2;
+    int k = 0;
+    for (; k + 2 <= cnt; k += 2) {   // two gathers in flight before either is consumed
+      const unsigned int va = row[(size_t)k * TILE];
+      const unsigned int vb = row[(size_t)(k + 1) * TILE];
+      const int fa = (int)(va & DUO_IDX), fb = (int)(vb & DUO_IDX);
+      const double4 pa = ld_pos(a.pos + fa);
+      const double4 pb = ld_pos(a.pos + fb);
+      if (va & DUO_B0) pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, p0, t0, q0, c1, pa, fa, s0);
+      if (va & DUO_B1) pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, p1, t1, q1, c1, pa, fa, s1);
+      if (vb & DUO_B0) pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, p0, t0, q0, c1, pb, fb, s0);
+      if (vb & DUO_B1) pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, p1, t1, q1, c1, pb, fb, s1);
+    }
+    if (k < cnt) {
+      const unsigned int va = row[(size_t)k * TILE];
+      const int fa = (int)(va & DUO_IDX);
+      const double4 pa = ld_pos(a.pos + fa);
+      if (va & DUO_B0) pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, p0, t0, q0, c1, pa, fa, s0);
+      if (va & DUO_B1) pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, p1, t1, q1, c1, pa, fa, s1);
+    }
+    if (!a.sGhost[e0]) Wb += finish_atom<LJ_FAST>(a, a.sMeta[e0].x, s0);
+    else s0 = PairAcc();
+    if (has1 && !a.sGhost[e1]) Wb += finish_atom<LJ_FAST>(a, a.sMeta[e1].x, s1);
+    else s1 = PairAcc();
+  }
+  reduce_scalars(a, s0.Ep + s1.Ep, s0.Ec + s1.Ec, s0.Wp + s1.Wp, s0.Wc + s1.Wc, Wb);
+}
+
+// ================================================================================================
 // Brick path (single-type systems whose cell occupancy fits): the real cells are tiled by bricks of
 // about b^3 cells; one CTA owns a brick, stages the positions of the brick plus its 2-cell halo in
 // shared memory with bulk asynchronous copies (cp.async.bulk -> UBLKCP, completion on an mbarrier: the
@@ -1402,6 +1508,12 @@ struct Engine::Impl {
   size_t scanTmpBytes = 0;
   bool list_valid = false;
 
+  // duo path: union rows of consecutive entry pairs
+  bool use_duos = false;
+  int cap2 = 0;
+  DBuf<unsigned int> duoNbr;
+  DBuf<int> duoCount;
+
   // brick path (single-type systems): per-brick descriptors and the 16-bit brick-local list
   bool use_bricks = false;
   BrickGrid bgrid{0, 0, 0, 0, 0};
@@ -1572,7 +1684,7 @@ Engine::~Engine() {
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
-  s.bdesc.release(); s.nbr16.release();
+  s.bdesc.release(); s.nbr16.release(); s.duoNbr.release(); s.duoCount.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
   if (s.h_mi) cudaFreeHost(s.h_mi);
@@ -1776,6 +1888,13 @@ template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR>
 void launch_force(const ForceArgs& a, bool compute, int grid, size_t smem, cudaStream_t st) {
   if (compute) k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, true><<<grid, TPB, smem, st>>>(a);
   else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false><<<grid, TPB, smem, st>>>(a);
+}
+
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR>
+void launch_force_duo(const ForceArgs& a, int cap2, const unsigned int* duoNbr, const int* duoCount, bool compute, int grid,
+                      size_t smem, cudaStream_t st) {
+  if (compute) k_pair_forces_duo<PK, PM, CK, CM, SINGLE, NEED_INVR, true><<<grid, TPB, smem, st>>>(a, cap2, duoNbr, duoCount);
+  else k_pair_forces_duo<PK, PM, CK, CM, SINGLE, NEED_INVR, false><<<grid, TPB, smem, st>>>(a, cap2, duoNbr, duoCount);
 }
 
 template <int PK, int PM, int CK, int CM, bool NEED_INVR>
@@ -1993,6 +2112,26 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       if (!hflags[1]) break;
       s.cap = (int)(hflags[0] * 1.15) + 8;   // overflow: regrow to the observed maximum and redo
     }
+    // ---- duo rows: sorted merge of the rows of entries (2d, 2d+1) ------------------------------------------
+    s.use_duos = !s.use_bricks && std::getenv("EMDEE_DUOS") != nullptr;   // opt-in: fewer LSU wavefronts but more FP64 issue + divergence; measured slower
+    if (s.use_duos) {
+      const int nduo = (Next + 1) / 2;
+      const long long dtiles = ((long long)nduo + TILE - 1) / TILE;
+      if (s.cap2 == 0) s.cap2 = (int)(1.45 * s.cap) + 8;
+      s.duoCount.ensure(nduo, 1.1);
+      for (;;) {
+        s.duoNbr.ensure((size_t)dtiles * s.cap2 * TILE, 1.1);
+        CUDA_CHECK(cudaMemsetAsync(s.flags.p, 0, 4 * sizeof(int), s.stream));
+        k_merge_duos<<<nblocks(nduo), TPB, 0, s.stream>>>(Next, s.cap, s.cap2, s.nbr.p, s.nbrCount.p, s.duoNbr.p,
+                                                          s.duoCount.p, s.flags.p);
+        stats_.launches += 1;
+        int hf[4];
+        CUDA_CHECK(cudaMemcpyAsync(hf, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        if (!hf[3]) break;
+        s.cap2 = (int)(hf[2] * 1.1) + 8;
+      }
+    }
     if (s.world > 1) {
       build_halo_lists(s);
       s.owned_valid = true;
@@ -2059,6 +2198,18 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     else if (lj_sf) launch_force_brick<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true>(a, k, compute, bgrid, bt, sm, s.stream);
     else if (lj_coul_sf) launch_force_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true>(a, k, compute, bgrid, bt, sm, s.stream);
     else launch_force_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true>(a, k, compute, bgrid, bt, sm, s.stream);
+  } else if (s.use_duos) {
+    const int dgrid = nblocks((Next + 1) / 2);
+    s.partial.ensure((size_t)dgrid * 5);
+    a.partial = s.partial.p;
+    if (s.nt == 1 && lj_plain)
+      launch_force_duo<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
+    else if (s.nt == 1 && lj_sf)
+      launch_force_duo<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
+    else if (s.nt == 1 && lj_coul_sf)
+      launch_force_duo<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
+    else
+      launch_force_duo<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, smem_dyn, s.stream);
   } else if (s.nt == 1 && lj_plain)
     launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false>(a, compute, grid, 0, s.stream);
   else if (s.nt == 1 && lj_sf)

@@ -364,3 +364,18 @@ def test_brick_path_opt_in(monkeypatch):
         outs.append(cm.run_nve(s, c, 100))
         s.finalize()
     assert np.abs(outs[0] - cm.kats()["lj_cut"]).max() < KTOL
+
+
+def test_duo_path_opt_in(monkeypatch):
+    """EMDEE_DUOS=1: one thread owns two consecutive entries and walks the sorted union of their rows (a shared
+    neighbor is gathered once). Same parity bars, every model goes through it. (Opt-in: measured slower.)"""
+    monkeypatch.setenv("EMDEE_DUOS", "1")
+    sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS["lj_cut"])[0])
+    assert_state_parity(sp, so)
+    sp.finalize(), so.finalize()
+    sp, so = both(lambda lib: cm.spce_sample_system(lib, COUL_VARIANTS["coul_damped_square_smoothed"])[0])
+    assert_state_parity(sp, so)
+    sp.finalize(), so.finalize()
+    sp, so = both(lambda lib: _two_type_system(lib, COUL_VARIANTS["coul_sf"]))
+    assert_state_parity(sp, so)
+    sp.finalize(), so.finalize()
