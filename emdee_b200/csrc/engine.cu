@@ -656,8 +656,9 @@ __device__ __forceinline__ void reduce_scalars(const ForceArgs& a, double Ep, do
   grid_finish<5>(mine, a.partial, a.ticket, a.out, 0.5);   // pair sums halved: the full list holds i-j and j-i
 }
 
-template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE>
-__global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ ForceArgs a) {
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE, int UNROLL = 2, int THREADS = TPB,
+          int MINBLOCKS = 1>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) k_pair_forces(const __grid_constant__ ForceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PairEntry* tab = a.tab;
   if (!SINGLE && a.nt <= MAX_SMEM_TYPES) {
@@ -681,15 +682,18 @@ __global__ void __launch_bounds__(TPB) k_pair_forces(const __grid_constant__ For
     const int* nb_ptr = a.nbr + ((size_t)(e >> 5) * a.cap) * TILE + lane;
     const double c1 = a.single.model.c * a.invL2;   // LJ_FAST: sr2 = sigsq * invL2 / r2
     int k = 0;
-    for (; k + 2 <= cnt; k += 2) {   // two gathers in flight before either is consumed
-      const int f0 = nb_ptr[(size_t)k * TILE];
-      const int f1 = nb_ptr[(size_t)(k + 1) * TILE];
-      const double4 p0 = ld_pos(a.pos + f0);
-      const double4 p1 = ld_pos(a.pos + f1);
-      pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p0, f0, s);
-      pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p1, f1, s);
+    for (; k + UNROLL <= cnt; k += UNROLL) {   // UNROLL gathers in flight before any is consumed
+      int f[UNROLL];
+      double4 p[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) f[u] = nb_ptr[(size_t)(k + u) * TILE];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) p[u] = ld_pos(a.pos + f[u]);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p[u], f[u], s);
     }
-    if (k < cnt) {
+    for (; k < cnt; ++k) {
       const int f0 = nb_ptr[(size_t)k * TILE];
       pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, ld_pos(a.pos + f0), f0, s);
     }
@@ -1884,10 +1888,15 @@ void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
 // ---- force-kernel dispatch ---------------------------------------------------------------------
 namespace {
 
-template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR>
-void launch_force(const ForceArgs& a, bool compute, int grid, size_t smem, cudaStream_t st) {
-  if (compute) k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, true><<<grid, TPB, smem, st>>>(a);
-  else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false><<<grid, TPB, smem, st>>>(a);
+// UNROLL gathers in flight per thread, THREADS per block, MINBLOCKS resident blocks (register cap); the plain
+// LJ instantiation runs 6 / 512 / 2 (tools/tune_force.py sweep, profiles/r1h_force_tuning.txt)
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, int UNROLL = 2, int THREADS = TPB, int MINBLOCKS = 1>
+void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem, cudaStream_t st) {
+  const int grid = nblocks(a.Next, THREADS);
+  partial.ensure((size_t)grid * 5);
+  a.partial = partial.p;
+  if (compute) k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, true, UNROLL, THREADS, MINBLOCKS><<<grid, THREADS, smem, st>>>(a);
+  else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false, UNROLL, THREADS, MINBLOCKS><<<grid, THREADS, smem, st>>>(a);
 }
 
 template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR>
@@ -2156,8 +2165,6 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   }
   const int Next = s.Next;
   k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
-  const int grid = nblocks(Next);
-  s.partial.ensure((size_t)grid * 5);
   ForceArgs a;
   a.Next = Next; a.cap = s.cap; a.nt = s.nt;
   a.Rc2s = (lt.useInRc ? s.InRcSq : s.RcSq) * invL2;
@@ -2210,14 +2217,29 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       launch_force_duo<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
     else
       launch_force_duo<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, smem_dyn, s.stream);
+  } else if (s.nt == 1 && lj_plain && compute && std::getenv("EMDEE_FORCE_TUNE") != nullptr) {
+    // tuning hook (bench experiments only): EMDEE_FORCE_TUNE="<variant>"
+    const int v = std::atoi(std::getenv("EMDEE_FORCE_TUNE"));
+#define EMDEE_TUNE_CASE(ID, UN, TH, MB) \
+    if (v == ID) launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, UN, TH, MB>(a, s.partial, true, 0, s.stream);
+    EMDEE_TUNE_CASE(0, 2, 128, 1)
+    EMDEE_TUNE_CASE(1, 4, 256, 4)
+    EMDEE_TUNE_CASE(2, 4, 256, 5)
+    EMDEE_TUNE_CASE(4, 3, 256, 5)
+    EMDEE_TUNE_CASE(5, 6, 256, 4)
+    EMDEE_TUNE_CASE(7, 4, 512, 2)
+    EMDEE_TUNE_CASE(10, 6, 512, 2)
+    EMDEE_TUNE_CASE(12, 8, 512, 2)
+    EMDEE_TUNE_CASE(13, 6, 1024, 1)
+#undef EMDEE_TUNE_CASE
   } else if (s.nt == 1 && lj_plain)
-    launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false>(a, compute, grid, 0, s.stream);
+    launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, 6, 512, 2>(a, s.partial, compute, 0, s.stream);
   else if (s.nt == 1 && lj_sf)
-    launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true>(a, compute, grid, 0, s.stream);
+    launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
   else if (s.nt == 1 && lj_coul_sf)
-    launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>(a, compute, grid, 0, s.stream);
+    launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
   else
-    launch_force<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, compute, grid, smem_dyn, s.stream);
+    launch_force<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 4, 256, 2>(a, s.partial, compute, smem_dyn, s.stream);
   if (timing_) CUDA_CHECK(cudaEventRecord(s.ev1, s.stream));
   stats_.launches += 2;
   stats_.force_launches += 1;
