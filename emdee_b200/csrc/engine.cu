@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(TPB) k_place(PlaceArgs a) {
   a.sBody[e] = a.atomBody[at];
   double x = a.Rs[3 * (size_t)at], y = a.Rs[3 * (size_t)at + 1], z = a.Rs[3 * (size_t)at + 2];
   a.sRs[e] = make_double4(x, y, z, 0.0);
-  a.sPosF[e] = make_float4((float)(x + (double)sx), (float)(y + (double)sy), (float)(z + (double)sz), 0.0f);
+  a.sPosF[e] = make_float4((float)(x + (double)sx), (float)(y + (double)sy), (float)(z + (double)sz),
+                            __int_as_float(a.atomBody[at]));   // w = body id bits: the build's body mask needs no extra gather
   a.nbrCount[e] = 0;
 }
 
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(TPB) k_place(PlaceArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct BuildArgs {
   int Next, cap, nt;
+  int all_interact;      // every type pair interacts: the per-candidate type lookup is skipped
   GridDesc g;
   double xRc2s;          // xRcSq * invL2
   double xRcs;           // sqrt of it, padded (run clipping only; conservative)
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
                                         strict_pbc_sq(ri.z, rj.z));
             if (!(r2 < a.xRc2s)) continue;
           }
-          bool ok = (a.sBody[f] != body_i) && a.interact[type_i * a.nt + a.sType[f]];
+          bool ok = (__float_as_int(qf.w) != body_i) && (a.all_interact || a.interact[type_i * a.nt + a.sType[f]]);
           if (ok && x0 < x1) {
             const int atom_j = a.sMeta[f].x;
             for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
@@ -1034,7 +1036,7 @@ __global__ void __launch_bounds__(BRICK_TPB) k_build_list_brick(const __grid_con
                                         strict_pbc_sq(ri.z, rj.z));
             if (!(r2 < a.xRc2s)) continue;
           }
-          bool ok = (a.sBody[f] != body_i) && a.interact[0];
+          bool ok = (__float_as_int(qf.w) != body_i) && a.all_interact;   // brick path: single type
           if (ok && x0 < x1) {
             const int atom_j = a.sMeta[f].x;
             for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
@@ -1494,6 +1496,7 @@ struct Engine::Impl {
   bool has_delta = false, has_R = false, any_charged = false;
   DBuf<int> exFirst, exItem;
   DBuf<unsigned char> interact;
+  bool all_interact = false;
   std::vector<LayerTable> layers;
   std::vector<DBuf<PairEntry>> tabs;
 
@@ -1840,6 +1843,8 @@ void Engine::set_charges(const double* q) {
 }
 
 void Engine::set_interact(const std::vector<char>& interact) {
+  d_->all_interact = true;
+  for (char c : interact) d_->all_interact = d_->all_interact && (c != 0);
   CUDA_CHECK(cudaMemcpy(d_->interact.p, interact.data(), interact.size(), cudaMemcpyHostToDevice));
 }
 
@@ -2083,7 +2088,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       }
     }
     BuildArgs b;
-    b.Next = Next; b.nt = s.nt; b.g = s.grid;
+    b.Next = Next; b.nt = s.nt; b.g = s.grid; b.all_interact = s.all_interact ? 1 : 0;
     b.xRc2s = s.xRcSq * invL2;
     b.xRcs = std::sqrt(b.xRc2s) * (1.0 + 1e-9);
     build_band(b.xRc2s, M, b.r2_accept, b.r2_reject);
