@@ -195,6 +195,56 @@ def workload_config(ncell, N, world, where):
             "l2_policy": "inputs larger than L2: the neighbor list streamed every step (>300 MB at 1M atoms) exceeds the 126 MB L2"}
 
 
+def spce_line(args):
+    """Informational (not the contract line): SPC/E water, NIST sample replicated n^3 times, rigid bodies,
+    LJ shifted-force on O + pair_none on H + coul_damped_smoothed(0.2, 1.0) (reference test/test_coul_*.f90).
+    The rigid-body integrator is outside the hot-path scope, so a step = upload the configuration rigidly
+    drifted a little further, EmDee_compute_forces, read the scalars (e2e by nature)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common as cm
+    lib = api.load()
+    n = args.replicas
+    K, W = min(args.steps, 30), 3
+    res = {}
+    for tag, thelib, steps in (("gpu", lib, K), ("cpu", oracle_lib(), 6)):
+        s, c = cm.spce_sample_system(thelib, lambda l: l.EmDee_coul_damped_smoothed(0.2, 1.0), replicas=n,
+                                     threads=os.cpu_count() or 1)
+        N, mol = c["N"], c["molecule"]
+        calls = {"k": 0}
+        drift = 0.17 * np.ones(3) / np.sqrt(3.0)
+        def advance():
+            # the whole configuration drifts rigidly by 0.17 A per call: the physical state (energies, forces) is
+            # unchanged, atoms keep crossing cells, and the displacement criterion (skin = 2 A) fires every ~6 calls
+            calls["k"] += 1
+            return c["R"] + calls["k"] * drift
+        for _ in range(W if tag == "gpu" else 1):
+            s.upload("coordinates", advance())
+            s.compute_forces()
+        if tag == "gpu":
+            s.set_kernel_timing(True)
+            st0 = s.stats()
+        b0 = s.md.Builds
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            s.upload("coordinates", advance())
+            s.compute_forces()
+        dt = time.perf_counter() - t0
+        res[tag] = {"atom_steps_per_s": N * steps / dt, "ms_per_step": 1e3 * dt / steps, "builds": s.md.Builds - b0,
+                    "steps": steps, "U": s.md.Energy.Potential}
+        if tag == "gpu":
+            st1 = s.stats()
+            fl = st1.force_launches - st0.force_launches
+            res[tag]["force_kernel_ms"] = (st1.force_ms - st0.force_ms) / max(fl, 1)
+            res[tag]["build_kernel_ms"] = (st1.build_ms - st0.build_ms) / max(st1.build_launches - st0.build_launches, 1)
+            res[tag]["list_entries_per_atom_half"] = st1.list_entries / 2.0 / N
+            res[tag]["interacting_per_atom_half"] = st1.interacting / 2.0 / N
+        s.finalize()
+    print(json.dumps({"metric": METRIC, "workload": f"SPC/E NIST sample x {n}^3 = {N} atoms, Rc=10 A, skin=2 A, rigid bodies, "
+                      "coul_damped_smoothed(0.2,1.0); upload + compute_forces per step", "informational": True,
+                      "gpu": res["gpu"], "cpu_port": res["cpu"], "cores": os.cpu_count()}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,6 +254,10 @@ def main():
     ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="fcc cells per dimension (atoms = 4*ncell^3)")
     ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="lj", choices=["lj", "spce"],
+                    help="lj: the contract workload (BASELINE.json configs[3]); spce: informational line for the "
+                         "SPC/E n^3 replica box (force evaluations on uploaded configurations)")
+    ap.add_argument("--replicas", type=int, default=8, help="spce: replicas per dimension of the NIST sample")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +266,9 @@ def main():
 
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.workload == "spce":
+        spce_line(args)
         return
 
     import torch

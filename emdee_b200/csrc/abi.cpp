@@ -81,7 +81,7 @@ HostModel* handle(void* p) {
 void* deliver(const HostModel& m) { return new HostModel(m); }   // never freed, like src/modelClass.f90:51-60
 
 void eval(const HostModel& m, double invR, double invR2, double& E, double& W) {
-  nb::eval_kind<nb::K_DYNAMIC>(m.dev, invR, invR2, E, W);
+  nb::eval_kind<nb::K_DYNAMIC>(m.dev, nb::make_dist(invR, invR2), E, W);
 }
 
 HostModel make_lj(double epsilon, double sigma) {   // src/pair_lj_cut.f90:52-69

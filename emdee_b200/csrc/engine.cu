@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(TPB) k_refresh_positions(int Next, double L, c
 struct ForceArgs {
   int Next, cap, nt;
   double Rc2s;      // cutoff^2 in scaled units (RcSq or InRcSq times invL2)
-  double L, invL, invL2;
+  double L, L2, invL, invL2;
   const double4* pos;
   const int* nbr;
   const int* nbrCount;
@@ -573,18 +573,21 @@ __device__ __forceinline__ void pair_term(const ForceArgs& a, const PairEntry* t
       s.fy = fma(t, dy, s.fy);
       s.fz = fma(t, dz, s.fz);
     } else {
-      double invR, invR2;
+      nb::Dist D;
       if (NEED_INVR) {
-        invR = rsqrt(r2) * a.invL;
-        invR2 = invR * invR;
+        D.invR = rsqrt(r2) * a.invL;
+        D.invR2 = D.invR * D.invR;
       } else {
-        invR2 = fast_rcp(r2) * a.invL2;
-        invR = 0.0;
+        D.invR2 = fast_rcp(r2) * a.invL2;
+        D.invR = 0.0;
       }
+      D.r2 = r2 * a.L2;          // real-unit r^2 and r, so that no model body divides
+      D.r = D.r2 * D.invR;
+      const double invR2 = D.invR2;
       const PairEntry& pe = SINGLE ? a.single : tab[itype * a.nt + a.sType[f]];
       double E, W;
-      nb::eval_kind<PK>(pe.model, invR, invR2, E, W);
-      nb::eval_modifier<PM>(pe.model, invR, invR2, E, W);
+      nb::eval_kind<PK>(pe.model, D, E, W);
+      nb::eval_modifier<PM>(pe.model, D, E, W);
       if (COMPUTE) s.Ep += E;
       s.Wp += W;
       double Wsum = W;
@@ -595,8 +598,8 @@ __device__ __forceinline__ void pair_term(const ForceArgs& a, const PairEntry* t
             Eq = 0.0;
             Wq = W;
           } else {
-            nb::eval_kind<CK>(a.coul, invR, invR2, Eq, Wq);
-            nb::eval_modifier<CM>(a.coul, invR, invR2, Eq, Wq);
+            nb::eval_kind<CK>(a.coul, D, Eq, Wq);
+            nb::eval_modifier<CM>(a.coul, D, Eq, Wq);
           }
           const double QiQj = pe.kCoul * pi.w * pj.w;
           if (COMPUTE) s.Ec += QiQj * Eq;
@@ -2176,7 +2179,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   ForceArgs a;
   a.Next = Next; a.cap = s.cap; a.nt = s.nt;
   a.Rc2s = (lt.useInRc ? s.InRcSq : s.RcSq) * invL2;
-  a.L = Lbox; a.invL = 1.0 / Lbox; a.invL2 = invL2;
+  a.L = Lbox; a.L2 = Lbox * Lbox; a.invL = 1.0 / Lbox; a.invL2 = invL2;
   a.pos = s.pos.p; a.nbr = s.nbr.p; a.nbrCount = s.nbrCount.p; a.sMeta = s.sMeta.p; a.sGhost = s.sGhost.p;
   a.sType = s.sType.p;
   a.delta = (s.has_delta && s.nbodies != 0) ? s.delta.p : nullptr;

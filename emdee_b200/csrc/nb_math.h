@@ -59,10 +59,39 @@ struct DevModel {
   double a, b, c, d;
 };
 
+// The pair distance in all the forms the model formulas use, so that no model body needs a division:
+// the reference writes `a/invR`, `1/invR2`, ...; here r and r2 are carried along (r = r2*invR), which is
+// the same number to within one rounding.
+struct Dist {
+  double invR, invR2, r, r2;
+};
+NB_HD Dist make_dist(double invR, double invR2) {   // host-side setup: the reference passes (1/r, 1/r^2)
+  Dist d;
+  d.invR = invR;
+  d.invR2 = invR2;
+  d.r = 1.0 / invR;
+  d.r2 = 1.0 / invR2;
+  return d;
+}
+
+// reciprocal: full-precision division on the host; on the device the 20-bit hardware seed plus one cubic
+// refinement (relative error < 2^-57)
+NB_HD double rcp(double a) {
+#if defined(__CUDA_ARCH__)
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  double t = fma(e, e, e);
+  return fma(x, t, x);
+#else
+  return 1.0 / a;
+#endif
+}
+
 NB_HD double uerfc(double x, double expmx2) {
   const double a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027,
                a5 = 1.061405429, p = 0.327591100;
-  double t = 1.0 / (1.0 + p * x);
+  double t = rcp(1.0 + p * x);
   return t * (a1 + t * (a2 + t * (a3 + t * (a4 + t * a5)))) * expmx2;
 }
 
@@ -77,7 +106,8 @@ NB_HD void quintic(double u, double coef, double& G, double& WGu) {
 // E(r), W(r) = -r dE/dr of model `m` (unit charges for Coulomb kinds). KIND is a compile-time kind
 // or K_DYNAMIC. invR = 1/r, invR2 = 1/r^2 in real (unscaled) units.
 template <int KIND>
-NB_HD void eval_kind(const DevModel& m, double invR, double invR2, double& E, double& W) {
+NB_HD void eval_kind(const DevModel& m, const Dist& D, double& E, double& W) {
+  const double invR = D.invR, invR2 = D.invR2;
   const int kind = (KIND == K_DYNAMIC) ? m.kind : KIND;
   switch (kind) {
     case K_PAIR_LJ_CUT: {
@@ -89,9 +119,9 @@ NB_HD void eval_kind(const DevModel& m, double invR, double invR2, double& E, do
       break;
     }
     case K_PAIR_SOFTCORE_CUT: {
-      double rsig2 = m.c / invR2;
+      double rsig2 = m.c * D.r2;
       double rsig6 = rsig2 * rsig2 * rsig2;
-      double sinv = 1.0 / (rsig6 + m.d);
+      double sinv = rcp(rsig6 + m.d);
       double sinvSq = sinv * sinv;
       double sinvCb = sinv * sinvSq;
       E = m.a * (sinvSq - sinv);
@@ -103,20 +133,20 @@ NB_HD void eval_kind(const DevModel& m, double invR, double invR2, double& E, do
       W = invR;
       break;
     case K_COUL_SF: {
-      double rFc = m.fshift / invR;
+      double rFc = m.fshift * D.r;
       E = invR + m.eshift + rFc;
       W = invR - rFc;
       break;
     }
     case K_COUL_DAMPED: {
-      double x = m.a / invR;
+      double x = m.a * D.r;
       double expmx2 = exp(-x * x);
       E = uerfc(x, expmx2) * invR;
       W = E + m.b * expmx2;
       break;
     }
     case K_COUL_DAMPED_SMOOTHED: {
-      double r = 1.0 / invR;
+      double r = D.r;
       double x = m.a * r;
       double expmx2 = exp(-x * x);
       E = uerfc(x, expmx2) * invR;
@@ -131,12 +161,12 @@ NB_HD void eval_kind(const DevModel& m, double invR, double invR2, double& E, do
       break;
     }
     case K_COUL_DAMPED_SQUARE_SMOOTHED: {
-      double x = m.a / invR;
+      double x = m.a * D.r;
       double expmx2 = exp(-x * x);
       E = uerfc(x, expmx2) * invR;
       W = E + m.b * expmx2;
       if (invR < m.d) {
-        double r2 = 1.0 / invR2;
+        double r2 = D.r2;
         double G, WG;
         quintic(m.factor * (r2 - m.c), -60.0, G, WG);
         WG = WG * m.factor * r2;
@@ -150,7 +180,7 @@ NB_HD void eval_kind(const DevModel& m, double invR, double invR2, double& E, do
       W = invR;
       E = (kind == K_COUL_SHIFTED_SQUARE_SMOOTHED) ? W + m.eshift : W;
       if (invR < m.d) {
-        double r2 = 1.0 / invR2;
+        double r2 = D.r2;
         double G, WG;
         quintic(m.factor * (r2 - m.c), -60.0, G, WG);
         WG = WG * m.factor * r2;
@@ -168,14 +198,14 @@ NB_HD void eval_kind(const DevModel& m, double invR, double invR2, double& E, do
 
 // src/apply_modifier.f90: post-processing of (E, W) by the model's modifier.
 template <int MOD>
-NB_HD void eval_modifier(const DevModel& m, double invR, double invR2, double& E, double& W) {
+NB_HD void eval_modifier(const DevModel& m, const Dist& D, double& E, double& W) {
   const int mod = (MOD == M_DYNAMIC) ? m.modifier : MOD;
   switch (mod) {
     case M_SHIFTED:
       E = E + m.eshift;
       break;
     case M_SHIFTED_FORCE: {
-      double rFc = m.fshift / invR;
+      double rFc = m.fshift * D.r;
       W = W - rFc;
       E = E + m.eshift + rFc;
       break;
@@ -186,7 +216,7 @@ NB_HD void eval_modifier(const DevModel& m, double invR, double invR2, double& E
     case M_SHIFTED_SQUARE_SMOOTHED: {
       const bool square = (mod == M_SQUARE_SMOOTHED || mod == M_SHIFTED_SQUARE_SMOOTHED);
       E = E + m.eshift;
-      double r2fac = square ? m.factor / invR2 : m.factor / invR;
+      double r2fac = square ? m.factor * D.r2 : m.factor * D.r;
       if (r2fac > m.Rm2fac) {
         double G, WG;
         quintic(r2fac - m.Rm2fac, square ? -60.0 : -30.0, G, WG);
