@@ -279,9 +279,14 @@ __device__ __forceinline__ int image_shifts_z(int cz, const GridDesc& g, int s[3
 __global__ void __launch_bounds__(TPB) k_bin(const double* __restrict__ R, int N, double L, GridDesc g,
                                              double* __restrict__ Rs, int* __restrict__ atomCell,
                                              int* __restrict__ atomFloor, unsigned char* __restrict__ owned,
-                                             int* __restrict__ cellCount) {
+                                             const unsigned char* __restrict__ known, int* __restrict__ cellCount) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (known != nullptr && !known[i]) {   // multi-GPU: this rank holds no current position for the atom
+    owned[i] = 0;
+    atomCell[i] = -1;
+    return;
+  }
   int c[3];
 #pragma unroll
   for (int x = 0; x < 3; ++x) {
@@ -312,6 +317,7 @@ __global__ void __launch_bounds__(TPB) k_fill(int N, GridDesc g, const int* __re
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   int pc = atomCell[i];
+  if (pc < 0) return;   // not known to this rank
   int c[3] = {pc & 1023, (pc >> 10) & 1023, (pc >> 20) & 1023};
   int sx[2], sy[2], sz[3], lz[3];
   int nx = image_shifts(c[0], g.M, sx), ny = image_shifts(c[1], g.M, sy), nz = image_shifts_z(c[2], g, sz, lz);
@@ -1338,6 +1344,56 @@ __global__ void __launch_bounds__(TPB) k_mask_owned(int N, const unsigned char* 
   for (int x = 0; x < 3; ++x) dst[3 * (size_t)i + x] = o ? src[3 * (size_t)i + x] : 0.0;
 }
 
+// Rebuild-time migration (multi-GPU): instead of re-assembling the full coordinate and momentum arrays on
+// every rank, each rank sends its owned atoms that now sit within three cell layers of a slab face (or just
+// beyond it) to the neighbor on that side, as (id, R, P) records. After that a rank "knows" its previously
+// owned atoms plus what it received -- a superset of its new slab + 2-layer halo, because nothing moves more
+// than skin/2 < one layer between rebuilds -- and re-bins only those.
+__global__ void __launch_bounds__(TPB) k_mig_flags(int N, double L, GridDesc g, const double* __restrict__ R,
+                                                   const unsigned char* __restrict__ owned,
+                                                   unsigned char* __restrict__ fl) {   // 2 flag arrays of N
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  bool up = false, dn = false;
+  if (owned[i]) {
+    const double rs = __ddiv_rn(R[3 * (size_t)i + 2], L);
+    int cz = (int)__dmul_rn((double)g.M, __dsub_rn(rs, floor(rs)));
+    if (cz >= g.M) cz = g.M - 1;
+    const int z1 = g.z0 + g.nzl;
+    up = ((cz - (z1 - 3)) % g.M + g.M) % g.M < 5;     // layers z1-3 .. z1+1 (periodic)
+    dn = (((g.z0 + 2) - cz) % g.M + g.M) % g.M < 5;   // layers z0-2 .. z0+2
+  }
+  fl[i] = up;
+  fl[(size_t)N + i] = dn;
+}
+
+__global__ void __launch_bounds__(TPB) k_pack7(int n, const int* __restrict__ list, const double* __restrict__ R,
+                                               const double* __restrict__ P, double* __restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int a = list[k];
+  double* b = buf + 7 * (size_t)k;
+  b[0] = (double)a;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    b[1 + x] = R[3 * (size_t)a + x];
+    b[4 + x] = P[3 * (size_t)a + x];
+  }
+}
+__global__ void __launch_bounds__(TPB) k_unpack7(int n, const double* __restrict__ buf, double* __restrict__ R,
+                                                 double* __restrict__ P, unsigned char* __restrict__ known) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double* b = buf + 7 * (size_t)k;
+  const int a = (int)b[0];
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    R[3 * (size_t)a + x] = b[1 + x];
+    P[3 * (size_t)a + x] = b[4 + x];
+  }
+  known[a] = 1;
+}
+
 // halo bookkeeping: which owned atoms sit in my top / bottom two layers (to send), which foreign atoms sit
 // in the two layers above / below my slab (to receive). Lists are compacted in ascending atom order, so
 // a sender's list and the matching receiver's list are identical without exchanging indices.
@@ -1345,6 +1401,10 @@ __global__ void __launch_bounds__(TPB) k_halo_flags(int N, GridDesc g, const int
                                                     unsigned char* __restrict__ fl) {   // 4 flag arrays of N
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (atomCell[i] < 0) {   // not known to this rank
+    fl[i] = fl[(size_t)N + i] = fl[2 * (size_t)N + i] = fl[3 * (size_t)N + i] = 0;
+    return;
+  }
   const int cz = (atomCell[i] >> 20) & 1023;
   const int z1 = g.z0 + g.nzl;
   const bool own = cz >= g.z0 && cz < z1;
@@ -1537,6 +1597,11 @@ struct Engine::Impl {
   DBuf<unsigned char> owned;       // per atom: this rank integrates it and computes its force
   bool owned_valid = false;        // false until the first distributed rebuild (all ranks hold full arrays)
   bool halo_fresh = true;          // halo positions are current (false after displace)
+  DBuf<unsigned char> known;       // per atom: this rank holds a current position (owned, halo or just received)
+  bool all_known = true;           // every rank holds full, current arrays (after uploads / downloads)
+  bool p_partial = false;          // momenta of non-owned atoms may be stale (coordinates were uploaded alone)
+  DBuf<int> migList[2];
+  DBuf<double> migSend[2], migRecv[2];
   DBuf<double> scratch3;           // 3N doubles: masked copies for the all-reduce that rebuilds full arrays
   DBuf<unsigned char> haloFlags;   // 4N
   DBuf<int> haloList[4];           // send up, send down, receive from below, receive from above
@@ -1697,6 +1762,8 @@ Engine::~Engine() {
   s.bdesc.release(); s.nbr16.release(); s.duoNbr.release(); s.duoCount.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
+  s.known.release();
+  for (int k = 0; k < 2; ++k) { s.migList[k].release(); s.migSend[k].release(); s.migRecv[k].release(); }
   if (s.h_mi) cudaFreeHost(s.h_mi);
   if (s.comm) nccl().CommDestroy(s.comm);
   s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release(); s.tickets.release();
@@ -1791,6 +1858,62 @@ void halo_exchange(Engine::Impl& s) {
   s.halo_fresh = true;
 }
 
+// rebuild-time migration: see k_mig_flags. Returns with R, P current for every atom this rank may need.
+void migrate(Engine::Impl& s, double Lbox) {
+  const int N = s.N;
+  s.known.ensure(N);
+  if (s.all_known) {   // arrays are full on every rank (first build, or after an upload/download)
+    if (s.p_partial) {
+      gather_full(s, s.P.p);
+      s.p_partial = false;
+    }
+    CUDA_CHECK(cudaMemsetAsync(s.known.p, 1, N, s.stream));
+    return;
+  }
+  const int up = (s.rank + 1) % s.world, dn = (s.rank + s.world - 1) % s.world;
+  s.haloFlags.ensure(4 * (size_t)N);
+  s.selCount.ensure(4);
+  k_mig_flags<<<nblocks(N), TPB, 0, s.stream>>>(N, Lbox, s.grid, s.R.p, s.owned.p, s.haloFlags.p);
+  cub::CountingInputIterator<int> ids(0);
+  size_t need = 0;
+  cub::DeviceSelect::Flagged(nullptr, need, ids, s.haloFlags.p, (int*)nullptr, s.selCount.p, N, s.stream);
+  if (need > s.scanTmpBytes) {
+    s.scanTmp.ensure(need);
+    s.scanTmpBytes = need;
+  }
+  for (int k = 0; k < 2; ++k) {
+    s.migList[k].ensure(N);
+    cub::DeviceSelect::Flagged(s.scanTmp.p, need, ids, s.haloFlags.p + (size_t)k * N, s.migList[k].p, s.selCount.p + k, N,
+                               s.stream);
+  }
+  // counts: mine -> neighbors, theirs -> me (selCount[2] = from below, selCount[3] = from above)
+  NCCL_CHECK(nccl().GroupStart());
+  NCCL_CHECK(nccl().Send(s.selCount.p + 0, 1, ncclInt, up, s.comm, s.stream));
+  NCCL_CHECK(nccl().Send(s.selCount.p + 1, 1, ncclInt, dn, s.comm, s.stream));
+  NCCL_CHECK(nccl().Recv(s.selCount.p + 2, 1, ncclInt, dn, s.comm, s.stream));
+  NCCL_CHECK(nccl().Recv(s.selCount.p + 3, 1, ncclInt, up, s.comm, s.stream));
+  NCCL_CHECK(nccl().GroupEnd());
+  int c[4];
+  CUDA_CHECK(cudaMemcpyAsync(c, s.selCount.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  for (int k = 0; k < 2; ++k) {
+    s.migSend[k].ensure(7 * (size_t)c[k] + 8, 1.2);
+    s.migRecv[k].ensure(7 * (size_t)c[2 + k] + 8, 1.2);
+    if (c[k] > 0) k_pack7<<<nblocks(c[k]), TPB, 0, s.stream>>>(c[k], s.migList[k].p, s.R.p, s.P.p, s.migSend[k].p);
+  }
+  NCCL_CHECK(nccl().GroupStart());
+  NCCL_CHECK(nccl().Send(s.migSend[0].p, 7 * (size_t)c[0], ncclDouble, up, s.comm, s.stream));
+  NCCL_CHECK(nccl().Send(s.migSend[1].p, 7 * (size_t)c[1], ncclDouble, dn, s.comm, s.stream));
+  NCCL_CHECK(nccl().Recv(s.migRecv[0].p, 7 * (size_t)c[2], ncclDouble, dn, s.comm, s.stream));
+  NCCL_CHECK(nccl().Recv(s.migRecv[1].p, 7 * (size_t)c[3], ncclDouble, up, s.comm, s.stream));
+  NCCL_CHECK(nccl().GroupEnd());
+  // known = previously owned + received
+  CUDA_CHECK(cudaMemcpyAsync(s.known.p, s.owned.p, N, cudaMemcpyDeviceToDevice, s.stream));
+  for (int k = 0; k < 2; ++k)
+    if (c[2 + k] > 0)
+      k_unpack7<<<nblocks(c[2 + k]), TPB, 0, s.stream>>>(c[2 + k], s.migRecv[k].p, s.R.p, s.P.p, s.known.p);
+}
+
 // distributed rebuild decision: identical on every rank (all inputs are all-gathered / all-reduced)
 bool rebuild_needed_dist(Engine::Impl& s) {
   const int N = s.N;
@@ -1865,6 +1988,10 @@ void Engine::upload_coordinates(const double* R) {
   s.has_R = true;
   s.check_cached = false;
   s.halo_fresh = true;   // every rank uploads the full array
+  if (s.world > 1 && s.owned_valid && !s.all_known) {
+    s.all_known = true;    // coordinates are full everywhere again ...
+    s.p_partial = true;    // ... but the momenta of atoms owned elsewhere are stale here until the next rebuild
+  }
 }
 void Engine::upload_body_delta(const double* delta) {
   Impl& s = *d_;
@@ -1874,6 +2001,7 @@ void Engine::upload_body_delta(const double* delta) {
 }
 void Engine::upload_momenta(const double* P) {
   CUDA_CHECK(cudaMemcpy(d_->P.p, P, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
+  d_->p_partial = false;
 }
 void Engine::upload_forces(int layer0, const double* F) {
   CUDA_CHECK(cudaMemcpy(d_->F.p + (size_t)layer0 * 3 * d_->N, F, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
@@ -2004,14 +2132,23 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     s.grid.z0 = 0;
     s.grid.nzl = M;
     if (s.world > 1) {
-      // every rank needs the current positions (and momenta: ownership may change) of all atoms to re-bin
-      gather_full(s, s.R.p);
-      gather_full(s, s.P.p);
       int z0, z1;
       slab_range(M, s.rank, s.world, z0, z1);
-      if (z1 - z0 < 2) fatal("neighbor list handling", "fewer than two cell layers per GPU: use fewer GPUs for this box");
-      s.grid.z0 = z0;
+      if (z1 - z0 < 3 || M / s.world < 3)
+        fatal("neighbor list handling", "fewer than three cell layers per GPU: use fewer GPUs for this box");
+      if (s.owned_valid && (s.grid.M != M || s.grid.z0 != z0)) {
+        // the cell grid itself changed (box rescaled): fall back to re-assembling the full arrays
+        gather_full(s, s.R.p);
+        gather_full(s, s.P.p);
+        s.all_known = true;
+        s.p_partial = false;
+      }
+      s.owned.ensure(N);
+      if (!s.owned_valid) CUDA_CHECK(cudaMemsetAsync(s.owned.p, 0, N, s.stream));
+      s.grid.z0 = z0;       // migrate() classifies against the slab faces of the grid being built
       s.grid.nzl = z1 - z0;
+      s.grid.Mz = s.grid.nzl + 4;
+      migrate(s, Lbox);
     }
     s.grid.Mz = s.grid.nzl + 4;
     s.owned.ensure(N);
@@ -2024,7 +2161,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     s.cellFill.ensure(ncell + 1);
     CUDA_CHECK(cudaMemsetAsync(s.cellCount.p, 0, (ncell + 1) * sizeof(int), s.stream));
     CUDA_CHECK(cudaMemsetAsync(s.cellFill.p, 0, (ncell + 1) * sizeof(int), s.stream));
-    k_bin<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, N, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p, s.owned.p, s.cellCount.p);
+    k_bin<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, N, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p, s.owned.p,
+                                            s.world > 1 ? s.known.p : nullptr, s.cellCount.p);
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, s.cellCount.p, s.cellStart.p, (int)(ncell + 1), s.stream);
     if (need > s.scanTmpBytes) {
@@ -2155,7 +2293,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     if (s.world > 1) {
       build_halo_lists(s);
       s.owned_valid = true;
-      s.halo_fresh = true;   // gather_full just made every position current
+      s.all_known = false;
+      s.halo_fresh = true;   // migrate() just made every needed position current
     }
     CUDA_CHECK(cudaMemcpyAsync(s.R0.p, s.R.p, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
     s.h_scalars[8] = 0.0;   // R0 = R: the criterion for the current coordinates is now zero displacement
@@ -2301,6 +2440,7 @@ void Engine::displace(double CR, double CP) {
     stats_.launches += 1;
     s.halo_fresh = false;
     s.check_cached = false;
+    s.all_known = false;   // from now on only owned + halo positions are current on this rank
   } else {
     k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p, s.chkPartial.p,
                                                    s.tickets.p + 2, s.scalars.p + 8);
