@@ -1600,7 +1600,7 @@ struct Engine::Impl {
   DBuf<unsigned char> known;       // per atom: this rank holds a current position (owned, halo or just received)
   bool all_known = true;           // every rank holds full, current arrays (after uploads / downloads)
   bool p_partial = false;          // momenta of non-owned atoms may be stale (coordinates were uploaded alone)
-  DBuf<int> migList[2];
+  DBuf<int> migList[2], migCounts;
   DBuf<double> migSend[2], migRecv[2];
   DBuf<double> scratch3;           // 3N doubles: masked copies for the all-reduce that rebuilds full arrays
   DBuf<unsigned char> haloFlags;   // 4N
@@ -1762,7 +1762,7 @@ Engine::~Engine() {
   s.bdesc.release(); s.nbr16.release(); s.duoNbr.release(); s.duoCount.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
-  s.known.release();
+  s.known.release(); s.migCounts.release();
   for (int k = 0; k < 2; ++k) { s.migList[k].release(); s.migSend[k].release(); s.migRecv[k].release(); }
   if (s.h_mi) cudaFreeHost(s.h_mi);
   if (s.comm) nccl().CommDestroy(s.comm);
@@ -1833,6 +1833,7 @@ void build_halo_lists(Engine::Impl& s) {
   int h[4];
   CUDA_CHECK(cudaMemcpyAsync(h, s.selCount.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee r%d] halo lists: send up %d dn %d, recv below %d above %d\n", s.rank, h[0], h[1], h[2], h[3]);
   for (int k = 0; k < 4; ++k) {
     s.haloCount[k] = h[k];
     s.haloBuf[k].ensure(3 * (size_t)h[k] + 8, 1.2);
@@ -1886,26 +1887,28 @@ void migrate(Engine::Impl& s, double Lbox) {
     cub::DeviceSelect::Flagged(s.scanTmp.p, need, ids, s.haloFlags.p + (size_t)k * N, s.migList[k].p, s.selCount.p + k, N,
                                s.stream);
   }
-  // counts: mine -> neighbors, theirs -> me (selCount[2] = from below, selCount[3] = from above)
-  NCCL_CHECK(nccl().GroupStart());
-  NCCL_CHECK(nccl().Send(s.selCount.p + 0, 1, ncclInt, up, s.comm, s.stream));
-  NCCL_CHECK(nccl().Send(s.selCount.p + 1, 1, ncclInt, dn, s.comm, s.stream));
-  NCCL_CHECK(nccl().Recv(s.selCount.p + 2, 1, ncclInt, dn, s.comm, s.stream));
-  NCCL_CHECK(nccl().Recv(s.selCount.p + 3, 1, ncclInt, up, s.comm, s.stream));
-  NCCL_CHECK(nccl().GroupEnd());
-  int c[4];
-  CUDA_CHECK(cudaMemcpyAsync(c, s.selCount.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  // counts: every rank learns every rank's (up, down) record counts with one small all-gather
+  s.migCounts.ensure(2 * (size_t)s.world);
+  NCCL_CHECK(nccl().AllGather(s.selCount.p, s.migCounts.p, 2, ncclInt, s.comm, s.stream));
+  std::vector<int> all(2 * (size_t)s.world);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), s.migCounts.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  int c[4];
+  c[0] = all[2 * s.rank];       // what I send up
+  c[1] = all[2 * s.rank + 1];   // what I send down
+  c[2] = all[2 * dn];           // what the rank below sends up = what arrives from below
+  c[3] = all[2 * up + 1];       // what the rank above sends down = what arrives from above
+  if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee r%d] migrate: send up %d dn %d, recv from-below %d from-above %d\n", s.rank, c[0], c[1], c[2], c[3]);
   for (int k = 0; k < 2; ++k) {
     s.migSend[k].ensure(7 * (size_t)c[k] + 8, 1.2);
     s.migRecv[k].ensure(7 * (size_t)c[2 + k] + 8, 1.2);
     if (c[k] > 0) k_pack7<<<nblocks(c[k]), TPB, 0, s.stream>>>(c[k], s.migList[k].p, s.R.p, s.P.p, s.migSend[k].p);
   }
-  NCCL_CHECK(nccl().GroupStart());
-  NCCL_CHECK(nccl().Send(s.migSend[0].p, 7 * (size_t)c[0], ncclDouble, up, s.comm, s.stream));
-  NCCL_CHECK(nccl().Send(s.migSend[1].p, 7 * (size_t)c[1], ncclDouble, dn, s.comm, s.stream));
-  NCCL_CHECK(nccl().Recv(s.migRecv[0].p, 7 * (size_t)c[2], ncclDouble, dn, s.comm, s.stream));
-  NCCL_CHECK(nccl().Recv(s.migRecv[1].p, 7 * (size_t)c[3], ncclDouble, up, s.comm, s.stream));
+  NCCL_CHECK(nccl().GroupStart());   // zero-length messages are skipped on both sides (both know the counts)
+  if (c[0] > 0) NCCL_CHECK(nccl().Send(s.migSend[0].p, 7 * (size_t)c[0], ncclDouble, up, s.comm, s.stream));
+  if (c[1] > 0) NCCL_CHECK(nccl().Send(s.migSend[1].p, 7 * (size_t)c[1], ncclDouble, dn, s.comm, s.stream));
+  if (c[2] > 0) NCCL_CHECK(nccl().Recv(s.migRecv[0].p, 7 * (size_t)c[2], ncclDouble, dn, s.comm, s.stream));
+  if (c[3] > 0) NCCL_CHECK(nccl().Recv(s.migRecv[1].p, 7 * (size_t)c[3], ncclDouble, up, s.comm, s.stream));
   NCCL_CHECK(nccl().GroupEnd());
   // known = previously owned + received
   CUDA_CHECK(cudaMemcpyAsync(s.known.p, s.owned.p, N, cudaMemcpyDeviceToDevice, s.stream));
@@ -2102,6 +2105,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   if (s.world > 1 && s.owned_valid) {
     halo_exchange(s);
     rebuild = rebuild_needed_dist(s);
+    if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee r%d] compute_forces: rebuild=%d all_known=%d\n", s.rank, (int)rebuild, (int)s.all_known);
     stats_.launches += 1;
   } else {
     if (s.check_cached) {
@@ -2127,6 +2131,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     if (2 * Lbox / s.xRc < 5.0)
       fatal("neighbor list handling", "box length is smaller than 2.5*(Rc + skin): the reference's 5x5x5 cell stencil cannot cover the cutoff sphere");
     if (M > 1019) fatal("neighbor list handling", "more than 1019 cells per dimension are not supported");
+    const int prevM = s.grid.M;   // the grid of the previous build (0 before the first one)
     s.grid.M = M;
     s.grid.Mx = M + 4;
     s.grid.z0 = 0;
@@ -2136,9 +2141,15 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       slab_range(M, s.rank, s.world, z0, z1);
       if (z1 - z0 < 3 || M / s.world < 3)
         fatal("neighbor list handling", "fewer than three cell layers per GPU: use fewer GPUs for this box");
-      if (s.owned_valid && (s.grid.M != M || s.grid.z0 != z0)) {
+      if (s.owned_valid && prevM != M) {   // same decision on every rank (M is global)
         // the cell grid itself changed (box rescaled): fall back to re-assembling the full arrays
         gather_full(s, s.R.p);
+        gather_full(s, s.P.p);
+        s.all_known = true;
+        s.p_partial = false;
+      }
+      if (s.owned_valid && !s.all_known && std::getenv("EMDEE_NO_MIGRATE") != nullptr) {
+        gather_full(s, s.R.p);   // simpler scheme: re-assemble the full arrays on every rank
         gather_full(s, s.P.p);
         s.all_known = true;
         s.p_partial = false;

@@ -33,7 +33,7 @@ def build_lj(lib, comm, ncell=14, charged=False):
     return s
 
 
-def build_spce(lib, comm):
+def build_spce(lib, comm, replicas=2):
     def pre(lib_, s_):
         if comm:
             edist.init_comm(lib_, s_)
@@ -49,7 +49,7 @@ def build_spce(lib, comm):
 
     cm.api.System.set_pair_model = patched
     try:
-        s, c = cm.spce_sample_system(lib, lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0), replicas=2)
+        s, c = cm.spce_sample_system(lib, lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0), replicas=replicas)
     finally:
         cm.api.System.set_pair_model = orig
     return s
@@ -104,9 +104,10 @@ def main():
         if rank == 0:
             so.finalize()
 
-    sp = build_spce(lib, True)
-    so = build_spce(orc, False) if rank == 0 else None
-    compare("spce 2x2x2 replicas (rigid bodies, body virial)", sp, so, rank)
+    nrep = 2 if world <= 3 else 3     # M = 5*nrep cell layers; every rank needs at least three
+    sp = build_spce(lib, True, nrep)
+    so = build_spce(orc, False, nrep) if rank == 0 else None
+    compare(f"spce {nrep}^3 replicas (rigid bodies, body virial)", sp, so, rank)
     sp.finalize()
     dist.barrier()
     if rank == 0:
