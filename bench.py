@@ -333,7 +333,7 @@ def main():
     P_half = st1.interacting / 2.0 / n_local     # entries with r < Rc per atom
 
     # ---- e2e arm: host buffers in the timed region -------------------------------------------------
-    nframes = 24
+    nframes = int(max(6, min(24, 1.0e9 // (24 * N))))   # at most ~1 GB of pinned frames per rank
     frames = torch.empty((nframes, N, 3), dtype=torch.float64).pin_memory()
     fout = torch.empty((N, 3), dtype=torch.float64).pin_memory()
     fr = frames.numpy()
@@ -374,6 +374,11 @@ def main():
     fp64_peak = lib.EmDeeX_measure_fp64_tflops() if rank == 0 else None
     ach_tf = flops_per_atom * n_local / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
 
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
+    if world == 1 and ncell == NCELL_DEFAULT and os.path.exists(tpath):
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]   # from the committed ncu --set full capture
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -398,7 +403,7 @@ def main():
                                            "EmDee_download(forces, pinned host) per step, wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_pair_forces", "achieved": ach_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "traffic": None,
+                         "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "traffic": traffic,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_atom": bytes_per_atom, "list_entries_per_atom_half": C_half,
                          "interacting_per_atom_half": P_half,
