@@ -98,7 +98,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._run, daemon=True)
@@ -248,8 +248,8 @@ def spce_line(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="fcc cells per dimension (atoms = 4*ncell^3)")
     ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the bounded CPU-baseline sample")
