@@ -26,55 +26,55 @@ extern "C" {
 #endif
 
 typedef struct {              /* src/EmDeeCode.f90:44-49 */
-  double Pair;                /* Time taken in force calculations */
-  double Motion;              /* Time taken in EmDee_displace */
-  double Neighbor;            /* Time taken in neighbor-list handling */
-  double Total;               /* Total time since EmDee_system */
+  double Pair;                /* seconds spent in the pair-force path */
+  double Motion;              /* seconds spent moving atoms (EmDee_displace) */
+  double Neighbor;            /* seconds spent checking / rebuilding the neighbor list */
+  double Total;               /* wall clock since the system was created */
 } tTime;
 
 typedef struct {              /* src/EmDeeData.f90:40-49 */
-  double Potential;           /* Total potential energy of the system */
-  double Dispersion;          /* Dispersion (vdW) part of the potential energy */
-  double Coulomb;             /* Electrostatic part of the potential energy */
+  double Potential;           /* sum of all potential-energy terms */
+  double Dispersion;          /* pair-model (van der Waals) term */
+  double Coulomb;             /* Coulomb-model term */
   double Bond;
   double Angle;
   double Dihedral;
   double ShadowPotential;
-  bool   UpToDate;            /* Flag to attest whether energies have been computed */
+  bool   UpToDate;            /* energies correspond to the current configuration */
 } tEnergy;
 
 typedef struct {              /* src/EmDeeData.f90:51-59 */
-  double Total;               /* Total kinetic energy of the system */
-  double TransPart[3];        /* Translational kinetic energy at each dimension */
-  double Rotational;          /* Total rotational kinetic energy of the system */
-  double RotPart[3];          /* Rotational kinetic energy around each principal axis */
+  double Total;               /* translational + rotational kinetic energy */
+  double TransPart[3];        /* translational part, per Cartesian direction */
+  double Rotational;          /* rotational part (rigid bodies) */
+  double RotPart[3];          /* rotational part, per principal axis */
   double ShadowKinetic;
   double ShadowRotational;
   bool   UpToDate;
 } tKinetic;
 
 typedef struct {              /* src/EmDeeData.f90:61-64 */
-  double Total;               /* Total internal virial of the system */
-  double Body;                /* Rigid body contribution to the internal virial */
+  double Total;               /* internal virial, all terms */
+  double Body;                /* rigid-body (constraint) contribution */
 } tVirial;
 
 typedef struct {              /* src/EmDeeCode.f90:36-42 */
-  bool   Translate;           /* Flag to activate/deactivate translations */
-  bool   Rotate;              /* Flag to activate/deactivate rotations */
-  int    RotationMode;        /* Algorithm used for free rotation of rigid bodies */
-  bool   AutoBodyUpdate;      /* Flag to activate/deactivate automatic rigid body update */
-  bool   Compute;             /* Flag to activate/deactivate energy computations */
+  bool   Translate;           /* integrate translations in boost/displace */
+  bool   Rotate;              /* integrate rigid-body rotations */
+  int    RotationMode;        /* free-rotor algorithm selector (0 = exact) */
+  bool   AutoBodyUpdate;      /* re-derive body frames when coordinates are uploaded */
+  bool   Compute;             /* evaluate energies (false: forces and virial only) */
 } tOpts;
 
 typedef struct {              /* src/EmDeeCode.f90:51-61 */
-  int      Builds;            /* Number of neighbor-list builds */
+  int      Builds;            /* how many times the neighbor list has been rebuilt */
   tTime    Time;
   tEnergy  Energy;
   tKinetic Kinetic;
   tVirial  Virial;
-  int      DoF;               /* Total number of degrees of freedom */
-  int      RotDoF;            /* Number of rotational degrees of freedom */
-  void*    Data;              /* Pointer to system data (opaque) */
+  int      DoF;               /* degrees of freedom, total */
+  int      RotDoF;            /* degrees of freedom, rotational */
+  void*    Data;              /* opaque handle of the system state */
   tOpts    Options;
 } tEmDee;
 
