@@ -1755,6 +1755,59 @@ long long EmDeeX_download_pairs(tEmDee md, int* pairs, long long capacity) {
   return n;
 }
 
+// Oracle-only (not part of the boundary in include/): flat dump of one layer's interaction tables, which
+// tests/test_host_tables.py compares with what the product's host shim hands to its kernels.
+// Records of 13 doubles {kind, modifier, eshift, fshift, Rm, factor, Rm2fac, a, b, c, d, kCoul, coulomb} for
+// the ntypes x ntypes pair entries (row-major) and then the Coulomb model, followed by the ntypes x ntypes
+// `interact` mask, `pairs_exist` and `useInRc`. Kind codes: 0 pair_none, 1 lj_cut, 2 softcore_cut, 10 coul_none,
+// 11 cut, 12 sf, 13 damped/long, 14 damped_smoothed, 15 damped_square_smoothed, 16 square_smoothed,
+// 17 shifted_square_smoothed. Slots: LJ a=4eps b=24eps c=sigma^2; softcore a=prefactor b=6*prefactor
+// c=1/sigma^2 d=shift; Coulomb a=alpha b=beta c=Rm^2 d=1/Rm. Returns the number of doubles written.
+int EmDeeX_dump_tables(tEmDee md, int layer, double* out, int cap) {
+  System* me = sys(md);
+  if (layer < 1 || layer > me->nlayers) return -1;
+  const int nt = me->ntypes;
+  const int need = 13 * (nt * nt + 1) + nt * nt + 2;
+  if (cap < need) return -need;
+  int k = 0;
+  auto code = [](Kind kd) {
+    switch (kd) {
+      case PAIR_NONE: return 0;
+      case PAIR_LJ_CUT: return 1;
+      case PAIR_SOFTCORE_CUT: return 2;
+      case COUL_NONE: return 10;
+      case COUL_CUT: return 11;
+      case COUL_SF: return 12;
+      case COUL_DAMPED: case COUL_LONG: return 13;
+      case COUL_DAMPED_SMOOTHED: return 14;
+      case COUL_DAMPED_SQUARE_SMOOTHED: return 15;
+      case COUL_SQUARE_SMOOTHED: return 16;
+      case COUL_SHIFTED_SQUARE_SMOOTHED: return 17;
+      default: return -1;
+    }
+  };
+  auto put = [&](const Model& m, double kCoul, double coulomb) {
+    double a = 0, b = 0, c = 0, d = 0;
+    if (m.kind == PAIR_LJ_CUT) { a = m.eps4; b = m.eps24; c = m.sigsq; }
+    else if (m.kind == PAIR_SOFTCORE_CUT) { a = m.prefactor; b = m.prefactor6; c = m.invSigSq; d = m.shift; }
+    else if (is_coul(m.kind)) { a = m.alpha; b = m.beta; c = m.Rm2; d = m.invRm; }
+    const double v[13] = {(double)code(m.kind), (double)m.modifier, m.eshift, m.fshift, m.Rm, m.factor, m.Rm2fac,
+                          a, b, c, d, kCoul, coulomb};
+    for (double x : v) out[k++] = x;
+  };
+  for (int i = 1; i <= nt; ++i)
+    for (int j = 1; j <= nt; ++j) {
+      PairContainer& p = me->pr(i, j, layer);
+      put(p.model, p.coulomb ? p.kCoul : 0.0, p.coulomb ? 1.0 : 0.0);
+    }
+  put(me->coul[layer - 1], 0.0, 0.0);
+  for (int i = 1; i <= nt; ++i)
+    for (int j = 1; j <= nt; ++j) out[k++] = me->tt(me->interact, i, j) ? 1.0 : 0.0;
+  out[k++] = me->pairs_exist[layer - 1] ? 1.0 : 0.0;
+  out[k++] = me->useInRc[layer - 1] ? 1.0 : 0.0;
+  return k;
+}
+
 void EmDeeX_finalize(tEmDee* md) {
   delete sys(*md);
   md->Data = nullptr;
