@@ -205,3 +205,32 @@ def test_layer_based_parameters_useInRc():
     t = compare(script, layers=2)
     nrec = 5
     assert t[0][13 * nrec + 4 + 1] == 0 and t[1][13 * nrec + 4 + 1] == 1   # useInRc per layer
+
+
+@pytest.mark.parametrize("adjust", [False, True])
+def test_random_momenta_stream(stub, adjust):
+    """KISS + ziggurat stream and the momentum adjustment (reference src/math.f90:94-236,
+    src/EmDeeCode.f90:950-1020) as implemented by the product's host shim, bit for bit against the oracle."""
+    N = 500
+    rng = np.random.default_rng(11)
+    L = 9.0
+    R = rng.uniform(0, L, (N, 3))
+    masses = np.array([1.0, 3.5])
+    types = (np.arange(N) % 2 + 1).astype(np.int32)
+    out = []
+    for lib in (stub, oracle_lib()):
+        s = lib.system(1, 1, 2.5, 0.5, N, types, masses, None)
+        s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0)
+        s.set_pair_model(2, 2, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0)
+        s.upload("box", [L])
+        s.upload("coordinates", R)
+        s.random_momenta(1.3, adjust, 86241)
+        out.append((s.download("momenta"), s.md.Kinetic.Total, s.md.DoF))
+        s.finalize()
+    (Pa, Ka, Da), (Pb, Kb, Db) = out
+    assert Da == Db
+    if adjust:
+        assert np.allclose(Pa, Pb, rtol=1e-13, atol=1e-15)
+    else:
+        assert np.array_equal(Pa, Pb)
+    assert Ka == pytest.approx(Kb, rel=1e-13)
