@@ -714,6 +714,114 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) k_pair_forces(const __grid
 }
 
 // ================================================================================================
+// Rows path (opt-in, EMDEE_ROWS=G with G in {8,16,32}; not yet measured on a GPU): G lanes share ONE atom and
+// take its neighbors G at a time, so the lanes of a gather read CONSECUTIVE entries of one row. Rows are
+// ascending in the sorted entry index and the sorted order is cell-major, so consecutive row entries are mostly
+// consecutive in memory: a warp-gather touches ~8-12 distinct 128-byte lines instead of ~26 when every lane
+// follows its own atom (tools/lsu_probe.cu measures exactly this trade). The price is a
+// G-lane shuffle reduction of the force per atom and a row-major copy of the list (k_transpose_rows, once per
+// rebuild). Summation order differs from the default path, results agree to rounding.
+// ================================================================================================
+constexpr int ROWS_TILES_PER_BLOCK = 8;
+
+// tile-major list (slot k of entry e at ((e/32)*cap + k)*32 + e%32) -> row-major (rows[e*pitch + k]), through
+// shared memory so that both the reads and the writes are 128-byte coalesced
+__global__ void __launch_bounds__(32 * ROWS_TILES_PER_BLOCK) k_transpose_rows(int Next, int cap, int pitch,
+                                                                              const int* __restrict__ nbr,
+                                                                              const int* __restrict__ nbrCount,
+                                                                              int* __restrict__ rows) {
+  __shared__ int tile[ROWS_TILES_PER_BLOCK][32][33];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * ROWS_TILES_PER_BLOCK + w;   // tile of 32 entries (warp-uniform)
+  const long long e = t * TILE + lane;
+  const int cnt = (e < Next) ? nbrCount[e] : 0;
+  int mx = cnt;
+  for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  for (int k0 = 0; k0 < mx; k0 += 32) {
+    for (int r = 0; r < 32 && k0 + r < mx; ++r)   // slot k0+r of the 32 entries: one coalesced 128-byte row
+      tile[w][r][lane] = nbr[((size_t)t * cap + k0 + r) * TILE + lane];
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {                // entry r of the tile: its slots k0 .. k0+31
+      const int c = __shfl_sync(0xffffffffu, cnt, r);
+      const int k = k0 + lane;
+      if (k < c) rows[(size_t)(t * TILE + r) * pitch + k] = tile[w][lane][r];
+    }
+    __syncwarp();
+  }
+}
+
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE, int G, int UNROLL>
+__global__ void __launch_bounds__(256) k_pair_forces_rows(const __grid_constant__ ForceArgs a, int pitch,
+                                                          const int* __restrict__ rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PairEntry* tab = a.tab;
+  if (!SINGLE && a.nt <= MAX_SMEM_TYPES) {
+    PairEntry* st = reinterpret_cast<PairEntry*>(smem_raw);
+    const int words = a.nt * a.nt * (int)(sizeof(PairEntry) / sizeof(int));
+    for (int w = threadIdx.x; w < words; w += blockDim.x)
+      reinterpret_cast<int*>(st)[w] = reinterpret_cast<const int*>(a.tab)[w];
+    __syncthreads();
+    tab = st;
+  }
+  constexpr bool LJ_FAST = SINGLE && PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
+  constexpr int APW = 32 / G;   // atoms per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (G - 1);
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long e = warp * APW + lane / G;   // the sorted entry this lane's group works on
+  const bool valid = e < a.Next;
+  PairAcc s;
+  double Wb = 0.0;
+  if (valid) {
+    const int cnt = a.nbrCount[e];   // ghosts hold 0
+    if (cnt > 0) {
+      const double4 pi = a.pos[e];
+      const int itype = SINGLE ? 0 : a.sType[e];
+      const bool icharged = fabs(pi.w) > DEPS;
+      const int* row = rows + (size_t)e * pitch;
+      const double c1 = a.single.model.c * a.invL2;
+      int k = sub;
+      for (; k + G * (UNROLL - 1) < cnt; k += G * UNROLL) {   // UNROLL gathers in flight per lane
+        int f[UNROLL];
+        double4 p[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) f[u] = row[k + G * u];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) p[u] = ld_pos(a.pos + f[u]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p[u], f[u], s);
+      }
+      for (; k < cnt; k += G) {
+        const int f0 = row[k];
+        pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, ld_pos(a.pos + f0), f0, s);
+      }
+    }
+  }
+  // every lane of the warp arrives here: fold the G partial forces of each atom (fixed butterfly order)
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) {
+    s.fx += __shfl_xor_sync(0xffffffffu, s.fx, off);
+    s.fy += __shfl_xor_sync(0xffffffffu, s.fy, off);
+    s.fz += __shfl_xor_sync(0xffffffffu, s.fz, off);
+  }
+  if (LJ_FAST) {   // the energy / virial partials stay per lane: scale each (cf. finish_atom)
+    s.Ep *= a.single.model.a;
+    s.Wp *= a.single.model.b;
+  }
+  if (valid && sub == 0 && !a.sGhost[e]) {
+    const double fs = LJ_FAST ? a.single.model.b * a.invL2 * a.L : a.L;
+    const size_t atom = (size_t)a.sMeta[e].x;
+    const double fx = s.fx * fs, fy = s.fy * fs, fz = s.fz * fs;
+    a.F[3 * atom] = fx;
+    a.F[3 * atom + 1] = fy;
+    a.F[3 * atom + 2] = fz;
+    if (a.delta != nullptr) Wb = -(fx * a.delta[3 * atom] + fy * a.delta[3 * atom + 1] + fz * a.delta[3 * atom + 2]);
+  }
+  reduce_scalars(a, s.Ep, s.Ec, s.Wp, s.Wc, Wb);
+}
+
+// ================================================================================================
 // Duo path: one thread owns TWO consecutive sorted entries (same or adjacent cell) and walks the UNION of
 // their neighbor rows, so a neighbor that both atoms see is gathered once. The LSU data path (one
 // wavefront per distinct 32-byte sector of a divergent gather) is what binds the force kernel; the union
@@ -1581,6 +1689,9 @@ struct Engine::Impl {
   // duo path: union rows of consecutive entry pairs
   bool use_duos = false;
   int cap2 = 0;
+  int rows_group = 0;   // EMDEE_ROWS: lanes per atom of the rows path (0 = off)
+  int rows_pitch = 0;
+  DBuf<int> rowsNbr;
   DBuf<unsigned int> duoNbr;
   DBuf<int> duoCount;
 
@@ -1759,7 +1870,7 @@ Engine::~Engine() {
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
-  s.bdesc.release(); s.nbr16.release(); s.duoNbr.release(); s.duoCount.release();
+  s.bdesc.release(); s.nbr16.release(); s.duoNbr.release(); s.duoCount.release(); s.rowsNbr.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
   s.known.release(); s.migCounts.release();
@@ -2045,6 +2156,24 @@ void launch_force_duo(const ForceArgs& a, int cap2, const unsigned int* duoNbr, 
   else k_pair_forces_duo<PK, PM, CK, CM, SINGLE, NEED_INVR, false><<<grid, TPB, smem, st>>>(a, cap2, duoNbr, duoCount);
 }
 
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, int UNROLL>
+void launch_force_rows(ForceArgs& a, DBuf<double>& partial, int group, int pitch, const int* rows, bool compute, size_t smem,
+                       cudaStream_t st) {
+  const long long warps = ((long long)a.Next * group + 31) / 32;   // 32/group atoms per warp
+  const int grid = (int)((warps + 7) / 8);                         // 8 warps per block
+  partial.ensure((size_t)grid * 5);
+  a.partial = partial.p;
+#define EMDEE_ROWS_CASE(GG)                                                                                               \
+  if (group == GG) {                                                                                                      \
+    if (compute) k_pair_forces_rows<PK, PM, CK, CM, SINGLE, NEED_INVR, true, GG, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows); \
+    else k_pair_forces_rows<PK, PM, CK, CM, SINGLE, NEED_INVR, false, GG, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows);       \
+  }
+  EMDEE_ROWS_CASE(8)
+  EMDEE_ROWS_CASE(16)
+  EMDEE_ROWS_CASE(32)
+#undef EMDEE_ROWS_CASE
+}
+
 template <int PK, int PM, int CK, int CM, bool NEED_INVR>
 void launch_force_brick(const ForceArgs& a, const BrickArgs& k, bool compute, int grid, int threads, size_t smem,
                         cudaStream_t st) {
@@ -2301,6 +2430,18 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
         s.cap2 = (int)(hf[2] * 1.1) + 8;
       }
     }
+    // ---- rows path: row-major copy of the list -------------------------------------------------------------
+    s.rows_group = 0;
+    if (!s.use_bricks && !s.use_duos && std::getenv("EMDEE_ROWS") != nullptr) {   // opt-in experiment (see k_pair_forces_rows)
+      const int g = std::atoi(std::getenv("EMDEE_ROWS"));
+      s.rows_group = (g == 8 || g == 16 || g == 32) ? g : 8;
+      s.rows_pitch = (s.cap + 7) & ~7;   // rows start on 32-byte boundaries
+      s.rowsNbr.ensure((size_t)Next * s.rows_pitch, 1.1);
+      const int tgrid = (int)((ntiles + ROWS_TILES_PER_BLOCK - 1) / ROWS_TILES_PER_BLOCK);
+      k_transpose_rows<<<tgrid, 32 * ROWS_TILES_PER_BLOCK, 0, s.stream>>>(Next, s.cap, s.rows_pitch, s.nbr.p, s.nbrCount.p,
+                                                                           s.rowsNbr.p);
+      stats_.launches += 1;
+    }
     if (s.world > 1) {
       build_halo_lists(s);
       s.owned_valid = true;
@@ -2378,6 +2519,17 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       launch_force_duo<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
     else
       launch_force_duo<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, smem_dyn, s.stream);
+  } else if (s.rows_group != 0) {
+    const int* rows = s.rowsNbr.p;
+    const int g = s.rows_group, pitch = s.rows_pitch;
+    if (s.nt == 1 && lj_plain)
+      launch_force_rows<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, 3>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
+    else if (s.nt == 1 && lj_sf)
+      launch_force_rows<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 2>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
+    else if (s.nt == 1 && lj_coul_sf)
+      launch_force_rows<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
+    else
+      launch_force_rows<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, g, pitch, rows, compute, smem_dyn, s.stream);
   } else if (s.nt == 1 && lj_plain && compute && std::getenv("EMDEE_FORCE_TUNE") != nullptr) {
     // tuning hook (bench experiments only): EMDEE_FORCE_TUNE="<variant>"
     const int v = std::atoi(std::getenv("EMDEE_FORCE_TUNE"));

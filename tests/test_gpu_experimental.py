@@ -1,0 +1,42 @@
+"""Opt-in kernel paths that have been written but NOT yet confirmed on a GPU. Gated twice: the `gpu` marker and
+EMDEE_TEST_EXPERIMENTAL=1, so the default `pytest -m gpu` run never depends on unconfirmed code. Once a path is
+confirmed its test moves to test_gpu_parity.py (as the brick and duo paths did).
+
+    EMDEE_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+import common as cm
+from test_gpu_parity import (COUL_VARIANTS, KTOL, PAIR_VARIANTS, _lj, _two_type_system, assert_state_parity, both)
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("EMDEE_TEST_EXPERIMENTAL") != "1",
+                                 reason="unconfirmed kernel paths: set EMDEE_TEST_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("group", [8, 16, 32])
+def test_rows_path(monkeypatch, group):
+    """EMDEE_ROWS=G: G lanes share one atom and read consecutive entries of its (row-major) neighbor row
+    (k_transpose_rows + k_pair_forces_rows). Same parity bars as the default path; every model goes through it."""
+    monkeypatch.setenv("EMDEE_ROWS", str(group))
+    for variant in ("lj_cut", "lj_shifted_force", "softcore_0.7"):
+        sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS[variant])[0])
+        assert_state_parity(sp, so)
+        sp.finalize(), so.finalize()
+    sp, so = both(lambda lib: cm.spce_sample_system(lib, COUL_VARIANTS["coul_damped_smoothed"])[0])
+    assert_state_parity(sp, so)
+    sp.finalize(), so.finalize()
+    sp, so = both(lambda lib: _two_type_system(lib, COUL_VARIANTS["coul_sf"]))
+    assert_state_parity(sp, so)
+    sp.finalize(), so.finalize()
+    outs = []
+    for lib in (cm.product(), cm.oracle()):
+        s, c = cm.lj_sample_system(lib, _lj)
+        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
+        outs.append(cm.run_nve(s, c, 100))
+        s.finalize()
+    assert np.abs(outs[0] - cm.kats()["lj_cut"]).max() < KTOL
+    assert np.abs(outs[0] - outs[1]).max() < KTOL

@@ -1,0 +1,26 @@
+#!/bin/bash
+# First GPU call of the next round (run under gpurun from the repo root; ~6 GPU-minutes):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/next_gpu_call.sh'
+# 1. gather-cost microbenchmark (decides between the layouts discussed in DESIGN.md section 5)
+# 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS) and of the box-rescale scenario
+# 3. LJ-1M bench: default path vs EMDEE_ROWS=8/16/32
+set -u
+mkdir -p gpurun_out
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lsu_probe tools/lsu_probe.cu && timeout 120 /tmp/lsu_probe > gpurun_out/lsu_probe.txt 2>&1
+EMDEE_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py tests/test_zz_box_rescale.py -m gpu -q > gpurun_out/experimental_tests.txt 2>&1
+tail -5 gpurun_out/experimental_tests.txt
+timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+for g in 8 16 32; do
+  EMDEE_ROWS=$g timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_rows$g.json 2> gpurun_out/bench_rows$g.err
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/bench_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, "value %.3e" % d["value"], "ms/step %.4f" % d["ms_per_step"], "force_ms %.4f" % d["timing"]["force_kernel_ms"],
+              "build_ms %.4f" % d["timing"]["build_kernel_ms"])
+    except Exception as ex:
+        print(f, "unreadable:", ex)
+PY
+cat gpurun_out/lsu_probe.txt
