@@ -927,6 +927,88 @@ __global__ void __launch_bounds__(TPB) k_pair_forces_duo(const __grid_constant__
   reduce_scalars(a, s0.Ep + s1.Ep, s0.Ec + s1.Ec, s0.Wp + s1.Wp, s0.Wc + s1.Wc, Wb);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster-2 path (opt-in, EMDEE_CLUSTER2=1; not yet measured on a GPU): one WARP owns the duo (2d, 2d+1): lanes
+// 0-15 work for the first atom, lanes 16-31 for the second, and lane pair (s, s+16) reads the SAME entry of the
+// duo's union row (row-major copy, k_transpose_rows), so a warp-gather touches 16 sectors (~7 lines) for up to 32
+// pair terms, and unlike the duo kernel above no thread carries two atoms (no extra registers, no two-body
+// divergence). A lane whose atom does not list the entry (mask bit clear) idles for that slot: ~68 % of the slots
+// are useful (tools/gather_model.py). Force partials are folded over the 16 lanes of each atom by shuffles.
+// ------------------------------------------------------------------------------------------------
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, bool COMPUTE, int UNROLL>
+__global__ void __launch_bounds__(256) k_pair_forces_cluster2(const __grid_constant__ ForceArgs a, int pitch,
+                                                              const unsigned int* __restrict__ rows,
+                                                              const int* __restrict__ duoCount) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PairEntry* tab = a.tab;
+  if (!SINGLE && a.nt <= MAX_SMEM_TYPES) {
+    PairEntry* st = reinterpret_cast<PairEntry*>(smem_raw);
+    const int words = a.nt * a.nt * (int)(sizeof(PairEntry) / sizeof(int));
+    for (int w = threadIdx.x; w < words; w += blockDim.x)
+      reinterpret_cast<int*>(st)[w] = reinterpret_cast<const int*>(a.tab)[w];
+    __syncthreads();
+    tab = st;
+  }
+  constexpr bool LJ_FAST = SINGLE && PK == nb::K_PAIR_LJ_CUT && PM == nb::M_NONE && CK == nb::K_COUL_NONE;
+  const int lane = threadIdx.x & 31;
+  const int which = lane >> 4, sub = lane & 15;
+  const unsigned int mybit = which ? DUO_B1 : DUO_B0;
+  const long long d = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // duo of this warp
+  const long long e = 2 * d + which;
+  const bool valid = e < a.Next;
+  PairAcc s;
+  double Wb = 0.0;
+  if (valid) {
+    const int cnt = duoCount[d];   // 2d < Next whenever e is valid
+    if (cnt > 0) {
+      const double4 pi = a.pos[e];
+      const int itype = SINGLE ? 0 : a.sType[e];
+      const bool icharged = fabs(pi.w) > DEPS;
+      const unsigned int* row = rows + (size_t)d * pitch;
+      const double c1 = a.single.model.c * a.invL2;
+      int k = sub;
+      for (; k + 16 * (UNROLL - 1) < cnt; k += 16 * UNROLL) {
+        unsigned int v[UNROLL];
+        double4 p[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = row[k + 16 * u];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) p[u] = ld_pos(a.pos + (v[u] & DUO_IDX));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (v[u] & mybit)
+            pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p[u], (int)(v[u] & DUO_IDX), s);
+      }
+      for (; k < cnt; k += 16) {
+        const unsigned int v0 = row[k];
+        const double4 p0 = ld_pos(a.pos + (v0 & DUO_IDX));
+        if (v0 & mybit)
+          pair_term<PK, PM, CK, CM, SINGLE, NEED_INVR, COMPUTE>(a, tab, pi, itype, icharged, c1, p0, (int)(v0 & DUO_IDX), s);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) {   // fold the 16 partial forces of each atom (fixed butterfly order)
+    s.fx += __shfl_xor_sync(0xffffffffu, s.fx, off);
+    s.fy += __shfl_xor_sync(0xffffffffu, s.fy, off);
+    s.fz += __shfl_xor_sync(0xffffffffu, s.fz, off);
+  }
+  if (LJ_FAST) {
+    s.Ep *= a.single.model.a;
+    s.Wp *= a.single.model.b;
+  }
+  if (valid && sub == 0 && !a.sGhost[e]) {
+    const double fs = LJ_FAST ? a.single.model.b * a.invL2 * a.L : a.L;
+    const size_t atom = (size_t)a.sMeta[e].x;
+    const double fx = s.fx * fs, fy = s.fy * fs, fz = s.fz * fs;
+    a.F[3 * atom] = fx;
+    a.F[3 * atom + 1] = fy;
+    a.F[3 * atom + 2] = fz;
+    if (a.delta != nullptr) Wb = -(fx * a.delta[3 * atom] + fy * a.delta[3 * atom + 1] + fz * a.delta[3 * atom + 2]);
+  }
+  reduce_scalars(a, s.Ep, s.Ec, s.Wp, s.Wc, Wb);
+}
+
 // ================================================================================================
 // Brick path (single-type systems whose cell occupancy fits): the real cells are tiled by bricks of
 // about b^3 cells; one CTA owns a brick, stages the positions of the brick plus its 2-cell halo in
@@ -1690,6 +1772,7 @@ struct Engine::Impl {
   bool use_duos = false;
   int cap2 = 0;
   int rows_group = 0;   // EMDEE_ROWS: lanes per atom of the rows path (0 = off)
+  bool use_cluster2 = false;   // EMDEE_CLUSTER2: warp-per-duo kernel over the row-major union rows
   int rows_pitch = 0;
   DBuf<int> rowsNbr;
   DBuf<unsigned int> duoNbr;
@@ -2174,6 +2257,17 @@ void launch_force_rows(ForceArgs& a, DBuf<double>& partial, int group, int pitch
 #undef EMDEE_ROWS_CASE
 }
 
+template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, int UNROLL>
+void launch_force_cluster2(ForceArgs& a, DBuf<double>& partial, int pitch, const unsigned int* rows, const int* duoCount,
+                           bool compute, size_t smem, cudaStream_t st) {
+  const long long nduo = ((long long)a.Next + 1) / 2;   // one warp per duo, 8 warps per block
+  const int grid = (int)((nduo + 7) / 8);
+  partial.ensure((size_t)grid * 5);
+  a.partial = partial.p;
+  if (compute) k_pair_forces_cluster2<PK, PM, CK, CM, SINGLE, NEED_INVR, true, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows, duoCount);
+  else k_pair_forces_cluster2<PK, PM, CK, CM, SINGLE, NEED_INVR, false, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows, duoCount);
+}
+
 template <int PK, int PM, int CK, int CM, bool NEED_INVR>
 void launch_force_brick(const ForceArgs& a, const BrickArgs& k, bool compute, int grid, int threads, size_t smem,
                         cudaStream_t st) {
@@ -2412,7 +2506,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     }
     // ---- duo rows: sorted merge of the rows of entries (2d, 2d+1) ------------------------------------------
     s.use_duos = !s.use_bricks && std::getenv("EMDEE_DUOS") != nullptr;   // opt-in: fewer LSU wavefronts but more FP64 issue + divergence; measured slower
-    if (s.use_duos) {
+    s.use_cluster2 = !s.use_bricks && !s.use_duos && std::getenv("EMDEE_CLUSTER2") != nullptr;   // opt-in, unmeasured
+    if (s.use_duos || s.use_cluster2) {
       const int nduo = (Next + 1) / 2;
       const long long dtiles = ((long long)nduo + TILE - 1) / TILE;
       if (s.cap2 == 0) s.cap2 = (int)(1.45 * s.cap) + 8;
@@ -2429,10 +2524,19 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
         if (!hf[3]) break;
         s.cap2 = (int)(hf[2] * 1.1) + 8;
       }
+      if (s.use_cluster2) {   // row-major copy of the union rows (one row per duo)
+        s.rows_pitch = (s.cap2 + 7) & ~7;
+        s.rowsNbr.ensure((size_t)nduo * s.rows_pitch, 1.1);
+        const int tgrid = (int)((dtiles + ROWS_TILES_PER_BLOCK - 1) / ROWS_TILES_PER_BLOCK);
+        k_transpose_rows<<<tgrid, 32 * ROWS_TILES_PER_BLOCK, 0, s.stream>>>(nduo, s.cap2, s.rows_pitch,
+                                                                             reinterpret_cast<const int*>(s.duoNbr.p), s.duoCount.p,
+                                                                             s.rowsNbr.p);
+        stats_.launches += 1;
+      }
     }
     // ---- rows path: row-major copy of the list -------------------------------------------------------------
     s.rows_group = 0;
-    if (!s.use_bricks && !s.use_duos && std::getenv("EMDEE_ROWS") != nullptr) {   // opt-in experiment (see k_pair_forces_rows)
+    if (!s.use_bricks && !s.use_duos && !s.use_cluster2 && std::getenv("EMDEE_ROWS") != nullptr) {   // opt-in experiment (see k_pair_forces_rows)
       const int g = std::atoi(std::getenv("EMDEE_ROWS"));
       s.rows_group = (g == 8 || g == 16 || g == 32) ? g : 8;
       s.rows_pitch = (s.cap + 7) & ~7;   // rows start on 32-byte boundaries
@@ -2519,6 +2623,16 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       launch_force_duo<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
     else
       launch_force_duo<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, smem_dyn, s.stream);
+  } else if (s.use_cluster2) {
+    const unsigned int* rows = reinterpret_cast<const unsigned int*>(s.rowsNbr.p);
+    if (s.nt == 1 && lj_plain)
+      launch_force_cluster2<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, 0, s.stream);
+    else if (s.nt == 1 && lj_sf)
+      launch_force_cluster2<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, 0, s.stream);
+    else if (s.nt == 1 && lj_coul_sf)
+      launch_force_cluster2<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, 0, s.stream);
+    else
+      launch_force_cluster2<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, smem_dyn, s.stream);
   } else if (s.rows_group != 0) {
     const int* rows = s.rowsNbr.p;
     const int g = s.rows_group, pitch = s.rows_pitch;

@@ -17,11 +17,7 @@ pytestmark = [pytest.mark.gpu,
                                  reason="unconfirmed kernel paths: set EMDEE_TEST_EXPERIMENTAL=1")]
 
 
-@pytest.mark.parametrize("group", [8, 16, 32])
-def test_rows_path(monkeypatch, group):
-    """EMDEE_ROWS=G: G lanes share one atom and read consecutive entries of its (row-major) neighbor row
-    (k_transpose_rows + k_pair_forces_rows). Same parity bars as the default path; every model goes through it."""
-    monkeypatch.setenv("EMDEE_ROWS", str(group))
+def _all_model_families():
     for variant in ("lj_cut", "lj_shifted_force", "softcore_0.7"):
         sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS[variant])[0])
         assert_state_parity(sp, so)
@@ -40,3 +36,18 @@ def test_rows_path(monkeypatch, group):
         s.finalize()
     assert np.abs(outs[0] - cm.kats()["lj_cut"]).max() < KTOL
     assert np.abs(outs[0] - outs[1]).max() < KTOL
+
+
+@pytest.mark.parametrize("group", [8, 16, 32])
+def test_rows_path(monkeypatch, group):
+    """EMDEE_ROWS=G: G lanes share one atom and read consecutive entries of its (row-major) neighbor row
+    (k_transpose_rows + k_pair_forces_rows). Same parity bars as the default path; every model goes through it."""
+    monkeypatch.setenv("EMDEE_ROWS", str(group))
+    _all_model_families()
+
+
+def test_cluster2_path(monkeypatch):
+    """EMDEE_CLUSTER2=1: one warp per duo of consecutive entries, half a warp per atom, lane pairs share each
+    entry of the duo's union row (k_merge_duos + k_transpose_rows + k_pair_forces_cluster2)."""
+    monkeypatch.setenv("EMDEE_CLUSTER2", "1")
+    _all_model_families()

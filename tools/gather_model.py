@@ -132,6 +132,36 @@ def rows_mapping(real, rows, G, nwarps, rng):
                 yield np.array(g), np.array(lanes)
 
 
+def cluster_mapping(real, rows, C, nwarps, rng):
+    """C consecutive entries share one UNION row; lane (a, s) handles atom a and union slot s of 32/C per
+    gather, computing only if the slot's entry is in atom a's own row (mask). Yields also the useful pairs."""
+    J = 32 // C
+    Next = len(real)
+    warps = rng.choice(np.arange(Next // C), size=min(nwarps, Next // C), replace=False)
+    for w in warps:
+        es = np.arange(C * w, C * w + C)
+        rr = [rows[e] if real[e] else np.zeros(0, np.int64) for e in es]
+        if max(len(r) for r in rr) == 0:
+            continue
+        union = np.unique(np.concatenate(rr))
+        member = [np.isin(union, r) for r in rr]
+        for k0 in range(0, len(union), J):
+            seg = union[k0:k0 + J]
+            useful = sum(int(m[k0:k0 + J].sum()) for m in member)
+            # every lane of a slot column reads the same entry: the request touches len(seg) sectors
+            yield seg, np.arange(len(seg)) * C, useful
+
+
+def count_cluster(gathers):
+    n = sectors = lines = useful = 0
+    for seg, lanes, u in gathers:
+        n += 1
+        sectors += len(seg)
+        lines += len(np.unique(seg >> 2))
+        useful += u
+    return dict(gathers=n, sectors=sectors / n, lines=lines / n, lanes_active=useful / (32.0 * n))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ncell", type=int, default=16)
@@ -149,6 +179,10 @@ def main():
     for G in (8, 16, 32):
         res[f"rows G={G:<2d} (G lanes per atom)"] = count(rows_mapping(real, rows, G, args.warps * (32 // G), rng))
     base = res["default (lane = atom)"]
+    for C in (2, 4, 8):
+        r = count_cluster(cluster_mapping(real, rows, C, args.warps * 4, rng))
+        r["quadlines"] = float("nan")
+        res[f"cluster {C} atoms x {32 // C:<2d} slots"] = r
     for name, r in res.items():
         per_pair = {k: r[k] / (32 * r["lanes_active"]) for k in ("sectors", "lines", "quadlines")}
         bp = {k: base[k] / (32 * base["lanes_active"]) for k in ("sectors", "lines", "quadlines")}

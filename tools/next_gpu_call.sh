@@ -2,8 +2,8 @@
 # First GPU call of the next round (run under gpurun from the repo root; ~6 GPU-minutes):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/next_gpu_call.sh'
 # 1. gather-cost microbenchmark (decides between the layouts discussed in DESIGN.md section 5)
-# 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS) and of the box-rescale scenario
-# 3. LJ-1M bench: default path vs EMDEE_ROWS=8/16/32
+# 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS, EMDEE_CLUSTER2) and of the box-rescale scenario
+# 3. LJ-1M bench: default path vs EMDEE_ROWS=8/16/32 vs EMDEE_CLUSTER2=1
 set -u
 mkdir -p gpurun_out
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lsu_probe tools/lsu_probe.cu && timeout 120 /tmp/lsu_probe > gpurun_out/lsu_probe.txt 2>&1
@@ -13,6 +13,7 @@ timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_o
 for g in 8 16 32; do
   EMDEE_ROWS=$g timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_rows$g.json 2> gpurun_out/bench_rows$g.err
 done
+EMDEE_CLUSTER2=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_cluster2.json 2> gpurun_out/bench_cluster2.err
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/bench_*.json")):
