@@ -125,6 +125,7 @@ ABI_EXT_PRODUCT = {
     "EmDeeX_stats": (None, [tEmDee, C.POINTER(tEmDeeXStats)]),
     "EmDeeX_set_kernel_timing": (None, [tEmDee, C.c_int]),
     "EmDeeX_synchronize": (None, [tEmDee]),
+    "EmDeeX_stream": (C.c_void_p, [tEmDee]),
     "EmDeeX_measure_fp64_tflops": (C.c_double, []),
     "EmDeeX_comm_unique_id": (None, [C.c_char_p]),
     "EmDeeX_comm_init": (None, [tEmDee, C.c_int, C.c_int, C.c_char_p]),
@@ -258,6 +259,10 @@ class System:
 
     def synchronize(self):
         self.lib.EmDeeX_synchronize(self.md)
+
+    def stream(self) -> int:
+        """cudaStream_t (as an integer) the system's kernels run on."""
+        return int(self.lib.EmDeeX_stream(self.md) or 0)
 
     def finalize(self):
         if self.md.Data:

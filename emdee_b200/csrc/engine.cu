@@ -2217,6 +2217,7 @@ void Engine::download_forces(int layer0, double* F) {
   CUDA_CHECK(cudaMemcpy(F, d_->F.p + (size_t)layer0 * 3 * d_->N, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
+void* Engine::stream_handle() { return (void*)d_->stream; }
 
 // ---- force-kernel dispatch ---------------------------------------------------------------------
 namespace {

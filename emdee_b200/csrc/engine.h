@@ -80,6 +80,7 @@ class Engine {
   long long download_pairs(int* pairs, long long capacity);
   void set_kernel_timing(bool on) { timing_ = on; }
   void synchronize();
+  void* stream_handle();   // the cudaStream_t every kernel of this system is launched on
   EngineStats stats() const { return stats_; }
 
   // ---- multi-GPU: one rank per GPU, z-slab decomposition (NCCL) ---------------------------------

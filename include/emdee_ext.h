@@ -55,6 +55,10 @@ void EmDeeX_set_kernel_timing( tEmDee md, int enabled );
 /* Block until all queued device work of this system has finished. */
 void EmDeeX_synchronize( tEmDee md );
 
+/* The CUDA stream (cudaStream_t) all kernels of this system are launched on, so that a client can record its
+   own events around a region or order its own work after the library's. */
+void* EmDeeX_stream( tEmDee md );
+
 /* DFMA microbenchmark on the current device: measured FP64 FMA throughput in TFLOP/s (the FP64
    roofline denominator; MEASURED_PEAKS.json carries only HBM and bf16 figures). */
 double EmDeeX_measure_fp64_tflops( void );

@@ -58,6 +58,7 @@ long long Engine::pair_count() { return 0; }
 void Engine::update_list_stats(int, double) {}
 long long Engine::download_pairs(int*, long long) { return 0; }
 void Engine::synchronize() {}
+void* Engine::stream_handle() { return nullptr; }
 void Engine::comm_init(int, int, const void*) {}
 void slab_range(int M, int rank, int world, int& z0, int& z1) {
   z0 = (int)(((long long)rank * M) / world);
