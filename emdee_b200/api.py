@@ -227,6 +227,14 @@ class System:
         return out[0] if option == "box" else out
 
     # dynamics -------------------------------------------------------------------------------
+    def rdf(self, bins: int, Rc: float, itype: Sequence[int], jtype: Sequence[int]) -> np.ndarray:
+        """EmDee_rdf: g[pair, bin] from the current neighbor list (reference src/EmDeeCode.f90:1281-1395)."""
+        it = np.ascontiguousarray(itype, dtype=np.int32)
+        jt = np.ascontiguousarray(jtype, dtype=np.int32)
+        g = np.zeros((len(it), bins), dtype=np.float64)
+        self.lib.EmDee_rdf(self.md, bins, float(Rc), len(it), _iptr(it), _iptr(jt), _dptr(g))
+        return g
+
     def random_momenta(self, kT: float, adjust: bool, seed: int):
         self.lib.EmDee_random_momenta(C.byref(self.md), float(kT), bool(adjust), int(seed))
 

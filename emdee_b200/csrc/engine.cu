@@ -1722,6 +1722,56 @@ __global__ void __launch_bounds__(TPB) k_brick_list_walk(BrickArgs k, int mode, 
   if (mode == 1 && n) atomicAdd(counter, n);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pair-distance histogram over the resident list (reference count_pairs, src/EmDeeCode.f90:1346-1388).
+// One thread per real entry walks its row of the FULL list, so every pair is met twice (host halves the
+// integer counts). Block-private shared-memory histogram when it fits, flushed with 64-bit global atomics:
+// integer sums, so the result does not depend on the order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_rdf(int Next, int cap, int nt, int bins, int nsym, double Rc2s, double binsByRcS,
+                                             const double4* __restrict__ pos, const int* __restrict__ nbr,
+                                             const int* __restrict__ nbrCount, const int* __restrict__ sType,
+                                             const unsigned short* __restrict__ pairSym, int use_smem,
+                                             unsigned long long* __restrict__ hist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned int* local = reinterpret_cast<unsigned int*>(smem_raw);
+  const int nbin = bins * nsym;
+  if (use_smem) {
+    for (int q = threadIdx.x; q < nbin; q += blockDim.x) local[q] = 0u;
+    __syncthreads();
+  }
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < Next) {
+    const int cnt = nbrCount[e];   // ghosts hold 0
+    if (cnt > 0) {
+      const int it = sType[e];
+      const double4 pi = pos[e];
+      const int* row = nbr + ((size_t)(e >> 5) * cap) * TILE + (e & 31);
+      for (int k = 0; k < cnt; ++k) {
+        const int f = row[(size_t)k * TILE];
+        const int sym = pairSym[it * nt + sType[f]];
+        if (sym == 0) continue;
+        const double4 pj = ld_pos(pos + f);
+        const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 < Rc2s) {
+          const int bin = (int)(sqrt(r2) * binsByRcS);
+          if (bin < bins) {
+            const int slot = (sym - 1) * bins + bin;
+            if (use_smem) atomicAdd(&local[slot], 1u);
+            else atomicAdd(&hist[slot], 1ull);
+          }
+        }
+      }
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < nbin; q += blockDim.x)
+      if (local[q] != 0u) atomicAdd(&hist[q], (unsigned long long)local[q]);
+  }
+}
+
 // ---- FP64 issue-rate microbenchmark (roofline denominator that MEASURED_PEAKS.json does not carry) ----
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -2776,6 +2826,36 @@ long long Engine::download_pairs(int* pairs, long long capacity) {
     CUDA_CHECK(cudaMemcpy(pairs, dp.p, 2 * (size_t)got * sizeof(int), cudaMemcpyDeviceToHost));
   dp.release();
   return pairs == nullptr ? (long long)n : got;
+}
+
+void Engine::rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_scaled,
+                 const std::vector<unsigned short>& pairSym, int nsym, std::vector<long long>& counts) {
+  Impl& s = *d_;
+  if (!s.list_valid) fatal("radial distribution calculation", "no neighbor list has been built yet");
+  if (s.world > 1) fatal("radial distribution calculation", "not available on a multi-GPU system yet");
+  if (s.use_bricks) fatal("radial distribution calculation", "not available with EMDEE_BRICKS");
+  const size_t nbin = (size_t)bins * nsym;
+  DBuf<unsigned long long> hist;
+  DBuf<unsigned short> sym;
+  hist.ensure(nbin);
+  sym.ensure(pairSym.size());
+  CUDA_CHECK(cudaMemsetAsync(hist.p, 0, nbin * sizeof(unsigned long long), s.stream));
+  CUDA_CHECK(cudaMemcpyAsync(sym.p, pairSym.data(), pairSym.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, s.stream));
+  // the list is walked with the CURRENT coordinates (the reference rescales me%R on entry, EmDeeCode.f90:1324)
+  k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
+  const int use_smem = nbin * sizeof(unsigned int) <= 40 * 1024 ? 1 : 0;
+  k_rdf<<<nblocks(s.Next), TPB, use_smem ? nbin * sizeof(unsigned int) : 0, s.stream>>>(
+      s.Next, s.cap, s.nt, bins, nsym, Rc2_scaled, bins_by_Rc_scaled, s.pos.p, s.nbr.p, s.nbrCount.p, s.sType.p, sym.p,
+      use_smem, hist.p);
+  stats_.launches += 2;
+  std::vector<unsigned long long> h(nbin);
+  CUDA_CHECK(cudaMemcpyAsync(h.data(), hist.p, nbin * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  CUDA_CHECK(cudaGetLastError());
+  counts.resize(nbin);
+  for (size_t q = 0; q < nbin; ++q) counts[q] = (long long)(h[q] / 2ull);   // full list: each pair met twice
+  hist.release();
+  sym.release();
 }
 
 double measure_fp64_fma_tflops() {

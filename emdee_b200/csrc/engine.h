@@ -78,6 +78,11 @@ class Engine {
   long long pair_count();
   void update_list_stats(int layer0, double Lbox);   // fills list_entries / interacting
   long long download_pairs(int* pairs, long long capacity);
+  // Pair-distance histogram over the resident neighbor list (reference EmDee_rdf, src/EmDeeCode.f90:1346-1388).
+  // pairSym[it*ntypes + jt] = 0 (pair not wanted) or 1-based packed symmetric index; counts[(sym-1)*bins + bin]
+  // comes back with every pair counted ONCE.
+  void rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_scaled, const std::vector<unsigned short>& pairSym,
+           int nsym, std::vector<long long>& counts);
   void set_kernel_timing(bool on) { timing_ = on; }
   void synchronize();
   void* stream_handle();   // the cudaStream_t every kernel of this system is launched on

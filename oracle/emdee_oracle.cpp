@@ -1673,7 +1673,82 @@ void EmDee_compute_forces(tEmDee* md) {
   md->Time.Total = time - me->startTime;
 }
 
-void EmDee_rdf(tEmDee, int, double, int, int*, int*, double*) { out_of_scope("radial distribution calculation"); }
+// reference src/EmDeeCode.f90:1281-1395 (pair counting over the EXISTING half neighbor list, no rebuild) and
+// src/math.f90:695-702 (symm1D). Restated literally, including: pairs the list does not hold (excluded, same
+// body, non-interacting types, beyond Rc+skin) are never counted; `pairOn(itype,jtype) = .true.` with vector
+// subscripts switches on every (itype(k), jtype(l)) combination; the `middle` split is used when
+// Rc < 1.0001*InRc. One guard added: a distance that rounds onto Rc exactly would index bin `bins+1`
+// (out of bounds in the reference); it is dropped here.
+void EmDee_rdf(tEmDee md, int bins, double Rc, int pairs, int* itype, int* jtype, double* g) {
+  System* me = sys(md);
+  const char* task = "radial distribution calculation";
+  for (int k = 0; k < pairs; ++k)
+    if (itype[k] < 1 || itype[k] > me->ntypes || jtype[k] < 1 || jtype[k] > me->ntypes)
+      error(task, "at least one provided type index is out of range");
+  auto symm1D = [](int i, int j) {
+    const int x = std::min(i, j) - 1, y = std::max(i, j) - 1;
+    return x + (y + 1) * y / 2 + 1;
+  };
+  const int nt = me->ntypes;
+  std::vector<char> hasPair(nt + 1, 0), pairOn((size_t)(nt + 1) * (nt + 1), 0);
+  int maxtype = 0;
+  for (int k = 0; k < pairs; ++k) {
+    hasPair[itype[k]] = hasPair[jtype[k]] = 1;
+    maxtype = std::max(maxtype, std::max(itype[k], jtype[k]));
+    for (int l = 0; l < pairs; ++l) {
+      pairOn[(size_t)itype[k] * (nt + 1) + jtype[l]] = 1;
+      pairOn[(size_t)jtype[l] * (nt + 1) + itype[k]] = 1;
+    }
+  }
+  const int nsym = symm1D(maxtype, maxtype);
+  std::vector<long long> pairCount((size_t)bins * nsym, 0);
+  const double invL = 1.0 / me->Lbox, invL2 = invL * invL;
+  const int N = me->natoms;
+  std::vector<double> Rs(3 * (size_t)N);
+  for (size_t q = 0; q < Rs.size(); ++q) Rs[q] = invL * me->R[q];
+  const double Rc2 = Rc * Rc * invL2;
+  const double binsByRc = bins / (Rc * invL);
+  const bool useMiddle = Rc < 1.0001 * me->InRc;
+  for (int thread = 1; thread <= me->nthreads; ++thread) {   // serial over the per-thread lists: integer counts
+    List& neighbor = me->neighbor[thread - 1];
+    const std::vector<int>& last = useMiddle ? neighbor.middle : neighbor.last;
+    const int tfirst = me->threadCell.first[thread - 1], tlast = me->threadCell.last[thread - 1];
+    if (tlast < tfirst) continue;
+    for (int k = me->cellAtom.first[tfirst - 1]; k <= me->cellAtom.last[tlast - 1]; ++k) {
+      const int i = me->cellAtom.item[k - 1];
+      const int it = me->atomType[i - 1];
+      if (!hasPair[it]) continue;
+      const double* Ri = &Rs[3 * (size_t)(i - 1)];
+      for (int m = neighbor.first[i - 1]; m <= last[i - 1]; ++m) {
+        const int j = neighbor.item[m - 1];
+        const int jt = me->atomType[j - 1];
+        if (!pairOn[(size_t)it * (nt + 1) + jt]) continue;
+        const double* Rj = &Rs[3 * (size_t)(j - 1)];
+        const double d0 = pbc(Ri[0] - Rj[0]), d1 = pbc(Ri[1] - Rj[1]), d2 = pbc(Ri[2] - Rj[2]);
+        const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+        if (r2 < Rc2) {
+          const int bin = (int)(std::sqrt(r2) * binsByRc) + 1;
+          if (bin <= bins) pairCount[(size_t)(symm1D(it, jt) - 1) * bins + (bin - 1)] += 1;
+        }
+      }
+    }
+  }
+  const double Pi4_3 = 4.188790204786391;
+  const double w = Rc * invL / bins;
+  const double shell0 = Pi4_3 * (w * w * w);
+  std::vector<long long> count(maxtype + 1, 0);
+  for (int a = 0; a < N; ++a)
+    if (me->atomType[a] <= maxtype) count[me->atomType[a]] += 1;
+  for (int p = 0; p < pairs; ++p) {
+    const int i = itype[p], j = jtype[p];
+    const double NiNj = (double)(count[i] * count[j]);
+    for (int b = 1; b <= bins; ++b) {
+      double rdf = (double)pairCount[(size_t)(symm1D(i, j) - 1) * bins + (b - 1)] / shell0;
+      rdf = rdf / (double)(3 * b * (b - 1) + 1);
+      g[(size_t)p * bins + (b - 1)] = (i == j) ? 2.0 * rdf / NiNj : rdf / NiNj;
+    }
+  }
+}
 
 // ---- modifiers (src/modelClass_nonbonded.f90:83-241) ---------------------------------------------
 static void* wrap_modifier(void* model, int modifier, double skin, bool has_skin, const char* task) {

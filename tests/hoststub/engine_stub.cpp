@@ -58,6 +58,9 @@ long long Engine::pair_count() { return 0; }
 void Engine::update_list_stats(int, double) {}
 long long Engine::download_pairs(int*, long long) { return 0; }
 void Engine::synchronize() {}
+void Engine::rdf(double, int bins, double, double, const std::vector<unsigned short>&, int nsym, std::vector<long long>& counts) {
+  counts.assign((size_t)bins * nsym, 0);
+}
 void* Engine::stream_handle() { return nullptr; }
 void Engine::comm_init(int, int, const void*) {}
 void slab_range(int M, int rank, int world, int& z0, int& z1) {
