@@ -34,6 +34,24 @@ def oracle(fast: bool = False) -> api.EmDeeLib:
     return _libs[path]
 
 
+HOSTSTUB = os.path.join(ROOT, "tests", "_build", "libemdee_hoststub.so")
+
+
+def hoststub() -> api.EmDeeLib:
+    """The product's host shim (emdee_b200/csrc/abi.cpp, unchanged) linked against a device-free stub of the
+    engine (tests/hoststub/engine_stub.cpp): host-side semantics without a GPU. Test infrastructure only."""
+    src = [os.path.join(ROOT, "emdee_b200", "csrc", "abi.cpp"), os.path.join(ROOT, "tests", "hoststub", "engine_stub.cpp")]
+    deps = src + [os.path.join(ROOT, "emdee_b200", "csrc", h) for h in ("engine.h", "nb_math.h")]
+    if HOSTSTUB not in _libs:
+        os.makedirs(os.path.dirname(HOSTSTUB), exist_ok=True)
+        if not os.path.exists(HOSTSTUB) or any(os.path.getmtime(f) > os.path.getmtime(HOSTSTUB) for f in deps):
+            subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                                   "-Wl,-Bsymbolic", "-Wl,--no-undefined", "-I" + os.path.join(ROOT, "include"),
+                                   "-x", "c++", *src, "-o", HOSTSTUB])
+        _libs[HOSTSTUB] = api.EmDeeLib(HOSTSTUB)
+    return _libs[HOSTSTUB]
+
+
 def product() -> api.EmDeeLib:
     return api.load()
 

@@ -10,29 +10,18 @@ Q3, Q3b): reference src/EmDeeCode.f90:309-520, src/EmDeeData.f90:193-264, src/mo
 src/modelClass_pair.f90:60-141.
 """
 import ctypes as C
-import os
-import subprocess
-
 import numpy as np
 import pytest
 
-from common import ROOT, api, oracle
-
-STUB = os.path.join(ROOT, "tests", "_build", "libemdee_hoststub.so")
-SRC = [os.path.join(ROOT, "emdee_b200", "csrc", "abi.cpp"), os.path.join(ROOT, "tests", "hoststub", "engine_stub.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "emdee_b200", "csrc", h) for h in ("engine.h", "nb_math.h")]
+import common as cm
+from common import api, oracle
 
 _dp = C.POINTER(C.c_double)
 
 
 @pytest.fixture(scope="module")
 def stub():
-    os.makedirs(os.path.dirname(STUB), exist_ok=True)
-    if not os.path.exists(STUB) or any(os.path.getmtime(f) > os.path.getmtime(STUB) for f in DEPS):
-        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-Wl,-Bsymbolic", "-Wl,--no-undefined", "-I" + os.path.join(ROOT, "include"),
-                               "-x", "c++", *SRC, "-o", STUB])
-    lib = api.EmDeeLib(STUB)
+    lib = cm.hoststub()
     lib.dump = lib._dll.EmDeeStub_dump_tables
     lib.dump.restype = C.c_int
     lib.dump.argtypes = [C.c_int, _dp, C.c_int]
