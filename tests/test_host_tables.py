@@ -223,3 +223,41 @@ def test_random_momenta_stream(stub, adjust):
     else:
         assert np.array_equal(Pa, Pb)
     assert Ka == pytest.approx(Kb, rel=1e-13)
+
+
+def test_struct_flags_follow_the_reference_state_machine(stub):
+    """tEmDee bookkeeping the host shim owns (reference src/EmDeeCode.f90:820-925, 1024-1065, 1215-1277):
+    DoF / RotDoF, Energy%UpToDate = Options%Compute after a force computation, invalidation on uploads, kinetic
+    flags, layer switching. The stub engine returns zero forces, so only the flags and counters are compared."""
+    N = 60
+    rng = np.random.default_rng(2)
+    L = 8.0
+    R = rng.uniform(0, L, (N, 3))
+
+    def trace(lib):
+        out = []
+        s = lib.system(1, 2, 2.5, 0.5, N, None, None, None)
+        snap = lambda tag: out.append((tag, s.md.DoF, s.md.RotDoF, bool(s.md.Energy.UpToDate), bool(s.md.Kinetic.UpToDate),
+                                       bool(s.md.Options.Compute), bool(s.md.Options.Translate), bool(s.md.Options.Rotate)))
+        snap("created")
+        s.set_pair_multimodel(1, 1, [lib.EmDee_pair_lj_cut(1.0, 1.0), lib.EmDee_pair_lj_cut(0.5, 1.0)], [0.0, 0.0])
+        s.upload("box", [L]); snap("box")
+        s.upload("coordinates", R); snap("initialised")
+        s.random_momenta(1.0, True, 5); snap("momenta")
+        s.upload("coordinates", R * 0.999); snap("coordinates again")
+        s.compute_forces(); snap("computed")
+        s.md.Options.Compute = False
+        s.compute_forces(); snap("computed, virial only")
+        s.boost(1.0, 0.0, 0.001); snap("boost, virial only")
+        s.md.Options.Compute = True
+        s.boost(1.0, 0.0, 0.001); snap("boost")
+        s.displace(1.0, 0.0, 0.001); snap("displace")
+        s.switch_model_layer(2); snap("layer 2")
+        s.upload("box", [L * 1.01]); snap("box again")
+        s.switch_model_layer(1); snap("layer 1")
+        s.upload("momenta", np.zeros((N, 3))); snap("momenta upload")
+        s.finalize()
+        return out
+
+    a, b = trace(stub), trace(oracle_lib())
+    assert a == b, [(x, y) for x, y in zip(a, b) if x != y]
