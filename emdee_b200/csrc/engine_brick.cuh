@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(TPB) k_brick_setup(BrickGrid g, const int* __r
 }
 
 // ---- mbarrier + bulk-copy helpers -------------------------------------------------------------------
+#if defined(__CUDACC__)
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -113,6 +114,21 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
       : "memory");
   return ok != 0;
 }
+#else   // tests/cusim emulation build: the copy is synchronous; the barrier word counts outstanding bytes
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int) { *bar = 0ull; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  *bar = ((*bar + bytes) & 0xffffffffull) | (1ull << 32);   // low word: bytes still expected; bit 32: arrived
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+  std::memcpy(dst, src, bytes);
+  *bar = (*bar & ~0xffffffffull) | ((*bar - bytes) & 0xffffffffull);
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned int) {
+  if (*bar == (1ull << 32)) return true;
+  cusim::yield();
+  return false;
+}
+#endif
 
 // stage `elem_bytes`-sized records of all runs of a brick into shared memory (one bulk copy per run)
 __device__ __forceinline__ void brick_stage(const BrickDesc& d, const int* sSegG, const int* sSegL, const void* src,

@@ -52,9 +52,13 @@ inline int nblocks(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tp
 // throw away the position lines the other resident blocks are still gathering from; measured: L1 hit rate
 // 75% -> 36% with a plain __threadfence() per block). Only the last block pays a full fence.
 __device__ __forceinline__ unsigned int take_ticket(unsigned int* ticket) {
+#if defined(__CUDACC__)
   unsigned int old;
   asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ticket) : "memory");
   return old;
+#else   // host-side kernel emulation used by tests/cusim (never part of the product build)
+  return atomicAdd(ticket, 1u);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -52,6 +52,17 @@ def hoststub() -> api.EmDeeLib:
     return _libs[HOSTSTUB]
 
 
+def emulated() -> api.EmDeeLib:
+    """The product's sources (abi.cpp, engine.cu, engine_*.cuh) compiled for the HOST against the CUDA
+    execution-model emulator tests/cusim/cusim.h: kernel logic without a GPU. Test infrastructure only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cusim"))
+    import build as cusim_build
+    path = cusim_build.build()
+    if path not in _libs:
+        _libs[path] = api.EmDeeLib(path)
+    return _libs[path]
+
+
 def product() -> api.EmDeeLib:
     return api.load()
 

@@ -1,0 +1,68 @@
+"""The GPU parity tests, run on the CPU through the CUDA execution-model emulator (tests/cusim).
+
+The emulated library is the product's own abi.cpp + engine.cu + engine_*.cuh compiled for the host (threads of a
+block as fibers; barriers, shuffles, ballots, atomics and shared memory emulated). Every test below is the SAME
+function the `-m gpu` run executes on the B200 (tests/test_gpu_parity.py and friends), with `common.product`
+pointed at the emulated library, so the kernels' logic -- indexing, loop bounds, masks, reductions, the
+criterion, the opt-in paths -- is checked against the oracle without a device. What this cannot show:
+performance, memory-model races, PTX-level behaviour (the few inline-PTX helpers have host stand-ins).
+The product itself still refuses to run without a GPU (tests/test_abi_surface.py).
+"""
+import itertools
+import os
+
+import pytest
+
+import common as cm
+import test_gpu_experimental as t_exp
+import test_gpu_parity as t_par
+import test_zz_box_rescale as t_box
+import test_zz_single_type_coulomb as t_stc
+
+
+def _cases(module, skip=()):
+    """(id, function, kwargs) for every test function of a GPU test module, parametrize marks expanded."""
+    out = []
+    for name in sorted(dir(module)):
+        fn = getattr(module, name)
+        if not name.startswith("test_") or not callable(fn) or name in skip:
+            continue
+        marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+        axes = []
+        for m in marks:
+            names = [n.strip() for n in m.args[0].split(",")] if isinstance(m.args[0], str) else list(m.args[0])
+            vals = [v if isinstance(v, (tuple, list)) and len(names) > 1 else (v,) for v in m.args[1]]
+            axes.append([dict(zip(names, v)) for v in vals])
+        for combo in itertools.product(*axes) if axes else [()]:
+            kw = {}
+            for d in combo:
+                kw.update(d)
+            ident = name + ("[" + "-".join(str(getattr(v, "__name__", v)) for v in kw.values()) + "]" if kw else "")
+            out.append(pytest.param(fn, kw, id=f"{module.__name__}::{ident}"))
+    return out
+
+
+# test_kernels_actually_ran reads device statistics whose launch counts the emulator also keeps: included.
+# test_reference_kat_replay_on_gpu (100 steps x 3 models) is covered here by one model to bound the run time.
+CASES = (_cases(t_par, skip=("test_brick_path_opt_in", "test_duo_path_opt_in"))
+         + _cases(t_box, skip=("test_scenario_on_the_oracle_builds",))
+         + _cases(t_stc)
+         + _cases(t_exp)
+         + [pytest.param(t_par.test_brick_path_opt_in, {}, id="test_gpu_parity::test_brick_path_opt_in"),
+            pytest.param(t_par.test_duo_path_opt_in, {}, id="test_gpu_parity::test_duo_path_opt_in")])
+
+
+@pytest.fixture(autouse=True)
+def _use_emulated_library(monkeypatch):
+    lib = cm.emulated()
+    monkeypatch.setattr(cm, "product", lambda: lib)
+    monkeypatch.setenv("EMDEE_TEST_EXPERIMENTAL", "1")
+    monkeypatch.setenv("EMDEE_TEST_REPLAY_STEPS", "20")
+
+
+@pytest.mark.parametrize("fn,kwargs", CASES)
+def test_on_emulator(fn, kwargs, monkeypatch):
+    import inspect
+    if "monkeypatch" in inspect.signature(fn).parameters:
+        kwargs = dict(kwargs, monkeypatch=monkeypatch)
+    fn(**kwargs)
