@@ -150,8 +150,10 @@ struct NcclApi {
 NcclApi& nccl() {
   static NcclApi api;
   if (api.handle == nullptr) {
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    // EMDEE_NCCL_LIB: explicit path (a site's own NCCL build; the test-suite's shared-memory stand-in)
+    const char* names[] = {std::getenv("EMDEE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
+      if (n == nullptr || *n == '\0') continue;
       api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (api.handle) break;
     }

@@ -1,0 +1,39 @@
+"""The multi-GPU parity script (tests/mgpu_check.py, the one `-m gpu` runs under torchrun on 2 and 4 B200s), run
+on the CPU: one process per rank, kernels through the execution-model emulator (tests/cusim/cusim.h),
+collectives through a shared-memory stand-in for NCCL (tests/cusim/fake_nccl.cpp) that the engine loads via
+EMDEE_NCCL_LIB. Covers what hangs or corrupts real multi-GPU runs: slab ownership, per-step halo exchange,
+neighbor-only migration at rebuilds, the two-phase distributed rebuild criterion, collective downloads -- with
+3 ranks as the first case where the up and down neighbors are different ranks. A collective that not every rank
+enters is reported by the stand-in after FAKE_NCCL_TIMEOUT seconds instead of hanging.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import common as cm
+
+WORLDS = [2, 3, 4, 8]
+
+
+@pytest.fixture(scope="module")
+def libs():
+    sys.path.insert(0, os.path.join(cm.ROOT, "tests", "cusim"))
+    import build as cusim_build
+    cusim_build.build()
+    return cusim_build.build_fake_nccl()
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_slab_decomposition_on_emulator(world, libs):
+    env = dict(os.environ, EMDEE_MGPU_EMULATED="1", EMDEE_NCCL_LIB=libs, FAKE_NCCL_TIMEOUT="120", EMDEE_QUIET="1",
+               OMP_NUM_THREADS="1")
+    if world >= 6:
+        env["EMDEE_MGPU_NCELL"] = "21"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world),
+           os.path.join(cm.ROOT, "tests", "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "[mgpu] ALL OK" in r.stdout
