@@ -220,6 +220,28 @@ inline void fiber_main() {
 
 constexpr size_t STACK_BYTES = 256 * 1024;
 
+// CUSIM_ORDER: unset/"forward" = threads of a block take turns in index order; "reverse"; "random[:seed]" = a new
+// random order every scheduling round (results must not depend on it: anything else is a missing barrier)
+inline unsigned long long& rng_state() { static unsigned long long s = 88172645463325252ull; return s; }
+inline unsigned long long next_random() {
+  unsigned long long& x = rng_state();
+  x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+  return x;
+}
+inline int schedule_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("CUSIM_ORDER");
+    mode = 0;
+    if (e != nullptr && std::strncmp(e, "reverse", 7) == 0) mode = 1;
+    if (e != nullptr && std::strncmp(e, "random", 6) == 0) {
+      mode = 2;
+      if (e[6] == ':') rng_state() = 0x9e3779b97f4a7c15ull * (std::strtoull(e + 7, nullptr, 10) + 1);
+    }
+  }
+  return mode;
+}
+
 inline unsigned char* stack_pool(size_t nthreads) {
   static std::vector<unsigned char> pool;
   if (pool.size() < nthreads * STACK_BYTES + 64) pool.resize(nthreads * STACK_BYTES + 64);
@@ -238,9 +260,17 @@ inline void launch(F fn, dim3 grid, dim3 block, size_t smem = 0, cudaStream_t = 
   block_dim() = block;
   b.body = &body;
   b.dyn = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 127) & ~(uintptr_t)127);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
+  // blocks run one after the other; CUSIM_ORDER also permutes WHICH block goes when (grid-wide finishes must not
+  // care which block happens to be the last one)
+  const size_t nblocks_total = (size_t)grid.x * grid.y * grid.z;
+  std::vector<size_t> block_order(nblocks_total);
+  for (size_t q = 0; q < nblocks_total; ++q) block_order[q] = q;
+  if (schedule_mode() == 1) std::reverse(block_order.begin(), block_order.end());
+  if (schedule_mode() >= 2)
+    for (size_t q = nblocks_total - 1; q > 0; --q) std::swap(block_order[q], block_order[next_random() % (q + 1)]);
+  for (size_t q = 0; q < nblocks_total; ++q) {
+        const size_t lin = block_order[q];
+        const unsigned bx = (unsigned)(lin % grid.x), by = (unsigned)((lin / grid.x) % grid.y), bz = (unsigned)(lin / ((size_t)grid.x * grid.y));
         block_idx() = dim3(bx, by, bz);
         b.fibers.assign(nthreads, Fiber());
         b.warps.assign((nthreads + 31) / 32, Warp());
@@ -266,9 +296,16 @@ inline void launch(F fn, dim3 grid, dim3 block, size_t smem = 0, cudaStream_t = 
           for (int l = 0; l < 32; ++l)
             if (w * 32 + l >= nthreads) b.warps[w].alive[l] = false;
         long long idle_rounds = 0;
+        std::vector<size_t> order(nthreads);
+        for (size_t t = 0; t < nthreads; ++t) order[t] = t;
+        const int mode = schedule_mode();
+        if (mode == 1) std::reverse(order.begin(), order.end());
         while (b.live > 0) {
           bool ran = false;
-          for (size_t t = 0; t < nthreads; ++t) {
+          if (mode >= 2)   // a fresh random interleaving every round: shakes out missing barriers
+            for (size_t t = nthreads - 1; t > 0; --t) std::swap(order[t], order[next_random() % (t + 1)]);
+          for (size_t k = 0; k < nthreads; ++k) {
+            const size_t t = order[k];
             Fiber& f = b.fibers[t];
             if (f.done || (f.wait != nullptr && *f.wait == f.wait_val)) continue;
             b.cur = &f;

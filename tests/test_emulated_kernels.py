@@ -66,3 +66,17 @@ def test_on_emulator(fn, kwargs, monkeypatch):
     if "monkeypatch" in inspect.signature(fn).parameters:
         kwargs = dict(kwargs, monkeypatch=monkeypatch)
     fn(**kwargs)
+
+
+@pytest.mark.parametrize("order", ["reverse", "random:11"])
+def test_results_do_not_depend_on_thread_interleaving(order):
+    """The emulator can run the threads of a block (and the blocks of a grid) in reverse or in a fresh random order
+    every scheduling round (CUSIM_ORDER). Parity must hold regardless: a failure here means a missing barrier or a
+    grid-wide finish that depends on which block comes last."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CUSIM_ORDER=order)
+    sel = "two_types or dynamics_with_rebuilds or kat_replay_on_gpu or spce_single_point or brick or duo or rdf or degenerate"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        f"test_on_emulator and ({sel})"], capture_output=True, text=True, env=env, cwd=cm.ROOT, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
