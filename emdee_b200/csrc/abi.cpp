@@ -970,11 +970,10 @@ void EmDee_compute_forces(tEmDee* md) {   // src/EmDeeCode.f90:1215-1277
 // `middle` split of its r^2-sorted half list when Rc < 1.0001*InRc; the full list kept here has no such split
 // and the current-distance test r < Rc selects the same pairs while the list is valid; (2) N(i)*N(j) is formed
 // in 64 bits (the reference's default-integer product overflows above ~46k atoms per type).
-// Gated by EMDEE_EXPERIMENTAL_RDF=1 until the kernel has been confirmed on a GPU; without it the call aborts as
-// every other out-of-scope entry point does.
+// The counting kernel was written after the last GPU session of round 1: its logic is verified on the CPU through
+// the kernel emulator (tests/test_emulated_kernels.py); its GPU parity test is tests/test_zz_rdf.py.
 void EmDee_rdf(tEmDee md, int bins, double Rc, int pairs, int* itype, int* jtype, double* g) {
   const char* task = "radial distribution calculation";
-  if (std::getenv("EMDEE_EXPERIMENTAL_RDF") == nullptr) unsupported(task);
   System* me = sys(md);
   for (int k = 0; k < pairs; ++k)
     if (!ranged({itype[k], jtype[k]}, me->ntypes)) error(task, "at least one provided type index is out of range");

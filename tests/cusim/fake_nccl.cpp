@@ -47,7 +47,7 @@ struct Comm {
   Header* hdr = nullptr;
   unsigned char* base = nullptr;
   size_t total = 0;
-  char name[80];
+  char name[128];
   unsigned char* slot(int r) const { return base + 4096 + (size_t)r * SLOT_BYTES; }
   Mail* mail(int src, int dst) const {
     return reinterpret_cast<Mail*>(base + 4096 + (size_t)nranks * SLOT_BYTES + ((size_t)src * nranks + dst) * (MAIL_BYTES + 64));

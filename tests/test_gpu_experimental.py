@@ -56,25 +56,3 @@ def test_cluster2_path(monkeypatch):
     entry of the duo's union row (k_merge_duos + k_transpose_rows + k_pair_forces_cluster2)."""
     monkeypatch.setenv("EMDEE_CLUSTER2", "1")
     _all_model_families()
-
-
-def test_rdf_matches_oracle(monkeypatch):
-    """EMDEE_EXPERIMENTAL_RDF=1: EmDee_rdf from the resident list (k_rdf) against the oracle's restatement of
-    reference src/EmDeeCode.f90:1281-1395: integer pair counts, so g must agree to rounding of the normalisation."""
-    monkeypatch.setenv("EMDEE_EXPERIMENTAL_RDF", "1")
-    sp, so = both(lambda lib: _two_type_system(lib, COUL_VARIANTS["coul_sf"]))
-    for s in (sp, so):
-        s.random_momenta(0.9, True, 777)
-    for _ in range(12):                      # a few steps: the list goes stale (no rebuild) and is then rebuilt
-        for s in (sp, so):
-            s.boost(1.0, 0.0, 0.002)
-            s.displace(1.0, 0.0, 0.004)
-            s.boost(1.0, 0.0, 0.002)
-        gp = sp.rdf(50, 2.5, [1, 1, 2], [1, 2, 2])
-        go = so.rdf(50, 2.5, [1, 1, 2], [1, 2, 2])
-        assert gp.shape == go.shape and np.allclose(gp, go, rtol=1e-12, atol=0.0)
-    gp, go = sp.rdf(2000, 2.85, [2], [1]), so.rdf(2000, 2.85, [2], [1])      # many bins, beyond Rc into the skin
-    assert np.allclose(gp, go, rtol=1e-12, atol=0.0) and gp.sum() > 0
-    gp, go = sp.rdf(20000, 2.0, [1, 2], [1, 2]), so.rdf(20000, 2.0, [1, 2], [1, 2])   # histogram too big for smem
-    assert np.allclose(gp, go, rtol=1e-12, atol=0.0)
-    sp.finalize(), so.finalize()
