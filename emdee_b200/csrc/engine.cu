@@ -1098,7 +1098,6 @@ void Engine::rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_sca
                  const std::vector<unsigned short>& pairSym, int nsym, std::vector<long long>& counts) {
   Impl& s = *d_;
   if (!s.list_valid) fatal("radial distribution calculation", "no neighbor list has been built yet");
-  if (s.world > 1) fatal("radial distribution calculation", "not available on a multi-GPU system yet");
   if (s.use_bricks) fatal("radial distribution calculation", "not available with EMDEE_BRICKS");
   const size_t nbin = (size_t)bins * nsym;
   DBuf<unsigned long long> hist;
@@ -1107,13 +1106,17 @@ void Engine::rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_sca
   sym.ensure(pairSym.size());
   CUDA_CHECK(cudaMemsetAsync(hist.p, 0, nbin * sizeof(unsigned long long), s.stream));
   CUDA_CHECK(cudaMemcpyAsync(sym.p, pairSym.data(), pairSym.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, s.stream));
-  // the list is walked with the CURRENT coordinates (the reference rescales me%R on entry, EmDeeCode.f90:1324)
+  // the list is walked with the CURRENT coordinates (the reference rescales me%R on entry, EmDeeCode.f90:1324);
+  // on several GPUs that includes the neighbors' halo atoms
+  halo_exchange(s);
   k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
   const int use_smem = nbin * sizeof(unsigned int) <= 40 * 1024 ? 1 : 0;
   k_rdf<<<nblocks(s.Next), TPB, use_smem ? nbin * sizeof(unsigned int) : 0, s.stream>>>(
       s.Next, s.cap, s.nt, bins, nsym, Rc2_scaled, bins_by_Rc_scaled, s.pos.p, s.nbr.p, s.nbrCount.p, s.sType.p, sym.p,
       use_smem, hist.p);
   stats_.launches += 2;
+  // slab decomposition: every rank walks the rows of the atoms it owns, so a pair is met twice over all ranks
+  if (s.world > 1) NCCL_CHECK(nccl().AllReduce(hist.p, hist.p, nbin, ncclUint64, ncclSum, s.comm, s.stream));
   std::vector<unsigned long long> h(nbin);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), hist.p, nbin * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));

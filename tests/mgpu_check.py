@@ -111,6 +111,15 @@ def main():
         Rp = sp.download("coordinates")
         if rank == 0:
             assert np.abs(Rp - so.download("coordinates")).max() < 1e-10
+        if not charged:
+            # EmDee_rdf over the slab-decomposed list (collective: histogram all-reduced). The two trajectories differ
+            # at rounding level after 40 steps, so a pair sitting on a bin edge may move one bin: compare counts
+            gp = sp.rdf(40, 2.5, [1], [1])
+            if rank == 0:
+                go = so.rdf(40, 2.5, [1], [1])
+                assert np.abs(gp - go).max() <= 2e-3 * np.abs(go).max(), np.abs(gp - go).max()
+                assert abs(gp.sum() - go.sum()) <= 1e-6 * go.sum()
+                print(f"[mgpu] rdf ok (max |dg| = {np.abs(gp - go).max():.2e})", flush=True)
         sp.finalize()
         if rank == 0:
             so.finalize()
