@@ -120,6 +120,19 @@ def main():
                 assert np.abs(gp - go).max() <= 2e-3 * np.abs(go).max(), np.abs(gp - go).max()
                 assert abs(gp.sum() - go.sum()) <= 1e-6 * go.sum()
                 print(f"[mgpu] rdf ok (max |dg| = {np.abs(gp - go).max():.2e})", flush=True)
+        if not charged:
+            # the host-buffer pattern of bench.py's e2e arm: every step a full set of coordinates comes from the host
+            # (all ranks upload the same array), forces are computed and downloaded (collective)
+            base = Rp.copy()
+            rng = np.random.default_rng(17)
+            for k in range(5):
+                base = base + rng.normal(0.0, 0.05, base.shape)      # large enough to force rebuilds + migration
+                for s in ([sp, so] if rank == 0 else [sp]):
+                    s.upload("coordinates", base)
+                    s.compute_forces()
+                compare(f"lj host-buffer step {k}", sp, so, rank)
+            if rank == 0:
+                assert sp.md.Builds == so.md.Builds
         sp.finalize()
         if rank == 0:
             so.finalize()
