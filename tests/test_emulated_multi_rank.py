@@ -27,6 +27,8 @@ def libs():
 
 @pytest.mark.parametrize("world", WORLDS)
 def test_slab_decomposition_on_emulator(world, libs):
+    if world > 2 * (os.cpu_count() or 1):
+        pytest.skip(f"{world} spinning ranks on {os.cpu_count()} cores")
     env = dict(os.environ, EMDEE_MGPU_EMULATED="1", EMDEE_NCCL_LIB=libs, FAKE_NCCL_TIMEOUT="120", EMDEE_QUIET="1",
                OMP_NUM_THREADS="1")
     if world >= 6:
