@@ -247,6 +247,20 @@ class System:
     def compute_forces(self):
         self.lib.EmDee_compute_forces(C.byref(self.md))
 
+    def verlet_step(self, dt: float):
+        self.lib.EmDee_verlet_step(C.byref(self.md), float(dt))
+
+    def memory_address(self, option: str, shape=None) -> np.ndarray:
+        """EmDee_memory_address: a numpy VIEW of the library's own array (reference src/EmDeeCode.f90:212-235)."""
+        ptr = self.lib.EmDee_memory_address(self.md, option.encode())
+        shape = shape if shape is not None else (self.N, 3)
+        n = int(np.prod(shape))
+        return np.ctypeslib.as_array(C.cast(ptr, _dp), shape=(n,)).reshape(shape)
+
+    def share_phase_space(self, other: "System"):
+        """EmDee_share_phase_space(self, other): `other` gives up its own R, P, bodies and box for `self`'s."""
+        self.lib.EmDee_share_phase_space(self.md, C.byref(other.md))
+
     # extensions -----------------------------------------------------------------------------
     def pairs(self) -> np.ndarray:
         """Neighbor pairs as a lexicographically sorted (npairs, 2) int32 array (0-based)."""

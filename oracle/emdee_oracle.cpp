@@ -35,6 +35,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -562,15 +563,486 @@ double inverse_of_x_plus_ln_x(double y) {
   return x;
 }
 
-// ---- rigid bodies: only what the hot path reads (src/ArBee.f90:29-106) ---------------------------
+// ---- helpers for the rigid-body integrator (src/math.f90:181-226, 428-436) ------------------------
+inline void cross3(const double a[3], const double b[3], double c[3]) {   // src/math.f90:181-185
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double sign1(double x) { return std::signbit(x) ? -1.0 : 1.0; }   // sign(one, x)
+inline int staircase(double x) {   // src/math.f90:428-436
+  return x > 0.0 ? (int)std::ceil(x - 0.5) : (int)std::floor(x + 0.5);
+}
+
+// The four quaternion matrices of src/ArBee.f90:134-176, applied to a vector (Fortran reshape is
+// column-major: column k of B / C multiplies v(k); Bt / Ct are their transposes).
+inline void mulB(const double q[4], const double v[3], double o[4]) {
+  o[0] = -q[1] * v[0] - q[2] * v[1] - q[3] * v[2];
+  o[1] = q[0] * v[0] - q[3] * v[1] + q[2] * v[2];
+  o[2] = q[3] * v[0] + q[0] * v[1] - q[1] * v[2];
+  o[3] = -q[2] * v[0] + q[1] * v[1] + q[0] * v[2];
+}
+inline void mulC(const double q[4], const double v[3], double o[4]) {
+  o[0] = -q[1] * v[0] - q[2] * v[1] - q[3] * v[2];
+  o[1] = q[0] * v[0] + q[3] * v[1] - q[2] * v[2];
+  o[2] = -q[3] * v[0] + q[0] * v[1] + q[1] * v[2];
+  o[3] = q[2] * v[0] - q[1] * v[1] + q[0] * v[2];
+}
+inline void mulBt(const double q[4], const double p[4], double o[3]) {
+  o[0] = -q[1] * p[0] + q[0] * p[1] + q[3] * p[2] - q[2] * p[3];
+  o[1] = -q[2] * p[0] - q[3] * p[1] + q[0] * p[2] + q[1] * p[3];
+  o[2] = -q[3] * p[0] + q[2] * p[1] - q[1] * p[2] + q[0] * p[3];
+}
+inline void mulCt(const double q[4], const double p[4], double o[3]) {
+  o[0] = -q[1] * p[0] + q[0] * p[1] - q[3] * p[2] + q[2] * p[3];
+  o[1] = -q[2] * p[0] + q[3] * p[1] + q[0] * p[2] - q[1] * p[3];
+  o[2] = -q[3] * p[0] - q[2] * p[1] + q[1] * p[2] + q[0] * p[3];
+}
+
+// src/math.f90:189-218 (Shepperd's method); A is row-major here, A[i][j] = A(i+1,j+1)
+void quaternion_from_matrix(const double A[3][3], double Q[4]) {
+  const double a11 = A[0][0], a22 = A[1][1], a33 = A[2][2];
+  const double Q2[4] = {1.0 + a11 + a22 + a33, 1.0 + a11 - a22 - a33, 1.0 - a11 + a22 - a33, 1.0 - a11 - a22 + a33};
+  int imax = 0;
+  for (int k = 1; k < 4; ++k)
+    if (Q2[k] > Q2[imax]) imax = k;   // maxloc: first maximum
+  const double Q2max = Q2[imax], f = std::sqrt(1.0 / Q2max);
+  double v[4];
+  switch (imax) {
+    case 0: v[0] = Q2max; v[1] = A[1][2] - A[2][1]; v[2] = A[2][0] - A[0][2]; v[3] = A[0][1] - A[1][0]; break;
+    case 1: v[0] = A[1][2] - A[2][1]; v[1] = Q2max; v[2] = A[0][1] + A[1][0]; v[3] = A[0][2] + A[2][0]; break;
+    case 2: v[0] = A[2][0] - A[0][2]; v[1] = A[0][1] + A[1][0]; v[2] = Q2max; v[3] = A[1][2] + A[2][1]; break;
+    default: v[0] = A[0][1] - A[1][0]; v[1] = A[0][2] + A[2][0]; v[2] = A[1][2] + A[2][1]; v[3] = Q2max; break;
+  }
+  for (int k = 0; k < 4; ++k) Q[k] = 0.5 * v[k] * f;
+}
+
+// src/math.f90:244-424 (Kopp's analytical 3x3 symmetric eigen-solver: Cardano eigenvalues sorted by
+// decreasing magnitude, eigenvectors from cross products). `m` holds the upper triangle; q[i][k] is
+// component i of eigenvector k, as in the reference's q(i,k).
+void diagonalization(const double m[3][3], double q[3][3], double w[3]) {
+  const double eps = 2.220446049250313e-16, sqrt3 = std::sqrt(3.0);
+  double a[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) a[i][j] = m[i][j];
+  const double de = a[0][1] * a[1][2], dd = a[0][1] * a[0][1], ee = a[1][2] * a[1][2], ff = a[0][2] * a[0][2];
+  const double tr = a[0][0] + a[1][1] + a[2][2];
+  const double c1 = (a[0][0] * a[1][1] + a[0][0] * a[2][2] + a[1][1] * a[2][2]) - (dd + ee + ff);
+  const double c0 = 27.0 * (a[2][2] * dd + a[0][0] * ee + a[1][1] * ff - a[0][0] * a[1][1] * a[2][2] - 2.0 * a[0][2] * de);
+  double p = tr * tr - 3.0 * c1;
+  const double r = tr * (p - 1.5 * c1) - 0.5 * c0;
+  const double sqrtp = std::sqrt(std::fabs(p));
+  const double ang = (1.0 / 3.0) * std::atan2(std::sqrt(std::fabs(6.75 * c1 * c1 * (p - c1) + c0 * (r + 0.25 * c0))), r);
+  const double c = sqrtp * std::cos(ang), s = (1.0 / sqrt3) * sqrtp * std::sin(ang);
+  p = (1.0 / 3.0) * (tr - c);
+  double w1 = p + c, w2 = p - s, w3 = p + s;
+  if (std::fabs(w1) < std::fabs(w3)) std::swap(w1, w3);
+  if (std::fabs(w1) < std::fabs(w2)) std::swap(w1, w2);
+  if (std::fabs(w2) < std::fabs(w3)) std::swap(w2, w3);
+  w[0] = w1; w[1] = w2; w[2] = w3;
+  const double wmax8eps = 8.0 * eps * std::fabs(w1), thresh = wmax8eps * wmax8eps;
+
+  // compute_eigenvector (379-416): normalise v = (A - w).e1 x (A - w).e2, with the degenerate-column exits
+  auto finish_vector = [&](double v[3], double n1tmp, double n2tmp) {
+    const double norm = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double n1 = n1tmp + a[0][0] * a[0][0], n2 = n2tmp + a[1][1] * a[1][1], err = n1 * n2;
+    if (n1 <= thresh) {
+      v[0] = 1.0; v[1] = 0.0; v[2] = 0.0;
+    } else if (n2 <= thresh) {
+      v[0] = 0.0; v[1] = 1.0; v[2] = 0.0;
+    } else if (norm < (64.0 * eps) * (64.0 * eps) * err) {
+      double t = std::fabs(a[0][1]), f = -a[0][0] / a[0][1];
+      if (std::fabs(a[1][1]) > t) { t = std::fabs(a[1][1]); f = -a[0][1] / a[1][1]; }
+      if (std::fabs(a[1][2]) > t) f = -a[0][2] / a[1][2];
+      const double nn = 1.0 / std::sqrt(1.0 + f * f);
+      v[0] = nn; v[1] = f * nn; v[2] = 0.0;
+    } else {
+      const double sc = std::sqrt(1.0 / norm);
+      for (int i = 0; i < 3; ++i) v[i] *= sc;
+    }
+  };
+
+  double n1 = a[0][1] * a[0][1] + a[0][2] * a[0][2], n2 = a[0][1] * a[0][1] + a[1][2] * a[1][2];
+  const double q12 = a[0][1] * a[1][2] - a[0][2] * a[1][1];   // q(1,2) = q(1,1) before the shift of the diagonal
+  const double q22 = a[0][2] * a[0][1] - a[1][2] * a[0][0];
+  const double q32 = a[0][1] * a[0][1];
+  a[0][0] -= w1;
+  a[1][1] -= w1;
+  double v1[3] = {q12 + a[0][2] * w1, q22 + a[1][2] * w1, a[0][0] * a[1][1] - q32};
+  finish_vector(v1, n1, n2);
+  double v2[3] = {0, 0, 0};
+  const double t = w1 - w2;
+  if (std::fabs(t) > wmax8eps) {
+    a[0][0] += t;
+    a[1][1] += t;
+    v2[0] = q12 + a[0][2] * w2; v2[1] = q22 + a[1][2] * w2; v2[2] = a[0][0] * a[1][1] - q32;
+    finish_vector(v2, n1, n2);
+  } else {   // degenerate pair (340-375)
+    a[1][0] = a[0][1];
+    a[2][0] = a[0][2];
+    a[2][1] = a[1][2];
+    a[0][0] += w1;
+    a[1][1] += w1;
+    bool success = false;
+    for (int i = 0; i < 3 && !success; ++i) {
+      a[i][i] -= w2;
+      const double col[3] = {a[0][i], a[1][i], a[2][i]};
+      n1 = col[0] * col[0] + col[1] * col[1] + col[2] * col[2];
+      success = n1 > thresh;
+      if (success) {
+        cross3(v1, col, v2);
+        const double norm = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+        success = norm > (256.0 * eps) * (256.0 * eps) * n1;
+        if (success) {
+          const double sc = std::sqrt(1.0 / norm);
+          for (int x = 0; x < 3; ++x) v2[x] *= sc;
+        }
+      }
+    }
+    if (!success) {   // any vector orthogonal to v1 will do
+      int i = 0;
+      while (v1[i] == 0.0) ++i;
+      const int j = (i + 1) % 3;
+      const double nn = 1.0 / std::sqrt(v1[i] * v1[i] + v1[j] * v1[j]);
+      v2[i] = v1[j] * nn;
+      v2[j] = -v1[i] * nn;
+      v2[(i + 2) % 3] = 0.0;
+    }
+  }
+  double v3[3];
+  cross3(v1, v2, v3);
+  for (int i = 0; i < 3; ++i) { q[i][0] = v1[i]; q[i][1] = v2[i]; q[i][2] = v3[i]; }
+}
+
+// src/math.f90:505-546, 550-577, 581-638: Carlson's symmetric elliptic integrals (duplication method)
+const double quiet_NaN = std::numeric_limits<double>::quiet_NaN();
+double Carlson_RF(double x, double y, double z) {
+  const double errtol = 0.001, tiny = 2.2250738585072014e-308, huge = 1.7976931348623157e308;
+  const double lolim = std::cbrt(5.0 * tiny), uplim = 0.3 * std::cbrt(0.2 * huge);
+  if (std::min({x, y, z}) < 0.0 || std::max({x, y, z}) > uplim || std::min({x + y, x + z, y + z}) < lolim) return quiet_NaN;
+  double xn = x, yn = y, zn = z, mu, xd, yd, zd;
+  for (;;) {
+    mu = (xn + yn + zn) / 3.0;
+    xd = 2.0 - (mu + xn) / mu;
+    yd = 2.0 - (mu + yn) / mu;
+    zd = 2.0 - (mu + zn) / mu;
+    if (std::max({std::fabs(xd), std::fabs(yd), std::fabs(zd)}) < errtol) break;
+    const double xr = std::sqrt(xn), yr = std::sqrt(yn), zr = std::sqrt(zn);
+    const double lam = xr * (yr + zr) + yr * zr;
+    xn = (xn + lam) * 0.25;
+    yn = (yn + lam) * 0.25;
+    zn = (zn + lam) * 0.25;
+  }
+  const double e2 = xd * yd - zd * zd, e3 = xd * yd * zd;
+  const double s = 1.0 + ((1.0 / 24.0) * e2 - 0.10 - (3.0 / 44.0) * e3) * e2 + (1.0 / 14.0) * e3;
+  return s / std::sqrt(mu);
+}
+double Carlson_RC(double x, double y) {
+  const double errtol = 0.001, tiny = 2.2250738585072014e-308, huge = 1.7976931348623157e308;
+  if (x < 0.0 || y <= 0.0 || std::max(x, y) > 0.2 * huge || x + y < 5.0 * tiny) return quiet_NaN;
+  double xn = x, yn = y, mu, sn;
+  for (;;) {
+    mu = (xn + yn + yn) / 3.0;
+    sn = (yn + mu) / mu - 2.0;
+    if (std::fabs(sn) < errtol) break;
+    const double lam = 2.0 * std::sqrt(xn) * std::sqrt(yn) + yn;
+    xn = (xn + lam) * 0.25;
+    yn = (yn + lam) * 0.25;
+  }
+  const double s = sn * sn * (0.30 + sn * ((1.0 / 7.0) + sn * (0.375 + sn * (9.0 / 22.0))));
+  return (1.0 + s) / std::sqrt(mu);
+}
+double Carlson_RJ(double x, double y, double z, double p) {
+  const double errtol = 0.001, tiny = 2.2250738585072014e-308, huge = 1.7976931348623157e308;
+  const double lolim = std::cbrt(5.0 * tiny), uplim = 0.30 * std::cbrt(0.2 * huge);
+  const double c1 = 3.0 / 14.0, c2 = 1.0 / 3.0, c3 = 3.0 / 22.0, c4 = 3.0 / 26.0;
+  if (std::min({x, y, z}) < 0.0 || std::max({x, y, z, p}) > uplim || std::min({x + y, x + z, y + z, p}) < lolim) return quiet_NaN;
+  double xn = x, yn = y, zn = z, pn = p, sigma = 0.0, power4 = 1.0, mu, xd, yd, zd, pd;
+  for (;;) {
+    mu = (xn + yn + zn + pn + pn) * 0.20;
+    xd = (mu - xn) / mu;
+    yd = (mu - yn) / mu;
+    zd = (mu - zn) / mu;
+    pd = (mu - pn) / mu;
+    if (std::max({std::fabs(xd), std::fabs(yd), std::fabs(zd), std::fabs(pd)}) < errtol) break;
+    const double xr = std::sqrt(xn), yr = std::sqrt(yn), zr = std::sqrt(zn);
+    const double lam = xr * (yr + zr) + yr * zr;
+    double alfa = pn * (xr + yr + zr) + xr * yr * zr;
+    alfa = alfa * alfa;
+    const double beta = pn * (pn + lam) * (pn + lam);
+    sigma = sigma + power4 * Carlson_RC(alfa, beta);
+    power4 = power4 * 0.25;
+    xn = (xn + lam) * 0.25;
+    yn = (yn + lam) * 0.25;
+    zn = (zn + lam) * 0.25;
+    pn = (pn + lam) * 0.25;
+  }
+  const double ea = xd * (yd + zd) + yd * zd, eb = xd * yd * zd, ec = pd * pd;
+  const double e2 = ea - 3.0 * ec, e3 = eb + 2.0 * pd * (ea - ec);
+  const double s1 = 1.0 + e2 * (-c1 + 0.75 * c3 * e2 - 1.5 * c4 * e3);
+  const double s2 = eb * (0.5 * c2 + pd * (-c3 - c3 + pd * c4));
+  const double s3 = pd * ea * (c2 - pd * c3) - c2 * pd * ec;
+  return 3.0 * sigma + power4 * (s1 + s2 + s3) / (mu * std::sqrt(mu));
+}
+
+// src/math.f90:440-501: Jacobi elliptic functions sn, cn, dn by descending Landen (AGM) steps
+void jacobi(double u, double m, double jac[3]) {
+  const int NN = 16;
+  const double eps = 2.220446049250313e-16;
+  if (std::fabs(m) > 1.0) {
+    jac[0] = jac[1] = jac[2] = quiet_NaN;
+  } else if (std::fabs(m) < 2.0 * eps) {
+    jac[0] = std::sin(u); jac[1] = std::cos(u); jac[2] = 1.0;
+  } else if (std::fabs(m - 1.0) < 2.0 * eps) {
+    jac[0] = std::tanh(u);
+    jac[1] = jac[2] = 1.0 / std::cosh(u);
+  } else {
+    double mu[NN], nu[NN], c[NN], d[NN];
+    int n = 0;
+    mu[0] = 1.0;
+    nu[0] = std::sqrt(1.0 - m);
+    while (std::fabs(mu[n] - nu[n]) > 4.0 * eps * std::fabs(mu[n] + nu[n])) {
+      mu[n + 1] = 0.5 * (mu[n] + nu[n]);
+      nu[n + 1] = std::sqrt(mu[n] * nu[n]);
+      ++n;
+      if (n >= NN - 1) { jac[0] = jac[1] = jac[2] = quiet_NaN; return; }
+    }
+    const double sin_umu = std::sin(u * mu[n]), cos_umu = std::cos(u * mu[n]);
+    const bool small_sin = std::fabs(sin_umu) < std::fabs(cos_umu);
+    const double t = small_sin ? sin_umu / cos_umu : cos_umu / sin_umu;
+    c[n] = mu[n] * t;
+    d[n] = 1.0;
+    while (n > 0) {
+      c[n - 1] = d[n] * c[n];
+      const double r = (c[n] * c[n]) / mu[n];
+      --n;
+      d[n] = (r + nu[n]) / (r + mu[n]);
+    }
+    double sn, cn, dn;
+    if (small_sin) {
+      dn = std::sqrt(1.0 - m) / d[n];
+      cn = dn * sign1(cos_umu) / std::hypot(1.0, c[n]);
+      sn = cn * c[n] / std::sqrt(1.0 - m);
+    } else {
+      dn = d[n];
+      sn = sign1(sin_umu) / std::hypot(1.0, c[n]);
+      cn = c[n] * sn;
+    }
+    jac[0] = sn; jac[1] = cn; jac[2] = dn;
+  }
+}
+
+// ---- rigid bodies (src/ArBee.f90) ------------------------------------------------------------------
 struct Body {
   int NP = 0;
   int dof = 6;
   double mass = 0, invMass = 0;
-  double rcm[3] = {0, 0, 0};
+  double MoI[3] = {0, 0, 0}, invMoI[3] = {0, 0, 0};
+  double rcm[3] = {0, 0, 0}, pcm[3] = {0, 0, 0};
+  double q[4] = {0, 0, 0, 0}, pi[4] = {0, 0, 0, 0};
+  double omega[3] = {0, 0, 0}, F[3] = {0, 0, 0}, tau[3] = {0, 0, 0};
+  double I113 = 0, I313 = 0, I223 = 0, I212 = 0, m312 = 0;
   std::vector<int> index;        // 0-based atom indices
   std::vector<double> M;         // masses
+  std::vector<double> d;         // 3*NP, body-frame positions
   std::vector<double> delta;     // 3*NP, space-frame positions relative to rcm
+
+  // tBody_update (97-130): centre of mass, inertia tensor -> principal frame, quaternion, body-frame coordinates
+  void update(const std::vector<double>& coords) {
+    for (int x = 0; x < 3; ++x) {
+      double s = 0.0;
+      for (int i = 0; i < NP; ++i) s += M[i] * coords[3 * i + x];
+      rcm[x] = s * invMass;
+    }
+    for (int i = 0; i < NP; ++i)
+      for (int x = 0; x < 3; ++x) delta[3 * i + x] = coords[3 * i + x] - rcm[x];
+    double inertia[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < NP; ++i) {
+      const double dx = delta[3 * i], dy = delta[3 * i + 1], dz = delta[3 * i + 2];
+      inertia[0][0] += M[i] * (dy * dy + dz * dz);
+      inertia[1][1] += M[i] * (dx * dx + dz * dz);
+      inertia[2][2] += M[i] * (dx * dx + dy * dy);
+      inertia[0][1] += M[i] * dx * dy;
+      inertia[0][2] += M[i] * dx * dz;
+      inertia[1][2] += M[i] * dy * dz;
+    }
+    inertia[0][1] = -inertia[0][1];
+    inertia[0][2] = -inertia[0][2];
+    inertia[1][2] = -inertia[1][2];
+    double vec[3][3], A[3][3];
+    diagonalization(inertia, vec, MoI);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) A[i][j] = vec[j][i];   // A = transpose(eigenvector matrix): rows are the principal axes
+    for (int x = 0; x < 3; ++x) invMoI[x] = 1.0 / MoI[x];
+    I113 = 1.0 / (MoI[0] * (MoI[0] - MoI[2]));
+    I313 = 1.0 / (MoI[2] * (MoI[0] - MoI[2]));
+    I223 = 1.0 / (MoI[1] * (MoI[1] - MoI[2]));
+    I212 = 1.0 / (MoI[1] * (MoI[0] - MoI[1]));
+    m312 = (MoI[2] - MoI[0]) / MoI[1];
+    quaternion_from_matrix(A, q);
+    for (int i = 0; i < NP; ++i)
+      for (int r = 0; r < 3; ++r)
+        d[3 * i + r] = A[r][0] * delta[3 * i] + A[r][1] * delta[3 * i + 1] + A[r][2] * delta[3 * i + 2];
+  }
+
+  // delta = Ct(q) B(q) d, the closing line of both rotation routines (190, 274)
+  void refresh_delta() {
+    for (int i = 0; i < NP; ++i) {
+      double t4[4];
+      mulB(q, &d[3 * i], t4);
+      mulCt(q, t4, &delta[3 * i]);
+    }
+  }
+
+  // tBody_rotate_uniaxial (194-217)
+  void rotate_uniaxial(int k, double dt) {
+    double BkQ[4], BkPi[4];
+    auto perm = [&](const double v[4], double o[4]) {
+      if (k == 1) { o[0] = -v[1]; o[1] = v[0]; o[2] = v[3]; o[3] = -v[2]; }
+      else if (k == 2) { o[0] = -v[2]; o[1] = -v[3]; o[2] = v[0]; o[3] = v[1]; }
+      else { o[0] = -v[3]; o[1] = v[2]; o[2] = -v[1]; o[3] = v[0]; }
+    };
+    perm(q, BkQ);
+    perm(pi, BkPi);
+    double dot = 0.0;
+    for (int x = 0; x < 4; ++x) dot += pi[x] * BkQ[x];
+    const double ang = dt * dot / (4.0 * MoI[k - 1]);
+    const double vs = std::sin(ang), vc = std::cos(ang);
+    for (int x = 0; x < 4; ++x) {
+      q[x] = vc * q[x] + vs * BkQ[x];
+      pi[x] = vc * pi[x] + vs * BkPi[x];
+    }
+  }
+
+  // tBody_rotate_no_squish (178-192): Miller et al. splitting, n sub-steps
+  void rotate_no_squish(double delta_t, int n) {
+    const double dt = delta_t / n, half_dt = 0.5 * dt;
+    for (int i = 0; i < n; ++i) {
+      rotate_uniaxial(3, half_dt);
+      rotate_uniaxial(2, half_dt);
+      rotate_uniaxial(1, dt);
+      rotate_uniaxial(2, half_dt);
+      rotate_uniaxial(3, half_dt);
+    }
+    refresh_delta();
+  }
+
+  // tBody_rotate_exact (221-313): torque-free rotation of an asymmetric top in closed form
+  // (Jacobi elliptic functions for omega, Carlson integrals for the precession angle)
+  void rotate_exact(double dt) {
+    const double eps = 2.220446049250313e-16, Pi = 3.14159265358979324;
+    const double w0[3] = {omega[0], omega[1], omega[2]};
+    double Iw[3] = {MoI[0] * w0[0], MoI[1] * w0[1], MoI[2] * w0[2]};
+    double Lsq = Iw[1] * Iw[1] + Iw[2] * Iw[2];
+    if (Lsq < eps) {
+      rotate_uniaxial(1, dt);   // returns WITHOUT refreshing delta, as the reference does
+      return;
+    }
+    Lsq = Iw[0] * Iw[0] + Lsq;
+    const double L = std::sqrt(Lsq);
+    const double TwoKr = Iw[0] * w0[0] + Iw[1] * w0[1] + Iw[2] * w0[2];
+    const double r1 = Lsq - TwoKr * MoI[2], r3 = TwoKr * MoI[0] - Lsq;
+    const double l1 = I223 * r1, l3 = I212 * r3, lmin = std::min(l1, l3);
+    double a[3] = {sign1(w0[0]) * std::sqrt(I113 * r1), std::sqrt(lmin), sign1(w0[2]) * std::sqrt(I313 * r3)};
+    const double m = lmin / std::max(l1, l3);
+    const double K = Carlson_RF(0.0, 1.0 - m, 1.0), inv2K = 0.5 / K;
+    double s0 = w0[1] / a[1], c0, u0;
+    int i0;
+    if (std::fabs(s0) < 1.0) {
+      c0 = (l1 < l3) ? w0[0] / a[0] : w0[2] / a[2];
+      u0 = s0 * Carlson_RF(1.0 - s0 * s0, 1.0 - m * s0 * s0, 1.0);
+      i0 = staircase(u0 * inv2K);
+    } else {
+      a[1] = std::fabs(w0[1]);
+      s0 = sign1(s0);
+      c0 = 0.0;
+      u0 = std::copysign(K, s0);
+      i0 = 0;
+    }
+    const double wp = m312 * a[0] * a[2] / a[1];
+    const double u = wp * dt + u0;
+    const int jump = staircase(u * inv2K) - i0;
+    double jac[3];
+    jacobi(u, m, jac);
+    const double sn = jac[0], cn = jac[1], dn = jac[2];
+    auto Theta = [](double x, double n, double mm) {
+      const double x2 = x * x;
+      return -(1.0 / 3.0) * n * x * x2 * Carlson_RJ(1.0 - x2, 1.0 - mm * x2, 1.0, 1.0 + n * x2);
+    };
+    const double alpha = MoI[0] * a[0] / L;
+    double deltaF;
+    if (l1 < l3) {
+      omega[0] = a[0] * cn; omega[1] = a[1] * sn; omega[2] = a[2] * dn;
+      const double d0 = w0[2] / a[2];
+      const double eta = alpha * alpha / (1.0 - alpha * alpha), C = std::sqrt(m + eta);
+      deltaF = u - u0 + sign1(cn) * Theta(sn, eta, m) - sign1(c0) * Theta(s0, eta, m) +
+               (alpha / C) * (std::atan(C * sn / dn) - std::atan(C * s0 / d0));
+      if (jump != 0) deltaF = deltaF + jump * 2.0 * Theta(1.0, eta, m);
+      deltaF = (eta + 1.0) * deltaF;
+    } else {
+      omega[0] = a[0] * dn; omega[1] = a[1] * sn; omega[2] = a[2] * cn;
+      double eta = alpha * alpha;
+      eta = eta / (1.0 - eta);
+      const double k2eta = m * eta, C = std::sqrt(1.0 + k2eta);
+      deltaF = u - u0 + sign1(cn) * Theta(sn, k2eta, m) - sign1(c0) * Theta(s0, k2eta, m) +
+               (alpha / C) * (std::atan(C * sn / cn) - std::atan(C * s0 / c0));
+      if (jump != 0) deltaF = deltaF + jump * (2.0 * Theta(1.0, k2eta, m) + (alpha / C) * Pi);
+      deltaF = (eta + 1.0) * deltaF;
+    }
+    const double ang = (Lsq * (u - u0) + r3 * deltaF) / (2.0 * L * MoI[0] * wp);
+    const double z0[4] = {Iw[2], Iw[1], L - Iw[0], 0.0};
+    for (int x = 0; x < 3; ++x) Iw[x] = MoI[x] * omega[x];
+    const double cph = std::cos(ang), sph = std::sin(ang);
+    const double z[4] = {Iw[2] * cph - Iw[1] * sph, Iw[1] * cph + Iw[2] * sph, (L - Iw[0]) * cph, (L - Iw[0]) * sph};
+    double z0q = 0.0;
+    for (int x = 0; x < 4; ++x) z0q += z0[x] * q[x];
+    double t3[3], t4[4], nq[4];
+    mulCt(z0, q, t3);
+    mulC(z, t3, t4);
+    double nrm = 0.0;
+    for (int x = 0; x < 4; ++x) { nq[x] = z[x] * z0q + t4[x]; nrm += nq[x] * nq[x]; }
+    nrm = std::sqrt(nrm);
+    for (int x = 0; x < 4; ++x) q[x] = nq[x] / nrm;
+    const double twoIw[3] = {2.0 * Iw[0], 2.0 * Iw[1], 2.0 * Iw[2]};
+    mulB(q, twoIw, pi);
+    refresh_delta();
+  }
+
+  // tBody_particle_momenta (317-326)
+  void particle_momenta(double* P) const {   // 3*NP
+    double t4[4], w[3];
+    mulB(q, omega, t4);
+    mulCt(q, t4, w);   // space-frame angular velocity
+    for (int k = 0; k < NP; ++k) {
+      double c[3];
+      cross3(w, &delta[3 * k], c);
+      for (int x = 0; x < 3; ++x) P[3 * k + x] = M[k] * (invMass * pcm[x] + c[x]);
+    }
+  }
+
+  // tBody_force_and_torque (330-343)
+  void force_and_torque(const double* Fall) {
+    for (int x = 0; x < 3; ++x) F[x] = tau[x] = 0.0;
+    for (int j = 0; j < NP; ++j) {
+      const double* Fj = Fall + 3 * (size_t)index[j];
+      double c[3];
+      cross3(&delta[3 * j], Fj, c);
+      for (int x = 0; x < 3; ++x) { F[x] = F[x] + Fj[x]; tau[x] = tau[x] + c[x]; }
+    }
+  }
+
+  // tBody_assign_momenta (347-357): from angular velocities (3) or from quaternion momenta (4)
+  void assign_omega(const double w[3]) {
+    const double v[3] = {2.0 * MoI[0] * w[0], 2.0 * MoI[1] * w[1], 2.0 * MoI[2] * w[2]};
+    for (int x = 0; x < 3; ++x) omega[x] = w[x];
+    mulB(q, v, pi);
+  }
+  void assign_pi(const double p[4]) {
+    for (int x = 0; x < 4; ++x) pi[x] = p[x];
+    double t3[3];
+    mulBt(q, pi, t3);
+    for (int x = 0; x < 3; ++x) omega[x] = 0.5 * invMoI[x] * t3[x];
+  }
 };
 
 // ---- system state (src/EmDeeData.f90:66-151) -----------------------------------------------------
@@ -683,6 +1155,7 @@ void allocate_rigid_bodies(System& me, const int* bodies) {
       for (double mm : b.M) b.mass += mm;
       b.invMass = 1.0 / b.mass;
       b.delta.assign(3 * b.NP, 0.0);
+      b.d.assign(3 * b.NP, 0.0);
     }
     int k = me.nbodies;
     for (int j = 0; j < N; ++j)
@@ -701,8 +1174,7 @@ void allocate_rigid_bodies(System& me, const int* bodies) {
   me.threadBodies = (me.nbodies + me.nthreads - 1) / me.nthreads;
 }
 
-// src/EmDeeData.f90:420-439 + tBody_update (src/ArBee.f90:97-106; inertia/quaternion parts belong to
-// the rigid-body integrator and are outside the hot path)
+// src/EmDeeData.f90:420-439: make each body whole with respect to its first atom, then tBody_update
 void update_rigid_bodies(System& me) {
   const double L = me.Lbox, invL = 1.0 / L;
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
@@ -713,16 +1185,132 @@ void update_rigid_bodies(System& me) {
       for (int x = 0; x < 3; ++x) R[3 * i + x] = me.R[3 * (size_t)b.index[i] + x];
     for (int i = 1; i < b.NP; ++i)
       for (int x = 0; x < 3; ++x) R[3 * i + x] = R[3 * i + x] - L * std::round(invL * (R[3 * i + x] - R[x]));
-    for (int x = 0; x < 3; ++x) {
-      double s = 0.0;
-      for (int i = 0; i < b.NP; ++i) s += b.M[i] * R[3 * i + x];
-      b.rcm[x] = s * b.invMass;
-    }
-    for (int i = 0; i < b.NP; ++i)
-      for (int x = 0; x < 3; ++x) b.delta[3 * i + x] = R[3 * i + x] - b.rcm[x];
+    b.update(R);
     for (int i = 0; i < b.NP; ++i)
       for (int x = 0; x < 3; ++x) me.R[3 * (size_t)b.index[i] + x] = R[3 * i + x];
   }
+}
+
+// src/EmDeeData.f90:823-860
+void move(System& me, double R_factor, double P_factor, double dt, bool translate, bool rotate, int mode) {
+  if (translate) {
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+    for (int i = 0; i < me.nbodies; ++i) {
+      Body& b = me.body[i];
+      for (int x = 0; x < 3; ++x) b.rcm[x] = R_factor * b.rcm[x] + P_factor * b.invMass * b.pcm[x];
+    }
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+    for (int f = 0; f < me.nfree; ++f) {
+      const int j = me.free_[f];
+      for (int x = 0; x < 3; ++x)
+        me.R[3 * (size_t)j + x] = R_factor * me.R[3 * (size_t)j + x] + P_factor * me.P[3 * (size_t)j + x] * me.invMass[j];
+    }
+  }
+  if (rotate) {
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+    for (int i = 0; i < me.nbodies; ++i) {
+      Body& b = me.body[i];
+      if (mode == 0) b.rotate_exact(dt);
+      else b.rotate_no_squish(dt, mode);
+      for (int k = 0; k < b.NP; ++k)
+        for (int x = 0; x < 3; ++x) me.R[3 * (size_t)b.index[k] + x] = b.rcm[x] + b.delta[3 * k + x];
+    }
+  }
+}
+
+// src/EmDeeData.f90:864-896
+void boost(System& me, double P_factor, double F_factor, const double* F, bool translate, bool rotate) {
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+  for (int i = 0; i < me.nbodies; ++i) me.body[i].force_and_torque(F);
+  if (translate) {
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+    for (int i = 0; i < me.nbodies; ++i) {
+      Body& b = me.body[i];
+      for (int x = 0; x < 3; ++x) b.pcm[x] = P_factor * b.pcm[x] + F_factor * b.F[x];
+    }
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+    for (int f = 0; f < me.nfree; ++f) {
+      const int j = me.free_[f];
+      for (int x = 0; x < 3; ++x) me.P[3 * (size_t)j + x] = P_factor * me.P[3 * (size_t)j + x] + F_factor * F[3 * (size_t)j + x];
+    }
+  }
+  if (rotate) {
+    const double Ctau = 2.0 * F_factor;
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+    for (int i = 0; i < me.nbodies; ++i) {
+      Body& b = me.body[i];
+      const double t3[3] = {Ctau * b.tau[0], Ctau * b.tau[1], Ctau * b.tau[2]};
+      double t4[4], np[4];
+      mulC(b.q, t3, t4);
+      for (int x = 0; x < 4; ++x) np[x] = P_factor * b.pi[x] + t4[x];
+      b.assign_pi(np);
+    }
+  }
+}
+
+// src/EmDeeData.f90:900-922; thread partials (blocks of threadBodies / threadFreeAtoms) summed in thread order
+void kinetic_energies(const System& me, bool translate, bool rotate, double twoKEt[3], double twoKEr[3]) {
+  const int T = me.nthreads;
+  if (translate) {
+    for (int x = 0; x < 3; ++x) twoKEt[x] = 0.0;
+    for (int t = 1; t <= T; ++t) {
+      double k[3] = {0, 0, 0};
+      for (int i = (t - 1) * me.threadBodies; i < std::min(t * me.threadBodies, me.nbodies); ++i)
+        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.body[i].invMass * me.body[i].pcm[x] * me.body[i].pcm[x];
+      for (int f = (t - 1) * me.threadFreeAtoms; f < std::min(t * me.threadFreeAtoms, me.nfree); ++f) {
+        const int j = me.free_[f];
+        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.invMass[j] * me.P[3 * (size_t)j + x] * me.P[3 * (size_t)j + x];
+      }
+      for (int x = 0; x < 3; ++x) twoKEt[x] += k[x];
+    }
+  }
+  if (rotate) {
+    for (int x = 0; x < 3; ++x) twoKEr[x] = 0.0;
+    for (int t = 1; t <= T; ++t) {
+      double k[3] = {0, 0, 0};
+      for (int i = (t - 1) * me.threadBodies; i < std::min(t * me.threadBodies, me.nbodies); ++i)
+        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.body[i].MoI[x] * me.body[i].omega[x] * me.body[i].omega[x];
+      for (int x = 0; x < 3; ++x) twoKEr[x] += k[x];
+    }
+  }
+}
+
+// src/EmDeeData.f90:157-189
+void assign_momenta(System& me, const double* P, double twoKEt[3], double twoKEr[3]) {
+  for (int x = 0; x < 3; ++x) twoKEt[x] = twoKEr[x] = 0.0;
+  for (int f = 0; f < me.nfree; ++f) {
+    const int i = me.free_[f];
+    for (int x = 0; x < 3; ++x) {
+      me.P[3 * (size_t)i + x] = P[3 * (size_t)i + x];
+      twoKEt[x] += me.invMass[i] * P[3 * (size_t)i + x] * P[3 * (size_t)i + x];
+    }
+  }
+  for (int i = 0; i < me.nbodies; ++i) {
+    Body& b = me.body[i];
+    double L[3] = {0, 0, 0};
+    for (int x = 0; x < 3; ++x) b.pcm[x] = 0.0;
+    for (int j = 0; j < b.NP; ++j) {
+      const double* Pj = P + 3 * (size_t)b.index[j];
+      double c[3];
+      cross3(&b.delta[3 * j], Pj, c);
+      for (int x = 0; x < 3; ++x) { b.pcm[x] = b.pcm[x] + Pj[x]; L[x] = L[x] + c[x]; }
+    }
+    for (int x = 0; x < 3; ++x) twoKEt[x] += b.invMass * b.pcm[x] * b.pcm[x];
+    const double twoL[3] = {2.0 * L[0], 2.0 * L[1], 2.0 * L[2]};
+    double np[4];
+    mulC(b.q, twoL, np);
+    b.assign_pi(np);
+    for (int x = 0; x < 3; ++x) twoKEr[x] += b.MoI[x] * b.omega[x] * b.omega[x];
+  }
+}
+
+void set_kinetic_from_sums(tEmDee* md, const double twoKEt[3], const double twoKEr[3]) {   // src/EmDeeCode.f90:862-868, 984-990
+  for (int x = 0; x < 3; ++x) { md->Kinetic.RotPart[x] = 0.5 * twoKEr[x]; md->Kinetic.TransPart[x] = 0.5 * twoKEt[x]; }
+  md->Kinetic.Rotational = md->Kinetic.RotPart[0] + md->Kinetic.RotPart[1] + md->Kinetic.RotPart[2];
+  md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] + md->Kinetic.Rotational;
+  md->Kinetic.ShadowKinetic = md->Kinetic.Total;
+  md->Kinetic.ShadowRotational = md->Kinetic.Rotational;
+  md->Kinetic.UpToDate = true;
 }
 
 // src/EmDeeData.f90:193-223
@@ -1396,9 +1984,15 @@ void EmDee_download(tEmDee md, const char* option, double* address) {
   } else if (item == "coordinates") {
     if (!me->hasR) error("download", "coordinates have not been allocated");
     std::copy(me->R.begin(), me->R.end(), address);
-  } else if (item == "momenta") {
-    if (me->nbodies != 0) out_of_scope("download (momenta of rigid bodies)");
-    std::copy(me->P.begin(), me->P.end(), address);
+  } else if (item == "momenta") {   // get_momenta (726-736)
+    for (int f = 0; f < me->nfree; ++f)
+      for (int x = 0; x < 3; ++x) address[3 * (size_t)me->free_[f] + x] = me->P[3 * (size_t)me->free_[f] + x];
+    for (const Body& b : me->body) {
+      std::vector<double> Pb(3 * (size_t)b.NP);
+      b.particle_momenta(Pb.data());
+      for (int k = 0; k < b.NP; ++k)
+        for (int x = 0; x < 3; ++x) address[3 * (size_t)b.index[k] + x] = Pb[3 * k + x];
+    }
   } else if (item == "forces") {
     if (!me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(&md);
     std::copy(me->F(), me->F() + n3, address);
@@ -1407,10 +2001,26 @@ void EmDee_download(tEmDee md, const char* option, double* address) {
       for (int x = 0; x < 3; ++x) address[3 * (size_t)b + x] = me->body[b].rcm[x];
     for (int f = 0; f < me->nfree; ++f)
       for (int x = 0; x < 3; ++x) address[3 * (size_t)(me->nbodies + f) + x] = me->R[3 * (size_t)me->free_[f] + x];
-  } else if (item == "quaternions" || item == "quatmom" || item == "quattau" || item == "angmom" ||
-             item == "bodycoord" || item == "bodymom" || item == "bodyforces" || item == "torques" ||
-             item == "inertia") {
-    out_of_scope("download (rigid-body dynamics)");
+  } else if (item == "quaternions" || item == "quatmom" || item == "quattau") {   // get_quaternions (759-775)
+    for (int i = 0; i < me->nbodies; ++i) {
+      const Body& b = me->body[i];
+      double v[4];
+      if (item == "quaternions") std::copy(b.q, b.q + 4, v);
+      else if (item == "quatmom") std::copy(b.pi, b.pi + 4, v);
+      else {
+        const double t2[3] = {2.0 * b.tau[0], 2.0 * b.tau[1], 2.0 * b.tau[2]};
+        mulC(b.q, t2, v);
+      }
+      std::copy(v, v + 4, address + 4 * (size_t)i);
+    }
+  } else if (item == "angmom" || item == "bodycoord" || item == "bodymom" || item == "bodyforces" ||
+             item == "torques" || item == "inertia") {   // get_body_properties (777-799)
+    for (int i = 0; i < me->nbodies; ++i) {
+      const Body& b = me->body[i];
+      const double* v = item == "angmom" ? b.omega : item == "bodycoord" ? b.rcm : item == "bodymom" ? b.pcm
+                      : item == "bodyforces" ? b.F : item == "torques" ? b.tau : b.MoI;
+      std::copy(v, v + 3, address + 3 * (size_t)i);
+    }
   } else {
     error("download", "invalid option");
   }
@@ -1456,23 +2066,9 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {
     }
   } else if (item == "momenta") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
-    if (me->nbodies != 0) out_of_scope("upload (momenta of rigid bodies)");
-    // assign_momenta, src/EmDeeData.f90:157-189 (free atoms)
-    double twoKEt[3] = {0, 0, 0};
-    for (int f = 0; f < me->nfree; ++f) {
-      int i = me->free_[f];
-      for (int x = 0; x < 3; ++x) {
-        me->P[3 * (size_t)i + x] = address[3 * (size_t)i + x];
-        twoKEt[x] += me->invMass[i] * address[3 * (size_t)i + x] * address[3 * (size_t)i + x];
-      }
-    }
-    for (int x = 0; x < 3; ++x) { md->Kinetic.RotPart[x] = 0.0; md->Kinetic.TransPart[x] = 0.5 * twoKEt[x]; }
-    md->Kinetic.Rotational = 0.0;
-    md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] +
-                        md->Kinetic.Rotational;
-    md->Kinetic.ShadowKinetic = md->Kinetic.Total;
-    md->Kinetic.ShadowRotational = md->Kinetic.Rotational;
-    md->Kinetic.UpToDate = true;
+    double twoKEt[3], twoKEr[3];
+    assign_momenta(*me, address, twoKEt, twoKEr);
+    set_kinetic_from_sums(md, twoKEt, twoKEr);
   } else if (item == "forces") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
     std::copy(address, address + n3, me->F());
@@ -1488,13 +2084,26 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {
   }
 }
 
-// src/EmDeeCode.f90:950-1020 (free atoms; rigid-body momenta need the ArBee integrator)
+// src/EmDeeCode.f90:950-1020
 void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {
   System* me = sys(*md);
   if (me->random.seeding_required) me->random.setup(seed);
-  if (me->nbodies != 0) out_of_scope("random_momenta (rigid bodies)");
-  double twoKEt[3] = {0, 0, 0};
+  double twoKEt[3] = {0, 0, 0}, twoKEr[3] = {0, 0, 0};
   Kiss& rng = me->random;
+  if (me->nbodies != 0) {
+    if (!me->initialized) error("random_momenta", "coordinates have not defined");
+    for (Body& b : me->body) {
+      const double s = std::sqrt(b.mass * kT);
+      for (int x = 0; x < 3; ++x) b.pcm[x] = s * rng.normal();
+      double w[3];
+      for (int x = 0; x < 3; ++x) w[x] = std::sqrt(b.invMoI[x] * kT) * rng.normal();
+      b.assign_omega(w);
+      for (int x = 0; x < 3; ++x) {
+        twoKEt[x] = twoKEt[x] + b.invMass * b.pcm[x] * b.pcm[x];
+        twoKEr[x] = twoKEr[x] + b.MoI[x] * b.omega[x] * b.omega[x];
+      }
+    }
+  }
   for (int f = 0; f < me->nfree; ++f) {
     int i = me->free_[f];
     double s = std::sqrt(me->mass[i] * kT);
@@ -1503,10 +2112,13 @@ void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {
   }
   if (adjust) {   // adjust_momenta, 994-1018
     double vcm[3];
+    int bodyDoF = 0;
+    for (const Body& b : me->body) bodyDoF += b.dof;
     for (int x = 0; x < 3; ++x) {
-      double s = 0.0;
+      double s = 0.0, sb = 0.0;
       for (int f = 0; f < me->nfree; ++f) s += me->P[3 * (size_t)me->free_[f] + x];
-      vcm[x] = s / me->totalMass;
+      for (const Body& b : me->body) sb += b.pcm[x];
+      vcm[x] = (s + sb) / me->totalMass;
     }
     for (int x = 0; x < 3; ++x) twoKEt[x] = 0.0;
     for (int f = 0; f < me->nfree; ++f) {
@@ -1516,62 +2128,45 @@ void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {
         twoKEt[x] += me->invMass[i] * me->P[3 * (size_t)i + x] * me->P[3 * (size_t)i + x];
       }
     }
-    double factor = std::sqrt((3 * me->nfree - 3) * kT / (twoKEt[0] + twoKEt[1] + twoKEt[2]));
+    for (Body& b : me->body)
+      for (int x = 0; x < 3; ++x) {
+        b.pcm[x] = b.pcm[x] - b.mass * vcm[x];
+        twoKEt[x] += b.invMass * b.pcm[x] * b.pcm[x];
+      }
+    double total = 0.0;
+    for (int x = 0; x < 3; ++x) total += twoKEt[x] + twoKEr[x];
+    double factor = std::sqrt((3 * me->nfree + bodyDoF - 3) * kT / total);
     for (int f = 0; f < me->nfree; ++f) {
       int i = me->free_[f];
       for (int x = 0; x < 3; ++x) me->P[3 * (size_t)i + x] = factor * me->P[3 * (size_t)i + x];
     }
-    for (int x = 0; x < 3; ++x) twoKEt[x] = factor * factor * twoKEt[x];
+    for (Body& b : me->body) {
+      for (int x = 0; x < 3; ++x) b.pcm[x] = factor * b.pcm[x];
+      const double w[3] = {factor * b.omega[0], factor * b.omega[1], factor * b.omega[2]};
+      b.assign_omega(w);
+    }
+    for (int x = 0; x < 3; ++x) { twoKEt[x] = factor * factor * twoKEt[x]; twoKEr[x] = factor * factor * twoKEr[x]; }
   }
-  for (int x = 0; x < 3; ++x) { md->Kinetic.RotPart[x] = 0.0; md->Kinetic.TransPart[x] = 0.5 * twoKEt[x]; }
-  md->Kinetic.Rotational = 0.0;
-  md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] +
-                      md->Kinetic.Rotational;
-  md->Kinetic.ShadowKinetic = md->Kinetic.Total;
-  md->Kinetic.ShadowRotational = md->Kinetic.Rotational;
-  md->Kinetic.UpToDate = true;
+  set_kinetic_from_sums(md, twoKEt, twoKEr);
 }
 
-// src/EmDeeCode.f90:1024-1065 with boost / kinetic_energies (src/EmDeeData.f90:864-922), free atoms
+// src/EmDeeCode.f90:1024-1065 with boost / kinetic_energies (src/EmDeeData.f90:864-922)
 void EmDee_boost(tEmDee* md, double lambda, double alpha, double dt) {
   System* me = sys(*md);
   double CF = phi(alpha * dt) * dt;
   double CP = 1.0 - alpha * CF;
   CF = lambda * CF;
   if (lambda != 0.0 && !me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(md);
-  if (me->nbodies != 0) out_of_scope("boost (rigid bodies)");
-  const int T = me->nthreads;
-  std::vector<double> twoKEt(3 * (size_t)T, 0.0);
-  const double* F = me->F();
-  const bool compute = md->Options.Compute, translate = md->Options.Translate;
-#pragma omp parallel num_threads(T)
-  {
-    const int thread = omp_get_thread_num() + 1;
-    const int f1 = (thread - 1) * me->threadFreeAtoms + 1, fN = std::min(thread * me->threadFreeAtoms, me->nfree);
-    if (translate)
-      for (int f = f1; f <= fN; ++f) {
-        int j = me->free_[f - 1];
-        for (int x = 0; x < 3; ++x) me->P[3 * (size_t)j + x] = CP * me->P[3 * (size_t)j + x] + CF * F[3 * (size_t)j + x];
-      }
-    if (compute && translate) {
-      double k[3] = {0, 0, 0};
-      for (int f = f1; f <= fN; ++f) {
-        int j = me->free_[f - 1];
-        for (int x = 0; x < 3; ++x) k[x] = k[x] + me->invMass[j] * me->P[3 * (size_t)j + x] * me->P[3 * (size_t)j + x];
-      }
-      for (int x = 0; x < 3; ++x) twoKEt[3 * (size_t)(thread - 1) + x] = k[x];
-    }
-  }
+  const bool compute = md->Options.Compute, translate = md->Options.Translate, rotate = md->Options.Rotate;
+  boost(*me, CP, CF, me->F(), translate, rotate);
   if (compute) {
+    double twoKEt[3], twoKEr[3];
+    kinetic_energies(*me, translate, rotate, twoKEt, twoKEr);
     if (translate)
-      for (int x = 0; x < 3; ++x) {
-        double s = 0.0;
-        for (int t = 0; t < T; ++t) s += twoKEt[3 * (size_t)t + x];
-        md->Kinetic.TransPart[x] = 0.5 * s;
-      }
-    if (md->Options.Rotate) {
-      for (int x = 0; x < 3; ++x) md->Kinetic.RotPart[x] = 0.0;
-      md->Kinetic.Rotational = 0.0;
+      for (int x = 0; x < 3; ++x) md->Kinetic.TransPart[x] = 0.5 * twoKEt[x];
+    if (rotate) {
+      for (int x = 0; x < 3; ++x) md->Kinetic.RotPart[x] = 0.5 * twoKEr[x];
+      md->Kinetic.Rotational = md->Kinetic.RotPart[0] + md->Kinetic.RotPart[1] + md->Kinetic.RotPart[2];
     }
     md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] +
                         md->Kinetic.Rotational;
@@ -1579,7 +2174,7 @@ void EmDee_boost(tEmDee* md, double lambda, double alpha, double dt) {
   md->Kinetic.UpToDate = compute;
 }
 
-// src/EmDeeCode.f90:1069-1103 with move (src/EmDeeData.f90:823-860), free atoms
+// src/EmDeeCode.f90:1069-1103 with move (src/EmDeeData.f90:823-860)
 void EmDee_displace(tEmDee* md, double lambda, double alpha, double dt) {
   System* me = sys(*md);
   md->Time.Motion -= omp_get_wtime();
@@ -1593,20 +2188,103 @@ void EmDee_displace(tEmDee* md, double lambda, double alpha, double dt) {
     CR = 1.0;
   }
   CP = lambda * CP;
-  if (me->nbodies != 0) out_of_scope("displace (rigid bodies)");
-  if (md->Options.Translate) {
-#pragma omp parallel for num_threads(me->nthreads) schedule(static)
-    for (int f = 0; f < me->nfree; ++f) {
-      int j = me->free_[f];
-      for (int x = 0; x < 3; ++x)
-        me->R[3 * (size_t)j + x] = CR * me->R[3 * (size_t)j + x] + CP * me->P[3 * (size_t)j + x] * me->invMass[j];
-    }
-  }
+  move(*me, CR, CP, dt, md->Options.Translate, md->Options.Rotate, md->Options.RotationMode);
   invalidate(*me, md);
   md->Time.Motion += omp_get_wtime();
 }
 
-void EmDee_verlet_step(tEmDee*, double) { out_of_scope("verlet_step"); }
+// src/EmDeeCode.f90:1107-1211: one velocity-Verlet step with the shadow-Hamiltonian bookkeeping
+void EmDee_verlet_step(tEmDee* md, double dt) {
+  System* me = sys(*md);
+  const double dt_2 = 0.5 * dt;
+  const bool compute = md->Options.Compute;
+  const int mode = md->Options.RotationMode;
+  double Us = 0.0, Ks_t = 0.0, Ks_r = 0.0;
+  std::vector<double> r0, q0, s0;
+  auto virtual_rotation = [&](const Body& b, double tstep, double q[4]) {   // 1150-1163
+    Body c = b;
+    const double t3[3] = {tstep * c.tau[0], tstep * c.tau[1], tstep * c.tau[2]};
+    double t4[4], np[4];
+    mulC(c.q, t3, t4);
+    for (int x = 0; x < 4; ++x) np[x] = c.pi[x] + t4[x];
+    c.assign_pi(np);
+    if (mode != 0) c.rotate_no_squish(tstep, mode);
+    else c.rotate_exact(tstep);
+    std::copy(c.q, c.q + 4, q);
+  };
+  // pre_force (1165-1182)
+  if (compute) {
+    r0.assign(3 * (size_t)me->nbodies, 0.0);
+    q0.assign(4 * (size_t)me->nbodies, 0.0);
+    s0.assign(3 * (size_t)me->nfree, 0.0);
+    for (int i = 0; i < me->nbodies; ++i) {
+      const Body& b = me->body[i];
+      for (int x = 0; x < 3; ++x) r0[3 * (size_t)i + x] = 2.5 * b.rcm[x] + dt_2 * b.invMass * (b.pcm[x] - dt_2 * b.F[x]);
+      double vq[4];
+      virtual_rotation(b, -dt, vq);
+      for (int x = 0; x < 4; ++x) q0[4 * (size_t)i + x] = 0.5 * vq[x] - 3.0 * b.q[x];
+    }
+    const double* F = me->F();
+    for (int f = 0; f < me->nfree; ++f) {
+      const int j = me->free_[f];
+      for (int x = 0; x < 3; ++x)
+        s0[3 * (size_t)f + x] = 2.5 * me->R[3 * (size_t)j + x] +
+                                dt_2 * me->invMass[j] * (me->P[3 * (size_t)j + x] - dt_2 * F[3 * (size_t)j + x]);
+    }
+  }
+  boost(*me, 1.0, dt_2, me->F(), true, true);
+  move(*me, 1.0, dt, dt, true, true, mode);
+
+  EmDee_compute_forces(md);
+
+  // post_force (1184-1209)
+  boost(*me, 1.0, dt_2, me->F(), true, true);
+  if (compute) {
+    double twoKEt[3], twoKEr[3];
+    kinetic_energies(*me, true, true, twoKEt, twoKEr);
+    for (int i = 0; i < me->nbodies; ++i) {
+      const Body& b = me->body[i];
+      double rdot[3], vq[4], qdot[4];
+      for (int x = 0; x < 3; ++x) {
+        rdot[x] = 2.5 * b.rcm[x] + dt * b.invMass * (b.pcm[x] + dt_2 * b.F[x]) - r0[3 * (size_t)i + x];
+        Ks_t = Ks_t + rdot[x] * b.pcm[x];   // sum(rdot*pcm), accumulated term by term
+      }
+      virtual_rotation(b, dt, vq);
+      double qq = 0.0;
+      for (int x = 0; x < 4; ++x) { qdot[x] = q0[4 * (size_t)i + x] + 1.5 * b.q[x] + vq[x]; }
+      for (int x = 0; x < 4; ++x) qq += qdot[x] * b.q[x];
+      double acc = 0.0;
+      for (int x = 0; x < 4; ++x) acc += (qdot[x] - qq * b.q[x]) * b.pi[x];
+      Ks_r = Ks_r + acc;
+      double t4[4], tau_b[3];
+      mulC(b.q, b.tau, t4);
+      mulBt(b.q, t4, tau_b);
+      double ff = 0.0, tt = 0.0;
+      for (int x = 0; x < 3; ++x) { ff += b.F[x] * b.F[x]; tt += b.invMoI[x] * tau_b[x] * tau_b[x]; }
+      Us = Us + b.invMass * ff + tt;
+    }
+    const double* F = me->F();
+    for (int f = 0; f < me->nfree; ++f) {
+      const int j = me->free_[f];
+      double ff = 0.0, rp = 0.0;
+      for (int x = 0; x < 3; ++x) {
+        const double rdot = 2.5 * me->R[3 * (size_t)j + x] +
+                            dt * me->invMass[j] * (me->P[3 * (size_t)j + x] + dt_2 * F[3 * (size_t)j + x]) - s0[3 * (size_t)f + x];
+        rp += rdot * me->P[3 * (size_t)j + x];
+        ff += F[3 * (size_t)j + x] * F[3 * (size_t)j + x];
+      }
+      Ks_t = Ks_t + rp;
+      Us = Us + me->invMass[j] * ff;
+    }
+    for (int x = 0; x < 3; ++x) { md->Kinetic.TransPart[x] = 0.5 * twoKEt[x]; md->Kinetic.RotPart[x] = 0.5 * twoKEr[x]; }
+    md->Kinetic.Rotational = md->Kinetic.RotPart[0] + md->Kinetic.RotPart[1] + md->Kinetic.RotPart[2];
+    md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] + md->Kinetic.Rotational;
+    md->Energy.ShadowPotential = md->Energy.ShadowPotential - dt * dt * Us / 24.0;
+    md->Kinetic.ShadowRotational = Ks_r / (6.0 * dt);
+    md->Kinetic.ShadowKinetic = (Ks_t + Ks_r) / (6.0 * dt);
+  }
+  md->Kinetic.UpToDate = compute;
+}
 
 // src/EmDeeCode.f90:1215-1277
 void EmDee_compute_forces(tEmDee* md) {
