@@ -507,6 +507,7 @@ void perform_initialization(System& me, tEmDee* md) {
     update_rigid_bodies(me, delta);
     me.engine->upload_coordinates(me.hostR.data());
     me.engine->upload_body_delta(delta.data());
+    me.engine->update_body_frames();   // tBody_update: principal frame, quaternion, body coordinates (on the device)
   }
   const int bodyDoF = 6 * me.nbodies();
   md->RotDoF = bodyDoF - 3 * me.nbodies();
@@ -550,12 +551,12 @@ void invalidate(System& me, tEmDee* md) {
   md->Energy.UpToDate = false;
 }
 
-void set_kinetic(tEmDee* md, const double twoKE[3]) {
+void set_kinetic(tEmDee* md, const double twoKE[3], const double* twoKEr = nullptr) {
   for (int x = 0; x < 3; ++x) {
     md->Kinetic.TransPart[x] = 0.5 * twoKE[x];
-    md->Kinetic.RotPart[x] = 0.0;
+    md->Kinetic.RotPart[x] = twoKEr ? 0.5 * twoKEr[x] : 0.0;
   }
-  md->Kinetic.Rotational = 0.0;
+  md->Kinetic.Rotational = md->Kinetic.RotPart[0] + md->Kinetic.RotPart[1] + md->Kinetic.RotPart[2];
   md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] + md->Kinetic.Rotational;
   md->Kinetic.ShadowKinetic = md->Kinetic.Total;
   md->Kinetic.ShadowRotational = md->Kinetic.Rotational;
@@ -629,6 +630,16 @@ tEmDee EmDee_system(int threads, int layers, double rc, double skin, int N, int*
   me->forcesUpToDate.assign(layers, 0);
   me->engine = new Engine(N, me->ntypes, layers, rc, skin, me->type.data(), me->mass.data(), me->invMass.data(),
                           me->atomBody.data(), me->nbodies());
+  if (me->nbodies() != 0) {
+    std::vector<int> first(1, 0), members;
+    std::vector<double> memberMass;
+    for (const RigidBody& b : me->bodies) {
+      members.insert(members.end(), b.atoms.begin(), b.atoms.end());
+      memberMass.insert(memberMass.end(), b.m.begin(), b.m.end());
+      first.push_back((int)members.size());
+    }
+    me->engine->set_bodies(first, members, memberMass);
+  }
 
   tEmDee md;
   std::memset(&md, 0, sizeof(md));
@@ -777,15 +788,48 @@ void EmDee_download(tEmDee md, const char* option, double* address) {
     if (!me->hasR) error("download", "coordinates have not been allocated");
     me->engine->download_coordinates(address);
   } else if (item == "momenta") {
-    if (me->nbodies() != 0) unsupported("download (momenta of rigid bodies)");
+    me->engine->refresh_member_momenta();   // body members: m_k (pcm/M + omega x delta_k), src/ArBee.f90:317-326
     me->engine->download_momenta(address);
   } else if (item == "forces") {
     if (!me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(&md);
     me->engine->download_forces(me->layer - 1, address);
-  } else if (item == "centersOfMass" || item == "quaternions" || item == "quatmom" || item == "quattau" ||
-             item == "angmom" || item == "bodycoord" || item == "bodymom" || item == "bodyforces" ||
-             item == "torques" || item == "inertia") {
-    unsupported("download (rigid-body properties)");
+  } else if (item == "centersOfMass") {   // bodies first, then the free atoms (src/EmDeeCode.f90:748-757)
+    const size_t nb = (size_t)me->nbodies();
+    me->engine->download_body(Engine::BODY_RCM, address);
+    std::vector<double> R(3 * (size_t)me->N);
+    me->engine->download_coordinates(R.data());
+    for (size_t f = 0; f < me->freeAtoms.size(); ++f)
+      for (int x = 0; x < 3; ++x) address[3 * (nb + f) + x] = R[3 * (size_t)me->freeAtoms[f] + x];
+  } else if (item == "quaternions") {
+    me->engine->download_body(Engine::BODY_QUATERNION, address);
+  } else if (item == "quatmom") {
+    me->engine->download_body(Engine::BODY_QUATMOM, address);
+  } else if (item == "quattau") {   // C(q) (2 tau), src/EmDeeCode.f90:770-771
+    const size_t nb = (size_t)me->nbodies();
+    std::vector<double> q(4 * nb), tau(3 * nb);
+    me->engine->download_body(Engine::BODY_QUATERNION, q.data());
+    me->engine->download_body(Engine::BODY_TORQUE, tau.data());
+    for (size_t b = 0; b < nb; ++b) {
+      const double* a = &q[4 * b];
+      const double v[3] = {2.0 * tau[3 * b], 2.0 * tau[3 * b + 1], 2.0 * tau[3 * b + 2]};
+      double* o = address + 4 * b;
+      o[0] = -a[1] * v[0] - a[2] * v[1] - a[3] * v[2];
+      o[1] = a[0] * v[0] + a[3] * v[1] - a[2] * v[2];
+      o[2] = -a[3] * v[0] + a[0] * v[1] + a[1] * v[2];
+      o[3] = a[2] * v[0] - a[1] * v[1] + a[0] * v[2];
+    }
+  } else if (item == "angmom") {
+    me->engine->download_body(Engine::BODY_OMEGA, address);
+  } else if (item == "bodycoord") {
+    me->engine->download_body(Engine::BODY_RCM, address);
+  } else if (item == "bodymom") {
+    me->engine->download_body(Engine::BODY_PCM, address);
+  } else if (item == "bodyforces") {
+    me->engine->download_body(Engine::BODY_FORCE, address);
+  } else if (item == "torques") {
+    me->engine->download_body(Engine::BODY_TORQUE, address);
+  } else if (item == "inertia") {
+    me->engine->download_body(Engine::BODY_INERTIA, address);
   } else {
     error("download", "invalid option");
   }
@@ -822,12 +866,15 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/Em
       me->hostR.assign(address, address + 3 * (size_t)me->N);
       if (me->initialized) {
         invalidate(*me, md);
+        bool reframe = false;
         if (md->Options.AutoBodyUpdate) {
           std::vector<double> delta;
           update_rigid_bodies(*me, delta);
           me->engine->upload_body_delta(delta.data());
+          reframe = true;
         }
         me->engine->upload_coordinates(me->hostR.data());
+        if (reframe) me->engine->update_body_frames();
       } else if (me->hasL) {
         initialize_system();   // uploads the body-updated coordinates itself
       }
@@ -838,12 +885,14 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/Em
     }
   } else if (item == "momenta") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
-    if (me->nbodies() != 0) unsupported("upload (momenta of rigid bodies)");
     me->engine->upload_momenta(address);
     double twoKE[3] = {0, 0, 0};
-    for (int i = 0; i < me->N; ++i)
+    for (int i : me->freeAtoms)
       for (int x = 0; x < 3; ++x) twoKE[x] += me->invMass[i] * address[3 * (size_t)i + x] * address[3 * (size_t)i + x];
-    set_kinetic(md, twoKE);
+    emdee::KineticAll kb;
+    me->engine->take_member_momenta(kb);   // assign_momenta of the bodies (src/EmDeeData.f90:173-187), on the device
+    for (int x = 0; x < 3; ++x) twoKE[x] += kb.twoKEt[x];
+    set_kinetic(md, twoKE, kb.twoKEr);
   } else if (item == "forces") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
     me->engine->upload_forces(me->layer - 1, address);
@@ -862,9 +911,24 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/Em
 void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {   // src/EmDeeCode.f90:950-1020
   System* me = sys(*md);
   if (me->random.seeding_required) me->random.seed(seed);
-  if (me->nbodies() != 0) unsupported("random_momenta (rigid bodies)");
-  std::vector<double> P(3 * (size_t)me->N, 0.0);
-  double twoKE[3] = {0, 0, 0};
+  // The reference draws from ONE sequential generator (bodies first, then free atoms), so the stream is produced
+  // on the host; the per-body algebra (pi = B(q) 2 I omega) runs on the device.
+  const size_t nb = (size_t)me->nbodies();
+  std::vector<double> P(3 * (size_t)me->N, 0.0), pcm(3 * nb), omega(3 * nb), MoI(3 * nb);
+  double twoKE[3] = {0, 0, 0}, twoKEr[3] = {0, 0, 0};
+  if (nb != 0) {
+    if (!me->initialized) error("random_momenta", "coordinates have not defined");
+    me->engine->download_body(Engine::BODY_INERTIA, MoI.data());
+    for (size_t b = 0; b < nb; ++b) {
+      const double s = std::sqrt(me->bodies[b].mass * kT);
+      for (int x = 0; x < 3; ++x) pcm[3 * b + x] = s * me->random.normal();
+      for (int x = 0; x < 3; ++x) omega[3 * b + x] = std::sqrt((1.0 / MoI[3 * b + x]) * kT) * me->random.normal();
+      for (int x = 0; x < 3; ++x) {
+        twoKE[x] += (1.0 / me->bodies[b].mass) * pcm[3 * b + x] * pcm[3 * b + x];
+        twoKEr[x] += MoI[3 * b + x] * omega[3 * b + x] * omega[3 * b + x];
+      }
+    }
+  }
   for (int i : me->freeAtoms) {
     const double s = std::sqrt(me->mass[i] * kT);
     for (int x = 0; x < 3; ++x) P[3 * (size_t)i + x] = s * me->random.normal();
@@ -873,8 +937,10 @@ void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {   // s
   if (adjust) {
     double vcm[3] = {0, 0, 0};
     for (int x = 0; x < 3; ++x) {
+      double sb = 0.0;
       for (int i : me->freeAtoms) vcm[x] += P[3 * (size_t)i + x];
-      vcm[x] /= me->totalMass;
+      for (size_t b = 0; b < nb; ++b) sb += pcm[3 * b + x];
+      vcm[x] = (vcm[x] + sb) / me->totalMass;
       twoKE[x] = 0.0;
     }
     for (int i : me->freeAtoms)
@@ -882,12 +948,28 @@ void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {   // s
         P[3 * (size_t)i + x] -= me->mass[i] * vcm[x];
         twoKE[x] += me->invMass[i] * P[3 * (size_t)i + x] * P[3 * (size_t)i + x];
       }
-    const double factor = std::sqrt((3 * (int)me->freeAtoms.size() - 3) * kT / (twoKE[0] + twoKE[1] + twoKE[2]));
+    for (size_t b = 0; b < nb; ++b)
+      for (int x = 0; x < 3; ++x) {
+        pcm[3 * b + x] -= me->bodies[b].mass * vcm[x];
+        twoKE[x] += (1.0 / me->bodies[b].mass) * pcm[3 * b + x] * pcm[3 * b + x];
+      }
+    const double total = (twoKE[0] + twoKEr[0]) + (twoKE[1] + twoKEr[1]) + (twoKE[2] + twoKEr[2]);
+    const double factor = std::sqrt((3 * (int)me->freeAtoms.size() + 6 * (int)nb - 3) * kT / total);
     for (double& p : P) p *= factor;
-    for (int x = 0; x < 3; ++x) twoKE[x] *= factor * factor;
+    for (double& p : pcm) p *= factor;
+    for (double& w : omega) w *= factor;
+    for (int x = 0; x < 3; ++x) {
+      twoKE[x] *= factor * factor;
+      twoKEr[x] *= factor * factor;
+    }
   }
   me->engine->upload_momenta(P.data());
-  set_kinetic(md, twoKE);
+  if (nb != 0) {
+    me->engine->upload_body(Engine::BODY_PCM, pcm.data());
+    me->engine->upload_body(Engine::BODY_OMEGA, omega.data());
+    me->engine->derive_quaternion_momenta();
+  }
+  set_kinetic(md, twoKE, twoKEr);
 }
 
 void EmDee_boost(tEmDee* md, double lambda, double alpha, double dt) {   // src/EmDeeCode.f90:1024-1065
@@ -896,8 +978,22 @@ void EmDee_boost(tEmDee* md, double lambda, double alpha, double dt) {   // src/
   const double CP = 1.0 - alpha * CF;
   CF = lambda * CF;
   if (lambda != 0.0 && !me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(md);
-  if (me->nbodies() != 0) unsupported("boost (rigid bodies)");
   const bool compute = md->Options.Compute;
+  if (me->nbodies() != 0) {
+    emdee::KineticAll ka;
+    me->engine->boost_all(me->layer - 1, CP, CF, md->Options.Translate, md->Options.Rotate, compute, ka);
+    if (compute) {
+      if (md->Options.Translate)
+        for (int x = 0; x < 3; ++x) md->Kinetic.TransPart[x] = 0.5 * ka.twoKEt[x];
+      if (md->Options.Rotate) {
+        for (int x = 0; x < 3; ++x) md->Kinetic.RotPart[x] = 0.5 * ka.twoKEr[x];
+        md->Kinetic.Rotational = md->Kinetic.RotPart[0] + md->Kinetic.RotPart[1] + md->Kinetic.RotPart[2];
+      }
+      md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] + md->Kinetic.Rotational;
+    }
+    md->Kinetic.UpToDate = compute;
+    return;
+  }
   emdee::KineticScalars ke;
   if (md->Options.Translate) me->engine->boost(me->layer - 1, CP, CF, compute, ke);
   if (compute) {
@@ -922,13 +1018,42 @@ void EmDee_displace(tEmDee* md, double lambda, double alpha, double dt) {   // s
     me->Lbox = CR * me->Lbox;
   }
   CP = lambda * CP;
-  if (me->nbodies() != 0) unsupported("displace (rigid bodies)");
-  if (md->Options.Translate) me->engine->displace(CR, CP);
+  if (me->nbodies() != 0)
+    me->engine->move_all(CR, CP, dt, md->Options.Translate, md->Options.Rotate, md->Options.RotationMode);
+  else if (md->Options.Translate)
+    me->engine->displace(CR, CP);
   invalidate(*me, md);
   md->Time.Motion += now() - t0;
 }
 
-void EmDee_verlet_step(tEmDee*, double) { unsupported("verlet_step"); }
+// src/EmDeeCode.f90:1107-1211: half kick, drift, forces, half kick -- translation and rotation always on -- plus, when
+// Options%Compute is set, the shadow-Hamiltonian corrections (pre_force / post_force bookkeeping on the device)
+void EmDee_verlet_step(tEmDee* md, double dt) {
+  System* me = sys(*md);
+  const double dt_2 = 0.5 * dt;
+  const bool compute = md->Options.Compute;
+  const int mode = md->Options.RotationMode;
+  emdee::KineticAll ka;
+  if (compute) me->engine->shadow_pre(me->layer - 1, dt, mode);
+  me->engine->boost_all(me->layer - 1, 1.0, dt_2, true, true, false, ka);
+  me->engine->move_all(1.0, dt, dt, true, true, mode);
+  EmDee_compute_forces(md);
+  me->engine->boost_all(me->layer - 1, 1.0, dt_2, true, true, compute, ka);
+  if (compute) {
+    double Us = 0, Ks_t = 0, Ks_r = 0;
+    me->engine->shadow_post(me->layer - 1, dt, mode, Us, Ks_t, Ks_r);
+    for (int x = 0; x < 3; ++x) {
+      md->Kinetic.TransPart[x] = 0.5 * ka.twoKEt[x];
+      md->Kinetic.RotPart[x] = 0.5 * ka.twoKEr[x];
+    }
+    md->Kinetic.Rotational = md->Kinetic.RotPart[0] + md->Kinetic.RotPart[1] + md->Kinetic.RotPart[2];
+    md->Kinetic.Total = md->Kinetic.TransPart[0] + md->Kinetic.TransPart[1] + md->Kinetic.TransPart[2] + md->Kinetic.Rotational;
+    md->Energy.ShadowPotential = md->Energy.ShadowPotential - dt * dt * Us / 24.0;
+    md->Kinetic.ShadowRotational = Ks_r / (6.0 * dt);
+    md->Kinetic.ShadowKinetic = (Ks_t + Ks_r) / (6.0 * dt);
+  }
+  md->Kinetic.UpToDate = compute;
+}
 
 void EmDee_compute_forces(tEmDee* md) {   // src/EmDeeCode.f90:1215-1277
   System* me = sys(*md);

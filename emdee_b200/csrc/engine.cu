@@ -5,7 +5,7 @@
 //   engine_common.cuh  error macros, DBuf, grid_finish      engine_brick.cuh     opt-in shared-memory brick path
 //   engine_list.cuh    criterion, binning/sort, list build  engine_dynamics.cuh  k_boost, k_displace
 //   engine_force.cuh   pair term + force kernels             engine_dist.cuh      multi-GPU kernels
-//   engine_extra.cuh   pair export, rdf histogram, FP64 probe
+//   engine_extra.cuh   pair export, rdf histogram, FP64 probe   engine_bodies.cuh    rigid-body integrator, verlet_step bookkeeping
 //
 // Reference loops replaced (paths relative to the reference tree):
 //   k_displacement_check, k_displace (fused check)  <- src/neighbor_lists.f90:41-59,184
@@ -16,6 +16,7 @@
 //                      src/EmDeeData.f90:644-685, src/EmDeeCode.f90:1236-1247 (reductions),
 //                      src/EmDeeData.f90:926-953 (rigid_body_virial, fused in the epilogue)
 //   k_boost / k_displace                            <- src/EmDeeData.f90:823-922 (free atoms)
+//   k_body_* / k_shadow_*                           <- src/ArBee.f90, src/EmDeeData.f90:157-189,823-922, src/EmDeeCode.f90:1107-1211
 //
 // Design: atoms are sorted by cell of an EXTENDED grid (M+4)^3 that carries explicit
 // periodic ghost images in a 2-cell shell, so the force kernel needs no minimum-image arithmetic; the
@@ -45,6 +46,7 @@
 #include "engine_force.cuh"
 #include "engine_brick.cuh"
 #include "engine_dynamics.cuh"
+#include "engine_bodies.cuh"
 #include "engine_dist.cuh"
 #include "engine_extra.cuh"
 
@@ -118,6 +120,14 @@ struct Engine::Impl {
   DBuf<int> selCount;
   DBuf<MaxIdx> miPartial, miResult;
   MaxIdx* h_mi = nullptr;          // pinned, world entries
+
+  // rigid bodies (engine_bodies.cuh): CSR of members + SoA state, 27 doubles per body
+  int nitems = 0;
+  DBuf<int> bFirst, bAtom;
+  DBuf<double> bMItem, bD, bState, bPartial, bScalars, shR0, shQ0, shS0;
+  DBuf<unsigned char> freeMask;    // per atom: 1 = free atom (integrated by k_boost / k_displace), 0 = body member
+  double* h_bscalars = nullptr;    // pinned, 16 doubles
+  bool frames_valid = false;
 
   // reductions
   DBuf<MaxNext> chkPartial;
@@ -273,6 +283,9 @@ Engine::~Engine() {
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
   s.known.release(); s.migCounts.release();
+  s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
+  s.bScalars.release(); s.shR0.release(); s.shQ0.release(); s.shS0.release(); s.freeMask.release();
+  if (s.h_bscalars) cudaFreeHost(s.h_bscalars);
   for (int k = 0; k < 2; ++k) { s.migList[k].release(); s.migSend[k].release(); s.migRecv[k].release(); }
   if (s.h_mi) cudaFreeHost(s.h_mi);
   if (s.comm) nccl().CommDestroy(s.comm);
@@ -1045,6 +1058,228 @@ void Engine::displace(double CR, double CP) {
   }
   s.t_displace += wall_now() - tp0;
   s.n_displace += 1;
+}
+
+// ---- rigid bodies ----------------------------------------------------------------------------------------------
+namespace {
+enum { B_MASS = 0, B_MOI = 1, B_RCM = 4, B_PCM = 7, B_Q = 10, B_PI = 14, B_OMEGA = 18, B_F = 21, B_TAU = 24, B_WIDTH = 27 };
+
+BodyView body_view(Engine::Impl& s) {
+  BodyView v;
+  const size_t nb = (size_t)s.nbodies;
+  v.nb = s.nbodies;
+  v.first = s.bFirst.p; v.atom = s.bAtom.p; v.mItem = s.bMItem.p; v.d = s.bD.p;
+  double* base = s.bState.p;
+  v.mass = base + B_MASS * nb; v.MoI = base + B_MOI * nb; v.rcm = base + B_RCM * nb; v.pcm = base + B_PCM * nb;
+  v.q = base + B_Q * nb; v.pi = base + B_PI * nb; v.omega = base + B_OMEGA * nb; v.Fb = base + B_F * nb;
+  v.tau = base + B_TAU * nb;
+  return v;
+}
+
+void require_single_gpu_bodies(Engine::Impl& s, const char* task) {
+  if (s.world > 1 && s.nbodies != 0) fatal(task, "rigid-body dynamics on several GPUs is not available yet (forces and energies are)");
+}
+}  // namespace
+
+void Engine::set_bodies(const std::vector<int>& first, const std::vector<int>& atoms, const std::vector<double>& memberMass) {
+  Impl& s = *d_;
+  const size_t nb = (size_t)s.nbodies;
+  if (nb == 0) return;
+  s.nitems = (int)atoms.size();
+  s.bFirst.ensure(nb + 1);
+  s.bAtom.ensure(atoms.size());
+  s.bMItem.ensure(atoms.size());
+  s.bD.ensure(3 * atoms.size());
+  s.bState.ensure(B_WIDTH * nb);
+  s.bPartial.ensure((size_t)std::max(nblocks(s.N), nblocks((long long)nb)) * 6);
+  s.bScalars.ensure(16);
+  s.freeMask.ensure(s.N);
+  CUDA_CHECK(cudaMallocHost(&s.h_bscalars, 16 * sizeof(double)));
+  CUDA_CHECK(cudaMemcpy(s.bFirst.p, first.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(s.bAtom.p, atoms.data(), atoms.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(s.bMItem.p, memberMass.data(), atoms.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemset(s.bState.p, 0, B_WIDTH * nb * sizeof(double)));
+  CUDA_CHECK(cudaMemset(s.bD.p, 0, 3 * atoms.size() * sizeof(double)));
+  std::vector<unsigned char> mask(s.N, 1);
+  for (int a : atoms) mask[a] = 0;
+  CUDA_CHECK(cudaMemcpy(s.freeMask.p, mask.data(), s.N, cudaMemcpyHostToDevice));
+}
+
+void Engine::update_body_frames() {
+  Impl& s = *d_;
+  if (s.nbodies == 0) return;
+  if (!s.has_delta || !s.has_R) fatal("rigid-body update", "coordinates have not been uploaded");
+  k_body_frame<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.R.p, s.delta.p);
+  stats_.launches += 1;
+  s.frames_valid = true;
+}
+
+void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool rotate, bool want_kinetic, KineticAll& ke) {
+  Impl& s = *d_;
+  require_single_gpu_bodies(s, "boost");
+  const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
+  const bool bodies = s.nbodies != 0;
+  if (translate && s.nitems < s.N) {   // free atoms
+    const int grid = nblocks((s.N + APT - 1) / APT);
+    k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, bodies ? s.freeMask.p : nullptr, want_kinetic ? 1 : 0,
+                                        s.partial.p, s.tickets.p + 1, s.scalars.p + 10);
+    stats_.launches += 1;
+  }
+  if (bodies) {
+    k_body_boost<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), Fl, s.delta.p, CP, CF, translate ? 1 : 0, rotate ? 1 : 0,
+                                                           want_kinetic ? 1 : 0, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
+    stats_.launches += 1;
+  }
+  if (!want_kinetic) return;
+  double free3[3] = {0, 0, 0}, body6[6] = {0, 0, 0, 0, 0, 0};
+  if (translate && s.nitems < s.N)
+    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  if (bodies) CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  if (translate && s.nitems < s.N)
+    for (int x = 0; x < 3; ++x) free3[x] = s.h_scalars[10 + x];
+  if (bodies)
+    for (int x = 0; x < 6; ++x) body6[x] = s.h_bscalars[x];
+  for (int x = 0; x < 3; ++x) {
+    ke.twoKEt[x] = free3[x] + body6[x];
+    ke.twoKEr[x] = body6[3 + x];
+  }
+}
+
+void Engine::move_all(double CR, double CP, double dt, bool translate, bool rotate, int mode) {
+  Impl& s = *d_;
+  require_single_gpu_bodies(s, "displace");
+  const bool bodies = s.nbodies != 0;
+  if (translate && s.nitems < s.N) {
+    // fused rebuild criterion only when every atom is free (body members move in k_body_move below)
+    k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p,
+                                                                      bodies ? s.freeMask.p : nullptr, s.R0.p, nullptr,
+                                                                      s.tickets.p + 2, s.scalars.p + 8);
+    stats_.launches += 1;
+  }
+  if (bodies) {
+    k_body_move<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.R.p, s.delta.p, CR, CP, dt, translate ? 1 : 0,
+                                                          rotate ? 1 : 0, mode);
+    stats_.launches += 1;
+  }
+  s.check_cached = false;   // compute_forces evaluates the rebuild criterion on the new coordinates
+}
+
+void Engine::refresh_member_momenta() {
+  Impl& s = *d_;
+  if (s.nbodies == 0) return;
+  k_body_momenta<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.delta.p, s.P.p);
+  stats_.launches += 1;
+}
+
+void Engine::take_member_momenta(KineticAll& ke) {
+  Impl& s = *d_;
+  for (int x = 0; x < 3; ++x) ke.twoKEt[x] = ke.twoKEr[x] = 0.0;
+  if (s.nbodies == 0) return;
+  k_body_take_momenta<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.delta.p, s.P.p, s.bPartial.p, s.tickets.p + 3,
+                                                                 s.bScalars.p);
+  stats_.launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  for (int x = 0; x < 3; ++x) {
+    ke.twoKEt[x] = s.h_bscalars[x];
+    ke.twoKEr[x] = s.h_bscalars[3 + x];
+  }
+}
+
+namespace {
+int body_item_offset(int what, int& width) {
+  switch (what) {
+    case Engine::BODY_QUATERNION: width = 4; return B_Q;
+    case Engine::BODY_QUATMOM: width = 4; return B_PI;
+    case Engine::BODY_OMEGA: width = 3; return B_OMEGA;
+    case Engine::BODY_RCM: width = 3; return B_RCM;
+    case Engine::BODY_PCM: width = 3; return B_PCM;
+    case Engine::BODY_FORCE: width = 3; return B_F;
+    case Engine::BODY_TORQUE: width = 3; return B_TAU;
+    case Engine::BODY_INERTIA: width = 3; return B_MOI;
+    default: width = 1; return B_MASS;
+  }
+}
+}  // namespace
+
+// out is body-major (width, nbodies) in the reference's Fortran sense: out[b*width + c]
+void Engine::download_body(int what, double* out) {
+  Impl& s = *d_;
+  const size_t nb = (size_t)s.nbodies;
+  if (nb == 0) return;
+  int width = 0;
+  const int off = body_item_offset(what, width);
+  std::vector<double> soa(width * nb);
+  CUDA_CHECK(cudaMemcpyAsync(soa.data(), s.bState.p + (size_t)off * nb, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  for (size_t b = 0; b < nb; ++b)
+    for (int c = 0; c < width; ++c) out[b * width + c] = soa[(size_t)c * nb + b];
+}
+
+void Engine::upload_body(int what, const double* in) {
+  Impl& s = *d_;
+  const size_t nb = (size_t)s.nbodies;
+  if (nb == 0) return;
+  int width = 0;
+  const int off = body_item_offset(what, width);
+  std::vector<double> soa(width * nb);
+  for (size_t b = 0; b < nb; ++b)
+    for (int c = 0; c < width; ++c) soa[(size_t)c * nb + b] = in[b * width + c];
+  CUDA_CHECK(cudaMemcpy(s.bState.p + (size_t)off * nb, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+void Engine::derive_quaternion_momenta() {
+  Impl& s = *d_;
+  if (s.nbodies == 0) return;
+  k_body_set_omega<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s));
+  stats_.launches += 1;
+}
+
+void Engine::shadow_pre(int layer0, double dt, int mode) {
+  Impl& s = *d_;
+  require_single_gpu_bodies(s, "verlet_step");
+  if (s.world > 1) fatal("verlet_step", "the shadow-Hamiltonian bookkeeping is not available on several GPUs");
+  const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
+  const bool bodies = s.nbodies != 0;
+  if (bodies) {
+    s.shR0.ensure(3 * (size_t)s.nbodies);
+    s.shQ0.ensure(4 * (size_t)s.nbodies);
+    k_shadow_pre_bodies<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), dt, mode, s.shR0.p, s.shQ0.p);
+    stats_.launches += 1;
+  }
+  if (s.nitems < s.N) {
+    s.shS0.ensure(3 * (size_t)s.N);
+    k_shadow_pre_atoms<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, bodies ? s.freeMask.p : nullptr, dt, s.R.p, s.P.p, Fl, s.invMass.p,
+                                                           s.shS0.p);
+    stats_.launches += 1;
+  }
+}
+
+void Engine::shadow_post(int layer0, double dt, int mode, double& Us, double& Ks_t, double& Ks_r) {
+  Impl& s = *d_;
+  const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
+  const bool bodies = s.nbodies != 0;
+  if (!bodies) {   // the reduction buffers of the body path are created by set_bodies
+    s.bPartial.ensure((size_t)nblocks(s.N) * 6);
+    s.bScalars.ensure(16);
+    if (s.h_bscalars == nullptr) CUDA_CHECK(cudaMallocHost(&s.h_bscalars, 16 * sizeof(double)));
+  }
+  Us = Ks_t = Ks_r = 0.0;
+  if (bodies) {
+    k_shadow_post_bodies<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), dt, mode, s.shR0.p, s.shQ0.p, s.bPartial.p,
+                                                                   s.tickets.p + 3, s.bScalars.p);
+    stats_.launches += 1;
+  }
+  if (s.nitems < s.N) {
+    k_shadow_post_atoms<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, bodies ? s.freeMask.p : nullptr, dt, s.R.p, s.P.p, Fl, s.invMass.p,
+                                                            s.shS0.p, s.bPartial.p, s.tickets.p + 3, s.bScalars.p + 8);
+    stats_.launches += 1;
+  }
+  CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  if (bodies) { Us += s.h_bscalars[0]; Ks_t += s.h_bscalars[1]; Ks_r += s.h_bscalars[2]; }
+  if (s.nitems < s.N) { Us += s.h_bscalars[8]; Ks_t += s.h_bscalars[9]; }
 }
 
 long long Engine::pair_count() { return download_pairs(nullptr, 0); }

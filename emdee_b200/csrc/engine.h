@@ -35,6 +35,11 @@ struct KineticScalars {
   double twoKE[3] = {0, 0, 0};   // sum over free atoms of p^2/m per dimension
 };
 
+struct KineticAll {
+  double twoKEt[3] = {0, 0, 0};  // free atoms p^2/m + bodies pcm^2/M, per dimension
+  double twoKEr[3] = {0, 0, 0};  // bodies I*omega^2, per principal axis
+};
+
 struct EngineStats {
   long long launches = 0, force_launches = 0, build_launches = 0;
   double force_ms = 0, build_ms = 0;
@@ -73,6 +78,21 @@ class Engine {
   // ---- device-resident dynamics for free atoms (reference boost / move / kinetic_energies) --
   void boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke);
   void displace(double CR, double CP);
+
+  // ---- rigid bodies (reference src/ArBee.f90; device-resident, one thread per body) -------------
+  enum BodyItem { BODY_QUATERNION, BODY_QUATMOM, BODY_OMEGA, BODY_RCM, BODY_PCM, BODY_FORCE, BODY_TORQUE, BODY_INERTIA };
+  void set_bodies(const std::vector<int>& first, const std::vector<int>& atoms,
+                  const std::vector<double>& memberMass);                // CSR of body members (0-based atoms)
+  void update_body_frames();                                             // tBody_update after coordinates + delta uploads
+  void boost_all(int layer0, double CP, double CF, bool translate, bool rotate, bool want_kinetic, KineticAll& ke);
+  void move_all(double CR, double CP, double dt, bool translate, bool rotate, int mode);
+  void refresh_member_momenta();                                         // particle_momenta into P (before download_momenta)
+  void take_member_momenta(KineticAll& ke);                              // assign_momenta from P (after upload_momenta)
+  void download_body(int what, double* out);                             // (width, nbodies), out[b*width + c]
+  void upload_body(int what, const double* in);
+  void derive_quaternion_momenta();                                      // pi = B(q) 2 I omega
+  void shadow_pre(int layer0, double dt, int mode);                      // EmDee_verlet_step pre_force bookkeeping
+  void shadow_post(int layer0, double dt, int mode, double& Us, double& Ks_t, double& Ks_r);
 
   // ---- extensions --------------------------------------------------------------------------
   long long pair_count();

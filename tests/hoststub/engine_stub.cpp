@@ -54,6 +54,17 @@ bool Engine::compute_forces(int, bool, double, ForceScalars& out, double&) {
 }
 void Engine::boost(int, double, double, bool, KineticScalars& ke) { ke = KineticScalars(); }
 void Engine::displace(double, double) {}
+void Engine::set_bodies(const std::vector<int>&, const std::vector<int>&, const std::vector<double>&) {}
+void Engine::update_body_frames() {}
+void Engine::boost_all(int, double, double, bool, bool, bool, KineticAll& ke) { ke = KineticAll(); }
+void Engine::move_all(double, double, double, bool, bool, int) {}
+void Engine::refresh_member_momenta() {}
+void Engine::take_member_momenta(KineticAll& ke) { ke = KineticAll(); }
+void Engine::download_body(int, double*) {}
+void Engine::upload_body(int, const double*) {}
+void Engine::derive_quaternion_momenta() {}
+void Engine::shadow_pre(int, double, int) {}
+void Engine::shadow_post(int, double, int, double& a, double& b, double& c) { a = b = c = 0.0; }
 long long Engine::pair_count() { return 0; }
 void Engine::update_list_stats(int, double) {}
 long long Engine::download_pairs(int*, long long) { return 0; }
