@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -303,7 +304,8 @@ struct RigidBody {   // the part of reference tBody (src/ArBee.f90:29-106) the h
 
 struct System {
   int N = 0, ntypes = 1, nlayers = 1, layer = 1, threads = 1;
-  double Rc = 0, skin = 0, InRc = 0, Lbox = 0, totalMass = 0, startTime = 0;
+  double Rc = 0, skin = 0, InRc = 0, totalMass = 0, startTime = 0;
+  std::shared_ptr<double> box = std::make_shared<double>(0.0);   // me%Lbox is a pointer in the reference: shared by EmDee_share_phase_space
   bool hasL = false, hasR = false, initialized = false, kspace_active = false;
   std::vector<int> type;                 // 1-based type of each atom
   std::vector<double> mass, invMass, charge;
@@ -419,7 +421,7 @@ void setup_bodies(System& me, const int* bodies) {
 // src/EmDeeData.f90:420-439 + src/ArBee.f90:97-106: make each body whole w.r.t. its first atom, then
 // delta = r - r_cm. Runs on the host copy of an uploaded configuration, before it is sent to HBM.
 void update_rigid_bodies(System& me, std::vector<double>& delta) {
-  const double L = me.Lbox, invL = 1.0 / L;
+  const double L = *me.box, invL = 1.0 / L;
   delta.assign(3 * (size_t)me.N, 0.0);
   for (const RigidBody& b : me.bodies) {
     const int first = b.atoms[0];
@@ -655,12 +657,42 @@ tEmDee EmDee_system(int threads, int layers, double rc, double skin, int N, int*
   return md;
 }
 
-void* EmDee_memory_address(tEmDee, const char*) {
-  // The reference hands out raw pointers into its host arrays (src/EmDeeCode.f90:212-235); here the
-  // state lives in HBM. Use EmDee_upload / EmDee_download.
-  unsupported("memory address retrieving");
+// src/EmDeeCode.f90:212-235. The returned pointer addresses the library's own array (moved into CUDA managed memory
+// on first request, see Engine::expose): valid on the host between library calls, for reading and for writing.
+void* EmDee_memory_address(tEmDee md, const char* option) {
+  System* me = sys(md);
+  const std::string item = opt(option);
+  if (item == "coordinates") {
+    if (!me->hasR) error("memory address retrieving", "coordinates have not been allocated");   // unassociated pointer in the reference
+    return me->engine->expose(Engine::EXPOSE_R, 0);
+  }
+  if (item == "momenta") return me->engine->expose(Engine::EXPOSE_P, 0);
+  if (item == "forces") return me->engine->expose(Engine::EXPOSE_F, me->layer - 1);
+  if (item == "layerForces") return me->engine->expose(Engine::EXPOSE_LAYER_F, 0);
+  error("memory address retrieving", "invalid option " + item);
 }
-void EmDee_share_phase_space(tEmDee, tEmDee*) { unsupported("phase space sharing"); }
+
+// src/EmDeeCode.f90:239-269
+void EmDee_share_phase_space(tEmDee mdkeep, tEmDee* mdlose) {
+  const char* task = "phase space sharing";
+  System* keep = sys(mdkeep);
+  System* lose = sys(*mdlose);
+  if (!(keep->initialized && lose->initialized)) error(task, "EmDee system 1 has not been initialized");
+  if (keep->N != lose->N) error(task, "different numbers of atoms");
+  if (keep->type != lose->type) error(task, "atom types do not match");
+  if (keep->mass != lose->mass) error(task, "atom masses do not match");
+  if (keep->atomBody != lose->atomBody) error(task, "rigid bodies do not match");
+  if (keep != lose) {
+    lose->engine->share_phase_space(*keep->engine);
+    lose->box = keep->box;
+  }
+  mdlose->Kinetic.Total = mdkeep.Kinetic.Total;
+  mdlose->Kinetic.Rotational = mdkeep.Kinetic.Rotational;
+  for (int x = 0; x < 3; ++x) {
+    mdlose->Kinetic.TransPart[x] = mdkeep.Kinetic.TransPart[x];
+    mdlose->Kinetic.RotPart[x] = mdkeep.Kinetic.RotPart[x];
+  }
+}
 
 void EmDee_layer_based_parameters(tEmDee md, double InternalRc, int* Apply, int* Bonded) {
   const char* task = "layer-based parameter setting";
@@ -783,7 +815,7 @@ void EmDee_download(tEmDee md, const char* option, double* address) {
   const std::string item = opt(option);
   if (address == nullptr) error("download", "provided address is invalid");
   if (item == "box") {
-    *address = me->Lbox;
+    *address = *me->box;
   } else if (item == "coordinates") {
     if (!me->hasR) error("download", "coordinates have not been allocated");
     me->engine->download_coordinates(address);
@@ -857,7 +889,7 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/Em
   };
   if (item == "box") {
     me->hasL = true;
-    me->Lbox = *address;
+    *me->box = *address;
     if (me->initialized) invalidate(*me, md);
     else if (me->hasR) initialize_system();
   } else if (item == "coordinates") {
@@ -1015,7 +1047,7 @@ void EmDee_displace(tEmDee* md, double lambda, double alpha, double dt) {   // s
   if (alpha != 0.0) {
     CP = phi(alpha * dt) * dt;
     CR = 1.0 - alpha * CP;
-    me->Lbox = CR * me->Lbox;
+    *me->box = CR * *me->box;
   }
   CP = lambda * CP;
   if (me->nbodies() != 0)
@@ -1063,7 +1095,7 @@ void EmDee_compute_forces(tEmDee* md) {   // src/EmDeeCode.f90:1215-1277
   emdee::ForceScalars r;
   double tn = 0.0;
   const double t0 = now();
-  const bool rebuilt = me->engine->compute_forces(me->layer - 1, compute, me->Lbox, r, tn);
+  const bool rebuilt = me->engine->compute_forces(me->layer - 1, compute, *me->box, r, tn);
   if (rebuilt) md->Builds += 1;
   md->Time.Neighbor += tn;
   double Wlong = 0.0;
@@ -1117,9 +1149,9 @@ void EmDee_rdf(tEmDee md, int bins, double Rc, int pairs, int* itype, int* jtype
       const int a = itype[k], b = jtype[l];
       pairSym[(size_t)(a - 1) * nt + (b - 1)] = pairSym[(size_t)(b - 1) * nt + (a - 1)] = (unsigned short)symm1D(a, b);
     }
-  const double invL = 1.0 / me->Lbox;
+  const double invL = 1.0 / *me->box;
   std::vector<long long> counts;
-  me->engine->rdf(me->Lbox, bins, Rc * Rc * invL * invL, bins / (Rc * invL), pairSym, nsym, counts);
+  me->engine->rdf(*me->box, bins, Rc * Rc * invL * invL, bins / (Rc * invL), pairSym, nsym, counts);
   const double Pi4_3 = 4.188790204786391;
   const double w = Rc * invL / bins;
   const double shell0 = Pi4_3 * (w * w * w);
@@ -1210,7 +1242,7 @@ void EmDeeX_finalize(tEmDee* md) {
 }
 void EmDeeX_stats(tEmDee md, tEmDeeXStats* out) {
   System* me = sys(md);
-  if (me->initialized) me->engine->update_list_stats(me->layer - 1, me->Lbox);
+  if (me->initialized) me->engine->update_list_stats(me->layer - 1, *me->box);
   emdee::EngineStats s = me->engine->stats();
   out->launches = s.launches;
   out->force_launches = s.force_launches;

@@ -128,6 +128,9 @@ struct Engine::Impl {
   DBuf<unsigned char> freeMask;    // per atom: 1 = free atom (integrated by k_boost / k_displace), 0 = body member
   double* h_bscalars = nullptr;    // pinned, 16 doubles
   bool frames_valid = false;
+  // EmDee_memory_address / EmDee_share_phase_space: coordinates may change behind the engine's back
+  bool exposed = false;            // a raw pointer to R, P or F was handed out: every call ends with a stream sync
+  bool foreign_R = false;          // R is written by the client or by another system: never trust the cached criterion
 
   // reductions
   DBuf<MaxNext> chkPartial;
@@ -653,6 +656,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   auto t_start = std::chrono::steady_clock::now();
 
   const double tp0 = wall_now();
+  if (s.foreign_R) s.check_cached = false;
   // ---- K0: rebuild trigger (reference handle_neighbor_lists) -----------------------------------
   bool rebuild;
   if (s.world > 1 && s.owned_valid) {
@@ -1033,6 +1037,8 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
     CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.h_scalars[10 + x];
+  } else if (s.exposed) {
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
   }
   s.t_boost += wall_now() - tp0;
   s.n_boost += 1;
@@ -1056,6 +1062,7 @@ void Engine::displace(double CR, double CP) {
     CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
     s.check_cached = true;
   }
+  if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
   s.t_displace += wall_now() - tp0;
   s.n_displace += 1;
 }
@@ -1130,7 +1137,10 @@ void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool ro
                                                            want_kinetic ? 1 : 0, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
     stats_.launches += 1;
   }
-  if (!want_kinetic) return;
+  if (!want_kinetic) {
+    if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    return;
+  }
   double free3[3] = {0, 0, 0}, body6[6] = {0, 0, 0, 0, 0, 0};
   if (translate && s.nitems < s.N)
     CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -1163,6 +1173,45 @@ void Engine::move_all(double CR, double CP, double dt, bool translate, bool rota
     stats_.launches += 1;
   }
   s.check_cached = false;   // compute_forces evaluates the rebuild criterion on the new coordinates
+  if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+// ---- EmDee_memory_address / EmDee_share_phase_space ---------------------------------------------------------------
+// The reference hands out pointers into its own host arrays (src/EmDeeCode.f90:212-235). Here the arrays live in HBM,
+// so the requested array is moved into CUDA managed memory once: the SAME allocation is then the kernels' array and
+// the client's. Contract: the client touches it only between library calls (every call now ends with a stream
+// synchronisation), and -- as with the reference -- writing coordinates through the pointer does not invalidate
+// anything by itself; the next EmDee_compute_forces re-evaluates the rebuild criterion on whatever it finds.
+void* Engine::expose(int what, int layer0) {
+  Impl& s = *d_;
+  if (s.world > 1) fatal("memory address retrieving", "not available on several GPUs (every rank holds a slab)");
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  s.exposed = true;
+  switch (what) {
+    case EXPOSE_R: s.R.to_managed(); s.foreign_R = true; return s.R.p;
+    case EXPOSE_P: s.P.to_managed(); return s.P.p;
+    case EXPOSE_F: s.F.to_managed(); return s.F.p + (size_t)layer0 * 3 * s.N;
+    default: s.F.to_managed(); return s.F.p;
+  }
+}
+
+// `this` gives up its own R, P and rigid-body state for `keep`'s (src/EmDeeCode.f90:259-263)
+void Engine::share_phase_space(Engine& keep) {
+  Impl& s = *d_;
+  Impl& k = *keep.d_;
+  if (s.world > 1 || k.world > 1) fatal("phase space sharing", "not available on several GPUs");
+  if (s.device != k.device) fatal("phase space sharing", "the two systems live on different GPUs");
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  s.R.alias(k.R);
+  s.P.alias(k.P);
+  if (s.nbodies != 0) {
+    s.delta.alias(k.delta);
+    s.bState.alias(k.bState);
+    s.bD.alias(k.bD);
+  }
+  s.foreign_R = k.foreign_R = true;   // either system may now move the atoms
+  s.check_cached = k.check_cached = false;
+  s.exposed = s.exposed || k.exposed;
 }
 
 void Engine::refresh_member_momenta() {

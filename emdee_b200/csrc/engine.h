@@ -94,6 +94,11 @@ class Engine {
   void shadow_pre(int layer0, double dt, int mode);                      // EmDee_verlet_step pre_force bookkeeping
   void shadow_post(int layer0, double dt, int mode, double& Us, double& Ks_t, double& Ks_r);
 
+  // ---- raw pointers and aliasing (reference EmDee_memory_address / EmDee_share_phase_space) ------
+  enum Exposed { EXPOSE_R, EXPOSE_P, EXPOSE_F, EXPOSE_LAYER_F };
+  void* expose(int what, int layer0);            // host-dereferenceable pointer to the library's own array
+  void share_phase_space(Engine& keep);          // this system gives up R, P, body state for keep's
+
   // ---- extensions --------------------------------------------------------------------------
   long long pair_count();
   void update_list_stats(int layer0, double Lbox);   // fills list_entries / interacting

@@ -25,17 +25,51 @@ template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  int* refs = nullptr;    // non-null once two systems share this allocation (EmDee_share_phase_space)
+  bool managed = false;   // cudaMallocManaged: the client holds a raw pointer to it (EmDee_memory_address)
   void ensure(size_t m, double slack = 1.0) {
     if (m > n) {
+      if (refs != nullptr) fatal("device buffer", "a shared phase-space array cannot be resized");
       if (p) CUDA_CHECK(cudaFree(p));
       n = (size_t)(m * slack) + 16;
-      CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+      if (managed) CUDA_CHECK(cudaMallocManaged(&p, n * sizeof(T)));
+      else CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
     }
   }
   void release() {
+    if (refs != nullptr && --*refs > 0) {   // another system still uses the allocation
+      p = nullptr;
+      refs = nullptr;
+      n = 0;
+      return;
+    }
+    delete refs;
+    refs = nullptr;
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
+  }
+  // this buffer becomes a second name for `o`'s allocation (reference: `lose%R => keep%R`)
+  void alias(DBuf& o) {
+    if (p == o.p) return;
+    release();
+    if (o.refs == nullptr) o.refs = new int(1);
+    ++*o.refs;
+    p = o.p;
+    n = o.n;
+    refs = o.refs;
+    managed = o.managed;
+  }
+  // move the contents into managed memory so that a host pointer to them can be handed out
+  void to_managed() {
+    if (managed || p == nullptr) return;
+    if (refs != nullptr) fatal("memory address retrieving", "request the address before EmDee_share_phase_space");
+    T* q = nullptr;
+    CUDA_CHECK(cudaMallocManaged(&q, n * sizeof(T)));
+    CUDA_CHECK(cudaMemcpy(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice));
+    CUDA_CHECK(cudaFree(p));
+    p = q;
+    managed = true;
   }
 };
 

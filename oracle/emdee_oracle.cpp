@@ -36,6 +36,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -1048,21 +1049,27 @@ struct Body {
 // ---- system state (src/EmDeeData.f90:66-151) -----------------------------------------------------
 struct Cell { int neighbor[nbcells]; };
 
+// What EmDee_share_phase_space aliases between two systems (src/EmDeeCode.f90:260-263: R, P, body, Lbox pointers)
+struct Phase {
+  bool hasL = false, hasR = false;
+  double Lbox = 0;
+  std::vector<double> R, P;
+  std::vector<Body> body;
+};
+
 struct System {
   int natoms = 0, mcells = 0, ncells = 0, maxcells = 0, maxatoms = 0, maxpairs = 0, ntypes = 1;
   int nbodies = 0, nfree = 0, nthreads = 1, threadAtoms = 0, threadFreeAtoms = 0, threadBodies = 0;
   int nlayers = 1, layer = 1;
-  bool hasL = false, hasR = false;
-  double Lbox = 0;
+  std::shared_ptr<Phase> ph = std::make_shared<Phase>();   // R, P, bodies, box (shared after EmDee_share_phase_space)
   double Rc = 0, skin = 0, RcSq = 0, xRc = 0, xRcSq = 0, skinSq = 0, InRc = 0, InRcSq = 0, xInRcSq = 0;
   double totalMass = 0, startTime = 0;
   bool initialized = false;
   Kiss random;
   List cellAtom, threadCell, excluded;
   std::vector<int> atomType, atomCell, atomBody, free_, atomsInCell;
-  std::vector<double> R, P, charge, mass, invMass, R0;
+  std::vector<double> charge, mass, invMass, R0;
   std::vector<char> charged;
-  std::vector<Body> body;
   std::vector<Cell> cell;
   std::vector<List> neighbor;
   std::vector<PairContainer> pair;   // (ntypes, ntypes, nlayers)
@@ -1141,15 +1148,15 @@ void allocate_rigid_bodies(System& me, const int* bodies) {
     for (int i = 0; i < N; ++i)
       if (me.atomBody[i] == 0) me.free_.push_back(i);
     me.nfree = (int)me.free_.size();
-    me.body.assign(me.nbodies, Body());
+    me.ph->body.assign(me.nbodies, Body());
     for (int i = 0; i < N; ++i) {
       int b = me.atomBody[i];
       if (b > 0) {
-        me.body[b - 1].index.push_back(i);
-        me.body[b - 1].M.push_back(me.mass[i]);
+        me.ph->body[b - 1].index.push_back(i);
+        me.ph->body[b - 1].M.push_back(me.mass[i]);
       }
     }
-    for (auto& b : me.body) {   // tBody_setup, src/ArBee.f90:78-93
+    for (auto& b : me.ph->body) {   // tBody_setup, src/ArBee.f90:78-93
       b.NP = (int)b.index.size();
       b.mass = 0.0;
       for (double mm : b.M) b.mass += mm;
@@ -1168,7 +1175,7 @@ void allocate_rigid_bodies(System& me, const int* bodies) {
       me.atomBody[i] = i + 1;
     }
     me.nfree = N;
-    me.body.clear();
+    me.ph->body.clear();
   }
   me.threadFreeAtoms = (me.nfree + me.nthreads - 1) / me.nthreads;
   me.threadBodies = (me.nbodies + me.nthreads - 1) / me.nthreads;
@@ -1176,18 +1183,18 @@ void allocate_rigid_bodies(System& me, const int* bodies) {
 
 // src/EmDeeData.f90:420-439: make each body whole with respect to its first atom, then tBody_update
 void update_rigid_bodies(System& me) {
-  const double L = me.Lbox, invL = 1.0 / L;
+  const double L = me.ph->Lbox, invL = 1.0 / L;
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
   for (int j = 0; j < me.nbodies; ++j) {
-    Body& b = me.body[j];
+    Body& b = me.ph->body[j];
     std::vector<double> R(3 * b.NP);
     for (int i = 0; i < b.NP; ++i)
-      for (int x = 0; x < 3; ++x) R[3 * i + x] = me.R[3 * (size_t)b.index[i] + x];
+      for (int x = 0; x < 3; ++x) R[3 * i + x] = me.ph->R[3 * (size_t)b.index[i] + x];
     for (int i = 1; i < b.NP; ++i)
       for (int x = 0; x < 3; ++x) R[3 * i + x] = R[3 * i + x] - L * std::round(invL * (R[3 * i + x] - R[x]));
     b.update(R);
     for (int i = 0; i < b.NP; ++i)
-      for (int x = 0; x < 3; ++x) me.R[3 * (size_t)b.index[i] + x] = R[3 * i + x];
+      for (int x = 0; x < 3; ++x) me.ph->R[3 * (size_t)b.index[i] + x] = R[3 * i + x];
   }
 }
 
@@ -1196,24 +1203,24 @@ void move(System& me, double R_factor, double P_factor, double dt, bool translat
   if (translate) {
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
     for (int i = 0; i < me.nbodies; ++i) {
-      Body& b = me.body[i];
+      Body& b = me.ph->body[i];
       for (int x = 0; x < 3; ++x) b.rcm[x] = R_factor * b.rcm[x] + P_factor * b.invMass * b.pcm[x];
     }
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
     for (int f = 0; f < me.nfree; ++f) {
       const int j = me.free_[f];
       for (int x = 0; x < 3; ++x)
-        me.R[3 * (size_t)j + x] = R_factor * me.R[3 * (size_t)j + x] + P_factor * me.P[3 * (size_t)j + x] * me.invMass[j];
+        me.ph->R[3 * (size_t)j + x] = R_factor * me.ph->R[3 * (size_t)j + x] + P_factor * me.ph->P[3 * (size_t)j + x] * me.invMass[j];
     }
   }
   if (rotate) {
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
     for (int i = 0; i < me.nbodies; ++i) {
-      Body& b = me.body[i];
+      Body& b = me.ph->body[i];
       if (mode == 0) b.rotate_exact(dt);
       else b.rotate_no_squish(dt, mode);
       for (int k = 0; k < b.NP; ++k)
-        for (int x = 0; x < 3; ++x) me.R[3 * (size_t)b.index[k] + x] = b.rcm[x] + b.delta[3 * k + x];
+        for (int x = 0; x < 3; ++x) me.ph->R[3 * (size_t)b.index[k] + x] = b.rcm[x] + b.delta[3 * k + x];
     }
   }
 }
@@ -1221,24 +1228,24 @@ void move(System& me, double R_factor, double P_factor, double dt, bool translat
 // src/EmDeeData.f90:864-896
 void boost(System& me, double P_factor, double F_factor, const double* F, bool translate, bool rotate) {
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
-  for (int i = 0; i < me.nbodies; ++i) me.body[i].force_and_torque(F);
+  for (int i = 0; i < me.nbodies; ++i) me.ph->body[i].force_and_torque(F);
   if (translate) {
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
     for (int i = 0; i < me.nbodies; ++i) {
-      Body& b = me.body[i];
+      Body& b = me.ph->body[i];
       for (int x = 0; x < 3; ++x) b.pcm[x] = P_factor * b.pcm[x] + F_factor * b.F[x];
     }
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
     for (int f = 0; f < me.nfree; ++f) {
       const int j = me.free_[f];
-      for (int x = 0; x < 3; ++x) me.P[3 * (size_t)j + x] = P_factor * me.P[3 * (size_t)j + x] + F_factor * F[3 * (size_t)j + x];
+      for (int x = 0; x < 3; ++x) me.ph->P[3 * (size_t)j + x] = P_factor * me.ph->P[3 * (size_t)j + x] + F_factor * F[3 * (size_t)j + x];
     }
   }
   if (rotate) {
     const double Ctau = 2.0 * F_factor;
 #pragma omp parallel for num_threads(me.nthreads) schedule(static)
     for (int i = 0; i < me.nbodies; ++i) {
-      Body& b = me.body[i];
+      Body& b = me.ph->body[i];
       const double t3[3] = {Ctau * b.tau[0], Ctau * b.tau[1], Ctau * b.tau[2]};
       double t4[4], np[4];
       mulC(b.q, t3, t4);
@@ -1256,10 +1263,10 @@ void kinetic_energies(const System& me, bool translate, bool rotate, double twoK
     for (int t = 1; t <= T; ++t) {
       double k[3] = {0, 0, 0};
       for (int i = (t - 1) * me.threadBodies; i < std::min(t * me.threadBodies, me.nbodies); ++i)
-        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.body[i].invMass * me.body[i].pcm[x] * me.body[i].pcm[x];
+        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.ph->body[i].invMass * me.ph->body[i].pcm[x] * me.ph->body[i].pcm[x];
       for (int f = (t - 1) * me.threadFreeAtoms; f < std::min(t * me.threadFreeAtoms, me.nfree); ++f) {
         const int j = me.free_[f];
-        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.invMass[j] * me.P[3 * (size_t)j + x] * me.P[3 * (size_t)j + x];
+        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.invMass[j] * me.ph->P[3 * (size_t)j + x] * me.ph->P[3 * (size_t)j + x];
       }
       for (int x = 0; x < 3; ++x) twoKEt[x] += k[x];
     }
@@ -1269,7 +1276,7 @@ void kinetic_energies(const System& me, bool translate, bool rotate, double twoK
     for (int t = 1; t <= T; ++t) {
       double k[3] = {0, 0, 0};
       for (int i = (t - 1) * me.threadBodies; i < std::min(t * me.threadBodies, me.nbodies); ++i)
-        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.body[i].MoI[x] * me.body[i].omega[x] * me.body[i].omega[x];
+        for (int x = 0; x < 3; ++x) k[x] = k[x] + me.ph->body[i].MoI[x] * me.ph->body[i].omega[x] * me.ph->body[i].omega[x];
       for (int x = 0; x < 3; ++x) twoKEr[x] += k[x];
     }
   }
@@ -1281,12 +1288,12 @@ void assign_momenta(System& me, const double* P, double twoKEt[3], double twoKEr
   for (int f = 0; f < me.nfree; ++f) {
     const int i = me.free_[f];
     for (int x = 0; x < 3; ++x) {
-      me.P[3 * (size_t)i + x] = P[3 * (size_t)i + x];
+      me.ph->P[3 * (size_t)i + x] = P[3 * (size_t)i + x];
       twoKEt[x] += me.invMass[i] * P[3 * (size_t)i + x] * P[3 * (size_t)i + x];
     }
   }
   for (int i = 0; i < me.nbodies; ++i) {
-    Body& b = me.body[i];
+    Body& b = me.ph->body[i];
     double L[3] = {0, 0, 0};
     for (int x = 0; x < 3; ++x) b.pcm[x] = 0.0;
     for (int j = 0; j < b.NP; ++j) {
@@ -1380,7 +1387,7 @@ void perform_initialization(System& me, int& DoF, int& RotDoF) {
   const char* task = "system initialization";
   update_rigid_bodies(me);
   int bodyDoF = 0;
-  for (auto& b : me.body) bodyDoF += b.dof;
+  for (auto& b : me.ph->body) bodyDoF += b.dof;
   RotDoF = bodyDoF - 3 * me.nbodies;
   DoF = 3 * me.nfree + bodyDoF - 3;
   check_actual_interactions(me);
@@ -1532,7 +1539,7 @@ inline double pbc(double x) { return x - std::round(x); }   // x - anint(x)
 
 // src/neighbor_lists.f90:199-300
 void build_neighbor_lists(System& me, int thread, const double* Rs) {
-  const double invL2 = 1.0 / (me.Lbox * me.Lbox);
+  const double invL2 = 1.0 / (me.ph->Lbox * me.ph->Lbox);
   const double xRc2 = me.xRcSq * invL2;
   const double xInRc2 = me.xInRcSq * invL2;
   std::vector<char> include(me.natoms, 1);
@@ -1603,10 +1610,10 @@ void build_neighbor_lists(System& me, int thread, const double* Rs) {
 // src/neighbor_lists.f90:175-195
 void handle_neighbor_lists(System& me, int& builds, double& time, const double* Rs) {
   time -= omp_get_wtime();
-  if (maximum_approach_sq(me.natoms, me.R.data(), me.R0.data()) > me.skinSq) {
-    int M = (int)std::floor(ndiv * me.Lbox / me.xRc);
+  if (maximum_approach_sq(me.natoms, me.ph->R.data(), me.R0.data()) > me.skinSq) {
+    int M = (int)std::floor(ndiv * me.ph->Lbox / me.xRc);
     distribute_atoms(me, std::max(M, 2 * ndiv + 1), Rs);
-    me.R0 = me.R;
+    me.R0 = me.ph->R;
     builds += 1;
 #pragma omp parallel num_threads(me.nthreads)
     build_neighbor_lists(me, omp_get_thread_num() + 1, Rs);
@@ -1625,7 +1632,7 @@ void compute_pairs(System& me, int thread, const double* Rs, double* F, double& 
   Epair = 0.0;
   // NOTE: Ecoul is intent(out) in the reference but only ever accumulated; the caller zeroes E(:).
   if (!me.pairs_exist[me.layer - 1]) return;
-  const double L2 = me.Lbox * me.Lbox;
+  const double L2 = me.ph->Lbox * me.ph->Lbox;
   const double invL2 = 1.0 / L2;
   double Rc2;
   const std::vector<int>* upper;
@@ -1685,7 +1692,7 @@ void compute_pairs(System& me, int thread, const double* Rs, double* F, double& 
     }
     for (int x = 0; x < 3; ++x) F[3 * (size_t)(i - 1) + x] = F[3 * (size_t)(i - 1) + x] + Fi[x];
   }
-  for (size_t q = 0; q < 3 * (size_t)N; ++q) F[q] = me.Lbox * F[q];
+  for (size_t q = 0; q < 3 * (size_t)N; ++q) F[q] = me.ph->Lbox * F[q];
 }
 
 // src/EmDeeData.f90:926-953
@@ -1697,7 +1704,7 @@ double rigid_body_virial(System& me) {
     double w = 0.0;
     const double* F = me.F();
     for (int i = (thread - 1) * me.threadBodies + 1; i <= std::min(thread * me.threadBodies, me.nbodies); ++i) {
-      const Body& b = me.body[i - 1];
+      const Body& b = me.ph->body[i - 1];
       double s = 0.0;
       for (int a = 0; a < b.NP; ++a)
         for (int x = 0; x < 3; ++x) s += F[3 * (size_t)b.index[a] + x] * b.delta[3 * a + x];
@@ -1771,7 +1778,7 @@ tEmDee EmDee_system(int threads, int layers, double rc, double skin, int N, int*
     me->totalMass = (double)N;
   }
   me->startTime = omp_get_wtime();
-  me->P.assign(3 * (size_t)N, 0.0);
+  me->ph->P.assign(3 * (size_t)N, 0.0);
   me->R0.assign(3 * (size_t)N, 0.0);
   me->charge.assign(N, 0.0);
   me->charged.assign(N, 0);
@@ -1818,14 +1825,31 @@ tEmDee EmDee_system(int threads, int layers, double rc, double skin, int N, int*
 void* EmDee_memory_address(tEmDee md, const char* option) {
   System* me = sys(md);
   std::string item = option_string(option);
-  if (item == "coordinates") return me->R.data();
-  if (item == "momenta") return me->P.data();
+  if (item == "coordinates") return me->ph->R.data();
+  if (item == "momenta") return me->ph->P.data();
   if (item == "forces") return me->F();
   if (item == "layerForces") return me->layerF.data();
   error("memory address retrieving", "invalid option " + item);
 }
 
-void EmDee_share_phase_space(tEmDee, tEmDee*) { out_of_scope("phase space sharing"); }
+// src/EmDeeCode.f90:239-269
+void EmDee_share_phase_space(tEmDee mdkeep, tEmDee* mdlose) {
+  const char* task = "phase space sharing";
+  System* keep = sys(mdkeep);
+  System* lose = sys(*mdlose);
+  if (!(keep->initialized && lose->initialized)) error(task, "EmDee system 1 has not been initialized");
+  if (keep->natoms != lose->natoms) error(task, "different numbers of atoms");
+  if (keep->atomType != lose->atomType) error(task, "atom types do not match");
+  if (keep->mass != lose->mass) error(task, "atom masses do not match");
+  if (keep->atomBody != lose->atomBody) error(task, "rigid bodies do not match");
+  lose->ph = keep->ph;
+  mdlose->Kinetic.Total = mdkeep.Kinetic.Total;
+  mdlose->Kinetic.Rotational = mdkeep.Kinetic.Rotational;
+  for (int x = 0; x < 3; ++x) {
+    mdlose->Kinetic.TransPart[x] = mdkeep.Kinetic.TransPart[x];
+    mdlose->Kinetic.RotPart[x] = mdkeep.Kinetic.RotPart[x];
+  }
+}
 
 // src/EmDeeCode.f90:273-305
 void EmDee_layer_based_parameters(tEmDee md, double InternalRc, int* Apply, int* Bonded) {
@@ -1980,14 +2004,14 @@ void EmDee_download(tEmDee md, const char* option, double* address) {
   if (address == nullptr) error("download", "provided address is invalid");
   const size_t n3 = 3 * (size_t)me->natoms;
   if (item == "box") {
-    *address = me->Lbox;
+    *address = me->ph->Lbox;
   } else if (item == "coordinates") {
-    if (!me->hasR) error("download", "coordinates have not been allocated");
-    std::copy(me->R.begin(), me->R.end(), address);
+    if (!me->ph->hasR) error("download", "coordinates have not been allocated");
+    std::copy(me->ph->R.begin(), me->ph->R.end(), address);
   } else if (item == "momenta") {   // get_momenta (726-736)
     for (int f = 0; f < me->nfree; ++f)
-      for (int x = 0; x < 3; ++x) address[3 * (size_t)me->free_[f] + x] = me->P[3 * (size_t)me->free_[f] + x];
-    for (const Body& b : me->body) {
+      for (int x = 0; x < 3; ++x) address[3 * (size_t)me->free_[f] + x] = me->ph->P[3 * (size_t)me->free_[f] + x];
+    for (const Body& b : me->ph->body) {
       std::vector<double> Pb(3 * (size_t)b.NP);
       b.particle_momenta(Pb.data());
       for (int k = 0; k < b.NP; ++k)
@@ -1998,12 +2022,12 @@ void EmDee_download(tEmDee md, const char* option, double* address) {
     std::copy(me->F(), me->F() + n3, address);
   } else if (item == "centersOfMass") {
     for (int b = 0; b < me->nbodies; ++b)
-      for (int x = 0; x < 3; ++x) address[3 * (size_t)b + x] = me->body[b].rcm[x];
+      for (int x = 0; x < 3; ++x) address[3 * (size_t)b + x] = me->ph->body[b].rcm[x];
     for (int f = 0; f < me->nfree; ++f)
-      for (int x = 0; x < 3; ++x) address[3 * (size_t)(me->nbodies + f) + x] = me->R[3 * (size_t)me->free_[f] + x];
+      for (int x = 0; x < 3; ++x) address[3 * (size_t)(me->nbodies + f) + x] = me->ph->R[3 * (size_t)me->free_[f] + x];
   } else if (item == "quaternions" || item == "quatmom" || item == "quattau") {   // get_quaternions (759-775)
     for (int i = 0; i < me->nbodies; ++i) {
-      const Body& b = me->body[i];
+      const Body& b = me->ph->body[i];
       double v[4];
       if (item == "quaternions") std::copy(b.q, b.q + 4, v);
       else if (item == "quatmom") std::copy(b.pi, b.pi + 4, v);
@@ -2016,7 +2040,7 @@ void EmDee_download(tEmDee md, const char* option, double* address) {
   } else if (item == "angmom" || item == "bodycoord" || item == "bodymom" || item == "bodyforces" ||
              item == "torques" || item == "inertia") {   // get_body_properties (777-799)
     for (int i = 0; i < me->nbodies; ++i) {
-      const Body& b = me->body[i];
+      const Body& b = me->ph->body[i];
       const double* v = item == "angmom" ? b.omega : item == "bodycoord" ? b.rcm : item == "bodymom" ? b.pcm
                       : item == "bodyforces" ? b.F : item == "torques" ? b.tau : b.MoI;
       std::copy(v, v + 3, address + 3 * (size_t)i);
@@ -2051,17 +2075,17 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {
   };
   const size_t n3 = 3 * (size_t)me->natoms;
   if (item == "box") {
-    me->hasL = true;
-    me->Lbox = *address;
+    me->ph->hasL = true;
+    me->ph->Lbox = *address;
     if (me->initialized) invalidate(*me, md);
-    else if (me->hasR) initialize_system();
+    else if (me->ph->hasR) initialize_system();
   } else if (item == "coordinates") {
-    if (!me->hasR) { me->R.assign(n3, 0.0); me->hasR = true; }
-    std::copy(address, address + n3, me->R.begin());
+    if (!me->ph->hasR) { me->ph->R.assign(n3, 0.0); me->ph->hasR = true; }
+    std::copy(address, address + n3, me->ph->R.begin());
     if (me->initialized) {
       invalidate(*me, md);
       if (md->Options.AutoBodyUpdate) update_rigid_bodies(*me);
-    } else if (me->hasL) {
+    } else if (me->ph->hasL) {
       initialize_system();
     }
   } else if (item == "momenta") {
@@ -2092,7 +2116,7 @@ void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {
   Kiss& rng = me->random;
   if (me->nbodies != 0) {
     if (!me->initialized) error("random_momenta", "coordinates have not defined");
-    for (Body& b : me->body) {
+    for (Body& b : me->ph->body) {
       const double s = std::sqrt(b.mass * kT);
       for (int x = 0; x < 3; ++x) b.pcm[x] = s * rng.normal();
       double w[3];
@@ -2107,28 +2131,28 @@ void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {
   for (int f = 0; f < me->nfree; ++f) {
     int i = me->free_[f];
     double s = std::sqrt(me->mass[i] * kT);
-    for (int x = 0; x < 3; ++x) me->P[3 * (size_t)i + x] = s * rng.normal();
-    for (int x = 0; x < 3; ++x) twoKEt[x] += me->invMass[i] * me->P[3 * (size_t)i + x] * me->P[3 * (size_t)i + x];
+    for (int x = 0; x < 3; ++x) me->ph->P[3 * (size_t)i + x] = s * rng.normal();
+    for (int x = 0; x < 3; ++x) twoKEt[x] += me->invMass[i] * me->ph->P[3 * (size_t)i + x] * me->ph->P[3 * (size_t)i + x];
   }
   if (adjust) {   // adjust_momenta, 994-1018
     double vcm[3];
     int bodyDoF = 0;
-    for (const Body& b : me->body) bodyDoF += b.dof;
+    for (const Body& b : me->ph->body) bodyDoF += b.dof;
     for (int x = 0; x < 3; ++x) {
       double s = 0.0, sb = 0.0;
-      for (int f = 0; f < me->nfree; ++f) s += me->P[3 * (size_t)me->free_[f] + x];
-      for (const Body& b : me->body) sb += b.pcm[x];
+      for (int f = 0; f < me->nfree; ++f) s += me->ph->P[3 * (size_t)me->free_[f] + x];
+      for (const Body& b : me->ph->body) sb += b.pcm[x];
       vcm[x] = (s + sb) / me->totalMass;
     }
     for (int x = 0; x < 3; ++x) twoKEt[x] = 0.0;
     for (int f = 0; f < me->nfree; ++f) {
       int i = me->free_[f];
       for (int x = 0; x < 3; ++x) {
-        me->P[3 * (size_t)i + x] = me->P[3 * (size_t)i + x] - me->mass[i] * vcm[x];
-        twoKEt[x] += me->invMass[i] * me->P[3 * (size_t)i + x] * me->P[3 * (size_t)i + x];
+        me->ph->P[3 * (size_t)i + x] = me->ph->P[3 * (size_t)i + x] - me->mass[i] * vcm[x];
+        twoKEt[x] += me->invMass[i] * me->ph->P[3 * (size_t)i + x] * me->ph->P[3 * (size_t)i + x];
       }
     }
-    for (Body& b : me->body)
+    for (Body& b : me->ph->body)
       for (int x = 0; x < 3; ++x) {
         b.pcm[x] = b.pcm[x] - b.mass * vcm[x];
         twoKEt[x] += b.invMass * b.pcm[x] * b.pcm[x];
@@ -2138,9 +2162,9 @@ void EmDee_random_momenta(tEmDee* md, double kT, bool adjust, int seed) {
     double factor = std::sqrt((3 * me->nfree + bodyDoF - 3) * kT / total);
     for (int f = 0; f < me->nfree; ++f) {
       int i = me->free_[f];
-      for (int x = 0; x < 3; ++x) me->P[3 * (size_t)i + x] = factor * me->P[3 * (size_t)i + x];
+      for (int x = 0; x < 3; ++x) me->ph->P[3 * (size_t)i + x] = factor * me->ph->P[3 * (size_t)i + x];
     }
-    for (Body& b : me->body) {
+    for (Body& b : me->ph->body) {
       for (int x = 0; x < 3; ++x) b.pcm[x] = factor * b.pcm[x];
       const double w[3] = {factor * b.omega[0], factor * b.omega[1], factor * b.omega[2]};
       b.assign_omega(w);
@@ -2182,7 +2206,7 @@ void EmDee_displace(tEmDee* md, double lambda, double alpha, double dt) {
   if (alpha != 0.0) {
     CP = phi(alpha * dt) * dt;
     CR = 1.0 - alpha * CP;
-    me->Lbox = CR * me->Lbox;
+    me->ph->Lbox = CR * me->ph->Lbox;
   } else {
     CP = dt;
     CR = 1.0;
@@ -2218,7 +2242,7 @@ void EmDee_verlet_step(tEmDee* md, double dt) {
     q0.assign(4 * (size_t)me->nbodies, 0.0);
     s0.assign(3 * (size_t)me->nfree, 0.0);
     for (int i = 0; i < me->nbodies; ++i) {
-      const Body& b = me->body[i];
+      const Body& b = me->ph->body[i];
       for (int x = 0; x < 3; ++x) r0[3 * (size_t)i + x] = 2.5 * b.rcm[x] + dt_2 * b.invMass * (b.pcm[x] - dt_2 * b.F[x]);
       double vq[4];
       virtual_rotation(b, -dt, vq);
@@ -2228,8 +2252,8 @@ void EmDee_verlet_step(tEmDee* md, double dt) {
     for (int f = 0; f < me->nfree; ++f) {
       const int j = me->free_[f];
       for (int x = 0; x < 3; ++x)
-        s0[3 * (size_t)f + x] = 2.5 * me->R[3 * (size_t)j + x] +
-                                dt_2 * me->invMass[j] * (me->P[3 * (size_t)j + x] - dt_2 * F[3 * (size_t)j + x]);
+        s0[3 * (size_t)f + x] = 2.5 * me->ph->R[3 * (size_t)j + x] +
+                                dt_2 * me->invMass[j] * (me->ph->P[3 * (size_t)j + x] - dt_2 * F[3 * (size_t)j + x]);
     }
   }
   boost(*me, 1.0, dt_2, me->F(), true, true);
@@ -2243,7 +2267,7 @@ void EmDee_verlet_step(tEmDee* md, double dt) {
     double twoKEt[3], twoKEr[3];
     kinetic_energies(*me, true, true, twoKEt, twoKEr);
     for (int i = 0; i < me->nbodies; ++i) {
-      const Body& b = me->body[i];
+      const Body& b = me->ph->body[i];
       double rdot[3], vq[4], qdot[4];
       for (int x = 0; x < 3; ++x) {
         rdot[x] = 2.5 * b.rcm[x] + dt * b.invMass * (b.pcm[x] + dt_2 * b.F[x]) - r0[3 * (size_t)i + x];
@@ -2268,9 +2292,9 @@ void EmDee_verlet_step(tEmDee* md, double dt) {
       const int j = me->free_[f];
       double ff = 0.0, rp = 0.0;
       for (int x = 0; x < 3; ++x) {
-        const double rdot = 2.5 * me->R[3 * (size_t)j + x] +
-                            dt * me->invMass[j] * (me->P[3 * (size_t)j + x] + dt_2 * F[3 * (size_t)j + x]) - s0[3 * (size_t)f + x];
-        rp += rdot * me->P[3 * (size_t)j + x];
+        const double rdot = 2.5 * me->ph->R[3 * (size_t)j + x] +
+                            dt * me->invMass[j] * (me->ph->P[3 * (size_t)j + x] + dt_2 * F[3 * (size_t)j + x]) - s0[3 * (size_t)f + x];
+        rp += rdot * me->ph->P[3 * (size_t)j + x];
         ff += F[3 * (size_t)j + x] * F[3 * (size_t)j + x];
       }
       Ks_t = Ks_t + rp;
@@ -2292,7 +2316,7 @@ void EmDee_compute_forces(tEmDee* md) {
   const int N = me->natoms, T = me->nthreads;
   enum { pair = 0, coul = 1, long_ = 2, bond = 3, angle = 4 };
   std::vector<double> Rs(3 * (size_t)N), Fs(3 * (size_t)N * T);
-  for (size_t q = 0; q < 3 * (size_t)N; ++q) Rs[q] = me->R[q] / me->Lbox;
+  for (size_t q = 0; q < 3 * (size_t)N; ++q) Rs[q] = me->ph->R[q] / me->ph->Lbox;
 
   handle_neighbor_lists(*me, md->Builds, md->Time.Neighbor, Rs.data());
 
@@ -2380,10 +2404,10 @@ void EmDee_rdf(tEmDee md, int bins, double Rc, int pairs, int* itype, int* jtype
   }
   const int nsym = symm1D(maxtype, maxtype);
   std::vector<long long> pairCount((size_t)bins * nsym, 0);
-  const double invL = 1.0 / me->Lbox, invL2 = invL * invL;
+  const double invL = 1.0 / me->ph->Lbox, invL2 = invL * invL;
   const int N = me->natoms;
   std::vector<double> Rs(3 * (size_t)N);
-  for (size_t q = 0; q < Rs.size(); ++q) Rs[q] = invL * me->R[q];
+  for (size_t q = 0; q < Rs.size(); ++q) Rs[q] = invL * me->ph->R[q];
   const double Rc2 = Rc * Rc * invL2;
   const double binsByRc = bins / (Rc * invL);
   const bool useMiddle = Rc < 1.0001 * me->InRc;

@@ -76,6 +76,8 @@ inline cudaError_t cudaMalloc(T** p, size_t bytes) {
 }
 template <class T>
 inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMalloc(p, bytes); }
+template <class T>
+inline cudaError_t cudaMallocManaged(T** p, size_t bytes) { return cudaMalloc(p, bytes); }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }

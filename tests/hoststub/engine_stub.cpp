@@ -63,6 +63,8 @@ void Engine::take_member_momenta(KineticAll& ke) { ke = KineticAll(); }
 void Engine::download_body(int, double*) {}
 void Engine::upload_body(int, const double*) {}
 void Engine::derive_quaternion_momenta() {}
+void* Engine::expose(int, int) { return nullptr; }
+void Engine::share_phase_space(Engine&) {}
 void Engine::shadow_pre(int, double, int) {}
 void Engine::shadow_post(int, double, int, double& a, double& b, double& c) { a = b = c = 0.0; }
 long long Engine::pair_count() { return 0; }
