@@ -37,10 +37,6 @@ using nb::DevModel;
 }
 void warning(const std::string& msg) { std::fprintf(stderr, "WARNING: %s.\n", msg.c_str()); }   // :60-64
 
-[[noreturn]] void unsupported(const char* task) {
-  error(task, "not available in the B200 hot-path build (outside the nonbonded neighbor-list/pair-force scope)");
-}
-
 double now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -315,9 +311,13 @@ struct System {
   std::vector<double> hostR;             // host copy, kept only when rigid bodies exist
   std::vector<std::vector<int>> excluded;   // per atom, sorted unique 1-based partners
   bool exclusions_dirty = true;
+  std::vector<emdee::BondedTerm> bondedTerms;   // bonds and angles in the order they were added (reference structList)
+  int ndihedrals = 0;
+  bool bonded_dirty = false;
   std::vector<PairSlot> pair;            // (ntypes, ntypes, nlayers)
   std::vector<HostModel> coul;           // per layer
   HostModel kspace = blank(F_KSPACE, 0, "ewald");
+  // bonded models keep their two parameters in dev.a, dev.b (k, r0 | k, theta0); dev.kind: 0 = none, 1 = harmonic
   std::vector<char> overridable, multilayer, interact, pairs_exist, useInRc, bonded, forcesUpToDate;
   std::vector<tEnergy> layerEnergy;
   std::vector<tVirial> layerVirial;
@@ -804,9 +804,42 @@ void EmDee_ignore_pair(tEmDee md, int i, int j) {   // src/EmDeeCode.f90:524-570
   insert(j, i);
 }
 
-void EmDee_add_bond(tEmDee, int, int, void*) { unsupported("add_bond"); }
-void EmDee_add_angle(tEmDee, int, int, int, void*) { unsupported("add_angle"); }
-void EmDee_add_dihedral(tEmDee, int, int, int, int, void*) { unsupported("add_dihedral"); }
+// src/EmDeeCode.f90:574-655: bonded structures are excluded from the neighbor lists as they are added
+void EmDee_add_bond(tEmDee md, int i, int j, void* model) {
+  System* me = sys(md);
+  if (!ranged({i, j}, me->N)) error("add_bond", "atom index out of range");
+  if (model == nullptr) error("add_bond", "a valid model must be provided");
+  HostModel* m = handle(model);
+  if (m == nullptr || m->family != F_BOND) error("add_bond", "the provided model must be a bond model");
+  me->bondedTerms.push_back({i - 1, j - 1, 0, m->dev.kind == 0 ? 0 : 1, m->dev.a, m->dev.b});
+  me->bonded_dirty = true;
+  EmDee_ignore_pair(md, i, j);
+}
+void EmDee_add_angle(tEmDee md, int i, int j, int k, void* model) {
+  System* me = sys(md);
+  if (!ranged({i, j, k}, me->N)) error("add_angle", "atom index out of range");
+  if (model == nullptr) error("add_angle", "a valid model must be provided");
+  HostModel* m = handle(model);
+  if (m == nullptr || m->family != F_ANGLE) error("add_angle", "the provided model must be an angle model");
+  me->bondedTerms.push_back({i - 1, j - 1, k - 1, m->dev.kind == 0 ? 2 : 3, m->dev.a, m->dev.b});
+  me->bonded_dirty = true;
+  EmDee_ignore_pair(md, i, j);
+  EmDee_ignore_pair(md, i, k);
+  EmDee_ignore_pair(md, j, k);
+}
+void EmDee_add_dihedral(tEmDee md, int i, int j, int k, int l, void* model) {
+  System* me = sys(md);
+  if (!ranged({i, j, k, l}, me->N)) error("add_dihedral", "atom index out of range");
+  if (model == nullptr) error("add_dihedral", "a valid model must be provided");
+  HostModel* m = handle(model);
+  if (m == nullptr || m->family != F_DIHEDRAL) error("add_dihedral", "the provided model must be a dihedral model");
+  // The reference stores dihedrals but EmDee_compute_forces never evaluates them (src/EmDeeCode.f90:1240-1241 call
+  // compute_bonds and compute_angles only) and dihedral_none is the only model: the exclusions are the whole effect.
+  me->ndihedrals += 1;
+  const int a[4] = {i, j, k, l};
+  for (int x = 0; x < 4; ++x)
+    for (int y = x + 1; y < 4; ++y) EmDee_ignore_pair(md, a[x], a[y]);
+}
 
 void EmDee_compute_forces(tEmDee* md);
 
@@ -1097,20 +1130,28 @@ void EmDee_compute_forces(tEmDee* md) {   // src/EmDeeCode.f90:1215-1277
   const double t0 = now();
   const bool rebuilt = me->engine->compute_forces(me->layer - 1, compute, *me->box, r, tn);
   if (rebuilt) md->Builds += 1;
+  emdee::BondedScalars bs;
+  if (!me->bondedTerms.empty() && me->bonded[me->layer - 1]) {   // compute_bonds / compute_angles, src/EmDeeData.f90:443-550
+    if (me->bonded_dirty) {
+      me->engine->set_bonded(me->bondedTerms);
+      me->bonded_dirty = false;
+    }
+    me->engine->add_bonded(me->layer - 1, *me->box, bs);
+  }
   md->Time.Neighbor += tn;
   double Wlong = 0.0;
   if (me->coul[me->layer - 1].requires_kspace) Wlong = r.Ecoul - r.Wcoul;   // W(long) = E(coul) + E(long) - W(coul), E(long) not evaluated
-  md->Virial.Total = r.Wpair + r.Wcoul + Wlong;
+  md->Virial.Total = r.Wpair + r.Wcoul + Wlong + bs.Wbond + bs.Wangle;
   if (me->nbodies() != 0) {
-    md->Virial.Body = r.Wbody;
+    md->Virial.Body = r.Wbody + bs.Wbody;
     md->Virial.Total = md->Virial.Total + md->Virial.Body;
   }
   if (compute) {
     md->Energy.Dispersion = r.Epair;
     md->Energy.Coulomb = r.Ecoul;
-    md->Energy.Bond = 0.0;
-    md->Energy.Angle = 0.0;
-    md->Energy.Potential = r.Epair + r.Ecoul;
+    md->Energy.Bond = bs.Ebond;
+    md->Energy.Angle = bs.Eangle;
+    md->Energy.Potential = r.Epair + r.Ecoul + bs.Ebond + bs.Eangle;
     md->Energy.ShadowPotential = md->Energy.Potential;
   }
   md->Energy.UpToDate = compute;
@@ -1220,8 +1261,18 @@ void* EmDee_coul_shifted_square_smoothed(double skinWidth) {
   m.shifted = true;
   return deliver(m);
 }
-void* EmDee_bond_harmonic(double, double) { return deliver(blank(F_BOND, 1, "harmonic")); }
-void* EmDee_angle_harmonic(double, double) { return deliver(blank(F_ANGLE, 1, "harmonic")); }
+void* EmDee_bond_harmonic(double k, double r0) {   // src/bond_harmonic.f90:48-64
+  HostModel m = blank(F_BOND, 1, "harmonic");
+  m.dev.a = k;
+  m.dev.b = r0;
+  return deliver(m);
+}
+void* EmDee_angle_harmonic(double k, double theta0) {   // src/angle_harmonic.f90:48-64
+  HostModel m = blank(F_ANGLE, 1, "harmonic");
+  m.dev.a = k;
+  m.dev.b = theta0;
+  return deliver(m);
+}
 void* EmDee_kspace_ewald(double accuracy) {
   HostModel m = blank(F_KSPACE, 1, "ewald");
   m.accuracy = accuracy;

@@ -47,6 +47,7 @@
 #include "engine_brick.cuh"
 #include "engine_dynamics.cuh"
 #include "engine_bodies.cuh"
+#include "engine_bonded.cuh"
 #include "engine_dist.cuh"
 #include "engine_extra.cuh"
 
@@ -128,6 +129,10 @@ struct Engine::Impl {
   DBuf<unsigned char> freeMask;    // per atom: 1 = free atom (integrated by k_boost / k_displace), 0 = body member
   double* h_bscalars = nullptr;    // pinned, 16 doubles
   bool frames_valid = false;
+  // bonded terms (engine_bonded.cuh): per-atom CSR of (term, role) references
+  int nterms = 0;
+  DBuf<BondedTerm> terms;
+  DBuf<int> termFirst, termRef;
   // EmDee_memory_address / EmDee_share_phase_space: coordinates may change behind the engine's back
   bool exposed = false;            // a raw pointer to R, P or F was handed out: every call ends with a stream sync
   bool foreign_R = false;          // R is written by the client or by another system: never trust the cached criterion
@@ -286,6 +291,7 @@ Engine::~Engine() {
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
   s.known.release(); s.migCounts.release();
+  s.terms.release(); s.termFirst.release(); s.termRef.release();
   s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
   s.bScalars.release(); s.shR0.release(); s.shQ0.release(); s.shS0.release(); s.freeMask.release();
   if (s.h_bscalars) cudaFreeHost(s.h_bscalars);
@@ -1174,6 +1180,53 @@ void Engine::move_all(double CR, double CP, double dt, bool translate, bool rota
   }
   s.check_cached = false;   // compute_forces evaluates the rebuild criterion on the new coordinates
   if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+// ---- bonded terms ---------------------------------------------------------------------------------------------------
+void Engine::set_bonded(const std::vector<BondedTerm>& terms) {
+  Impl& s = *d_;
+  s.nterms = (int)terms.size();
+  if (s.nterms == 0) return;
+  std::vector<int> first(s.N + 1, 0), ref;
+  auto members = [](const BondedTerm& t) { return t.kind <= T_BOND_HARMONIC ? 2 : 3; };
+  for (const BondedTerm& t : terms) {
+    const int m[3] = {t.a0, t.a1, t.a2};
+    for (int r = 0; r < members(t); ++r) first[m[r] + 1] += 1;
+  }
+  for (int a = 0; a < s.N; ++a) first[a + 1] += first[a];
+  ref.resize(first[s.N]);
+  std::vector<int> fill(first.begin(), first.end() - 1);
+  for (size_t q = 0; q < terms.size(); ++q) {   // terms in the order they were added: fixed summation order per atom
+    const int m[3] = {terms[q].a0, terms[q].a1, terms[q].a2};
+    for (int r = 0; r < members(terms[q]); ++r) ref[fill[m[r]]++] = (int)(q << 2) | r;
+  }
+  s.terms.ensure(terms.size());
+  s.termFirst.ensure(s.N + 1);
+  s.termRef.ensure(ref.size() + 1);
+  CUDA_CHECK(cudaMemcpy(s.terms.p, terms.data(), terms.size() * sizeof(BondedTerm), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(s.termFirst.p, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(s.termRef.p, ref.data(), ref.size() * sizeof(int), cudaMemcpyHostToDevice));
+  s.bPartial.ensure((size_t)nblocks(s.N) * 6);
+  s.bScalars.ensure(16);
+  if (s.h_bscalars == nullptr) CUDA_CHECK(cudaMallocHost(&s.h_bscalars, 16 * sizeof(double)));
+}
+
+void Engine::add_bonded(int layer0, double Lbox, BondedScalars& out) {
+  Impl& s = *d_;
+  out = BondedScalars();
+  if (s.nterms == 0) return;
+  if (s.world > 1) fatal("force computation", "bonded terms are not available on several GPUs yet");
+  const double* delta = (s.has_delta && s.nbodies != 0) ? s.delta.p : nullptr;
+  k_bonded<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, s.termFirst.p, s.termRef.p, s.terms.p, s.R.p, Lbox,
+                                               s.F.p + (size_t)layer0 * 3 * s.N, delta, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
+  stats_.launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  out.Ebond = s.h_bscalars[0];
+  out.Wbond = s.h_bscalars[1];
+  out.Eangle = s.h_bscalars[2];
+  out.Wangle = s.h_bscalars[3];
+  out.Wbody = s.h_bscalars[4];
 }
 
 // ---- EmDee_memory_address / EmDee_share_phase_space ---------------------------------------------------------------

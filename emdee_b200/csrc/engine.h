@@ -40,6 +40,16 @@ struct KineticAll {
   double twoKEr[3] = {0, 0, 0};  // bodies I*omega^2, per principal axis
 };
 
+// One bonded term (reference tStruct, src/structs.f90:27-30): a bond a0-a1 or an angle a0-a1-a2 (vertex a1), 0-based atoms
+struct BondedTerm {
+  int a0, a1, a2, kind;   // kind: 0 bond_none, 1 bond_harmonic, 2 angle_none, 3 angle_harmonic
+  double p1, p2;          // k, r0 | k, theta0
+};
+
+struct BondedScalars {
+  double Ebond = 0, Wbond = 0, Eangle = 0, Wangle = 0, Wbody = 0;
+};
+
 struct EngineStats {
   long long launches = 0, force_launches = 0, build_launches = 0;
   double force_ms = 0, build_ms = 0;
@@ -93,6 +103,10 @@ class Engine {
   void derive_quaternion_momenta();                                      // pi = B(q) 2 I omega
   void shadow_pre(int layer0, double dt, int mode);                      // EmDee_verlet_step pre_force bookkeeping
   void shadow_post(int layer0, double dt, int mode, double& Us, double& Ks_t, double& Ks_r);
+
+  // ---- bonded terms (reference compute_bonds / compute_angles, src/EmDeeData.f90:443-550) --------
+  void set_bonded(const std::vector<BondedTerm>& terms);
+  void add_bonded(int layer0, double Lbox, BondedScalars& out);   // adds to the layer's forces (after compute_forces)
 
   // ---- raw pointers and aliasing (reference EmDee_memory_address / EmDee_share_phase_space) ------
   enum Exposed { EXPOSE_R, EXPOSE_P, EXPOSE_F, EXPOSE_LAYER_F };

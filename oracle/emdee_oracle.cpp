@@ -1077,6 +1077,8 @@ struct System {
   Model kspace;
   std::vector<char> multilayer, overridable, interact, pairs_exist;
   std::vector<char> bonded, useInRc, forcesUpToDate;
+  struct Struct { int i, j, k, l; Model model; };          // src/structs.f90:27-30 (1-based atom indices)
+  std::vector<Struct> bonds, angles, dihedrals;
   std::vector<double> layerF;        // (3, N, nlayers)
   std::vector<tEnergy> layerEnergy;
   std::vector<tVirial> layerVirial;
@@ -1695,6 +1697,72 @@ void compute_pairs(System& me, int thread, const double* Rs, double* F, double& 
   for (size_t q = 0; q < 3 * (size_t)N; ++q) F[q] = me.ph->Lbox * F[q];
 }
 
+// src/EmDeeData.f90:443-487 with bond_harmonic_compute (src/bond_harmonic.f90:68-80); R holds SCALED coordinates.
+// The `kspace` branch (Ewald discount of bonded pairs, 470-476) belongs to the reciprocal-space solver: not restated.
+void compute_bonds(System& me, const double* Rs, double* F, double& Potential, double& Virial) {
+  if (me.bonds.empty() || !me.bonded[me.layer - 1]) return;
+  const double L = me.ph->Lbox, invL2 = 1.0 / (L * L);
+  for (const System::Struct& b : me.bonds) {
+    double Rij[3], r2 = 0.0;
+    for (int x = 0; x < 3; ++x) {
+      Rij[x] = Rs[3 * (size_t)(b.i - 1) + x] - Rs[3 * (size_t)(b.j - 1) + x];
+      Rij[x] = Rij[x] - std::round(Rij[x]);
+      r2 += Rij[x] * Rij[x];
+    }
+    const double invR2 = invL2 / r2;
+    double E = 0.0, W = 0.0;
+    if (b.model.kind == BOND_HARMONIC) {
+      const double r = 1.0 / std::sqrt(invR2), delta = r - b.model.p2;
+      E = (0.5 * b.model.p1) * delta * delta;
+      W = (-b.model.p1) * delta * r;
+    }
+    Potential = Potential + E;
+    Virial = Virial + W;
+    for (int x = 0; x < 3; ++x) {
+      const double Fij = W * invR2 * L * Rij[x];
+      F[3 * (size_t)(b.i - 1) + x] += Fij;
+      F[3 * (size_t)(b.j - 1) + x] -= Fij;
+    }
+  }
+}
+
+// src/EmDeeData.f90:491-550 with angle_harmonic_compute (src/angle_harmonic.f90:68-78)
+void compute_angles(System& me, const double* Rs, double* F, double& Potential, double& Virial) {
+  if (me.angles.empty() || !me.bonded[me.layer - 1]) return;
+  const double L = me.ph->Lbox;
+  for (const System::Struct& a : me.angles) {
+    const size_t i = a.i - 1, j = a.j - 1, k = a.k - 1;
+    double av[3], bv[3], aa = 0.0, bb = 0.0, ab = 0.0;
+    for (int x = 0; x < 3; ++x) {
+      av[x] = Rs[3 * i + x] - Rs[3 * j + x];
+      bv[x] = Rs[3 * k + x] - Rs[3 * j + x];
+      av[x] = L * (av[x] - std::round(av[x]));
+      bv[x] = L * (bv[x] - std::round(bv[x]));
+      aa += av[x] * av[x];
+      bb += bv[x] * bv[x];
+      ab += av[x] * bv[x];
+    }
+    const double theta = std::acos(ab / std::sqrt(aa * bb));
+    double Ea = 0.0, Fa = 0.0;
+    if (a.model.kind == ANGLE_HARMONIC) {
+      const double delta = theta - a.model.p2;
+      Ea = (0.5 * a.model.p1) * delta * delta;
+      Fa = (-a.model.p1) * delta;
+    }
+    const double factor = Fa / std::sqrt(aa * bb - ab * ab);
+    double w = 0.0;
+    for (int x = 0; x < 3; ++x) {
+      const double Fi = ((ab / aa) * av[x] - bv[x]) * factor, Fk = ((ab / bb) * bv[x] - av[x]) * factor;
+      F[3 * i + x] += Fi;
+      F[3 * k + x] += Fk;
+      F[3 * j + x] -= (Fi + Fk);
+      w += Fi * av[x] + Fk * bv[x];
+    }
+    Potential = Potential + Ea;
+    Virial = Virial + w;
+  }
+}
+
 // src/EmDeeData.f90:926-953
 double rigid_body_virial(System& me) {
   std::vector<double> W(me.nthreads, 0.0);
@@ -1721,10 +1789,6 @@ void invalidate(System& me, tEmDee* md) {
   std::fill(me.forcesUpToDate.begin(), me.forcesUpToDate.end(), 0);
   for (auto& e : me.layerEnergy) e.UpToDate = false;
   md->Energy.UpToDate = false;
-}
-
-[[noreturn]] void out_of_scope(const char* task) {
-  error(task, "this entry point is outside the nonbonded hot-path scope of the oracle");
 }
 
 }  // namespace
@@ -1991,9 +2055,38 @@ void EmDee_ignore_pair(tEmDee md, int i, int j) {
   ex.count = n;
 }
 
-void EmDee_add_bond(tEmDee, int, int, void*) { out_of_scope("add_bond"); }
-void EmDee_add_angle(tEmDee, int, int, int, void*) { out_of_scope("add_angle"); }
-void EmDee_add_dihedral(tEmDee, int, int, int, int, void*) { out_of_scope("add_dihedral"); }
+// src/EmDeeCode.f90:574-655
+void EmDee_add_bond(tEmDee md, int i, int j, void* model) {
+  System* me = sys(md);
+  if (!ranged({i, j}, me->natoms)) error("add_bond", "atom index out of range");
+  if (model == nullptr) error("add_bond", "a valid model must be provided");
+  Model* m = as_model(model);
+  if (m == nullptr || !(m->kind == BOND_NONE || m->kind == BOND_HARMONIC)) error("add_bond", "the provided model must be a bond model");
+  me->bonds.push_back({i, j, 0, 0, *m});
+  EmDee_ignore_pair(md, i, j);
+}
+void EmDee_add_angle(tEmDee md, int i, int j, int k, void* model) {
+  System* me = sys(md);
+  if (!ranged({i, j, k}, me->natoms)) error("add_angle", "atom index out of range");
+  if (model == nullptr) error("add_angle", "a valid model must be provided");
+  Model* m = as_model(model);
+  if (m == nullptr || !(m->kind == ANGLE_NONE || m->kind == ANGLE_HARMONIC)) error("add_angle", "the provided model must be an angle model");
+  me->angles.push_back({i, j, k, 0, *m});
+  EmDee_ignore_pair(md, i, j);
+  EmDee_ignore_pair(md, i, k);
+  EmDee_ignore_pair(md, j, k);
+}
+void EmDee_add_dihedral(tEmDee md, int i, int j, int k, int l, void* model) {
+  System* me = sys(md);
+  if (!ranged({i, j, k, l}, me->natoms)) error("add_dihedral", "atom index out of range");
+  if (model == nullptr) error("add_dihedral", "a valid model must be provided");
+  Model* m = as_model(model);
+  if (m == nullptr || m->kind != DIHEDRAL_NONE) error("add_dihedral", "the provided model must be a dihedral model");
+  me->dihedrals.push_back({i, j, k, l, *m});   // stored and excluded; EmDee_compute_forces never evaluates dihedrals (1240-1241)
+  const int a[4] = {i, j, k, l};
+  for (int x = 0; x < 4; ++x)
+    for (int y = x + 1; y < 4; ++y) EmDee_ignore_pair(md, a[x], a[y]);
+}
 
 void EmDee_compute_forces(tEmDee* md);
 
@@ -2349,6 +2442,8 @@ void EmDee_compute_forces(tEmDee* md) {
     for (int t = 0; t < T; ++t) s += Fs[(size_t)t * 3 * N + q];
     Fm[q] = s;
   }
+  compute_bonds(*me, Rs.data(), Fm, E[bond], W[bond]);      // 1240: after the thread sum here (addition commutes)
+  compute_angles(*me, Rs.data(), Fm, E[angle], W[angle]);   // 1241
   if (me->coul[me->layer - 1].requires_kspace) {
     // compute_kspace (src/EmDeeData.f90:689-700) is outside the hot-path scope: E(long) stays zero.
     W[long_] = E[coul] + E[long_] - W[coul];

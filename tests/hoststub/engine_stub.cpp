@@ -63,6 +63,8 @@ void Engine::take_member_momenta(KineticAll& ke) { ke = KineticAll(); }
 void Engine::download_body(int, double*) {}
 void Engine::upload_body(int, const double*) {}
 void Engine::derive_quaternion_momenta() {}
+void Engine::set_bonded(const std::vector<BondedTerm>&) {}
+void Engine::add_bonded(int, double, BondedScalars& out) { out = BondedScalars(); }
 void* Engine::expose(int, int) { return nullptr; }
 void Engine::share_phase_space(Engine&) {}
 void Engine::shadow_pre(int, double, int) {}
