@@ -1057,6 +1057,30 @@ struct Phase {
   std::vector<Body> body;
 };
 
+// Reciprocal-space Ewald solver: cKspaceModel (src/modelClass_kspace.f90:38-72) + kspace_ewald (src/kspace_ewald.f90:37-58)
+struct Ewald {
+  double alpha = 0, beta = 0, kmax = 0, Volume = 0;
+  int ntypes = 0, nTypePairs = 0, nvecs = 0, nlayers = 1;
+  int nmax[3] = {-1, -1, -1};
+  std::vector<int> type;                     // distinct charged types, ascending (1-based type ids)
+  std::vector<int> first, last, item;        // atoms of those types grouped by type (0-based items / atoms)
+  std::vector<double> value;                 // their charges
+  std::vector<double> Erigid;                // (nTypePairs) intrabody + self terms, unscaled by the Coulomb constant
+  std::vector<double> lambda, lambda1D;      // (ntypes, ntypes, nlayers), (nTypePairs, nlayers)
+  std::vector<int> n;                        // (3, nvecs)
+  std::vector<double> prefac, vec;           // (nvecs), (3, nvecs)
+  static int symm1D(int i, int j) {          // src/math.f90:695-702 (1-based)
+    const int x = std::min(i, j) - 1, y = std::max(i, j) - 1;
+    return x + (y + 1) * y / 2 + 1;
+  }
+  // cKspaceModel_discount (src/modelClass_kspace.f90:320-334): minus the smooth (erf) part of a pair interaction
+  void discount(double& E, double& W, double rsq, double QiQj) const {
+    const double r = std::sqrt(rsq), x = alpha * r, expmx2 = std::exp(-x * x);
+    E = -QiQj * (1.0 - uerfc(x, expmx2)) / r;
+    W = E + QiQj * beta * expmx2;
+  }
+};
+
 struct System {
   int natoms = 0, mcells = 0, ncells = 0, maxcells = 0, maxatoms = 0, maxpairs = 0, ntypes = 1;
   int nbodies = 0, nfree = 0, nthreads = 1, threadAtoms = 0, threadFreeAtoms = 0, threadBodies = 0;
@@ -1075,6 +1099,7 @@ struct System {
   std::vector<PairContainer> pair;   // (ntypes, ntypes, nlayers)
   std::vector<Model> coul;           // (nlayers)
   Model kspace;
+  Ewald ewald;
   std::vector<char> multilayer, overridable, interact, pairs_exist;
   std::vector<char> bonded, useInRc, forcesUpToDate;
   struct Struct { int i, j, k, l; Model model; };          // src/structs.f90:27-30 (1-based atom indices)
@@ -1384,6 +1409,187 @@ void set_pair_type(System& me, int itype, int jtype, int layer, const Model& mod
   }
 }
 
+// kspace_ewald_update (src/kspace_ewald.f90:103-184): the half-space of wave vectors inside the cutoff sphere,
+// their Gaussian prefactors and force vectors. Called once, at initialization (the reference never calls it again).
+void ewald_update(System& me, double L) {
+  Ewald& k = me.ewald;
+  const double unit = 2.0 * Pi / L, unitSq = unit * unit;
+  const int nm = (int)std::ceil(k.kmax / unit);
+  for (int x = 0; x < 3; ++x) k.nmax[x] = nm;
+  const int M = 2 * nm + 1, maxnvecs = (M * M * M) / 2, M2 = M, M2M3 = M * M;
+  const double kmaxSq = unitSq * nm * nm;
+  k.n.clear();
+  for (int i = maxnvecs + 1; i <= 2 * maxnvecs; ++i) {
+    const int n1 = i / M2M3, j = i - n1 * M2M3, n2 = j / M2, n3 = j - n2 * M2;
+    const int kv[3] = {n1 - nm, n2 - nm, n3 - nm};
+    if (unitSq * kv[0] * kv[0] + unitSq * kv[1] * kv[1] + unitSq * kv[2] * kv[2] <= kmaxSq) k.n.insert(k.n.end(), kv, kv + 3);
+  }
+  k.nvecs = (int)k.n.size() / 3;
+  const double B = -0.25 / (k.alpha * k.alpha);
+  k.Volume = L * L * L;
+  const double fourPiByV = 4.0 * Pi / k.Volume;
+  k.prefac.assign(k.nvecs, 0.0);
+  k.vec.assign(3 * (size_t)k.nvecs, 0.0);
+  for (int i = 0; i < k.nvecs; ++i) {
+    const double kk[3] = {unit * k.n[3 * i], unit * k.n[3 * i + 1], unit * k.n[3 * i + 2]};
+    const double ksq = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2];
+    k.prefac[i] = fourPiByV * std::exp(ksq * B) / ksq;
+    for (int x = 0; x < 3; ++x) k.vec[3 * (size_t)i + x] = 2.0 * k.prefac[i] * kk[x];
+  }
+}
+
+// cKspaceModel_initialize (src/modelClass_kspace.f90:108-273) + kspace_ewald_set_parameters (src/kspace_ewald.f90:82-99)
+void ewald_initialize(System& me, double Rc) {
+  const char* task = "kspace model initialization";
+  Ewald& k = me.ewald;
+  const int N = me.natoms;
+  const double L = me.ph->Lbox;
+  int ncharged = 0;
+  for (int i = 0; i < N; ++i) ncharged += me.charged[i] ? 1 : 0;
+  if (ncharged == 0) error(task, "system has no charged atoms");
+  // distinct types of charged atoms, ascending
+  std::vector<char> seen(me.ntypes + 1, 0);
+  for (int i = 0; i < N; ++i)
+    if (me.charged[i]) seen[me.atomType[i]] = 1;
+  k.type.clear();
+  for (int t = 1; t <= me.ntypes; ++t)
+    if (seen[t]) k.type.push_back(t);
+  k.ntypes = (int)k.type.size();
+  // every atom of those types, grouped by type (143-161: pack(seq, types == type(i)), charged or not)
+  k.first.assign(k.ntypes, 0);
+  k.last.assign(k.ntypes, 0);
+  k.item.clear();
+  k.value.clear();
+  for (int t = 0; t < k.ntypes; ++t) {
+    k.first[t] = (int)k.item.size();
+    for (int i = 0; i < N; ++i)
+      if (me.atomType[i] == k.type[t]) { k.item.push_back(i); k.value.push_back(me.charge[i]); }
+    k.last[t] = (int)k.item.size() - 1;
+  }
+  // accuracy = exp(-s^2)/s^2, alpha = s/Rc, kmax = 2*alpha*s
+  const double sacc = std::sqrt(inverse_of_x_plus_ln_x(-std::log(me.kspace.accuracy)));
+  k.alpha = sacc / Rc;
+  k.kmax = 2.0 * k.alpha * sacc;
+  std::printf("KSPACE PARAMETERS: alpha = %10.5f and kmax = %10.5f\n", k.alpha, k.kmax);
+  k.beta = 2.0 * k.alpha / std::sqrt(Pi);
+  // intrabody pairs of charged atoms: their smooth part is taken back out, as is the self energy (169-236)
+  k.nTypePairs = k.ntypes * (k.ntypes - 1) / 2 + k.ntypes;
+  k.Erigid.assign(k.nTypePairs, 0.0);
+  std::vector<int> local(me.ntypes + 1, 0);
+  for (int t = 0; t < k.ntypes; ++t) local[k.type[t]] = t + 1;
+  const double invL = 1.0 / L;
+  for (const Body& b : me.ph->body)
+    for (int ii = 0; ii < b.NP - 1; ++ii) {
+      const int i = b.index[ii];
+      if (!me.charged[i]) continue;
+      for (int jj = ii + 1; jj < b.NP; ++jj) {
+        const int j = b.index[jj];
+        if (!me.charged[j]) continue;
+        double rsq = 0.0;
+        for (int x = 0; x < 3; ++x) {
+          double d = me.ph->R[3 * (size_t)i + x] - me.ph->R[3 * (size_t)j + x];
+          d = d - L * std::round(invL * d);
+          rsq += d * d;
+        }
+        double Eij, Wij;
+        k.discount(Eij, Wij, rsq, me.charge[i] * me.charge[j]);
+        k.Erigid[Ewald::symm1D(local[me.atomType[i]], local[me.atomType[j]]) - 1] += Eij;
+      }
+    }
+  for (int t = 0; t < k.ntypes; ++t) {
+    double q2 = 0.0;
+    for (int q = k.first[t]; q <= k.last[t]; ++q) q2 += k.value[q] * k.value[q];
+    k.Erigid[Ewald::symm1D(t + 1, t + 1) - 1] -= k.alpha * q2 / std::sqrt(Pi);
+  }
+  // Coulomb constants of the type pairs, per layer (238-252)
+  k.nlayers = me.nlayers;
+  k.lambda.assign((size_t)k.ntypes * k.ntypes * k.nlayers, 0.0);
+  k.lambda1D.assign((size_t)k.nTypePairs * k.nlayers, 0.0);
+  for (int l = 1; l <= me.nlayers; ++l)
+    for (int i = 0; i < k.ntypes; ++i)
+      for (int j = i; j < k.ntypes; ++j) {
+        const double lam = me.pr(k.type[i], k.type[j], l).kCoul;
+        k.lambda[((size_t)(l - 1) * k.ntypes + j) * k.ntypes + i] = lam;
+        k.lambda[((size_t)(l - 1) * k.ntypes + i) * k.ntypes + j] = lam;
+        k.lambda1D[(size_t)(l - 1) * k.nTypePairs + Ewald::symm1D(i + 1, j + 1) - 1] = lam;
+      }
+  ewald_update(me, L);
+}
+
+// compute_kspace (src/EmDeeData.f90:689-700): kspace_ewald_prepare + kspace_ewald_compute (src/kspace_ewald.f90:188-314)
+// + the energy part of discount_rigid_pairs (src/modelClass_kspace.f90:277-316; forces are not discounted there either)
+void compute_kspace(System& me, const double* Rs, double& Elong, double* F) {
+  const Ewald& k = me.ewald;
+  const int nv = k.nvecs, nt = k.ntypes, nm = k.nmax[0], nch = (int)k.item.size();
+  const int layer = me.layer;
+  // q_j exp(i k.r_j) for every listed atom: powers of exp(2 pi i s) along each axis (recursion, 208-219, 241-255)
+  std::vector<double> qre((size_t)nv * nch), qim((size_t)nv * nch);
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+  for (int j = 0; j < nch; ++j) {
+    const int i = k.item[j];
+    std::vector<double> gre(3 * (size_t)(2 * nm + 1)), gim(3 * (size_t)(2 * nm + 1));
+    for (int x = 0; x < 3; ++x) {
+      double* re = gre.data() + (size_t)x * (2 * nm + 1) + nm;   // index -nm..nm
+      double* im = gim.data() + (size_t)x * (2 * nm + 1) + nm;
+      const double theta = 2.0 * Pi * Rs[3 * (size_t)i + x];
+      const double zr = std::cos(theta), zi = std::sin(theta);
+      re[0] = 1.0; im[0] = 0.0;
+      double br = zr, bi = zi;
+      for (int p = 1; p <= nm; ++p) {
+        re[p] = br; im[p] = bi;
+        const double tr = br * zr - bi * zi, ti = br * zi + bi * zr;
+        br = tr; bi = ti;
+      }
+      for (int p = 1; p <= nm; ++p) { re[-p] = re[p]; im[-p] = -im[p]; }
+    }
+    const int W1 = 2 * nm + 1;
+    for (int v = 0; v < nv; ++v) {
+      const int a = k.n[3 * v] + nm, b = k.n[3 * v + 1] + nm, c = k.n[3 * v + 2] + nm;
+      const double ar = gre[a], ai = gim[a], br = gre[W1 + b], bi = gim[W1 + b], cr = gre[2 * W1 + c], ci = gim[2 * W1 + c];
+      const double abr = ar * br - ai * bi, abi = ar * bi + ai * br;
+      qre[(size_t)j * nv + v] = k.value[j] * (abr * cr - abi * ci);
+      qim[(size_t)j * nv + v] = k.value[j] * (abr * ci + abi * cr);
+    }
+  }
+  // type-specific structure factors S(k, t) and sigma = S . lambda(layer)
+  std::vector<double> Sre((size_t)nv * nt, 0.0), Sim((size_t)nv * nt, 0.0), gre_((size_t)nv * nt, 0.0), gim_((size_t)nv * nt, 0.0);
+  for (int t = 0; t < nt; ++t)
+    for (int j = k.first[t]; j <= k.last[t]; ++j)
+      for (int v = 0; v < nv; ++v) {
+        Sre[(size_t)t * nv + v] += qre[(size_t)j * nv + v];
+        Sim[(size_t)t * nv + v] += qim[(size_t)j * nv + v];
+      }
+  const double* lam = k.lambda.data() + (size_t)(layer - 1) * nt * nt;
+  for (int t = 0; t < nt; ++t)
+    for (int u = 0; u < nt; ++u)
+      for (int v = 0; v < nv; ++v) {
+        gre_[(size_t)t * nv + v] += Sre[(size_t)u * nv + v] * lam[(size_t)t * nt + u];
+        gim_[(size_t)t * nv + v] += Sim[(size_t)u * nv + v] * lam[(size_t)t * nt + u];
+      }
+  double E = 0.0;
+  for (int v = 0; v < nv; ++v) {
+    double d = 0.0;
+    for (int t = 0; t < nt; ++t) d += Sre[(size_t)t * nv + v] * gre_[(size_t)t * nv + v] + Sim[(size_t)t * nv + v] * gim_[(size_t)t * nv + v];
+    E += k.prefac[v] * d;
+  }
+  Elong = Elong + E;
+  // forces: F_i += sum_k vec(k) * (Re sigma Im q - Re q Im sigma)
+  for (int t = 0; t < nt; ++t)
+#pragma omp parallel for num_threads(me.nthreads) schedule(static)
+    for (int j = k.first[t]; j <= k.last[t]; ++j) {
+      double f[3] = {0, 0, 0};
+      for (int v = 0; v < nv; ++v) {
+        const double c = gre_[(size_t)t * nv + v] * qim[(size_t)j * nv + v] - qre[(size_t)j * nv + v] * gim_[(size_t)t * nv + v];
+        for (int x = 0; x < 3; ++x) f[x] += k.vec[3 * (size_t)v + x] * c;
+      }
+      for (int x = 0; x < 3; ++x) F[3 * (size_t)k.item[j] + x] += f[x];
+    }
+  // rigid pairs + self energy
+  double Er = 0.0;
+  for (int p = 0; p < k.nTypePairs; ++p) Er += k.lambda1D[(size_t)(layer - 1) * k.nTypePairs + p] * k.Erigid[p];
+  Elong = Elong + Er;
+}
+
 // src/EmDeeData.f90:359-416
 void perform_initialization(System& me, int& DoF, int& RotDoF) {
   const char* task = "system initialization";
@@ -1409,18 +1615,12 @@ void perform_initialization(System& me, int& DoF, int& RotDoF) {
     else error(task, "a kspace solver is required, but has not been defined");
   }
   if (me.kspace_active) {
-    // cKspaceModel_initialize -> kspace_ewald_set_parameters (src/kspace_ewald.f90:82-99): only the
-    // Ewald splitting parameter feeds the real-space hot path. The reciprocal-space sum itself
-    // (src/kspace_ewald.f90:188-314) is outside the hot-path scope and is NOT evaluated.
-    double s = std::sqrt(inverse_of_x_plus_ln_x(-std::log(me.kspace.accuracy)));
-    double alpha = s / kspaceRc;
-    std::printf("KSPACE PARAMETERS: alpha = %10.5f and kmax = %10.5f\n", alpha, 2.0 * alpha * s);
-    warning("reciprocal-space Ewald terms are outside the hot-path scope and are not evaluated");
+    ewald_initialize(me, kspaceRc);
     for (int l = 1; l <= me.nlayers; ++l) {
       Model& c = me.coul[l - 1];
       if (c.requires_kspace) {   // coul_long_kspace_setup, src/coul_long.f90:66-73
-        c.alpha = alpha;
-        c.beta = 2.0 * alpha / std::sqrt(Pi);
+        c.alpha = me.ewald.alpha;
+        c.beta = 2.0 * me.ewald.alpha / std::sqrt(Pi);
       }
     }
   }
@@ -1698,9 +1898,10 @@ void compute_pairs(System& me, int thread, const double* Rs, double* F, double& 
 }
 
 // src/EmDeeData.f90:443-487 with bond_harmonic_compute (src/bond_harmonic.f90:68-80); R holds SCALED coordinates.
-// The `kspace` branch (Ewald discount of bonded pairs, 470-476) belongs to the reciprocal-space solver: not restated.
-void compute_bonds(System& me, const double* Rs, double* F, double& Potential, double& Virial) {
-  if (me.bonds.empty() || !me.bonded[me.layer - 1]) return;
+// With an Ewald-type Coulomb model the smooth part of each bonded (excluded) pair is taken back out (470-478).
+void compute_bonds(System& me, const double* Rs, double* F, double& Potential, double& Virial, double& Ecoul) {
+  const bool bonded = me.bonded[me.layer - 1], kspace = me.coul[me.layer - 1].requires_kspace;
+  if (me.bonds.empty() || !(bonded || kspace)) return;
   const double L = me.ph->Lbox, invL2 = 1.0 / (L * L);
   for (const System::Struct& b : me.bonds) {
     double Rij[3], r2 = 0.0;
@@ -1711,13 +1912,22 @@ void compute_bonds(System& me, const double* Rs, double* F, double& Potential, d
     }
     const double invR2 = invL2 / r2;
     double E = 0.0, W = 0.0;
-    if (b.model.kind == BOND_HARMONIC) {
-      const double r = 1.0 / std::sqrt(invR2), delta = r - b.model.p2;
-      E = (0.5 * b.model.p1) * delta * delta;
-      W = (-b.model.p1) * delta * r;
+    if (bonded) {
+      if (b.model.kind == BOND_HARMONIC) {
+        const double r = 1.0 / std::sqrt(invR2), delta = r - b.model.p2;
+        E = (0.5 * b.model.p1) * delta * delta;
+        W = (-b.model.p1) * delta * r;
+      }
+      Potential = Potential + E;
+      Virial = Virial + W;
     }
-    Potential = Potential + E;
-    Virial = Virial + W;
+    if (kspace) {
+      const double QiQj = me.pr(me.atomType[b.i - 1], me.atomType[b.j - 1], me.layer).kCoul * me.charge[b.i - 1] * me.charge[b.j - 1];
+      double EL, WL;
+      me.ewald.discount(EL, WL, 1.0 / invR2, QiQj);
+      Ecoul = Ecoul + EL;
+      W = W + WL;
+    }
     for (int x = 0; x < 3; ++x) {
       const double Fij = W * invR2 * L * Rij[x];
       F[3 * (size_t)(b.i - 1) + x] += Fij;
@@ -1727,8 +1937,9 @@ void compute_bonds(System& me, const double* Rs, double* F, double& Potential, d
 }
 
 // src/EmDeeData.f90:491-550 with angle_harmonic_compute (src/angle_harmonic.f90:68-78)
-void compute_angles(System& me, const double* Rs, double* F, double& Potential, double& Virial) {
-  if (me.angles.empty() || !me.bonded[me.layer - 1]) return;
+void compute_angles(System& me, const double* Rs, double* F, double& Potential, double& Virial, double& Ecoul) {
+  const bool bonded = me.bonded[me.layer - 1], kspace = me.coul[me.layer - 1].requires_kspace;
+  if (me.angles.empty() || !(bonded || kspace)) return;
   const double L = me.ph->Lbox;
   for (const System::Struct& a : me.angles) {
     const size_t i = a.i - 1, j = a.j - 1, k = a.k - 1;
@@ -1742,24 +1953,39 @@ void compute_angles(System& me, const double* Rs, double* F, double& Potential, 
       bb += bv[x] * bv[x];
       ab += av[x] * bv[x];
     }
-    const double theta = std::acos(ab / std::sqrt(aa * bb));
-    double Ea = 0.0, Fa = 0.0;
-    if (a.model.kind == ANGLE_HARMONIC) {
-      const double delta = theta - a.model.p2;
-      Ea = (0.5 * a.model.p1) * delta * delta;
-      Fa = (-a.model.p1) * delta;
+    if (bonded) {
+      const double theta = std::acos(ab / std::sqrt(aa * bb));
+      double Ea = 0.0, Fa = 0.0;
+      if (a.model.kind == ANGLE_HARMONIC) {
+        const double delta = theta - a.model.p2;
+        Ea = (0.5 * a.model.p1) * delta * delta;
+        Fa = (-a.model.p1) * delta;
+      }
+      const double factor = Fa / std::sqrt(aa * bb - ab * ab);
+      double w = 0.0;
+      for (int x = 0; x < 3; ++x) {
+        const double Fi = ((ab / aa) * av[x] - bv[x]) * factor, Fk = ((ab / bb) * bv[x] - av[x]) * factor;
+        F[3 * i + x] += Fi;
+        F[3 * k + x] += Fk;
+        F[3 * j + x] -= (Fi + Fk);
+        w += Fi * av[x] + Fk * bv[x];
+      }
+      Potential = Potential + Ea;
+      Virial = Virial + w;
     }
-    const double factor = Fa / std::sqrt(aa * bb - ab * ab);
-    double w = 0.0;
-    for (int x = 0; x < 3; ++x) {
-      const double Fi = ((ab / aa) * av[x] - bv[x]) * factor, Fk = ((ab / bb) * bv[x] - av[x]) * factor;
-      F[3 * i + x] += Fi;
-      F[3 * k + x] += Fk;
-      F[3 * j + x] -= (Fi + Fk);
-      w += Fi * av[x] + Fk * bv[x];
+    if (kspace) {   // the 1-3 pair of the angle (532-546)
+      double Rik[3], RikSq = 0.0;
+      for (int x = 0; x < 3; ++x) { Rik[x] = av[x] - bv[x]; RikSq += Rik[x] * Rik[x]; }
+      const double QiQk = me.pr(me.atomType[i], me.atomType[k], me.layer).kCoul * me.charge[i] * me.charge[k];
+      double EL, WL;
+      me.ewald.discount(EL, WL, RikSq, QiQk);
+      Ecoul = Ecoul + EL;
+      for (int x = 0; x < 3; ++x) {
+        const double Fik = WL * Rik[x] / RikSq;
+        F[3 * i + x] += Fik;
+        F[3 * k + x] -= Fik;
+      }
     }
-    Potential = Potential + Ea;
-    Virial = Virial + w;
   }
 }
 
@@ -2442,10 +2668,10 @@ void EmDee_compute_forces(tEmDee* md) {
     for (int t = 0; t < T; ++t) s += Fs[(size_t)t * 3 * N + q];
     Fm[q] = s;
   }
-  compute_bonds(*me, Rs.data(), Fm, E[bond], W[bond]);      // 1240: after the thread sum here (addition commutes)
-  compute_angles(*me, Rs.data(), Fm, E[angle], W[angle]);   // 1241
+  compute_bonds(*me, Rs.data(), Fm, E[bond], W[bond], E[coul]);      // 1240: after the thread sum here (addition commutes)
+  compute_angles(*me, Rs.data(), Fm, E[angle], W[angle], E[coul]);   // 1241
   if (me->coul[me->layer - 1].requires_kspace) {
-    // compute_kspace (src/EmDeeData.f90:689-700) is outside the hot-path scope: E(long) stays zero.
+    compute_kspace(*me, Rs.data(), E[long_], Fm);
     W[long_] = E[coul] + E[long_] - W[coul];
   }
   md->Virial.Total = W[0] + W[1] + W[2] + W[3] + W[4];
