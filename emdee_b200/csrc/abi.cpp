@@ -311,6 +311,7 @@ struct System {
   std::vector<double> hostR;             // host copy, kept only when rigid bodies exist
   std::vector<std::vector<int>> excluded;   // per atom, sorted unique 1-based partners
   bool exclusions_dirty = true;
+  std::vector<double> ewaldRigid;                // per layer: sum over type pairs of kCoul * (intrabody erf terms + self energy)
   std::vector<emdee::BondedTerm> bondedTerms;   // bonds and angles in the order they were added (reference structList)
   int ndihedrals = 0;
   bool bonded_dirty = false;
@@ -501,6 +502,95 @@ void push_exclusions(System& me) {
   me.exclusions_dirty = false;
 }
 
+// cKspaceModel_initialize (src/modelClass_kspace.f90:108-273) and kspace_ewald_set_parameters / kspace_ewald_update
+// (src/kspace_ewald.f90:82-184): everything about the reciprocal-space solver that is fixed at initialization -- the
+// splitting parameter, the half space of wave vectors with their prefactors, the charged types, the Coulomb constants
+// of the type pairs, and the constant energy that takes the smooth part of intrabody pairs and the self term back out.
+// The per-step sums run on the device (engine_ewald.cuh). Like the reference, the wave vectors are NOT rebuilt when
+// the box changes later.
+void setup_ewald(System& me, double Rc) {
+  const char* task = "kspace model initialization";
+  const double PI = 3.14159265358979324, L = *me.box;
+  bool any = false;
+  std::vector<char> hasCharge(me.ntypes + 1, 0);
+  for (int a = 0; a < me.N; ++a)
+    if (me.charged[a]) { any = true; hasCharge[me.type[a]] = 1; }
+  if (!any) error(task, "system has no charged atoms");
+  std::vector<int> local(me.ntypes + 1, -1), kinds;
+  for (int t = 1; t <= me.ntypes; ++t)
+    if (hasCharge[t]) { local[t] = (int)kinds.size(); kinds.push_back(t); }
+  const int ntk = (int)kinds.size();
+  emdee::EwaldSetup e;
+  e.ntk = ntk;
+  e.atomKType.resize(me.N);
+  for (int a = 0; a < me.N; ++a) e.atomKType[a] = local[me.type[a]];
+  const double s = std::sqrt(inverse_of_x_plus_ln_x(-std::log(me.kspace.accuracy)));   // accuracy = exp(-s^2)/s^2
+  e.alpha = s / Rc;
+  e.beta = 2.0 * e.alpha / std::sqrt(PI);
+  const double kmax = 2.0 * e.alpha * s;
+  std::printf("KSPACE PARAMETERS: alpha = %10.5f and kmax = %10.5f\n", e.alpha, kmax);
+  for (HostModel& c : me.coul)
+    if (c.requires_kspace) {   // src/coul_long.f90:66-73
+      c.dev.a = e.alpha;
+      c.dev.b = e.beta;
+    }
+  // wave vectors: upper half of the (2 nmax + 1)^3 lattice (third index fastest), inside the sphere of radius nmax * 2pi/L
+  const double unit = 2.0 * PI / L, unitSq = unit * unit;
+  const int nmax = (int)std::ceil(kmax / unit), M = 2 * nmax + 1, half = (M * M * M) / 2;
+  const double kmaxSq = unitSq * nmax * nmax, B = -0.25 / (e.alpha * e.alpha), fourPiByV = 4.0 * PI / (L * L * L);
+  for (int i = half + 1; i <= 2 * half; ++i) {
+    const int n1 = i / (M * M), rem = i - n1 * M * M, n2 = rem / M, n3 = rem - n2 * M;
+    const int kv[3] = {n1 - nmax, n2 - nmax, n3 - nmax};
+    if (unitSq * kv[0] * kv[0] + unitSq * kv[1] * kv[1] + unitSq * kv[2] * kv[2] > kmaxSq) continue;
+    const double k[3] = {unit * kv[0], unit * kv[1], unit * kv[2]};
+    const double ksq = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
+    e.n.insert(e.n.end(), kv, kv + 3);
+    e.prefac.push_back(fourPiByV * std::exp(ksq * B) / ksq);
+  }
+  // Coulomb constants of the charged type pairs, per layer
+  e.lambda.assign((size_t)me.nlayers * ntk * ntk, 0.0);
+  for (int l = 1; l <= me.nlayers; ++l)
+    for (int i = 0; i < ntk; ++i)
+      for (int j = 0; j < ntk; ++j) {
+        const int lo = std::min(i, j), hi = std::max(i, j);   // the reference reads kCoul(itype, jtype) with i <= j
+        e.lambda[((size_t)(l - 1) * ntk + i) * ntk + j] = me.slot(kinds[lo], kinds[hi], l).kCoul;
+      }
+  // constant energy: -erf(alpha r)/r of every intrabody charged pair and -alpha q^2/sqrt(pi) of every listed atom,
+  // grouped by type pair so that each layer can weight them with its own Coulomb constants
+  std::vector<double> Erigid((size_t)ntk * ntk, 0.0);   // [lo*ntk + hi]
+  const double invL = 1.0 / L;
+  for (const RigidBody& b : me.bodies)
+    for (size_t x = 0; x + 1 < b.atoms.size(); ++x) {
+      const int i = b.atoms[x];
+      if (!me.charged[i]) continue;
+      for (size_t y = x + 1; y < b.atoms.size(); ++y) {
+        const int j = b.atoms[y];
+        if (!me.charged[j]) continue;
+        double rsq = 0.0;
+        for (int c = 0; c < 3; ++c) {
+          double d = me.hostR[3 * (size_t)i + c] - me.hostR[3 * (size_t)j + c];
+          d -= L * std::round(invL * d);
+          rsq += d * d;
+        }
+        const double r = std::sqrt(rsq), xx = e.alpha * r;
+        const double Eij = -(me.charge[i] * me.charge[j]) * (1.0 - nb::uerfc(xx, std::exp(-xx * xx))) / r;
+        const int ti = local[me.type[i]], tj = local[me.type[j]];
+        Erigid[(size_t)std::min(ti, tj) * ntk + std::max(ti, tj)] += Eij;
+      }
+    }
+  for (int a = 0; a < me.N; ++a)
+    if (local[me.type[a]] >= 0) {
+      const int t = local[me.type[a]];
+      Erigid[(size_t)t * ntk + t] -= e.alpha * (me.charge[a] * me.charge[a]) / std::sqrt(PI);
+    }
+  me.ewaldRigid.assign(me.nlayers, 0.0);
+  for (int l = 1; l <= me.nlayers; ++l)
+    for (int i = 0; i < ntk; ++i)
+      for (int j = i; j < ntk; ++j)
+        me.ewaldRigid[l - 1] += me.slot(kinds[i], kinds[j], l).kCoul * Erigid[(size_t)i * ntk + j];
+  me.engine->set_ewald(e);
+}
+
 // src/EmDeeData.f90:359-416
 void perform_initialization(System& me, tEmDee* md) {
   const char* task = "system initialization";
@@ -528,19 +618,7 @@ void perform_initialization(System& me, tEmDee* md) {
     if (me.kspace_active) me.kspace_active = false;
     else error(task, "a kspace solver is required, but has not been defined");
   }
-  if (me.kspace_active) {
-    // src/kspace_ewald.f90:82-99: only the splitting parameter feeds the real-space pair loop. The
-    // reciprocal-space sum (src/kspace_ewald.f90:188-314) is outside this build's scope.
-    const double s = std::sqrt(inverse_of_x_plus_ln_x(-std::log(me.kspace.accuracy)));
-    const double alpha = s / kspaceRc;
-    std::printf("KSPACE PARAMETERS: alpha = %10.5f and kmax = %10.5f\n", alpha, 2.0 * alpha * s);
-    warning("reciprocal-space Ewald terms are outside the hot-path scope and are not evaluated");
-    for (HostModel& c : me.coul)
-      if (c.requires_kspace) {   // src/coul_long.f90:66-73
-        c.dev.a = alpha;
-        c.dev.b = 2.0 * alpha / std::sqrt(3.14159265358979323846);
-      }
-  }
+  if (me.kspace_active) setup_ewald(me, kspaceRc);
   me.engine->set_charges(me.charge.data());
   push_tables(me);
   push_exclusions(me);
@@ -1131,27 +1209,34 @@ void EmDee_compute_forces(tEmDee* md) {   // src/EmDeeCode.f90:1215-1277
   const bool rebuilt = me->engine->compute_forces(me->layer - 1, compute, *me->box, r, tn);
   if (rebuilt) md->Builds += 1;
   emdee::BondedScalars bs;
-  if (!me->bondedTerms.empty() && me->bonded[me->layer - 1]) {   // compute_bonds / compute_angles, src/EmDeeData.f90:443-550
+  const bool kspace = me->coul[me->layer - 1].requires_kspace;
+  if (!me->bondedTerms.empty() && (me->bonded[me->layer - 1] || kspace)) {   // compute_bonds / compute_angles, src/EmDeeData.f90:443-550
     if (me->bonded_dirty) {
       me->engine->set_bonded(me->bondedTerms);
       me->bonded_dirty = false;
     }
-    me->engine->add_bonded(me->layer - 1, *me->box, bs);
+    me->engine->add_bonded(me->layer - 1, *me->box, me->bonded[me->layer - 1] != 0, kspace, bs);
+  }
+  r.Ecoul += bs.Ecoul;
+  double Elong = 0.0, WbodyLong = 0.0;
+  if (kspace) {   // compute_kspace, src/EmDeeData.f90:689-700
+    me->engine->add_ewald(me->layer - 1, *me->box, Elong, WbodyLong);
+    Elong += me->ewaldRigid[me->layer - 1];
   }
   md->Time.Neighbor += tn;
   double Wlong = 0.0;
-  if (me->coul[me->layer - 1].requires_kspace) Wlong = r.Ecoul - r.Wcoul;   // W(long) = E(coul) + E(long) - W(coul), E(long) not evaluated
+  if (kspace) Wlong = r.Ecoul + Elong - r.Wcoul;   // W(long) = E(coul) + E(long) - W(coul), src/EmDeeCode.f90:1251
   md->Virial.Total = r.Wpair + r.Wcoul + Wlong + bs.Wbond + bs.Wangle;
   if (me->nbodies() != 0) {
-    md->Virial.Body = r.Wbody + bs.Wbody;
+    md->Virial.Body = r.Wbody + bs.Wbody + WbodyLong;
     md->Virial.Total = md->Virial.Total + md->Virial.Body;
   }
   if (compute) {
     md->Energy.Dispersion = r.Epair;
-    md->Energy.Coulomb = r.Ecoul;
+    md->Energy.Coulomb = r.Ecoul + Elong;
     md->Energy.Bond = bs.Ebond;
     md->Energy.Angle = bs.Eangle;
-    md->Energy.Potential = r.Epair + r.Ecoul + bs.Ebond + bs.Eangle;
+    md->Energy.Potential = r.Epair + r.Ecoul + Elong + bs.Ebond + bs.Eangle;
     md->Energy.ShadowPotential = md->Energy.Potential;
   }
   md->Energy.UpToDate = compute;

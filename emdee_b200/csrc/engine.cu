@@ -48,6 +48,7 @@
 #include "engine_dynamics.cuh"
 #include "engine_bodies.cuh"
 #include "engine_bonded.cuh"
+#include "engine_ewald.cuh"
 #include "engine_dist.cuh"
 #include "engine_extra.cuh"
 
@@ -133,6 +134,12 @@ struct Engine::Impl {
   int nterms = 0;
   DBuf<BondedTerm> terms;
   DBuf<int> termFirst, termRef;
+  // reciprocal-space Ewald (engine_ewald.cuh)
+  bool ewald_on = false;
+  double ew_alpha = 0, ew_beta = 0;
+  int ew_nvecs = 0, ew_ntk = 0;
+  DBuf<int> ewN, ewKType;
+  DBuf<double> ewPrefac, ewLambda, ewSigma, ewPartial;
   // EmDee_memory_address / EmDee_share_phase_space: coordinates may change behind the engine's back
   bool exposed = false;            // a raw pointer to R, P or F was handed out: every call ends with a stream sync
   bool foreign_R = false;          // R is written by the client or by another system: never trust the cached criterion
@@ -292,6 +299,7 @@ Engine::~Engine() {
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
   s.known.release(); s.migCounts.release();
   s.terms.release(); s.termFirst.release(); s.termRef.release();
+  s.ewN.release(); s.ewKType.release(); s.ewPrefac.release(); s.ewLambda.release(); s.ewSigma.release(); s.ewPartial.release();
   s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
   s.bScalars.release(); s.shR0.release(); s.shQ0.release(); s.shS0.release(); s.freeMask.release();
   if (s.h_bscalars) cudaFreeHost(s.h_bscalars);
@@ -1211,13 +1219,17 @@ void Engine::set_bonded(const std::vector<BondedTerm>& terms) {
   if (s.h_bscalars == nullptr) CUDA_CHECK(cudaMallocHost(&s.h_bscalars, 16 * sizeof(double)));
 }
 
-void Engine::add_bonded(int layer0, double Lbox, BondedScalars& out) {
+void Engine::add_bonded(int layer0, double Lbox, bool bonded, bool kspace, BondedScalars& out) {
   Impl& s = *d_;
   out = BondedScalars();
   if (s.nterms == 0) return;
   if (s.world > 1) fatal("force computation", "bonded terms are not available on several GPUs yet");
   const double* delta = (s.has_delta && s.nbodies != 0) ? s.delta.p : nullptr;
-  k_bonded<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, s.termFirst.p, s.termRef.p, s.terms.p, s.R.p, Lbox,
+  BondedEwald ks;
+  ks.on = (kspace && s.ewald_on) ? 1 : 0;
+  ks.alpha = s.ew_alpha; ks.beta = s.ew_beta; ks.q = s.q.p; ks.type = s.type.p; ks.tab = s.tabs[layer0].p; ks.nt = s.nt;
+  if (!bonded && !ks.on) return;
+  k_bonded<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, s.termFirst.p, s.termRef.p, s.terms.p, s.R.p, Lbox, bonded ? 1 : 0, ks,
                                                s.F.p + (size_t)layer0 * 3 * s.N, delta, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
   stats_.launches += 1;
   CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -1227,6 +1239,50 @@ void Engine::add_bonded(int layer0, double Lbox, BondedScalars& out) {
   out.Eangle = s.h_bscalars[2];
   out.Wangle = s.h_bscalars[3];
   out.Wbody = s.h_bscalars[4];
+  out.Ecoul = s.h_bscalars[5];
+}
+
+// ---- reciprocal-space Ewald ---------------------------------------------------------------------------------------
+void Engine::set_ewald(const EwaldSetup& e) {
+  Impl& s = *d_;
+  if (e.ntk > EWALD_MAX_TYPES) fatal("kspace model initialization", "more than 8 distinct types of charged atoms are not supported");
+  s.ewald_on = true;
+  s.ew_alpha = e.alpha;
+  s.ew_beta = e.beta;
+  s.ew_ntk = e.ntk;
+  s.ew_nvecs = (int)e.prefac.size();
+  s.ewN.ensure(e.n.size() + 1);
+  s.ewKType.ensure(s.N);
+  s.ewPrefac.ensure(e.prefac.size() + 1);
+  s.ewLambda.ensure(e.lambda.size() + 1);
+  s.ewSigma.ensure(2 * (size_t)e.ntk * s.ew_nvecs + 1);
+  s.ewPartial.ensure((size_t)std::max(s.ew_nvecs, nblocks(s.N)) * 2 + 2);
+  CUDA_CHECK(cudaMemcpy(s.ewN.p, e.n.data(), e.n.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(s.ewKType.p, e.atomKType.data(), s.N * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(s.ewPrefac.p, e.prefac.data(), e.prefac.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(s.ewLambda.p, e.lambda.data(), e.lambda.size() * sizeof(double), cudaMemcpyHostToDevice));
+  s.bScalars.ensure(16);
+  if (s.h_bscalars == nullptr) CUDA_CHECK(cudaMallocHost(&s.h_bscalars, 16 * sizeof(double)));
+}
+
+void Engine::add_ewald(int layer0, double Lbox, double& Elong, double& Wbody) {
+  Impl& s = *d_;
+  Elong = Wbody = 0.0;
+  if (!s.ewald_on || s.ew_nvecs == 0) return;
+  if (s.world > 1) fatal("force computation", "the reciprocal-space Ewald sum is not available on several GPUs yet");
+  EwaldView v;
+  v.nvecs = s.ew_nvecs; v.ntk = s.ew_ntk; v.N = s.N; v.n = s.ewN.p; v.prefac = s.ewPrefac.p; v.ktype = s.ewKType.p;
+  v.q = s.q.p; v.R = s.R.p; v.sigma = s.ewSigma.p;
+  const double* lambda = s.ewLambda.p + (size_t)layer0 * s.ew_ntk * s.ew_ntk;
+  const double* delta = (s.has_delta && s.nbodies != 0) ? s.delta.p : nullptr;
+  k_ewald_structure<<<s.ew_nvecs, TPB, 0, s.stream>>>(v, Lbox, lambda, s.ewPartial.p, s.tickets.p + 3, s.bScalars.p + 12);
+  k_ewald_forces<<<nblocks(s.N), TPB, 0, s.stream>>>(v, Lbox, s.F.p + (size_t)layer0 * 3 * s.N, delta, s.ewPartial.p,
+                                                     s.tickets.p + 3, s.bScalars.p + 13);
+  stats_.launches += 2;
+  CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars + 12, s.bScalars.p + 12, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  Elong = s.h_bscalars[12];
+  Wbody = s.h_bscalars[13];
 }
 
 // ---- EmDee_memory_address / EmDee_share_phase_space ---------------------------------------------------------------

@@ -47,7 +47,17 @@ struct BondedTerm {
 };
 
 struct BondedScalars {
-  double Ebond = 0, Wbond = 0, Eangle = 0, Wangle = 0, Wbody = 0;
+  double Ebond = 0, Wbond = 0, Eangle = 0, Wangle = 0, Wbody = 0, Ecoul = 0;
+};
+
+// Reciprocal-space Ewald solver, as set up on the host (reference cKspaceModel_initialize + kspace_ewald_update)
+struct EwaldSetup {
+  double alpha = 0, beta = 0;
+  int ntk = 0;                    // distinct types of charged atoms
+  std::vector<int> atomKType;     // per atom: index among those types, or -1
+  std::vector<int> n;             // 3 per wave vector (half space)
+  std::vector<double> prefac;     // per wave vector
+  std::vector<double> lambda;     // (nlayers, ntk, ntk) Coulomb constants of the type pairs
 };
 
 struct EngineStats {
@@ -106,7 +116,11 @@ class Engine {
 
   // ---- bonded terms (reference compute_bonds / compute_angles, src/EmDeeData.f90:443-550) --------
   void set_bonded(const std::vector<BondedTerm>& terms);
-  void add_bonded(int layer0, double Lbox, BondedScalars& out);   // adds to the layer's forces (after compute_forces)
+  void add_bonded(int layer0, double Lbox, bool bonded, bool kspace, BondedScalars& out);   // adds to the layer's forces (after compute_forces)
+
+  // ---- reciprocal space (reference compute_kspace, src/EmDeeData.f90:689-700; src/kspace_ewald.f90:188-314) ----
+  void set_ewald(const EwaldSetup& e);
+  void add_ewald(int layer0, double Lbox, double& Elong, double& Wbody);   // adds to the layer's forces
 
   // ---- raw pointers and aliasing (reference EmDee_memory_address / EmDee_share_phase_space) ------
   enum Exposed { EXPOSE_R, EXPOSE_P, EXPOSE_F, EXPOSE_LAYER_F };

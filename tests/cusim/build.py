@@ -16,7 +16,7 @@ OUT = os.path.join(ROOT, "tests", "_build")
 GEN = os.path.join(OUT, "cusim_src")
 LIB = os.path.join(OUT, "libemdee_cusim.so")
 PARTS = ["engine.cu", "engine_common.cuh", "engine_list.cuh", "engine_force.cuh", "engine_brick.cuh",
-         "engine_dynamics.cuh", "engine_bodies.cuh", "engine_bonded.cuh", "engine_dist.cuh", "engine_extra.cuh"]
+         "engine_dynamics.cuh", "engine_bodies.cuh", "engine_bonded.cuh", "engine_ewald.cuh", "engine_dist.cuh", "engine_extra.cuh"]
 
 
 def _match_back(text, i, open_ch, close_ch):

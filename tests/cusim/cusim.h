@@ -397,6 +397,7 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
+inline void sincospi(double x, double* s, double* c) { sincos(3.14159265358979323846 * x, s, c); }
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 template <class T>

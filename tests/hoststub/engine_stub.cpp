@@ -64,7 +64,9 @@ void Engine::download_body(int, double*) {}
 void Engine::upload_body(int, const double*) {}
 void Engine::derive_quaternion_momenta() {}
 void Engine::set_bonded(const std::vector<BondedTerm>&) {}
-void Engine::add_bonded(int, double, BondedScalars& out) { out = BondedScalars(); }
+void Engine::add_bonded(int, double, bool, bool, BondedScalars& out) { out = BondedScalars(); }
+void Engine::set_ewald(const EwaldSetup&) {}
+void Engine::add_ewald(int, double, double& e, double& w) { e = w = 0.0; }
 void* Engine::expose(int, int) { return nullptr; }
 void Engine::share_phase_space(Engine&) {}
 void Engine::shadow_pre(int, double, int) {}

@@ -19,6 +19,7 @@ import test_gpu_parity as t_par
 import test_zz_box_rescale as t_box
 import test_zz_rdf as t_rdf
 import test_zzz_bonded as t_bd
+import test_zzz_ewald as t_ew
 import test_zzz_phase_space as t_ps
 import test_zzz_rigid_bodies as t_rb
 import test_zz_single_type_coulomb as t_stc
@@ -55,6 +56,7 @@ CASES = (_cases(t_par, skip=("test_brick_path_opt_in", "test_duo_path_opt_in"))
          + _cases(t_rb)
          + _cases(t_ps)
          + _cases(t_bd)
+         + _cases(t_ew)
          + _cases(t_exp)
          + [pytest.param(t_par.test_brick_path_opt_in, {}, id="test_gpu_parity::test_brick_path_opt_in"),
             pytest.param(t_par.test_duo_path_opt_in, {}, id="test_gpu_parity::test_duo_path_opt_in")])
