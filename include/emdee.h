@@ -111,7 +111,8 @@ void EmDee_set_coul_multimodel( tEmDee md, void* model[] );
 /* src/EmDeeCode.f90:524-570 */
 void EmDee_ignore_pair( tEmDee md, int i, int j );
 
-/* src/EmDeeCode.f90:574-655 (bonded terms: outside the hot-path scope of this build) */
+/* src/EmDeeCode.f90:574-655 (harmonic bonds and angles run on the device; dihedrals are stored and excluded only,
+   exactly as in the reference, whose EmDee_compute_forces never evaluates them) */
 void EmDee_add_bond( tEmDee md, int i, int j, void* model );
 void EmDee_add_angle( tEmDee md, int i, int j, int k, void* model );
 void EmDee_add_dihedral( tEmDee md, int i, int j, int k, int l, void* model );

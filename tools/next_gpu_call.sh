@@ -2,12 +2,13 @@
 # First GPU call of the next round (run under gpurun from the repo root; ~6 GPU-minutes):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/next_gpu_call.sh'
 # 1. gather-cost microbenchmark (decides between the layouts discussed in DESIGN.md section 5)
-# 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS, EMDEE_CLUSTER2) and of the box-rescale scenario
+# 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS, EMDEE_CLUSTER2), of the box-rescale scenario and of the
+#    kernels written after the last GPU session (rigid bodies, verlet_step, bonded, Ewald, memory_address, sharing)
 # 3. LJ-1M bench: default path vs EMDEE_ROWS=8/16/32 vs EMDEE_CLUSTER2=1
 set -u
 mkdir -p gpurun_out
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lsu_probe tools/lsu_probe.cu && timeout 120 /tmp/lsu_probe > gpurun_out/lsu_probe.txt 2>&1
-EMDEE_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py tests/test_zz_box_rescale.py tests/test_zz_single_type_coulomb.py tests/test_zz_rdf.py tests/test_zz_edge_cases.py -m gpu -q > gpurun_out/experimental_tests.txt 2>&1
+EMDEE_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py tests/test_zz_box_rescale.py tests/test_zz_single_type_coulomb.py tests/test_zz_rdf.py tests/test_zz_edge_cases.py tests/test_zzz_rigid_bodies.py tests/test_zzz_phase_space.py tests/test_zzz_bonded.py tests/test_zzz_ewald.py -m gpu -q > gpurun_out/experimental_tests.txt 2>&1
 tail -5 gpurun_out/experimental_tests.txt
 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 for g in 8 16 32; do
@@ -24,4 +25,6 @@ for f in sorted(glob.glob("gpurun_out/bench_*.json")):
     except Exception as ex:
         print(f, "unreadable:", ex)
 PY
+timeout 600 python bench.py --workload spce --steps 20 > gpurun_out/bench_spce.json 2> gpurun_out/bench_spce.err
+tail -c 1500 gpurun_out/bench_spce.json
 cat gpurun_out/lsu_probe.txt
