@@ -86,7 +86,8 @@ def test_results_do_not_depend_on_thread_interleaving(order):
     import subprocess
     import sys
     env = dict(os.environ, CUSIM_ORDER=order)
-    sel = "two_types or dynamics_with_rebuilds or kat_replay_on_gpu or spce_single_point or brick or duo or rdf or degenerate"
+    sel = ("two_types or dynamics_with_rebuilds or kat_replay_on_gpu or spce_single_point or brick or duo or rdf or degenerate "
+           "or verlet_step_with_shadow or next_to_rigid or rock_salt or share_phase_space")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
                         f"test_on_emulator and ({sel})"], capture_output=True, text=True, env=env, cwd=cm.ROOT, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
