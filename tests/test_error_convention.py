@@ -56,6 +56,26 @@ CASES = {
                                  "s.set_coul_model(lib.EmDee_coul_long()); s.upload('charges', np.ones(N)); "
                                  "s.upload('box', [L]); s.upload('coordinates', R)"),
     "atom types not starting at 1": "lib.system(1, 1, 2.5, 0.3, N, types + 1, None, None)",
+    "bond atom out of range": "s = fresh(); lib.EmDee_add_bond(s.md, 1, N + 1, lib.EmDee_bond_harmonic(1.0, 1.0))",
+    "bond with a null model": "s = fresh(); lib.EmDee_add_bond(s.md, 1, 2, None)",
+    "bond with an angle model": "s = fresh(); lib.EmDee_add_bond(s.md, 1, 2, lib.EmDee_angle_harmonic(1.0, 1.0))",
+    "angle atom out of range": "s = fresh(); lib.EmDee_add_angle(s.md, 0, 1, 2, lib.EmDee_angle_harmonic(1.0, 1.0))",
+    "angle with a bond model": "s = fresh(); lib.EmDee_add_angle(s.md, 1, 2, 3, lib.EmDee_bond_none())",
+    "dihedral with a pair model": "s = fresh(); lib.EmDee_add_dihedral(s.md, 1, 2, 3, 4, lib.EmDee_pair_lj_cut(1.0, 1.0))",
+    "dihedral atom out of range": "s = fresh(); lib.EmDee_add_dihedral(s.md, 1, 2, 3, N + 7, lib.EmDee_dihedral_none())",
+    "sharing before initialisation": "a = ready(); b = fresh(); a.share_phase_space(b)",
+    "sharing with different types": ("a = ready(); b = lib.system(1, 1, 2.5, 0.3, N, np.ones(N, dtype=np.int32), None, None); "
+                                     "b.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0); b.upload('box', [L]); "
+                                     "b.upload('coordinates', R); a.share_phase_space(b)"),
+    "sharing with different masses": ("a = ready(); b = lib.system(1, 1, 2.5, 0.3, N, types, np.array([1.0, 2.0]), None); "
+                                      "b.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0); b.upload('box', [L]); "
+                                      "b.upload('coordinates', R); a.share_phase_space(b)"),
+    "memory address of an unknown array": "s = ready(); lib.EmDee_memory_address(s.md, b'velocities')",
+    "random momenta of bodies before initialisation": ("s = lib.system(1, 1, 2.5, 0.3, N, types, None, (np.arange(N) // 2 + 1).astype(np.int32)); "
+                                                       "s.random_momenta(1.0, True, 1)"),
+    "ewald without charges": ("s = fresh(); s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 1.0); "
+                              "s.set_coul_model(lib.EmDee_coul_long()); s.set_kspace_model(lib.EmDee_kspace_ewald(1e-4)); "
+                              "s.upload('box', [L]); s.upload('coordinates', R)"),
 }
 
 
