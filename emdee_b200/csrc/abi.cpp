@@ -308,7 +308,6 @@ struct System {
   std::vector<char> charged;
   std::vector<int> atomBody, freeAtoms;
   std::vector<RigidBody> bodies;
-  std::vector<double> hostR;             // host copy, kept only when rigid bodies exist
   std::vector<std::vector<int>> excluded;   // per atom, sorted unique 1-based partners
   bool exclusions_dirty = true;
   std::vector<double> ewaldRigid;                // per layer: sum over type pairs of kCoul * (intrabody erf terms + self energy)
@@ -417,28 +416,6 @@ void setup_bodies(System& me, const int* bodies) {
   int next = nb_;
   for (int i = 0; i < N; ++i)
     if (me.atomBody[i] == 0) me.atomBody[i] = ++next;
-}
-
-// src/EmDeeData.f90:420-439 + src/ArBee.f90:97-106: make each body whole w.r.t. its first atom, then
-// delta = r - r_cm. Runs on the host copy of an uploaded configuration, before it is sent to HBM.
-void update_rigid_bodies(System& me, std::vector<double>& delta) {
-  const double L = *me.box, invL = 1.0 / L;
-  delta.assign(3 * (size_t)me.N, 0.0);
-  for (const RigidBody& b : me.bodies) {
-    const int first = b.atoms[0];
-    double rcm[3] = {0, 0, 0};
-    for (size_t k = 0; k < b.atoms.size(); ++k) {
-      const int a = b.atoms[k];
-      for (int x = 0; x < 3; ++x) {
-        double& r = me.hostR[3 * (size_t)a + x];
-        if (k > 0) r = r - L * std::round(invL * (r - me.hostR[3 * (size_t)first + x]));
-        rcm[x] += b.m[k] * r;
-      }
-    }
-    for (int x = 0; x < 3; ++x) rcm[x] *= 1.0 / b.mass;
-    for (int a : b.atoms)
-      for (int x = 0; x < 3; ++x) delta[3 * (size_t)a + x] = me.hostR[3 * (size_t)a + x] - rcm[x];
-  }
 }
 
 // src/EmDeeData.f90:193-223
@@ -559,6 +536,11 @@ void setup_ewald(System& me, double Rc) {
   // grouped by type pair so that each layer can weight them with its own Coulomb constants
   std::vector<double> Erigid((size_t)ntk * ntk, 0.0);   // [lo*ntk + hi]
   const double invL = 1.0 / L;
+  std::vector<double> hostR;
+  if (!me.bodies.empty()) {
+    hostR.resize(3 * (size_t)me.N);
+    me.engine->download_coordinates(hostR.data());
+  }
   for (const RigidBody& b : me.bodies)
     for (size_t x = 0; x + 1 < b.atoms.size(); ++x) {
       const int i = b.atoms[x];
@@ -568,7 +550,7 @@ void setup_ewald(System& me, double Rc) {
         if (!me.charged[j]) continue;
         double rsq = 0.0;
         for (int c = 0; c < 3; ++c) {
-          double d = me.hostR[3 * (size_t)i + c] - me.hostR[3 * (size_t)j + c];
+          double d = hostR[3 * (size_t)i + c] - hostR[3 * (size_t)j + c];
           d -= L * std::round(invL * d);
           rsq += d * d;
         }
@@ -594,13 +576,9 @@ void setup_ewald(System& me, double Rc) {
 // src/EmDeeData.f90:359-416
 void perform_initialization(System& me, tEmDee* md) {
   const char* task = "system initialization";
-  if (me.nbodies() != 0) {
-    std::vector<double> delta;
-    update_rigid_bodies(me, delta);
-    me.engine->upload_coordinates(me.hostR.data());
-    me.engine->upload_body_delta(delta.data());
-    me.engine->update_body_frames();   // tBody_update: principal frame, quaternion, body coordinates (on the device)
-  }
+  // update_rigid_bodies (src/EmDeeData.f90:420-439) + tBody_update: unwrapping, centres of mass, member offsets,
+  // principal frames and quaternions, all on the device, in place on the coordinates uploaded earlier
+  if (me.nbodies() != 0) me.engine->update_body_frames(*me.box);
   const int bodyDoF = 6 * me.nbodies();
   md->RotDoF = bodyDoF - 3 * me.nbodies();
   md->DoF = 3 * (int)me.freeAtoms.size() + bodyDoF - 3;
@@ -1005,26 +983,12 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/Em
     else if (me->hasR) initialize_system();
   } else if (item == "coordinates") {
     me->hasR = true;
-    if (me->nbodies() != 0) {
-      me->hostR.assign(address, address + 3 * (size_t)me->N);
-      if (me->initialized) {
-        invalidate(*me, md);
-        bool reframe = false;
-        if (md->Options.AutoBodyUpdate) {
-          std::vector<double> delta;
-          update_rigid_bodies(*me, delta);
-          me->engine->upload_body_delta(delta.data());
-          reframe = true;
-        }
-        me->engine->upload_coordinates(me->hostR.data());
-        if (reframe) me->engine->update_body_frames();
-      } else if (me->hasL) {
-        initialize_system();   // uploads the body-updated coordinates itself
-      }
-    } else {
-      me->engine->upload_coordinates(address);
-      if (me->initialized) invalidate(*me, md);
-      else if (me->hasL) initialize_system();
+    me->engine->upload_coordinates(address);
+    if (me->initialized) {
+      invalidate(*me, md);
+      if (md->Options.AutoBodyUpdate && me->nbodies() != 0) me->engine->update_body_frames(*me->box);
+    } else if (me->hasL) {
+      initialize_system();
     }
   } else if (item == "momenta") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");

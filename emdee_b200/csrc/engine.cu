@@ -536,12 +536,6 @@ void Engine::upload_coordinates(const double* R) {
     s.p_partial = true;    // ... but the momenta of atoms owned elsewhere are stale here until the next rebuild
   }
 }
-void Engine::upload_body_delta(const double* delta) {
-  Impl& s = *d_;
-  s.delta.ensure(3 * (size_t)s.N);
-  CUDA_CHECK(cudaMemcpy(s.delta.p, delta, 3 * (size_t)s.N * sizeof(double), cudaMemcpyHostToDevice));
-  s.has_delta = true;
-}
 void Engine::upload_momenta(const double* P) {
   CUDA_CHECK(cudaMemcpy(d_->P.p, P, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
   d_->p_partial = false;
@@ -1126,13 +1120,19 @@ void Engine::set_bodies(const std::vector<int>& first, const std::vector<int>& a
   CUDA_CHECK(cudaMemcpy(s.freeMask.p, mask.data(), s.N, cudaMemcpyHostToDevice));
 }
 
-void Engine::update_body_frames() {
+void Engine::update_body_frames(double Lbox) {
   Impl& s = *d_;
   if (s.nbodies == 0) return;
-  if (!s.has_delta || !s.has_R) fatal("rigid-body update", "coordinates have not been uploaded");
-  k_body_frame<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.R.p, s.delta.p);
+  if (!s.has_R) fatal("rigid-body update", "coordinates have not been uploaded");
+  if (!s.has_delta) {
+    s.delta.ensure(3 * (size_t)s.N);
+    CUDA_CHECK(cudaMemsetAsync(s.delta.p, 0, 3 * (size_t)s.N * sizeof(double), s.stream));   // free atoms keep a zero offset
+    s.has_delta = true;
+  }
+  k_body_frame<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.R.p, s.delta.p, Lbox);
   stats_.launches += 1;
   s.frames_valid = true;
+  s.check_cached = false;   // member coordinates may have been shifted by whole box lengths
 }
 
 void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool rotate, bool want_kinetic, KineticAll& ke) {

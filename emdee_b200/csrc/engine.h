@@ -83,7 +83,6 @@ class Engine {
 
   // ---- transfers (host pointers; pinned or pageable) ---------------------------------------
   void upload_coordinates(const double* R);
-  void upload_body_delta(const double* delta);                           // (3,N), zero for free atoms
   void upload_momenta(const double* P);
   void upload_forces(int layer0, const double* F);
   void download_coordinates(double* R);
@@ -103,7 +102,7 @@ class Engine {
   enum BodyItem { BODY_QUATERNION, BODY_QUATMOM, BODY_OMEGA, BODY_RCM, BODY_PCM, BODY_FORCE, BODY_TORQUE, BODY_INERTIA };
   void set_bodies(const std::vector<int>& first, const std::vector<int>& atoms,
                   const std::vector<double>& memberMass);                // CSR of body members (0-based atoms)
-  void update_body_frames();                                             // tBody_update after coordinates + delta uploads
+  void update_body_frames(double Lbox);                                  // update_rigid_bodies + tBody_update on the uploaded coordinates
   void boost_all(int layer0, double CP, double CF, bool translate, bool rotate, bool want_kinetic, KineticAll& ke);
   void move_all(double CR, double CP, double dt, bool translate, bool rotate, int mode);
   void refresh_member_momenta();                                         // particle_momenta into P (before download_momenta)

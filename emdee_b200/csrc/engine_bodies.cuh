@@ -2,7 +2,8 @@
 // Part of the single translation unit engine.cu (included there, in order; not a standalone header).
 //
 // Reference loops replaced (paths relative to the reference tree):
-//   k_body_frame          <- src/ArBee.f90:97-130 (tBody_update: inertia tensor, principal frame, quaternion, body coordinates)
+//   k_body_frame          <- src/EmDeeData.f90:420-439 + src/ArBee.f90:97-130 (update_rigid_bodies, tBody_update: unwrapping,
+//                            centre of mass, member offsets, inertia tensor, principal frame, quaternion, body coordinates)
 //   k_body_boost          <- src/ArBee.f90:330-357 + src/EmDeeData.f90:864-922 (force_and_torque, boost, kinetic_energies)
 //   k_body_move           <- src/EmDeeData.f90:823-860 + src/ArBee.f90:178-313 (move, rotate_no_squish, rotate_exact)
 //   k_body_momenta        <- src/ArBee.f90:317-326 (particle_momenta, for EmDee_download "momenta")
@@ -464,21 +465,48 @@ __device__ __forceinline__ void reduce_and_finish(const double (&mine)[W], doubl
 }
 
 // ---- kernels ----------------------------------------------------------------------------------------------------------
-// tBody_update: centre of mass from the (already whole) member coordinates; inertia tensor of the member offsets;
-// principal frame -> MoI, quaternion, body-frame member coordinates. Momenta are left as they are.
-__global__ void __launch_bounds__(TPB) k_body_frame(BodyView v, const double* __restrict__ R, const double* __restrict__ delta) {
+// update_rigid_bodies + tBody_update (reference src/EmDeeData.f90:420-439, src/ArBee.f90:97-130): make the body whole
+// around its first member (minimum image, written back to R), centre of mass, member offsets delta = r - rcm (what the
+// force kernel's rigid-body virial reads), inertia tensor -> principal frame -> MoI, quaternion, body-frame member
+// coordinates. Momenta are left as they are. The unwrapping uses individually rounded operations so that the
+// coordinates are the reference's to the last bit.
+__global__ void __launch_bounds__(TPB) k_body_frame(BodyView v, double* __restrict__ R, double* __restrict__ delta, double L) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= v.nb) return;
   const int k0 = v.first[b], k1 = v.first[b + 1];
-  double msum = 0.0, c[3] = {0.0, 0.0, 0.0}, t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const double invL = 1.0 / L;
+  const size_t a0 = (size_t)v.atom[k0];
+  const double r0[3] = {R[3 * a0], R[3 * a0 + 1], R[3 * a0 + 2]};
+  double msum = 0.0, c[3] = {0.0, 0.0, 0.0};
   for (int k = k0; k < k1; ++k) {
-    const int a = v.atom[k];
+    const size_t a = (size_t)v.atom[k];
     const double m = v.mItem[k];
-    const double x = delta[3 * (size_t)a], y = delta[3 * (size_t)a + 1], z = delta[3 * (size_t)a + 2];
     msum += m;
-    c[0] += m * R[3 * (size_t)a];
-    c[1] += m * R[3 * (size_t)a + 1];
-    c[2] += m * R[3 * (size_t)a + 2];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      double r = R[3 * a + x];
+      if (k > k0) {
+        r = __dsub_rn(r, __dmul_rn(L, round(__dmul_rn(invL, __dsub_rn(r, r0[x])))));
+        R[3 * a + x] = r;
+      }
+      c[x] = __dadd_rn(c[x], __dmul_rn(m, r));
+    }
+  }
+  const double inv = 1.0 / msum;
+  v.mass[b] = msum;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    c[x] = __dmul_rn(c[x], inv);
+    v.rcm[(size_t)x * v.nb + b] = c[x];
+  }
+  double t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int k = k0; k < k1; ++k) {
+    const size_t a = (size_t)v.atom[k];
+    const double m = v.mItem[k];
+    const double x = __dsub_rn(R[3 * a], c[0]), y = __dsub_rn(R[3 * a + 1], c[1]), z = __dsub_rn(R[3 * a + 2], c[2]);
+    delta[3 * a] = x;
+    delta[3 * a + 1] = y;
+    delta[3 * a + 2] = z;
     t[0] += m * (y * y + z * z);
     t[3] += m * (x * x + z * z);
     t[5] += m * (x * x + y * y);
@@ -487,10 +515,6 @@ __global__ void __launch_bounds__(TPB) k_body_frame(BodyView v, const double* __
     t[4] += m * y * z;
   }
   t[1] = -t[1]; t[2] = -t[2]; t[4] = -t[4];
-  const double inv = 1.0 / msum;
-  v.mass[b] = msum;
-#pragma unroll
-  for (int x = 0; x < 3; ++x) v.rcm[(size_t)x * v.nb + b] = c[x] * inv;
   double w[3], ax[3][3], q[4];
   principal_axes(t, w, ax);
   quaternion_of_axes(ax, q);
@@ -499,8 +523,8 @@ __global__ void __launch_bounds__(TPB) k_body_frame(BodyView v, const double* __
 #pragma unroll
   for (int x = 0; x < 4; ++x) v.q[(size_t)x * v.nb + b] = q[x];
   for (int k = k0; k < k1; ++k) {
-    const int a = v.atom[k];
-    const double dl[3] = {delta[3 * (size_t)a], delta[3 * (size_t)a + 1], delta[3 * (size_t)a + 2]};
+    const size_t a = (size_t)v.atom[k];
+    const double dl[3] = {delta[3 * a], delta[3 * a + 1], delta[3 * a + 2]};
 #pragma unroll
     for (int x = 0; x < 3; ++x) v.d[3 * (size_t)k + x] = ax[x][0] * dl[0] + ax[x][1] * dl[1] + ax[x][2] * dl[2];
   }

@@ -42,7 +42,6 @@ void Engine::set_charges(const double*) {}
 void Engine::set_interact(const std::vector<char>& interact) { d_->interact = interact; }
 void Engine::set_layer(int layer0, const LayerTable& t) { d_->layers[layer0] = t; }
 void Engine::upload_coordinates(const double* R) { std::memcpy(d_->R.data(), R, d_->R.size() * sizeof(double)); }
-void Engine::upload_body_delta(const double*) {}
 void Engine::upload_momenta(const double* P) { std::memcpy(d_->P.data(), P, d_->P.size() * sizeof(double)); }
 void Engine::upload_forces(int, const double*) {}
 void Engine::download_coordinates(double* R) { std::memcpy(R, d_->R.data(), d_->R.size() * sizeof(double)); }
@@ -55,7 +54,7 @@ bool Engine::compute_forces(int, bool, double, ForceScalars& out, double&) {
 void Engine::boost(int, double, double, bool, KineticScalars& ke) { ke = KineticScalars(); }
 void Engine::displace(double, double) {}
 void Engine::set_bodies(const std::vector<int>&, const std::vector<int>&, const std::vector<double>&) {}
-void Engine::update_body_frames() {}
+void Engine::update_body_frames(double) {}
 void Engine::boost_all(int, double, double, bool, bool, bool, KineticAll& ke) { ke = KineticAll(); }
 void Engine::move_all(double, double, double, bool, bool, int) {}
 void Engine::refresh_member_momenta() {}
