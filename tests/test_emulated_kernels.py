@@ -68,6 +68,7 @@ def _use_emulated_library(monkeypatch):
     monkeypatch.setattr(cm, "product", lambda: lib)
     monkeypatch.setenv("EMDEE_TEST_EXPERIMENTAL", "1")
     monkeypatch.setenv("EMDEE_TEST_REPLAY_STEPS", "20")
+    monkeypatch.setenv("EMDEE_TEST_REPLICAS", "1")
 
 
 @pytest.mark.parametrize("fn,kwargs", CASES)

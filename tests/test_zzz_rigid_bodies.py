@@ -183,6 +183,42 @@ def test_mixed_bodies_and_free_atoms():
     sp.finalize(), so.finalize()
 
 
+def test_replicated_spce_rigid_nve_properties():
+    """Size-independent properties on a replicated SPC/E box (4^3 x 2250 = 144 000 atoms on the GPU; the emulator run
+    keeps one replica): n^3-replica identity of the energies, then rigid-body NVE on the device -- total energy and
+    linear momentum conserved, every molecule still rigid, centres of mass consistent with the member coordinates."""
+    import os
+    n = int(os.environ.get("EMDEE_TEST_REPLICAS", "4"))
+    f = lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0)
+    s1, c1 = cm.spce_sample_system(cm.product(), f)
+    U1, W1 = s1.md.Energy.Potential, s1.md.Virial.Total
+    s1.finalize()
+    s, c = cm.spce_sample_system(cm.product(), f, replicas=n)
+    assert cm.rel(s.md.Energy.Potential, n ** 3 * U1) < 1e-10 and cm.rel(s.md.Virial.Total, n ** 3 * W1) < 1e-9
+    N, nb = c["N"], c["N"] // 3
+    s.random_momenta(c["kB"] * c["Temp"], True, 2024)
+    R0 = s.download("coordinates")
+    d0 = np.linalg.norm(R0[0::3] - R0[1::3], axis=1)
+    E0 = s.md.Energy.Potential + s.md.Kinetic.Total
+    for _ in range(10):
+        s.boost(1.0, 0.0, 0.5)
+        s.displace(1.0, 0.0, 1.0)
+        s.boost(1.0, 0.0, 0.5)
+    E1 = s.md.Energy.Potential + s.md.Kinetic.Total
+    assert abs(E1 - E0) < 5e-4 * s.md.Kinetic.Total
+    R, P = s.download("coordinates"), s.download("momenta")
+    assert np.abs(np.linalg.norm(R[0::3] - R[1::3], axis=1) - d0).max() < 1e-10          # O-H bonds still rigid
+    assert np.abs(P.sum(axis=0)).max() < 1e-9 * np.abs(P).sum()                          # no net momentum
+    m = c["mass"][c["atomType"] - 1]
+    com = (m[:, None] * R).reshape(nb, 3, 3).sum(axis=1) / m.reshape(nb, 3).sum(axis=1)[:, None]
+    assert np.abs(s.download("bodycoord", (nb, 3)) - com).max() < 1e-9
+    K = 0.5 * (P ** 2 / m[:, None]).sum()
+    assert cm.rel(K, s.md.Kinetic.Total) < 1e-10                                         # atom momenta carry the same kinetic energy
+    q = s.download("quaternions", (nb, 4))
+    assert np.abs((q ** 2).sum(axis=1) - 1.0).max() < 1e-12
+    s.finalize()
+
+
 def test_free_rotor_long_exact_rotation():
     """One isolated body, many periods of torque-free motion in single calls: Jacobi / Carlson code paths with period
     jumps (src/ArBee.f90:262-268) on the device against the oracle."""
