@@ -8,6 +8,9 @@
 //
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o lsu_probe tools/lsu_probe.cu && ./lsu_probe
 //
+// Also measured: the same gather through the texture front-end (TLD), LDG/TEX alternation (do the two front-ends add
+// up or share one data stage?) and a 16-byte record (what a compact position format would buy).
+//
 // Output: one line per (path, pattern): SM cycles per warp-gather at full occupancy (throughput, not latency).
 #include <cstdio>
 #include <cstdlib>
@@ -63,9 +66,13 @@ constexpr int ITER = 2048;
 constexpr int UNROLL = 4;
 
 // path 0: LDG.E.256 of an AoS record   path 1: 2 x LDG.E.128   path 2: 3 x LDG.E.64 from SoA arrays
+// path 3: the same 32-byte record through the TEXTURE front-end (2 x tex1Dfetch<int4>)
+// path 4: alternate gathers between LDG.E.256 and the texture front-end (do the two front-ends overlap?)
+// path 5: a 16-byte record (what a cell-relative fixed-point position format would gather), one LDG.E.128
 template <int PATH>
 __global__ void __launch_bounds__(256) k_global(const double4* __restrict__ rec, const double* __restrict__ soa,
-                                                unsigned mask, int pattern, double* sink, long long* cycles) {
+                                                cudaTextureObject_t tex, unsigned mask, int pattern, double* sink,
+                                                long long* cycles) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double acc = 0.0;
@@ -81,9 +88,17 @@ __global__ void __launch_bounds__(256) k_global(const double4* __restrict__ rec,
         const double2* p = reinterpret_cast<const double2*>(rec + j);
         const double2 a = __ldg(p), b = __ldg(p + 1);
         v[u] = make_double4(a.x, a.y, b.x, b.y);
-      } else {
+      } else if (PATH == 2) {
         const size_t n = (size_t)mask + 1;
         v[u] = make_double4(__ldg(soa + j), __ldg(soa + n + j), __ldg(soa + 2 * n + j), 0.0);
+      } else if (PATH == 3 || (PATH == 4 && (u & 1))) {
+        const int4 a = tex1Dfetch<int4>(tex, 2 * (int)j), b = tex1Dfetch<int4>(tex, 2 * (int)j + 1);
+        v[u] = make_double4(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(b.y, b.x), 0.0);
+      } else if (PATH == 4) {
+        v[u] = ldg256(rec + j);
+      } else {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(rec) + j);   // 16-byte records, same index pattern
+        v[u] = make_double4(a.x, a.y, 0.0, 0.0);
       }
     }
 #pragma unroll
@@ -163,16 +178,32 @@ int main() {
     CK(cudaMalloc(&soa, 3 * n * sizeof(double)));
     CK(cudaMemset(rec, 0, n * sizeof(double4)));
     CK(cudaMemset(soa, 0, 3 * n * sizeof(double)));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = rec;
+    rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+    rd.res.linear.sizeInBytes = n * sizeof(double4);
+    cudaTextureDesc td{};
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
     const char* foot = logn == 11 ? "L1 64KB" : "L2 32MB";
     const int blocks = sms * 4;
     for (int p = 0; p < NPATTERN; ++p) {
-      for (int rep = 0; rep < 2; ++rep) k_global<0><<<blocks, 256>>>(rec, soa, (unsigned)n - 1, p, sink, cycles);
+      for (int rep = 0; rep < 2; ++rep) k_global<0><<<blocks, 256>>>(rec, soa, tex, (unsigned)n - 1, p, sink, cycles);
       report("LDG.E.256 AoS", foot, p, blocks, 4);
-      for (int rep = 0; rep < 2; ++rep) k_global<1><<<blocks, 256>>>(rec, soa, (unsigned)n - 1, p, sink, cycles);
+      for (int rep = 0; rep < 2; ++rep) k_global<1><<<blocks, 256>>>(rec, soa, tex, (unsigned)n - 1, p, sink, cycles);
       report("2 x LDG.E.128 AoS", foot, p, blocks, 4);
-      for (int rep = 0; rep < 2; ++rep) k_global<2><<<blocks, 256>>>(rec, soa, (unsigned)n - 1, p, sink, cycles);
+      for (int rep = 0; rep < 2; ++rep) k_global<2><<<blocks, 256>>>(rec, soa, tex, (unsigned)n - 1, p, sink, cycles);
       report("3 x LDG.E.64 SoA", foot, p, blocks, 4);
+      for (int rep = 0; rep < 2; ++rep) k_global<3><<<blocks, 256>>>(rec, soa, tex, (unsigned)n - 1, p, sink, cycles);
+      report("2 x TEX int4 AoS", foot, p, blocks, 4);
+      for (int rep = 0; rep < 2; ++rep) k_global<4><<<blocks, 256>>>(rec, soa, tex, (unsigned)n - 1, p, sink, cycles);
+      report("LDG.256 / TEX alternating", foot, p, blocks, 4);
+      for (int rep = 0; rep < 2; ++rep) k_global<5><<<blocks, 256>>>(rec, soa, tex, (unsigned)n - 1, p, sink, cycles);
+      report("LDG.E.128 16-byte record", foot, p, blocks, 4);
     }
+    CK(cudaDestroyTextureObject(tex));
     CK(cudaFree(rec));
     CK(cudaFree(soa));
   }
