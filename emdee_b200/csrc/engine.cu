@@ -128,6 +128,7 @@ struct Engine::Impl {
   DBuf<int> bFirst, bAtom;
   DBuf<double> bMItem, bD, bState, bPartial, bScalars, shR0, shQ0, shS0;
   DBuf<unsigned char> freeMask;    // per atom: 1 = free atom (integrated by k_boost / k_displace), 0 = body member
+  DBuf<unsigned char> ownedFree;   // several GPUs: free atoms this rank owns (refreshed after every distributed rebuild)
   double* h_bscalars = nullptr;    // pinned, 16 doubles
   bool frames_valid = false;
   // bonded terms (engine_bonded.cuh): per-atom CSR of (term, role) references
@@ -301,7 +302,7 @@ Engine::~Engine() {
   s.terms.release(); s.termFirst.release(); s.termRef.release();
   s.ewN.release(); s.ewKType.release(); s.ewPrefac.release(); s.ewLambda.release(); s.ewSigma.release(); s.ewPartial.release();
   s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
-  s.bScalars.release(); s.shR0.release(); s.shQ0.release(); s.shS0.release(); s.freeMask.release();
+  s.bScalars.release(); s.shR0.release(); s.shQ0.release(); s.shS0.release(); s.freeMask.release(); s.ownedFree.release();
   if (s.h_bscalars) cudaFreeHost(s.h_bscalars);
   for (int k = 0; k < 2; ++k) { s.migList[k].release(); s.migSend[k].release(); s.migRecv[k].release(); }
   if (s.h_mi) cudaFreeHost(s.h_mi);
@@ -890,6 +891,11 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     }
     if (s.world > 1) {
       build_halo_lists(s);
+      if (s.nbodies != 0) {   // free atoms this rank integrates (body state is replicated, see boost_all / move_all)
+        s.ownedFree.ensure(N);
+        k_mask_and<<<nblocks(N), TPB, 0, s.stream>>>(N, s.owned.p, s.freeMask.p, s.ownedFree.p);
+        stats_.launches += 1;
+      }
       s.owned_valid = true;
       s.all_known = false;
       s.halo_fresh = true;   // migrate() just made every needed position current
@@ -1137,30 +1143,47 @@ void Engine::update_body_frames(double Lbox) {
 
 void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool rotate, bool want_kinetic, KineticAll& ke) {
   Impl& s = *d_;
-  require_single_gpu_bodies(s, "boost");
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   const bool bodies = s.nbodies != 0;
-  if (translate && s.nitems < s.N) {   // free atoms
+  const bool dist = s.world > 1 && s.owned_valid;   // several GPUs: forces exist only for the atoms this rank owns
+  const bool have_free = translate && s.nitems < s.N;
+  if (have_free) {
+    const unsigned char* mask = !bodies ? (dist ? s.owned.p : nullptr) : (dist ? s.ownedFree.p : s.freeMask.p);
     const int grid = nblocks((s.N + APT - 1) / APT);
-    k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, bodies ? s.freeMask.p : nullptr, want_kinetic ? 1 : 0,
+    k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, mask, want_kinetic ? 1 : 0,
                                         s.partial.p, s.tickets.p + 1, s.scalars.p + 10);
     stats_.launches += 1;
+    if (dist && want_kinetic)
+      NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
   }
   if (bodies) {
-    k_body_boost<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), Fl, s.delta.p, CP, CF, translate ? 1 : 0, rotate ? 1 : 0,
-                                                           want_kinetic ? 1 : 0, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
-    stats_.launches += 1;
+    const BodyView v = body_view(s);
+    const int grid = nblocks(s.nbodies);
+    if (dist) {
+      // the body state is replicated: sum the owned members' forces and torques, all-reduce them (F and tau are
+      // contiguous, 6 doubles per body), then every rank applies the same kick to every body
+      k_body_boost<<<grid, TPB, 0, s.stream>>>(v, Fl, s.delta.p, s.owned.p, 1, CP, CF, 0, 0, 0, s.bPartial.p, s.tickets.p + 3,
+                                               s.bScalars.p);
+      NCCL_CHECK(nccl().AllReduce(v.Fb, v.Fb, 6 * (size_t)s.nbodies, ncclDouble, ncclSum, s.comm, s.stream));
+      k_body_boost<<<grid, TPB, 0, s.stream>>>(v, Fl, s.delta.p, nullptr, 2, CP, CF, translate ? 1 : 0, rotate ? 1 : 0,
+                                               want_kinetic ? 1 : 0, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
+      stats_.launches += 2;
+    } else {
+      k_body_boost<<<grid, TPB, 0, s.stream>>>(v, Fl, s.delta.p, nullptr, 0, CP, CF, translate ? 1 : 0, rotate ? 1 : 0,
+                                               want_kinetic ? 1 : 0, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
+      stats_.launches += 1;
+    }
   }
   if (!want_kinetic) {
     if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
     return;
   }
   double free3[3] = {0, 0, 0}, body6[6] = {0, 0, 0, 0, 0, 0};
-  if (translate && s.nitems < s.N)
+  if (have_free)
     CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   if (bodies) CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
-  if (translate && s.nitems < s.N)
+  if (have_free)
     for (int x = 0; x < 3; ++x) free3[x] = s.h_scalars[10 + x];
   if (bodies)
     for (int x = 0; x < 6; ++x) body6[x] = s.h_bscalars[x];
@@ -1172,21 +1195,25 @@ void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool ro
 
 void Engine::move_all(double CR, double CP, double dt, bool translate, bool rotate, int mode) {
   Impl& s = *d_;
-  require_single_gpu_bodies(s, "displace");
   const bool bodies = s.nbodies != 0;
+  const bool dist = s.world > 1 && s.owned_valid;
   if (translate && s.nitems < s.N) {
-    // fused rebuild criterion only when every atom is free (body members move in k_body_move below)
-    k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p,
-                                                                      bodies ? s.freeMask.p : nullptr, s.R0.p, nullptr,
+    // the fused rebuild criterion is not used here: body members move in k_body_move below
+    const unsigned char* mask = !bodies ? (dist ? s.owned.p : nullptr) : (dist ? s.ownedFree.p : s.freeMask.p);
+    k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, mask, s.R0.p, nullptr,
                                                                       s.tickets.p + 2, s.scalars.p + 8);
     stats_.launches += 1;
   }
-  if (bodies) {
+  if (bodies) {   // several GPUs: every rank moves every body (replicated state), so member coordinates stay current everywhere
     k_body_move<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.R.p, s.delta.p, CR, CP, dt, translate ? 1 : 0,
                                                           rotate ? 1 : 0, mode);
     stats_.launches += 1;
   }
   s.check_cached = false;   // compute_forces evaluates the rebuild criterion on the new coordinates
+  if (dist) {
+    s.halo_fresh = false;
+    s.all_known = false;    // free atoms: only owned + halo positions are current on this rank
+  }
   if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
 }
 

@@ -532,7 +532,12 @@ __global__ void __launch_bounds__(TPB) k_body_frame(BodyView v, double* __restri
 
 // force_and_torque + boost of the centre-of-mass and quaternion momenta (+ the body part of kinetic_energies).
 // out[0..2] = sum 1/M pcm^2 per dimension, out[3..5] = sum I omega^2 per principal axis.
+// Several GPUs: body state is replicated on every rank, but a rank only holds the forces of the atoms it owns. So the
+// kernel runs in two phases around an all-reduce of (F, tau): phase 1 sums the members this rank owns, phase 2 kicks
+// every body with the reduced sums -- identical arithmetic on identical inputs, so the replicas stay bit-identical.
+// phase 0 (one GPU) does both at once.
 __global__ void __launch_bounds__(TPB) k_body_boost(BodyView v, const double* __restrict__ F, const double* __restrict__ delta,
+                                                    const unsigned char* __restrict__ owned, int phase,
                                                     double CP, double CF, int translate, int rotate, int want_ke,
                                                     double* __restrict__ partial, unsigned int* __restrict__ ticket,
                                                     double* __restrict__ out) {
@@ -540,46 +545,66 @@ __global__ void __launch_bounds__(TPB) k_body_boost(BodyView v, const double* __
   double ke[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (b < v.nb) {
     double Fb[3] = {0.0, 0.0, 0.0}, tq[3] = {0.0, 0.0, 0.0};
-    for (int k = v.first[b]; k < v.first[b + 1]; ++k) {
-      const size_t a = (size_t)v.atom[k];
-      const double f[3] = {F[3 * a], F[3 * a + 1], F[3 * a + 2]};
-      const double dl[3] = {delta[3 * a], delta[3 * a + 1], delta[3 * a + 2]};
-      double c[3];
-      cross3(dl, f, c);
+    if (phase != 2) {
+      for (int k = v.first[b]; k < v.first[b + 1]; ++k) {
+        const size_t a = (size_t)v.atom[k];
+        if (owned != nullptr && !owned[a]) continue;
+        const double f[3] = {F[3 * a], F[3 * a + 1], F[3 * a + 2]};
+        const double dl[3] = {delta[3 * a], delta[3 * a + 1], delta[3 * a + 2]};
+        double c[3];
+        cross3(dl, f, c);
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          Fb[x] += f[x];
+          tq[x] += c[x];
+        }
+      }
 #pragma unroll
       for (int x = 0; x < 3; ++x) {
-        Fb[x] += f[x];
-        tq[x] += c[x];
+        v.Fb[(size_t)x * v.nb + b] = Fb[x];
+        v.tau[(size_t)x * v.nb + b] = tq[x];
+      }
+    } else {
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        Fb[x] = v.Fb[(size_t)x * v.nb + b];
+        tq[x] = v.tau[(size_t)x * v.nb + b];
       }
     }
-    const double invM = 1.0 / v.mass[b];
+    if (phase != 1) {
+      const double invM = 1.0 / v.mass[b];
 #pragma unroll
-    for (int x = 0; x < 3; ++x) {
-      v.Fb[(size_t)x * v.nb + b] = Fb[x];
-      v.tau[(size_t)x * v.nb + b] = tq[x];
-      double p = v.pcm[(size_t)x * v.nb + b];
-      if (translate) {
-        p = CP * p + CF * Fb[x];
-        v.pcm[(size_t)x * v.nb + b] = p;
+      for (int x = 0; x < 3; ++x) {
+        double p = v.pcm[(size_t)x * v.nb + b];
+        if (translate) {
+          p = CP * p + CF * Fb[x];
+          v.pcm[(size_t)x * v.nb + b] = p;
+        }
+        ke[x] = invM * p * p;
       }
-      ke[x] = invM * p * p;
-    }
-    Rotor r;
-    load_rotor(v, b, r);
-    if (rotate) {
-      const double t3[3] = {2.0 * CF * tq[0], 2.0 * CF * tq[1], 2.0 * CF * tq[2]};
-      double t4[4];
-      vec_times_quat(t3, r.q, t4);
+      Rotor r;
+      load_rotor(v, b, r);
+      if (rotate) {
+        const double t3[3] = {2.0 * CF * tq[0], 2.0 * CF * tq[1], 2.0 * CF * tq[2]};
+        double t4[4];
+        vec_times_quat(t3, r.q, t4);
 #pragma unroll
-      for (int x = 0; x < 4; ++x) r.pi[x] = CP * r.pi[x] + t4[x];
-      rotor_omega_from_pi(r);
-      store_rotor(v, b, r);
-    }
+        for (int x = 0; x < 4; ++x) r.pi[x] = CP * r.pi[x] + t4[x];
+        rotor_omega_from_pi(r);
+        store_rotor(v, b, r);
+      }
 #pragma unroll
-    for (int x = 0; x < 3; ++x) ke[3 + x] = r.I[x] * r.w[x] * r.w[x];
+      for (int x = 0; x < 3; ++x) ke[3 + x] = r.I[x] * r.w[x] * r.w[x];
+    }
   }
-  if (!want_ke) return;
+  if (!want_ke || phase == 1) return;
   reduce_and_finish<6>(ke, partial, ticket, out);
+}
+
+__global__ void __launch_bounds__(TPB) k_mask_and(int N, const unsigned char* __restrict__ a, const unsigned char* __restrict__ b,
+                                                  unsigned char* __restrict__ o) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) o[i] = (unsigned char)(a[i] && b[i]);
 }
 
 // move: centre of mass drift + free rotation + member coordinates R = rcm + delta (only when rotating, like the reference)
