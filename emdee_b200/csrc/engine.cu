@@ -96,6 +96,12 @@ struct Engine::Impl {
   DBuf<unsigned int> duoNbr;
   DBuf<int> duoCount;
 
+  // texture path (EMDEE_TEX, opt-in experiment): texture object over `pos`
+  int tex_mode = 0;
+  cudaTextureObject_t posTex = 0;
+  const double4* posTexBase = nullptr;
+  size_t posTexCount = 0;
+
   // brick path (single-type systems): per-brick descriptors and the 16-bit brick-local list
   bool use_bricks = false;
   BrickGrid bgrid{0, 0, 0, 0, 0};
@@ -305,6 +311,7 @@ Engine::~Engine() {
   s.bScalars.release(); s.shR0.release(); s.shQ0.release(); s.shS0.release(); s.freeMask.release(); s.ownedFree.release();
   if (s.h_bscalars) cudaFreeHost(s.h_bscalars);
   for (int k = 0; k < 2; ++k) { s.migList[k].release(); s.migSend[k].release(); s.migRecv[k].release(); }
+  if (s.posTex) cudaDestroyTextureObject(s.posTex);
   if (s.h_mi) cudaFreeHost(s.h_mi);
   if (s.comm) nccl().CommDestroy(s.comm);
   s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release(); s.tickets.release();
@@ -992,6 +999,34 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       launch_force_rows<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
     else
       launch_force_rows<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, g, pitch, rows, compute, smem_dyn, s.stream);
+  } else if (s.nt == 1 && lj_plain && std::getenv("EMDEE_TEX") != nullptr) {
+    // opt-in experiment (see k_pair_forces_tex): position gathers through the texture front-end of L1TEX
+    s.tex_mode = std::atoi(std::getenv("EMDEE_TEX")) == 2 ? 2 : 1;
+    if (s.posTex == 0 || s.posTexBase != s.pos.p || s.posTexCount != s.pos.n) {
+      if (s.posTex) CUDA_CHECK(cudaDestroyTextureObject(s.posTex));
+      cudaResourceDesc rd;
+      std::memset(&rd, 0, sizeof(rd));
+      rd.resType = cudaResourceTypeLinear;
+      rd.res.linear.devPtr = s.pos.p;
+      rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+      rd.res.linear.sizeInBytes = s.pos.n * sizeof(double4);
+      cudaTextureDesc td;
+      std::memset(&td, 0, sizeof(td));
+      td.readMode = cudaReadModeElementType;
+      CUDA_CHECK(cudaCreateTextureObject(&s.posTex, &rd, &td, nullptr));
+      s.posTexBase = s.pos.p;
+      s.posTexCount = s.pos.n;
+    }
+    const int tgrid = nblocks(a.Next, 512);
+    s.partial.ensure((size_t)tgrid * 5);
+    a.partial = s.partial.p;
+    if (s.tex_mode == 1) {
+      if (compute) k_pair_forces_tex<true, 1, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
+      else k_pair_forces_tex<false, 1, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
+    } else {
+      if (compute) k_pair_forces_tex<true, 2, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
+      else k_pair_forces_tex<false, 2, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
+    }
   } else if (s.nt == 1 && lj_plain && compute && std::getenv("EMDEE_FORCE_TUNE") != nullptr) {
     // tuning hook (bench experiments only): EMDEE_FORCE_TUNE="<variant>"
     const int v = std::atoi(std::getenv("EMDEE_FORCE_TUNE"));

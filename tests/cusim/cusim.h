@@ -61,6 +61,18 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDe
 enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+// texture objects over linear memory: the "object" is the base pointer
+typedef unsigned long long cudaTextureObject_t;
+enum cudaResourceType { cudaResourceTypeLinear = 2 };
+enum cudaTextureReadMode { cudaReadModeElementType = 0 };
+struct cudaChannelFormatDesc { int x, y, z, w, f; };
+template <class T>
+inline cudaChannelFormatDesc cudaCreateChannelDesc() { return cudaChannelFormatDesc{32, 32, 32, 32, 0}; }
+struct cudaResourceDesc {
+  cudaResourceType resType;
+  struct { struct { void* devPtr; cudaChannelFormatDesc desc; size_t sizeInBytes; } linear; } res;
+};
+struct cudaTextureDesc { cudaTextureReadMode readMode; };
 
 inline const char* cudaGetErrorString(cudaError_t) { return "cusim error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -396,6 +408,19 @@ inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline int cudaCreateTextureObject(cudaTextureObject_t* t, const cudaResourceDesc* r, const cudaTextureDesc*, const void*) {
+  *t = reinterpret_cast<cudaTextureObject_t>(r->res.linear.devPtr);
+  return 0;
+}
+inline int cudaDestroyTextureObject(cudaTextureObject_t) { return 0; }
+template <class T>
+inline T tex1Dfetch(cudaTextureObject_t t, int i) { return reinterpret_cast<const T*>(t)[i]; }
+inline double __hiloint2double(int hi, int lo) {
+  const unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+  double d;
+  std::memcpy(&d, &u, 8);
+  return d;
+}
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 inline void sincospi(double x, double* s, double* c) { sincos(3.14159265358979323846 * x, s, c); }
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }

@@ -56,3 +56,21 @@ def test_cluster2_path(monkeypatch):
     entry of the duo's union row (k_merge_duos + k_transpose_rows + k_pair_forces_cluster2)."""
     monkeypatch.setenv("EMDEE_CLUSTER2", "1")
     _all_model_families()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_texture_path(monkeypatch, mode):
+    """EMDEE_TEX=1|2: plain single-type LJ gathers its neighbor positions through the texture front-end of L1TEX
+    (k_pair_forces_tex; mode 2 alternates with LDG.E.256). Only the plain-LJ instantiation exists; every other model
+    falls through to the default kernels, so the whole family list must still pass."""
+    monkeypatch.setenv("EMDEE_TEX", str(mode))
+    _all_model_families()
+    # virial-only mode goes through the COMPUTE=false instantiation
+    sp, so = both(lambda lib: cm.lj_sample_system(lib, _lj)[0])
+    for s in (sp, so):
+        s.md.Options.Compute = False
+        s.upload("coordinates", s.download("coordinates") + 0.01)
+        s.compute_forces()
+    assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-12
+    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
+    sp.finalize(), so.finalize()

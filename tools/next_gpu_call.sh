@@ -4,7 +4,7 @@
 # 1. gather-cost microbenchmark (decides between the layouts discussed in DESIGN.md section 5)
 # 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS, EMDEE_CLUSTER2), of the box-rescale scenario and of the
 #    kernels written after the last GPU session (rigid bodies, verlet_step, bonded, Ewald, memory_address, sharing)
-# 3. LJ-1M bench: default path vs EMDEE_ROWS=8/16/32 vs EMDEE_CLUSTER2=1
+# 3. LJ-1M bench: default path vs EMDEE_ROWS=8/16/32 vs EMDEE_CLUSTER2=1 vs EMDEE_TEX=1/2 (texture-pipe gathers)
 set -u
 mkdir -p gpurun_out
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lsu_probe tools/lsu_probe.cu && timeout 120 /tmp/lsu_probe > gpurun_out/lsu_probe.txt 2>&1
@@ -15,6 +15,9 @@ for g in 8 16 32; do
   EMDEE_ROWS=$g timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_rows$g.json 2> gpurun_out/bench_rows$g.err
 done
 EMDEE_CLUSTER2=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_cluster2.json 2> gpurun_out/bench_cluster2.err
+for m in 1 2; do
+  EMDEE_TEX=$m timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_tex$m.json 2> gpurun_out/bench_tex$m.err
+done
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/bench_*.json")):
