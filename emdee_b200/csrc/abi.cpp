@@ -16,6 +16,7 @@
 #include <initializer_list>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/emdee.h"
@@ -381,18 +382,21 @@ void setup_bodies(System& me, const int* bodies) {
     return;
   }
   // ids that occur more than once become bodies, numbered by first appearance
-  std::vector<int> ids, count, firstAtom, which(N, -1);
+  // (the reference searches its list of ids linearly for every atom, O(N x bodies); a hash map gives the same numbering)
+  std::vector<int> ids, count, which(N, -1);
+  std::unordered_map<int, int> slotOf;
+  slotOf.reserve((size_t)N);
   for (int i = 0; i < N; ++i) {
     if (bodies[i] <= 0) continue;
-    int k = -1;
-    for (size_t q = 0; q < ids.size(); ++q)
-      if (ids[q] == bodies[i]) { k = (int)q; break; }
-    if (k < 0) {
+    auto it = slotOf.find(bodies[i]);
+    int k;
+    if (it == slotOf.end()) {
+      k = (int)ids.size();
+      slotOf.emplace(bodies[i], k);
       ids.push_back(bodies[i]);
       count.push_back(1);
-      firstAtom.push_back(i);
-      k = (int)ids.size() - 1;
     } else {
+      k = it->second;
       count[k] += 1;
     }
     which[i] = k;
