@@ -1285,15 +1285,17 @@ void Engine::add_bonded(int layer0, double Lbox, bool bonded, bool kspace, Bonde
   Impl& s = *d_;
   out = BondedScalars();
   if (s.nterms == 0) return;
-  if (s.world > 1) fatal("force computation", "bonded terms are not available on several GPUs yet");
+  const bool dist = s.world > 1 && s.owned_valid;   // partners of an owned atom lie inside the halo (bonds are shorter than the cutoff)
   const double* delta = (s.has_delta && s.nbodies != 0) ? s.delta.p : nullptr;
   BondedEwald ks;
   ks.on = (kspace && s.ewald_on) ? 1 : 0;
   ks.alpha = s.ew_alpha; ks.beta = s.ew_beta; ks.q = s.q.p; ks.type = s.type.p; ks.tab = s.tabs[layer0].p; ks.nt = s.nt;
   if (!bonded && !ks.on) return;
   k_bonded<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, s.termFirst.p, s.termRef.p, s.terms.p, s.R.p, Lbox, bonded ? 1 : 0, ks,
-                                               s.F.p + (size_t)layer0 * 3 * s.N, delta, s.bPartial.p, s.tickets.p + 3, s.bScalars.p);
+                                               dist ? s.owned.p : nullptr, s.F.p + (size_t)layer0 * 3 * s.N, delta, s.bPartial.p,
+                                               s.tickets.p + 3, s.bScalars.p);
   stats_.launches += 1;
+  if (dist) NCCL_CHECK(nccl().AllReduce(s.bScalars.p, s.bScalars.p, 6, ncclDouble, ncclSum, s.comm, s.stream));
   CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
   out.Ebond = s.h_bscalars[0];
@@ -1331,20 +1333,30 @@ void Engine::add_ewald(int layer0, double Lbox, double& Elong, double& Wbody) {
   Impl& s = *d_;
   Elong = Wbody = 0.0;
   if (!s.ewald_on || s.ew_nvecs == 0) return;
-  if (s.world > 1) fatal("force computation", "the reciprocal-space Ewald sum is not available on several GPUs yet");
+  const bool dist = s.world > 1 && s.owned_valid;
   EwaldView v;
   v.nvecs = s.ew_nvecs; v.ntk = s.ew_ntk; v.N = s.N; v.n = s.ewN.p; v.prefac = s.ewPrefac.p; v.ktype = s.ewKType.p;
-  v.q = s.q.p; v.R = s.R.p; v.sigma = s.ewSigma.p;
+  v.q = s.q.p; v.owned = dist ? s.owned.p : nullptr; v.R = s.R.p; v.sigma = s.ewSigma.p;
   const double* lambda = s.ewLambda.p + (size_t)layer0 * s.ew_ntk * s.ew_ntk;
   const double* delta = (s.has_delta && s.nbodies != 0) ? s.delta.p : nullptr;
-  k_ewald_structure<<<s.ew_nvecs, TPB, 0, s.stream>>>(v, Lbox, lambda, s.ewPartial.p, s.tickets.p + 3, s.bScalars.p + 12);
+  if (dist) {
+    // every rank sums the structure factors of the atoms it owns; one all-reduce makes them global, after which sigma
+    // and the energy are the same numbers on every rank and each rank finishes the forces of its own atoms
+    k_ewald_structure<<<s.ew_nvecs, TPB, 0, s.stream>>>(v, Lbox, lambda, 1, s.ewPartial.p, s.tickets.p + 3, s.bScalars.p + 12);
+    NCCL_CHECK(nccl().AllReduce(s.ewSigma.p, s.ewSigma.p, 2 * (size_t)s.ew_ntk * s.ew_nvecs, ncclDouble, ncclSum, s.comm, s.stream));
+    k_ewald_sigma<<<nblocks(s.ew_nvecs), TPB, 0, s.stream>>>(v, lambda, s.ewPartial.p, s.tickets.p + 3, s.bScalars.p + 12);
+    stats_.launches += 1;
+  } else {
+    k_ewald_structure<<<s.ew_nvecs, TPB, 0, s.stream>>>(v, Lbox, lambda, 0, s.ewPartial.p, s.tickets.p + 3, s.bScalars.p + 12);
+  }
   k_ewald_forces<<<nblocks(s.N), TPB, 0, s.stream>>>(v, Lbox, s.F.p + (size_t)layer0 * 3 * s.N, delta, s.ewPartial.p,
-                                                     s.tickets.p + 3, s.bScalars.p + 13);
+                                                     s.tickets.p + 3, s.bScalars.p + 14);
   stats_.launches += 2;
+  if (dist) NCCL_CHECK(nccl().AllReduce(s.bScalars.p + 14, s.bScalars.p + 14, 1, ncclDouble, ncclSum, s.comm, s.stream));
   CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars + 12, s.bScalars.p + 12, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
   Elong = s.h_bscalars[12];
-  Wbody = s.h_bscalars[13];
+  Wbody = s.h_bscalars[14];
 }
 
 // ---- EmDee_memory_address / EmDee_share_phase_space ---------------------------------------------------------------

@@ -35,12 +35,13 @@ __device__ __forceinline__ void ewald_discount(const BondedEwald& k, int a, int 
 //      [5] Coulomb energy taken back out of the bonded pairs (k-space layers only)
 __global__ void __launch_bounds__(TPB) k_bonded(int N, const int* __restrict__ first, const int* __restrict__ ref,
                                                 const BondedTerm* __restrict__ terms, const double* __restrict__ R, double L,
-                                                int bonded, BondedEwald ks, double* __restrict__ F,
+                                                int bonded, BondedEwald ks, const unsigned char* __restrict__ owned,
+                                                double* __restrict__ F,
                                                 const double* __restrict__ delta, double* __restrict__ partial,
                                                 unsigned int* __restrict__ ticket, double* __restrict__ out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (a < N && first[a + 1] > first[a]) {
+  if (a < N && first[a + 1] > first[a] && (owned == nullptr || owned[a])) {   // several GPUs: each rank finishes the atoms it owns
     double f[3] = {0.0, 0.0, 0.0};
     for (int t = first[a]; t < first[a + 1]; ++t) {
       const int role = ref[t] & 3;

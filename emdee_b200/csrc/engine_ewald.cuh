@@ -20,6 +20,7 @@ struct EwaldView {
   const double* prefac;    // (4 pi / V) exp(-k^2 / 4 alpha^2) / k^2
   const int* ktype;        // per atom: index among the charged types, or -1
   const double* q;         // per atom charge
+  const unsigned char* owned;   // several GPUs: atoms this rank sums / finishes (nullptr on one GPU)
   const double* R;
   double* sigma;           // 2 * ntk per wave vector: (re, im) per type
 };
@@ -30,8 +31,10 @@ __device__ __forceinline__ double turn_fraction(const int* __restrict__ n, const
   return f - rint(f);
 }
 
-// one block per wave vector; out[0] accumulates sum_k prefac(k) sum_t Re(S conj(sigma))
-__global__ void __launch_bounds__(TPB) k_ewald_structure(EwaldView v, double L, const double* __restrict__ lambda,
+// one block per wave vector; out[0] accumulates sum_k prefac(k) sum_t Re(S conj(sigma)).
+// raw_only (several GPUs): store this rank's partial S(k,t) in the sigma buffer and stop; after the all-reduce of that
+// buffer, k_ewald_sigma turns it into sigma and adds up the energy.
+__global__ void __launch_bounds__(TPB) k_ewald_structure(EwaldView v, double L, const double* __restrict__ lambda, int raw_only,
                                                          double* __restrict__ partial, unsigned int* __restrict__ ticket,
                                                          double* __restrict__ out) {
   __shared__ double red[TPB / 32][2 * EWALD_MAX_TYPES];
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(TPB) k_ewald_structure(EwaldView v, double L, 
   for (int t = 0; t < 2 * EWALD_MAX_TYPES; ++t) S[t] = 0.0;
   for (int a = threadIdx.x; a < v.N; a += blockDim.x) {
     const int t = v.ktype[a];
-    if (t < 0) continue;
+    if (t < 0 || (v.owned != nullptr && !v.owned[a])) continue;
     double s, c;
     sincospi(2.0 * turn_fraction(nk, v.R, (size_t)a, L), &s, &c);
     const double qa = v.q[a];
@@ -68,6 +71,10 @@ __global__ void __launch_bounds__(TPB) k_ewald_structure(EwaldView v, double L, 
       T[t] = 0.0;
       for (int w = 0; w < TPB / 32; ++w) T[t] += red[w][t];
     }
+    if (raw_only) {
+      for (int t = 0; t < 2 * v.ntk; ++t) v.sigma[(size_t)kv * v.ntk * 2 + t] = T[t];
+      return;
+    }
     double e = 0.0;
     for (int t = 0; t < v.ntk; ++t) {
       double gr = 0.0, gi = 0.0;
@@ -81,7 +88,38 @@ __global__ void __launch_bounds__(TPB) k_ewald_structure(EwaldView v, double L, 
     }
     mine[0] = v.prefac[kv] * e;
   }
+  if (raw_only) return;
   grid_finish<1>(mine, partial, ticket, out, 1.0);
+}
+
+// several GPUs, after the all-reduce of the raw structure factors: one thread per wave vector forms sigma in place and
+// the vector's energy (identical on every rank)
+__global__ void __launch_bounds__(TPB) k_ewald_sigma(EwaldView v, const double* __restrict__ lambda, double* __restrict__ partial,
+                                                     unsigned int* __restrict__ ticket, double* __restrict__ out) {
+  const int kv = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[2] = {0.0, 0.0};
+  if (kv < v.nvecs) {
+    double T[2 * EWALD_MAX_TYPES];
+#pragma unroll
+    for (int t = 0; t < 2 * EWALD_MAX_TYPES; ++t) T[t] = t < 2 * v.ntk ? v.sigma[(size_t)kv * v.ntk * 2 + t] : 0.0;
+    double e = 0.0;
+    for (int t = 0; t < v.ntk; ++t) {
+      double gr = 0.0, gi = 0.0;
+#pragma unroll
+      for (int u = 0; u < EWALD_MAX_TYPES; ++u)
+        if (u < v.ntk) {
+          gr += T[2 * u] * lambda[u * v.ntk + t];
+          gi += T[2 * u + 1] * lambda[u * v.ntk + t];
+        }
+      v.sigma[((size_t)kv * v.ntk + t) * 2] = gr;
+      v.sigma[((size_t)kv * v.ntk + t) * 2 + 1] = gi;
+#pragma unroll
+      for (int u = 0; u < EWALD_MAX_TYPES; ++u)
+        if (u == t) e += T[2 * u] * gr + T[2 * u + 1] * gi;
+    }
+    acc[0] = v.prefac[kv] * e;
+  }
+  reduce_and_finish<2>(acc, partial, ticket, out);
 }
 
 // one thread per atom: F_a += sum_k 2 prefac(k) k (Re sigma Im(q e^{ikr}) - Re(q e^{ikr}) Im sigma); out[0] = -sum F.delta
@@ -90,7 +128,7 @@ __global__ void __launch_bounds__(TPB) k_ewald_forces(EwaldView v, double L, dou
                                                       unsigned int* __restrict__ ticket, double* __restrict__ out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[2] = {0.0, 0.0};
-  if (a < v.N && v.ktype[a] >= 0) {
+  if (a < v.N && v.ktype[a] >= 0 && (v.owned == nullptr || v.owned[a])) {
     const int t = v.ktype[a];
     const double qa = v.q[a], unit = 2.0 * 3.14159265358979324 / L;
     double f[3] = {0.0, 0.0, 0.0};

@@ -164,6 +164,79 @@ def main():
         sp.finalize()
     elif rank == 0:
         print(f"[mgpu] spce skipped: {world} ranks would need more than {nrep}^3 replicas", flush=True)
+    # ---- Ewald (coul_long + kspace_ewald) and bonded terms on the slab-decomposed path ---------------------------
+    import test_oracle_bonded as t_bonded
+    import test_oracle_ewald as t_ewald
+    ncell = {2: 6, 3: 8, 4: 10}.get(world)     # M = floor(2L/3.1) cell layers with L = 2*ncell: at least three per rank
+    if ncell is not None and os.environ.get("EMDEE_MGPU_SKIP_EWALD") != "1":
+        rng = np.random.default_rng(9)
+        g = 2 * ncell
+        Rsalt = (np.stack(np.meshgrid(np.arange(g), np.arange(g), np.arange(g), indexing="ij"), axis=-1).reshape(-1, 3) + 0.25
+                 + rng.normal(scale=0.06, size=(g ** 3, 3)))
+
+        def salt(lib, comm):
+            orig = cm.api.System.set_pair_model
+            state = {"done": not comm}
+
+            def patched(self, *a, **k):
+                if not state["done"]:
+                    edist.init_comm(self.lib, self)
+                    state["done"] = True
+                return orig(self, *a, **k)
+            cm.api.System.set_pair_model = patched
+            try:
+                return t_ewald.rock_salt(lib, ncell=ncell, R=Rsalt, accuracy=1e-4)[0]
+            finally:
+                cm.api.System.set_pair_model = orig
+        sp = salt(lib, True)
+        so = salt(orc, False) if rank == 0 else None
+        compare(f"ewald rock salt {g}^3 ions", sp, so, rank, ftol=1e-9, stol=1e-11)
+        for s in ([sp, so] if rank == 0 else [sp]):
+            s.random_momenta(0.05, True, 3)
+            for _ in range(4):
+                s.boost(1.0, 0.0, 0.01)
+                s.displace(1.0, 0.0, 0.02)
+                s.boost(1.0, 0.0, 0.01)
+        compare("ewald rock salt after 4 steps", sp, so, rank, ftol=1e-8, stol=1e-10)
+        sp.finalize()
+    if world == 2:
+        def water(lib, comm):
+            orig = cm.api.System.set_pair_model
+            state = {"done": not comm}
+
+            def patched(self, *a, **k):
+                if not state["done"]:
+                    edist.init_comm(self.lib, self)
+                    state["done"] = True
+                return orig(self, *a, **k)
+            cm.api.System.set_pair_model = patched
+            try:
+                return _flexible(lib)
+            finally:
+                cm.api.System.set_pair_model = orig
+
+        def _flexible(lib):
+            L = 18.0                      # M = floor(2L/5.8) = 6 cell layers: three per rank
+            rng = np.random.default_rng(3)
+            nmol = 125
+            grid = np.array([[i, j, k] for i in range(5) for j in range(5) for k in range(5)], dtype=float) * 3.5 + 0.7
+            mol = np.array([[0.0, 0.0, 0.0], [0.8, 0.58, 0.0], [-0.8, 0.58, 0.0]])
+            R = (grid[:, None, :] + mol[None, :, :]).reshape(-1, 3) + rng.normal(scale=0.05, size=(3 * nmol, 3))
+            return t_bonded.flexible_water(lib, R=R, L=L, nmol=nmol)[0]
+        sp = water(lib, True)
+        so = water(orc, False) if rank == 0 else None
+        compare("flexible water (bonds + angles), static", sp, so, rank)
+        if rank == 0:
+            assert abs(sp.md.Energy.Bond - so.md.Energy.Bond) <= 1e-12 * abs(so.md.Energy.Potential)
+            assert abs(sp.md.Energy.Angle - so.md.Energy.Angle) <= 1e-12 * abs(so.md.Energy.Potential)
+        for s in ([sp, so] if rank == 0 else [sp]):
+            s.random_momenta(0.0006, True, 13)
+            for _ in range(6):
+                s.boost(1.0, 0.0, 0.25)
+                s.displace(1.0, 0.0, 0.5)
+                s.boost(1.0, 0.0, 0.25)
+        compare("flexible water after 6 steps", sp, so, rank, ftol=1e-8, stol=1e-10)
+        sp.finalize()
     dist.barrier()
     if rank == 0:
         print("[mgpu] ALL OK", flush=True)
