@@ -146,21 +146,22 @@ def main():
         # owns are all-reduced per kick (Engine::boost_all), every rank moves every body
         c = cm.load_fixture("NIST_spce_sample")
         nsteps = int(os.environ.get("EMDEE_MGPU_BODY_STEPS", "6"))
-        for s in ([sp, so] if rank == 0 else [sp]):
+        for s in (([sp, so] if rank == 0 else [sp]) if nsteps > 0 else []):
             s.random_momenta(c["kB"] * c["Temp"], True, 4242)
             for step in range(nsteps):
                 s.md.Options.Compute = (step == nsteps - 1)
                 s.boost(1.0, 0.0, 0.5)
                 s.displace(1.0, 0.0, 1.0)
                 s.boost(1.0, 0.0, 0.5)
-        Rp, Pp = sp.download("coordinates"), sp.download("momenta")
-        if rank == 0:
+        Rp, Pp = (sp.download("coordinates"), sp.download("momenta")) if nsteps > 0 else (None, None)
+        if rank == 0 and nsteps > 0:
             assert np.abs(Rp - so.download("coordinates")).max() < 1e-9
             assert np.abs(Pp - so.download("momenta")).max() <= 1e-8 * np.abs(Pp).max()
             assert sp.md.Builds == so.md.Builds
             for a, b, nm in [(sp.md.Kinetic.Total, so.md.Kinetic.Total, "K"), (sp.md.Kinetic.Rotational, so.md.Kinetic.Rotational, "Krot")]:
                 assert abs(a - b) <= 1e-9 * abs(b), f"spce dynamics: {nm} {a!r} vs {b!r}"
-        compare(f"spce {nrep}^3 replicas after {nsteps} rigid-body NVE steps", sp, so, rank, ftol=1e-8, stol=1e-9)
+        if nsteps > 0:
+            compare(f"spce {nrep}^3 replicas after {nsteps} rigid-body NVE steps", sp, so, rank, ftol=1e-8, stol=1e-9)
         sp.finalize()
     elif rank == 0:
         print(f"[mgpu] spce skipped: {world} ranks would need more than {nrep}^3 replicas", flush=True)
