@@ -25,7 +25,7 @@ def test_slab_decomposition_matches_oracle(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(cm.ROOT, "tests", "mgpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "[mgpu] ALL OK" in r.stdout
