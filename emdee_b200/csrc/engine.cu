@@ -96,6 +96,11 @@ struct Engine::Impl {
   DBuf<unsigned int> duoNbr;
   DBuf<int> duoCount;
 
+  // typed path (EMDEE_TYPED, opt-in experiment): compact per-layer tables, built on first use
+  std::vector<DBuf<TypedEntry>> ttabs;
+  std::vector<int> typedState;     // per layer: 0 = not examined, 1 = eligible, -1 = not eligible
+  std::vector<int> typedPM;
+
   // texture path (EMDEE_TEX, opt-in experiment): texture object over `pos`
   int tex_mode = 0;
   cudaTextureObject_t posTex = 0;
@@ -267,6 +272,9 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   CUDA_CHECK(cudaMemset(s.interact.p, 0, (size_t)ntypes * ntypes));
   s.layers.resize(nlayers);
   s.tabs.resize(nlayers);
+  s.ttabs.resize(nlayers);
+  s.typedState.assign(nlayers, 0);
+  s.typedPM.assign(nlayers, 0);
   s.flags.ensure(4);
   s.scalars.ensure(16);
   s.counter.ensure(2);
@@ -297,6 +305,7 @@ Engine::~Engine() {
   s.delta.release(); s.type.release(); s.body.release(); s.exFirst.release(); s.exItem.release();
   s.interact.release();
   for (auto& t : s.tabs) t.release();
+  for (auto& t : s.ttabs) t.release();
   s.Rs.release(); s.sRs.release(); s.sPosF.release(); s.atomCell.release(); s.atomFloor.release();
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
@@ -528,6 +537,7 @@ void Engine::set_interact(const std::vector<char>& interact) {
 void Engine::set_layer(int layer0, const LayerTable& t) {
   Impl& s = *d_;
   s.layers[layer0] = t;
+  s.typedState[layer0] = 0;
   s.tabs[layer0].ensure(t.pair.size());
   CUDA_CHECK(cudaMemcpy(s.tabs[layer0].p, t.pair.data(), t.pair.size() * sizeof(PairEntry), cudaMemcpyHostToDevice));
 }
@@ -644,6 +654,64 @@ void configure_brick_kernels() {
   allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, false>, fb);
   allow_big_smem(k_pair_forces_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true, true>, fb);
   allow_big_smem(k_pair_forces_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true, false>, fb);
+}
+
+// ---- typed path (EMDEE_TYPED=1): eligibility + compact table of one layer ----------------------------------------
+// eligible: every pair entry is pair_none or pair_lj_cut, all LJ entries carry the same modifier (none or shifted_force)
+bool build_typed_table(const LayerTable& lt, std::vector<TypedEntry>& out, int& pm) {
+  pm = -1;
+  for (const PairEntry& pe : lt.pair) {
+    if (pe.model.kind == nb::K_PAIR_NONE) continue;
+    if (pe.model.kind != nb::K_PAIR_LJ_CUT) return false;
+    if (pe.model.modifier != nb::M_NONE && pe.model.modifier != nb::M_SHIFTED_FORCE) return false;
+    if (pm >= 0 && pm != pe.model.modifier) return false;
+    pm = pe.model.modifier;
+  }
+  if (pm < 0) pm = nb::M_NONE;
+  out.clear();
+  for (const PairEntry& pe : lt.pair) {
+    TypedEntry te;
+    const bool lj = pe.model.kind == nb::K_PAIR_LJ_CUT;
+    te.a = lj ? pe.model.a : 0.0;        // pair_none == Lennard-Jones of zero strength
+    te.b = lj ? pe.model.b : 0.0;
+    te.c = lj ? pe.model.c : 1.0;
+    te.eshift = lj ? pe.model.eshift : 0.0;
+    te.fshift = lj ? pe.model.fshift : 0.0;
+    te.kCoul = pe.kCoul;
+    te.coulomb = pe.coulomb;
+    te.pad = 0;
+    out.push_back(te);
+  }
+  return true;
+}
+
+template <int PM, int CK>
+void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
+  const int grid = nblocks(a.Next, 256);
+  partial.ensure((size_t)grid * 5);
+  a.partial = partial.p;
+  const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
+  if (a.nt == 2) {
+    if (compute) k_pair_forces_typed<PM, CK, true, true><<<grid, 256, 0, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, true><<<grid, 256, 0, st>>>(a, ttab);
+  } else {
+    if (compute) k_pair_forces_typed<PM, CK, true, false><<<grid, 256, smem, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, false><<<grid, 256, smem, st>>>(a, ttab);
+  }
+}
+
+template <int PM>
+bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
+  using namespace nb;
+  switch (ck) {
+    case K_COUL_NONE: launch_typed<PM, K_COUL_NONE>(a, partial, ttab, compute, st); return true;
+    case K_COUL_CUT: launch_typed<PM, K_COUL_CUT>(a, partial, ttab, compute, st); return true;
+    case K_COUL_SF: launch_typed<PM, K_COUL_SF>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED: launch_typed<PM, K_COUL_DAMPED>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SMOOTHED>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED_SQUARE_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SQUARE_SMOOTHED>(a, partial, ttab, compute, st); return true;
+    default: return false;
+  }
 }
 
 // FP32 pre-test band (see k_build_list). Positions are ghost-shifted scaled coordinates, |p| <= pmax.
@@ -999,6 +1067,27 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       launch_force_rows<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
     else
       launch_force_rows<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, g, pitch, rows, compute, smem_dyn, s.stream);
+  } else if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && std::getenv("EMDEE_TYPED") != nullptr &&
+             [&] {   // opt-in experiment (see k_pair_forces_typed): compile-time kinds for LJ/none + cut-family Coulomb layers
+               if (s.typedState[layer0] == 0) {
+                 std::vector<TypedEntry> tt;
+                 int pmod = 0;
+                 if (build_typed_table(lt, tt, pmod)) {
+                   s.ttabs[layer0].ensure(tt.size());
+                   CUDA_CHECK(cudaMemcpyAsync(s.ttabs[layer0].p, tt.data(), tt.size() * sizeof(TypedEntry), cudaMemcpyHostToDevice, s.stream));
+                   CUDA_CHECK(cudaStreamSynchronize(s.stream));   // `tt` is a local
+                   s.typedState[layer0] = 1;
+                   s.typedPM[layer0] = pmod;
+                   if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee] typed path: layer %d eligible (modifier %d, coulomb kind %d, %d types)\n", layer0, pmod, ck, s.nt);
+                 } else {
+                   s.typedState[layer0] = -1;
+                 }
+               }
+               if (s.typedState[layer0] != 1) return false;
+               return s.typedPM[layer0] == M_NONE ? launch_typed_ck<M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream)
+                                                  : launch_typed_ck<M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream);
+             }()) {
+    // launched inside the condition: an ineligible layer falls through to the generic kernel below
   } else if (s.nt == 1 && lj_plain && std::getenv("EMDEE_TEX") != nullptr) {
     // opt-in experiment (see k_pair_forces_tex): position gathers through the texture front-end of L1TEX
     s.tex_mode = std::atoi(std::getenv("EMDEE_TEX")) == 2 ? 2 : 1;

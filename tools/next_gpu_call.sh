@@ -30,4 +30,6 @@ for f in sorted(glob.glob("gpurun_out/bench_*.json")):
 PY
 timeout 600 python bench.py --workload spce --steps 20 > gpurun_out/bench_spce.json 2> gpurun_out/bench_spce.err
 tail -c 1500 gpurun_out/bench_spce.json
+EMDEE_TYPED=1 timeout 600 python bench.py --workload spce --steps 20 > gpurun_out/bench_spce_typed.json 2> gpurun_out/bench_spce_typed.err
+tail -c 1500 gpurun_out/bench_spce_typed.json
 cat gpurun_out/lsu_probe.txt
