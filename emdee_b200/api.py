@@ -210,6 +210,15 @@ class System:
     def ignore_pair(self, i: int, j: int):
         self.lib.EmDee_ignore_pair(self.md, int(i), int(j))
 
+    def add_bond(self, i: int, j: int, model):
+        self.lib.EmDee_add_bond(self.md, int(i), int(j), model)
+
+    def add_angle(self, i: int, j: int, k: int, model):
+        self.lib.EmDee_add_angle(self.md, int(i), int(j), int(k), model)
+
+    def add_dihedral(self, i: int, j: int, k: int, l: int, model):
+        self.lib.EmDee_add_dihedral(self.md, int(i), int(j), int(k), int(l), model)
+
     def switch_model_layer(self, layer: int):
         self.lib.EmDee_switch_model_layer(C.byref(self.md), int(layer))
 
