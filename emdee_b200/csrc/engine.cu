@@ -29,6 +29,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <dlfcn.h>
@@ -95,6 +96,12 @@ struct Engine::Impl {
   DBuf<int> rowsNbr;
   DBuf<unsigned int> duoNbr;
   DBuf<int> duoCount;
+
+  // tile schedule (EMDEE_TILESCHED, opt-in experiment): brick-ordered permutation of the list tiles
+  bool use_sched = false;
+  int ntiles = 0;
+  DBuf<unsigned int> schedKeys, schedKeysOut;
+  DBuf<int> schedTiles, tileOrder;
 
   // typed path (EMDEE_TYPED, opt-in experiment): compact per-layer tables, built on first use
   std::vector<DBuf<TypedEntry>> ttabs;
@@ -306,6 +313,7 @@ Engine::~Engine() {
   s.interact.release();
   for (auto& t : s.tabs) t.release();
   for (auto& t : s.ttabs) t.release();
+  s.schedKeys.release(); s.schedKeysOut.release(); s.schedTiles.release(); s.tileOrder.release();
   s.Rs.release(); s.sRs.release(); s.sPosF.release(); s.atomCell.release(); s.atomFloor.release();
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
@@ -964,6 +972,25 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
                                                                            s.rowsNbr.p);
       stats_.launches += 1;
     }
+    // ---- tile schedule: brick-ordered permutation of the tiles (see k_pair_forces_sched) ----------------------------
+    s.use_sched = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.rows_group == 0 && s.nt == 1 &&
+                  std::getenv("EMDEE_TILESCHED") != nullptr;
+    if (s.use_sched) {
+      s.ntiles = (int)ntiles;
+      s.schedKeys.ensure(ntiles, 1.1);
+      s.schedKeysOut.ensure(ntiles, 1.1);
+      s.schedTiles.ensure(ntiles, 1.1);
+      s.tileOrder.ensure(ntiles, 1.1);
+      k_tile_keys<<<nblocks(ntiles), TPB, 0, s.stream>>>((int)ntiles, Next, s.grid.Mx, s.sCell.p, s.schedKeys.p, s.schedTiles.p);
+      size_t sortBytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, s.schedKeys.p, s.schedKeysOut.p, s.schedTiles.p, s.tileOrder.p, (int)ntiles, 0, 32, s.stream);
+      if (sortBytes > s.scanTmpBytes) {
+        s.scanTmp.ensure(sortBytes);
+        s.scanTmpBytes = sortBytes;
+      }
+      cub::DeviceRadixSort::SortPairs(s.scanTmp.p, sortBytes, s.schedKeys.p, s.schedKeysOut.p, s.schedTiles.p, s.tileOrder.p, (int)ntiles, 0, 32, s.stream);
+      stats_.launches += 2;
+    }
     if (s.world > 1) {
       build_halo_lists(s);
       if (s.nbodies != 0) {   // free atoms this rank integrates (body state is replicated, see boost_all / move_all)
@@ -1088,6 +1115,12 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
                                                   : launch_typed_ck<M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream);
              }()) {
     // launched inside the condition: an ineligible layer falls through to the generic kernel below
+  } else if (s.nt == 1 && lj_plain && s.use_sched) {
+    const int sgrid = nblocks((long long)s.ntiles * TILE, 512);
+    s.partial.ensure((size_t)sgrid * 5);
+    a.partial = s.partial.p;
+    if (compute) k_pair_forces_sched<true, 6, 512, 2><<<sgrid, 512, 0, s.stream>>>(a, s.ntiles, s.tileOrder.p);
+    else k_pair_forces_sched<false, 6, 512, 2><<<sgrid, 512, 0, s.stream>>>(a, s.ntiles, s.tileOrder.p);
   } else if (s.nt == 1 && lj_plain && std::getenv("EMDEE_TEX") != nullptr) {
     // opt-in experiment (see k_pair_forces_tex): position gathers through the texture front-end of L1TEX
     s.tex_mode = std::atoi(std::getenv("EMDEE_TEX")) == 2 ? 2 : 1;

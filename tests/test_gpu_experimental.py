@@ -117,3 +117,19 @@ def test_typed_path(monkeypatch):
     sp, so = both(lambda lib: _two_type_system(lib, COUL_VARIANTS["coul_sf"]))   # softcore present: generic kernel
     assert_state_parity(sp, so)
     sp.finalize(), so.finalize()
+
+
+def test_tile_schedule_path(monkeypatch):
+    """EMDEE_TILESCHED=1: plain single-type LJ; warps take the list tiles in a brick-ordered permutation built at every
+    rebuild (k_tile_keys + radix sort, k_pair_forces_sched). Results are per-thread identical to the default path; the
+    reductions run over a different block order, so totals agree to rounding."""
+    monkeypatch.setenv("EMDEE_TILESCHED", "1")
+    _all_model_families()
+    sp, so = both(lambda lib: cm.lj_sample_system(lib, _lj)[0])
+    for s in (sp, so):                                   # virial-only instantiation
+        s.md.Options.Compute = False
+        s.upload("coordinates", s.download("coordinates") + 0.01)
+        s.compute_forces()
+    assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-12
+    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
+    sp.finalize(), so.finalize()

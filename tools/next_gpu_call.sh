@@ -15,6 +15,7 @@ for g in 8 16 32; do
   EMDEE_ROWS=$g timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_rows$g.json 2> gpurun_out/bench_rows$g.err
 done
 EMDEE_CLUSTER2=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_cluster2.json 2> gpurun_out/bench_cluster2.err
+EMDEE_TILESCHED=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_tilesched.json 2> gpurun_out/bench_tilesched.err
 for m in 1 2; do
   EMDEE_TEX=$m timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_tex$m.json 2> gpurun_out/bench_tex$m.err
 done
