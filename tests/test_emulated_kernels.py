@@ -19,6 +19,7 @@ import test_gpu_parity as t_par
 import test_zz_box_rescale as t_box
 import test_zz_rdf as t_rdf
 import test_zzz_bonded as t_bd
+import test_zzz_config_c1 as t_c1
 import test_zzz_ewald as t_ew
 import test_zzz_phase_space as t_ps
 import test_zzz_rigid_bodies as t_rb
@@ -57,6 +58,7 @@ CASES = (_cases(t_par, skip=("test_brick_path_opt_in", "test_duo_path_opt_in"))
          + _cases(t_ps)
          + _cases(t_bd)
          + _cases(t_ew)
+         + _cases(t_c1)
          + _cases(t_exp)
          + [pytest.param(t_par.test_brick_path_opt_in, {}, id="test_gpu_parity::test_brick_path_opt_in"),
             pytest.param(t_par.test_duo_path_opt_in, {}, id="test_gpu_parity::test_duo_path_opt_in")])
@@ -69,6 +71,7 @@ def _use_emulated_library(monkeypatch):
     monkeypatch.setenv("EMDEE_TEST_EXPERIMENTAL", "1")
     monkeypatch.setenv("EMDEE_TEST_REPLAY_STEPS", "20")
     monkeypatch.setenv("EMDEE_TEST_REPLICAS", "1")
+    monkeypatch.setenv("EMDEE_TEST_C1_ATOMS", "1000")
 
 
 @pytest.mark.parametrize("fn,kwargs", CASES)
