@@ -14,7 +14,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "emdee_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_build")
 GEN = os.path.join(OUT, "cusim_src")
-LIB = os.path.join(OUT, "libemdee_cusim.so")
+# CUSIM_FMA=1: a second build that lets g++ contract a*b+c into fused multiply-adds (as nvcc does by default), to check on
+# the CPU that the tolerances of the GPU tests survive the different rounding of the device build
+FMA = os.environ.get("CUSIM_FMA") == "1"
+LIB = os.path.join(OUT, "libemdee_cusim_fma.so" if FMA else "libemdee_cusim.so")
 PARTS = ["engine.cu", "engine_common.cuh", "engine_list.cuh", "engine_force.cuh", "engine_brick.cuh",
          "engine_dynamics.cuh", "engine_bodies.cuh", "engine_bonded.cuh", "engine_ewald.cuh", "engine_dist.cuh", "engine_extra.cuh"]
 
@@ -102,7 +105,8 @@ def build(force=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     generate()
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,-Bsymbolic",
+    fp = ["-O2", "-march=x86-64-v3", "-ffp-contract=fast"] if FMA else ["-O1", "-g", "-ffp-contract=off"]
+    cmd = ["/usr/bin/g++", "-std=c++17", *fp, "-fPIC", "-shared", "-Wl,-Bsymbolic",
            "-Wl,--no-undefined", "-Wno-unused-function", "-Wno-unused-variable",
            "-I" + os.path.join(HERE, "include"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
            "-x", "c++", os.path.join(CSRC, "abi.cpp"), os.path.join(GEN, "engine.cpp"), "-o", LIB, "-ldl"]

@@ -95,3 +95,17 @@ def test_results_do_not_depend_on_thread_interleaving(order):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
                         f"test_on_emulator and ({sel})"], capture_output=True, text=True, env=env, cwd=cm.ROOT, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_tolerances_survive_fma_contraction():
+    """nvcc contracts a*b+c into fused multiply-adds by default; the regular emulator build does not (-ffp-contract=off),
+    so a tolerance that only holds without FMAs would first fail on the B200. A second emulator build with contraction on
+    (CUSIM_FMA=1: -O2 -march=x86-64-v3 -ffp-contract=fast) runs the parity tests of the kernels written after the last GPU
+    session at their GPU tolerances."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CUSIM_FMA="1")
+    sel = "nve_trajectory or verlet_step_with_shadow or bonded or ewald or testfortran or body_frames or spce_single_point"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        f"test_on_emulator and ({sel})"], capture_output=True, text=True, env=env, cwd=cm.ROOT, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
