@@ -105,7 +105,7 @@ def test_tolerances_survive_fma_contraction():
     import subprocess
     import sys
     env = dict(os.environ, CUSIM_FMA="1")
-    sel = "nve_trajectory or verlet_step_with_shadow or bonded or ewald or testfortran or body_frames or spce_single_point"
+    sel = "nve_trajectory or verlet_step_with_shadow or bonded or rock_salt or testfortran or body_frames"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
                         f"test_on_emulator and ({sel})"], capture_output=True, text=True, env=env, cwd=cm.ROOT, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
