@@ -1254,9 +1254,6 @@ BodyView body_view(Engine::Impl& s) {
   return v;
 }
 
-void require_single_gpu_bodies(Engine::Impl& s, const char* task) {
-  if (s.world > 1 && s.nbodies != 0) fatal(task, "rigid-body dynamics on several GPUs is not available yet (forces and energies are)");
-}
 }  // namespace
 
 void Engine::set_bodies(const std::vector<int>& first, const std::vector<int>& atoms, const std::vector<double>& memberMass) {
@@ -1592,21 +1589,24 @@ void Engine::derive_quaternion_momenta() {
 
 void Engine::shadow_pre(int layer0, double dt, int mode) {
   Impl& s = *d_;
-  require_single_gpu_bodies(s, "verlet_step");
-  if (s.world > 1) fatal("verlet_step", "the shadow-Hamiltonian bookkeeping is not available on several GPUs");
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   const bool bodies = s.nbodies != 0;
-  if (bodies) {
+  const bool dist = s.world > 1 && s.owned_valid;
+  if (bodies) {   // several GPUs: body state (incl. the all-reduced F and tau of the last kick) is replicated
     s.shR0.ensure(3 * (size_t)s.nbodies);
     s.shQ0.ensure(4 * (size_t)s.nbodies);
     k_shadow_pre_bodies<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), dt, mode, s.shR0.p, s.shQ0.p);
     stats_.launches += 1;
   }
   if (s.nitems < s.N) {
+    const unsigned char* mask = !bodies ? (dist ? s.owned.p : nullptr) : (dist ? s.ownedFree.p : s.freeMask.p);
     s.shS0.ensure(3 * (size_t)s.N);
-    k_shadow_pre_atoms<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, bodies ? s.freeMask.p : nullptr, dt, s.R.p, s.P.p, Fl, s.invMass.p,
-                                                           s.shS0.p);
+    if (dist) CUDA_CHECK(cudaMemsetAsync(s.shS0.p, 0, 3 * (size_t)s.N * sizeof(double), s.stream));
+    k_shadow_pre_atoms<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, mask, dt, s.R.p, s.P.p, Fl, s.invMass.p, s.shS0.p);
     stats_.launches += 1;
+    // several GPUs: the force call in the middle of the step may rebuild the list and hand atoms to another rank, whose
+    // post_force sum then needs the s0 the old owner stored: make s0 full on every rank (all-reduce of the owned parts)
+    if (dist) gather_full(s, s.shS0.p);
   }
 }
 
@@ -1614,6 +1614,7 @@ void Engine::shadow_post(int layer0, double dt, int mode, double& Us, double& Ks
   Impl& s = *d_;
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   const bool bodies = s.nbodies != 0;
+  const bool dist = s.world > 1 && s.owned_valid;
   if (!bodies) {   // the reduction buffers of the body path are created by set_bodies
     s.bPartial.ensure((size_t)nblocks(s.N) * 6);
     s.bScalars.ensure(16);
@@ -1626,9 +1627,12 @@ void Engine::shadow_post(int layer0, double dt, int mode, double& Us, double& Ks
     stats_.launches += 1;
   }
   if (s.nitems < s.N) {
-    k_shadow_post_atoms<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, bodies ? s.freeMask.p : nullptr, dt, s.R.p, s.P.p, Fl, s.invMass.p,
-                                                            s.shS0.p, s.bPartial.p, s.tickets.p + 3, s.bScalars.p + 8);
+    // (an atom that migrated during this step is summed by its NEW owner: s0 was made full on every rank in shadow_pre)
+    const unsigned char* mask = !bodies ? (dist ? s.owned.p : nullptr) : (dist ? s.ownedFree.p : s.freeMask.p);
+    k_shadow_post_atoms<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, mask, dt, s.R.p, s.P.p, Fl, s.invMass.p, s.shS0.p, s.bPartial.p,
+                                                            s.tickets.p + 3, s.bScalars.p + 8);
     stats_.launches += 1;
+    if (dist) NCCL_CHECK(nccl().AllReduce(s.bScalars.p + 8, s.bScalars.p + 8, 2, ncclDouble, ncclSum, s.comm, s.stream));
   }
   CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));

@@ -109,8 +109,9 @@ def build(force=False):
     cmd = ["/usr/bin/g++", "-std=c++17", *fp, "-fPIC", "-shared", "-Wl,-Bsymbolic",
            "-Wl,--no-undefined", "-Wno-unused-function", "-Wno-unused-variable",
            "-I" + os.path.join(HERE, "include"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
-           "-x", "c++", os.path.join(CSRC, "abi.cpp"), os.path.join(GEN, "engine.cpp"), "-o", LIB, "-ldl"]
+           "-x", "c++", os.path.join(CSRC, "abi.cpp"), os.path.join(GEN, "engine.cpp"), "-o", LIB + f".tmp{os.getpid()}", "-ldl"]
     subprocess.check_call(cmd)
+    os.replace(LIB + f".tmp{os.getpid()}", LIB)   # atomic: concurrent builders (several ranks) never expose a half-written file
     return LIB
 
 

@@ -111,6 +111,18 @@ def main():
         Rp = sp.download("coordinates")
         if rank == 0:
             assert np.abs(Rp - so.download("coordinates")).max() < 1e-10
+        if charged:
+            # EmDee_verlet_step with the shadow-Hamiltonian bookkeeping (s0 of migrating atoms is all-reduced)
+            for step in range(12):
+                for s in ([sp, so] if rank == 0 else [sp]):
+                    s.md.Options.Compute = True
+                    s.verlet_step(0.005)
+            if rank == 0:
+                assert sp.md.Builds == so.md.Builds
+                for grp, nm in (("Energy", "ShadowPotential"), ("Kinetic", "ShadowKinetic"), ("Kinetic", "Total"), ("Energy", "Potential")):
+                    a, b = getattr(getattr(sp.md, grp), nm), getattr(getattr(so.md, grp), nm)
+                    assert abs(a - b) <= 1e-9 * abs(b), f"verlet_step {grp}.{nm}: {a!r} vs {b!r}"
+                print(f"[mgpu] verlet_step with shadow terms ok ({sp.md.Builds} builds)", flush=True)
         if not charged:
             # EmDee_rdf over the slab-decomposed list (collective: histogram all-reduced). The two trajectories differ
             # at rounding level after 40 steps, so a pair sitting on a bin edge may move one bin: compare counts
