@@ -111,7 +111,7 @@ def main():
         Rp = sp.download("coordinates")
         if rank == 0:
             assert np.abs(Rp - so.download("coordinates")).max() < 1e-10
-        if charged:
+        if charged and os.environ.get("EMDEE_MGPU_SKIP_VERLET") != "1":
             # EmDee_verlet_step with the shadow-Hamiltonian bookkeeping (s0 of migrating atoms is all-reduced)
             for step in range(12):
                 for s in ([sp, so] if rank == 0 else [sp]):
