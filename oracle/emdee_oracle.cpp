@@ -3,7 +3,10 @@
 //
 // CPU (C++17 + OpenMP) restatement of the nonbonded hot path of atoms-ufrj/EmDee ("15 Oct 2018"):
 // the cell-list Verlet neighbor-list build and the pairwise force/energy/virial loop, behind the
-// same C ABI (include/emdee.h). The reference is Fortran 2008 and no Fortran compiler exists in the
+// same C ABI (include/emdee.h) -- and, since the widening of SURVEY.md section 8(f), of the callers around
+// it: the rigid-body integrator (src/ArBee.f90), EmDee_verlet_step, harmonic bonds / angles, the Ewald
+// reciprocal sum (src/kspace_ewald.f90, src/modelClass_kspace.f90), EmDee_rdf, EmDee_memory_address and
+// EmDee_share_phase_space. The reference is Fortran 2008 and no Fortran compiler exists in the
 // build image, so the reference itself cannot be compiled (oracle/_ref is therefore absent); this
 // file follows the reference sources function by function and every function cites the file:line
 // it restates (paths relative to the reference tree).
@@ -16,8 +19,10 @@
 //   test/test_pair_lj_cut.f90:46, test/test_pair_lj_sf.f90:46 (100-step NVE, 800-atom NIST LJ),
 //   test/test_pair_lj_smoothed.f90:46 (valid for skin = 1.0),
 // NIST SRSW reference energies for the LJ sample, and the survey's independent O(N^2) probes.
-// Coulomb models, soft-core and rigid-body totals are NOT pinned by any reference test
-// ("parity unpinned" for those rows; self-consistency checks only).
+// Coulomb models, soft-core, rigid-body dynamics, bonded terms and Ewald are NOT pinned by any reference
+// test (the reference's programs for them assert nothing): "parity unpinned" for those rows. They are
+// pinned by physics instead -- conservation laws and the group property of the exact free-rotor map,
+// finite-difference forces and virials, the Madelung constant of rock salt (tests/test_oracle_*.py).
 //
 // Two builds (oracle/Makefile): strict (-O2 -ffp-contract=off, defines bit-level truth for list
 // membership) and fast (-Ofast -march=native -fopenmp, mirrors reference Makefile:13,21; used for
