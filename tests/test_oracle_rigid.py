@@ -111,6 +111,17 @@ def test_exact_rotation_is_a_group_and_the_limit_of_the_splitting():
         b.displace(1.0, 0.0, 1.5)
     assert np.allclose(a.download("coordinates"), b.download("coordinates"), atol=1e-11)
     assert np.allclose(a.download("quatmom", (1, 4)), b.download("quatmom", (1, 4)), atol=1e-11)
+    # many periods in one call (the period-jump terms of src/ArBee.f90:262-268, 298-309) against ten shorter calls
+    for seed in (3, 4, 5):
+        c, _ = free_rotor(lib, mode=0, seed=seed, kT=1.5)
+        d, _ = free_rotor(lib, mode=0, seed=seed, kT=1.5)
+        c.displace(1.0, 0.0, 90.0)
+        for _ in range(10):
+            d.displace(1.0, 0.0, 9.0)
+        assert np.allclose(c.download("quaternions", (1, 4)), d.download("quaternions", (1, 4)), atol=1e-10), seed
+        assert np.allclose(c.download("angmom", (1, 3)), d.download("angmom", (1, 3)), atol=1e-10), seed
+        c.finalize()
+        d.finalize()
     # Miller's NO_SQUISH splitting with n sub-steps converges to the exact map as 1/n^2
     err = []
     for n in (8, 16, 32):
