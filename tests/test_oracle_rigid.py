@@ -135,6 +135,33 @@ def test_exact_rotation_is_a_group_and_the_limit_of_the_splitting():
     b.finalize()
 
 
+def test_exact_rotation_against_direct_integration_of_euler_equations():
+    """Independent of both integrators of the library: Euler's equations for the body-frame angular velocity and
+    dq/dt = q (x) (0, omega)/2 for the orientation, integrated by scipy (DOP853, rtol 1e-13), must land on the same
+    orientation and angular velocity as ONE call of the closed-form map."""
+    from scipy.integrate import solve_ivp
+    lib = cm.oracle()
+    for seed, t in ((7, 5.0), (8, 12.0)):
+        s, m = free_rotor(lib, mode=0, seed=seed, kT=0.8)
+        q0 = s.download("quaternions", (1, 4))[0].copy()
+        w0 = s.download("angmom", (1, 3))[0].copy()
+        I = s.download("inertia", (1, 3))[0].copy()
+
+        def rhs(_, y):
+            q, w = y[:4], y[4:]
+            dw = np.array([(I[1] - I[2]) * w[1] * w[2] / I[0], (I[2] - I[0]) * w[2] * w[0] / I[1], (I[0] - I[1]) * w[0] * w[1] / I[2]])
+            dq = 0.5 * np.array([-q[1] * w[0] - q[2] * w[1] - q[3] * w[2], q[0] * w[0] - q[3] * w[1] + q[2] * w[2],
+                                 q[3] * w[0] + q[0] * w[1] - q[1] * w[2], -q[2] * w[0] + q[1] * w[1] + q[0] * w[2]])   # B(q) w / 2
+            return np.concatenate([dq, dw])
+        sol = solve_ivp(rhs, (0.0, t), np.concatenate([q0, w0]), method="DOP853", rtol=1e-13, atol=1e-14)
+        s.displace(1.0, 0.0, t)
+        q1, w1 = s.download("quaternions", (1, 4))[0], s.download("angmom", (1, 3))[0]
+        qs = sol.y[:4, -1] / np.linalg.norm(sol.y[:4, -1])
+        assert min(np.abs(q1 - qs).max(), np.abs(q1 + qs).max()) < 1e-9, (seed, q1, qs)
+        assert np.abs(w1 - sol.y[4:, -1]).max() < 1e-9 * max(1.0, np.abs(w1).max()), (seed, w1, sol.y[4:, -1])
+        s.finalize()
+
+
 def _spce(lib, mode=0, seed=4321):
     s, c = cm.spce_sample_system(lib, lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0))
     s.md.Options.RotationMode = mode
