@@ -82,30 +82,28 @@ def test_on_emulator(fn, kwargs, monkeypatch):
     fn(**kwargs)
 
 
-@pytest.mark.parametrize("order", ["reverse", "random:11"])
-def test_results_do_not_depend_on_thread_interleaving(order):
-    """The emulator can run the threads of a block (and the blocks of a grid) in reverse or in a fresh random order
-    every scheduling round (CUSIM_ORDER). Parity must hold regardless: a failure here means a missing barrier or a
-    grid-wide finish that depends on which block comes last."""
+def test_scheduling_order_and_fma_contraction_do_not_matter():
+    """Three re-runs of a selection of the cases above, as concurrent subprocesses:
+    * CUSIM_ORDER=reverse / random:11 -- the emulator runs the threads of a block (and the blocks of a grid) in reverse
+      or in a fresh random order every scheduling round. Parity must hold regardless: a failure means a missing barrier
+      or a grid-wide finish that depends on which block comes last.
+    * CUSIM_FMA=1 -- nvcc contracts a*b+c into fused multiply-adds by default; the regular emulator build does not
+      (-ffp-contract=off), so a tolerance that only holds without FMAs would first fail on the B200. A second emulator
+      build with contraction on (-O2 -march=x86-64-v3 -ffp-contract=fast) runs the parity tests of the kernels written
+      after the last GPU session at their GPU tolerances."""
     import subprocess
     import sys
-    env = dict(os.environ, CUSIM_ORDER=order)
-    sel = ("two_types or dynamics_with_rebuilds or kat_replay_on_gpu or spce_single_point or brick or duo or rdf or degenerate "
-           "or verlet_step_with_shadow or next_to_rigid or rock_salt or share_phase_space")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        f"test_on_emulator and ({sel})"], capture_output=True, text=True, env=env, cwd=cm.ROOT, timeout=1200)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-
-
-def test_tolerances_survive_fma_contraction():
-    """nvcc contracts a*b+c into fused multiply-adds by default; the regular emulator build does not (-ffp-contract=off),
-    so a tolerance that only holds without FMAs would first fail on the B200. A second emulator build with contraction on
-    (CUSIM_FMA=1: -O2 -march=x86-64-v3 -ffp-contract=fast) runs the parity tests of the kernels written after the last GPU
-    session at their GPU tolerances."""
-    import subprocess
-    import sys
-    env = dict(os.environ, CUSIM_FMA="1")
-    sel = "nve_trajectory or verlet_step_with_shadow or bonded or rock_salt or testfortran or body_frames"
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        f"test_on_emulator and ({sel})"], capture_output=True, text=True, env=env, cwd=cm.ROOT, timeout=1500)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    order_sel = ("two_types or dynamics_with_rebuilds or kat_replay_on_gpu or spce_single_point or brick or duo or rdf or degenerate "
+                 "or verlet_step_with_shadow or next_to_rigid or rock_salt or share_phase_space")
+    fma_sel = "nve_trajectory or verlet_step_with_shadow or bonded or rock_salt or testfortran or body_frames"
+    cm.emulated()   # build the regular library once, before the children need it
+    runs = [({"CUSIM_ORDER": "reverse"}, order_sel), ({"CUSIM_ORDER": "random:11"}, order_sel), ({"CUSIM_FMA": "1"}, fma_sel)]
+    procs = []
+    for extra, sel in runs:
+        env = dict(os.environ, **extra)
+        procs.append((extra, subprocess.Popen([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                                               f"test_on_emulator and ({sel})"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                              text=True, env=env, cwd=cm.ROOT)))
+    for extra, p in procs:
+        out, _ = p.communicate(timeout=1800)
+        assert p.returncode == 0, f"{extra}: " + out[-3000:]

@@ -14,7 +14,7 @@ import pytest
 
 import common as cm
 
-WORLDS = [2, 3, 4, 8]
+WORLDS = [2, 3, 8]   # 4 ranks run on real GPUs (tests/test_multi_gpu.py); 8 covers every multi-neighbor pattern here
 
 
 @pytest.fixture(scope="module")
