@@ -34,7 +34,8 @@ def test_slab_decomposition_on_emulator(world, libs):
     if world >= 6:
         env["EMDEE_MGPU_NCELL"] = "21"
     if world >= 4:
-        env["EMDEE_MGPU_SKIP_VERLET"] = "1"   # verlet_step with migration is covered at 2 and 3 ranks
+        env["EMDEE_MGPU_SKIP_VERLET"] = "1"    # verlet_step with migration is covered at 2 and 3 ranks
+        env["EMDEE_MGPU_SKIP_CHARGED"] = "1"   # the charged LJ system repeats the neutral one with a Coulomb model
     if world >= 3:   # keep the CPU suite short: the Ewald crystal grows with the rank count (three cell layers per rank)
         env["EMDEE_MGPU_SKIP_EWALD"] = "1"
     env["EMDEE_MGPU_BODY_STEPS"] = "3" if world <= 3 else "0"   # rigid-body dynamics: 2 and 3 ranks cover both neighbor patterns

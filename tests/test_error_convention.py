@@ -79,11 +79,15 @@ CASES = {
 }
 
 
-def run(which, body):
+def start(which, body):
     code = textwrap.dedent(PRELUDE).format(tests=cm.ROOT + "/tests", which=which) + body + "\nprint('NO ERROR RAISED')\n"
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=cm.ROOT, timeout=120)
-    lines = [l for l in r.stderr.splitlines() if l.startswith("Error in")]
-    return r.returncode, (lines[-1] if lines else ""), r.stdout, r.stderr
+    return subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=cm.ROOT)
+
+
+def finish(p):
+    out, err = p.communicate(timeout=120)
+    lines = [l for l in err.splitlines() if l.startswith("Error in")]
+    return p.returncode, (lines[-1] if lines else ""), out, err
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -94,8 +98,9 @@ def _built():
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_misuse_exits_with_the_same_message(name):
-    rc_s, msg_s, out_s, err_s = run("stub", CASES[name])
-    rc_o, msg_o, out_o, err_o = run("oracle", CASES[name])
+    ps, po = start("stub", CASES[name]), start("oracle", CASES[name])   # the two libraries side by side
+    rc_s, msg_s, out_s, err_s = finish(ps)
+    rc_o, msg_o, out_o, err_o = finish(po)
     assert rc_o == 1 and msg_o.startswith("Error in ") and msg_o.endswith("."), (rc_o, out_o, err_o)
     assert rc_s == 1, (rc_s, out_s, err_s)
     assert msg_s == msg_o
