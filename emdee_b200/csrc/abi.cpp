@@ -997,13 +997,9 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/Em
   } else if (item == "momenta") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
     me->engine->upload_momenta(address);
-    double twoKE[3] = {0, 0, 0};
-    for (int i : me->freeAtoms)
-      for (int x = 0; x < 3; ++x) twoKE[x] += me->invMass[i] * address[3 * (size_t)i + x] * address[3 * (size_t)i + x];
-    emdee::KineticAll kb;
-    me->engine->take_member_momenta(kb);   // assign_momenta of the bodies (src/EmDeeData.f90:173-187), on the device
-    for (int x = 0; x < 3; ++x) twoKE[x] += kb.twoKEt[x];
-    set_kinetic(md, twoKE, kb.twoKEr);
+    emdee::KineticAll k;
+    me->engine->take_member_momenta(k);   // assign_momenta (src/EmDeeData.f90:157-189) on the device: free atoms and bodies
+    set_kinetic(md, k.twoKEt, k.twoKEr);
   } else if (item == "forces") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
     me->engine->upload_forces(me->layer - 1, address);

@@ -1523,9 +1523,21 @@ void Engine::refresh_member_momenta() {
   stats_.launches += 1;
 }
 
+// kinetic sums of the momenta just uploaded: free atoms (k_free_kinetic) + bodies (k_body_take_momenta = assign_momenta)
 void Engine::take_member_momenta(KineticAll& ke) {
   Impl& s = *d_;
   for (int x = 0; x < 3; ++x) ke.twoKEt[x] = ke.twoKEr[x] = 0.0;
+  if (s.nitems < s.N) {
+    s.bPartial.ensure((size_t)nblocks(s.N) * 6);
+    s.bScalars.ensure(16);
+    if (s.h_bscalars == nullptr) CUDA_CHECK(cudaMallocHost(&s.h_bscalars, 16 * sizeof(double)));
+    k_free_kinetic<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, s.nbodies != 0 ? s.freeMask.p : nullptr, s.P.p, s.invMass.p,
+                                                       s.bPartial.p, s.tickets.p + 3, s.bScalars.p + 8);
+    stats_.launches += 1;
+    CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars + 8, s.bScalars.p + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    for (int x = 0; x < 3; ++x) ke.twoKEt[x] = s.h_bscalars[8 + x];
+  }
   if (s.nbodies == 0) return;
   k_body_take_momenta<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.delta.p, s.P.p, s.bPartial.p, s.tickets.p + 3,
                                                                  s.bScalars.p);
@@ -1533,7 +1545,7 @@ void Engine::take_member_momenta(KineticAll& ke) {
   CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
   for (int x = 0; x < 3; ++x) {
-    ke.twoKEt[x] = s.h_bscalars[x];
+    ke.twoKEt[x] += s.h_bscalars[x];
     ke.twoKEr[x] = s.h_bscalars[3 + x];
   }
 }

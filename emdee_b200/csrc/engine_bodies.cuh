@@ -707,6 +707,24 @@ __global__ void __launch_bounds__(TPB) k_body_take_momenta(BodyView v, const dou
   reduce_and_finish<6>(ke, partial, ticket, out);
 }
 
+// sum over free atoms of p^2/m per dimension (EmDee_upload "momenta", reference assign_momenta src/EmDeeData.f90:168-172);
+// 4 wide with the last slot unused so that the grid_finish<3> instantiation of k_boost keeps its shared-memory layout
+__global__ void __launch_bounds__(TPB) k_free_kinetic(int N, const unsigned char* __restrict__ isFree, const double* __restrict__ P,
+                                                      const double* __restrict__ invMass, double* __restrict__ partial,
+                                                      unsigned int* __restrict__ ticket, double* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (a < N && (isFree == nullptr || isFree[a])) {
+    const double im = invMass[a];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      const double p = P[3 * (size_t)a + x];
+      acc[x] = im * p * p;
+    }
+  }
+  reduce_and_finish<4>(acc, partial, ticket, out);
+}
+
 // omega (and pcm) were just written by the host (random momenta): derive the quaternion momenta
 __global__ void __launch_bounds__(TPB) k_body_set_omega(BodyView v) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
