@@ -997,9 +997,17 @@ void EmDee_upload(tEmDee* md, const char* option, double* address) {   // src/Em
   } else if (item == "momenta") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
     me->engine->upload_momenta(address);
-    emdee::KineticAll k;
-    me->engine->take_member_momenta(k);   // assign_momenta (src/EmDeeData.f90:157-189) on the device: free atoms and bodies
-    set_kinetic(md, k.twoKEt, k.twoKEr);
+    if (me->nbodies() == 0) {
+      // body-less systems keep the GPU-verified round-1 path: the three sums are formed from the client's buffer
+      double twoKE[3] = {0, 0, 0};
+      for (int i = 0; i < me->N; ++i)
+        for (int x = 0; x < 3; ++x) twoKE[x] += me->invMass[i] * address[3 * (size_t)i + x] * address[3 * (size_t)i + x];
+      set_kinetic(md, twoKE);
+    } else {
+      emdee::KineticAll k;
+      me->engine->take_member_momenta(k);   // assign_momenta (src/EmDeeData.f90:157-189) on the device: free atoms and bodies
+      set_kinetic(md, k.twoKEt, k.twoKEr);
+    }
   } else if (item == "forces") {
     if (!me->initialized) error("upload", "box and coordinates have not been defined");
     me->engine->upload_forces(me->layer - 1, address);
