@@ -176,7 +176,7 @@ def main():
     print(f"# per warp-gather: distinct 32B sectors | distinct 128B lines | lines summed over 4-lane groups | active lanes")
     rng = np.random.default_rng(0)
     res = {"default (lane = atom)": count(default_mapping(real, rows, args.warps, rng))}
-    for G in (8, 16, 32):
+    for G in (2, 4, 8, 16, 32):
         res[f"rows G={G:<2d} (G lanes per atom)"] = count(rows_mapping(real, rows, G, args.warps * (32 // G), rng))
     base = res["default (lane = atom)"]
     for C in (2, 4, 8):
