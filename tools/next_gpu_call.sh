@@ -19,6 +19,13 @@ EMDEE_TILESCHED=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-b
 for m in 1 2; do
   EMDEE_TEX=$m timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_tex$m.json 2> gpurun_out/bench_tex$m.err
 done
+# one full ncu capture of the force kernel per mapping worth comparing (wavefronts, L1 hit rate, pipe utilisation)
+NCU="ncu --set full --clock-control none --import-source on -s 30 -c 1"
+timeout 300 $NCU -k regex:k_pair_forces -o gpurun_out/r2a_force_default python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
+EMDEE_ROWS=8 timeout 300 $NCU -k regex:k_pair_forces_rows -o gpurun_out/r2a_force_rows8 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
+EMDEE_TEX=2 timeout 300 $NCU -k regex:k_pair_forces_tex -o gpurun_out/r2a_force_tex2 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
+EMDEE_TILESCHED=1 timeout 300 $NCU -k regex:k_pair_forces_sched -o gpurun_out/r2a_force_sched python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
+for f in gpurun_out/r2a_force_*.ncu-rep; do python tools/ncu_summary.py "$f" > "${f%.ncu-rep}.txt" 2>&1; done
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/bench_*.json")):
