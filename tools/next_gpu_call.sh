@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU call of the next round (run under gpurun from the repo root; ~6 GPU-minutes):
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/next_gpu_call.sh'
+# First GPU call of the next round (run under gpurun from the repo root; ~30 GPU-minutes):
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash tools/next_gpu_call.sh'
 # 1. gather-cost microbenchmark (decides between the layouts discussed in DESIGN.md section 5)
 # 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS, EMDEE_CLUSTER2), of the box-rescale scenario and of the
 #    kernels written after the last GPU session (rigid bodies, verlet_step, bonded, Ewald, memory_address, sharing)
