@@ -195,6 +195,73 @@ def workload_config(ncell, N, world, where):
             "l2_policy": "inputs larger than L2: the neighbor list streamed every step (>300 MB at 1M atoms) exceeds the 126 MB L2"}
 
 
+def spce_line_multi_gpu(args, world):
+    """Informational: the resident rigid-body NVE arm of spce_line on `world` GPUs (one rank per GPU, z-slabs). Body state
+    is replicated on every rank and the bodies' (F, tau) are all-reduced per kick. The box stays
+    cubic, so the replica count per dimension is the nearest integer to replicas * world^(1/3) (weak scaling, approximately)."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common as cm
+    from emdee_b200 import dist as edist
+    rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    emulated = os.environ.get("EMDEE_MGPU_EMULATED") == "1"   # CPU rehearsal of this function (tests/cusim + fake NCCL + gloo)
+    if emulated:
+        dist.init_process_group("gloo")
+        lib, dev = cm.emulated(), "cpu"
+    else:
+        torch.cuda.set_device(local_rank)
+        os.environ["EMDEE_DEVICE"] = str(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        lib, dev = api.load(), "cuda"
+    sync = (lambda: None) if emulated else torch.cuda.synchronize
+    n = int(round(args.replicas * world ** (1.0 / 3.0)))
+    K, W = min(args.steps, 30), 3
+    orig = cm.api.System.set_pair_model
+    state = {"done": False}
+
+    def hooked(self, *a, **k):          # the communicator must exist before the first upload
+        if not state["done"]:
+            edist.init_comm(self.lib, self)
+            state["done"] = True
+        return orig(self, *a, **k)
+    cm.api.System.set_pair_model = hooked
+    try:
+        s, c = cm.spce_sample_system(lib, lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0), replicas=n, threads=1)
+    finally:
+        cm.api.System.set_pair_model = orig
+    N = c["N"]
+    s.random_momenta(c["kB"] * c["Temp"], True, 86245)
+
+    def nve(k):
+        for _ in range(k):
+            s.boost(1.0, 0.0, 0.5)
+            s.displace(1.0, 0.0, 1.0)
+            s.boost(1.0, 0.0, 0.5)
+    nve(W)
+    E0 = s.md.Energy.Potential + s.md.Kinetic.Total
+    b0 = s.md.Builds
+    dist.barrier()
+    sync()
+    t0 = time.perf_counter()
+    nve(K)
+    sync()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sec = float(dt.item())
+        print(json.dumps({"metric": METRIC, "informational": True, "n_gpus": world,
+                          "workload": f"SPC/E NIST sample x {n}^3 = {N} atoms in one cubic box, Rc=10 A, skin=2 A, rigid bodies, "
+                                      "coul_damped_square_smoothed(0.2,1.0); resident NVE with the device rigid-body integrator, "
+                                      "z-slab decomposition, replicated body state",
+                          "value": N * K / sec, "unit": "atom-steps/s", "ms_per_step": 1e3 * sec / K, "steps": K,
+                          "builds": s.md.Builds - b0,
+                          "energy_drift_rel": abs(s.md.Energy.Potential + s.md.Kinetic.Total - E0) / abs(s.md.Kinetic.Total)}), flush=True)
+    s.finalize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def spce_line(args):
     """Informational (not the contract line): SPC/E water, NIST sample replicated n^3 times, rigid bodies,
     LJ shifted-force on O + pair_none on H + coul_damped_square_smoothed(0.2, 1.0) (reference test/test_coul_*.f90).
@@ -205,6 +272,10 @@ def spce_line(args):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import common as cm
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        spce_line_multi_gpu(args, world)
+        return
     lib = api.load()
     n = args.replicas
     K, W = min(args.steps, 30), 3

@@ -41,3 +41,5 @@ tail -c 1500 gpurun_out/bench_spce.json
 EMDEE_TYPED=1 timeout 600 python bench.py --workload spce --steps 20 > gpurun_out/bench_spce_typed.json 2> gpurun_out/bench_spce_typed.err
 tail -c 1500 gpurun_out/bench_spce_typed.json
 cat gpurun_out/lsu_probe.txt
+# Multi-GPU follow-up (separate call, `gpurun --gpus 2|4|8`): python -m pytest tests/test_multi_gpu.py -m gpu -q ;
+#   torchrun bench.py --gpus N (LJ, contract line) ; torchrun bench.py --workload spce --gpus N (rigid water, informational)
