@@ -722,6 +722,29 @@ bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEnt
   }
 }
 
+// opt-in typed path (EMDEE_TYPED=1): builds the layer's compact table on first use and launches k_pair_forces_typed.
+// Returns false (nothing launched) when the layer is not eligible.
+bool try_typed_path(Engine::Impl& s, int layer0, const LayerTable& lt, int ck, ForceArgs& a, bool compute) {
+  if (s.typedState[layer0] == 0) {
+    std::vector<TypedEntry> tt;
+    int pmod = 0;
+    if (build_typed_table(lt, tt, pmod)) {
+      s.ttabs[layer0].ensure(tt.size());
+      CUDA_CHECK(cudaMemcpyAsync(s.ttabs[layer0].p, tt.data(), tt.size() * sizeof(TypedEntry), cudaMemcpyHostToDevice, s.stream));
+      CUDA_CHECK(cudaStreamSynchronize(s.stream));   // `tt` is a local
+      s.typedState[layer0] = 1;
+      s.typedPM[layer0] = pmod;
+      if (std::getenv("EMDEE_DEBUG"))
+        std::fprintf(stderr, "[emdee] typed path: layer %d eligible (modifier %d, coulomb kind %d, %d types)\n", layer0, pmod, ck, s.nt);
+    } else {
+      s.typedState[layer0] = -1;
+    }
+  }
+  if (s.typedState[layer0] != 1) return false;
+  return s.typedPM[layer0] == nb::M_NONE ? launch_typed_ck<nb::M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream)
+                                         : launch_typed_ck<nb::M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream);
+}
+
 // FP32 pre-test band (see k_build_list). Positions are ghost-shifted scaled coordinates, |p| <= pmax.
 // Rounding p to FP32 moves each coordinate by <= 2^-24*pmax; the FP32 difference adds <= 2^-24*|d|.
 // So every component of the FP32 separation is within delta of the true one, and
@@ -1095,26 +1118,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     else
       launch_force_rows<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, g, pitch, rows, compute, smem_dyn, s.stream);
   } else if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && std::getenv("EMDEE_TYPED") != nullptr &&
-             [&] {   // opt-in experiment (see k_pair_forces_typed): compile-time kinds for LJ/none + cut-family Coulomb layers
-               if (s.typedState[layer0] == 0) {
-                 std::vector<TypedEntry> tt;
-                 int pmod = 0;
-                 if (build_typed_table(lt, tt, pmod)) {
-                   s.ttabs[layer0].ensure(tt.size());
-                   CUDA_CHECK(cudaMemcpyAsync(s.ttabs[layer0].p, tt.data(), tt.size() * sizeof(TypedEntry), cudaMemcpyHostToDevice, s.stream));
-                   CUDA_CHECK(cudaStreamSynchronize(s.stream));   // `tt` is a local
-                   s.typedState[layer0] = 1;
-                   s.typedPM[layer0] = pmod;
-                   if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee] typed path: layer %d eligible (modifier %d, coulomb kind %d, %d types)\n", layer0, pmod, ck, s.nt);
-                 } else {
-                   s.typedState[layer0] = -1;
-                 }
-               }
-               if (s.typedState[layer0] != 1) return false;
-               return s.typedPM[layer0] == M_NONE ? launch_typed_ck<M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream)
-                                                  : launch_typed_ck<M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream);
-             }()) {
-    // launched inside the condition: an ineligible layer falls through to the generic kernel below
+             try_typed_path(s, layer0, lt, ck, a, compute)) {
+    // opt-in experiment (see k_pair_forces_typed), launched by try_typed_path; an ineligible layer falls through to the generic kernel
   } else if (s.nt == 1 && lj_plain && s.use_sched) {
     const int sgrid = nblocks((long long)s.ntiles * TILE, 512);
     s.partial.ensure((size_t)sgrid * 5);
