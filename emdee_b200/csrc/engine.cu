@@ -618,6 +618,7 @@ void launch_force_rows(ForceArgs& a, DBuf<double>& partial, int group, int pitch
     if (compute) k_pair_forces_rows<PK, PM, CK, CM, SINGLE, NEED_INVR, true, GG, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows); \
     else k_pair_forces_rows<PK, PM, CK, CM, SINGLE, NEED_INVR, false, GG, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows);       \
   }
+  EMDEE_ROWS_CASE(4)
   EMDEE_ROWS_CASE(8)
   EMDEE_ROWS_CASE(16)
   EMDEE_ROWS_CASE(32)
@@ -987,7 +988,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     s.rows_group = 0;
     if (!s.use_bricks && !s.use_duos && !s.use_cluster2 && std::getenv("EMDEE_ROWS") != nullptr) {   // opt-in experiment (see k_pair_forces_rows)
       const int g = std::atoi(std::getenv("EMDEE_ROWS"));
-      s.rows_group = (g == 8 || g == 16 || g == 32) ? g : 8;
+      s.rows_group = (g == 4 || g == 8 || g == 16 || g == 32) ? g : 8;
       s.rows_pitch = (s.cap + 7) & ~7;   // rows start on 32-byte boundaries
       s.rowsNbr.ensure((size_t)Next * s.rows_pitch, 1.1);
       const int tgrid = (int)((ntiles + ROWS_TILES_PER_BLOCK - 1) / ROWS_TILES_PER_BLOCK);

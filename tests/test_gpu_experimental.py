@@ -43,7 +43,7 @@ def _all_model_families():
     assert np.abs(outs[0] - outs[1]).max() < KTOL and builds[0] == builds[1]
 
 
-@pytest.mark.parametrize("group", [8, 16, 32])
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
 def test_rows_path(monkeypatch, group):
     """EMDEE_ROWS=G: G lanes share one atom and read consecutive entries of its (row-major) neighbor row
     (k_transpose_rows + k_pair_forces_rows). Same parity bars as the default path; every model goes through it."""
