@@ -97,6 +97,11 @@ struct Engine::Impl {
   DBuf<unsigned int> duoNbr;
   DBuf<int> duoCount;
 
+  // compact-record path (EMDEE_REC16, opt-in experiment): 16-byte fixed-point positions + cell-tagged copy of the list
+  bool use_rec16 = false;
+  DBuf<Rec16> rec16;
+  DBuf<unsigned int> taggedNbr;
+
   // tile schedule (EMDEE_TILESCHED, opt-in experiment): brick-ordered permutation of the list tiles
   bool use_sched = false;
   int ntiles = 0;
@@ -314,6 +319,7 @@ Engine::~Engine() {
   for (auto& t : s.tabs) t.release();
   for (auto& t : s.ttabs) t.release();
   s.schedKeys.release(); s.schedKeysOut.release(); s.schedTiles.release(); s.tileOrder.release();
+  s.rec16.release(); s.taggedNbr.release();
   s.Rs.release(); s.sRs.release(); s.sPosF.release(); s.atomCell.release(); s.atomFloor.release();
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
@@ -996,6 +1002,16 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
                                                                            s.rowsNbr.p);
       stats_.launches += 1;
     }
+    // ---- compact records: tagged copy of the list (see k_pair_forces_rec16) ---------------------------------------------
+    s.use_rec16 = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.rows_group == 0 && s.nt == 1 &&
+                  std::getenv("EMDEE_REC16") != nullptr;
+    if (s.use_rec16) {
+      if (Next >= (1 << REC16_INDEX_BITS)) fatal("neighbor list handling", "EMDEE_REC16 supports at most 2^25 sorted entries");
+      s.taggedNbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
+      s.rec16.ensure(Next, 1.1);
+      k_tag_list<<<nblocks(Next), TPB, 0, s.stream>>>(Next, s.cap, s.grid.Mx, s.nbr.p, s.nbrCount.p, s.sCell.p, s.taggedNbr.p);
+      stats_.launches += 1;
+    }
     // ---- tile schedule: brick-ordered permutation of the tiles (see k_pair_forces_sched) ----------------------------
     s.use_sched = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.rows_group == 0 && s.nt == 1 &&
                   std::getenv("EMDEE_TILESCHED") != nullptr;
@@ -1121,6 +1137,14 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   } else if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && std::getenv("EMDEE_TYPED") != nullptr &&
              try_typed_path(s, layer0, lt, ck, a, compute)) {
     // opt-in experiment (see k_pair_forces_typed), launched by try_typed_path; an ineligible layer falls through to the generic kernel
+  } else if (s.nt == 1 && lj_plain && s.use_rec16) {
+    k_refresh_rec16<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.grid.M, s.grid.Mx, s.R.p, s.sMeta.p, s.sCell.p, s.rec16.p);
+    stats_.launches += 1;
+    const int rgrid = nblocks(a.Next, 512);
+    s.partial.ensure((size_t)rgrid * 5);
+    a.partial = s.partial.p;
+    if (compute) k_pair_forces_rec16<true, 6, 512, 2><<<rgrid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
+    else k_pair_forces_rec16<false, 6, 512, 2><<<rgrid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
   } else if (s.nt == 1 && lj_plain && s.use_sched) {
     const int sgrid = nblocks((long long)s.ntiles * TILE, 512);
     s.partial.ensure((size_t)sgrid * 5);

@@ -421,6 +421,7 @@ inline double __hiloint2double(int hi, int lo) {
   std::memcpy(&d, &u, 8);
   return d;
 }
+inline long long __double2ll_rn(double a) { return std::llrint(a); }
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 inline void sincospi(double x, double* s, double* c) { sincos(3.14159265358979323846 * x, s, c); }
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }

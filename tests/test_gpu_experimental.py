@@ -133,3 +133,35 @@ def test_tile_schedule_path(monkeypatch):
     assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-12
     assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
     sp.finalize(), so.finalize()
+
+
+def test_rec16_path(monkeypatch):
+    """EMDEE_REC16=1: plain single-type LJ with 16-byte fixed-point position records (42 bits per coordinate, relative to
+    the entry's build-time cell) and a cell-tagged copy of the list; separations are formed exactly in 64-bit integers
+    (k_tag_list, k_refresh_rec16, k_pair_forces_rec16). The positions are quantised at 2^-41 of a cell, so forces agree
+    with the oracle to ~1e-11 relative (bar 1e-10) and totals to 1e-11 (bar of this test; the default path meets 1e-12)."""
+    monkeypatch.setenv("EMDEE_REC16", "1")
+    sp, so = both(lambda lib: cm.lj_sample_system(lib, _lj)[0])
+    assert np.array_equal(sp.pairs(), so.pairs())
+    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
+    assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-11
+    assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-11
+    c = cm.load_fixture("NIST_lj_sample")
+    for s in (sp, so):
+        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
+    for step in range(1, 31):                          # drift between rebuilds, rebuilds, virial-only steps
+        for s in (sp, so):
+            s.md.Options.Compute = (step % 5 == 0)
+            s.boost(1.0, 0.0, 0.5 * c["Dt"])
+            s.displace(1.0, 0.0, c["Dt"])
+            s.boost(1.0, 0.0, 0.5 * c["Dt"])
+    assert sp.md.Builds == so.md.Builds and sp.md.Builds >= 2
+    assert np.array_equal(sp.pairs(), so.pairs())
+    assert np.abs(sp.download("coordinates") - so.download("coordinates")).max() < 1e-9
+    assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-9
+    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-8
+    sp.finalize(), so.finalize()
+    for variant in ("lj_shifted_force", "softcore_0.7"):   # every other model falls through to the default kernels (strict bars)
+        sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS[variant])[0])
+        assert_state_parity(sp, so)
+        sp.finalize(), so.finalize()
