@@ -101,6 +101,7 @@ struct Engine::Impl {
   bool use_rec16 = false;
   DBuf<Rec16> rec16;
   DBuf<unsigned int> taggedNbr;
+  DBuf<int> rowsTagged;            // row-major copy of the tagged list (EMDEE_REC16 together with EMDEE_ROWS)
 
   // tile schedule (EMDEE_TILESCHED, opt-in experiment): brick-ordered permutation of the list tiles
   bool use_sched = false;
@@ -319,7 +320,7 @@ Engine::~Engine() {
   for (auto& t : s.tabs) t.release();
   for (auto& t : s.ttabs) t.release();
   s.schedKeys.release(); s.schedKeysOut.release(); s.schedTiles.release(); s.tileOrder.release();
-  s.rec16.release(); s.taggedNbr.release();
+  s.rec16.release(); s.taggedNbr.release(); s.rowsTagged.release();
   s.Rs.release(); s.sRs.release(); s.sPosF.release(); s.atomCell.release(); s.atomFloor.release();
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
@@ -1003,14 +1004,20 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       stats_.launches += 1;
     }
     // ---- compact records: tagged copy of the list (see k_pair_forces_rec16) ---------------------------------------------
-    s.use_rec16 = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.rows_group == 0 && s.nt == 1 &&
-                  std::getenv("EMDEE_REC16") != nullptr;
+    s.use_rec16 = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.nt == 1 && std::getenv("EMDEE_REC16") != nullptr;
     if (s.use_rec16) {
       if (Next >= (1 << REC16_INDEX_BITS)) fatal("neighbor list handling", "EMDEE_REC16 supports at most 2^25 sorted entries");
       s.taggedNbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
       s.rec16.ensure(Next, 1.1);
       k_tag_list<<<nblocks(Next), TPB, 0, s.stream>>>(Next, s.cap, s.grid.Mx, s.nbr.p, s.nbrCount.p, s.sCell.p, s.taggedNbr.p);
       stats_.launches += 1;
+      if (s.rows_group != 0) {   // EMDEE_ROWS too: the row-major copy is made from the TAGGED list (see k_pair_forces_rows16)
+        const int tgrid = (int)((ntiles + ROWS_TILES_PER_BLOCK - 1) / ROWS_TILES_PER_BLOCK);
+        s.rowsTagged.ensure((size_t)Next * s.rows_pitch, 1.1);   // its own buffer: other layers may still use the plain rows
+        k_transpose_rows<<<tgrid, 32 * ROWS_TILES_PER_BLOCK, 0, s.stream>>>(Next, s.cap, s.rows_pitch, reinterpret_cast<const int*>(s.taggedNbr.p),
+                                                                             s.nbrCount.p, s.rowsTagged.p);
+        stats_.launches += 1;
+      }
     }
     // ---- tile schedule: brick-ordered permutation of the tiles (see k_pair_forces_sched) ----------------------------
     s.use_sched = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.rows_group == 0 && s.nt == 1 &&
@@ -1123,6 +1130,25 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       launch_force_cluster2<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, 0, s.stream);
     else
       launch_force_cluster2<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, smem_dyn, s.stream);
+  } else if (s.nt == 1 && lj_plain && s.use_rec16 && s.rows_group != 0) {
+    k_refresh_rec16<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.grid.M, s.grid.Mx, s.R.p, s.sMeta.p, s.sCell.p, s.rec16.p);
+    stats_.launches += 1;
+    const int g = s.rows_group;
+    const long long warps = ((long long)a.Next * g + 31) / 32;
+    const int rgrid = (int)((warps + 7) / 8);
+    s.partial.ensure((size_t)rgrid * 5);
+    a.partial = s.partial.p;
+    const unsigned int* trows = reinterpret_cast<const unsigned int*>(s.rowsTagged.p);
+#define EMDEE_ROWS16_CASE(GG)                                                                                                    \
+    if (g == GG) {                                                                                                               \
+      if (compute) k_pair_forces_rows16<true, GG, 3><<<rgrid, 256, 0, s.stream>>>(a, s.grid.M, s.rows_pitch, s.rec16.p, trows);   \
+      else k_pair_forces_rows16<false, GG, 3><<<rgrid, 256, 0, s.stream>>>(a, s.grid.M, s.rows_pitch, s.rec16.p, trows);          \
+    }
+    EMDEE_ROWS16_CASE(4)
+    EMDEE_ROWS16_CASE(8)
+    EMDEE_ROWS16_CASE(16)
+    EMDEE_ROWS16_CASE(32)
+#undef EMDEE_ROWS16_CASE
   } else if (s.rows_group != 0) {
     const int* rows = s.rowsNbr.p;
     const int g = s.rows_group, pitch = s.rows_pitch;

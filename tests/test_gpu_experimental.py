@@ -165,3 +165,33 @@ def test_rec16_path(monkeypatch):
         sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS[variant])[0])
         assert_state_parity(sp, so)
         sp.finalize(), so.finalize()
+
+
+@pytest.mark.parametrize("group", [4, 8])
+def test_rows16_path(monkeypatch, group):
+    """EMDEE_REC16=1 together with EMDEE_ROWS=G: G lanes per atom over the row-major TAGGED list, 16-byte records
+    (k_pair_forces_rows16). Same bars as test_rec16_path; non-LJ layers keep using the plain rows / default kernels."""
+    monkeypatch.setenv("EMDEE_REC16", "1")
+    monkeypatch.setenv("EMDEE_ROWS", str(group))
+    sp, so = both(lambda lib: cm.lj_sample_system(lib, _lj)[0])
+    assert np.array_equal(sp.pairs(), so.pairs())
+    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
+    assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-11
+    assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-11
+    c = cm.load_fixture("NIST_lj_sample")
+    for s in (sp, so):
+        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
+    for step in range(1, 21):
+        for s in (sp, so):
+            s.md.Options.Compute = (step % 5 == 0)
+            s.boost(1.0, 0.0, 0.5 * c["Dt"])
+            s.displace(1.0, 0.0, c["Dt"])
+            s.boost(1.0, 0.0, 0.5 * c["Dt"])
+    assert sp.md.Builds == so.md.Builds and np.array_equal(sp.pairs(), so.pairs())
+    assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-9
+    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-8
+    sp.finalize(), so.finalize()
+    for variant in ("lj_shifted_force", "softcore_0.7"):   # these go through the plain rows path
+        sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS[variant])[0])
+        assert_state_parity(sp, so)
+        sp.finalize(), so.finalize()

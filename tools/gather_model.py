@@ -86,7 +86,7 @@ def build_layout(R, L, xRc):
 
 def count(gathers):
     """gathers: iterable of int arrays (entry indices read by the active lanes of one warp-gather, lane order)."""
-    n = sectors = lines = quad = pairs = 0
+    n = sectors = lines = quad = pairs = oct16 = 0
     for g, lanes in gathers:
         n += 1
         pairs += len(g)
@@ -96,7 +96,11 @@ def count(gathers):
             sel = g[(lanes >> 2) == q]
             if len(sel):
                 quad += len(np.unique(sel >> 2))
-    return dict(gathers=n, pairs=pairs, sectors=sectors / n, lines=lines / n, quadlines=quad / n,
+        for q in range(4):                                          # 16-byte records: 8-lane groups, 8 records per 128-byte line
+            sel = g[(lanes >> 3) == q]
+            if len(sel):
+                oct16 += len(np.unique(sel >> 3))
+    return dict(gathers=n, pairs=pairs, sectors=sectors / n, lines=lines / n, quadlines=quad / n, oct16=oct16 / n,
                 lanes_active=pairs / (32.0 * n))
 
 
@@ -183,12 +187,15 @@ def main():
         r = count_cluster(cluster_mapping(real, rows, C, args.warps * 4, rng))
         r["quadlines"] = float("nan")
         res[f"cluster {C} atoms x {32 // C:<2d} slots"] = r
+    print("# last column: 16-byte records (EMDEE_REC16): 128-byte line segments summed over 8-lane groups, per pair, relative to the "
+          "default mapping's quad-lines with 32-byte records")
     for name, r in res.items():
         per_pair = {k: r[k] / (32 * r["lanes_active"]) for k in ("sectors", "lines", "quadlines")}
         bp = {k: base[k] / (32 * base["lanes_active"]) for k in ("sectors", "lines", "quadlines")}
         print(f"{name:28s} sectors {r['sectors']:5.1f}  lines {r['lines']:5.1f}  quad-lines {r['quadlines']:5.1f}  "
               f"active {100 * r['lanes_active']:4.0f}%   per pair vs default: sectors x{per_pair['sectors'] / bp['sectors']:.2f} "
-              f"lines x{per_pair['lines'] / bp['lines']:.2f} quad-lines x{per_pair['quadlines'] / bp['quadlines']:.2f}")
+              f"lines x{per_pair['lines'] / bp['lines']:.2f} quad-lines x{per_pair['quadlines'] / bp['quadlines']:.2f}"
+              + (f"   rec16 oct-lines {r['oct16']:5.1f} x{r['oct16'] / (32 * r['lanes_active']) / bp['quadlines']:.2f}" if 'oct16' in r else ""))
 
 
 if __name__ == "__main__":

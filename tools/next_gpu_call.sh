@@ -16,6 +16,9 @@ for g in 4 8 16 32; do
 done
 EMDEE_CLUSTER2=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_cluster2.json 2> gpurun_out/bench_cluster2.err
 EMDEE_REC16=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_rec16.json 2> gpurun_out/bench_rec16.err
+for g in 4 8; do
+  EMDEE_REC16=1 EMDEE_ROWS=$g timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_rows16_$g.json 2> gpurun_out/bench_rows16_$g.err
+done
 EMDEE_TILESCHED=1 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_tilesched.json 2> gpurun_out/bench_tilesched.err
 for m in 1 2; do
   EMDEE_TEX=$m timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_tex$m.json 2> gpurun_out/bench_tex$m.err
@@ -25,6 +28,7 @@ NCU="ncu --set full --clock-control none --import-source on -s 30 -c 1"
 timeout 300 $NCU -k regex:k_pair_forces -o gpurun_out/r2a_force_default python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
 EMDEE_ROWS=8 timeout 300 $NCU -k regex:k_pair_forces_rows -o gpurun_out/r2a_force_rows8 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
 EMDEE_TEX=2 timeout 300 $NCU -k regex:k_pair_forces_tex -o gpurun_out/r2a_force_tex2 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
+EMDEE_REC16=1 EMDEE_ROWS=8 timeout 300 $NCU -k regex:k_pair_forces_rows16 -o gpurun_out/r2a_force_rows16_8 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
 EMDEE_REC16=1 timeout 300 $NCU -k regex:k_pair_forces_rec16 -o gpurun_out/r2a_force_rec16 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
 EMDEE_TILESCHED=1 timeout 300 $NCU -k regex:k_pair_forces_sched -o gpurun_out/r2a_force_sched python bench.py --steps 30 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
 for f in gpurun_out/r2a_force_*.ncu-rep; do python tools/ncu_summary.py "$f" > "${f%.ncu-rep}.txt" 2>&1; done
