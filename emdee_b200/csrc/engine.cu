@@ -1004,7 +1004,8 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       stats_.launches += 1;
     }
     // ---- compact records: tagged copy of the list (see k_pair_forces_rec16) ---------------------------------------------
-    s.use_rec16 = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.nt == 1 && std::getenv("EMDEE_REC16") != nullptr;
+    s.use_rec16 = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.nt == 1 && s.world == 1 &&   // (cell origins ignore the slab offset z0)
+                  std::getenv("EMDEE_REC16") != nullptr;
     if (s.use_rec16) {
       if (Next >= (1 << REC16_INDEX_BITS)) fatal("neighbor list handling", "EMDEE_REC16 supports at most 2^25 sorted entries");
       s.taggedNbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
