@@ -21,7 +21,7 @@ import test_zz_rdf as t_rdf
 import test_zzz_bonded as t_bd
 import test_zzz_config_c1 as t_c1
 import test_zzz_ewald as t_ew
-import test_zzz_phase_space as t_ps
+import test_zzzz_phase_space as t_ps
 import test_zzz_rigid_bodies as t_rb
 import test_zz_single_type_coulomb as t_stc
 
