@@ -74,7 +74,8 @@ def test_ewald_forces_are_the_gradient_of_the_total_energy():
 
 
 def _water(lib, mode):
-    """216 SPC/E waters cut from the NIST sample into a smaller periodic box is not periodic-safe; use the full sample."""
+    """The NIST SPC/E sample (750 waters) with coul_long + kspace_ewald(1e-4): waters as rigid bodies ("rigid"), or as free
+    atoms tied by bond / angle structures with `none` models ("structures")."""
     c = cm.load_fixture("NIST_spce_sample")
     N = c["N"]
     mol = c["molecule"]
