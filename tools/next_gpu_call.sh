@@ -4,7 +4,7 @@
 # 1. gather-cost microbenchmark (decides between the layouts discussed in DESIGN.md section 5)
 # 2. parity of the unconfirmed opt-in paths (EMDEE_ROWS, EMDEE_CLUSTER2), of the box-rescale scenario and of the
 #    kernels written after the last GPU session (rigid bodies, verlet_step, bonded, Ewald, memory_address, sharing)
-# 3. LJ-1M bench: default path vs EMDEE_ROWS=8/16/32 vs EMDEE_CLUSTER2=1 vs EMDEE_TEX=1/2 (texture-pipe gathers) vs EMDEE_REC16=1 (16-byte records) vs EMDEE_TILESCHED=1
+# 3. LJ-1M bench + one ncu capture each: default path vs EMDEE_ROWS=4/8/16/32 vs EMDEE_CLUSTER2=1 vs EMDEE_TEX=1/2 (texture-pipe gathers) vs EMDEE_REC16=1 (16-byte records; also with EMDEE_ROWS=4/8) vs EMDEE_TILESCHED=1; SPC/E line with and without EMDEE_TYPED=1
 set -u
 mkdir -p gpurun_out
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lsu_probe tools/lsu_probe.cu && timeout 120 /tmp/lsu_probe > gpurun_out/lsu_probe.txt 2>&1
