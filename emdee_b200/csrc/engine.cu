@@ -1068,7 +1068,10 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     return rebuild;
   }
   const int Next = s.Next;
-  k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
+  // (the compact-record experiment keeps its own fixed-point records and never reads `pos`: skip the refresh there)
+  const bool rec16_layer = s.use_rec16 && lt.pair[0].model.kind == nb::K_PAIR_LJ_CUT && lt.pair[0].model.modifier == nb::M_NONE &&
+                           !(s.any_charged && lt.pair[0].coulomb);
+  if (!rec16_layer) k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
   ForceArgs a;
   a.Next = Next; a.cap = s.cap; a.nt = s.nt;
   a.Rc2s = (lt.useInRc ? s.InRcSq : s.RcSq) * invL2;
