@@ -14,7 +14,7 @@ from test_gpu_parity import both
 pytestmark = pytest.mark.gpu
 
 
-def testfortran_system(lib, N, seed=86245, rho=0.88, Temp=2.0):
+def _make_testfortran_system(lib, N, seed=86245, rho=0.88, Temp=2.0):
     L = (N / rho) ** (1.0 / 3.0)
     Nd = int(np.ceil(N ** (1.0 / 3.0) - 1e-9))
     m = np.arange(N)
@@ -42,7 +42,7 @@ def testfortran_system(lib, N, seed=86245, rho=0.88, Temp=2.0):
 def test_testfortran_data_inp():
     N = int(os.environ.get("EMDEE_TEST_C1_ATOMS", "10000"))
     nsteps, nprop = (100, 50) if N == 10000 else (20, 10)
-    sp, so = both(lambda lib: testfortran_system(lib, N))
+    sp, so = both(lambda lib: _make_testfortran_system(lib, N))
     assert np.array_equal(sp.pairs(), so.pairs())
     assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
     assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-12
