@@ -125,6 +125,7 @@ ABI_EXT_PRODUCT = {
     "EmDeeX_stats": (None, [tEmDee, C.POINTER(tEmDeeXStats)]),
     "EmDeeX_set_kernel_timing": (None, [tEmDee, C.c_int]),
     "EmDeeX_synchronize": (None, [tEmDee]),
+    "EmDeeX_tune": (None, [tEmDee, C.c_char_p, C.c_int]),
     "EmDeeX_stream": (C.c_void_p, [tEmDee]),
     "EmDeeX_measure_fp64_tflops": (C.c_double, []),
     "EmDeeX_comm_unique_id": (None, [C.c_char_p]),

@@ -1364,6 +1364,7 @@ void EmDeeX_stats(tEmDee md, tEmDeeXStats* out) {
 }
 void EmDeeX_set_kernel_timing(tEmDee md, int enabled) { sys(md)->engine->set_kernel_timing(enabled != 0); }
 void EmDeeX_synchronize(tEmDee md) { sys(md)->engine->synchronize(); }
+void EmDeeX_tune(tEmDee md, const char* knob, int value) { sys(md)->engine->tune(knob, value); }
 void* EmDeeX_stream(tEmDee md) { return sys(md)->engine->stream_handle(); }
 double EmDeeX_measure_fp64_tflops(void) { return emdee::measure_fp64_fma_tflops(); }
 void EmDeeX_comm_unique_id(char* out128) { emdee::comm_unique_id(out128); }

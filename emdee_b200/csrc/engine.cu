@@ -36,6 +36,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -45,7 +46,6 @@
 #include "engine_common.cuh"
 #include "engine_list.cuh"
 #include "engine_force.cuh"
-#include "engine_brick.cuh"
 #include "engine_dynamics.cuh"
 #include "engine_bodies.cuh"
 #include "engine_bonded.cuh"
@@ -87,45 +87,10 @@ struct Engine::Impl {
   size_t scanTmpBytes = 0;
   bool list_valid = false;
 
-  // duo path: union rows of consecutive entry pairs
-  bool use_duos = false;
-  int cap2 = 0;
-  int rows_group = 0;   // EMDEE_ROWS: lanes per atom of the rows path (0 = off)
-  bool use_cluster2 = false;   // EMDEE_CLUSTER2: warp-per-duo kernel over the row-major union rows
-  int rows_pitch = 0;
-  DBuf<int> rowsNbr;
-  DBuf<unsigned int> duoNbr;
-  DBuf<int> duoCount;
-
-  // compact-record path (EMDEE_REC16, opt-in experiment): 16-byte fixed-point positions + cell-tagged copy of the list
-  bool use_rec16 = false;
-  DBuf<Rec16> rec16;
-  DBuf<unsigned int> taggedNbr;
-  DBuf<int> rowsTagged;            // row-major copy of the tagged list (EMDEE_REC16 together with EMDEE_ROWS)
-
-  // tile schedule (EMDEE_TILESCHED, opt-in experiment): brick-ordered permutation of the list tiles
-  bool use_sched = false;
-  int ntiles = 0;
-  DBuf<unsigned int> schedKeys, schedKeysOut;
-  DBuf<int> schedTiles, tileOrder;
-
   // typed path (EMDEE_TYPED, opt-in experiment): compact per-layer tables, built on first use
   std::vector<DBuf<TypedEntry>> ttabs;
   std::vector<int> typedState;     // per layer: 0 = not examined, 1 = eligible, -1 = not eligible
   std::vector<int> typedPM;
-
-  // texture path (EMDEE_TEX, opt-in experiment): texture object over `pos`
-  int tex_mode = 0;
-  cudaTextureObject_t posTex = 0;
-  const double4* posTexBase = nullptr;
-  size_t posTexCount = 0;
-
-  // brick path (single-type systems): per-brick descriptors and the 16-bit brick-local list
-  bool use_bricks = false;
-  BrickGrid bgrid{0, 0, 0, 0, 0};
-  int nbricks = 0, Bmax = 0, brick_threads = 0;
-  DBuf<BrickDesc> bdesc;
-  DBuf<unsigned short> nbr16;
 
   // multi-GPU (one rank per GPU, z-slabs): NCCL is loaded lazily, only when EmDeeX_comm_init is called
   int rank = 0, world = 1;
@@ -168,6 +133,41 @@ struct Engine::Impl {
   // EmDee_memory_address / EmDee_share_phase_space: coordinates may change behind the engine's back
   bool exposed = false;            // a raw pointer to R, P or F was handed out: every call ends with a stream sync
   bool foreign_R = false;          // R is written by the client or by another system: never trust the cached criterion
+
+  // environment switches, read once at construction (nothing on the per-step path calls getenv)
+  bool env_debug = false, env_profile = false, env_no_migrate = false;
+  // developer knobs (EmDeeX_tune; tools/force_lab.py): force-kernel variant and L1/shared carveout of the plain-LJ kernel
+  int tune_variant = 0, tune_carveout = -1;
+
+  // host-visible results: pinned slots the last block of a reducing kernel writes; the host spins on the sequence number
+  HostSlot* slots = nullptr;
+  unsigned long long slot_seq[NSLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long next_seq(int slot) { return ++slot_seq[slot]; }
+  void wait_slot(int slot) {
+    const volatile unsigned long long* flag = &slots[slot].seq;
+    const unsigned long long want = slot_seq[slot];
+    for (unsigned int spins = 1; *flag != want; ++spins) {
+      if ((spins & 0xffffu) == 0u) {   // a kernel that died would leave us spinning: ask the runtime now and then
+        cudaError_t err = cudaStreamQuery(stream);
+        if (err != cudaSuccess && err != cudaErrorNotReady) {
+          std::fprintf(stderr, "Error in CUDA runtime: %s (while waiting for a kernel result).\n", cudaGetErrorString(err));
+          std::exit(1);
+        }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+
+  // non-intrusive kernel timing (EmDeeX_set_kernel_timing): event pairs in a ring, harvested when the ring wraps or when
+  // the statistics are read, never by a synchronisation on the step path
+  static constexpr int NTIMERS = 64;
+  struct Timer { cudaEvent_t a = nullptr, b = nullptr; int kind = -1; };
+  Timer timers[NTIMERS];
+  int timer_head = 0, last_force_timer = -1;
+  double timed_ms[2] = {0.0, 0.0};   // [0] force kernel, [1] list-build kernel
 
   // reductions
   DBuf<MaxNext> chkPartial;
@@ -296,6 +296,11 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.chkPartial.ensure(nblocks(natoms));
   s.partial.ensure((size_t)nblocks(natoms) * 5);
   CUDA_CHECK(cudaMallocHost(&s.h_scalars, 16 * sizeof(double)));
+  CUDA_CHECK(cudaHostAlloc(&s.slots, NSLOTS * sizeof(HostSlot), cudaHostAllocMapped | cudaHostAllocPortable));
+  std::memset(s.slots, 0, NSLOTS * sizeof(HostSlot));
+  s.env_debug = std::getenv("EMDEE_DEBUG") != nullptr;
+  s.env_profile = std::getenv("EMDEE_PROFILE") != nullptr;
+  s.env_no_migrate = s.env_no_migrate;
   CUDA_CHECK(cudaEventCreate(&s.ev0));
   CUDA_CHECK(cudaEventCreate(&s.ev1));
   CUDA_CHECK(cudaEventCreateWithFlags(&s.check_event, cudaEventDisableTiming));
@@ -309,7 +314,7 @@ static inline double wall_now() {
 Engine::~Engine() {
   Impl& s = *d_;
   cudaDeviceSynchronize();
-  if (std::getenv("EMDEE_PROFILE") != nullptr)
+  if (s.env_profile)
     std::fprintf(stderr, "[emdee profile] host ms per call: check %.3f (n=%lld) rebuild %.3f (n=%lld) force %.3f boost %.3f (n=%lld) displace %.3f (n=%lld)\n",
                  1e3 * s.t_check / std::max(1LL, s.n_force), s.n_force, 1e3 * s.t_rebuild / std::max(1LL, s.n_rebuild), s.n_rebuild,
                  1e3 * s.t_force / std::max(1LL, s.n_force), 1e3 * s.t_boost / std::max(1LL, s.n_boost), s.n_boost,
@@ -319,13 +324,10 @@ Engine::~Engine() {
   s.interact.release();
   for (auto& t : s.tabs) t.release();
   for (auto& t : s.ttabs) t.release();
-  s.schedKeys.release(); s.schedKeysOut.release(); s.schedTiles.release(); s.tileOrder.release();
-  s.rec16.release(); s.taggedNbr.release(); s.rowsTagged.release();
   s.Rs.release(); s.sRs.release(); s.sPosF.release(); s.atomCell.release(); s.atomFloor.release();
   s.cellCount.release(); s.cellStart.release(); s.cellFill.release(); s.slotAtom.release(); s.slotImg.release();
   s.slotCell.release(); s.sMeta.release(); s.sCell.release(); s.sType.release(); s.sBody.release(); s.nbr.release();
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
-  s.bdesc.release(); s.nbr16.release(); s.duoNbr.release(); s.duoCount.release(); s.rowsNbr.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
   s.known.release(); s.migCounts.release();
@@ -335,11 +337,15 @@ Engine::~Engine() {
   s.bScalars.release(); s.shR0.release(); s.shQ0.release(); s.shS0.release(); s.freeMask.release(); s.ownedFree.release();
   if (s.h_bscalars) cudaFreeHost(s.h_bscalars);
   for (int k = 0; k < 2; ++k) { s.migList[k].release(); s.migSend[k].release(); s.migRecv[k].release(); }
-  if (s.posTex) cudaDestroyTextureObject(s.posTex);
   if (s.h_mi) cudaFreeHost(s.h_mi);
   if (s.comm) nccl().CommDestroy(s.comm);
   s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release(); s.tickets.release();
   if (s.h_scalars) cudaFreeHost(s.h_scalars);
+  if (s.slots) cudaFreeHost(s.slots);
+  for (auto& t : s.timers) {
+    if (t.a) cudaEventDestroy(t.a);
+    if (t.b) cudaEventDestroy(t.b);
+  }
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
   if (s.check_event) cudaEventDestroy(s.check_event);
@@ -405,7 +411,7 @@ void build_halo_lists(Engine::Impl& s) {
   int h[4];
   CUDA_CHECK(cudaMemcpyAsync(h, s.selCount.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
-  if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee r%d] halo lists: send up %d dn %d, recv below %d above %d\n", s.rank, h[0], h[1], h[2], h[3]);
+  if (s.env_debug) std::fprintf(stderr, "[emdee r%d] halo lists: send up %d dn %d, recv below %d above %d\n", s.rank, h[0], h[1], h[2], h[3]);
   for (int k = 0; k < 4; ++k) {
     s.haloCount[k] = h[k];
     s.haloBuf[k].ensure(3 * (size_t)h[k] + 8, 1.2);
@@ -470,7 +476,7 @@ void migrate(Engine::Impl& s, double Lbox) {
   c[1] = all[2 * s.rank + 1];   // what I send down
   c[2] = all[2 * dn];           // what the rank below sends up = what arrives from below
   c[3] = all[2 * up + 1];       // what the rank above sends down = what arrives from above
-  if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee r%d] migrate: send up %d dn %d, recv from-below %d from-above %d\n", s.rank, c[0], c[1], c[2], c[3]);
+  if (s.env_debug) std::fprintf(stderr, "[emdee r%d] migrate: send up %d dn %d, recv from-below %d from-above %d\n", s.rank, c[0], c[1], c[2], c[3]);
   for (int k = 0; k < 2; ++k) {
     s.migSend[k].ensure(7 * (size_t)c[k] + 8, 1.2);
     s.migRecv[k].ensure(7 * (size_t)c[2 + k] + 8, 1.2);
@@ -590,6 +596,11 @@ void Engine::download_forces(int layer0, double* F) {
   CUDA_CHECK(cudaMemcpy(F, d_->F.p + (size_t)layer0 * 3 * d_->N, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
+void Engine::tune(const char* knob, int value) {
+  if (std::strcmp(knob, "force_variant") == 0) d_->tune_variant = value;
+  else if (std::strcmp(knob, "carveout") == 0) d_->tune_carveout = value;
+  else fatal("tuning", "unknown knob");
+}
 void* Engine::stream_handle() { return (void*)d_->stream; }
 
 // ---- force-kernel dispatch ---------------------------------------------------------------------
@@ -606,73 +617,53 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
   else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false, UNROLL, THREADS, MINBLOCKS><<<grid, THREADS, smem, st>>>(a);
 }
 
-template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR>
-void launch_force_duo(const ForceArgs& a, int cap2, const unsigned int* duoNbr, const int* duoCount, bool compute, int grid,
-                      size_t smem, cudaStream_t st) {
-  if (compute) k_pair_forces_duo<PK, PM, CK, CM, SINGLE, NEED_INVR, true><<<grid, TPB, smem, st>>>(a, cap2, duoNbr, duoCount);
-  else k_pair_forces_duo<PK, PM, CK, CM, SINGLE, NEED_INVR, false><<<grid, TPB, smem, st>>>(a, cap2, duoNbr, duoCount);
-}
+// Plain single-type Lennard-Jones: the benchmark kernel. Variant 0 is what ships; the others exist for tools/force_lab.py
+// (EmDeeX_tune "force_variant" / "carveout"), which times them back to back on one resident system.
+//   columns: UNROLL, THREADS, MINBLOCKS, index-stream load, position-gather load, PROBE
+#define EMDEE_LJ_VARIANTS(X)                                  \
+  X(0, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0)                      \
+  X(1, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
+  X(2, 6, 512, 2, LD_NO_ALLOCATE, LD_EVICT_LAST, 0)           \
+  X(3, 6, 512, 2, LD_PLAIN, LD_PLAIN, 1)                      \
+  X(4, 6, 512, 2, LD_PLAIN, LD_PLAIN, 2)                      \
+  X(5, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 1)                \
+  X(6, 4, 256, 4, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
+  X(7, 8, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
+  X(8, 6, 1024, 1, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
+  X(9, 3, 256, 5, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
+  X(10, 2, 128, 8, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
+  X(11, 6, 256, 4, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
+  X(12, 4, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
+  X(13, 6, 512, 2, LD_EVICT_FIRST, LD_PLAIN, 0)               \
+  X(14, 6, 512, 2, LD_EVICT_FIRST, LD_EVICT_LAST, 0)          \
+  X(15, 3, 128, 10, LD_NO_ALLOCATE, LD_PLAIN, 0)              \
+  X(16, 6, 128, 8, LD_NO_ALLOCATE, LD_PLAIN, 0)
 
-template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, int UNROLL>
-void launch_force_rows(ForceArgs& a, DBuf<double>& partial, int group, int pitch, const int* rows, bool compute, size_t smem,
-                       cudaStream_t st) {
-  const long long warps = ((long long)a.Next * group + 31) / 32;   // 32/group atoms per warp
-  const int grid = (int)((warps + 7) / 8);                         // 8 warps per block
-  partial.ensure((size_t)grid * 5);
-  a.partial = partial.p;
-#define EMDEE_ROWS_CASE(GG)                                                                                               \
-  if (group == GG) {                                                                                                      \
-    if (compute) k_pair_forces_rows<PK, PM, CK, CM, SINGLE, NEED_INVR, true, GG, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows); \
-    else k_pair_forces_rows<PK, PM, CK, CM, SINGLE, NEED_INVR, false, GG, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows);       \
-  }
-  EMDEE_ROWS_CASE(4)
-  EMDEE_ROWS_CASE(8)
-  EMDEE_ROWS_CASE(16)
-  EMDEE_ROWS_CASE(32)
-#undef EMDEE_ROWS_CASE
-}
-
-template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, int UNROLL>
-void launch_force_cluster2(ForceArgs& a, DBuf<double>& partial, int pitch, const unsigned int* rows, const int* duoCount,
-                           bool compute, size_t smem, cudaStream_t st) {
-  const long long nduo = ((long long)a.Next + 1) / 2;   // one warp per duo, 8 warps per block
-  const int grid = (int)((nduo + 7) / 8);
-  partial.ensure((size_t)grid * 5);
-  a.partial = partial.p;
-  if (compute) k_pair_forces_cluster2<PK, PM, CK, CM, SINGLE, NEED_INVR, true, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows, duoCount);
-  else k_pair_forces_cluster2<PK, PM, CK, CM, SINGLE, NEED_INVR, false, UNROLL><<<grid, 256, smem, st>>>(a, pitch, rows, duoCount);
-}
-
-template <int PK, int PM, int CK, int CM, bool NEED_INVR>
-void launch_force_brick(const ForceArgs& a, const BrickArgs& k, bool compute, int grid, int threads, size_t smem,
-                        cudaStream_t st) {
-  if (compute) k_pair_forces_brick<PK, PM, CK, CM, NEED_INVR, true><<<grid, threads, smem, st>>>(a, k);
-  else k_pair_forces_brick<PK, PM, CK, CM, NEED_INVR, false><<<grid, threads, smem, st>>>(a, k);
-}
-
-template <class K>
-void allow_big_smem(K kernel, size_t bytes) {
-  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-}
-
-void configure_brick_kernels() {
-  static bool done = false;
-  if (done) return;
-  done = true;
+void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
-  const size_t fb = (size_t)BRICK_SMAX * sizeof(double4), bb = (size_t)BRICK_SMAX * sizeof(float4);
-  allow_big_smem(k_build_list_brick, bb);
-  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, false, true>, fb);
-  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, false, false>, fb);
-  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true>, fb);
-  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, false>, fb);
-  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>, fb);
-  allow_big_smem(k_pair_forces_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, false>, fb);
-  allow_big_smem(k_pair_forces_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true, true>, fb);
-  allow_big_smem(k_pair_forces_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true, false>, fb);
+  switch (s.tune_variant) {
+#define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR)                                                                          \
+    case ID: {                                                                                                             \
+      const int grid = nblocks(a.Next, TH);                                                                                \
+      s.partial.ensure((size_t)grid * 5);                                                                                  \
+      a.partial = s.partial.p;                                                                                             \
+      auto kt = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, true, UN, TH, MB, LL, PL, PR>;       \
+      auto kf = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, false, UN, TH, MB, LL, PL, PR>;      \
+      if (s.tune_carveout >= 0) {                                                                                          \
+        CUDA_CHECK(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, s.tune_carveout));             \
+        CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, s.tune_carveout));             \
+      }                                                                                                                    \
+      if (compute) kt<<<grid, TH, 0, s.stream>>>(a);                                                                       \
+      else kf<<<grid, TH, 0, s.stream>>>(a);                                                                               \
+      break;                                                                                                               \
+    }
+    EMDEE_LJ_VARIANTS(EMDEE_LJ_CASE)
+#undef EMDEE_LJ_CASE
+    default: fatal("force kernel selection", "unknown force_variant");
+  }
 }
 
-// ---- typed path (EMDEE_TYPED=1): eligibility + compact table of one layer ----------------------------------------
+// ---- typed path (k_pair_forces_typed): eligibility + compact table of one layer ----------------------------------------
 // eligible: every pair entry is pair_none or pair_lj_cut, all LJ entries carry the same modifier (none or shifted_force)
 bool build_typed_table(const LayerTable& lt, std::vector<TypedEntry>& out, int& pm) {
   pm = -1;
@@ -730,7 +721,7 @@ bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEnt
   }
 }
 
-// opt-in typed path (EMDEE_TYPED=1): builds the layer's compact table on first use and launches k_pair_forces_typed.
+// typed path: builds the layer's compact table on first use and launches k_pair_forces_typed.
 // Returns false (nothing launched) when the layer is not eligible.
 bool try_typed_path(Engine::Impl& s, int layer0, const LayerTable& lt, int ck, ForceArgs& a, bool compute) {
   if (s.typedState[layer0] == 0) {
@@ -742,7 +733,7 @@ bool try_typed_path(Engine::Impl& s, int layer0, const LayerTable& lt, int ck, F
       CUDA_CHECK(cudaStreamSynchronize(s.stream));   // `tt` is a local
       s.typedState[layer0] = 1;
       s.typedPM[layer0] = pmod;
-      if (std::getenv("EMDEE_DEBUG"))
+      if (s.env_debug)
         std::fprintf(stderr, "[emdee] typed path: layer %d eligible (modifier %d, coulomb kind %d, %d types)\n", layer0, pmod, ck, s.nt);
     } else {
       s.typedState[layer0] = -1;
@@ -772,6 +763,43 @@ void build_band(double xRc2s, int M, float& accept, float& reject) {
 
 }  // namespace
 
+// Kernel timing without a synchronisation on the step path: an event pair from the ring brackets the launch; a pair is
+// read back (it finished long ago) when its slot is reused, and all pending pairs when the statistics are requested.
+void Engine::timer_harvest(int idx) {
+  Impl& s = *d_;
+  Impl::Timer& t = s.timers[idx];
+  if (t.kind < 0) return;
+  CUDA_CHECK(cudaEventSynchronize(t.b));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, t.a, t.b));
+  s.timed_ms[t.kind] += ms;
+  t.kind = -1;
+}
+int Engine::timer_begin(int kind) {
+  Impl& s = *d_;
+  if (!timing_) return -1;
+  const int idx = s.timer_head;
+  s.timer_head = (s.timer_head + 1) % Impl::NTIMERS;
+  timer_harvest(idx);
+  Impl::Timer& t = s.timers[idx];
+  if (t.a == nullptr) {
+    CUDA_CHECK(cudaEventCreate(&t.a));
+    CUDA_CHECK(cudaEventCreate(&t.b));
+  }
+  t.kind = kind;
+  CUDA_CHECK(cudaEventRecord(t.a, s.stream));
+  return idx;
+}
+void Engine::timer_end(int idx) {
+  if (idx >= 0) CUDA_CHECK(cudaEventRecord(d_->timers[idx].b, d_->stream));
+}
+EngineStats Engine::stats() {
+  for (int k = 0; k < Impl::NTIMERS; ++k) timer_harvest(k);
+  stats_.force_ms = d_->timed_ms[0];
+  stats_.build_ms = d_->timed_ms[1];
+  return stats_;
+}
+
 bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars& out, double& neighbor_seconds) {
   Impl& s = *d_;
   const int N = s.N;
@@ -781,31 +809,89 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   const double tp0 = wall_now();
   if (s.foreign_R) s.check_cached = false;
   // ---- K0: rebuild trigger (reference handle_neighbor_lists) -----------------------------------
-  bool rebuild;
+  // Single GPU, coordinates moved by k_displace: the criterion of the current coordinates is (or will be) in
+  // scalars[8] on the device and the host does not wait for it -- the pair kernel is launched SPECULATIVELY, checks the
+  // criterion itself and reports "rebuild needed" instead of forces when it fires (about one step in seven at LJ-1M).
+  bool rebuild = false, speculative = false;
   if (s.world > 1 && s.owned_valid) {
     halo_exchange(s);
     rebuild = rebuild_needed_dist(s);
-    if (std::getenv("EMDEE_DEBUG")) std::fprintf(stderr, "[emdee r%d] compute_forces: rebuild=%d all_known=%d\n", s.rank, (int)rebuild, (int)s.all_known);
+    if (s.env_debug) std::fprintf(stderr, "[emdee r%d] compute_forces: rebuild=%d all_known=%d\n", s.rank, (int)rebuild, (int)s.all_known);
     stats_.launches += 1;
+  } else if (s.check_cached && s.list_valid && s.world == 1) {
+    speculative = true;
   } else {
-    if (s.check_cached) {
-      CUDA_CHECK(cudaEventSynchronize(s.check_event));   // evaluated by k_displace when the atoms moved
-    } else {
-      k_displacement_check<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p, s.tickets.p + 2,
-                                                             s.scalars.p + 8);
-      stats_.launches += 1;
-      CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-      CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
-      CUDA_CHECK(cudaEventSynchronize(s.check_event));
-      s.check_cached = true;   // stays valid until the coordinates or R0 change
-    }
-    rebuild = s.h_scalars[8] > s.skinSq;
+    const unsigned long long seq = s.next_seq(SLOT_CHECK);
+    k_displacement_check<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p, s.tickets.p + 2,
+                                                           s.scalars.p + 8, s.slots + SLOT_CHECK, seq);
+    stats_.launches += 1;
+    s.wait_slot(SLOT_CHECK);
+    s.check_cached = true;   // scalars[8] stays valid until the coordinates or R0 change
+    rebuild = s.slots[SLOT_CHECK].v[0] > s.skinSq;
   }
   const double tp1 = wall_now();
   s.t_check += tp1 - tp0;
+  if (rebuild) rebuild_list(Lbox);
+  neighbor_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  const double tp2 = wall_now();
+  if (rebuild) { s.t_rebuild += tp2 - tp1; s.n_rebuild += 1; }
 
+  // ---- pair loop -------------------------------------------------------------------------------
+  if (!lt.pairs_exist) {
+    if (speculative) {   // no pair kernel to carry the speculation: ask for the criterion now
+      CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+      CUDA_CHECK(cudaStreamSynchronize(s.stream));
+      if (s.h_scalars[8] > s.skinSq) {
+        rebuild = true;
+        rebuild_list(Lbox);
+      }
+    }
+    CUDA_CHECK(cudaMemsetAsync(s.F.p + (size_t)layer0 * 3 * N, 0, 3 * (size_t)N * sizeof(double), s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    out = ForceScalars();
+    return rebuild;
+  }
+  launch_pair_kernel(layer0, compute, Lbox, speculative);
+  if (s.world > 1) {
+    NCCL_CHECK(nccl().AllReduce(s.scalars.p, s.scalars.p, 5, ncclDouble, ncclSum, s.comm, s.stream));
+    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars, s.scalars.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    CUDA_CHECK(cudaGetLastError());
+    for (int q = 0; q < 5; ++q) s.slots[SLOT_FORCE].v[q] = s.h_scalars[q];
+  } else {
+    s.wait_slot(SLOT_FORCE);
+    if (speculative && s.slots[SLOT_FORCE].v[SLOT_STATUS] != 0.0) {   // the criterion fired: rebuild, then the real launch
+      const double tr0 = wall_now();
+      auto t_rb = std::chrono::steady_clock::now();
+      rebuild = true;
+      if (s.last_force_timer >= 0) s.timers[s.last_force_timer].kind = -1;   // the aborted launch is not a force evaluation
+      stats_.force_launches -= 1;
+      rebuild_list(Lbox);
+      neighbor_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_rb).count();
+      s.t_rebuild += wall_now() - tr0;
+      s.n_rebuild += 1;
+      launch_pair_kernel(layer0, compute, Lbox, false);
+      s.wait_slot(SLOT_FORCE);
+    }
+  }
+  s.t_force += wall_now() - tp2;
+  s.n_force += 1;
+  const double* v = s.slots[SLOT_FORCE].v;
+  out.Epair = v[0];
+  out.Ecoul = v[1];
+  out.Wpair = v[2];
+  out.Wcoul = v[3];
+  out.Wbody = v[4];
+  return rebuild;
+}
+
+// List rebuild (reference distribute_atoms + build_neighbor_lists); ends with R0 = R and a zero criterion on the device.
+void Engine::rebuild_list(double Lbox) {
+  Impl& s = *d_;
+  const int N = s.N;
   const double invL2 = 1.0 / (Lbox * Lbox);
-  if (rebuild) {
+  {
+
     int M = (int)std::floor(2 * Lbox / s.xRc);
     M = std::max(M, 5);
     if (2 * Lbox / s.xRc < 5.0)
@@ -828,7 +914,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
         s.all_known = true;
         s.p_partial = false;
       }
-      if (s.owned_valid && !s.all_known && std::getenv("EMDEE_NO_MIGRATE") != nullptr) {
+      if (s.owned_valid && !s.all_known && s.env_no_migrate) {
         gather_full(s, s.R.p);   // simpler scheme: re-assemble the full arrays on every rank
         gather_full(s, s.P.p);
         s.all_known = true;
@@ -891,34 +977,6 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       double nbar = (double)N / (Lbox * Lbox * Lbox) * (4.0 / 3.0) * 3.14159265358979323846 * s.xRc * s.xRcSq;
       s.cap = std::max(16, (int)(1.35 * nbar) + 16);
     }
-    // ---- brick decomposition (single-type systems): largest brick whose staged halo fits shared memory ----
-    s.use_bricks = false;
-    if (s.nt == 1 && s.world == 1 && std::getenv("EMDEE_BRICKS") != nullptr) {   // opt-in: measured slower than the global path
-      configure_brick_kernels();
-      const double per_cell = (double)Next / (double)ncell;
-      for (int b = 6; b >= 2 && !s.use_bricks; --b) {
-        if ((b + 4.0) * (b + 4.0) * (b + 4.0) * per_cell > 1.02 * BRICK_SMAX) continue;
-        BrickGrid bg;
-        bg.M = M;
-        bg.Mx = M + 4;
-        bg.nbx = bg.nby = bg.nbz = (M + b - 1) / b;
-        const int nbricks = bg.nbx * bg.nby * bg.nbz;
-        s.bdesc.ensure(nbricks, 1.0);
-        CUDA_CHECK(cudaMemsetAsync(s.flags.p, 0, 4 * sizeof(int), s.stream));
-        k_brick_setup<<<nbricks, TPB, 0, s.stream>>>(bg, s.cellStart.p, s.bdesc.p, s.flags.p);
-        stats_.launches += 1;
-        int hf[4];
-        CUDA_CHECK(cudaMemcpyAsync(hf, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-        CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        if (hf[2] <= BRICK_SMAX && hf[2] < 65536) {
-          s.use_bricks = true;
-          s.bgrid = bg;
-          s.nbricks = nbricks;
-          s.Bmax = ((hf[3] + 31) / 32) * 32;
-          s.brick_threads = std::max(TPB, std::min(BRICK_TPB, s.Bmax));   // >= TPB: grid_finish folds with TPB threads
-        }
-      }
-    }
     BuildArgs b;
     b.Next = Next; b.nt = s.nt; b.g = s.grid; b.all_interact = s.all_interact ? 1 : 0;
     b.xRc2s = s.xRcSq * invL2;
@@ -931,113 +989,22 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     for (;;) {
       CUDA_CHECK(cudaMemsetAsync(s.flags.p, 0, 4 * sizeof(int), s.stream));
       b.cap = s.cap;
-      if (timing_) CUDA_CHECK(cudaEventRecord(s.ev0, s.stream));
-      if (s.use_bricks) {
-        s.nbr16.ensure((size_t)s.nbricks * s.cap * s.Bmax, 1.1);
-        b.nbr = nullptr;
-        BrickArgs k;
-        k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
-        k_build_list_brick<<<s.nbricks, s.brick_threads, (size_t)BRICK_SMAX * sizeof(float4), s.stream>>>(b, k);
-      } else {
-        s.nbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
-        b.nbr = s.nbr.p;
-        // (a warp-per-tile variant with __ballot_sync compaction into shared-memory rows and a transposed
-        // write-out was measured 6x slower at LJ-1M -- serial per-atom dependency chains at ~12 warps/SM --
-        // and removed)
-        k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
-      }
-      if (timing_) CUDA_CHECK(cudaEventRecord(s.ev1, s.stream));
+      s.nbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
+      b.nbr = s.nbr.p;
+      // (a warp-per-tile variant with __ballot_sync compaction into shared-memory rows and a transposed
+      // write-out was measured 6x slower at LJ-1M -- serial per-atom dependency chains at ~12 warps/SM --
+      // and removed)
+      const int tmr = timer_begin(1);
+      k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      timer_end(tmr);
       stats_.launches += 1;
       stats_.build_launches += 1;
       int hflags[4];
       CUDA_CHECK(cudaMemcpyAsync(hflags, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
       CUDA_CHECK(cudaStreamSynchronize(s.stream));
       CUDA_CHECK(cudaGetLastError());
-      if (timing_) {
-        float ms = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
-        stats_.build_ms += ms;
-      }
       if (!hflags[1]) break;
       s.cap = (int)(hflags[0] * 1.15) + 8;   // overflow: regrow to the observed maximum and redo
-    }
-    // ---- duo rows: sorted merge of the rows of entries (2d, 2d+1) ------------------------------------------
-    s.use_duos = !s.use_bricks && std::getenv("EMDEE_DUOS") != nullptr;   // opt-in: fewer LSU wavefronts but more FP64 issue + divergence; measured slower
-    s.use_cluster2 = !s.use_bricks && !s.use_duos && std::getenv("EMDEE_CLUSTER2") != nullptr;   // opt-in, unmeasured
-    if (s.use_duos || s.use_cluster2) {
-      const int nduo = (Next + 1) / 2;
-      const long long dtiles = ((long long)nduo + TILE - 1) / TILE;
-      if (s.cap2 == 0) s.cap2 = (int)(1.45 * s.cap) + 8;
-      s.duoCount.ensure(nduo, 1.1);
-      for (;;) {
-        s.duoNbr.ensure((size_t)dtiles * s.cap2 * TILE, 1.1);
-        CUDA_CHECK(cudaMemsetAsync(s.flags.p, 0, 4 * sizeof(int), s.stream));
-        k_merge_duos<<<nblocks(nduo), TPB, 0, s.stream>>>(Next, s.cap, s.cap2, s.nbr.p, s.nbrCount.p, s.duoNbr.p,
-                                                          s.duoCount.p, s.flags.p);
-        stats_.launches += 1;
-        int hf[4];
-        CUDA_CHECK(cudaMemcpyAsync(hf, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-        CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        if (!hf[3]) break;
-        s.cap2 = (int)(hf[2] * 1.1) + 8;
-      }
-      if (s.use_cluster2) {   // row-major copy of the union rows (one row per duo)
-        s.rows_pitch = (s.cap2 + 7) & ~7;
-        s.rowsNbr.ensure((size_t)nduo * s.rows_pitch, 1.1);
-        const int tgrid = (int)((dtiles + ROWS_TILES_PER_BLOCK - 1) / ROWS_TILES_PER_BLOCK);
-        k_transpose_rows<<<tgrid, 32 * ROWS_TILES_PER_BLOCK, 0, s.stream>>>(nduo, s.cap2, s.rows_pitch,
-                                                                             reinterpret_cast<const int*>(s.duoNbr.p), s.duoCount.p,
-                                                                             s.rowsNbr.p);
-        stats_.launches += 1;
-      }
-    }
-    // ---- rows path: row-major copy of the list -------------------------------------------------------------
-    s.rows_group = 0;
-    if (!s.use_bricks && !s.use_duos && !s.use_cluster2 && std::getenv("EMDEE_ROWS") != nullptr) {   // opt-in experiment (see k_pair_forces_rows)
-      const int g = std::atoi(std::getenv("EMDEE_ROWS"));
-      s.rows_group = (g == 4 || g == 8 || g == 16 || g == 32) ? g : 8;
-      s.rows_pitch = (s.cap + 7) & ~7;   // rows start on 32-byte boundaries
-      s.rowsNbr.ensure((size_t)Next * s.rows_pitch, 1.1);
-      const int tgrid = (int)((ntiles + ROWS_TILES_PER_BLOCK - 1) / ROWS_TILES_PER_BLOCK);
-      k_transpose_rows<<<tgrid, 32 * ROWS_TILES_PER_BLOCK, 0, s.stream>>>(Next, s.cap, s.rows_pitch, s.nbr.p, s.nbrCount.p,
-                                                                           s.rowsNbr.p);
-      stats_.launches += 1;
-    }
-    // ---- compact records: tagged copy of the list (see k_pair_forces_rec16) ---------------------------------------------
-    s.use_rec16 = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.nt == 1 && s.world == 1 &&   // (cell origins ignore the slab offset z0)
-                  std::getenv("EMDEE_REC16") != nullptr;
-    if (s.use_rec16) {
-      if (Next >= (1 << REC16_INDEX_BITS)) fatal("neighbor list handling", "EMDEE_REC16 supports at most 2^25 sorted entries");
-      s.taggedNbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
-      s.rec16.ensure(Next, 1.1);
-      k_tag_list<<<nblocks(Next), TPB, 0, s.stream>>>(Next, s.cap, s.grid.Mx, s.nbr.p, s.nbrCount.p, s.sCell.p, s.taggedNbr.p);
-      stats_.launches += 1;
-      if (s.rows_group != 0) {   // EMDEE_ROWS too: the row-major copy is made from the TAGGED list (see k_pair_forces_rows16)
-        const int tgrid = (int)((ntiles + ROWS_TILES_PER_BLOCK - 1) / ROWS_TILES_PER_BLOCK);
-        s.rowsTagged.ensure((size_t)Next * s.rows_pitch, 1.1);   // its own buffer: other layers may still use the plain rows
-        k_transpose_rows<<<tgrid, 32 * ROWS_TILES_PER_BLOCK, 0, s.stream>>>(Next, s.cap, s.rows_pitch, reinterpret_cast<const int*>(s.taggedNbr.p),
-                                                                             s.nbrCount.p, s.rowsTagged.p);
-        stats_.launches += 1;
-      }
-    }
-    // ---- tile schedule: brick-ordered permutation of the tiles (see k_pair_forces_sched) ----------------------------
-    s.use_sched = !s.use_bricks && !s.use_duos && !s.use_cluster2 && s.rows_group == 0 && s.nt == 1 &&
-                  std::getenv("EMDEE_TILESCHED") != nullptr;
-    if (s.use_sched) {
-      s.ntiles = (int)ntiles;
-      s.schedKeys.ensure(ntiles, 1.1);
-      s.schedKeysOut.ensure(ntiles, 1.1);
-      s.schedTiles.ensure(ntiles, 1.1);
-      s.tileOrder.ensure(ntiles, 1.1);
-      k_tile_keys<<<nblocks(ntiles), TPB, 0, s.stream>>>((int)ntiles, Next, s.grid.Mx, s.sCell.p, s.schedKeys.p, s.schedTiles.p);
-      size_t sortBytes = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, s.schedKeys.p, s.schedKeysOut.p, s.schedTiles.p, s.tileOrder.p, (int)ntiles, 0, 32, s.stream);
-      if (sortBytes > s.scanTmpBytes) {
-        s.scanTmp.ensure(sortBytes);
-        s.scanTmpBytes = sortBytes;
-      }
-      cub::DeviceRadixSort::SortPairs(s.scanTmp.p, sortBytes, s.schedKeys.p, s.schedKeysOut.p, s.schedTiles.p, s.tileOrder.p, (int)ntiles, 0, 32, s.stream);
-      stats_.launches += 2;
     }
     if (s.world > 1) {
       build_halo_lists(s);
@@ -1051,27 +1018,22 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       s.halo_fresh = true;   // migrate() just made every needed position current
     }
     CUDA_CHECK(cudaMemcpyAsync(s.R0.p, s.R.p, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
-    s.h_scalars[8] = 0.0;   // R0 = R: the criterion for the current coordinates is now zero displacement
+    CUDA_CHECK(cudaMemsetAsync(s.scalars.p + 8, 0, sizeof(double), s.stream));   // R0 = R: zero displacement
+    s.check_cached = true;
     s.list_valid = true;
     stats_.cells_per_dim = M;
   }
-  neighbor_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-  const double tp2 = wall_now();
-  if (rebuild) { s.t_rebuild += tp2 - tp1; s.n_rebuild += 1; }
+}
 
-  // ---- pair loop -------------------------------------------------------------------------------
+// Position refresh + pair kernel of one layer. `speculative`: the kernel reads the rebuild criterion itself (see above).
+void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool speculative) {
+  Impl& s = *d_;
+  const int N = s.N;
+  const LayerTable& lt = s.layers[layer0];
+  const double invL2 = 1.0 / (Lbox * Lbox);
   double* Fl = s.F.p + (size_t)layer0 * 3 * N;
-  if (!lt.pairs_exist) {
-    CUDA_CHECK(cudaMemsetAsync(Fl, 0, 3 * (size_t)N * sizeof(double), s.stream));
-    CUDA_CHECK(cudaStreamSynchronize(s.stream));
-    out = ForceScalars();
-    return rebuild;
-  }
   const int Next = s.Next;
-  // (the compact-record experiment keeps its own fixed-point records and never reads `pos`: skip the refresh there)
-  const bool rec16_layer = s.use_rec16 && lt.pair[0].model.kind == nb::K_PAIR_LJ_CUT && lt.pair[0].model.modifier == nb::M_NONE &&
-                           !(s.any_charged && lt.pair[0].coulomb);
-  if (!rec16_layer) k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
+  k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
   ForceArgs a;
   a.Next = Next; a.cap = s.cap; a.nt = s.nt;
   a.Rc2s = (lt.useInRc ? s.InRcSq : s.RcSq) * invL2;
@@ -1083,6 +1045,10 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   a.single = lt.pair[0];
   a.coul = lt.coul;
   a.F = Fl; a.partial = s.partial.p; a.ticket = s.tickets.p; a.out = s.scalars.p;
+  a.crit = speculative ? s.scalars.p + 8 : nullptr;
+  a.skinSq = s.skinSq;
+  a.hs = (s.world > 1) ? nullptr : s.slots + SLOT_FORCE;   // several GPUs: the scalars are all-reduced first
+  a.seq = s.next_seq(SLOT_FORCE);
 
   // classify the layer for kernel selection
   bool uniform = true;
@@ -1096,162 +1062,25 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   const int ck = coul_active ? lt.coul.kind : (int)nb::K_COUL_NONE, cm = lt.coul.modifier;
   const size_t smem_dyn = (s.nt <= MAX_SMEM_TYPES) ? (size_t)s.nt * s.nt * sizeof(PairEntry) : 0;
 
-  if (timing_) CUDA_CHECK(cudaEventRecord(s.ev0, s.stream));
+  const int tmr = timer_begin(0);
   using namespace nb;
   const bool lj_plain = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_NONE && !a.q4_quirk;
   const bool lj_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_SHIFTED_FORCE && ck == K_COUL_NONE && !a.q4_quirk;
   const bool lj_coul_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_SF && cm == M_NONE;
-  if (s.use_bricks) {
-    BrickArgs k;
-    k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
-    const int bgrid = s.nbricks, bt = s.brick_threads;
-    s.partial.ensure((size_t)bgrid * 5);
-    a.partial = s.partial.p;
-    const size_t sm = (size_t)BRICK_SMAX * sizeof(double4);
-    if (lj_plain) launch_force_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, false>(a, k, compute, bgrid, bt, sm, s.stream);
-    else if (lj_sf) launch_force_brick<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true>(a, k, compute, bgrid, bt, sm, s.stream);
-    else if (lj_coul_sf) launch_force_brick<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true>(a, k, compute, bgrid, bt, sm, s.stream);
-    else launch_force_brick<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, true>(a, k, compute, bgrid, bt, sm, s.stream);
-  } else if (s.use_duos) {
-    const int dgrid = nblocks((Next + 1) / 2);
-    s.partial.ensure((size_t)dgrid * 5);
-    a.partial = s.partial.p;
-    if (s.nt == 1 && lj_plain)
-      launch_force_duo<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
-    else if (s.nt == 1 && lj_sf)
-      launch_force_duo<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
-    else if (s.nt == 1 && lj_coul_sf)
-      launch_force_duo<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, 0, s.stream);
-    else
-      launch_force_duo<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true>(a, s.cap2, s.duoNbr.p, s.duoCount.p, compute, dgrid, smem_dyn, s.stream);
-  } else if (s.use_cluster2) {
-    const unsigned int* rows = reinterpret_cast<const unsigned int*>(s.rowsNbr.p);
-    if (s.nt == 1 && lj_plain)
-      launch_force_cluster2<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, 0, s.stream);
-    else if (s.nt == 1 && lj_sf)
-      launch_force_cluster2<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, 0, s.stream);
-    else if (s.nt == 1 && lj_coul_sf)
-      launch_force_cluster2<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, 0, s.stream);
-    else
-      launch_force_cluster2<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, s.rows_pitch, rows, s.duoCount.p, compute, smem_dyn, s.stream);
-  } else if (s.nt == 1 && lj_plain && s.use_rec16 && s.rows_group != 0) {
-    k_refresh_rec16<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.grid.M, s.grid.Mx, s.R.p, s.sMeta.p, s.sCell.p, s.rec16.p);
-    stats_.launches += 1;
-    const int g = s.rows_group;
-    const long long warps = ((long long)a.Next * g + 31) / 32;
-    const int rgrid = (int)((warps + 7) / 8);
-    s.partial.ensure((size_t)rgrid * 5);
-    a.partial = s.partial.p;
-    const unsigned int* trows = reinterpret_cast<const unsigned int*>(s.rowsTagged.p);
-#define EMDEE_ROWS16_CASE(GG)                                                                                                    \
-    if (g == GG) {                                                                                                               \
-      if (compute) k_pair_forces_rows16<true, GG, 3><<<rgrid, 256, 0, s.stream>>>(a, s.grid.M, s.rows_pitch, s.rec16.p, trows);   \
-      else k_pair_forces_rows16<false, GG, 3><<<rgrid, 256, 0, s.stream>>>(a, s.grid.M, s.rows_pitch, s.rec16.p, trows);          \
-    }
-    EMDEE_ROWS16_CASE(4)
-    EMDEE_ROWS16_CASE(8)
-    EMDEE_ROWS16_CASE(16)
-    EMDEE_ROWS16_CASE(32)
-#undef EMDEE_ROWS16_CASE
-  } else if (s.rows_group != 0) {
-    const int* rows = s.rowsNbr.p;
-    const int g = s.rows_group, pitch = s.rows_pitch;
-    if (s.nt == 1 && lj_plain)
-      launch_force_rows<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, 3>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
-    else if (s.nt == 1 && lj_sf)
-      launch_force_rows<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 2>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
-    else if (s.nt == 1 && lj_coul_sf)
-      launch_force_rows<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2>(a, s.partial, g, pitch, rows, compute, 0, s.stream);
-    else
-      launch_force_rows<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 2>(a, s.partial, g, pitch, rows, compute, smem_dyn, s.stream);
-  } else if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && std::getenv("EMDEE_TYPED") != nullptr &&
-             try_typed_path(s, layer0, lt, ck, a, compute)) {
-    // opt-in experiment (see k_pair_forces_typed), launched by try_typed_path; an ineligible layer falls through to the generic kernel
-  } else if (s.nt == 1 && lj_plain && s.use_rec16) {
-    k_refresh_rec16<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.grid.M, s.grid.Mx, s.R.p, s.sMeta.p, s.sCell.p, s.rec16.p);
-    stats_.launches += 1;
-    const int rgrid = nblocks(a.Next, 512);
-    s.partial.ensure((size_t)rgrid * 5);
-    a.partial = s.partial.p;
-    if (compute) k_pair_forces_rec16<true, 6, 512, 2><<<rgrid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
-    else k_pair_forces_rec16<false, 6, 512, 2><<<rgrid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
-  } else if (s.nt == 1 && lj_plain && s.use_sched) {
-    const int sgrid = nblocks((long long)s.ntiles * TILE, 512);
-    s.partial.ensure((size_t)sgrid * 5);
-    a.partial = s.partial.p;
-    if (compute) k_pair_forces_sched<true, 6, 512, 2><<<sgrid, 512, 0, s.stream>>>(a, s.ntiles, s.tileOrder.p);
-    else k_pair_forces_sched<false, 6, 512, 2><<<sgrid, 512, 0, s.stream>>>(a, s.ntiles, s.tileOrder.p);
-  } else if (s.nt == 1 && lj_plain && std::getenv("EMDEE_TEX") != nullptr) {
-    // opt-in experiment (see k_pair_forces_tex): position gathers through the texture front-end of L1TEX
-    s.tex_mode = std::atoi(std::getenv("EMDEE_TEX")) == 2 ? 2 : 1;
-    if (s.posTex == 0 || s.posTexBase != s.pos.p || s.posTexCount != s.pos.n) {
-      if (s.posTex) CUDA_CHECK(cudaDestroyTextureObject(s.posTex));
-      cudaResourceDesc rd;
-      std::memset(&rd, 0, sizeof(rd));
-      rd.resType = cudaResourceTypeLinear;
-      rd.res.linear.devPtr = s.pos.p;
-      rd.res.linear.desc = cudaCreateChannelDesc<int4>();
-      rd.res.linear.sizeInBytes = s.pos.n * sizeof(double4);
-      cudaTextureDesc td;
-      std::memset(&td, 0, sizeof(td));
-      td.readMode = cudaReadModeElementType;
-      CUDA_CHECK(cudaCreateTextureObject(&s.posTex, &rd, &td, nullptr));
-      s.posTexBase = s.pos.p;
-      s.posTexCount = s.pos.n;
-    }
-    const int tgrid = nblocks(a.Next, 512);
-    s.partial.ensure((size_t)tgrid * 5);
-    a.partial = s.partial.p;
-    if (s.tex_mode == 1) {
-      if (compute) k_pair_forces_tex<true, 1, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
-      else k_pair_forces_tex<false, 1, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
-    } else {
-      if (compute) k_pair_forces_tex<true, 2, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
-      else k_pair_forces_tex<false, 2, 6, 512, 2><<<tgrid, 512, 0, s.stream>>>(a, s.posTex);
-    }
-  } else if (s.nt == 1 && lj_plain && compute && std::getenv("EMDEE_FORCE_TUNE") != nullptr) {
-    // tuning hook (bench experiments only): EMDEE_FORCE_TUNE="<variant>"
-    const int v = std::atoi(std::getenv("EMDEE_FORCE_TUNE"));
-#define EMDEE_TUNE_CASE(ID, UN, TH, MB) \
-    if (v == ID) launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, UN, TH, MB>(a, s.partial, true, 0, s.stream);
-    EMDEE_TUNE_CASE(0, 2, 128, 1)
-    EMDEE_TUNE_CASE(1, 4, 256, 4)
-    EMDEE_TUNE_CASE(2, 4, 256, 5)
-    EMDEE_TUNE_CASE(4, 3, 256, 5)
-    EMDEE_TUNE_CASE(5, 6, 256, 4)
-    EMDEE_TUNE_CASE(7, 4, 512, 2)
-    EMDEE_TUNE_CASE(10, 6, 512, 2)
-    EMDEE_TUNE_CASE(12, 8, 512, 2)
-    EMDEE_TUNE_CASE(13, 6, 1024, 1)
-#undef EMDEE_TUNE_CASE
+  if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && try_typed_path(s, layer0, lt, ck, a, compute)) {
+    // several types, every pair model pair_lj_cut (one modifier) or pair_none: k_pair_forces_typed, launched by try_typed_path
   } else if (s.nt == 1 && lj_plain)
-    launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, 6, 512, 2>(a, s.partial, compute, 0, s.stream);
+    launch_lj_plain(s, a, compute);
   else if (s.nt == 1 && lj_sf)
     launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
   else if (s.nt == 1 && lj_coul_sf)
     launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
   else
     launch_force<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 4, 256, 2>(a, s.partial, compute, smem_dyn, s.stream);
-  if (timing_) CUDA_CHECK(cudaEventRecord(s.ev1, s.stream));
+  timer_end(tmr);
+  s.last_force_timer = tmr;
   stats_.launches += 2;
   stats_.force_launches += 1;
-  if (s.world > 1) NCCL_CHECK(nccl().AllReduce(s.scalars.p, s.scalars.p, 5, ncclDouble, ncclSum, s.comm, s.stream));
-  CUDA_CHECK(cudaMemcpyAsync(s.h_scalars, s.scalars.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-  CUDA_CHECK(cudaStreamSynchronize(s.stream));
-  CUDA_CHECK(cudaGetLastError());
-  if (timing_) {
-    float ms = 0;
-    CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
-    stats_.force_ms += ms;
-  }
-  s.t_force += wall_now() - tp2;
-  s.n_force += 1;
-  out.Epair = s.h_scalars[0];
-  out.Ecoul = s.h_scalars[1];
-  out.Wpair = s.h_scalars[2];
-  out.Wcoul = s.h_scalars[3];
-  out.Wbody = s.h_scalars[4];
-  return rebuild;
 }
 
 void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke) {
@@ -1259,12 +1088,17 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
   const double tp0 = wall_now();
   const int grid = nblocks((s.N + APT - 1) / APT);
   const unsigned char* owned = (s.world > 1 && s.owned_valid) ? s.owned.p : nullptr;
+  const bool direct = want_kinetic && owned == nullptr;   // single GPU: the last block writes the sums to the host slot
+  HostSlot* hs = direct ? s.slots + SLOT_KINETIC : nullptr;
+  const unsigned long long seq = direct ? s.next_seq(SLOT_KINETIC) : 0ull;
   k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, s.F.p + (size_t)layer0 * 3 * s.N, s.invMass.p, owned,
-                                      want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10);
+                                      want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10, hs, seq);
   stats_.launches += 1;
-  if (want_kinetic) {
-    if (owned != nullptr)
-      NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
+  if (direct) {
+    s.wait_slot(SLOT_KINETIC);
+    for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
+  } else if (want_kinetic) {
+    NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
     CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.h_scalars[10 + x];
@@ -1286,11 +1120,11 @@ void Engine::displace(double CR, double CP) {
     s.check_cached = false;
     s.all_known = false;   // from now on only owned + halo positions are current on this rank
   } else {
+    // the rebuild criterion of the new coordinates lands in scalars[8] on the device; compute_forces launches the pair
+    // kernel speculatively against it instead of waiting for it here
     k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p, s.chkPartial.p,
                                                    s.tickets.p + 2, s.scalars.p + 8);
     stats_.launches += 1;
-    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_CHECK(cudaEventRecord(s.check_event, s.stream));
     s.check_cached = true;
   }
   if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -1365,7 +1199,7 @@ void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool ro
     const unsigned char* mask = !bodies ? (dist ? s.owned.p : nullptr) : (dist ? s.ownedFree.p : s.freeMask.p);
     const int grid = nblocks((s.N + APT - 1) / APT);
     k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, mask, want_kinetic ? 1 : 0,
-                                        s.partial.p, s.tickets.p + 1, s.scalars.p + 10);
+                                        s.partial.p, s.tickets.p + 1, s.scalars.p + 10, nullptr, 0ull);
     stats_.launches += 1;
     if (dist && want_kinetic)
       NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
@@ -1722,11 +1556,7 @@ void Engine::update_list_stats(int layer0, double Lbox) {
   const double Rc2s = (s.layers[layer0].useInRc ? s.InRcSq : s.RcSq) * invL2;
   CUDA_CHECK(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned long long), s.stream));
   k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
-  if (s.use_bricks) {
-    BrickArgs k;
-    k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
-    k_brick_list_walk<<<s.nbricks, TPB, 0, s.stream>>>(k, 1, s.nbrCount.p, s.sMeta.p, s.pos.p, Rc2s, nullptr, 0, s.counter.p);
-  } else {
+  {
     k_count_interacting<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, Rc2s, s.pos.p, s.nbr.p, s.nbrCount.p, s.counter.p);
   }
   unsigned long long n = 0;
@@ -1741,11 +1571,7 @@ long long Engine::download_pairs(int* pairs, long long capacity) {
   DBuf<int> dp;
   if (pairs != nullptr && capacity > 0) dp.ensure(2 * (size_t)capacity);
   CUDA_CHECK(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned long long), s.stream));
-  if (s.use_bricks) {
-    BrickArgs k;
-    k.g = s.bgrid; k.desc = s.bdesc.p; k.nbr16 = s.nbr16.p; k.cap = s.cap; k.Bmax = s.Bmax;
-    k_brick_list_walk<<<s.nbricks, TPB, 0, s.stream>>>(k, 0, s.nbrCount.p, s.sMeta.p, s.pos.p, 0.0, dp.p, capacity, s.counter.p);
-  } else {
+  {
     k_export_pairs<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, s.nbr.p, s.nbrCount.p, s.sMeta.p, dp.p, capacity, s.counter.p);
   }
   unsigned long long n = 0;
@@ -1763,7 +1589,6 @@ void Engine::rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_sca
                  const std::vector<unsigned short>& pairSym, int nsym, std::vector<long long>& counts) {
   Impl& s = *d_;
   if (!s.list_valid) fatal("radial distribution calculation", "no neighbor list has been built yet");
-  if (s.use_bricks) fatal("radial distribution calculation", "not available with EMDEE_BRICKS");
   const size_t nbin = (size_t)bins * nsym;
   DBuf<unsigned long long> hist;
   DBuf<unsigned short> sym;

@@ -136,9 +136,10 @@ class Engine {
   void rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_scaled, const std::vector<unsigned short>& pairSym,
            int nsym, std::vector<long long>& counts);
   void set_kernel_timing(bool on) { timing_ = on; }
+  void tune(const char* knob, int value);   // developer knobs (tools/force_lab.py): "force_variant", "carveout"
   void synchronize();
   void* stream_handle();   // the cudaStream_t every kernel of this system is launched on
-  EngineStats stats() const { return stats_; }
+  EngineStats stats();
 
   // ---- multi-GPU: one rank per GPU, z-slab decomposition (NCCL) ---------------------------------
   void comm_init(int rank, int world, const void* nccl_unique_id);
@@ -146,6 +147,11 @@ class Engine {
   struct Impl;
 
  private:
+  void rebuild_list(double Lbox);
+  void launch_pair_kernel(int layer0, bool compute, double Lbox, bool speculative);
+  int timer_begin(int kind);
+  void timer_end(int idx);
+  void timer_harvest(int idx);
   Impl* d_;
   bool timing_ = false;
   EngineStats stats_;

@@ -96,6 +96,27 @@ __device__ __forceinline__ unsigned int take_ticket(unsigned int* ticket) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Host-visible result slot in pinned (mapped) host memory. The last block of a reducing kernel stores its scalars
+// here, fences system-wide and then publishes a sequence number; the host spins on `seq` (Engine::Impl::wait_slot)
+// instead of paying a D2H copy + stream synchronisation per result. One 64-byte line per slot.
+// ------------------------------------------------------------------------------------------------
+struct HostSlot {
+  double v[7];
+  unsigned long long seq;   // written last
+};
+constexpr int SLOT_FORCE = 0, SLOT_KINETIC = 1, SLOT_CHECK = 2, SLOT_BODY = 3, SLOT_AUX = 4, NSLOTS = 8;
+constexpr int SLOT_STATUS = 5;   // v[5] of the force slot: 0 = forces computed, 1 = the kernel found "rebuild needed" and did nothing
+
+__device__ __forceinline__ void slot_publish(HostSlot* hs, unsigned long long seq) {
+#if defined(__CUDACC__)
+  __threadfence_system();
+  asm volatile("st.global.release.sys.u64 [%0], %1;" ::"l"(&hs->seq), "l"(seq) : "memory");
+#else   // tests/cusim emulation build
+  hs->seq = seq;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // Grid-wide finish without a second launch: every block publishes WIDTH partial sums, takes a ticket,
 // and the block drawing the last ticket folds all partials in a FIXED order (thread t sums blocks
 // t, t+T, ...; then a fixed shared-memory tree), so the result never depends on which block is last.
@@ -103,7 +124,7 @@ __device__ __forceinline__ unsigned int take_ticket(unsigned int* ticket) {
 template <int WIDTH>
 __device__ __forceinline__ void grid_finish(const double (&mine)[WIDTH], double* __restrict__ partial,
                                             unsigned int* __restrict__ ticket, double* __restrict__ out,
-                                            double scale_first4) {
+                                            double scale_first4, HostSlot* hs = nullptr, unsigned long long seq = 0ull) {
   __shared__ double fin[TPB][WIDTH];
   __shared__ bool last;
   if (threadIdx.x == 0) {
@@ -136,8 +157,16 @@ __device__ __forceinline__ void grid_finish(const double (&mine)[WIDTH], double*
   }
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < WIDTH; ++q) out[q] = fin[0][q] * ((q < 4) ? scale_first4 : 1.0);
+    for (int q = 0; q < WIDTH; ++q) {
+      const double r = fin[0][q] * ((q < 4) ? scale_first4 : 1.0);
+      out[q] = r;
+      if (hs != nullptr) hs->v[q] = r;
+    }
     *ticket = 0u;
+    if (hs != nullptr) {
+      if (WIDTH <= SLOT_STATUS) hs->v[SLOT_STATUS] = 0.0;
+      slot_publish(hs, seq);
+    }
   }
 }
 

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
                                                const double* __restrict__ F, const double* __restrict__ invMass,
                                                const unsigned char* __restrict__ owned, int want_ke,
                                                double* __restrict__ partial, unsigned int* __restrict__ ticket,
-                                               double* __restrict__ out) {
+                                               double* __restrict__ out, HostSlot* hs, unsigned long long seq) {
   __shared__ double red[TPB / 32][3];
   const long long a0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * APT;
   const int n = (a0 >= N) ? 0 : (int)min((long long)APT, N - a0);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
     for (int x = 0; x < 3; ++x)
       for (int w = 0; w < TPB / 32; ++w) mine[x] += red[w][x];
   }
-  grid_finish<3>(mine, partial, ticket, out, 1.0);
+  grid_finish<3>(mine, partial, ticket, out, 1.0, hs, seq);
 }
 
 // R = CR*R + CP*P/m, fused with the rebuild criterion on the NEW coordinates (|R - R0|^2 ordered scan).

@@ -50,58 +50,6 @@ __global__ void __launch_bounds__(TPB) k_count_interacting(int Next, int cap, do
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
 }
 
-// brick-local staged index -> global sorted entry
-__device__ __forceinline__ int brick_to_global(const BrickDesc& d, int lf) {
-  int lo = 0, hi = d.nseg - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (d.segL[mid] <= lf) lo = mid;
-    else hi = mid - 1;
-  }
-  return d.segG[lo] + (lf - d.segL[lo]);
-}
-
-// mode 0: export pairs (ai < aj); mode 1: count entries with r^2 < Rc2s
-__global__ void __launch_bounds__(TPB) k_brick_list_walk(BrickArgs k, int mode, const int* __restrict__ nbrCount,
-                                                         const int4* __restrict__ sMeta, const double4* __restrict__ pos,
-                                                         double Rc2s, int* __restrict__ pairs, long long capacity,
-                                                         unsigned long long* __restrict__ counter) {
-  const int brick = blockIdx.x;
-  const BrickDesc& d = k.desc[brick];
-  unsigned long long n = 0;
-  for (int b = threadIdx.x; b < d.B; b += blockDim.x) {
-    int lo = 0, hi = d.nrows - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (d.rowT[mid] <= b) lo = mid;
-      else hi = mid - 1;
-    }
-    const int e = d.rowG[lo] + (b - d.rowT[lo]);
-    const int cnt = nbrCount[e];
-    const int ai = sMeta[e].x;
-    const double4 pi = pos[e];
-    const unsigned short* p = k.nbr16 + ((size_t)brick * k.cap) * k.Bmax + b;
-    for (int q = 0; q < cnt; ++q) {
-      const int f = brick_to_global(d, p[(size_t)q * k.Bmax]);
-      if (mode == 0) {
-        const int aj = sMeta[f].x;
-        if (ai < aj) {
-          unsigned long long slot = atomicAdd(counter, 1ull);
-          if (pairs != nullptr && (long long)slot < capacity) {
-            pairs[2 * slot] = ai;
-            pairs[2 * slot + 1] = aj;
-          }
-        }
-      } else {
-        const double4 pj = pos[f];
-        const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-        if (dx * dx + dy * dy + dz * dz < Rc2s) ++n;
-      }
-    }
-  }
-  if (mode == 1 && n) atomicAdd(counter, n);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Pair-distance histogram over the resident list (reference count_pairs, src/EmDeeCode.f90:1346-1388).
 // One thread per real entry walks its row of the FULL list, so every pair is met twice (host halves the

@@ -66,7 +66,8 @@ __device__ __forceinline__ MaxNext block_ordered_reduce(MaxNext s) {
 // publish this block's state; the last block folds all block states in block order and writes
 // maximum + 2*sqrt(maximum*next) + next (reference neighbor_lists.f90:57)
 __device__ __forceinline__ void check_finish(MaxNext mine, MaxNext* __restrict__ partial,
-                                             unsigned int* __restrict__ ticket, double* __restrict__ result) {
+                                             unsigned int* __restrict__ ticket, double* __restrict__ result,
+                                             HostSlot* hs = nullptr, unsigned long long seq = 0ull) {
   __shared__ bool last;
   if (threadIdx.x == 0) {
     __stcg(&partial[blockIdx.x].m, mine.m);
@@ -90,8 +91,13 @@ __device__ __forceinline__ void check_finish(MaxNext mine, MaxNext* __restrict__
   }
   s = block_ordered_reduce(s);
   if (threadIdx.x == 0) {
-    result[0] = __dadd_rn(__dadd_rn(s.m, __dmul_rn(2.0, __dsqrt_rn(__dmul_rn(s.m, s.n)))), s.n);
+    const double value = __dadd_rn(__dadd_rn(s.m, __dmul_rn(2.0, __dsqrt_rn(__dmul_rn(s.m, s.n)))), s.n);
+    result[0] = value;
     *ticket = 0u;
+    if (hs != nullptr) {
+      hs->v[0] = value;
+      slot_publish(hs, seq);
+    }
   }
 }
 
@@ -99,11 +105,12 @@ __global__ void __launch_bounds__(TPB) k_displacement_check(const double* __rest
                                                             const double* __restrict__ R0, int N,
                                                             MaxNext* __restrict__ partial,
                                                             unsigned int* __restrict__ ticket,
-                                                            double* __restrict__ result) {
+                                                            double* __restrict__ result, HostSlot* hs,
+                                                            unsigned long long seq) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   MaxNext s = (i < N) ? mn_atom(R, R0, i) : mn_identity();
   s = block_ordered_reduce(s);
-  check_finish(s, partial, ticket, result);
+  check_finish(s, partial, ticket, result, hs, seq);
 }
 
 // ------------------------------------------------------------------------------------------------

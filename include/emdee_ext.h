@@ -49,11 +49,16 @@ typedef struct {
 
 void EmDeeX_stats( tEmDee md, tEmDeeXStats* out );
 
-/* Enable per-kernel CUDA-event timing of the force and build kernels (adds a sync per call). */
+/* Enable per-kernel CUDA-event timing of the force and build kernels (event pairs in a ring, read back lazily:
+   no synchronisation is added to the step). */
 void EmDeeX_set_kernel_timing( tEmDee md, int enabled );
 
 /* Block until all queued device work of this system has finished. */
 void EmDeeX_synchronize( tEmDee md );
+
+/* Developer knobs of the plain-LJ force kernel ("force_variant": launch shape / cache-policy variant, "carveout":
+   preferred shared-memory carveout in percent); used by tools/force_lab.py to time variants on one resident system. */
+void EmDeeX_tune( tEmDee md, const char* knob, int value );
 
 /* The CUDA stream (cudaStream_t) all kernels of this system are launched on, so that a client can record its
    own events around a region or order its own work after the library's. */

@@ -18,7 +18,7 @@ GEN = os.path.join(OUT, "cusim_src")
 # the CPU that the tolerances of the GPU tests survive the different rounding of the device build
 FMA = os.environ.get("CUSIM_FMA") == "1"
 LIB = os.path.join(OUT, "libemdee_cusim_fma.so" if FMA else "libemdee_cusim.so")
-PARTS = ["engine.cu", "engine_common.cuh", "engine_list.cuh", "engine_force.cuh", "engine_brick.cuh",
+PARTS = ["engine.cu", "engine_common.cuh", "engine_list.cuh", "engine_force.cuh",
          "engine_dynamics.cuh", "engine_bodies.cuh", "engine_bonded.cuh", "engine_ewald.cuh", "engine_dist.cuh", "engine_extra.cuh"]
 
 

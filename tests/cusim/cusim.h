@@ -56,10 +56,11 @@ inline int2 make_int2(int x, int y) { return int2{x, y}; }
 typedef int cudaError_t;
 typedef struct cusimStream* cudaStream_t;
 typedef struct cusimEvent* cudaEvent_t;
-enum { cudaSuccess = 0 };
+enum { cudaSuccess = 0, cudaErrorNotReady = 600 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum { cudaHostAllocMapped = 2, cudaHostAllocPortable = 1 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 // texture objects over linear memory: the "object" is the base pointer
 typedef unsigned long long cudaTextureObject_t;
@@ -89,6 +90,8 @@ inline cudaError_t cudaMalloc(T** p, size_t bytes) {
 template <class T>
 inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMalloc(p, bytes); }
 template <class T>
+inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
+template <class T>
 inline cudaError_t cudaMallocManaged(T** p, size_t bytes) { return cudaMalloc(p, bytes); }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
@@ -100,6 +103,7 @@ inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cuda
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
@@ -375,6 +379,7 @@ inline T shuffle(T v, int src_lane) {
 inline void __syncthreads() { cusim::sync_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { cusim::sync_warp(); }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src, int = 32) { return cusim::shuffle(v, src); }
 template <class T>

@@ -74,6 +74,8 @@ long long Engine::pair_count() { return 0; }
 void Engine::update_list_stats(int, double) {}
 long long Engine::download_pairs(int*, long long) { return 0; }
 void Engine::synchronize() {}
+EngineStats Engine::stats() { return stats_; }
+void Engine::tune(const char*, int) {}
 void Engine::rdf(double, int bins, double, double, const std::vector<unsigned short>&, int nsym, std::vector<long long>& counts) {
   counts.assign((size_t)bins * nsym, 0);
 }

@@ -14,7 +14,6 @@ import os
 import pytest
 
 import common as cm
-import test_gpu_experimental as t_exp
 import test_gpu_parity as t_par
 import test_zz_box_rescale as t_box
 import test_zz_rdf as t_rdf
@@ -50,7 +49,7 @@ def _cases(module, skip=()):
 
 # test_kernels_actually_ran reads device statistics whose launch counts the emulator also keeps: included.
 # test_reference_kat_replay_on_gpu (100 steps x 3 models) is covered here by one model to bound the run time.
-CASES = (_cases(t_par, skip=("test_brick_path_opt_in", "test_duo_path_opt_in"))
+CASES = (_cases(t_par)
          + _cases(t_box, skip=("test_scenario_on_the_oracle_builds",))
          + _cases(t_stc)
          + _cases(t_rdf)
@@ -59,16 +58,13 @@ CASES = (_cases(t_par, skip=("test_brick_path_opt_in", "test_duo_path_opt_in"))
          + _cases(t_bd)
          + _cases(t_ew)
          + _cases(t_c1)
-         + [c for c in _cases(t_exp) if not c.id.endswith(("test_rows_path[16]", "test_rows_path[32]"))]   # G = 4, 8 here; all four on the GPU
-         + [pytest.param(t_par.test_brick_path_opt_in, {}, id="test_gpu_parity::test_brick_path_opt_in"),
-            pytest.param(t_par.test_duo_path_opt_in, {}, id="test_gpu_parity::test_duo_path_opt_in")])
+         )
 
 
 @pytest.fixture(autouse=True)
 def _use_emulated_library(monkeypatch):
     lib = cm.emulated()
     monkeypatch.setattr(cm, "product", lambda: lib)
-    monkeypatch.setenv("EMDEE_TEST_EXPERIMENTAL", "1")
     monkeypatch.setenv("EMDEE_TEST_REPLAY_STEPS", "20")
     monkeypatch.setenv("EMDEE_TEST_REPLICAS", "1")
     monkeypatch.setenv("EMDEE_TEST_C1_ATOMS", "1000")
@@ -93,7 +89,7 @@ def test_scheduling_order_and_fma_contraction_do_not_matter():
       after the last GPU session at their GPU tolerances."""
     import subprocess
     import sys
-    order_sel = ("two_types or dynamics_with_rebuilds or kat_replay_on_gpu or spce_single_point or brick or duo or rdf or degenerate "
+    order_sel = ("two_types or dynamics_with_rebuilds or kat_replay_on_gpu or spce_single_point or typed or rdf or degenerate "
                  "or verlet_step_with_shadow or next_to_rigid or rock_salt or share_phase_space")
     fma_sel = "nve_trajectory or verlet_step_with_shadow or bonded or rock_salt or testfortran or body_frames"
     cm.emulated()   # build the regular library once, before the children need it

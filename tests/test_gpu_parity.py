@@ -349,33 +349,43 @@ def test_kernels_actually_ran():
     s.finalize()
 
 
-def test_brick_path_opt_in(monkeypatch):
-    """EMDEE_BRICKS=1 selects the shared-memory (cp.async.bulk staged, 16-bit local index) kernels for
-    single-type systems; same parity bars. (Kept opt-in: measured slower than the global-gather path.)"""
-    monkeypatch.setenv("EMDEE_BRICKS", "1")
-    for variant in ("lj_cut", "lj_shifted_force", "softcore_0.7"):
-        sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS[variant])[0])
+def test_typed_path():
+    """Several atom types, pair models all pair_lj_cut (one modifier) or pair_none, Coulomb kind fixed at
+    compile time (k_pair_forces_typed; with two types the table row lives in registers). SPC/E with every eligible
+    Coulomb model, a three-type LJ mixture (shared-memory table), virial-only mode, ineligible systems falling back."""
+    for variant in ("coul_none", "coul_cut", "coul_sf", "coul_damped", "coul_damped_smoothed", "coul_damped_square_smoothed",
+                    "shifted_force(coul_cut)"):                                   # the last one is not eligible: generic kernel
+        sp, so = both(lambda lib: cm.spce_sample_system(lib, COUL_VARIANTS[variant])[0])
         assert_state_parity(sp, so)
+        if variant == "coul_damped_square_smoothed":
+            for s in (sp, so):                                                    # virial-only instantiation + rigid-body steps
+                s.random_momenta(0.0005, True, 5)
+                for step in range(4):
+                    s.md.Options.Compute = (step == 3)
+                    s.boost(1.0, 0.0, 0.5)
+                    s.displace(1.0, 0.0, 1.0)
+                    s.boost(1.0, 0.0, 0.5)
+            assert np.abs(sp.download("coordinates") - so.download("coordinates")).max() < 1e-9
+            assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-10
+            assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-9
         sp.finalize(), so.finalize()
-    outs = []
-    for lib in (cm.product(), cm.oracle()):
-        s, c = cm.lj_sample_system(lib, _lj)
-        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
-        outs.append(cm.run_nve(s, c, 100))
-        s.finalize()
-    assert np.abs(outs[0] - cm.kats()["lj_cut"]).max() < KTOL
 
-
-def test_duo_path_opt_in(monkeypatch):
-    """EMDEE_DUOS=1: one thread owns two consecutive entries and walks the sorted union of their rows (a shared
-    neighbor is gathered once). Same parity bars, every model goes through it. (Opt-in: measured slower.)"""
-    monkeypatch.setenv("EMDEE_DUOS", "1")
-    sp, so = both(lambda lib: cm.lj_sample_system(lib, PAIR_VARIANTS["lj_cut"])[0])
+    def three_types(lib):
+        R, L = cm.fcc_lj_box(7, rho=0.80, jitter=0.08, seed=23)
+        N = R.shape[0]
+        types = (np.arange(N) % 3 + 1).astype(np.int32)
+        s = lib.system(2, 1, 2.5, 0.4, N, types, np.array([1.0, 2.0, 3.0]), None)
+        for t, (e, sg) in enumerate(((1.0, 1.0), (0.7, 1.1), (1.3, 0.9)), start=1):
+            s.set_pair_model(t, t, lib.EmDee_pair_lj_cut(e, sg), 1.0)     # plain LJ everywhere: cross pairs mix to plain LJ too
+        s.set_pair_model(1, 3, lib.EmDee_pair_none(), 1.0)                # one explicit non-interacting pair
+        s.set_coul_model(lib.EmDee_coul_damped(0.3))
+        s.upload("charges", np.where(types == 2, 0.0, np.where(types == 1, 0.5, -0.5)))
+        s.upload("box", np.array([L]))
+        s.upload("coordinates", R)
+        return s
+    sp, so = both(three_types)
     assert_state_parity(sp, so)
     sp.finalize(), so.finalize()
-    sp, so = both(lambda lib: cm.spce_sample_system(lib, COUL_VARIANTS["coul_damped_square_smoothed"])[0])
-    assert_state_parity(sp, so)
-    sp.finalize(), so.finalize()
-    sp, so = both(lambda lib: _two_type_system(lib, COUL_VARIANTS["coul_sf"]))
+    sp, so = both(lambda lib: _two_type_system(lib, COUL_VARIANTS["coul_sf"]))   # softcore present: generic kernel
     assert_state_parity(sp, so)
     sp.finalize(), so.finalize()

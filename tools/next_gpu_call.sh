@@ -8,8 +8,8 @@
 set -u
 mkdir -p gpurun_out
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lsu_probe tools/lsu_probe.cu && timeout 120 /tmp/lsu_probe > gpurun_out/lsu_probe.txt 2>&1
-EMDEE_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py tests/test_zz_box_rescale.py tests/test_zz_single_type_coulomb.py tests/test_zz_rdf.py tests/test_zz_edge_cases.py tests/test_zzz_rigid_bodies.py tests/test_zzzz_phase_space.py tests/test_zzz_bonded.py tests/test_zzz_ewald.py tests/test_zzz_config_c1.py tests/test_zzz_fuzz.py -m gpu -q > gpurun_out/experimental_tests.txt 2>&1
-tail -5 gpurun_out/experimental_tests.txt
+EMDEE_TEST_EXPERIMENTAL=1 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/experimental_tests.txt 2>&1
+tail -30 gpurun_out/experimental_tests.txt
 timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 for g in 4 8 16 32; do
   EMDEE_ROWS=$g timeout 200 python bench.py --steps 200 --warmup 30 --no-cpu-baseline > gpurun_out/bench_rows$g.json 2> gpurun_out/bench_rows$g.err
