@@ -111,6 +111,12 @@ struct Engine::Impl {
   DBuf<int> selCount;
   DBuf<MaxIdx> miPartial, miResult;
   MaxIdx* h_mi = nullptr;          // pinned, world entries
+  DBuf<int> ownedList;             // compact ascending list of the atoms this rank owns (per-step kernels run over it)
+  int nOwn = 0;
+  bool mi_fresh = false;           // miResult[world] holds phase 1 of the criterion for the current coordinates (k_displace_owned)
+  // local I/O (EmDeeX_tune "local_io", several GPUs): coordinate uploads read only the atoms this rank owns or keeps as
+  // halo, force downloads write only the atoms it owns, both straight from / to the caller's pinned host array
+  bool local_io = false;
 
   // rigid bodies (engine_bodies.cuh): CSR of members + SoA state, 27 doubles per body
   int nitems = 0;
@@ -289,7 +295,8 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.typedState.assign(nlayers, 0);
   s.typedPM.assign(nlayers, 0);
   s.flags.ensure(4);
-  s.scalars.ensure(16);
+  s.scalars.ensure(32);
+  CUDA_CHECK(cudaMemset(s.scalars.p, 0, 32 * sizeof(double)));
   s.counter.ensure(2);
   s.tickets.ensure(4);
   CUDA_CHECK(cudaMemset(s.tickets.p, 0, 4 * sizeof(unsigned int)));
@@ -330,7 +337,7 @@ Engine::~Engine() {
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
-  s.known.release(); s.migCounts.release();
+  s.known.release(); s.migCounts.release(); s.ownedList.release();
   s.terms.release(); s.termFirst.release(); s.termRef.release();
   s.ewN.release(); s.ewKType.release(); s.ewPrefac.release(); s.ewLambda.release(); s.ewSigma.release(); s.ewPartial.release();
   s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
@@ -389,11 +396,11 @@ void gather_full(Engine::Impl& s, double* X) {
   NCCL_CHECK(nccl().AllReduce(s.scratch3.p, X, 3 * (size_t)s.N, ncclDouble, ncclSum, s.comm, s.stream));
 }
 
-// per-rebuild: compact the four halo lists (ascending atom index) from the cell layers
+// per-rebuild: compact the four halo lists and the owned list (all ascending in the atom index) from the cell layers
 void build_halo_lists(Engine::Impl& s) {
   const int N = s.N;
   s.haloFlags.ensure(4 * (size_t)N);
-  s.selCount.ensure(4);
+  s.selCount.ensure(8);
   k_halo_flags<<<nblocks(N), TPB, 0, s.stream>>>(N, s.grid, s.atomCell.p, s.haloFlags.p);
   cub::CountingInputIterator<int> ids(0);
   size_t need = 0;
@@ -408,34 +415,60 @@ void build_halo_lists(Engine::Impl& s) {
     cub::DeviceSelect::Flagged(s.scanTmp.p, need, ids, s.haloFlags.p + (size_t)k * N, s.haloList[k].p, s.selCount.p + k, N,
                                s.stream);
   }
-  int h[4];
-  CUDA_CHECK(cudaMemcpyAsync(h, s.selCount.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  s.ownedList.ensure(N);
+  cub::DeviceSelect::Flagged(s.scanTmp.p, need, ids, s.owned.p, s.ownedList.p, s.selCount.p + 4, N, s.stream);
+  int h[5];
+  CUDA_CHECK(cudaMemcpyAsync(h, s.selCount.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
-  if (s.env_debug) std::fprintf(stderr, "[emdee r%d] halo lists: send up %d dn %d, recv below %d above %d\n", s.rank, h[0], h[1], h[2], h[3]);
+  if (s.env_debug) std::fprintf(stderr, "[emdee r%d] halo lists: send up %d dn %d, recv below %d above %d, owned %d\n", s.rank, h[0], h[1], h[2], h[3], h[4]);
   for (int k = 0; k < 4; ++k) {
     s.haloCount[k] = h[k];
     s.haloBuf[k].ensure(3 * (size_t)h[k] + 8, 1.2);
   }
+  s.nOwn = h[4];
 }
 
-// per step: ghost positions of the two layers above and below the slab (no reverse exchange: full list)
-void halo_exchange(Engine::Impl& s) {
-  if (s.world <= 1 || !s.owned_valid || s.halo_fresh) return;
+// Per step, ONE NCCL group (one launch): the ghost positions of the two layers above and below the slab (no reverse
+// exchange: full list) and -- with_criterion -- every rank's phase-1 state of the rebuild criterion (16 bytes to and from
+// every peer); the decision is then taken on the device by k_decide (same inputs, same result on every rank) and read by
+// the speculatively launched pair kernel, so the host does not wait here.
+void exchange_step(Engine::Impl& s, bool with_criterion) {
+  if (s.world <= 1 || !s.owned_valid) return;
+  const bool halo = !s.halo_fresh;
+  if (!halo && !with_criterion) return;
   const int up = (s.rank + 1) % s.world, dn = (s.rank + s.world - 1) % s.world;
-  for (int k = 0; k < 2; ++k)
-    if (s.haloCount[k] > 0)
-      k_pack3<<<nblocks(s.haloCount[k]), TPB, 0, s.stream>>>(s.haloCount[k], s.haloList[k].p, s.R.p, s.haloBuf[k].p);
+  if (with_criterion && !s.mi_fresh) {   // coordinates did not come from k_displace_owned (upload, first step after a rebuild)
+    const long long all = 0x7fffffffffffffffLL;
+    k_check_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.R.p, s.R0.p, all, s.miPartial.p,
+                                                                      s.tickets.p + 2, s.miResult.p + s.world);
+    s.mi_fresh = true;
+  }
+  if (halo)
+    for (int k = 0; k < 2; ++k)
+      if (s.haloCount[k] > 0)
+        k_pack3<<<nblocks(s.haloCount[k]), TPB, 0, s.stream>>>(s.haloCount[k], s.haloList[k].p, s.R.p, s.haloBuf[k].p);
   NCCL_CHECK(nccl().GroupStart());
-  NCCL_CHECK(nccl().Send(s.haloBuf[0].p, 3 * (size_t)s.haloCount[0], ncclDouble, up, s.comm, s.stream));
-  NCCL_CHECK(nccl().Send(s.haloBuf[1].p, 3 * (size_t)s.haloCount[1], ncclDouble, dn, s.comm, s.stream));
-  NCCL_CHECK(nccl().Recv(s.haloBuf[2].p, 3 * (size_t)s.haloCount[2], ncclDouble, dn, s.comm, s.stream));
-  NCCL_CHECK(nccl().Recv(s.haloBuf[3].p, 3 * (size_t)s.haloCount[3], ncclDouble, up, s.comm, s.stream));
+  if (halo) {
+    NCCL_CHECK(nccl().Send(s.haloBuf[0].p, 3 * (size_t)s.haloCount[0], ncclDouble, up, s.comm, s.stream));
+    NCCL_CHECK(nccl().Send(s.haloBuf[1].p, 3 * (size_t)s.haloCount[1], ncclDouble, dn, s.comm, s.stream));
+    NCCL_CHECK(nccl().Recv(s.haloBuf[2].p, 3 * (size_t)s.haloCount[2], ncclDouble, dn, s.comm, s.stream));
+    NCCL_CHECK(nccl().Recv(s.haloBuf[3].p, 3 * (size_t)s.haloCount[3], ncclDouble, up, s.comm, s.stream));
+  }
+  if (with_criterion)
+    for (int r = 0; r < s.world; ++r) {
+      if (r == s.rank) continue;
+      NCCL_CHECK(nccl().Send(s.miResult.p + s.world, sizeof(MaxIdx), ncclChar, r, s.comm, s.stream));
+      NCCL_CHECK(nccl().Recv(s.miResult.p + r, sizeof(MaxIdx), ncclChar, r, s.comm, s.stream));
+    }
   NCCL_CHECK(nccl().GroupEnd());
-  for (int k = 2; k < 4; ++k)
-    if (s.haloCount[k] > 0)
-      k_unpack3<<<nblocks(s.haloCount[k]), TPB, 0, s.stream>>>(s.haloCount[k], s.haloList[k].p, s.haloBuf[k].p, s.R.p);
+  if (halo)
+    for (int k = 2; k < 4; ++k)
+      if (s.haloCount[k] > 0)
+        k_unpack3<<<nblocks(s.haloCount[k]), TPB, 0, s.stream>>>(s.haloCount[k], s.haloList[k].p, s.haloBuf[k].p, s.R.p);
   s.halo_fresh = true;
+  if (with_criterion) k_decide<<<1, 32, 0, s.stream>>>(s.world, s.rank, s.miResult.p, s.skinSq, s.scalars.p + CRIT_DIST);
 }
+void halo_exchange(Engine::Impl& s) { exchange_step(s, false); }
 
 // rebuild-time migration: see k_mig_flags. Returns with R, P current for every atom this rank may need.
 void migrate(Engine::Impl& s, double Lbox) {
@@ -495,32 +528,35 @@ void migrate(Engine::Impl& s, double Lbox) {
       k_unpack7<<<nblocks(c[2 + k]), TPB, 0, s.stream>>>(c[2 + k], s.migRecv[k].p, s.R.p, s.P.p, s.known.p);
 }
 
-// distributed rebuild decision: identical on every rank (all inputs are all-gathered / all-reduced)
-bool rebuild_needed_dist(Engine::Impl& s) {
-  const int N = s.N;
-  const long long all = 0x7fffffffffffffffLL;
-  k_check_dist<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, s.owned.p, N, all, s.miPartial.p, s.tickets.p + 2,
-                                                 s.miResult.p + s.world);
+// Distributed rebuild decision, phase 2 (rare: maximum <= skin^2 < 4*maximum and i* > 0): `next` = max of d_i over the
+// atoms with index below i*, then the reference's value. Identical on every rank (all inputs are all-gathered).
+bool rebuild_needed_phase2(Engine::Impl& s, double maximum, long long istar) {
+  k_check_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.R.p, s.R0.p, istar, s.miPartial.p,
+                                                                    s.tickets.p + 2, s.miResult.p + s.world);
   NCCL_CHECK(nccl().AllGather(s.miResult.p + s.world, s.miResult.p, sizeof(MaxIdx), ncclChar, s.comm, s.stream));
   CUDA_CHECK(cudaMemcpyAsync(s.h_mi, s.miResult.p, (size_t)s.world * sizeof(MaxIdx), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
-  MaxIdx g = s.h_mi[0];
-  for (int r = 1; r < s.world; ++r)
-    if (s.h_mi[r].m > g.m || (s.h_mi[r].m == g.m && s.h_mi[r].i < g.i)) g = s.h_mi[r];
-  if (g.m > s.skinSq) return true;            // value >= maximum
-  if (4.0 * g.m <= s.skinSq) return false;    // value <= 4*maximum
-  double next = g.m;                          // i* == 0: `next` still holds the first atom's value
-  if (g.i > 0) {
-    k_check_dist<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, s.owned.p, N, g.i, s.miPartial.p, s.tickets.p + 2,
-                                                   s.miResult.p + s.world);
-    NCCL_CHECK(nccl().AllGather(s.miResult.p + s.world, s.miResult.p, sizeof(MaxIdx), ncclChar, s.comm, s.stream));
-    CUDA_CHECK(cudaMemcpyAsync(s.h_mi, s.miResult.p, (size_t)s.world * sizeof(MaxIdx), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_CHECK(cudaStreamSynchronize(s.stream));
-    next = s.h_mi[0].m;
-    for (int r = 1; r < s.world; ++r) next = std::max(next, s.h_mi[r].m);
-  }
-  const double value = g.m + 2 * std::sqrt(g.m * next) + next;   // reference neighbor_lists.f90:57
+  double next = s.h_mi[0].m;
+  for (int r = 1; r < s.world; ++r) next = std::max(next, s.h_mi[r].m);
+  s.mi_fresh = false;   // miResult[world] now holds the phase-2 state
+  const double value = maximum + 2 * std::sqrt(maximum * next) + next;   // reference neighbor_lists.f90:57
   return value > s.skinSq;
+}
+
+// energies / virial of all ranks summed and delivered to the host slot together with the device-side rebuild decision:
+// one collective, one host wait per force evaluation
+void finish_pair_dist(Engine::Impl& s, bool with_decision) {
+  NCCL_CHECK(nccl().AllReduce(s.scalars.p, s.scalars.p, 5, ncclDouble, ncclSum, s.comm, s.stream));
+  k_publish_force<<<1, 32, 0, s.stream>>>(s.scalars.p, with_decision ? s.scalars.p + CRIT_DIST : nullptr, s.slots + SLOT_FORCE,
+                                          s.slot_seq[SLOT_FORCE]);
+  s.wait_slot(SLOT_FORCE);
+}
+
+// the decision alone (layers without a pair kernel)
+void publish_decision(Engine::Impl& s) {
+  s.next_seq(SLOT_FORCE);
+  k_publish_force<<<1, 32, 0, s.stream>>>(s.scalars.p, s.scalars.p + CRIT_DIST, s.slots + SLOT_FORCE, s.slot_seq[SLOT_FORCE]);
+  s.wait_slot(SLOT_FORCE);
 }
 
 }  // namespace
@@ -569,6 +605,7 @@ void Engine::upload_coordinates(const double* R) {
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
   s.has_R = true;
   s.check_cached = false;
+  s.mi_fresh = false;
   s.halo_fresh = true;   // every rank uploads the full array
   if (s.world > 1 && s.owned_valid && !s.all_known) {
     s.all_known = true;    // coordinates are full everywhere again ...
@@ -813,11 +850,13 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   // scalars[8] on the device and the host does not wait for it -- the pair kernel is launched SPECULATIVELY, checks the
   // criterion itself and reports "rebuild needed" instead of forces when it fires (about one step in seven at LJ-1M).
   bool rebuild = false, speculative = false;
-  if (s.world > 1 && s.owned_valid) {
-    halo_exchange(s);
-    rebuild = rebuild_needed_dist(s);
-    if (s.env_debug) std::fprintf(stderr, "[emdee r%d] compute_forces: rebuild=%d all_known=%d\n", s.rank, (int)rebuild, (int)s.all_known);
-    stats_.launches += 1;
+  const bool dist = s.world > 1 && s.owned_valid;
+  if (dist) {
+    // several GPUs: halo positions + every rank's criterion state travel in one NCCL group, the decision is taken on the
+    // device (scalars[CRIT_DIST..]) and the pair kernel is launched speculatively against it, as on one GPU
+    exchange_step(s, true);
+    speculative = true;
+    stats_.launches += 2;
   } else if (s.check_cached && s.list_valid && s.world == 1) {
     speculative = true;
   } else {
@@ -837,8 +876,28 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   if (rebuild) { s.t_rebuild += tp2 - tp1; s.n_rebuild += 1; }
 
   // ---- pair loop -------------------------------------------------------------------------------
+  // several GPUs: what to do with the decision that came back with the scalars (code 1 = rebuild, 2 = phase 2 needed)
+  auto settle_dist = [&](int code) -> bool {
+    const double maximum = s.slots[SLOT_FORCE].v[0];
+    const long long istar = (long long)s.slots[SLOT_FORCE].v[6];
+    const bool rb = code == 1 || rebuild_needed_phase2(s, maximum, istar);
+    if (s.env_debug) std::fprintf(stderr, "[emdee r%d] compute_forces: code=%d rebuild=%d\n", s.rank, code, (int)rb);
+    if (rb) {
+      const double tr0 = wall_now();
+      auto t_rb = std::chrono::steady_clock::now();
+      rebuild_list(Lbox);
+      neighbor_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_rb).count();
+      s.t_rebuild += wall_now() - tr0;
+      s.n_rebuild += 1;
+    }
+    return rb;
+  };
   if (!lt.pairs_exist) {
-    if (speculative) {   // no pair kernel to carry the speculation: ask for the criterion now
+    if (speculative && dist) {   // no pair kernel to carry the speculation: ask for the decision now
+      publish_decision(s);
+      const int code = (int)s.slots[SLOT_FORCE].v[5];
+      if (code != 0) rebuild = settle_dist(code);
+    } else if (speculative) {
       CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 8, s.scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
       CUDA_CHECK(cudaStreamSynchronize(s.stream));
       if (s.h_scalars[8] > s.skinSq) {
@@ -853,11 +912,15 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   }
   launch_pair_kernel(layer0, compute, Lbox, speculative);
   if (s.world > 1) {
-    NCCL_CHECK(nccl().AllReduce(s.scalars.p, s.scalars.p, 5, ncclDouble, ncclSum, s.comm, s.stream));
-    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars, s.scalars.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_CHECK(cudaStreamSynchronize(s.stream));
-    CUDA_CHECK(cudaGetLastError());
-    for (int q = 0; q < 5; ++q) s.slots[SLOT_FORCE].v[q] = s.h_scalars[q];
+    finish_pair_dist(s, dist);
+    const int code = dist ? (int)s.slots[SLOT_FORCE].v[5] : 0;
+    if (code != 0) {   // the speculative launch did nothing: settle the decision, then the real launch
+      if (s.last_force_timer >= 0) s.timers[s.last_force_timer].kind = -1;   // the aborted launch is not a force evaluation
+      stats_.force_launches -= 1;
+      rebuild = settle_dist(code);
+      launch_pair_kernel(layer0, compute, Lbox, false);
+      finish_pair_dist(s, false);
+    }
   } else {
     s.wait_slot(SLOT_FORCE);
     if (speculative && s.slots[SLOT_FORCE].v[SLOT_STATUS] != 0.0) {   // the criterion fired: rebuild, then the real launch
@@ -1020,6 +1083,7 @@ void Engine::rebuild_list(double Lbox) {
     CUDA_CHECK(cudaMemcpyAsync(s.R0.p, s.R.p, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
     CUDA_CHECK(cudaMemsetAsync(s.scalars.p + 8, 0, sizeof(double), s.stream));   // R0 = R: zero displacement
     s.check_cached = true;
+    s.mi_fresh = false;   // R0 changed: the distributed criterion state is re-evaluated on the next force call
     s.list_valid = true;
     stats_.cells_per_dim = M;
   }
@@ -1045,7 +1109,7 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   a.single = lt.pair[0];
   a.coul = lt.coul;
   a.F = Fl; a.partial = s.partial.p; a.ticket = s.tickets.p; a.out = s.scalars.p;
-  a.crit = speculative ? s.scalars.p + 8 : nullptr;
+  a.crit = !speculative ? nullptr : (s.world > 1 ? s.scalars.p + CRIT_DIST : s.scalars.p + 8);
   a.skinSq = s.skinSq;
   a.hs = (s.world > 1) ? nullptr : s.slots + SLOT_FORCE;   // several GPUs: the scalars are all-reduced first
   a.seq = s.next_seq(SLOT_FORCE);
@@ -1086,24 +1150,34 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
 void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke) {
   Impl& s = *d_;
   const double tp0 = wall_now();
-  const int grid = nblocks((s.N + APT - 1) / APT);
-  const unsigned char* owned = (s.world > 1 && s.owned_valid) ? s.owned.p : nullptr;
-  const bool direct = want_kinetic && owned == nullptr;   // single GPU: the last block writes the sums to the host slot
-  HostSlot* hs = direct ? s.slots + SLOT_KINETIC : nullptr;
-  const unsigned long long seq = direct ? s.next_seq(SLOT_KINETIC) : 0ull;
-  k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, s.F.p + (size_t)layer0 * 3 * s.N, s.invMass.p, owned,
-                                      want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10, hs, seq);
-  stats_.launches += 1;
-  if (direct) {
-    s.wait_slot(SLOT_KINETIC);
-    for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
-  } else if (want_kinetic) {
-    NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
-    CUDA_CHECK(cudaMemcpyAsync(s.h_scalars + 10, s.scalars.p + 10, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_CHECK(cudaStreamSynchronize(s.stream));
-    for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.h_scalars[10 + x];
-  } else if (s.exposed) {
-    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
+  if (s.world > 1 && s.owned_valid) {
+    // several GPUs: the kick runs over the compact list of owned atoms (work ~ atoms of this rank, not N); the kinetic
+    // sums take one all-reduce and reach the host through the pinned slot
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CP, CF, s.P.p, Fl, s.invMass.p,
+                                                                      want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1,
+                                                                      s.scalars.p + 10);
+    stats_.launches += 1;
+    if (want_kinetic) {
+      NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
+      const unsigned long long seq = s.next_seq(SLOT_KINETIC);
+      k_publish3<<<1, 32, 0, s.stream>>>(s.scalars.p + 10, s.slots + SLOT_KINETIC, seq);
+      s.wait_slot(SLOT_KINETIC);
+      for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
+    }
+  } else {
+    const int grid = nblocks((s.N + APT - 1) / APT);
+    HostSlot* hs = want_kinetic ? s.slots + SLOT_KINETIC : nullptr;   // the last block writes the sums to the host slot
+    const unsigned long long seq = want_kinetic ? s.next_seq(SLOT_KINETIC) : 0ull;
+    k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, nullptr, want_kinetic ? 1 : 0, s.partial.p,
+                                        s.tickets.p + 1, s.scalars.p + 10, hs, seq);
+    stats_.launches += 1;
+    if (want_kinetic) {
+      s.wait_slot(SLOT_KINETIC);
+      for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
+    } else if (s.exposed) {
+      CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    }
   }
   s.t_boost += wall_now() - tp0;
   s.n_boost += 1;
@@ -1113,9 +1187,12 @@ void Engine::displace(double CR, double CP) {
   Impl& s = *d_;
   const double tp0 = wall_now();
   if (s.world > 1 && s.owned_valid) {
-    k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, s.owned.p, s.R0.p, nullptr,
-                                                   s.tickets.p + 2, s.scalars.p + 8);
+    // owned atoms only (compact list); phase 1 of the rebuild criterion on the new coordinates lands in miResult[world]
+    k_displace_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
+                                                                         s.R0.p, s.miPartial.p, s.tickets.p + 2,
+                                                                         s.miResult.p + s.world);
     stats_.launches += 1;
+    s.mi_fresh = true;
     s.halo_fresh = false;
     s.check_cached = false;
     s.all_known = false;   // from now on only owned + halo positions are current on this rank
@@ -1187,6 +1264,7 @@ void Engine::update_body_frames(double Lbox) {
   stats_.launches += 1;
   s.frames_valid = true;
   s.check_cached = false;   // member coordinates may have been shifted by whole box lengths
+  s.mi_fresh = false;
 }
 
 void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool rotate, bool want_kinetic, KineticAll& ke) {
@@ -1258,6 +1336,7 @@ void Engine::move_all(double CR, double CP, double dt, bool translate, bool rota
     stats_.launches += 1;
   }
   s.check_cached = false;   // compute_forces evaluates the rebuild criterion on the new coordinates
+  s.mi_fresh = false;
   if (dist) {
     s.halo_fresh = false;
     s.all_known = false;    // free atoms: only owned + halo positions are current on this rank

@@ -19,21 +19,11 @@ struct MaxIdx {
 };
 __device__ __forceinline__ MaxIdx mi_better(MaxIdx a, MaxIdx b) { return (b.m > a.m || (b.m == a.m && b.i < a.i)) ? b : a; }
 
-__global__ void __launch_bounds__(TPB) k_check_dist(const double* __restrict__ R, const double* __restrict__ R0,
-                                                    const unsigned char* __restrict__ owned, int N, long long below,
-                                                    MaxIdx* __restrict__ partial, unsigned int* __restrict__ ticket,
-                                                    MaxIdx* __restrict__ result) {
+// Block-wide then grid-wide (last block, fixed order) fold of MaxIdx states; thread 0 of the last block writes the result.
+__device__ __forceinline__ void maxidx_finish(MaxIdx v, MaxIdx* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                              MaxIdx* __restrict__ result) {
   __shared__ MaxIdx sm[TPB];
   __shared__ bool last;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  MaxIdx v;
-  v.m = -1.0 / 0.0;
-  v.i = 0x7fffffffffffffffLL;
-  if (i < N && owned[i] && i < below) {
-    MaxNext d = mn_atom(R, R0, i);
-    v.m = d.m;
-    v.i = i;
-  }
   sm[threadIdx.x] = v;
   __syncthreads();
   for (int off = TPB / 2; off > 0; off >>= 1) {
@@ -67,6 +57,133 @@ __global__ void __launch_bounds__(TPB) k_check_dist(const double* __restrict__ R
     result[0] = sm[0];
     *ticket = 0u;
   }
+}
+
+// phase 1 / phase 2 of the criterion over the rank's OWNED atoms (compact ascending list): max of d_i over owned i < below
+__global__ void __launch_bounds__(TPB) k_check_owned(int n, const int* __restrict__ list, const double* __restrict__ R,
+                                                     const double* __restrict__ R0, long long below,
+                                                     MaxIdx* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                                     MaxIdx* __restrict__ result) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  MaxIdx v;
+  v.m = -1.0 / 0.0;
+  v.i = 0x7fffffffffffffffLL;
+  if (k < n) {
+    const long long i = list[k];
+    if (i < below) {
+      v.m = mn_atom(R, R0, i).m;
+      v.i = i;
+    }
+  }
+  maxidx_finish(v, partial, ticket, result);
+}
+
+// Free-atom kick of the owned atoms (k_boost through the owned list: the work is O(atoms of this rank), not O(N))
+__global__ void __launch_bounds__(TPB) k_boost_owned(int n, const int* __restrict__ list, double CP, double CF,
+                                                     double* __restrict__ P, const double* __restrict__ F,
+                                                     const double* __restrict__ invMass, int want_ke,
+                                                     double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                                     double* __restrict__ out) {
+  __shared__ double red[TPB / 32][3];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double ke[3] = {0.0, 0.0, 0.0};
+  if (k < n) {
+    const size_t a = (size_t)list[k];
+    const double im = invMass[a];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      const double q = __dadd_rn(__dmul_rn(CP, P[3 * a + x]), __dmul_rn(CF, F[3 * a + x]));
+      P[3 * a + x] = q;
+      ke[x] = __dmul_rn(__dmul_rn(im, q), q);
+    }
+  }
+  if (!want_ke) return;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    double v = ke[x];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red[threadIdx.x >> 5][x] = v;
+  }
+  __syncthreads();
+  double mine[3] = {0.0, 0.0, 0.0};
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+      for (int w = 0; w < TPB / 32; ++w) mine[x] += red[w][x];
+  }
+  grid_finish<3>(mine, partial, ticket, out, 1.0);
+}
+
+// Drift of the owned atoms fused with phase 1 of the criterion on the NEW coordinates: (max d_i, first index) over the list
+__global__ void __launch_bounds__(TPB) k_displace_owned(int n, const int* __restrict__ list, double CR, double CP,
+                                                        double* __restrict__ R, const double* __restrict__ P,
+                                                        const double* __restrict__ invMass, const double* __restrict__ R0,
+                                                        MaxIdx* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                                        MaxIdx* __restrict__ result) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  MaxIdx v;
+  v.m = -1.0 / 0.0;
+  v.i = 0x7fffffffffffffffLL;
+  if (k < n) {
+    const size_t a = (size_t)list[k];
+    const double im = invMass[a];
+    double r[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      r[x] = __dadd_rn(__dmul_rn(CR, R[3 * a + x]), __dmul_rn(__dmul_rn(CP, P[3 * a + x]), im));
+      R[3 * a + x] = r[x];
+    }
+    const double dx = __dsub_rn(r[0], R0[3 * a]), dy = __dsub_rn(r[1], R0[3 * a + 1]), dz = __dsub_rn(r[2], R0[3 * a + 2]);
+    v.m = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    v.i = (long long)a;
+  }
+  maxidx_finish(v, partial, ticket, result);
+}
+
+// Global rebuild decision from every rank's phase-1 state (all[r] for the peers, all[world] for this rank), identical on
+// every rank:  crit[0] = what the speculative pair kernel compares with skinSq (+inf = do not compute),
+//              crit[1] = code: 0 no rebuild, 1 rebuild, 2 undecided (maximum <= skin^2 < 4*maximum with i* > 0: phase 2 needed),
+//              crit[2] = i*, crit[3] = maximum   (reference neighbor_lists.f90:41-59)
+constexpr int CRIT_DIST = 16;   // offset of this block in Engine::Impl::scalars
+__global__ void k_decide(int world, int rank, const MaxIdx* __restrict__ all, double skinSq, double* __restrict__ crit) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  MaxIdx g = all[world];
+  for (int r = 0; r < world; ++r)
+    if (r != rank) g = mi_better(g, all[r]);
+  int code;
+  if (g.m > skinSq) code = 1;
+  else if (__dmul_rn(4.0, g.m) <= skinSq) code = 0;
+  else if (g.i == 0)   // `next` still holds the first atom's value
+    code = (__dadd_rn(__dadd_rn(g.m, __dmul_rn(2.0, __dsqrt_rn(__dmul_rn(g.m, g.m)))), g.m) > skinSq) ? 1 : 0;
+  else code = 2;
+  crit[0] = (code == 0) ? 0.0 : 1.0 / 0.0;
+  crit[1] = (double)code;
+  crit[2] = (double)g.i;
+  crit[3] = g.m;
+}
+
+// force scalars (already summed over the ranks) + the decision block -> pinned host slot:
+// v[0..4] scalars, v[5] code, v[6] i*; when the pair kernel did not run (code != 0) v[0] carries `maximum` instead
+__global__ void k_publish_force(const double* __restrict__ scalars, const double* __restrict__ crit, HostSlot* hs,
+                                unsigned long long seq) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int q = 0; q < 5; ++q) hs->v[q] = scalars[q];
+  hs->v[5] = 0.0;
+  hs->v[6] = 0.0;
+  if (crit != nullptr) {
+    hs->v[5] = crit[1];
+    hs->v[6] = crit[2];
+    if (crit[1] != 0.0) hs->v[0] = crit[3];
+  }
+  slot_publish(hs, seq);
+}
+
+// three kinetic sums (already summed over the ranks) -> pinned host slot
+__global__ void k_publish3(const double* __restrict__ src, HostSlot* hs, unsigned long long seq) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int q = 0; q < 3; ++q) hs->v[q] = src[q];
+  slot_publish(hs, seq);
 }
 
 // dst = owned ? src : 0 (three doubles per atom): the summand of the all-reduce that rebuilds a full array
