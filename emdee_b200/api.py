@@ -125,6 +125,7 @@ ABI_EXT_PRODUCT = {
     "EmDeeX_stats": (None, [tEmDee, C.POINTER(tEmDeeXStats)]),
     "EmDeeX_set_kernel_timing": (None, [tEmDee, C.c_int]),
     "EmDeeX_synchronize": (None, [tEmDee]),
+    "EmDeeX_kernel_times": (None, [tEmDee, _dp, C.POINTER(C.c_longlong)]),
     "EmDeeX_tune": (None, [tEmDee, C.c_char_p, C.c_int]),
     "EmDeeX_stream": (C.c_void_p, [tEmDee]),
     "EmDeeX_measure_fp64_tflops": (C.c_double, []),
@@ -291,6 +292,15 @@ class System:
 
     def synchronize(self):
         self.lib.EmDeeX_synchronize(self.md)
+
+    KERNEL_KINDS = ("force", "build", "boost", "displace", "refresh", "exchange", "binning", "other")
+
+    def kernel_times(self) -> dict:
+        """{kind: (accumulated ms, launches)} from the library's CUDA-event ring (set_kernel_timing(True) first)."""
+        ms = (C.c_double * 8)()
+        n = (C.c_longlong * 8)()
+        self.lib.EmDeeX_kernel_times(self.md, ms, n)
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_KINDS)}
 
     def stream(self) -> int:
         """cudaStream_t (as an integer) the system's kernels run on."""

@@ -144,6 +144,9 @@ struct Engine::Impl {
   bool env_debug = false, env_profile = false, env_no_migrate = false;
   // developer knobs (EmDeeX_tune; tools/force_lab.py): force-kernel variant and L1/shared carveout of the plain-LJ kernel
   int tune_variant = 0, tune_carveout = -1;
+  DBuf<double> labSoa;             // tools/force_lab.py variants only
+  DBuf<int> labHalf, labHalfCount;
+  long long labHalfBuild = -1, buildSerial = 0;
 
   // host-visible results: pinned slots the last block of a reducing kernel writes; the host spins on the sequence number
   HostSlot* slots = nullptr;
@@ -169,11 +172,12 @@ struct Engine::Impl {
 
   // non-intrusive kernel timing (EmDeeX_set_kernel_timing): event pairs in a ring, harvested when the ring wraps or when
   // the statistics are read, never by a synchronisation on the step path
-  static constexpr int NTIMERS = 64;
+  static constexpr int NTIMERS = 256, NKINDS = 8;
   struct Timer { cudaEvent_t a = nullptr, b = nullptr; int kind = -1; };
   Timer timers[NTIMERS];
   int timer_head = 0, last_force_timer = -1;
-  double timed_ms[2] = {0.0, 0.0};   // [0] force kernel, [1] list-build kernel
+  double timed_ms[NKINDS] = {0, 0, 0, 0, 0, 0, 0, 0};   // [0] force kernel, [1] list-build kernel, then engine.h TIMER_* kinds
+  long long timed_n[NKINDS] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   // reductions
   DBuf<MaxNext> chkPartial;
@@ -337,7 +341,7 @@ Engine::~Engine() {
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
-  s.known.release(); s.migCounts.release(); s.ownedList.release();
+  s.known.release(); s.migCounts.release(); s.ownedList.release(); s.labSoa.release(); s.labHalf.release(); s.labHalfCount.release();
   s.terms.release(); s.termFirst.release(); s.termRef.release();
   s.ewN.release(); s.ewKType.release(); s.ewPrefac.release(); s.ewLambda.release(); s.ewSigma.release(); s.ewPartial.release();
   s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
@@ -656,36 +660,64 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
 
 // Plain single-type Lennard-Jones: the benchmark kernel. Variant 0 is what ships; the others exist for tools/force_lab.py
 // (EmDeeX_tune "force_variant" / "carveout"), which times them back to back on one resident system.
-//   columns: UNROLL, THREADS, MINBLOCKS, index-stream load, position-gather load, PROBE
-#define EMDEE_LJ_VARIANTS(X)                                  \
-  X(0, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0)                      \
-  X(1, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
-  X(2, 6, 512, 2, LD_NO_ALLOCATE, LD_EVICT_LAST, 0)           \
-  X(3, 6, 512, 2, LD_PLAIN, LD_PLAIN, 1)                      \
-  X(4, 6, 512, 2, LD_PLAIN, LD_PLAIN, 2)                      \
-  X(5, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 1)                \
-  X(6, 4, 256, 4, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
-  X(7, 8, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
-  X(8, 6, 1024, 1, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
-  X(9, 3, 256, 5, LD_NO_ALLOCATE, LD_PLAIN, 0)                \
-  X(10, 2, 128, 8, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
-  X(11, 6, 256, 4, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
-  X(12, 4, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0)               \
-  X(13, 6, 512, 2, LD_EVICT_FIRST, LD_PLAIN, 0)               \
-  X(14, 6, 512, 2, LD_EVICT_FIRST, LD_EVICT_LAST, 0)          \
-  X(15, 3, 128, 10, LD_NO_ALLOCATE, LD_PLAIN, 0)              \
-  X(16, 6, 128, 8, LD_NO_ALLOCATE, LD_PLAIN, 0)
+//   columns: UNROLL, THREADS, MINBLOCKS, index-stream load, position-gather load, PROBE, FORM
+#define EMDEE_LJ_VARIANTS(X)                                                \
+  X(0, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
+  X(1, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0, FORM_DEFAULT)                \
+  X(3, 6, 512, 2, LD_PLAIN, LD_PLAIN, 1, FORM_DEFAULT)                      \
+  X(4, 6, 512, 2, LD_PLAIN, LD_PLAIN, 2, FORM_DEFAULT)                      \
+  X(6, 4, 256, 4, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
+  X(7, 8, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
+  X(10, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
+  X(11, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
+  X(12, 8, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
+  X(13, 4, 256, 4, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
+  X(14, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_SOA)                         \
+  X(15, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_SOA)                         \
+  X(16, 8, 256, 3, LD_PLAIN, LD_PLAIN, 0, FORM_SOA)
+constexpr int VARIANT_SOA_FIRST = 14, VARIANT_SOA_LAST = 16, VARIANT_N3 = 19, VARIANT_N3_B = 20;
 
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
-  switch (s.tune_variant) {
-#define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR)                                                                          \
+  const int v = s.tune_variant;
+  if (v >= VARIANT_SOA_FIRST && v <= VARIANT_SOA_LAST) {   // lab only: x[], y[], z[] copies of the refreshed positions
+    s.labSoa.ensure(3 * (size_t)a.Next);
+    k_pos_to_soa<<<nblocks(a.Next), TPB, 0, s.stream>>>(a.Next, a.pos, s.labSoa.p);
+    a.soa = s.labSoa.p;
+  }
+  if (v == VARIANT_N3 || v == VARIANT_N3_B) {   // lab only: Newton's third law over a half list, scatter by red.global.add.f64
+    if (s.labHalfBuild != s.buildSerial) {
+      s.labHalf.ensure(s.nbr.n);
+      s.labHalfCount.ensure((size_t)a.Next + 32);
+      k_halve_list<<<nblocks(a.Next), TPB, 0, s.stream>>>(a.Next, a.cap, a.nbr, a.nbrCount, a.sMeta, s.labHalf.p, s.labHalfCount.p);
+      s.labHalfBuild = s.buildSerial;
+    }
+    a.nbrHalf = s.labHalf.p;
+    a.nbrCountHalf = s.labHalfCount.p;
+    CUDA_CHECK(cudaMemsetAsync(a.F, 0, 3 * (size_t)s.N * sizeof(double), s.stream));
+    if (v == VARIANT_N3) {
+      const int grid = nblocks(a.Next, 256);
+      s.partial.ensure((size_t)grid * 5);
+      a.partial = s.partial.p;
+      if (compute) k_pair_forces_n3<true, 4, 256, 4><<<grid, 256, 0, s.stream>>>(a);
+      else k_pair_forces_n3<false, 4, 256, 4><<<grid, 256, 0, s.stream>>>(a);
+    } else {
+      const int grid = nblocks(a.Next, 512);
+      s.partial.ensure((size_t)grid * 5);
+      a.partial = s.partial.p;
+      if (compute) k_pair_forces_n3<true, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a);
+      else k_pair_forces_n3<false, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a);
+    }
+    return;
+  }
+  switch (v) {
+#define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
       const int grid = nblocks(a.Next, TH);                                                                                \
       s.partial.ensure((size_t)grid * 5);                                                                                  \
       a.partial = s.partial.p;                                                                                             \
-      auto kt = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, true, UN, TH, MB, LL, PL, PR>;       \
-      auto kf = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, false, UN, TH, MB, LL, PL, PR>;      \
+      auto kt = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, true, UN, TH, MB, LL, PL, PR, FO>;   \
+      auto kf = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, false, UN, TH, MB, LL, PL, PR, FO>;  \
       if (s.tune_carveout >= 0) {                                                                                          \
         CUDA_CHECK(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, s.tune_carveout));             \
         CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, s.tune_carveout));             \
@@ -810,6 +842,7 @@ void Engine::timer_harvest(int idx) {
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, t.a, t.b));
   s.timed_ms[t.kind] += ms;
+  s.timed_n[t.kind] += 1;
   t.kind = -1;
 }
 int Engine::timer_begin(int kind) {
@@ -836,6 +869,13 @@ EngineStats Engine::stats() {
   stats_.build_ms = d_->timed_ms[1];
   return stats_;
 }
+void Engine::kernel_times(double* ms8, long long* n8) {
+  for (int k = 0; k < Impl::NTIMERS; ++k) timer_harvest(k);
+  for (int k = 0; k < Impl::NKINDS; ++k) {
+    ms8[k] = d_->timed_ms[k];
+    n8[k] = d_->timed_n[k];
+  }
+}
 
 bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars& out, double& neighbor_seconds) {
   Impl& s = *d_;
@@ -854,7 +894,9 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   if (dist) {
     // several GPUs: halo positions + every rank's criterion state travel in one NCCL group, the decision is taken on the
     // device (scalars[CRIT_DIST..]) and the pair kernel is launched speculatively against it, as on one GPU
+    const int tmr_x = timer_begin(TIMER_EXCHANGE);
     exchange_step(s, true);
+    timer_end(tmr_x);
     speculative = true;
     stats_.launches += 2;
   } else if (s.check_cached && s.list_valid && s.world == 1) {
@@ -1001,6 +1043,7 @@ void Engine::rebuild_list(double Lbox) {
     s.cellFill.ensure(ncell + 1);
     CUDA_CHECK(cudaMemsetAsync(s.cellCount.p, 0, (ncell + 1) * sizeof(int), s.stream));
     CUDA_CHECK(cudaMemsetAsync(s.cellFill.p, 0, (ncell + 1) * sizeof(int), s.stream));
+    const int tmr_b = timer_begin(TIMER_BINNING);
     k_bin<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, N, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p, s.owned.p,
                                             s.world > 1 ? s.known.p : nullptr, s.cellCount.p);
     size_t need = 0;
@@ -1034,6 +1077,7 @@ void Engine::rebuild_list(double Lbox) {
     pa.atomBody = s.body.p; pa.owned = s.owned.p; pa.sMeta = s.sMeta.p; pa.sCell = s.sCell.p; pa.sGhost = s.sGhost.p; pa.sType = s.sType.p;
     pa.sBody = s.sBody.p; pa.sRs = s.sRs.p; pa.sPosF = s.sPosF.p; pa.nbrCount = s.nbrCount.p;
     k_place<<<nblocks(Next), TPB, 0, s.stream>>>(pa);
+    timer_end(tmr_b);
     stats_.launches += 4;
     // capacity guess from the mean density; grown on overflow
     if (s.cap == 0) {
@@ -1062,6 +1106,7 @@ void Engine::rebuild_list(double Lbox) {
       timer_end(tmr);
       stats_.launches += 1;
       stats_.build_launches += 1;
+      s.buildSerial += 1;
       int hflags[4];
       CUDA_CHECK(cudaMemcpyAsync(hflags, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
       CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -1097,7 +1142,9 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   const double invL2 = 1.0 / (Lbox * Lbox);
   double* Fl = s.F.p + (size_t)layer0 * 3 * N;
   const int Next = s.Next;
+  const int tmr_r = timer_begin(TIMER_REFRESH);
   k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
+  timer_end(tmr_r);
   ForceArgs a;
   a.Next = Next; a.cap = s.cap; a.nt = s.nt;
   a.Rc2s = (lt.useInRc ? s.InRcSq : s.RcSq) * invL2;
@@ -1113,6 +1160,7 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   a.skinSq = s.skinSq;
   a.hs = (s.world > 1) ? nullptr : s.slots + SLOT_FORCE;   // several GPUs: the scalars are all-reduced first
   a.seq = s.next_seq(SLOT_FORCE);
+  a.soa = nullptr; a.nbrHalf = nullptr; a.nbrCountHalf = nullptr;
 
   // classify the layer for kernel selection
   bool uniform = true;
@@ -1154,9 +1202,11 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
   if (s.world > 1 && s.owned_valid) {
     // several GPUs: the kick runs over the compact list of owned atoms (work ~ atoms of this rank, not N); the kinetic
     // sums take one all-reduce and reach the host through the pinned slot
+    const int tmr = timer_begin(TIMER_BOOST);
     k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CP, CF, s.P.p, Fl, s.invMass.p,
                                                                       want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1,
                                                                       s.scalars.p + 10);
+    timer_end(tmr);
     stats_.launches += 1;
     if (want_kinetic) {
       NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
@@ -1169,8 +1219,10 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
     const int grid = nblocks((s.N + APT - 1) / APT);
     HostSlot* hs = want_kinetic ? s.slots + SLOT_KINETIC : nullptr;   // the last block writes the sums to the host slot
     const unsigned long long seq = want_kinetic ? s.next_seq(SLOT_KINETIC) : 0ull;
+    const int tmr = timer_begin(TIMER_BOOST);
     k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, nullptr, want_kinetic ? 1 : 0, s.partial.p,
                                         s.tickets.p + 1, s.scalars.p + 10, hs, seq);
+    timer_end(tmr);
     stats_.launches += 1;
     if (want_kinetic) {
       s.wait_slot(SLOT_KINETIC);
@@ -1188,9 +1240,11 @@ void Engine::displace(double CR, double CP) {
   const double tp0 = wall_now();
   if (s.world > 1 && s.owned_valid) {
     // owned atoms only (compact list); phase 1 of the rebuild criterion on the new coordinates lands in miResult[world]
+    const int tmr = timer_begin(TIMER_DISPLACE);
     k_displace_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
                                                                          s.R0.p, s.miPartial.p, s.tickets.p + 2,
                                                                          s.miResult.p + s.world);
+    timer_end(tmr);
     stats_.launches += 1;
     s.mi_fresh = true;
     s.halo_fresh = false;
@@ -1199,8 +1253,10 @@ void Engine::displace(double CR, double CP) {
   } else {
     // the rebuild criterion of the new coordinates lands in scalars[8] on the device; compute_forces launches the pair
     // kernel speculatively against it instead of waiting for it here
+    const int tmr = timer_begin(TIMER_DISPLACE);
     k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p, s.chkPartial.p,
                                                    s.tickets.p + 2, s.scalars.p + 8);
+    timer_end(tmr);
     stats_.launches += 1;
     s.check_cached = true;
   }

@@ -140,6 +140,9 @@ class Engine {
   void synchronize();
   void* stream_handle();   // the cudaStream_t every kernel of this system is launched on
   EngineStats stats();
+  // accumulated CUDA-event time (ms) and launch count per kernel kind (TIMER_*), when kernel timing is on
+  enum { TIMER_FORCE = 0, TIMER_BUILD = 1, TIMER_BOOST = 2, TIMER_DISPLACE = 3, TIMER_REFRESH = 4, TIMER_EXCHANGE = 5, TIMER_BINNING = 6, TIMER_OTHER = 7 };
+  void kernel_times(double* ms8, long long* n8);
 
   // ---- multi-GPU: one rank per GPU, z-slab decomposition (NCCL) ---------------------------------
   void comm_init(int rank, int world, const void* nccl_unique_id);

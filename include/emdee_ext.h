@@ -53,6 +53,11 @@ void EmDeeX_stats( tEmDee md, tEmDeeXStats* out );
    no synchronisation is added to the step). */
 void EmDeeX_set_kernel_timing( tEmDee md, int enabled );
 
+/* Accumulated device time (ms) and launch count per kernel kind while kernel timing is enabled:
+   [0] pair forces, [1] list build, [2] boost, [3] displace, [4] position refresh, [5] halo/criterion exchange (several GPUs),
+   [6] binning + cell sort of a rebuild, [7] unused. Both arrays hold 8 entries. */
+void EmDeeX_kernel_times( tEmDee md, double* ms8, long long* n8 );
+
 /* Block until all queued device work of this system has finished. */
 void EmDeeX_synchronize( tEmDee md );
 

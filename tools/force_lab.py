@@ -59,6 +59,25 @@ def main():
                   f"force launches/step {fl / args.steps:.2f} | builds {s.md.Builds - b0} | U {s.md.Energy.Potential:.6f}", flush=True)
     lib.EmDeeX_tune(s.md, b"force_variant", 0)
     lib.EmDeeX_tune(s.md, b"carveout", -1)
+    # per-kernel device time of the default step (CUDA events from the library's ring), in-situ (warm caches)
+    k0 = s.kernel_times()
+    b0 = s.md.Builds
+    t0 = time.perf_counter()
+    for _ in range(2 * args.steps):
+        bench.md_step(s)
+    s.synchronize()
+    dt = time.perf_counter() - t0
+    k1 = s.kernel_times()
+    nst = 2 * args.steps
+    line = []
+    tot = 0.0
+    for kind in s.KERNEL_KINDS:
+        ms, n = k1[kind][0] - k0[kind][0], k1[kind][1] - k0[kind][1]
+        if n:
+            line.append(f"{kind} {ms / n * 1e3:.1f} us x {n / nst:.2f}/step")
+            tot += ms
+    print(f"# default step, {nst} steps, {s.md.Builds - b0} builds: {1e3 * dt / nst:.4f} ms/step wall; kernels: " + "; ".join(line) +
+          f"; timed kernels sum {tot / nst:.4f} ms/step", flush=True)
     s.finalize()
 
 
