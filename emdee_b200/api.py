@@ -125,6 +125,7 @@ ABI_EXT_PRODUCT = {
     "EmDeeX_stats": (None, [tEmDee, C.POINTER(tEmDeeXStats)]),
     "EmDeeX_set_kernel_timing": (None, [tEmDee, C.c_int]),
     "EmDeeX_synchronize": (None, [tEmDee]),
+    "EmDeeX_io_bytes": (None, [tEmDee, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "EmDeeX_kernel_times": (None, [tEmDee, _dp, C.POINTER(C.c_longlong)]),
     "EmDeeX_tune": (None, [tEmDee, C.c_char_p, C.c_int]),
     "EmDeeX_stream": (C.c_void_p, [tEmDee]),
@@ -273,6 +274,10 @@ class System:
         self.lib.EmDee_share_phase_space(self.md, C.byref(other.md))
 
     # extensions -----------------------------------------------------------------------------
+    def pair_count(self) -> int:
+        """Number of neighbor pairs held by this process's list (each pair once)."""
+        return int(self.lib.EmDeeX_pair_count(self.md))
+
     def pairs(self) -> np.ndarray:
         """Neighbor pairs as a lexicographically sorted (npairs, 2) int32 array (0-based)."""
         n = int(self.lib.EmDeeX_pair_count(self.md))
@@ -292,6 +297,12 @@ class System:
 
     def synchronize(self):
         self.lib.EmDeeX_synchronize(self.md)
+
+    def io_bytes(self):
+        """(h2d, d2h) bytes moved so far by coordinate uploads / force downloads."""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self.lib.EmDeeX_io_bytes(self.md, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     KERNEL_KINDS = ("force", "build", "boost", "displace", "refresh", "exchange", "binning", "other")
 

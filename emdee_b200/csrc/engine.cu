@@ -117,6 +117,7 @@ struct Engine::Impl {
   // local I/O (EmDeeX_tune "local_io", several GPUs): coordinate uploads read only the atoms this rank owns or keeps as
   // halo, force downloads write only the atoms it owns, both straight from / to the caller's pinned host array
   bool local_io = false;
+  long long io_h2d = 0, io_d2h = 0;   // bytes moved by coordinate uploads / force downloads (EmDeeX_io_bytes)
 
   // rigid bodies (engine_bodies.cuh): CSR of members + SoA state, 27 doubles per body
   int nitems = 0;
@@ -143,7 +144,7 @@ struct Engine::Impl {
   // environment switches, read once at construction (nothing on the per-step path calls getenv)
   bool env_debug = false, env_profile = false, env_no_migrate = false;
   // developer knobs (EmDeeX_tune; tools/force_lab.py): force-kernel variant and L1/shared carveout of the plain-LJ kernel
-  int tune_variant = 0, tune_carveout = -1;
+  int tune_variant = 0, tune_carveout = -1, tune_build = 0;
   DBuf<double> labSoa;             // tools/force_lab.py variants only
   DBuf<int> labHalf, labHalfCount;
   long long labHalfBuild = -1, buildSerial = 0;
@@ -603,10 +604,40 @@ void Engine::set_layer(int layer0, const LayerTable& t) {
   CUDA_CHECK(cudaMemcpy(s.tabs[layer0].p, t.pair.data(), t.pair.size() * sizeof(PairEntry), cudaMemcpyHostToDevice));
 }
 
+namespace {
+// device-side alias of a pinned (page-locked, mapped) host pointer, or nullptr when the memory is pageable
+double* mapped_alias(const double* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return at.type == cudaMemoryTypeHost ? static_cast<double*>(at.devicePointer) : nullptr;
+}
+}  // namespace
+
 void Engine::upload_coordinates(const double* R) {
   Impl& s = *d_;
+  if (s.local_io && s.world > 1 && s.owned_valid && !s.all_known) {
+    // local I/O: this rank reads only the atoms it owns and its halo atoms, straight from the caller's pinned array.
+    // Contract (as for the resident dynamics): between two uploads no atom moves further than one cell layer.
+    if (const double* src = mapped_alias(R)) {
+      if (s.nOwn > 0) k_copy3_listed<<<nblocks(s.nOwn), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, src, s.R.p);
+      for (int k = 2; k < 4; ++k)
+        if (s.haloCount[k] > 0)
+          k_copy3_listed<<<nblocks(s.haloCount[k]), TPB, 0, s.stream>>>(s.haloCount[k], s.haloList[k].p, src, s.R.p);
+      CUDA_CHECK(cudaStreamSynchronize(s.stream));
+      stats_.launches += 3;
+      s.io_h2d += 24LL * ((long long)s.nOwn + s.haloCount[2] + s.haloCount[3]);
+      s.check_cached = false;
+      s.mi_fresh = false;
+      s.halo_fresh = true;
+      return;
+    }
+  }
   CUDA_CHECK(cudaMemcpyAsync(s.R.p, R, 3 * (size_t)s.N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  s.io_h2d += 24LL * s.N;
   s.has_R = true;
   s.check_cached = false;
   s.mi_fresh = false;
@@ -633,13 +664,30 @@ void Engine::download_momenta(double* P) {
   CUDA_CHECK(cudaMemcpy(P, d_->P.p, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::download_forces(int layer0, double* F) {
-  gather_full(*d_, d_->F.p + (size_t)layer0 * 3 * d_->N);
-  CUDA_CHECK(cudaMemcpy(F, d_->F.p + (size_t)layer0 * 3 * d_->N, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
+  Impl& s = *d_;
+  double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
+  if (s.local_io && s.world > 1 && s.owned_valid) {
+    // local I/O: only the forces of the atoms this rank owns are written (the caller's array keeps its other entries);
+    // not a collective
+    if (double* dst = mapped_alias(F)) {
+      if (s.nOwn > 0) k_copy3_listed<<<nblocks(s.nOwn), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, Fl, dst);
+      CUDA_CHECK(cudaStreamSynchronize(s.stream));
+      stats_.launches += 1;
+      s.io_d2h += 24LL * s.nOwn;
+      return;
+    }
+  }
+  gather_full(s, Fl);
+  CUDA_CHECK(cudaMemcpy(F, Fl, 3 * (size_t)s.N * sizeof(double), cudaMemcpyDeviceToHost));
+  s.io_d2h += 24LL * s.N;
 }
+void Engine::io_bytes(long long& h2d, long long& d2h) { h2d = d_->io_h2d; d2h = d_->io_d2h; }
 void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
 void Engine::tune(const char* knob, int value) {
   if (std::strcmp(knob, "force_variant") == 0) d_->tune_variant = value;
   else if (std::strcmp(knob, "carveout") == 0) d_->tune_carveout = value;
+  else if (std::strcmp(knob, "build_variant") == 0) d_->tune_build = value;
+  else if (std::strcmp(knob, "local_io") == 0) d_->local_io = value != 0;
   else fatal("tuning", "unknown knob");
 }
 void* Engine::stream_handle() { return (void*)d_->stream; }
@@ -1102,7 +1150,8 @@ void Engine::rebuild_list(double Lbox) {
       // write-out was measured 6x slower at LJ-1M -- serial per-atom dependency chains at ~12 warps/SM --
       // and removed)
       const int tmr = timer_begin(1);
-      k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      if (s.tune_build == 1) k_build_list_nested<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      else k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
       timer_end(tmr);
       stats_.launches += 1;
       stats_.build_launches += 1;

@@ -136,8 +136,9 @@ class Engine {
   void rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_scaled, const std::vector<unsigned short>& pairSym,
            int nsym, std::vector<long long>& counts);
   void set_kernel_timing(bool on) { timing_ = on; }
-  void tune(const char* knob, int value);   // developer knobs (tools/force_lab.py): "force_variant", "carveout"
+  void tune(const char* knob, int value);   // "local_io" (several GPUs, see upload_coordinates); developer knobs of tools/force_lab.py: "force_variant", "carveout"
   void synchronize();
+  void io_bytes(long long& h2d, long long& d2h);   // bytes moved so far by coordinate uploads / force downloads
   void* stream_handle();   // the cudaStream_t every kernel of this system is launched on
   EngineStats stats();
   // accumulated CUDA-event time (ms) and launch count per kernel kind (TIMER_*), when kernel timing is on

@@ -268,6 +268,19 @@ __global__ void __launch_bounds__(TPB) k_halo_flags(int N, GridDesc g, const int
   fl[3 * (size_t)N + i] = !own && (cz == up0 || cz == up1);   // receive from above
 }
 
+// local I/O (EmDeeX_tune "local_io"): three doubles per listed atom between the caller's pinned, device-mapped host array
+// and the device array, both indexed by the atom; dst[a] = src[a] for a in list (zero-copy over PCIe, no staging buffer)
+__global__ void __launch_bounds__(TPB) k_copy3_listed(int n, const int* __restrict__ list, const double* __restrict__ src,
+                                                      double* __restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const size_t a = (size_t)list[k];
+  const double x = src[3 * a], y = src[3 * a + 1], z = src[3 * a + 2];
+  dst[3 * a] = x;
+  dst[3 * a + 1] = y;
+  dst[3 * a + 2] = z;
+}
+
 __global__ void __launch_bounds__(TPB) k_pack3(int n, const int* __restrict__ list, const double* __restrict__ X,
                                                double* __restrict__ buf) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -58,6 +58,9 @@ void EmDeeX_set_kernel_timing( tEmDee md, int enabled );
    [6] binning + cell sort of a rebuild, [7] unused. Both arrays hold 8 entries. */
 void EmDeeX_kernel_times( tEmDee md, double* ms8, long long* n8 );
 
+/* Bytes moved so far between host and device by EmDee_upload("coordinates") and EmDee_download("forces"). */
+void EmDeeX_io_bytes( tEmDee md, long long* h2d, long long* d2h );
+
 /* Block until all queued device work of this system has finished. */
 void EmDeeX_synchronize( tEmDee md );
 

@@ -77,6 +77,13 @@ struct cudaTextureDesc { cudaTextureReadMode readMode; };
 
 inline const char* cudaGetErrorString(cudaError_t) { return "cusim error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+// every host pointer counts as pinned + mapped (the emulated "device" is the host)
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  a->type = cudaMemoryTypeHost; a->device = 0; a->devicePointer = const_cast<void*>(p); a->hostPointer = const_cast<void*>(p);
+  return cudaSuccess;
+}
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
