@@ -59,11 +59,18 @@ def make_workload(ncell, seed=86245):
     return np.ascontiguousarray(R), np.ascontiguousarray(P), L
 
 
-def build_system(lib, R, P, L, threads, before_upload=None):
+def build_system(lib, R, P, L, threads, before_upload=None, workload="lj"):
     s = lib.system(threads, 1, RC, SKIN, R.shape[0], None, None, None)
     if before_upload is not None:
         before_upload(s)          # multi-GPU: hand the system its communicator before any upload
-    s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0)
+    if workload == "lj_coul_sf":
+        # BASELINE.json configs[4] / SURVEY 8(d): charges +0.5/-0.5 alternating by fcc basis index (neutral), kCoul = 1,
+        # coul_sf through the reference's own setter order (quirk Q1 applies to both arms alike)
+        s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 1.0)
+        s.set_coul_model(lib.EmDee_coul_sf())
+        s.upload("charges", np.where(np.arange(R.shape[0]) % 2 == 0, 0.5, -0.5))
+    else:
+        s.set_pair_model(1, 1, lib.EmDee_pair_lj_cut(1.0, 1.0), 0.0)
     s.upload("box", np.array([L]))
     s.upload("coordinates", R)
     s.upload("momenta", P)
@@ -143,11 +150,12 @@ def oracle_lib():
     return api.EmDeeLib(path)
 
 
-def cpu_run(ncell, steps, warmup, threads):
+def cpu_run(ncell, steps, warmup, threads, workload="lj"):
     """Times the reference algorithm (oracle port) on `threads` host cores: same workload, same step."""
     lib = oracle_lib()
     R, P, L = make_workload(ncell)
-    s = build_system(lib, R, P, L, threads)
+    s = build_system(lib, R, P, L, threads, workload=workload)
+    U0, W0 = s.md.Energy.Potential, s.md.Virial.Total   # step-0 state (the first upload evaluates the forces)
     for _ in range(warmup):
         md_step(s)
     t0 = time.perf_counter()
@@ -156,43 +164,65 @@ def cpu_run(ncell, steps, warmup, threads):
     dt = time.perf_counter() - t0
     N = R.shape[0]
     out = {"value": N * steps / dt, "seconds": dt, "steps": steps, "N": N, "builds": int(s.md.Builds),
-           "U": s.md.Energy.Potential}
+           "U": s.md.Energy.Potential, "W": s.md.Virial.Total, "K": s.md.Kinetic.Total, "U0": U0, "W0": W0}
     s.finalize()
     return out
 
 
+def total_ncell(args, world):
+    """fcc cells per dimension of the whole job: weak scaling grows the box with the rank count (about `--ncell`^3 x 4
+    atoms per GPU, cubic box), strong scaling keeps the `--ncell` box whatever the rank count."""
+    base = args.ncell
+    if args.atoms_per_gpu:
+        base = max(8, int(round((args.atoms_per_gpu / 4.0) ** (1.0 / 3.0))))
+    if world == 1 or args.scaling == "strong":
+        return base
+    return int(round(base * world ** (1.0 / 3.0)))
+
+
+def parallelism(world):
+    return "single GPU" if world == 1 else (f"z-slab decomposition over {world} GPUs: one NCCL group per step (halo positions + "
+                                            f"rebuild-criterion state), one all-reduce of the energies, no reverse force exchange")
+
+
+def workload_config(args, ncell, N, world):
+    what = {"lj": "pair_lj_cut(1,1) (BASELINE.json configs[3])",
+            "lj_coul_sf": "pair_lj_cut(1,1) + coul_sf, charges +-0.5 by basis index, kCoul=1 (BASELINE.json configs[4])"}[args.workload]
+    return {"workload": f"synthetic fluid, fcc {ncell}^3 x 4 = {N} atoms in one cubic box, rho*=0.8442, Rc=2.5, skin=0.3, "
+                        f"{what}, T*=1.44, dt=0.005, energy+virial every step",
+            "atoms_per_gpu": N // world, "atoms_total": N, "rc": RC, "skin": SKIN, "dt": DT,
+            "parallelism": parallelism(world),
+            "l2_policy": "inputs larger than L2: the neighbor list streamed every step (>300 MB per million atoms) exceeds the 126 MB L2"}
+
+
 def reference_arm(args, rank, world):
+    """The reference ALGORITHM on the box's host cores (C++/OpenMP restatement, oracle/): same box, same step as the product
+    arm at this rank count; each run a bounded sample (the step count below) so that it ends within minutes."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     threads = int(os.environ.get("EMDEE_CPU_THREADS", cores))
-    ncell = args.ncell if world == 1 else int(round(args.ncell * world ** (1.0 / 3.0)))
+    ncell = total_ncell(args, world)
     N = 4 * ncell ** 3
-    # bounded sample: the same box as the product arm at this N, a few steps (~0.2-1 s each per million atoms)
-    steps = max(1, min(args.steps, 20 if world == 1 else max(2, 20 // world)))
+    # bounded sample: about 0.2-0.4 s per step and million atoms on 16-32 cores
+    budget_steps = max(2, int(20e6 // N))
+    steps = max(1, min(args.steps, budget_steps))
     warmup = max(1, min(args.warmup, 3))
-    r = cpu_run(ncell, steps, warmup, threads)
+    r = cpu_run(ncell, steps, warmup, threads, args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(ncell, N, 1, "host cores (no GPU)"),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, ncell, N, world),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} velocity-Verlet steps of the {N}-atom LJ box after {warmup} warm-up "
-                                   f"({r['builds']} list builds); reference algorithm restated in C++/OpenMP "
-                                   f"(-Ofast), the Fortran reference cannot be built in this image"},
+                         "sample": f"{steps} velocity-Verlet steps of the {N}-atom box after {warmup} warm-up "
+                                   f"({r['builds']} list builds) on host cores, no GPU; reference algorithm restated in "
+                                   f"C++/OpenMP (-Ofast), the Fortran reference cannot be built in this image"},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "state": {"U": r["U"], "W": r["W"], "K": r["K"], "U_step0": r["U0"], "W_step0": r["W0"], "builds_total": r["builds"]},
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(ncell, N, world, where):
-    return {"workload": f"synthetic LJ fluid, fcc {ncell}^3 x 4 = {N} atoms in one cubic box, rho*=0.8442, Rc=2.5, skin=0.3, "
-                        f"pair_lj_cut(1,1), T*=1.44, dt=0.005, energy+virial every step (BASELINE.json configs[3])",
-            "atoms_per_gpu": N // world, "atoms_total": N, "rc": RC, "skin": SKIN, "dt": DT,
-            "parallelism": where,
-            "l2_policy": "inputs larger than L2: the neighbor list streamed every step (>300 MB at 1M atoms) exceeds the 126 MB L2"}
 
 
 def spce_line_multi_gpu(args, world):
@@ -262,28 +292,24 @@ def spce_line_multi_gpu(args, world):
     dist.destroy_process_group()
 
 
-def spce_line(args):
-    """Informational (not the contract line): SPC/E water, NIST sample replicated n^3 times, rigid bodies,
-    LJ shifted-force on O + pair_none on H + coul_damped_square_smoothed(0.2, 1.0) (reference test/test_coul_*.f90).
+def spce_measure(args, cpu=True):
+    """SPC/E water, NIST sample replicated n^3 times (n = 8: 1 152 000 atoms), rigid bodies, LJ shifted-force on O +
+    pair_none on H + coul_damped_square_smoothed(0.2, 1.0) (reference test/test_coul_damped_smoothed.f90:45).
     Two arms: (1) host buffers: a step = upload the configuration rigidly drifted a little further,
     EmDee_compute_forces, read the scalars (e2e by nature); (2) resident: NVE with the device-resident rigid-body
     integrator (EmDee_boost / EmDee_displace / EmDee_boost, exact free-rotor rotation), nothing crosses PCIe but the
-    per-step scalars. The CPU port runs the same two loops."""
-    import torch
+    per-step scalars. The CPU port runs the same two loops on a bounded sample. One GPU."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import common as cm
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        spce_line_multi_gpu(args, world)
-        return
     lib = api.load()
     n = args.replicas
     K, W = min(args.steps, 30), 3
     res = {}
-    for tag, thelib, steps in (("gpu", lib, K), ("cpu", oracle_lib(), 6)):
+    arms = [("gpu", lib, K)] + ([("cpu", oracle_lib(), 4)] if cpu else [])
+    for tag, thelib, steps in arms:
         s, c = cm.spce_sample_system(thelib, lambda l: l.EmDee_coul_damped_square_smoothed(0.2, 1.0), replicas=n,
                                      threads=os.cpu_count() or 1)
-        N, mol = c["N"], c["molecule"]
+        N = c["N"]
         calls = {"k": 0}
         drift = 0.17 * np.ones(3) / np.sqrt(3.0)
         def advance():
@@ -304,7 +330,7 @@ def spce_line(args):
             s.compute_forces()
         dt = time.perf_counter() - t0
         res[tag] = {"atom_steps_per_s": N * steps / dt, "ms_per_step": 1e3 * dt / steps, "builds": s.md.Builds - b0,
-                    "steps": steps, "U": s.md.Energy.Potential}
+                    "steps": steps, "U": s.md.Energy.Potential, "N": N}
         if tag == "gpu":
             st1 = s.stats()
             fl = st1.force_launches - st0.force_launches
@@ -315,7 +341,7 @@ def spce_line(args):
         # ---- resident arm: rigid-body NVE on the device (dt = 1 fs, 298 K) ----
         s.upload("coordinates", c["R"])
         s.random_momenta(c["kB"] * c["Temp"], True, 86245)
-        dt_fs, nres = 1.0, (steps if tag == "gpu" else 4)
+        dt_fs, nres = 1.0, (steps if tag == "gpu" else 3)
         def nve(k):
             for _ in range(k):
                 s.boost(1.0, 0.0, 0.5 * dt_fs)
@@ -331,10 +357,88 @@ def spce_line(args):
                                 "builds": s.md.Builds - b0,
                                 "energy_drift_rel": abs(s.md.Energy.Potential + s.md.Kinetic.Total - E0) / abs(s.md.Kinetic.Total)}
         s.finalize()
-    print(json.dumps({"metric": METRIC, "workload": f"SPC/E NIST sample x {n}^3 = {N} atoms, Rc=10 A, skin=2 A, rigid bodies, "
-                      "coul_damped_square_smoothed(0.2,1.0) as in reference test/test_coul_damped_smoothed.f90:45; arm 1: upload + compute_forces per step; arm 'resident': NVE with the "
-                      "device-resident rigid-body integrator", "informational": True,
-                      "gpu": res["gpu"], "cpu_port": res["cpu"], "cores": os.cpu_count()}), flush=True)
+    res["workload"] = (f"SPC/E NIST sample x {n}^3 = {res['gpu']['N']} atoms, Rc=10 A, skin=2 A, rigid bodies, "
+                       "coul_damped_square_smoothed(0.2,1.0) as in reference test/test_coul_damped_smoothed.f90:45")
+    return res
+
+
+def spce_block(args, cpu=True):
+    """The SPC/E half of the headline metric ("LJ & SPC/E"), shaped like the contract line: value = resident rigid-body NVE,
+    e2e = the host-buffer arm, roofline of the pair kernel, CPU port beside it."""
+    r = spce_measure(args, cpu)
+    g = r["gpu"]
+    N = g["N"]
+    C_half, P_half = g["list_entries_per_atom_half"], g["interacting_per_atom_half"]
+    # SURVEY 8(d): 15 per listed pair (separation + cutoff test); per interacting pair 1 sqrt + ~24 for the damped, smoothed
+    # Coulomb term (1 exp, 2 div) on the charged pairs (all of them in water) and 22 + 4 for the shifted-force LJ term on the
+    # O-O pairs (1/9 of the pairs)
+    flops_per_atom = 15.0 * C_half + P_half * (25.0 + 26.0 / 9.0) + 6.0
+    fm = g["force_kernel_ms"]
+    peak = api.load().EmDeeX_measure_fp64_tflops()
+    ach = flops_per_atom * N / (fm * 1e-3) / 1e12 if fm > 0 else None
+    out = {"workload": r["workload"], "value": g["resident"]["atom_steps_per_s"], "unit": UNIT,
+           "ms_per_step": g["resident"]["ms_per_step"], "steps": g["resident"]["steps"], "builds": g["resident"]["builds"],
+           "energy_drift_rel": g["resident"]["energy_drift_rel"],
+           "what": "value: resident NVE with the device rigid-body integrator (EmDee_boost / EmDee_displace / EmDee_boost); "
+                   "e2e: EmDee_upload(coordinates, host) + EmDee_compute_forces per step",
+           "e2e": {"value": g["atom_steps_per_s"], "unit": UNIT, "ms_per_step": g["ms_per_step"], "h2d_bytes_per_step": 24 * N,
+                   "d2h_bytes_per_step": 40, "steps": g["steps"], "builds": g["builds"]},
+           "timing": {"force_kernel_ms": fm, "build_kernel_ms": g["build_kernel_ms"]},
+           "roofline": {"bound": "fp64", "kernel": "k_pair_forces_typed", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": (ach / peak) if (ach and peak) else None, "algorithmic_flops_per_atom": flops_per_atom,
+                        "list_entries_per_atom_half": C_half, "interacting_per_atom_half": P_half,
+                        "peak_source": "DFMA microbenchmark run in this process"},
+           "state": {"U": g["U"]}}
+    if "cpu" in r:
+        c = r["cpu"]
+        out["cpu_baseline"] = {"value": c["resident"]["atom_steps_per_s"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": f"{c['resident']['steps']} rigid-body NVE steps of the same box (resident arm); host-buffer arm "
+                                         f"{c['atom_steps_per_s']:.4g} atom-steps/s over {c['steps']} evaluations; U = {c['U']!r}",
+                               "e2e_value": c["atom_steps_per_s"]}
+    return out
+
+
+def spce_line(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        spce_line_multi_gpu(args, world)
+        return
+    r = spce_measure(args)
+    print(json.dumps({"metric": METRIC, "workload": r["workload"] + "; arm 1: upload + compute_forces per step; arm 'resident': NVE "
+                      "with the device-resident rigid-body integrator", "informational": True,
+                      "gpu": r["gpu"], "cpu_port": r.get("cpu"), "cores": os.cpu_count()}), flush=True)
+
+
+def parity_block(lib, s, args, world, rank, dist, ncell, R, P, L, before_upload):
+    """Step-0 parity of the distributed (or single-GPU) product against the CPU oracle on rank 0, outside the timed region:
+    potential energy, virial and the number of neighbor pairs (pair SETS are compared bit for bit in tests/). Boxes the
+    oracle cannot hold (more than ~10M atoms) are checked on an 8M-atom box cut into the same number of slabs."""
+    import torch
+    sub = None
+    if R.shape[0] > 10_000_000:
+        sub = 126
+        Rc_, Pc_, Lc_ = make_workload(sub)
+        sp = build_system(lib, Rc_, Pc_, Lc_, 1, before_upload=before_upload, workload=args.workload)
+    else:
+        sp, Rc_, Pc_, Lc_ = s, R, P, L
+    U, W = sp.md.Energy.Potential, sp.md.Virial.Total
+    npairs = torch.tensor([sp.pair_count()], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(npairs)
+    out = None
+    if rank == 0:
+        so = build_system(oracle_lib(), Rc_, Pc_, Lc_, os.cpu_count() or 1, workload=args.workload)
+        Uo, Wo, no = so.md.Energy.Potential, so.md.Virial.Total, so.pair_count()
+        so.finalize()
+        out = {"U_rel": abs(U - Uo) / abs(Uo), "W_rel": abs(W - Wo) / abs(Wo), "pairs_equal": int(npairs.item()) == int(no),
+               "pairs": int(npairs.item()), "U": U, "U_oracle": Uo, "atoms": int(Rc_.shape[0]),
+               "what": "step-0 potential energy, virial and neighbor-pair count vs the CPU oracle (strict reference arithmetic) "
+                       "on rank 0" + (f"; {R.shape[0]}-atom box exceeds the oracle: checked on fcc {sub}^3 x 4 over the same ranks" if sub else "")}
+    if sub is not None:
+        sp.finalize()
+    if world > 1:
+        dist.barrier()
+    return out
 
 
 def main():
@@ -343,12 +447,18 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
-    ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="fcc cells per dimension (atoms = 4*ncell^3)")
+    ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="fcc cells per dimension per GPU (atoms = 4*ncell^3)")
+    ap.add_argument("--atoms-per-gpu", type=int, default=0, help="alternative to --ncell: atoms per GPU (rounded to an fcc box)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the box grows with the rank count; strong: the --ncell box is cut into more slabs")
     ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="lj", choices=["lj", "spce"],
-                    help="lj: the contract workload (BASELINE.json configs[3]); spce: informational line for the "
-                         "SPC/E n^3 replica box (force evaluations on uploaded configurations)")
+    ap.add_argument("--no-spce", action="store_true", help="skip the SPC/E block of the line")
+    ap.add_argument("--no-parity", action="store_true", help="skip the step-0 oracle check")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (development runs)")
+    ap.add_argument("--workload", default="lj", choices=["lj", "lj_coul_sf", "spce"],
+                    help="lj: the contract workload (BASELINE.json configs[3]); lj_coul_sf: configs[4] (LJ + coul_sf, charged); "
+                         "spce: the SPC/E n^3 replica box alone (informational line)")
     ap.add_argument("--replicas", type=int, default=8, help="spce: replicas per dimension of the NIST sample")
     args = ap.parse_args()
 
@@ -357,6 +467,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
+        if args.workload == "spce":
+            args.workload = "lj"
         reference_arm(args, rank, world)
         return
     if args.workload == "spce":
@@ -382,19 +494,24 @@ def main():
     from emdee_b200 import dist as edist
     W = max(args.warmup, 3)
     K = args.steps
-    # Multi-GPU (weak scaling): ONE box of about world x 1M atoms (the reference only knows cubic boxes), cut
-    # into z-slabs of cell layers, one per rank; ghost positions are exchanged every step over NCCL, energies
-    # all-reduced, rebuilds re-bin after an all-reduce of the owned coordinates.
-    ncell = args.ncell if world == 1 else int(round(args.ncell * world ** (1.0 / 3.0)))
+    # Multi-GPU: ONE cubic box (the reference only knows cubic boxes) cut into z-slabs of cell layers, one per rank
+    # (DESIGN.md section 7). Weak scaling: about 4*ncell^3 atoms per rank; strong scaling: the same box for every rank count.
+    ncell = total_ncell(args, world)
     R, P, L = make_workload(ncell)
     N = R.shape[0]                      # atoms of the whole job
-    s = build_system(lib, R, P, L, 1, before_upload=(lambda sy: edist.init_comm(lib, sy)) if world > 1 else None)
+    before_upload = (lambda sy: edist.init_comm(lib, sy)) if world > 1 else None
+    s = build_system(lib, R, P, L, 1, before_upload=before_upload, workload=args.workload)
+    torch.cuda.reset_peak_memory_stats()
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(lib, s, args, world, rank, dist, ncell, R, P, L, before_upload)
     s.set_kernel_timing(True)
 
     # ---- resident arm ---------------------------------------------------------------------------
     for _ in range(W):
         md_step(s)
     st0 = s.stats()
+    kt0 = s.kernel_times()
     builds0 = s.md.Builds
     # Device timing: CUDA events on the stream the library launches its kernels on (EmDeeX_stream). Every step
     # ends with a host-visible result (EmDee_boost returns the kinetic energy), so events on torch's idle default
@@ -433,6 +550,7 @@ def main():
         except Exception:   # pragma: no cover
             pass
     st1 = s.stats()
+    kt1 = s.kernel_times()
     builds = s.md.Builds - builds0
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -448,96 +566,121 @@ def main():
     n_local = N / world                          # atoms per rank (list statistics below are rank 0's)
     C_half = st1.list_entries / 2.0 / n_local    # neighbor-list entries per atom (half-list count, as SURVEY 8(d))
     P_half = st1.interacting / 2.0 / n_local     # entries with r < Rc per atom
+    # in-situ device time per kernel kind and step (CUDA events from the library's ring; warm caches, unlike ncu)
+    per_step = {k: (kt1[k][0] - kt0[k][0]) / K for k in kt1 if kt1[k][1] > kt0[k][1]}
+    state_res = {"U": s.md.Energy.Potential, "W": s.md.Virial.Total, "K": s.md.Kinetic.Total, "builds_total": int(s.md.Builds)}
+    peak_mem = torch.cuda.max_memory_allocated()   # torch's own share; the library's buffers are reported by the driver query
+    free_b, total_b = torch.cuda.mem_get_info()
+    mem_used = total_b - free_b
 
     # ---- e2e arm: host buffers in the timed region -------------------------------------------------
-    nframes = int(max(6, min(24, 1.0e9 // (24 * N))))   # at most ~1 GB of pinned frames per rank
-    frames = torch.empty((nframes, N, 3), dtype=torch.float64).pin_memory()
-    fout = torch.empty((N, 3), dtype=torch.float64).pin_memory()
-    fr = frames.numpy()
-    for k in range(nframes):
-        md_step(s)
-        fr[k] = s.download("coordinates")
-    order = list(range(nframes)) + list(range(nframes - 2, 0, -1))   # ping-pong: displacements evolve like a trajectory
-    e2eK = min(K, 50)
-    import ctypes as C
-    fptr = C.c_void_p(fout.data_ptr())
+    e2e = None
+    if not args.no_e2e:
+        nframes = int(max(6, min(24, 1.0e9 // (24 * N))))   # at most ~1 GB of pinned frames per rank
+        frames = torch.empty((nframes, N, 3), dtype=torch.float64).pin_memory()
+        fout = torch.empty((N, 3), dtype=torch.float64).pin_memory()
+        fr = frames.numpy()
+        for k in range(nframes):
+            md_step(s)
+            fr[k] = s.download("coordinates")
+        order = list(range(nframes)) + list(range(nframes - 2, 0, -1))   # ping-pong: displacements evolve like a trajectory
+        e2eK = min(K, 50)
+        import ctypes as C
+        fptr = C.c_void_p(fout.data_ptr())
+        if world > 1:
+            # several GPUs: every rank moves only its own slab across PCIe (owned + halo coordinates up, owned forces down,
+            # zero-copy from / to its pinned arrays); assembling a full force array, if wanted, is the caller's gather
+            lib.EmDeeX_tune(s.md, b"local_io", 1)
 
-    def e2e_step(k):
-        frame = frames[order[k % len(order)]]
-        lib.EmDee_upload(C.byref(s.md), b"coordinates", C.c_void_p(frame.data_ptr()))
-        lib.EmDee_compute_forces(C.byref(s.md))
-        lib.EmDee_download(s.md, b"forces", fptr)
+        def e2e_step(k):
+            frame = frames[order[k % len(order)]]
+            lib.EmDee_upload(C.byref(s.md), b"coordinates", C.c_void_p(frame.data_ptr()))
+            lib.EmDee_compute_forces(C.byref(s.md))
+            lib.EmDee_download(s.md, b"forces", fptr)
 
-    for k in range(3):
-        e2e_step(k)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    for k in range(e2eK):
-        e2e_step(3 + k)
-    ev1.record()
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-    t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = N * e2eK / float(t.item())
+        for k in range(3):
+            e2e_step(k)
+        io0 = s.io_bytes()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2eK):
+            e2e_step(3 + k)
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        io1 = s.io_bytes()
+        t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": N * e2eK / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": (io1[0] - io0[0]) // e2eK, "d2h_bytes_per_step": (io1[1] - io0[1]) // e2eK + 40,
+               "steps": e2eK, "ms_per_step": 1e3 * float(t.item()) / e2eK,
+               "what": "EmDee_upload(coordinates, pinned host) + EmDee_compute_forces + EmDee_download(forces, pinned host) per step, "
+                       "wall clock, max over ranks; bytes are per rank, counted by the library" +
+                       ("; several GPUs: each rank moves its own slab only (EmDeeX_tune local_io)" if world > 1 else "")}
 
     # ---- rooflines for the dominant kernel (pair forces) -------------------------------------------
     hbm_peak, peak_src = measured_peaks()
-    bytes_per_atom = 56.0 + 4.0 * C_half                     # 24 r + 24 F + 8 offsets + 4*C list
-    flops_per_atom = 15.0 * C_half + 22.0 * P_half + 6.0
+    coul = args.workload == "lj_coul_sf"
+    bytes_per_atom = 56.0 + 4.0 * C_half + (12.0 if coul else 0.0)   # 24 r + 24 F + 8 offsets + 4*C list (+ charge, type)
+    flops_per_atom = 15.0 * C_half + (22.0 + (13.0 if coul else 0.0)) * P_half + 6.0     # SURVEY 8(d); coul_sf: +1 sqrt +11 +1 div
     ach_gbs = bytes_per_atom * n_local / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
     fp64_peak = lib.EmDeeX_measure_fp64_tflops() if rank == 0 else None
     ach_tf = flops_per_atom * n_local / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
 
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
-    if world == 1 and ncell == NCELL_DEFAULT and os.path.exists(tpath):
+    if world == 1 and ncell == NCELL_DEFAULT and args.workload == "lj" and os.path.exists(tpath):
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]   # from the committed ncu --set full capture
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        r = cpu_run(ncell, args.cpu_steps, 1, cores)
+        r = cpu_run(ncell, args.cpu_steps, 1, cores, args.workload)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_steps} velocity-Verlet steps of the same {N}-atom box after 1 warm-up, "
                                   f"{r['seconds']:.1f} s; reference algorithm restated in C++/OpenMP (-Ofast)"}
+    spce = None
+    if rank == 0 and world == 1 and not args.no_spce and args.workload == "lj":
+        s.finalize()
+        s = None
+        spce = spce_block(args, cpu=not args.no_cpu_baseline)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(ncell, N, world, "single GPU" if world == 1 else
-                                      f"z-slab decomposition over {world} GPUs (NCCL halo of ghost positions per step, "
-                                      f"all-reduced energies, no reverse force exchange)"),
+            "config": workload_config(args, ncell, N, world),
             "timing": {"device_ms_total": dev_ms_max, "events_on": ev_where, "wall_s": wall, "list_builds_in_timed_region": int(builds),
                        "force_kernel_ms": force_ms, "build_kernel_ms": build_ms,
-                       "force_kernel_share_of_step": force_ms / (dev_ms_max / K) if K else None},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 24 * N + 40,   # per rank (SPMD: every rank moves the full arrays)
-                    "steps": e2eK, "what": "EmDee_upload(coordinates, pinned host) + EmDee_compute_forces + "
-                                           "EmDee_download(forces, pinned host) per step, wall clock, max over ranks"},
+                       "force_kernel_share_of_step": force_ms / (dev_ms_max / K) if K else None,
+                       "kernel_ms_per_step": per_step, "device_memory_used_bytes": int(mem_used)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_pair_forces", "achieved": ach_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "traffic": traffic,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_atom": bytes_per_atom, "list_entries_per_atom_half": C_half,
                          "interacting_per_atom_half": P_half,
-                         "note": "FP64-issue-bound kernel: see roofline_fp64; HBM fraction reported because "
-                                 "MEASURED_PEAKS.json carries only HBM and bf16 peaks"},
+                         "note": "the kernel is bound by the L1 gather path and FP64 issue, not by HBM: see roofline_fp64; HBM "
+                                 "fraction reported because MEASURED_PEAKS.json carries only HBM and bf16 peaks"},
             "roofline_fp64": {"bound": "fp64", "kernel": "k_pair_forces", "achieved": ach_tf, "peak": fp64_peak,
                               "unit": "TFLOP/s", "frac": (ach_tf / fp64_peak) if (ach_tf and fp64_peak) else None,
                               "algorithmic_flops_per_atom": flops_per_atom,
                               "peak_source": "DFMA microbenchmark run in this process (EmDeeX_measure_fp64_tflops)"},
             "clocks": clocks.summary(),
-            "state": {"U": s.md.Energy.Potential, "W": s.md.Virial.Total, "K": s.md.Kinetic.Total,
-                      "builds_total": int(s.md.Builds)},
+            "state": state_res,
         }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if parity is not None:
+            line["parity"] = parity
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if spce is not None:
+            line["spce"] = spce
         print(json.dumps(line), flush=True)
-    s.finalize()
+    if s is not None:
+        s.finalize()
     if world > 1:
         dist.destroy_process_group()
 
