@@ -145,9 +145,6 @@ struct Engine::Impl {
   bool env_debug = false, env_profile = false, env_no_migrate = false;
   // developer knobs (EmDeeX_tune; tools/force_lab.py): force-kernel variant and L1/shared carveout of the plain-LJ kernel
   int tune_variant = 0, tune_carveout = -1, tune_build = 0;
-  DBuf<double> labSoa;             // tools/force_lab.py variants only
-  DBuf<int> labHalf, labHalfCount;
-  long long labHalfBuild = -1, buildSerial = 0;
 
   // host-visible results: pinned slots the last block of a reducing kernel writes; the host spins on the sequence number
   HostSlot* slots = nullptr;
@@ -342,7 +339,7 @@ Engine::~Engine() {
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
-  s.known.release(); s.migCounts.release(); s.ownedList.release(); s.labSoa.release(); s.labHalf.release(); s.labHalfCount.release();
+  s.known.release(); s.migCounts.release(); s.ownedList.release();
   s.terms.release(); s.termFirst.release(); s.termRef.release();
   s.ewN.release(); s.ewKType.release(); s.ewPrefac.release(); s.ewLambda.release(); s.ewSigma.release(); s.ewPartial.release();
   s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
@@ -710,54 +707,22 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
 // (EmDeeX_tune "force_variant" / "carveout"), which times them back to back on one resident system.
 //   columns: UNROLL, THREADS, MINBLOCKS, index-stream load, position-gather load, PROBE, FORM
 #define EMDEE_LJ_VARIANTS(X)                                                \
-  X(0, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
-  X(1, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0, FORM_DEFAULT)                \
+  X(0, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
+  X(1, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
+  X(2, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0, FORM_BRANCHLESS)             \
   X(3, 6, 512, 2, LD_PLAIN, LD_PLAIN, 1, FORM_DEFAULT)                      \
   X(4, 6, 512, 2, LD_PLAIN, LD_PLAIN, 2, FORM_DEFAULT)                      \
-  X(6, 4, 256, 4, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
-  X(7, 8, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
-  X(10, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
-  X(11, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
-  X(12, 8, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
-  X(13, 4, 256, 4, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
-  X(14, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_SOA)                         \
-  X(15, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_SOA)                         \
-  X(16, 8, 256, 3, LD_PLAIN, LD_PLAIN, 0, FORM_SOA)
-constexpr int VARIANT_SOA_FIRST = 14, VARIANT_SOA_LAST = 16, VARIANT_N3 = 19, VARIANT_N3_B = 20;
+  X(5, 5, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
+  X(6, 6, 256, 4, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
+  X(7, 7, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
+  X(8, 6, 1024, 1, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
+  X(9, 6, 512, 2, LD_PLAIN, LD_EVICT_LAST, 0, FORM_BRANCHLESS)              \
+  X(10, 6, 128, 8, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
+  X(11, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)
 
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
   const int v = s.tune_variant;
-  if (v >= VARIANT_SOA_FIRST && v <= VARIANT_SOA_LAST) {   // lab only: x[], y[], z[] copies of the refreshed positions
-    s.labSoa.ensure(3 * (size_t)a.Next);
-    k_pos_to_soa<<<nblocks(a.Next), TPB, 0, s.stream>>>(a.Next, a.pos, s.labSoa.p);
-    a.soa = s.labSoa.p;
-  }
-  if (v == VARIANT_N3 || v == VARIANT_N3_B) {   // lab only: Newton's third law over a half list, scatter by red.global.add.f64
-    if (s.labHalfBuild != s.buildSerial) {
-      s.labHalf.ensure(s.nbr.n);
-      s.labHalfCount.ensure((size_t)a.Next + 32);
-      k_halve_list<<<nblocks(a.Next), TPB, 0, s.stream>>>(a.Next, a.cap, a.nbr, a.nbrCount, a.sMeta, s.labHalf.p, s.labHalfCount.p);
-      s.labHalfBuild = s.buildSerial;
-    }
-    a.nbrHalf = s.labHalf.p;
-    a.nbrCountHalf = s.labHalfCount.p;
-    CUDA_CHECK(cudaMemsetAsync(a.F, 0, 3 * (size_t)s.N * sizeof(double), s.stream));
-    if (v == VARIANT_N3) {
-      const int grid = nblocks(a.Next, 256);
-      s.partial.ensure((size_t)grid * 5);
-      a.partial = s.partial.p;
-      if (compute) k_pair_forces_n3<true, 4, 256, 4><<<grid, 256, 0, s.stream>>>(a);
-      else k_pair_forces_n3<false, 4, 256, 4><<<grid, 256, 0, s.stream>>>(a);
-    } else {
-      const int grid = nblocks(a.Next, 512);
-      s.partial.ensure((size_t)grid * 5);
-      a.partial = s.partial.p;
-      if (compute) k_pair_forces_n3<true, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a);
-      else k_pair_forces_n3<false, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a);
-    }
-    return;
-  }
   switch (v) {
 #define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
@@ -1150,12 +1115,11 @@ void Engine::rebuild_list(double Lbox) {
       // write-out was measured 6x slower at LJ-1M -- serial per-atom dependency chains at ~12 warps/SM --
       // and removed)
       const int tmr = timer_begin(1);
-      if (s.tune_build == 1) k_build_list_nested<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      if (s.tune_build == 1) k_build_list_flat<<<nblocks(Next), TPB, 0, s.stream>>>(b);
       else k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
       timer_end(tmr);
       stats_.launches += 1;
       stats_.build_launches += 1;
-      s.buildSerial += 1;
       int hflags[4];
       CUDA_CHECK(cudaMemcpyAsync(hflags, s.flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
       CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -1209,7 +1173,6 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   a.skinSq = s.skinSq;
   a.hs = (s.world > 1) ? nullptr : s.slots + SLOT_FORCE;   // several GPUs: the scalars are all-reduced first
   a.seq = s.next_seq(SLOT_FORCE);
-  a.soa = nullptr; a.nbrHalf = nullptr; a.nbrCountHalf = nullptr;
 
   // classify the layer for kernel selection
   bool uniform = true;

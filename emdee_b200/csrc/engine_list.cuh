@@ -301,6 +301,7 @@ __device__ __forceinline__ double strict_pbc_sq(double a, double b) {
   return __dmul_rn(d, d);
 }
 
+// EXPERIMENTAL form (EmDeeX_tune "build_variant" = 1; tools/force_lab.py times both on one resident system).
 // Two phases per thread, both written so that the lanes of a warp stay converged:
 //   1. the (at most 25) clipped x-runs of the entry are computed in lock step and their non-empty intervals (first
 //      entry, length) stored in shared memory (column per thread);
@@ -308,7 +309,7 @@ __device__ __forceinline__ double strict_pbc_sq(double a, double b) {
 //      with predicated instructions when the current one is used up and tests one candidate, so a lane never waits for
 //      the longest run of its warp in each of the 25 rows. The common candidate test is branch-free; the exact re-test
 //      inside the FP32 uncertainty band, the type mask and the exclusion scan share ONE rarely taken branch.
-__global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ BuildArgs a) {
+__global__ void __launch_bounds__(TPB) k_build_list_flat(const __grid_constant__ BuildArgs a) {
   __shared__ int runFirst[25][TPB];
   __shared__ unsigned char runLen[25][TPB];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -430,9 +431,8 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
   }
 }
 
-// The round-1 form (25 nested x-runs per thread), kept selectable (EmDeeX_tune "build_variant" = 1) so that tools/force_lab.py
-// can time both forms on one resident system.
-__global__ void __launch_bounds__(TPB) k_build_list_nested(const __grid_constant__ BuildArgs a) {
+// The default form: 25 nested x-runs per thread (0.658 ms at LJ-1M against 0.847 ms for the flat form above, round 2).
+__global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ BuildArgs a) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
   const int lane = threadIdx.x & 31;
