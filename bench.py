@@ -181,8 +181,9 @@ def total_ncell(args, world):
 
 
 def parallelism(world):
-    return "single GPU" if world == 1 else (f"z-slab decomposition over {world} GPUs: one NCCL group per step (halo positions + "
-                                            f"rebuild-criterion state), one all-reduce of the energies, no reverse force exchange")
+    return "single GPU" if world == 1 else (f"z-slab decomposition over {world} GPUs: per step halo positions + rebuild-criterion "
+                                            f"state to the neighbors / peers and small all-reduces of energies and kinetic sums "
+                                            f"(the library's own kernels over NVLink peer memory, else NCCL), no reverse force exchange")
 
 
 def workload_config(args, ncell, N, world):
@@ -568,6 +569,7 @@ def main():
     P_half = st1.interacting / 2.0 / n_local     # entries with r < Rc per atom
     # in-situ device time per kernel kind and step (CUDA events from the library's ring; warm caches, unlike ncu)
     per_step = {k: (kt1[k][0] - kt0[k][0]) / K for k in kt1 if kt1[k][1] > kt0[k][1]}
+    comm_mode = int(lib.EmDeeX_comm_mode(s.md))
     state_res = {"U": s.md.Energy.Potential, "W": s.md.Virial.Total, "K": s.md.Kinetic.Total, "builds_total": int(s.md.Builds)}
     peak_mem = torch.cuda.max_memory_allocated()   # torch's own share; the library's buffers are reported by the driver query
     free_b, total_b = torch.cuda.mem_get_info()
@@ -654,7 +656,8 @@ def main():
             "timing": {"device_ms_total": dev_ms_max, "events_on": ev_where, "wall_s": wall, "list_builds_in_timed_region": int(builds),
                        "force_kernel_ms": force_ms, "build_kernel_ms": build_ms,
                        "force_kernel_share_of_step": force_ms / (dev_ms_max / K) if K else None,
-                       "kernel_ms_per_step": per_step, "device_memory_used_bytes": int(mem_used)},
+                       "kernel_ms_per_step": per_step, "device_memory_used_bytes": int(mem_used),
+                       "comm_mode": {0: "single GPU", 1: "NCCL per step", 2: "NVLink peer kernels per step, NCCL at rebuilds"}[comm_mode]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_pair_forces", "achieved": ach_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "traffic": traffic,

@@ -125,6 +125,7 @@ ABI_EXT_PRODUCT = {
     "EmDeeX_stats": (None, [tEmDee, C.POINTER(tEmDeeXStats)]),
     "EmDeeX_set_kernel_timing": (None, [tEmDee, C.c_int]),
     "EmDeeX_synchronize": (None, [tEmDee]),
+    "EmDeeX_comm_mode": (C.c_int, [tEmDee]),
     "EmDeeX_io_bytes": (None, [tEmDee, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "EmDeeX_kernel_times": (None, [tEmDee, _dp, C.POINTER(C.c_longlong)]),
     "EmDeeX_tune": (None, [tEmDee, C.c_char_p, C.c_int]),

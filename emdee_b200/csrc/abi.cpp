@@ -1365,6 +1365,7 @@ void EmDeeX_stats(tEmDee md, tEmDeeXStats* out) {
 void EmDeeX_set_kernel_timing(tEmDee md, int enabled) { sys(md)->engine->set_kernel_timing(enabled != 0); }
 void EmDeeX_kernel_times(tEmDee md, double* ms8, long long* n8) { sys(md)->engine->kernel_times(ms8, n8); }
 void EmDeeX_synchronize(tEmDee md) { sys(md)->engine->synchronize(); }
+int EmDeeX_comm_mode(tEmDee md) { return sys(md)->engine->comm_mode(); }
 void EmDeeX_io_bytes(tEmDee md, long long* h2d, long long* d2h) { sys(md)->engine->io_bytes(*h2d, *d2h); }
 void EmDeeX_tune(tEmDee md, const char* knob, int value) { sys(md)->engine->tune(knob, value); }
 void* EmDeeX_stream(tEmDee md) { return sys(md)->engine->stream_handle(); }

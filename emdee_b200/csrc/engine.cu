@@ -117,6 +117,12 @@ struct Engine::Impl {
   // local I/O (EmDeeX_tune "local_io", several GPUs): coordinate uploads read only the atoms this rank owns or keeps as
   // halo, force downloads write only the atoms it owns, both straight from / to the caller's pinned host array
   bool local_io = false;
+  // NVLink peer path (engine_dist.cuh): every rank's mailbox and R array mapped into every peer (cudaIpc)
+  bool peer_ok = false;
+  PeerBox* box = nullptr;          // this rank's mailbox (device memory, 2 MB allocation of its own)
+  PeerPtrs peers{};                // every rank's mailbox as seen from this device
+  double* peerR[PEER_MAX] = {};    // every rank's coordinate array as seen from this device
+  unsigned long long xseq = 0, rseq = 0;   // exchange / small-reduction sequence numbers (advance in lock step on all ranks)
   long long io_h2d = 0, io_d2h = 0;   // bytes moved by coordinate uploads / force downloads (EmDeeX_io_bytes)
 
   // rigid bodies (engine_bodies.cuh): CSR of members + SoA state, 27 doubles per body
@@ -347,6 +353,15 @@ Engine::~Engine() {
   if (s.h_bscalars) cudaFreeHost(s.h_bscalars);
   for (int k = 0; k < 2; ++k) { s.migList[k].release(); s.migSend[k].release(); s.migRecv[k].release(); }
   if (s.h_mi) cudaFreeHost(s.h_mi);
+#if defined(__CUDACC__)
+  if (s.peer_ok)
+    for (int r = 0; r < s.world; ++r)
+      if (r != s.rank) {
+        cudaIpcCloseMemHandle(s.peers.box[r]);
+        cudaIpcCloseMemHandle(s.peerR[r]);
+      }
+  if (s.box) cudaFree(s.box);
+#endif
   if (s.comm) nccl().CommDestroy(s.comm);
   s.chkPartial.release(); s.partial.release(); s.scalars.release(); s.counter.release(); s.tickets.release();
   if (s.h_scalars) cudaFreeHost(s.h_scalars);
@@ -372,6 +387,69 @@ void comm_unique_id(void* out128) {
   std::memcpy(out128, &id, sizeof(id));
 }
 
+namespace {
+// Maps every rank's mailbox and coordinate array into this process (cudaIpc over NVLink). All-or-nothing across the
+// ranks: the flags are all-reduced, so either every rank uses the peer kernels or every rank uses NCCL per step.
+void setup_peer_links(Engine::Impl& s) {
+#if defined(__CUDACC__)
+  if (std::getenv("EMDEE_NO_PEER") != nullptr || s.world > PEER_MAX) return;
+  int ok = 1;
+  // allocations of their own (>= 2 MB), so that an IPC handle opens at the array's first byte
+  const size_t n3 = std::max(3 * (size_t)s.N, (size_t)(2u << 20) / sizeof(double) + 16);
+  s.R.release();
+  s.R.ensure(n3);
+  CUDA_CHECK(cudaMemset(s.R.p, 0, n3 * sizeof(double)));
+  void* raw = nullptr;
+  CUDA_CHECK(cudaMalloc(&raw, std::max(sizeof(PeerBox), (size_t)(2u << 20))));
+  s.box = static_cast<PeerBox*>(raw);
+  CUDA_CHECK(cudaMemset(s.box, 0, sizeof(PeerBox)));
+  struct Handles { cudaIpcMemHandle_t box, R; };
+  Handles mine;
+  if (cudaIpcGetMemHandle(&mine.box, s.box) != cudaSuccess || cudaIpcGetMemHandle(&mine.R, s.R.p) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0;
+    std::memset(&mine, 0, sizeof(mine));
+  }
+  DBuf<unsigned char> all;
+  all.ensure((size_t)s.world * sizeof(Handles));
+  CUDA_CHECK(cudaMemcpy(all.p + (size_t)s.rank * sizeof(Handles), &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+  NCCL_CHECK(nccl().AllGather(all.p + (size_t)s.rank * sizeof(Handles), all.p, sizeof(Handles), ncclChar, s.comm, s.stream));
+  std::vector<Handles> h(s.world);
+  CUDA_CHECK(cudaMemcpyAsync(h.data(), all.p, (size_t)s.world * sizeof(Handles), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  all.release();
+  for (int r = 0; r < s.world && ok; ++r) {
+    if (r == s.rank) {
+      s.peers.box[r] = s.box;
+      s.peerR[r] = s.R.p;
+      continue;
+    }
+    void *pb = nullptr, *pr = nullptr;
+    if (cudaIpcOpenMemHandle(&pb, h[r].box, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pr, h[r].R, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    s.peers.box[r] = static_cast<PeerBox*>(pb);
+    s.peerR[r] = static_cast<double*>(pr);
+  }
+  // agree: all ranks or none
+  DBuf<int> flag;
+  flag.ensure(1);
+  CUDA_CHECK(cudaMemcpy(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  NCCL_CHECK(nccl().AllReduce(flag.p, flag.p, 1, ncclInt, ncclMin, s.comm, s.stream));
+  CUDA_CHECK(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  flag.release();
+  s.peer_ok = ok != 0;
+  if (s.env_debug) std::fprintf(stderr, "[emdee r%d] NVLink peer path %s\n", s.rank, s.peer_ok ? "on" : "off (NCCL per step)");
+#else
+  (void)s;
+#endif
+}
+}  // namespace
+
 void Engine::comm_init(int rank, int world, const void* unique_id) {
   Impl& s = *d_;
   if (world <= 1) return;
@@ -386,6 +464,7 @@ void Engine::comm_init(int rank, int world, const void* unique_id) {
   s.miPartial.ensure(nblocks(s.N));
   s.scratch3.ensure(3 * (size_t)s.N);
   s.check_cached = false;
+  setup_peer_links(s);
 }
 
 namespace {
@@ -444,6 +523,19 @@ void exchange_step(Engine::Impl& s, bool with_criterion) {
     k_check_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.R.p, s.R0.p, all, s.miPartial.p,
                                                                       s.tickets.p + 2, s.miResult.p + s.world);
     s.mi_fresh = true;
+  }
+  if (s.peer_ok) {
+    // NVLink peer path: halo coordinates go straight into the neighbors' arrays, the criterion state into every mailbox
+    const unsigned long long seq = ++s.xseq;
+    const int nUp = halo ? s.haloCount[0] : 0, nDn = halo ? s.haloCount[1] : 0;
+    k_push_step<<<std::max(1, nblocks(nUp + nDn)), TPB, 0, s.stream>>>(nUp, s.haloList[0].p, nDn, s.haloList[1].p, s.R.p, s.peerR[up],
+                                                                      s.peerR[dn], halo ? 1 : 0, with_criterion ? 1 : 0,
+                                                                      s.miResult.p + s.world, s.peers, s.world, s.rank, up, dn, seq,
+                                                                      s.tickets.p + 3);
+    k_wait_decide<<<1, 32, 0, s.stream>>>(s.box, s.world, s.rank, halo ? 1 : 0, with_criterion ? 1 : 0, seq, s.miResult.p + s.world,
+                                          s.skinSq, s.scalars.p + CRIT_DIST);
+    s.halo_fresh = true;
+    return;
   }
   if (halo)
     for (int k = 0; k < 2; ++k)
@@ -548,6 +640,13 @@ bool rebuild_needed_phase2(Engine::Impl& s, double maximum, long long istar) {
 // energies / virial of all ranks summed and delivered to the host slot together with the device-side rebuild decision:
 // one collective, one host wait per force evaluation
 void finish_pair_dist(Engine::Impl& s, bool with_decision) {
+  if (s.peer_ok) {
+    k_reduce_small<<<1, 32, 0, s.stream>>>(5, s.scalars.p, s.peers, s.box, s.world, s.rank, ++s.rseq, s.scalars.p,
+                                           with_decision ? s.scalars.p + CRIT_DIST : nullptr, s.slots + SLOT_FORCE,
+                                           s.slot_seq[SLOT_FORCE]);
+    s.wait_slot(SLOT_FORCE);
+    return;
+  }
   NCCL_CHECK(nccl().AllReduce(s.scalars.p, s.scalars.p, 5, ncclDouble, ncclSum, s.comm, s.stream));
   k_publish_force<<<1, 32, 0, s.stream>>>(s.scalars.p, with_decision ? s.scalars.p + CRIT_DIST : nullptr, s.slots + SLOT_FORCE,
                                           s.slot_seq[SLOT_FORCE]);
@@ -679,6 +778,7 @@ void Engine::download_forces(int layer0, double* F) {
   s.io_d2h += 24LL * s.N;
 }
 void Engine::io_bytes(long long& h2d, long long& d2h) { h2d = d_->io_h2d; d2h = d_->io_d2h; }
+int Engine::comm_mode() { return d_->world <= 1 ? 0 : (d_->peer_ok ? 2 : 1); }
 void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
 void Engine::tune(const char* knob, int value) {
   if (std::strcmp(knob, "force_variant") == 0) d_->tune_variant = value;
@@ -1221,9 +1321,14 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
     timer_end(tmr);
     stats_.launches += 1;
     if (want_kinetic) {
-      NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
       const unsigned long long seq = s.next_seq(SLOT_KINETIC);
-      k_publish3<<<1, 32, 0, s.stream>>>(s.scalars.p + 10, s.slots + SLOT_KINETIC, seq);
+      if (s.peer_ok) {
+        k_reduce_small<<<1, 32, 0, s.stream>>>(3, s.scalars.p + 10, s.peers, s.box, s.world, s.rank, ++s.rseq, s.scalars.p + 10,
+                                               nullptr, s.slots + SLOT_KINETIC, seq);
+      } else {
+        NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
+        k_publish3<<<1, 32, 0, s.stream>>>(s.scalars.p + 10, s.slots + SLOT_KINETIC, seq);
+      }
       s.wait_slot(SLOT_KINETIC);
       for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
     }

@@ -138,6 +138,7 @@ class Engine {
   void set_kernel_timing(bool on) { timing_ = on; }
   void tune(const char* knob, int value);   // "local_io" (several GPUs, see upload_coordinates); developer knobs of tools/force_lab.py: "force_variant", "carveout"
   void synchronize();
+  int comm_mode();   // 0 single GPU, 1 NCCL per step, 2 NVLink peer kernels per step (NCCL at rebuilds only)
   void io_bytes(long long& h2d, long long& d2h);   // bytes moved so far by coordinate uploads / force downloads
   void* stream_handle();   // the cudaStream_t every kernel of this system is launched on
   EngineStats stats();

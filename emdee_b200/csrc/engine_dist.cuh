@@ -186,6 +186,162 @@ __global__ void k_publish3(const double* __restrict__ src, HostSlot* hs, unsigne
   slot_publish(hs, seq);
 }
 
+// ================================================================================================
+// NVLink peer path (one process per GPU, every rank's mailbox and coordinate array mapped into every peer with cudaIpc):
+// the per-step communication is done by these kernels with plain peer stores -- no NCCL call between two rebuilds.
+//   k_push_step    halo coordinates written straight into the neighbors' R arrays (same atom index on every rank: the
+//                  arrays are full-length), this rank's criterion state into every peer's mailbox, then the flags
+//   k_wait_decide  waits for the neighbors' flags and the peers' criterion states, takes the rebuild decision (k_decide)
+//   k_reduce_small all-reduce of <= 6 doubles: contribution stored into every peer's mailbox, sum in RANK ORDER (the same
+//                  bits on every rank), result + decision published to the pinned host slot
+// Flow control: a rank pushes the halo of step n+1 only after its host has the reduced scalars of step n, and a peer
+// contributes to that reduction after its own force kernel of step n -- so nobody's R is overwritten while it is being read.
+// Mail slots are double-buffered by sequence parity (a rank can be at most one collective ahead of a peer).
+// ================================================================================================
+constexpr int PEER_MAX = 16;
+struct alignas(64) PeerMail {
+  double v[6];
+  unsigned long long seq;   // written last (release.sys)
+  unsigned long long pad;
+};
+struct PeerBox {
+  PeerMail red[2][PEER_MAX];
+  PeerMail crit[2][PEER_MAX];
+  unsigned long long haloFrom[2];   // [0] written by the rank below, [1] by the rank above: exchange sequence number
+  unsigned long long pad[6];
+};
+struct PeerPtrs {
+  PeerBox* box[PEER_MAX];   // box[rank] is this rank's own
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ double ld_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+#else   // tests/cusim emulation build: single address space, no peers (the path is never taken there)
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return *p; }
+__device__ __forceinline__ void st_sys(double* p, double v) { *p = v; }
+__device__ __forceinline__ double ld_sys(const double* p) { return *p; }
+#endif
+
+__global__ void __launch_bounds__(TPB) k_push_step(int nUp, const int* __restrict__ listUp, int nDn, const int* __restrict__ listDn,
+                                                   const double* __restrict__ R, double* __restrict__ Rup, double* __restrict__ Rdn,
+                                                   int with_halo, int with_crit, const MaxIdx* __restrict__ myCrit, PeerPtrs peers,
+                                                   int world, int rank, int up, int dn, unsigned long long seq,
+                                                   unsigned int* __restrict__ ticket) {
+  __shared__ bool last;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (with_halo && k < nUp + nDn) {
+    const bool isUp = k < nUp;
+    const size_t a = (size_t)(isUp ? listUp[k] : listDn[k - nUp]);
+    double* dst = isUp ? Rup : Rdn;
+    const double x = R[3 * a], y = R[3 * a + 1], z = R[3 * a + 2];
+    dst[3 * a] = x;
+    dst[3 * a + 1] = y;
+    dst[3 * a + 2] = z;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) last = (take_ticket(ticket) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) *ticket = 0u;
+  const int t = threadIdx.x;
+  if (with_crit && t < world && t != rank) {
+    PeerMail* m = &peers.box[t]->crit[seq & 1ull][rank];
+    st_sys(&m->v[0], myCrit->m);
+    st_sys(&m->v[1], __longlong_as_double(myCrit->i));
+    st_release_sys(&m->seq, seq);
+  }
+  if (with_halo && t == PEER_MAX) st_release_sys(&peers.box[up]->haloFrom[0], seq);       // I am the rank below `up`
+  if (with_halo && t == PEER_MAX + 1) st_release_sys(&peers.box[dn]->haloFrom[1], seq);   // and the rank above `dn`
+}
+
+__global__ void k_wait_decide(PeerBox* mine, int world, int rank, int with_halo, int with_crit, unsigned long long seq,
+                              const MaxIdx* __restrict__ myCrit, double skinSq, double* __restrict__ crit) {
+  __shared__ MaxIdx got[PEER_MAX];
+  const int t = threadIdx.x;
+  if (with_crit && t < world) {
+    if (t == rank) {
+      got[t] = *myCrit;
+    } else {
+      const PeerMail* m = &mine->crit[seq & 1ull][t];
+      while (ld_acquire_sys(&m->seq) != seq) {
+      }
+      got[t].m = ld_sys(&m->v[0]);
+      got[t].i = __double_as_longlong(ld_sys(&m->v[1]));
+    }
+  }
+  if (with_halo && (t == PEER_MAX || t == PEER_MAX + 1)) {
+    while (ld_acquire_sys(&mine->haloFrom[t - PEER_MAX]) != seq) {
+    }
+  }
+  __syncthreads();
+  if (t != 0 || !with_crit) return;
+  MaxIdx g = got[0];
+  for (int r = 1; r < world; ++r) g = mi_better(g, got[r]);
+  int code;
+  if (g.m > skinSq) code = 1;
+  else if (__dmul_rn(4.0, g.m) <= skinSq) code = 0;
+  else if (g.i == 0)
+    code = (__dadd_rn(__dadd_rn(g.m, __dmul_rn(2.0, __dsqrt_rn(__dmul_rn(g.m, g.m)))), g.m) > skinSq) ? 1 : 0;
+  else code = 2;
+  crit[0] = (code == 0) ? 0.0 : 1.0 / 0.0;
+  crit[1] = (double)code;
+  crit[2] = (double)g.i;
+  crit[3] = g.m;
+}
+
+// mode 0: n plain sums to the host slot; mode 1: force scalars + the decision block (as k_publish_force)
+__global__ void k_reduce_small(int n, const double* __restrict__ src, PeerPtrs peers, PeerBox* mine, int world, int rank,
+                               unsigned long long seq, double* __restrict__ out, const double* __restrict__ crit, HostSlot* hs,
+                               unsigned long long hseq) {
+  __shared__ double got[PEER_MAX][6];
+  const int t = threadIdx.x;
+  if (t < world) {
+    PeerMail* m = &peers.box[t]->red[seq & 1ull][rank];
+    for (int q = 0; q < n; ++q) st_sys(&m->v[q], src[q]);
+    st_release_sys(&m->seq, seq);
+  }
+  if (t < world) {
+    const PeerMail* m = &mine->red[seq & 1ull][t];
+    while (ld_acquire_sys(&m->seq) != seq) {
+    }
+    for (int q = 0; q < n; ++q) got[t][q] = ld_sys(&m->v[q]);
+  }
+  __syncthreads();
+  if (t != 0) return;
+  for (int q = 0; q < n; ++q) {
+    double sum = got[0][q];
+    for (int r = 1; r < world; ++r) sum += got[r][q];
+    out[q] = sum;
+    hs->v[q] = sum;
+  }
+  if (n == 5) {
+    hs->v[5] = 0.0;
+    hs->v[6] = 0.0;
+    if (crit != nullptr) {
+      hs->v[5] = crit[1];
+      hs->v[6] = crit[2];
+      if (crit[1] != 0.0) hs->v[0] = crit[3];
+    }
+  }
+  slot_publish(hs, hseq);
+}
+
 // dst = owned ? src : 0 (three doubles per atom): the summand of the all-reduce that rebuilds a full array
 __global__ void __launch_bounds__(TPB) k_mask_owned(int N, const unsigned char* __restrict__ owned,
                                                     const double* __restrict__ src, double* __restrict__ dst) {
@@ -269,16 +425,23 @@ __global__ void __launch_bounds__(TPB) k_halo_flags(int N, GridDesc g, const int
 }
 
 // local I/O (EmDeeX_tune "local_io"): three doubles per listed atom between the caller's pinned, device-mapped host array
-// and the device array, both indexed by the atom; dst[a] = src[a] for a in list (zero-copy over PCIe, no staging buffer)
+// and the device array, both indexed by the atom; dst[a] = src[a] for a in list (zero-copy over PCIe, no staging buffer).
+// A warp moves the 96 doubles of its 32 listed atoms element-wise (lane l takes elements l, l+32, l+64), so a run of
+// consecutive atom indices -- what a slab of a lattice-ordered system consists of -- becomes full, contiguous sectors on
+// the PCIe side instead of 8-byte pieces at a 24-byte stride.
 __global__ void __launch_bounds__(TPB) k_copy3_listed(int n, const int* __restrict__ list, const double* __restrict__ src,
                                                       double* __restrict__ dst) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const size_t a = (size_t)list[k];
-  const double x = src[3 * a], y = src[3 * a + 1], z = src[3 * a + 2];
-  dst[3 * a] = x;
-  dst[3 * a + 1] = y;
-  dst[3 * a + 2] = z;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int mine = (k < n) ? list[k] : -1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int e = c * 32 + lane;          // element of the warp's 96
+    const int from = e / 3;               // lane that holds the atom index
+    const int comp = e - 3 * from;
+    const int a = __shfl_sync(0xffffffffu, mine, from);
+    if (a >= 0) dst[3 * (size_t)a + comp] = src[3 * (size_t)a + comp];
+  }
 }
 
 __global__ void __launch_bounds__(TPB) k_pack3(int n, const int* __restrict__ list, const double* __restrict__ X,

@@ -58,6 +58,10 @@ void EmDeeX_set_kernel_timing( tEmDee md, int enabled );
    [6] binning + cell sort of a rebuild, [7] unused. Both arrays hold 8 entries. */
 void EmDeeX_kernel_times( tEmDee md, double* ms8, long long* n8 );
 
+/* How the ranks of a multi-GPU system talk between two list rebuilds: 0 = single GPU, 1 = NCCL calls every step,
+   2 = the library's own kernels over NVLink peer memory (mailboxes + halo stores; NCCL only at rebuilds). */
+int EmDeeX_comm_mode( tEmDee md );
+
 /* Bytes moved so far between host and device by EmDee_upload("coordinates") and EmDee_download("forces"). */
 void EmDeeX_io_bytes( tEmDee md, long long* h2d, long long* d2h );
 

@@ -163,6 +163,7 @@ struct Warp {
   int live = 0, count = 0;
   unsigned gen = 0;
   unsigned long long slot[2][32];   // double-buffered: exchange k uses buffer k&1, so one barrier per exchange suffices
+  unsigned snap[2] = {0u, 0u};      // lanes that took part in the exchange (a lane may have RETURNED by the time a slower lane reads)
   bool alive[32];
 };
 
@@ -358,6 +359,12 @@ inline const unsigned long long* exchange(unsigned long long mine) {
   Warp& w = b.warps[b.cur->linear >> 5];
   const unsigned buf = b.cur->exchanges++ & 1u;
   w.slot[buf][b.cur->linear & 31] = mine;
+  if (w.count + 1 >= w.live) {   // last lane to arrive: record who is taking part
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l)
+      if (w.alive[l]) m |= 1u << l;
+    w.snap[buf] = m;
+  }
   sync_warp();
   return w.slot[buf];
 }
@@ -367,11 +374,12 @@ inline T shuffle(T v, int src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
   unsigned long long raw = 0;
   std::memcpy(&raw, &v, sizeof(T));
+  const unsigned buf = st().cur->exchanges & 1u;
   const unsigned long long* all = exchange(raw);
   BlockState& b = st();
   const Warp& w = b.warps[b.cur->linear >> 5];
   T r = v;
-  if (src_lane >= 0 && src_lane < 32 && w.alive[src_lane]) std::memcpy(&r, &all[src_lane], sizeof(T));
+  if (src_lane >= 0 && src_lane < 32 && ((w.snap[buf] >> src_lane) & 1u)) std::memcpy(&r, &all[src_lane], sizeof(T));
   return r;
 }
 
@@ -397,12 +405,13 @@ inline T __shfl_down_sync(unsigned, T v, unsigned delta, int = 32) {
   return cusim::shuffle(v, lane + (int)delta < 32 ? lane + (int)delta : lane);
 }
 inline unsigned __ballot_sync(unsigned, int pred) {
+  const unsigned buf = cusim::st().cur->exchanges & 1u;
   const unsigned long long* all = cusim::exchange(pred ? 1ull : 0ull);
   cusim::BlockState& b = cusim::st();
   const cusim::Warp& w = b.warps[b.cur->linear >> 5];
   unsigned bits = 0;
   for (int l = 0; l < 32; ++l)
-    if (w.alive[l] && all[l]) bits |= 1u << l;
+    if (((w.snap[buf] >> l) & 1u) && all[l]) bits |= 1u << l;
   return bits;
 }
 
@@ -437,6 +446,8 @@ inline long long __double2ll_rn(double a) { return std::llrint(a); }
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 inline void sincospi(double x, double* s, double* c) { sincos(3.14159265358979323846 * x, s, c); }
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 template <class T>
 inline T __ldg(const T* p) { return *p; }

@@ -58,6 +58,18 @@ def build_spce(lib, comm, replicas=2):
     return s
 
 
+def pinned(shape):
+    """Page-locked float64 host array (numpy view); on the CPU emulator any array will do."""
+    if os.environ.get("EMDEE_MGPU_EMULATED") == "1":
+        return np.empty(shape)
+    t = torch.empty(shape, dtype=torch.float64).pin_memory()
+    _keep.append(t)
+    return t.numpy()
+
+
+_keep = []
+
+
 def compare(tag, sp, so, rank, ftol=1e-10, stol=1e-12):
     F = sp.download("forces")          # collective on the product side
     pairs = edist.gather_pairs(sp.pairs())
@@ -152,16 +164,21 @@ def main():
             h2d0, d2h0 = sp.io_bytes()
             for k in range(6):
                 base = base + rng.normal(0.0, 0.03, base.shape)      # continuous motion: well under one cell layer per upload
-                for s in ([sp, so] if rank == 0 else [sp]):
-                    s.upload("coordinates", base)
-                    s.compute_forces()
-                Fl = np.full((N, 3), np.nan)
+                hb = pinned((N, 3))
+                hb[:] = base
+                sp.upload("coordinates", hb)
+                sp.compute_forces()
+                if rank == 0:
+                    so.upload("coordinates", base)
+                    so.compute_forces()
+                Fl = pinned((N, 3))        # local I/O needs page-locked host memory (pageable arrays take the collective path)
+                Fl[:] = np.nan
                 sp.lib.EmDee_download(sp.md, b"forces", Fl.ctypes.data_as(cm.api._dp))
                 mine = torch.from_numpy(np.isfinite(Fl[:, 0]).astype(np.float64)).to(dev)
                 Fsum = torch.from_numpy(np.nan_to_num(Fl)).to(dev)
                 dist.all_reduce(mine)
                 dist.all_reduce(Fsum)
-                assert float(mine.min()) == 1.0 and float(mine.max()) == 1.0, "every atom must be written by exactly one rank"
+                assert float(mine.min()) == 1.0 and float(mine.max()) == 1.0, f"every atom must be written by exactly one rank: min {float(mine.min())} max {float(mine.max())} sum {float(mine.sum())} N {N} local finite {int(np.isfinite(Fl[:, 0]).sum())} {int(np.isfinite(Fl).sum())}"
                 if rank == 0:
                     err = cm.rel_force_error(Fsum.cpu().numpy(), so.download("forces"))
                     assert err <= 1e-10, f"local I/O step {k}: force error {err:.3e}"
