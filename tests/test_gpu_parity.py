@@ -389,3 +389,15 @@ def test_typed_path():
     sp, so = both(lambda lib: _two_type_system(lib, COUL_VARIANTS["coul_sf"]))   # softcore present: generic kernel
     assert_state_parity(sp, so)
     sp.finalize(), so.finalize()
+
+
+# ---- golden numbers that came from neither C++ restatement (tests/golden/numpy_models.py) -----------------------------
+import golden_cases as gc  # noqa: E402
+
+
+@pytest.mark.parametrize("name", gc.ALL_CASES)
+def test_numpy_golden_on_gpu(name):
+    """every pair modifier, pair_softcore_cut, every cutoff Coulomb model and the Q1 / Q1b / Q3b setter orders: the CUDA
+    product against the committed output of the independent numpy evaluator (the oracle is held to the same rows in
+    tests/test_numpy_golden.py)"""
+    gc.check(cm.product(), name)
