@@ -1092,8 +1092,16 @@ void EmDee_boost(tEmDee* md, double lambda, double alpha, double dt) {   // src/
   double CF = phi(alpha * dt) * dt;
   const double CP = 1.0 - alpha * CF;
   CF = lambda * CF;
-  if (lambda != 0.0 && !me->forcesUpToDate[me->layer - 1]) EmDee_compute_forces(md);
   const bool compute = md->Options.Compute;
+  if (lambda != 0.0 && !me->forcesUpToDate[me->layer - 1]) {
+    // free atoms whose forces come from the pair kernel alone: the kick is launched right behind that kernel and shares
+    // its host wait (engine.h: plan_kick); the call of Engine::boost below then only returns the sums
+    const bool extras = (!me->bondedTerms.empty() && (me->bonded[me->layer - 1] || me->coul[me->layer - 1].requires_kspace)) ||
+                        me->coul[me->layer - 1].requires_kspace;
+    if (me->initialized && me->nbodies() == 0 && md->Options.Translate && !extras)
+      me->engine->plan_kick(me->layer - 1, CP, CF, compute);
+    EmDee_compute_forces(md);
+  }
   if (me->nbodies() != 0) {
     emdee::KineticAll ka;
     me->engine->boost_all(me->layer - 1, CP, CF, md->Options.Translate, md->Options.Rotate, compute, ka);

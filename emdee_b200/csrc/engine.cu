@@ -152,6 +152,15 @@ struct Engine::Impl {
   // developer knobs (EmDeeX_tune; tools/force_lab.py): force-kernel variant and L1/shared carveout of the plain-LJ kernel
   int tune_variant = 0, tune_carveout = -1, tune_build = 0;
 
+  // kick bookkeeping (Engine::boost): the sums of the NEXT identical kick predicted by the last one, and a kick that
+  // compute_forces launches itself right behind the pair kernel (Engine::plan_kick)
+  bool ke_valid = false;
+  double ke_CP = 0, ke_CF = 0, ke_next[3] = {0, 0, 0};
+  int ke_layer = -1;
+  bool kick_planned = false, kick_done = false, kick_want_ke = false;
+  double kick_CP = 0, kick_CF = 0, kick_ke[3] = {0, 0, 0};
+  int kick_layer = -1;
+
   // host-visible results: pinned slots the last block of a reducing kernel writes; the host spins on the sequence number
   HostSlot* slots = nullptr;
   unsigned long long slot_seq[NSLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -309,7 +318,7 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.tickets.ensure(4);
   CUDA_CHECK(cudaMemset(s.tickets.p, 0, 4 * sizeof(unsigned int)));
   s.chkPartial.ensure(nblocks(natoms));
-  s.partial.ensure((size_t)nblocks(natoms) * 5);
+  s.partial.ensure((size_t)nblocks(natoms) * 6);
   CUDA_CHECK(cudaMallocHost(&s.h_scalars, 16 * sizeof(double)));
   CUDA_CHECK(cudaHostAlloc(&s.slots, NSLOTS * sizeof(HostSlot), cudaHostAllocMapped | cudaHostAllocPortable));
   std::memset(s.slots, 0, NSLOTS * sizeof(HostSlot));
@@ -641,10 +650,14 @@ bool rebuild_needed_phase2(Engine::Impl& s, double maximum, long long istar) {
 // one collective, one host wait per force evaluation
 void finish_pair_dist(Engine::Impl& s, bool with_decision) {
   if (s.peer_ok) {
-    k_reduce_small<<<1, 32, 0, s.stream>>>(5, s.scalars.p, s.peers, s.box, s.world, s.rank, ++s.rseq, s.scalars.p,
+    // a planned kick (launched behind the pair kernel, sums at scalars[5..10]) shares the reduction and the host wait
+    const bool kick = s.kick_planned && s.kick_want_ke;
+    const unsigned long long kseq = kick ? s.next_seq(SLOT_KINETIC) : 0ull;
+    k_reduce_small<<<1, 32, 0, s.stream>>>(5, kick ? 6 : 0, s.scalars.p, s.peers, s.box, s.world, s.rank, ++s.rseq, s.scalars.p,
                                            with_decision ? s.scalars.p + CRIT_DIST : nullptr, s.slots + SLOT_FORCE,
-                                           s.slot_seq[SLOT_FORCE]);
+                                           s.slot_seq[SLOT_FORCE], s.slots + SLOT_KINETIC, kseq);
     s.wait_slot(SLOT_FORCE);
+    if (kick) s.wait_slot(SLOT_KINETIC);
     return;
   }
   NCCL_CHECK(nccl().AllReduce(s.scalars.p, s.scalars.p, 5, ncclDouble, ncclSum, s.comm, s.stream));
@@ -744,10 +757,12 @@ void Engine::upload_coordinates(const double* R) {
   }
 }
 void Engine::upload_momenta(const double* P) {
+  d_->ke_valid = false;
   CUDA_CHECK(cudaMemcpy(d_->P.p, P, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
   d_->p_partial = false;
 }
 void Engine::upload_forces(int layer0, const double* F) {
+  d_->ke_valid = false;
   CUDA_CHECK(cudaMemcpy(d_->F.p + (size_t)layer0 * 3 * d_->N, F, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
 }
 void Engine::download_coordinates(double* R) {
@@ -997,6 +1012,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
   auto t_start = std::chrono::steady_clock::now();
 
   const double tp0 = wall_now();
+  s.ke_valid = false;   // new forces: the sums predicted by the last kick no longer describe the next one
   if (s.foreign_R) s.check_cached = false;
   // ---- K0: rebuild trigger (reference handle_neighbor_lists) -----------------------------------
   // Single GPU, coordinates moved by k_displace: the criterion of the current coordinates is (or will be) in
@@ -1063,6 +1079,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     CUDA_CHECK(cudaMemsetAsync(s.F.p + (size_t)layer0 * 3 * N, 0, 3 * (size_t)N * sizeof(double), s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     out = ForceScalars();
+    s.kick_planned = false;   // no pair kernel to follow: EmDee_boost issues the kick itself
     return rebuild;
   }
   launch_pair_kernel(layer0, compute, Lbox, speculative);
@@ -1092,6 +1109,7 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
       s.wait_slot(SLOT_FORCE);
     }
   }
+  collect_planned_kick();
   s.t_force += wall_now() - tp2;
   s.n_force += 1;
   const double* v = s.slots[SLOT_FORCE].v;
@@ -1305,48 +1323,124 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   s.last_force_timer = tmr;
   stats_.launches += 2;
   stats_.force_launches += 1;
+  if (s.kick_planned && s.kick_layer == layer0) launch_planned_kick(speculative);
+}
+
+// A kick that EmDee_boost is about to issue right after the force evaluation it triggers: compute_forces launches it
+// itself behind the pair kernel (one host wait, and on several GPUs one reduction, for both). Only where the kick can
+// follow the pair kernel directly: free atoms, no bonded / reciprocal-space terms added afterwards (abi.cpp decides).
+void Engine::plan_kick(int layer0, double CP, double CF, bool want_kinetic) {
+  Impl& s = *d_;
+  if (s.world > 1 && !(s.owned_valid && s.peer_ok)) return;   // NCCL-per-step mode: the kick stays a call of its own
+  if (s.exposed || s.foreign_R) return;
+  s.kick_planned = true;
+  s.kick_done = false;
+  s.kick_layer = layer0;
+  s.kick_CP = CP;
+  s.kick_CF = CF;
+  s.kick_want_ke = want_kinetic;
+}
+
+// launches the planned kick behind the pair kernel of the same layer (`speculative`: it checks the criterion like the pair kernel)
+void Engine::launch_planned_kick(bool speculative) {
+  Impl& s = *d_;
+  const double* Fl = s.F.p + (size_t)s.kick_layer * 3 * s.N;
+  const int ke = s.kick_want_ke ? 1 : 0;
+  const int tmr = timer_begin(TIMER_BOOST);
+  if (s.world > 1) {
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.kick_CP, s.kick_CF, s.P.p, Fl,
+                                                                      s.invMass.p, ke, s.partial.p, s.tickets.p + 1, s.scalars.p + 5,
+                                                                      speculative ? s.scalars.p + CRIT_DIST : nullptr, s.skinSq);
+  } else {
+    const unsigned long long seq = ke ? s.next_seq(SLOT_KINETIC) : 0ull;
+    k_boost<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, s.kick_CP, s.kick_CF, s.P.p, Fl, s.invMass.p, nullptr, ke,
+                                                                 s.partial.p, s.tickets.p + 1, s.scalars.p + 10,
+                                                                 ke ? s.slots + SLOT_KINETIC : nullptr, seq,
+                                                                 speculative ? s.scalars.p + 8 : nullptr, s.skinSq);
+  }
+  timer_end(tmr);
+  stats_.launches += 1;
+}
+
+// the planned kick has run (its sums, if any, are in the kinetic slot): remember them for Engine::boost
+void Engine::collect_planned_kick() {
+  Impl& s = *d_;
+  if (!s.kick_planned) return;
+  if (s.kick_want_ke) {
+    if (s.world == 1) s.wait_slot(SLOT_KINETIC);   // several GPUs: finish_pair_dist has waited for both slots
+    for (int x = 0; x < 3; ++x) {
+      s.kick_ke[x] = s.slots[SLOT_KINETIC].v[x];
+      s.ke_next[x] = s.slots[SLOT_KINETIC].v[3 + x];
+    }
+    s.ke_valid = true;
+    s.ke_CP = s.kick_CP;
+    s.ke_CF = s.kick_CF;
+    s.ke_layer = s.kick_layer;
+  }
+  s.kick_planned = false;
+  s.kick_done = true;
 }
 
 void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke) {
   Impl& s = *d_;
   const double tp0 = wall_now();
+  if (s.kick_done) {   // compute_forces has already executed this very kick (plan_kick)
+    s.kick_done = false;
+    if (s.kick_layer == layer0 && s.kick_CP == CP && s.kick_CF == CF && s.kick_want_ke == want_kinetic) {
+      for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.kick_ke[x];
+      s.t_boost += wall_now() - tp0;
+      s.n_boost += 1;
+      return;
+    }
+    fatal("momentum update", "internal: a planned kick does not match the kick requested");
+  }
+  s.kick_planned = false;
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
-  if (s.world > 1 && s.owned_valid) {
-    // several GPUs: the kick runs over the compact list of owned atoms (work ~ atoms of this rank, not N); the kinetic
-    // sums take one all-reduce and reach the host through the pinned slot
-    const int tmr = timer_begin(TIMER_BOOST);
-    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CP, CF, s.P.p, Fl, s.invMass.p,
-                                                                      want_kinetic ? 1 : 0, s.partial.p, s.tickets.p + 1,
-                                                                      s.scalars.p + 10);
+  const bool dist = s.world > 1 && s.owned_valid;
+  // the previous kick predicted this one's sums (same coefficients, same forces, momenta untouched in between)
+  const bool predicted = want_kinetic && s.ke_valid && s.ke_layer == layer0 && s.ke_CP == CP && s.ke_CF == CF && !s.exposed;
+  const int want = (want_kinetic && !predicted) ? 1 : 0;
+  s.ke_valid = false;
+  const int tmr = timer_begin(TIMER_BOOST);
+  if (dist) {
+    // several GPUs: the kick runs over the compact list of owned atoms (work ~ atoms of this rank, not N)
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CP, CF, s.P.p, Fl, s.invMass.p, want,
+                                                                      s.partial.p, s.tickets.p + 1, s.scalars.p + 10, nullptr, 0.0);
     timer_end(tmr);
     stats_.launches += 1;
-    if (want_kinetic) {
+    if (want) {
       const unsigned long long seq = s.next_seq(SLOT_KINETIC);
       if (s.peer_ok) {
-        k_reduce_small<<<1, 32, 0, s.stream>>>(3, s.scalars.p + 10, s.peers, s.box, s.world, s.rank, ++s.rseq, s.scalars.p + 10,
-                                               nullptr, s.slots + SLOT_KINETIC, seq);
+        k_reduce_small<<<1, 32, 0, s.stream>>>(0, 6, s.scalars.p + 10, s.peers, s.box, s.world, s.rank, ++s.rseq, s.scalars.p + 10,
+                                               nullptr, nullptr, 0ull, s.slots + SLOT_KINETIC, seq);
       } else {
-        NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));
-        k_publish3<<<1, 32, 0, s.stream>>>(s.scalars.p + 10, s.slots + SLOT_KINETIC, seq);
+        NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 6, ncclDouble, ncclSum, s.comm, s.stream));
+        k_publish_n<<<1, 32, 0, s.stream>>>(6, s.scalars.p + 10, s.slots + SLOT_KINETIC, seq);
       }
       s.wait_slot(SLOT_KINETIC);
-      for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
     }
   } else {
     const int grid = nblocks((s.N + APT - 1) / APT);
-    HostSlot* hs = want_kinetic ? s.slots + SLOT_KINETIC : nullptr;   // the last block writes the sums to the host slot
-    const unsigned long long seq = want_kinetic ? s.next_seq(SLOT_KINETIC) : 0ull;
-    const int tmr = timer_begin(TIMER_BOOST);
-    k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, nullptr, want_kinetic ? 1 : 0, s.partial.p,
-                                        s.tickets.p + 1, s.scalars.p + 10, hs, seq);
+    HostSlot* hs = want ? s.slots + SLOT_KINETIC : nullptr;   // the last block writes the sums to the host slot
+    const unsigned long long seq = want ? s.next_seq(SLOT_KINETIC) : 0ull;
+    k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, nullptr, want, s.partial.p, s.tickets.p + 1,
+                                        s.scalars.p + 10, hs, seq, nullptr, 0.0);
     timer_end(tmr);
     stats_.launches += 1;
-    if (want_kinetic) {
-      s.wait_slot(SLOT_KINETIC);
-      for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
-    } else if (s.exposed) {
-      CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    if (want) s.wait_slot(SLOT_KINETIC);
+    else if (s.exposed) CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  }
+  if (want) {
+    for (int x = 0; x < 3; ++x) {
+      ke.twoKE[x] = s.slots[SLOT_KINETIC].v[x];
+      s.ke_next[x] = s.slots[SLOT_KINETIC].v[3 + x];
     }
+    s.ke_valid = !s.exposed;
+    s.ke_CP = CP;
+    s.ke_CF = CF;
+    s.ke_layer = layer0;
+  } else if (predicted) {
+    for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.ke_next[x];
   }
   s.t_boost += wall_now() - tp0;
   s.n_boost += 1;
@@ -1446,11 +1540,12 @@ void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool ro
   const bool bodies = s.nbodies != 0;
   const bool dist = s.world > 1 && s.owned_valid;   // several GPUs: forces exist only for the atoms this rank owns
   const bool have_free = translate && s.nitems < s.N;
+  s.ke_valid = false;
   if (have_free) {
     const unsigned char* mask = !bodies ? (dist ? s.owned.p : nullptr) : (dist ? s.ownedFree.p : s.freeMask.p);
     const int grid = nblocks((s.N + APT - 1) / APT);
     k_boost<<<grid, TPB, 0, s.stream>>>(s.N, CP, CF, s.P.p, Fl, s.invMass.p, mask, want_kinetic ? 1 : 0,
-                                        s.partial.p, s.tickets.p + 1, s.scalars.p + 10, nullptr, 0ull);
+                                        s.partial.p, s.tickets.p + 1, s.scalars.p + 10, nullptr, 0ull, nullptr, 0.0);
     stats_.launches += 1;
     if (dist && want_kinetic)
       NCCL_CHECK(nccl().AllReduce(s.scalars.p + 10, s.scalars.p + 10, 3, ncclDouble, ncclSum, s.comm, s.stream));

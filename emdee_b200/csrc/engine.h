@@ -96,6 +96,9 @@ class Engine {
 
   // ---- device-resident dynamics for free atoms (reference boost / move / kinetic_energies) --
   void boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke);
+  // announce the kick that follows the next compute_forces of this layer (EmDee_boost with stale forces): it is then
+  // launched behind the pair kernel and shares its host wait / reduction; boost() afterwards just returns its sums
+  void plan_kick(int layer0, double CP, double CF, bool want_kinetic);
   void displace(double CR, double CP);
 
   // ---- rigid bodies (reference src/ArBee.f90; device-resident, one thread per body) -------------
@@ -154,6 +157,8 @@ class Engine {
  private:
   void rebuild_list(double Lbox);
   void launch_pair_kernel(int layer0, bool compute, double Lbox, bool speculative);
+  void launch_planned_kick(bool speculative);
+  void collect_planned_kick();
   int timer_begin(int kind);
   void timer_end(int idx);
   void timer_harvest(int idx);

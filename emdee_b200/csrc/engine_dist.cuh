@@ -78,41 +78,46 @@ __global__ void __launch_bounds__(TPB) k_check_owned(int n, const int* __restric
   maxidx_finish(v, partial, ticket, result);
 }
 
-// Free-atom kick of the owned atoms (k_boost through the owned list: the work is O(atoms of this rank), not O(N))
+// Free-atom kick of the owned atoms (k_boost through the owned list: the work is O(atoms of this rank), not O(N)); the
+// two sets of kinetic sums and the speculative `crit` as in k_boost
 __global__ void __launch_bounds__(TPB) k_boost_owned(int n, const int* __restrict__ list, double CP, double CF,
                                                      double* __restrict__ P, const double* __restrict__ F,
                                                      const double* __restrict__ invMass, int want_ke,
                                                      double* __restrict__ partial, unsigned int* __restrict__ ticket,
-                                                     double* __restrict__ out) {
-  __shared__ double red[TPB / 32][3];
+                                                     double* __restrict__ out, const double* __restrict__ crit, double skinSq) {
+  __shared__ double red[TPB / 32][6];
+  if (crit != nullptr && __ldcg(crit) > skinSq) return;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  double ke[3] = {0.0, 0.0, 0.0};
+  double ke[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (k < n) {
     const size_t a = (size_t)list[k];
     const double im = invMass[a];
 #pragma unroll
     for (int x = 0; x < 3; ++x) {
-      const double q = __dadd_rn(__dmul_rn(CP, P[3 * a + x]), __dmul_rn(CF, F[3 * a + x]));
+      const double f = F[3 * a + x];
+      const double q = __dadd_rn(__dmul_rn(CP, P[3 * a + x]), __dmul_rn(CF, f));
       P[3 * a + x] = q;
       ke[x] = __dmul_rn(__dmul_rn(im, q), q);
+      const double q2 = __dadd_rn(__dmul_rn(CP, q), __dmul_rn(CF, f));
+      ke[3 + x] = __dmul_rn(__dmul_rn(im, q2), q2);
     }
   }
   if (!want_ke) return;
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int x = 0; x < 3; ++x) {
+  for (int x = 0; x < 6; ++x) {
     double v = ke[x];
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (lane == 0) red[threadIdx.x >> 5][x] = v;
   }
   __syncthreads();
-  double mine[3] = {0.0, 0.0, 0.0};
+  double mine[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int x = 0; x < 3; ++x)
+    for (int x = 0; x < 6; ++x)
       for (int w = 0; w < TPB / 32; ++w) mine[x] += red[w][x];
   }
-  grid_finish<3>(mine, partial, ticket, out, 1.0);
+  grid_finish<6>(mine, partial, ticket, out, 1.0);
 }
 
 // Drift of the owned atoms fused with phase 1 of the criterion on the NEW coordinates: (max d_i, first index) over the list
@@ -179,10 +184,10 @@ __global__ void k_publish_force(const double* __restrict__ scalars, const double
   slot_publish(hs, seq);
 }
 
-// three kinetic sums (already summed over the ranks) -> pinned host slot
-__global__ void k_publish3(const double* __restrict__ src, HostSlot* hs, unsigned long long seq) {
+// n kinetic sums (already summed over the ranks) -> pinned host slot
+__global__ void k_publish_n(int n, const double* __restrict__ src, HostSlot* hs, unsigned long long seq) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  for (int q = 0; q < 3; ++q) hs->v[q] = src[q];
+  for (int q = 0; q < n; ++q) hs->v[q] = src[q];
   slot_publish(hs, seq);
 }
 
@@ -199,8 +204,9 @@ __global__ void k_publish3(const double* __restrict__ src, HostSlot* hs, unsigne
 // Mail slots are double-buffered by sequence parity (a rank can be at most one collective ahead of a peer).
 // ================================================================================================
 constexpr int PEER_MAX = 16;
-struct alignas(64) PeerMail {
-  double v[6];
+constexpr int MAIL_DOUBLES = 14;
+struct alignas(128) PeerMail {
+  double v[MAIL_DOUBLES];
   unsigned long long seq;   // written last (release.sys)
   unsigned long long pad;
 };
@@ -305,12 +311,15 @@ __global__ void k_wait_decide(PeerBox* mine, int world, int rank, int with_halo,
   crit[3] = g.m;
 }
 
-// mode 0: n plain sums to the host slot; mode 1: force scalars + the decision block (as k_publish_force)
-__global__ void k_reduce_small(int n, const double* __restrict__ src, PeerPtrs peers, PeerBox* mine, int world, int rank,
-                               unsigned long long seq, double* __restrict__ out, const double* __restrict__ crit, HostSlot* hs,
-                               unsigned long long hseq) {
-  __shared__ double got[PEER_MAX][6];
+// All-reduce of n1 + n2 <= MAIL_DOUBLES doubles (contiguous in `src`): the first n1 sums go to host slot hs1 -- when
+// n1 == 5 they are the force scalars and the decision block rides along as in k_publish_force --, the next n2 to hs2
+// (the kinetic sums of a kick that was launched right behind the pair kernel). Either slot may be absent (n = 0).
+__global__ void k_reduce_small(int n1, int n2, const double* __restrict__ src, PeerPtrs peers, PeerBox* mine, int world, int rank,
+                               unsigned long long seq, double* __restrict__ out, const double* __restrict__ crit, HostSlot* hs1,
+                               unsigned long long hseq1, HostSlot* hs2, unsigned long long hseq2) {
+  __shared__ double got[PEER_MAX][MAIL_DOUBLES];
   const int t = threadIdx.x;
+  const int n = n1 + n2;
   if (t < world) {
     PeerMail* m = &peers.box[t]->red[seq & 1ull][rank];
     for (int q = 0; q < n; ++q) st_sys(&m->v[q], src[q]);
@@ -328,18 +337,20 @@ __global__ void k_reduce_small(int n, const double* __restrict__ src, PeerPtrs p
     double sum = got[0][q];
     for (int r = 1; r < world; ++r) sum += got[r][q];
     out[q] = sum;
-    hs->v[q] = sum;
+    if (q < n1) hs1->v[q] = sum;
+    else hs2->v[q - n1] = sum;
   }
-  if (n == 5) {
-    hs->v[5] = 0.0;
-    hs->v[6] = 0.0;
+  if (n1 == 5) {
+    hs1->v[5] = 0.0;
+    hs1->v[6] = 0.0;
     if (crit != nullptr) {
-      hs->v[5] = crit[1];
-      hs->v[6] = crit[2];
-      if (crit[1] != 0.0) hs->v[0] = crit[3];
+      hs1->v[5] = crit[1];
+      hs1->v[6] = crit[2];
+      if (crit[1] != 0.0) hs1->v[0] = crit[3];
     }
   }
-  slot_publish(hs, hseq);
+  if (n1 > 0) slot_publish(hs1, hseq1);
+  if (n2 > 0) slot_publish(hs2, hseq2);
 }
 
 // dst = owned ? src : 0 (three doubles per atom): the summand of the all-reduce that rebuilds a full array

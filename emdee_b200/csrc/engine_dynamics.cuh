@@ -39,15 +39,23 @@ __device__ __forceinline__ void store12(double* __restrict__ p, long long a0, in
   }
 }
 
+// The kinetic sums come in two sets: [0..2] for the momenta this kick produces and [3..5] for the momenta ONE MORE
+// identical kick would produce from the same forces (velocity Verlet issues the second half kick of a step and the first
+// half kick of the next back to back): Engine::boost answers that next call from these sums without a reduction or a
+// host wait. Same operations, same order as the kernel that executes the next kick, so the numbers are bit-identical.
+// `crit`: speculative launch behind a speculative pair kernel (Engine::compute_forces): nothing happens when the rebuild
+// criterion fired.
 __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, double* __restrict__ P,
                                                const double* __restrict__ F, const double* __restrict__ invMass,
                                                const unsigned char* __restrict__ owned, int want_ke,
                                                double* __restrict__ partial, unsigned int* __restrict__ ticket,
-                                               double* __restrict__ out, HostSlot* hs, unsigned long long seq) {
-  __shared__ double red[TPB / 32][3];
+                                               double* __restrict__ out, HostSlot* hs, unsigned long long seq,
+                                               const double* __restrict__ crit, double skinSq) {
+  __shared__ double red[TPB / 32][6];
+  if (crit != nullptr && __ldcg(crit) > skinSq) return;
   const long long a0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * APT;
   const int n = (a0 >= N) ? 0 : (int)min((long long)APT, N - a0);
-  double k[3] = {0.0, 0.0, 0.0};
+  double k[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (n > 0) {
     bool own[APT];
     bool any = false;
@@ -69,6 +77,8 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
             const double q = __dadd_rn(__dmul_rn(CP, p[3 * j + x]), __dmul_rn(CF, f[3 * j + x]));
             p[3 * j + x] = q;
             k[x] += __dmul_rn(__dmul_rn(im, q), q);
+            const double q2 = __dadd_rn(__dmul_rn(CP, q), __dmul_rn(CF, f[3 * j + x]));
+            k[3 + x] += __dmul_rn(__dmul_rn(im, q2), q2);
           }
         }
       }
@@ -78,19 +88,19 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
   if (!want_ke) return;
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int x = 0; x < 3; ++x) {
+  for (int x = 0; x < 6; ++x) {
     double v = k[x];
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (lane == 0) red[threadIdx.x >> 5][x] = v;
   }
   __syncthreads();
-  double mine[3] = {0.0, 0.0, 0.0};
+  double mine[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int x = 0; x < 3; ++x)
+    for (int x = 0; x < 6; ++x)
       for (int w = 0; w < TPB / 32; ++w) mine[x] += red[w][x];
   }
-  grid_finish<3>(mine, partial, ticket, out, 1.0, hs, seq);
+  grid_finish<6>(mine, partial, ticket, out, 1.0, hs, seq);
 }
 
 // R = CR*R + CP*P/m, fused with the rebuild criterion on the NEW coordinates (|R - R0|^2 ordered scan).

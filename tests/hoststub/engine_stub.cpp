@@ -75,6 +75,7 @@ void Engine::update_list_stats(int, double) {}
 long long Engine::download_pairs(int*, long long) { return 0; }
 void Engine::synchronize() {}
 EngineStats Engine::stats() { return stats_; }
+void Engine::plan_kick(int, double, double, bool) {}
 int Engine::comm_mode() { return 0; }
 void Engine::io_bytes(long long& h2d, long long& d2h) { h2d = d2h = 0; }
 void Engine::kernel_times(double* ms8, long long* n8) { for (int k = 0; k < 8; ++k) { ms8[k] = 0.0; n8[k] = 0; } }
