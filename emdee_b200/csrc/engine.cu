@@ -111,6 +111,11 @@ struct Engine::Impl {
   DBuf<int> selCount;
   DBuf<MaxIdx> miPartial, miResult;
   MaxIdx* h_mi = nullptr;          // pinned, world entries
+  // compact rebuild path: the atoms this rank bins at a rebuild (previously owned + just received), a per-atom stamp that
+  // tells which atoms are in that list, and scratch for sorting the halo lists of the NCCL-per-step mode
+  DBuf<int> candList, stamp, sortTmp, recvIds;
+  int nCand = 0, epoch = 0;
+  bool compact = false;            // the current rebuild runs over candList
   DBuf<int> ownedList;             // compact ascending list of the atoms this rank owns (per-step kernels run over it)
   int nOwn = 0;
   bool mi_fresh = false;           // miResult[world] holds phase 1 of the criterion for the current coordinates (k_displace_owned)
@@ -354,7 +359,7 @@ Engine::~Engine() {
   s.nbrCount.release(); s.flags.release(); s.sGhost.release(); s.pos.release(); s.scanTmp.release();
   s.owned.release(); s.scratch3.release(); s.haloFlags.release(); s.selCount.release(); s.miPartial.release(); s.miResult.release();
   for (int k = 0; k < 4; ++k) { s.haloList[k].release(); s.haloBuf[k].release(); }
-  s.known.release(); s.migCounts.release(); s.ownedList.release();
+  s.known.release(); s.migCounts.release(); s.ownedList.release(); s.candList.release(); s.stamp.release(); s.sortTmp.release(); s.recvIds.release();
   s.terms.release(); s.termFirst.release(); s.termRef.release();
   s.ewN.release(); s.ewKType.release(); s.ewPrefac.release(); s.ewLambda.release(); s.ewSigma.release(); s.ewPartial.release();
   s.bFirst.release(); s.bAtom.release(); s.bMItem.release(); s.bD.release(); s.bState.release(); s.bPartial.release();
@@ -489,6 +494,50 @@ void gather_full(Engine::Impl& s, double* X) {
 // per-rebuild: compact the four halo lists and the owned list (all ascending in the atom index) from the cell layers
 void build_halo_lists(Engine::Impl& s) {
   const int N = s.N;
+  if (s.compact) {
+    // over the atoms this rank just binned (candList) instead of all N; stable compactions keep candList's order, which
+    // is the same from run to run. The NCCL-per-step mode needs a sender's list and the matching receiver's list in the
+    // SAME order (no indices travel): there the four small halo lists are sorted by atom index afterwards.
+    const int n = s.nCand;
+    s.haloFlags.ensure(5 * (size_t)n + 16);
+    s.selCount.ensure(8);
+    k_halo_flags_listed<<<std::max(1, nblocks(n)), TPB, 0, s.stream>>>(n, s.candList.p, s.grid, s.atomCell.p, s.haloFlags.p);
+    size_t need = 0;
+    cub::DeviceSelect::Flagged(nullptr, need, s.candList.p, s.haloFlags.p, (int*)nullptr, s.selCount.p, n, s.stream);
+    if (need > s.scanTmpBytes) {
+      s.scanTmp.ensure(need);
+      s.scanTmpBytes = need;
+    }
+    s.ownedList.ensure((size_t)n + 16);
+    for (int k = 0; k < 4; ++k) {
+      s.haloList[k].ensure((size_t)n + 16);
+      cub::DeviceSelect::Flagged(s.scanTmp.p, need, s.candList.p, s.haloFlags.p + (size_t)k * n, s.haloList[k].p, s.selCount.p + k, n,
+                                 s.stream);
+    }
+    cub::DeviceSelect::Flagged(s.scanTmp.p, need, s.candList.p, s.haloFlags.p + 4 * (size_t)n, s.ownedList.p, s.selCount.p + 4, n,
+                               s.stream);
+    int h[5];
+    CUDA_CHECK(cudaMemcpyAsync(h, s.selCount.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    if (s.env_debug) std::fprintf(stderr, "[emdee r%d] halo lists (compact, %d candidates): send up %d dn %d, recv below %d above %d, owned %d\n", s.rank, n, h[0], h[1], h[2], h[3], h[4]);
+    for (int k = 0; k < 4; ++k) {
+      s.haloCount[k] = h[k];
+      s.haloBuf[k].ensure(3 * (size_t)h[k] + 8, 1.2);
+      if (!s.peer_ok && h[k] > 1) {   // NCCL-per-step mode: ascending atom index on both sides of every message
+        s.sortTmp.ensure((size_t)h[k] + 16);
+        size_t sb = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, sb, s.haloList[k].p, s.sortTmp.p, h[k], 0, 32, s.stream);
+        if (sb > s.scanTmpBytes) {
+          s.scanTmp.ensure(sb);
+          s.scanTmpBytes = sb;
+        }
+        cub::DeviceRadixSort::SortKeys(s.scanTmp.p, sb, s.haloList[k].p, s.sortTmp.p, h[k], 0, 32, s.stream);
+        CUDA_CHECK(cudaMemcpyAsync(s.haloList[k].p, s.sortTmp.p, (size_t)h[k] * sizeof(int), cudaMemcpyDeviceToDevice, s.stream));
+      }
+    }
+    s.nOwn = h[4];
+    return;
+  }
   s.haloFlags.ensure(4 * (size_t)N);
   s.selCount.ensure(8);
   k_halo_flags<<<nblocks(N), TPB, 0, s.stream>>>(N, s.grid, s.atomCell.p, s.haloFlags.p);
@@ -586,19 +635,22 @@ void migrate(Engine::Impl& s, double Lbox) {
     return;
   }
   const int up = (s.rank + 1) % s.world, dn = (s.rank + s.world - 1) % s.world;
-  s.haloFlags.ensure(4 * (size_t)N);
-  s.selCount.ensure(4);
-  k_mig_flags<<<nblocks(N), TPB, 0, s.stream>>>(N, Lbox, s.grid, s.R.p, s.owned.p, s.haloFlags.p);
-  cub::CountingInputIterator<int> ids(0);
+  // Compact path: everything below runs over the atoms this rank owned at the last build (ownedList) and the records it
+  // receives -- O(atoms of the slab), not O(N). The atoms to bin afterwards are collected in candList:
+  //   [previously owned atoms, in ownedList's order | records from below | records from above (minus duplicates)]
+  const int n = s.nOwn;
+  s.haloFlags.ensure(5 * (size_t)std::max(n, 1) + 16);
+  s.selCount.ensure(8);
+  k_mig_flags_listed<<<std::max(1, nblocks(n)), TPB, 0, s.stream>>>(n, s.ownedList.p, Lbox, s.grid, s.R.p, s.haloFlags.p);
   size_t need = 0;
-  cub::DeviceSelect::Flagged(nullptr, need, ids, s.haloFlags.p, (int*)nullptr, s.selCount.p, N, s.stream);
+  cub::DeviceSelect::Flagged(nullptr, need, s.ownedList.p, s.haloFlags.p, (int*)nullptr, s.selCount.p, std::max(n, 1), s.stream);
   if (need > s.scanTmpBytes) {
     s.scanTmp.ensure(need);
     s.scanTmpBytes = need;
   }
   for (int k = 0; k < 2; ++k) {
-    s.migList[k].ensure(N);
-    cub::DeviceSelect::Flagged(s.scanTmp.p, need, ids, s.haloFlags.p + (size_t)k * N, s.migList[k].p, s.selCount.p + k, N,
+    s.migList[k].ensure((size_t)n + 16);
+    cub::DeviceSelect::Flagged(s.scanTmp.p, need, s.ownedList.p, s.haloFlags.p + (size_t)k * n, s.migList[k].p, s.selCount.p + k, n,
                                s.stream);
   }
   // counts: every rank learns every rank's (up, down) record counts with one small all-gather
@@ -624,11 +676,46 @@ void migrate(Engine::Impl& s, double Lbox) {
   if (c[2] > 0) NCCL_CHECK(nccl().Recv(s.migRecv[0].p, 7 * (size_t)c[2], ncclDouble, dn, s.comm, s.stream));
   if (c[3] > 0) NCCL_CHECK(nccl().Recv(s.migRecv[1].p, 7 * (size_t)c[3], ncclDouble, up, s.comm, s.stream));
   NCCL_CHECK(nccl().GroupEnd());
-  // known = previously owned + received
-  CUDA_CHECK(cudaMemcpyAsync(s.known.p, s.owned.p, N, cudaMemcpyDeviceToDevice, s.stream));
-  for (int k = 0; k < 2; ++k)
-    if (c[2 + k] > 0)
-      k_unpack7<<<nblocks(c[2 + k]), TPB, 0, s.stream>>>(c[2 + k], s.migRecv[k].p, s.R.p, s.P.p, s.known.p);
+  // candList = previously owned + received
+  s.epoch += 1;
+  if (s.stamp.n < (size_t)N) {
+    s.stamp.ensure(N);
+    CUDA_CHECK(cudaMemsetAsync(s.stamp.p, 0, (size_t)N * sizeof(int), s.stream));
+  }
+  s.candList.ensure((size_t)n + c[2] + c[3] + 16, 1.1);
+  s.recvIds.ensure((size_t)c[3] + 16, 1.1);
+  if (n > 0) {
+    CUDA_CHECK(cudaMemcpyAsync(s.candList.p, s.ownedList.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s.stream));
+    k_stamp_listed<<<nblocks(n), TPB, 0, s.stream>>>(n, s.ownedList.p, s.stamp.p, s.epoch);
+  }
+  if (c[2] > 0)
+    k_unpack7_listed<<<nblocks(c[2]), TPB, 0, s.stream>>>(c[2], s.migRecv[0].p, s.R.p, s.P.p, s.stamp.p, s.epoch, 0, s.candList.p + n,
+                                                          nullptr);
+  int fresh = c[3];
+  if (c[3] > 0) {
+    if (s.world > 2) {   // the two messages come from different ranks: no atom can be in both
+      k_unpack7_listed<<<nblocks(c[3]), TPB, 0, s.stream>>>(c[3], s.migRecv[1].p, s.R.p, s.P.p, s.stamp.p, s.epoch, 0,
+                                                            s.candList.p + n + c[2], nullptr);
+    } else {             // two ranks: both messages come from the same peer and may name the same atom
+      unsigned char* fl = s.haloFlags.p;   // (the migration flags are no longer needed)
+      if (s.haloFlags.n < (size_t)c[3] + 16) {
+        s.haloFlags.ensure((size_t)c[3] + 16);
+        fl = s.haloFlags.p;
+      }
+      k_unpack7_listed<<<nblocks(c[3]), TPB, 0, s.stream>>>(c[3], s.migRecv[1].p, s.R.p, s.P.p, s.stamp.p, s.epoch, 1, s.recvIds.p, fl);
+      size_t nb2 = 0;
+      cub::DeviceSelect::Flagged(nullptr, nb2, s.recvIds.p, fl, (int*)nullptr, s.selCount.p + 5, c[3], s.stream);
+      if (nb2 > s.scanTmpBytes) {
+        s.scanTmp.ensure(nb2);
+        s.scanTmpBytes = nb2;
+      }
+      cub::DeviceSelect::Flagged(s.scanTmp.p, nb2, s.recvIds.p, fl, s.candList.p + n + c[2], s.selCount.p + 5, c[3], s.stream);
+      CUDA_CHECK(cudaMemcpyAsync(&fresh, s.selCount.p + 5, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+      CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    }
+  }
+  s.nCand = n + c[2] + fresh;
+  s.compact = true;
 }
 
 // Distributed rebuild decision, phase 2 (rare: maximum <= skin^2 < 4*maximum and i* > 0): `next` = max of d_i over the
@@ -1187,8 +1274,12 @@ void Engine::rebuild_list(double Lbox) {
     CUDA_CHECK(cudaMemsetAsync(s.cellCount.p, 0, (ncell + 1) * sizeof(int), s.stream));
     CUDA_CHECK(cudaMemsetAsync(s.cellFill.p, 0, (ncell + 1) * sizeof(int), s.stream));
     const int tmr_b = timer_begin(TIMER_BINNING);
-    k_bin<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, N, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p, s.owned.p,
-                                            s.world > 1 ? s.known.p : nullptr, s.cellCount.p);
+    if (s.compact)
+      k_bin<<<std::max(1, nblocks(s.nCand)), TPB, 0, s.stream>>>(s.R.p, s.nCand, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p,
+                                                                 s.owned.p, nullptr, s.cellCount.p, s.candList.p);
+    else
+      k_bin<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, N, Lbox, s.grid, s.Rs.p, s.atomCell.p, s.atomFloor.p, s.owned.p,
+                                              s.world > 1 ? s.known.p : nullptr, s.cellCount.p, nullptr);
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, s.cellCount.p, s.cellStart.p, (int)(ncell + 1), s.stream);
     if (need > s.scanTmpBytes) {
@@ -1212,8 +1303,12 @@ void Engine::rebuild_list(double Lbox) {
     s.sPosF.ensure(Next, 1.1);
     s.nbrCount.ensure(Next, 1.1);
     s.pos.ensure(Next, 1.1);
-    k_fill<<<nblocks(N), TPB, 0, s.stream>>>(N, s.grid, s.atomCell.p, s.cellStart.p, s.cellFill.p, s.slotAtom.p,
-                                             s.slotImg.p, s.slotCell.p);
+    if (s.compact)
+      k_fill<<<std::max(1, nblocks(s.nCand)), TPB, 0, s.stream>>>(s.nCand, s.grid, s.atomCell.p, s.cellStart.p, s.cellFill.p, s.slotAtom.p,
+                                                                  s.slotImg.p, s.slotCell.p, s.candList.p);
+    else
+      k_fill<<<nblocks(N), TPB, 0, s.stream>>>(N, s.grid, s.atomCell.p, s.cellStart.p, s.cellFill.p, s.slotAtom.p,
+                                               s.slotImg.p, s.slotCell.p, nullptr);
     PlaceArgs pa;
     pa.Next = Next; pa.slotAtom = s.slotAtom.p; pa.slotImg = s.slotImg.p; pa.slotCell = s.slotCell.p;
     pa.cellStart = s.cellStart.p; pa.atomFloor = s.atomFloor.p; pa.Rs = s.Rs.p; pa.atomType = s.type.p;
@@ -1268,7 +1363,12 @@ void Engine::rebuild_list(double Lbox) {
       s.all_known = false;
       s.halo_fresh = true;   // migrate() just made every needed position current
     }
-    CUDA_CHECK(cudaMemcpyAsync(s.R0.p, s.R.p, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
+    if (s.compact) {   // the criterion of a rank only looks at the atoms it owns
+      if (s.nOwn > 0) k_copy3_listed<<<nblocks(s.nOwn), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.R.p, s.R0.p);
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(s.R0.p, s.R.p, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
+    }
+    s.compact = false;
     CUDA_CHECK(cudaMemsetAsync(s.scalars.p + 8, 0, sizeof(double), s.stream));   // R0 = R: zero displacement
     s.check_cached = true;
     s.mi_fresh = false;   // R0 changed: the distributed criterion state is re-evaluated on the next force call

@@ -413,6 +413,60 @@ __global__ void __launch_bounds__(TPB) k_unpack7(int n, const double* __restrict
   known[a] = 1;
 }
 
+// ---- compact forms: the same decisions over a LIST of atoms (what this rank owned at the last build, plus what it just
+// received) instead of all N, so that a rebuild costs O(atoms of the slab) on every rank ----
+__global__ void __launch_bounds__(TPB) k_mig_flags_listed(int n, const int* __restrict__ list, double L, GridDesc g,
+                                                          const double* __restrict__ R, unsigned char* __restrict__ fl) {   // 2 flag arrays of n
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const size_t i = (size_t)list[k];
+  const double rs = __ddiv_rn(R[3 * i + 2], L);
+  int cz = (int)__dmul_rn((double)g.M, __dsub_rn(rs, floor(rs)));
+  if (cz >= g.M) cz = g.M - 1;
+  const int z1 = g.z0 + g.nzl;
+  fl[k] = ((cz - (z1 - 3)) % g.M + g.M) % g.M < 5;                 // layers z1-3 .. z1+1 (periodic)
+  fl[(size_t)n + k] = (((g.z0 + 2) - cz) % g.M + g.M) % g.M < 5;   // layers z0-2 .. z0+2
+}
+__global__ void __launch_bounds__(TPB) k_stamp_listed(int n, const int* __restrict__ list, int* __restrict__ stamp, int epoch) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) stamp[list[k]] = epoch;
+}
+// received (id, R, P) records: coordinates and momenta stored; mode 0: every record is new to this rank -> id appended at
+// cand[k] and stamped; mode 1: ids[k] = id and fresh[k] = "not seen in this rebuild yet" (two ranks only: the same atom can
+// arrive in both messages), the caller compacts the fresh ones behind the others
+__global__ void __launch_bounds__(TPB) k_unpack7_listed(int n, const double* __restrict__ buf, double* __restrict__ R,
+                                                        double* __restrict__ P, int* __restrict__ stamp, int epoch, int mode,
+                                                        int* __restrict__ ids, unsigned char* __restrict__ fresh) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double* b = buf + 7 * (size_t)k;
+  const int a = (int)b[0];
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    R[3 * (size_t)a + x] = b[1 + x];
+    P[3 * (size_t)a + x] = b[4 + x];
+  }
+  ids[k] = a;
+  if (mode == 0) stamp[a] = epoch;
+  else fresh[k] = stamp[a] != epoch;
+}
+// five flag arrays of n over the listed atoms: send up, send down, receive from below, receive from above, owned
+__global__ void __launch_bounds__(TPB) k_halo_flags_listed(int n, const int* __restrict__ list, GridDesc g,
+                                                           const int* __restrict__ atomCell, unsigned char* __restrict__ fl) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int cz = (atomCell[list[k]] >> 20) & 1023;
+  const int z1 = g.z0 + g.nzl;
+  const bool own = cz >= g.z0 && cz < z1;
+  const int up0 = z1 % g.M, up1 = (z1 + 1) % g.M;
+  const int dn0 = (g.z0 - 2 + g.M) % g.M, dn1 = (g.z0 - 1 + g.M) % g.M;
+  fl[k] = own && cz >= z1 - 2;
+  fl[(size_t)n + k] = own && cz < g.z0 + 2;
+  fl[2 * (size_t)n + k] = !own && (cz == dn0 || cz == dn1);
+  fl[3 * (size_t)n + k] = !own && (cz == up0 || cz == up1);
+  fl[4 * (size_t)n + k] = own;
+}
+
 // halo bookkeeping: which owned atoms sit in my top / bottom two layers (to send), which foreign atoms sit
 // in the two layers above / below my slab (to receive). Lists are compacted in ascending atom order, so
 // a sender's list and the matching receiver's list are identical without exchanging indices.

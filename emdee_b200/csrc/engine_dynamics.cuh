@@ -29,6 +29,18 @@ __device__ __forceinline__ void load12(const double* __restrict__ p, long long a
     for (int k = 0; k < 3 * APT; ++k) v[k] = (k < 3 * n) ? p[3 * a0 + k] : 0.0;
   }
 }
+// masked store: only the atoms flagged in `own` are written. On several GPUs the slots of atoms another rank owns must
+// not be touched at all -- not even rewritten with the value just read: the neighbor's halo push (k_push_step) may land
+// between the read and the write.
+__device__ __forceinline__ void store12_own(double* __restrict__ p, long long a0, const bool (&own)[APT], const double (&v)[3 * APT]) {
+#pragma unroll
+  for (int j = 0; j < APT; ++j)
+    if (own[j]) {
+      p[3 * (a0 + j)] = v[3 * j];
+      p[3 * (a0 + j) + 1] = v[3 * j + 1];
+      p[3 * (a0 + j) + 2] = v[3 * j + 2];
+    }
+}
 __device__ __forceinline__ void store12(double* __restrict__ p, long long a0, int n, const double (&v)[3 * APT]) {
   if (vec_ok(p, a0, n)) {
     double4* q = reinterpret_cast<double4*>(p + 3 * a0);
@@ -82,7 +94,8 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
           }
         }
       }
-      store12(P, a0, n, p);   // non-owned slots are written back unchanged
+      if (owned == nullptr) store12(P, a0, n, p);
+      else store12_own(P, a0, own, p);
     }
   }
   if (!want_ke) return;
@@ -135,7 +148,8 @@ __global__ void __launch_bounds__(TPB) k_displace(int N, double CR, double CP, d
             r[3 * j + x] = __dadd_rn(__dmul_rn(CR, r[3 * j + x]), __dmul_rn(__dmul_rn(CP, p[3 * j + x]), im));
         }
       }
-      store12(R, a0, n, r);
+      if (owned == nullptr) store12(R, a0, n, r);
+      else store12_own(R, a0, own, r);
       if (partial != nullptr) {
         double r0[3 * APT];
         load12(R0, a0, n, r0);

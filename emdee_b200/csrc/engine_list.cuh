@@ -154,12 +154,16 @@ __device__ __forceinline__ int image_shifts_z(int cz, const GridDesc& g, int s[3
   return n;
 }
 
+// `list` (several GPUs between full uploads): only the n listed atoms are binned -- the atoms this rank owned at the last
+// build plus what the neighbors just sent -- so that the work follows the slab, not the whole system
 __global__ void __launch_bounds__(TPB) k_bin(const double* __restrict__ R, int N, double L, GridDesc g,
                                              double* __restrict__ Rs, int* __restrict__ atomCell,
                                              int* __restrict__ atomFloor, unsigned char* __restrict__ owned,
-                                             const unsigned char* __restrict__ known, int* __restrict__ cellCount) {
+                                             const unsigned char* __restrict__ known, int* __restrict__ cellCount,
+                                             const int* __restrict__ list) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (list != nullptr) i = list[i];   // N is the list length
   if (known != nullptr && !known[i]) {   // multi-GPU: this rank holds no current position for the atom
     owned[i] = 0;
     atomCell[i] = -1;
@@ -191,9 +195,10 @@ __global__ void __launch_bounds__(TPB) k_bin(const double* __restrict__ R, int N
 __global__ void __launch_bounds__(TPB) k_fill(int N, GridDesc g, const int* __restrict__ atomCell,
                                               const int* __restrict__ cellStart, int* __restrict__ cellFill,
                                               int* __restrict__ slotAtom, int* __restrict__ slotImg,
-                                              int* __restrict__ slotCell) {
+                                              int* __restrict__ slotCell, const int* __restrict__ list) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (list != nullptr) i = list[i];
   int pc = atomCell[i];
   if (pc < 0) return;   // not known to this rank
   int c[3] = {pc & 1023, (pc >> 10) & 1023, (pc >> 20) & 1023};
