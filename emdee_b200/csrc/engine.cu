@@ -155,7 +155,7 @@ struct Engine::Impl {
   // environment switches, read once at construction (nothing on the per-step path calls getenv)
   bool env_debug = false, env_profile = false, env_no_migrate = false;
   // developer knobs (EmDeeX_tune; tools/force_lab.py): force-kernel variant and L1/shared carveout of the plain-LJ kernel
-  int tune_variant = 0, tune_carveout = -1, tune_build = 0, tune_typed = 0;
+  int tune_variant = 0, tune_carveout = -1, tune_build = 0;
 
   // kick bookkeeping (Engine::boost): the sums of the NEXT identical kick predicted by the last one, and a kick that
   // compute_forces launches itself right behind the pair kernel (Engine::plan_kick)
@@ -886,7 +886,6 @@ void Engine::tune(const char* knob, int value) {
   if (std::strcmp(knob, "force_variant") == 0) d_->tune_variant = value;
   else if (std::strcmp(knob, "carveout") == 0) d_->tune_carveout = value;
   else if (std::strcmp(knob, "build_variant") == 0) d_->tune_build = value;
-  else if (std::strcmp(knob, "typed_variant") == 0) d_->tune_typed = value;
   else if (std::strcmp(knob, "local_io") == 0) d_->local_io = value != 0;
   else fatal("tuning", "unknown knob");
 }
@@ -977,42 +976,31 @@ bool build_typed_table(const LayerTable& lt, std::vector<TypedEntry>& out, int& 
   return true;
 }
 
-// `variant` (EmDeeX_tune "typed_variant", tools/force_lab.py --spce): 0 = branch per pair, 1-3 = branch-free pair term with
-// 4 / 2 / 3 pairs in flight
-template <int PM, int CK, bool FLAT, int UNROLL>
-void launch_typed_v(ForceArgs& a, const TypedEntry* ttab, bool compute, cudaStream_t st, int grid, size_t smem) {
-  if (a.nt == 2) {
-    if (compute) k_pair_forces_typed<PM, CK, true, true, FLAT, UNROLL><<<grid, 256, 0, st>>>(a, ttab);
-    else k_pair_forces_typed<PM, CK, false, true, FLAT, UNROLL><<<grid, 256, 0, st>>>(a, ttab);
-  } else {
-    if (compute) k_pair_forces_typed<PM, CK, true, false, FLAT, UNROLL><<<grid, 256, smem, st>>>(a, ttab);
-    else k_pair_forces_typed<PM, CK, false, false, FLAT, UNROLL><<<grid, 256, smem, st>>>(a, ttab);
-  }
-}
 template <int PM, int CK>
-void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st, int variant) {
+void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
   const int grid = nblocks(a.Next, 256);
   partial.ensure((size_t)grid * 5);
   a.partial = partial.p;
   const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
-  switch (variant) {
-    case 1: launch_typed_v<PM, CK, true, 4>(a, ttab, compute, st, grid, smem); break;
-    case 2: launch_typed_v<PM, CK, true, 2>(a, ttab, compute, st, grid, smem); break;
-    case 3: launch_typed_v<PM, CK, true, 3>(a, ttab, compute, st, grid, smem); break;
-    default: launch_typed_v<PM, CK, false, 4>(a, ttab, compute, st, grid, smem); break;
+  if (a.nt == 2) {
+    if (compute) k_pair_forces_typed<PM, CK, true, true><<<grid, 256, 0, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, true><<<grid, 256, 0, st>>>(a, ttab);
+  } else {
+    if (compute) k_pair_forces_typed<PM, CK, true, false><<<grid, 256, smem, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, false><<<grid, 256, smem, st>>>(a, ttab);
   }
 }
 
 template <int PM>
-bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st, int variant) {
+bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
   using namespace nb;
   switch (ck) {
-    case K_COUL_NONE: launch_typed<PM, K_COUL_NONE>(a, partial, ttab, compute, st, variant); return true;
-    case K_COUL_CUT: launch_typed<PM, K_COUL_CUT>(a, partial, ttab, compute, st, variant); return true;
-    case K_COUL_SF: launch_typed<PM, K_COUL_SF>(a, partial, ttab, compute, st, variant); return true;
-    case K_COUL_DAMPED: launch_typed<PM, K_COUL_DAMPED>(a, partial, ttab, compute, st, variant); return true;
-    case K_COUL_DAMPED_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SMOOTHED>(a, partial, ttab, compute, st, variant); return true;
-    case K_COUL_DAMPED_SQUARE_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SQUARE_SMOOTHED>(a, partial, ttab, compute, st, variant); return true;
+    case K_COUL_NONE: launch_typed<PM, K_COUL_NONE>(a, partial, ttab, compute, st); return true;
+    case K_COUL_CUT: launch_typed<PM, K_COUL_CUT>(a, partial, ttab, compute, st); return true;
+    case K_COUL_SF: launch_typed<PM, K_COUL_SF>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED: launch_typed<PM, K_COUL_DAMPED>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SMOOTHED>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED_SQUARE_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SQUARE_SMOOTHED>(a, partial, ttab, compute, st); return true;
     default: return false;
   }
 }
@@ -1036,8 +1024,8 @@ bool try_typed_path(Engine::Impl& s, int layer0, const LayerTable& lt, int ck, F
     }
   }
   if (s.typedState[layer0] != 1) return false;
-  return s.typedPM[layer0] == nb::M_NONE ? launch_typed_ck<nb::M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream, s.tune_typed)
-                                         : launch_typed_ck<nb::M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream, s.tune_typed);
+  return s.typedPM[layer0] == nb::M_NONE ? launch_typed_ck<nb::M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream)
+                                         : launch_typed_ck<nb::M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream);
 }
 
 // FP32 pre-test band (see k_build_list). Positions are ghost-shifted scaled coordinates, |p| <= pmax.

@@ -33,3 +33,7 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_bu
 python tools/ncu_summary.py gpurun_out/r2d_build.ncu-rep > gpurun_out/r2d_build.txt 2>&1; head -12 gpurun_out/r2d_build.txt
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2d_launches.csv python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-spce --no-parity --no-e2e > /dev/null 2>&1
 ls -la gpurun_out | tail -8
+for kn in k_boost k_displace k_refresh_positions; do
+timeout 300 ncu --set full --clock-control none -k regex:$kn -s 20 -c 1 -o gpurun_out/r2d_$kn python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-spce --no-parity --no-e2e > /dev/null 2>&1
+python tools/ncu_summary.py gpurun_out/r2d_$kn.ncu-rep > gpurun_out/r2d_$kn.txt 2>&1; head -22 gpurun_out/r2d_$kn.txt
+done
