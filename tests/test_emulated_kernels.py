@@ -104,11 +104,3 @@ def test_scheduling_order_and_fma_contraction_do_not_matter():
         out, _ = p.communicate(timeout=1800)
         assert p.returncode == 0, f"{extra}: " + out[-3000:]
 
-
-# ---- the product's sources (abi.cpp + kernels through the emulator) against the independent numpy golden ---------------
-import golden_cases as gc  # noqa: E402
-
-
-@pytest.mark.parametrize("name", [n for n in gc.ALL_CASES if not n.startswith("spce_")] + ["spce_coul_damped_square_smoothed", "spce_two_lj_types_mixed"])
-def test_emulated_product_matches_numpy_golden(name):
-    gc.check(cm.emulated(), name)

@@ -391,6 +391,49 @@ def test_typed_path():
     sp.finalize(), so.finalize()
 
 
+def test_kicks_with_energies_every_step():
+    """Options.Compute on at every call, as bench.py runs: the kick EmDee_boost issues after a force evaluation is
+    launched behind the pair kernel (Engine::plan_kick) and the first kick of the next step is answered from the sums
+    the previous kick predicted. Every value a call returns must be what the oracle returns at that call."""
+    def lj(lib, e, s):
+        return lib.EmDee_pair_lj_cut(e, s)
+    sp, c = cm.lj_sample_system(cm.product(), lj)
+    so, _ = cm.lj_sample_system(cm.oracle(), lj)
+    for s in (sp, so):
+        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
+        s.md.Options.Compute = True
+    dt = c["Dt"]
+    for step in range(25):
+        for call in range(3):
+            for s in (sp, so):
+                if call == 1:
+                    s.displace(1.0, 0.0, dt)
+                else:
+                    s.boost(1.0, 0.0, 0.5 * dt)
+            if call != 1:
+                assert cm.rel(sp.md.Kinetic.Total, so.md.Kinetic.Total) < 1e-11, (step, call)
+                for x in range(3):
+                    assert cm.rel(sp.md.Kinetic.TransPart[x], so.md.Kinetic.TransPart[x]) < 1e-11
+        assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-10, step
+        assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-9, step
+    # a kick with other coefficients, a momentum upload and a thermostat-like scaling in between: predictions must not be reused
+    for s in (sp, so):
+        s.boost(1.0, 0.0, 0.25 * dt)
+        s.boost(1.0, 0.1, 0.25 * dt)
+        s.boost(1.0, 0.1, 0.25 * dt)
+    assert cm.rel(sp.md.Kinetic.Total, so.md.Kinetic.Total) < 1e-11
+    P = so.download("momenta")
+    for s in (sp, so):
+        s.upload("momenta", 0.5 * P)
+        s.boost(1.0, 0.0, 0.5 * dt)
+        s.boost(1.0, 0.0, 0.5 * dt)
+    assert cm.rel(sp.md.Kinetic.Total, so.md.Kinetic.Total) < 1e-11
+    assert sp.md.Builds == so.md.Builds
+    assert cm.rel_force_error(sp.download("momenta"), so.download("momenta")) < 1e-9
+    sp.finalize()
+    so.finalize()
+
+
 # ---- golden numbers that came from neither C++ restatement (tests/golden/numpy_models.py) -----------------------------
 import golden_cases as gc  # noqa: E402
 
