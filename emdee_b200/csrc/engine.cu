@@ -155,7 +155,7 @@ struct Engine::Impl {
   // environment switches, read once at construction (nothing on the per-step path calls getenv)
   bool env_debug = false, env_profile = false, env_no_migrate = false;
   // developer knobs (EmDeeX_tune; tools/force_lab.py): force-kernel variant and L1/shared carveout of the plain-LJ kernel
-  int tune_variant = 0, tune_carveout = -1, tune_build = 0;
+  int tune_variant = 0, tune_carveout = -1;
 
   // kick bookkeeping (Engine::boost): the sums of the NEXT identical kick predicted by the last one, and a kick that
   // compute_forces launches itself right behind the pair kernel (Engine::plan_kick)
@@ -885,7 +885,6 @@ void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
 void Engine::tune(const char* knob, int value) {
   if (std::strcmp(knob, "force_variant") == 0) d_->tune_variant = value;
   else if (std::strcmp(knob, "carveout") == 0) d_->tune_carveout = value;
-  else if (std::strcmp(knob, "build_variant") == 0) d_->tune_build = value;
   else if (std::strcmp(knob, "local_io") == 0) d_->local_io = value != 0;
   else fatal("tuning", "unknown knob");
 }
@@ -1328,8 +1327,7 @@ void Engine::rebuild_list(double Lbox) {
       // write-out was measured 6x slower at LJ-1M -- serial per-atom dependency chains at ~12 warps/SM --
       // and removed)
       const int tmr = timer_begin(1);
-      if (s.tune_build == 1) k_build_list_flat<<<nblocks(Next), TPB, 0, s.stream>>>(b);
-      else k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
       timer_end(tmr);
       stats_.launches += 1;
       stats_.build_launches += 1;

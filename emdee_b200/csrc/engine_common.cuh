@@ -140,6 +140,7 @@ __device__ __forceinline__ void grid_finish(const double (&mine)[WIDTH], double*
     double acc[WIDTH];
 #pragma unroll
     for (int q = 0; q < WIDTH; ++q) acc[q] = 0.0;
+#pragma unroll 4   // the loads of four blocks in flight; the additions keep their order
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += TPB) {
 #pragma unroll
       for (int q = 0; q < WIDTH; ++q) acc[q] += __ldcg(&partial[(size_t)b * WIDTH + q]);

@@ -306,137 +306,9 @@ __device__ __forceinline__ double strict_pbc_sq(double a, double b) {
   return __dmul_rn(d, d);
 }
 
-// EXPERIMENTAL form (EmDeeX_tune "build_variant" = 1; tools/force_lab.py times both on one resident system).
-// Two phases per thread, both written so that the lanes of a warp stay converged:
-//   1. the (at most 25) clipped x-runs of the entry are computed in lock step and their non-empty intervals (first
-//      entry, length) stored in shared memory (column per thread);
-//   2. ONE flat loop with a per-lane trip count = the entry's candidate total: an iteration steps to the next interval
-//      with predicated instructions when the current one is used up and tests one candidate, so a lane never waits for
-//      the longest run of its warp in each of the 25 rows. The common candidate test is branch-free; the exact re-test
-//      inside the FP32 uncertainty band, the type mask and the exclusion scan share ONE rarely taken branch.
-__global__ void __launch_bounds__(TPB) k_build_list_flat(const __grid_constant__ BuildArgs a) {
-  __shared__ int runFirst[25][TPB];
-  __shared__ unsigned char runLen[25][TPB];
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  int cnt = 0;
-  const int lane = threadIdx.x & 31;
-  if (e < a.Next && !a.sGhost[e]) {
-    int* out = a.nbr + ((size_t)(e >> 5) * a.cap) * TILE + lane;
-    const int atom_i = a.sMeta[e].x;
-    const int type_i = a.sType[e], body_i = a.sBody[e];
-    const double4 ri = a.sRs[e];
-    const float4 pf = a.sPosF[e];
-    const int x0 = a.exFirst[atom_i], x1 = a.exFirst[atom_i + 1];
-    const bool plain = a.all_interact && x0 >= x1;   // no type mask, no exclusions: the test below is the whole decision
-    const int cell = a.sCell[e];
-    const int Mx = a.g.Mx;
-    const int ez = cell / (Mx * Mx), ey = (cell - ez * Mx * Mx) / Mx, ex = cell - Mx * (ey + Mx * ez);
-    // geometry for run clipping, in scaled units: extended cell c spans [(c-2)/M, (c-1)/M)
-    const float w = 1.0f / (float)a.g.M;
-    const float slack = 1.0e-5f * w + 4.0e-7f;   // covers FP32 rounding of the clip arithmetic and positions
-    const float rc = (float)a.xRcs + slack;
-    const float rc2 = rc * rc;
-    int nruns = 0, total = 0;
-#pragma unroll 1
-    for (int dz = -2; dz <= 2; ++dz) {
-      const float zlo = (float)(ez + dz - 2 + a.g.z0) * w, zhi = zlo + w;   // local layer -> global coordinate
-      const float gz = fmaxf(0.0f, fmaxf(zlo - pf.z, pf.z - zhi) - slack);
-#pragma unroll
-      for (int dy = -2; dy <= 2; ++dy) {
-        const float ylo = (float)(ey + dy - 2) * w, yhi = ylo + w;
-        const float gy = fmaxf(0.0f, fmaxf(ylo - pf.y, pf.y - yhi) - slack);
-        const float rem = rc2 - gz * gz - gy * gy;
-        const float hx = sqrtf(fmaxf(rem, 0.0f)) + slack;
-        int cl = (int)floorf((pf.x - hx) * (float)a.g.M) + 2;   // `slack` (inside hx) exceeds the FP32 rounding here
-        int ch = (int)floorf((pf.x + hx) * (float)a.g.M) + 2;
-        cl = max(cl, ex - 2);
-        ch = min(ch, ex + 2);
-        const int row = Mx * ((ey + dy) + Mx * (ez + dz));
-        int f0 = 0, f1 = 0;
-        if (rem > 0.0f && cl <= ch) {
-          f0 = a.cellStart[row + cl];
-          f1 = a.cellStart[row + ch + 1];
-        }
-        while (f1 > f0) {   // (a run longer than 255 entries is split; five cells hold ~12)
-          const int len = min(f1 - f0, 255);
-          if (nruns < 25) {
-            runFirst[nruns][threadIdx.x] = f0;
-            runLen[nruns][threadIdx.x] = (unsigned char)len;
-            ++nruns;
-            total += len;
-            f0 += len;
-          } else {
-            f1 = f0;   // cannot happen with <= 25 rows unless a row was split; handled by the overflow path below
-            total = -1;
-          }
-        }
-      }
-    }
-    if (total >= 0) {
-      int r = 0, f = 0, left = 0;
-#pragma unroll 1
-      for (int it = 0; it < total; ++it) {
-        if (left == 0) {   // next interval: a thread reads only its own column (no barrier needed)
-          f = runFirst[r][threadIdx.x];
-          left = runLen[r][threadIdx.x];
-          ++r;
-        }
-        const float4 qf = __ldg(&a.sPosF[f]);
-        const float dxf = pf.x - qf.x, dyf = pf.y - qf.y, dzf = pf.z - qf.z;
-        const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
-        bool ok = (r2f <= a.r2_reject) & (f != e) & (__float_as_int(qf.w) != body_i);
-        if (ok && (r2f >= a.r2_accept || !plain)) {   // rare: decide exactly / apply the masks
-          if (r2f >= a.r2_accept) {
-            const double4 rj = a.sRs[f];
-            const double r2 = __dadd_rn(__dadd_rn(strict_pbc_sq(ri.x, rj.x), strict_pbc_sq(ri.y, rj.y)),
-                                        strict_pbc_sq(ri.z, rj.z));
-            ok = r2 < a.xRc2s;
-          }
-          if (ok && !a.all_interact) ok = a.interact[type_i * a.nt + a.sType[f]] != 0;
-          if (ok && x0 < x1) {
-            const int atom_j = a.sMeta[f].x;
-            for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
-          }
-        }
-        if (ok & (cnt < a.cap)) out[(size_t)cnt * TILE] = f;
-        cnt += ok ? 1 : 0;
-        ++f;
-        --left;
-      }
-    } else {   // overflow of the interval table (pathological cell occupancy): plain nested walk of the rows
-      for (int dz = -2; dz <= 2; ++dz)
-        for (int dy = -2; dy <= 2; ++dy) {
-          const int row = Mx * ((ey + dy) + Mx * (ez + dz));
-          const int f0 = a.cellStart[row + ex - 2], f1 = a.cellStart[row + ex + 3];
-          for (int f = f0; f < f1; ++f) {
-            if (f == e || a.sBody[f] == body_i) continue;
-            const double4 rj = a.sRs[f];
-            const double r2 = __dadd_rn(__dadd_rn(strict_pbc_sq(ri.x, rj.x), strict_pbc_sq(ri.y, rj.y)),
-                                        strict_pbc_sq(ri.z, rj.z));
-            bool ok = r2 < a.xRc2s;
-            if (ok && !a.all_interact) ok = a.interact[type_i * a.nt + a.sType[f]] != 0;
-            if (ok && x0 < x1) {
-              const int atom_j = a.sMeta[f].x;
-              for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
-            }
-            if (ok) {
-              if (cnt < a.cap) out[(size_t)cnt * TILE] = f;
-              ++cnt;
-            }
-          }
-        }
-    }
-    a.nbrCount[e] = min(cnt, a.cap);
-  }
-  int mx = cnt;
-  for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-  if (lane == 0 && mx > 0) {
-    atomicMax(&a.flags[0], mx);
-    if (mx > a.cap) a.flags[1] = 1;
-  }
-}
-
-// The default form: 25 nested x-runs per thread (0.658 ms at LJ-1M against 0.847 ms for the flat form above, round 2).
+// (A flat form -- runs pre-clipped in lock step into shared memory, then ONE predicated loop with a per-lane trip count
+// -- was measured in round 2: 3.4x fewer warp-iterations but ~40 SASS instructions per candidate against ~16 here, and
+// 29 % slower overall (0.847 vs 0.658 ms at LJ-1M, profiles/r2c_force_build_variants.txt); removed.)
 __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ BuildArgs a) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;

@@ -26,7 +26,6 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--ncell", type=int, default=63)
-    ap.add_argument("--build-variants", default="", help="comma list of list-build kernel forms to time (0 flat, 1 nested)")
     args = ap.parse_args()
     lib = api.load()
     R, P, L = bench.make_workload(args.ncell)
@@ -60,22 +59,6 @@ def main():
                   f"force launches/step {fl / args.steps:.2f} | builds {s.md.Builds - b0} | U {s.md.Energy.Potential:.6f}", flush=True)
     lib.EmDeeX_tune(s.md, b"force_variant", 0)
     lib.EmDeeX_tune(s.md, b"carveout", -1)
-    for bv in [int(x) for x in args.build_variants.split(",") if x != ""]:
-        lib.EmDeeX_tune(s.md, b"build_variant", bv)
-        for _ in range(10):
-            bench.md_step(s)
-        s.synchronize()
-        st0, b0 = s.stats(), s.md.Builds
-        t0 = time.perf_counter()
-        for _ in range(2 * args.steps):
-            bench.md_step(s)
-        s.synchronize()
-        dt = time.perf_counter() - t0
-        st1 = s.stats()
-        bl = st1.build_launches - st0.build_launches
-        print(f"build variant {bv} | build {(st1.build_ms - st0.build_ms) / max(bl, 1):.4f} ms x {bl} | step {1e3 * dt / (2 * args.steps):.4f} ms | "
-              f"builds {s.md.Builds - b0} | pairs {s.pair_count()} | U {s.md.Energy.Potential:.6f}", flush=True)
-    lib.EmDeeX_tune(s.md, b"build_variant", 0)
     # per-kernel device time of the default step (CUDA events from the library's ring), in-situ (warm caches)
     k0 = s.kernel_times()
     b0 = s.md.Builds
