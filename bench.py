@@ -537,8 +537,13 @@ def main():
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
         mark(ev0, dv0)
+        trace = [] if os.environ.get("EMDEE_BENCH_TRACE") else None   # development: host wall time of every step
         for _ in range(K):
+            if trace is not None:
+                tb, b_before = time.perf_counter(), s.md.Builds
             md_step(s)
+            if trace is not None:
+                trace.append((time.perf_counter() - tb, int(s.md.Builds - b_before)))
         mark(ev1, dv1)
         barrier()
         wall = time.perf_counter() - t0
@@ -553,6 +558,13 @@ def main():
     st1 = s.stats()
     kt1 = s.kernel_times()
     builds = s.md.Builds - builds0
+    if trace is not None:
+        ts = sorted(((w, k, b) for k, (w, b) in enumerate(trace)), reverse=True)[:12]
+        plain = sorted(w for w, b in trace if b == 0)
+        rb = sorted(w for w, b in trace if b != 0)
+        sys.stderr.write(f"[bench trace r{rank}] median step without rebuild {1e3 * plain[len(plain) // 2]:.3f} ms, with rebuild "
+                         f"{1e3 * rb[len(rb) // 2] if rb else 0:.3f} ms ({len(rb)} of {len(trace)}); slowest: " +
+                         ", ".join(f"#{k}:{1e3 * w:.2f}ms{'R' if b else ''}" for w, k, b in ts) + "\n")
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -499,7 +499,7 @@ void build_halo_lists(Engine::Impl& s) {
     // is the same from run to run. The NCCL-per-step mode needs a sender's list and the matching receiver's list in the
     // SAME order (no indices travel): there the four small halo lists are sorted by atom index afterwards.
     const int n = s.nCand;
-    s.haloFlags.ensure(5 * (size_t)n + 16);
+    s.haloFlags.ensure(5 * (size_t)n + 16, 1.25);   // (slack: the candidate count wobbles from rebuild to rebuild; no re-allocation in steady state)
     s.selCount.ensure(8);
     k_halo_flags_listed<<<std::max(1, nblocks(n)), TPB, 0, s.stream>>>(n, s.candList.p, s.grid, s.atomCell.p, s.haloFlags.p);
     size_t need = 0;
@@ -508,9 +508,9 @@ void build_halo_lists(Engine::Impl& s) {
       s.scanTmp.ensure(need);
       s.scanTmpBytes = need;
     }
-    s.ownedList.ensure((size_t)n + 16);
+    s.ownedList.ensure((size_t)n + 16, 1.25);
     for (int k = 0; k < 4; ++k) {
-      s.haloList[k].ensure((size_t)n + 16);
+      s.haloList[k].ensure((size_t)n + 16, 1.25);
       cub::DeviceSelect::Flagged(s.scanTmp.p, need, s.candList.p, s.haloFlags.p + (size_t)k * n, s.haloList[k].p, s.selCount.p + k, n,
                                  s.stream);
     }
@@ -524,7 +524,7 @@ void build_halo_lists(Engine::Impl& s) {
       s.haloCount[k] = h[k];
       s.haloBuf[k].ensure(3 * (size_t)h[k] + 8, 1.2);
       if (!s.peer_ok && h[k] > 1) {   // NCCL-per-step mode: ascending atom index on both sides of every message
-        s.sortTmp.ensure((size_t)h[k] + 16);
+        s.sortTmp.ensure((size_t)h[k] + 16, 1.25);
         size_t sb = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, sb, s.haloList[k].p, s.sortTmp.p, h[k], 0, 32, s.stream);
         if (sb > s.scanTmpBytes) {
@@ -639,7 +639,7 @@ void migrate(Engine::Impl& s, double Lbox) {
   // receives -- O(atoms of the slab), not O(N). The atoms to bin afterwards are collected in candList:
   //   [previously owned atoms, in ownedList's order | records from below | records from above (minus duplicates)]
   const int n = s.nOwn;
-  s.haloFlags.ensure(5 * (size_t)std::max(n, 1) + 16);
+  s.haloFlags.ensure(5 * (size_t)std::max(n, 1) + 16, 1.25);
   s.selCount.ensure(8);
   k_mig_flags_listed<<<std::max(1, nblocks(n)), TPB, 0, s.stream>>>(n, s.ownedList.p, Lbox, s.grid, s.R.p, s.haloFlags.p);
   size_t need = 0;
@@ -649,7 +649,7 @@ void migrate(Engine::Impl& s, double Lbox) {
     s.scanTmpBytes = need;
   }
   for (int k = 0; k < 2; ++k) {
-    s.migList[k].ensure((size_t)n + 16);
+    s.migList[k].ensure((size_t)n + 16, 1.25);
     cub::DeviceSelect::Flagged(s.scanTmp.p, need, s.ownedList.p, s.haloFlags.p + (size_t)k * n, s.migList[k].p, s.selCount.p + k, n,
                                s.stream);
   }
@@ -682,8 +682,8 @@ void migrate(Engine::Impl& s, double Lbox) {
     s.stamp.ensure(N);
     CUDA_CHECK(cudaMemsetAsync(s.stamp.p, 0, (size_t)N * sizeof(int), s.stream));
   }
-  s.candList.ensure((size_t)n + c[2] + c[3] + 16, 1.1);
-  s.recvIds.ensure((size_t)c[3] + 16, 1.1);
+  s.candList.ensure((size_t)n + c[2] + c[3] + 16, 1.25);
+  s.recvIds.ensure((size_t)c[3] + 16, 1.25);
   if (n > 0) {
     CUDA_CHECK(cudaMemcpyAsync(s.candList.p, s.ownedList.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s.stream));
     k_stamp_listed<<<nblocks(n), TPB, 0, s.stream>>>(n, s.ownedList.p, s.stamp.p, s.epoch);
@@ -699,7 +699,7 @@ void migrate(Engine::Impl& s, double Lbox) {
     } else {             // two ranks: both messages come from the same peer and may name the same atom
       unsigned char* fl = s.haloFlags.p;   // (the migration flags are no longer needed)
       if (s.haloFlags.n < (size_t)c[3] + 16) {
-        s.haloFlags.ensure((size_t)c[3] + 16);
+        s.haloFlags.ensure((size_t)c[3] + 16, 1.25);
         fl = s.haloFlags.p;
       }
       k_unpack7_listed<<<nblocks(c[3]), TPB, 0, s.stream>>>(c[3], s.migRecv[1].p, s.R.p, s.P.p, s.stamp.p, s.epoch, 1, s.recvIds.p, fl);
@@ -1372,7 +1372,9 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   double* Fl = s.F.p + (size_t)layer0 * 3 * N;
   const int Next = s.Next;
   const int tmr_r = timer_begin(TIMER_REFRESH);
-  k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
+  k_refresh_positions<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p,
+                                                           !speculative ? nullptr : (s.world > 1 ? s.scalars.p + CRIT_DIST : s.scalars.p + 8),
+                                                           s.skinSq);
   timer_end(tmr_r);
   ForceArgs a;
   a.Next = Next; a.cap = s.cap; a.nt = s.nt;
@@ -2000,7 +2002,7 @@ void Engine::update_list_stats(int layer0, double Lbox) {
   const double invL2 = 1.0 / (Lbox * Lbox);
   const double Rc2s = (s.layers[layer0].useInRc ? s.InRcSq : s.RcSq) * invL2;
   CUDA_CHECK(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned long long), s.stream));
-  k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
+  k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p, nullptr, 0.0);
   {
     k_count_interacting<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, s.cap, Rc2s, s.pos.p, s.nbr.p, s.nbrCount.p, s.counter.p);
   }
@@ -2044,7 +2046,7 @@ void Engine::rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_sca
   // the list is walked with the CURRENT coordinates (the reference rescales me%R on entry, EmDeeCode.f90:1324);
   // on several GPUs that includes the neighbors' halo atoms
   halo_exchange(s);
-  k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p);
+  k_refresh_positions<<<nblocks(s.Next), TPB, 0, s.stream>>>(s.Next, Lbox, s.R.p, s.q.p, s.sMeta.p, s.pos.p, nullptr, 0.0);
   const int use_smem = nbin * sizeof(unsigned int) <= 40 * 1024 ? 1 : 0;
   k_rdf<<<nblocks(s.Next), TPB, use_smem ? nbin * sizeof(unsigned int) : 0, s.stream>>>(
       s.Next, s.cap, s.nt, bins, nsym, Rc2_scaled, bins_by_Rc_scaled, s.pos.p, s.nbr.p, s.nbrCount.p, s.sType.p, sym.p,
