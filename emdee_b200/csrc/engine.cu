@@ -323,7 +323,7 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.tickets.ensure(4);
   CUDA_CHECK(cudaMemset(s.tickets.p, 0, 4 * sizeof(unsigned int)));
   s.chkPartial.ensure(nblocks(natoms));
-  s.partial.ensure((size_t)nblocks(natoms) * 6);
+  s.partial.ensure((size_t)nblocks(natoms) * FORCE_PARTIALS);
   CUDA_CHECK(cudaMallocHost(&s.h_scalars, 16 * sizeof(double)));
   CUDA_CHECK(cudaHostAlloc(&s.slots, NSLOTS * sizeof(HostSlot), cudaHostAllocMapped | cudaHostAllocPortable));
   std::memset(s.slots, 0, NSLOTS * sizeof(HostSlot));
@@ -898,7 +898,7 @@ namespace {
 template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, int UNROLL = 2, int THREADS = TPB, int MINBLOCKS = 1>
 void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem, cudaStream_t st) {
   const int grid = nblocks(a.Next, THREADS);
-  partial.ensure((size_t)grid * 5);
+  partial.ensure((size_t)grid * FORCE_PARTIALS);
   a.partial = partial.p;
   if (compute) k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, true, UNROLL, THREADS, MINBLOCKS><<<grid, THREADS, smem, st>>>(a);
   else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false, UNROLL, THREADS, MINBLOCKS><<<grid, THREADS, smem, st>>>(a);
@@ -928,7 +928,7 @@ void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
 #define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
       const int grid = nblocks(a.Next, TH);                                                                                \
-      s.partial.ensure((size_t)grid * 5);                                                                                  \
+      s.partial.ensure((size_t)grid * FORCE_PARTIALS);                                                                               \
       a.partial = s.partial.p;                                                                                             \
       auto kt = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, true, UN, TH, MB, LL, PL, PR, FO>;   \
       auto kf = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, false, UN, TH, MB, LL, PL, PR, FO>;  \
@@ -978,7 +978,7 @@ bool build_typed_table(const LayerTable& lt, std::vector<TypedEntry>& out, int& 
 template <int PM, int CK>
 void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
   const int grid = nblocks(a.Next, 256);
-  partial.ensure((size_t)grid * 5);
+  partial.ensure((size_t)grid * FORCE_PARTIALS);
   a.partial = partial.p;
   const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
   if (a.nt == 2) {
@@ -1388,6 +1388,14 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   a.coul = lt.coul;
   a.F = Fl; a.partial = s.partial.p; a.ticket = s.tickets.p; a.out = s.scalars.p;
   a.crit = !speculative ? nullptr : (s.world > 1 ? s.scalars.p + CRIT_DIST : s.scalars.p + 8);
+  // the planned kick (Engine::plan_kick) rides in the pair kernel's epilogue
+  a.kick = (s.kick_planned && s.kick_layer == layer0) ? 1 : 0;
+  a.kick_ke = (a.kick && s.kick_want_ke) ? 1 : 0;
+  a.kCP = s.kick_CP; a.kCF = s.kick_CF;
+  a.P = s.P.p; a.invMass = s.invMass.p;
+  a.kout = (s.world > 1) ? s.scalars.p + 5 : s.scalars.p + 10;   // several GPUs: contiguous with the force scalars for the reduction
+  a.khs = (s.world > 1 || !a.kick_ke) ? nullptr : s.slots + SLOT_KINETIC;
+  a.kseq = (a.khs != nullptr) ? s.next_seq(SLOT_KINETIC) : 0ull;
   a.skinSq = s.skinSq;
   a.hs = (s.world > 1) ? nullptr : s.slots + SLOT_FORCE;   // several GPUs: the scalars are all-reduced first
   a.seq = s.next_seq(SLOT_FORCE);
@@ -1423,11 +1431,11 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   s.last_force_timer = tmr;
   stats_.launches += 2;
   stats_.force_launches += 1;
-  if (s.kick_planned && s.kick_layer == layer0) launch_planned_kick(speculative);
 }
 
-// A kick that EmDee_boost is about to issue right after the force evaluation it triggers: compute_forces launches it
-// itself behind the pair kernel (one host wait, and on several GPUs one reduction, for both). Only where the kick can
+// A kick that EmDee_boost is about to issue right after the force evaluation it triggers: the pair kernel applies it in its
+// epilogue (the thread that finishes an atom's force updates its momentum; the kinetic sums join the kernel's reduction):
+// no kick kernel, one host wait, and on several GPUs one reduction, for both. Only where the kick can
 // follow the pair kernel directly: free atoms, no bonded / reciprocal-space terms added afterwards (abi.cpp decides).
 void Engine::plan_kick(int layer0, double CP, double CF, bool want_kinetic) {
   Impl& s = *d_;
@@ -1439,27 +1447,6 @@ void Engine::plan_kick(int layer0, double CP, double CF, bool want_kinetic) {
   s.kick_CP = CP;
   s.kick_CF = CF;
   s.kick_want_ke = want_kinetic;
-}
-
-// launches the planned kick behind the pair kernel of the same layer (`speculative`: it checks the criterion like the pair kernel)
-void Engine::launch_planned_kick(bool speculative) {
-  Impl& s = *d_;
-  const double* Fl = s.F.p + (size_t)s.kick_layer * 3 * s.N;
-  const int ke = s.kick_want_ke ? 1 : 0;
-  const int tmr = timer_begin(TIMER_BOOST);
-  if (s.world > 1) {
-    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.kick_CP, s.kick_CF, s.P.p, Fl,
-                                                                      s.invMass.p, ke, s.partial.p, s.tickets.p + 1, s.scalars.p + 5,
-                                                                      speculative ? s.scalars.p + CRIT_DIST : nullptr, s.skinSq);
-  } else {
-    const unsigned long long seq = ke ? s.next_seq(SLOT_KINETIC) : 0ull;
-    k_boost<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, s.kick_CP, s.kick_CF, s.P.p, Fl, s.invMass.p, nullptr, ke,
-                                                                 s.partial.p, s.tickets.p + 1, s.scalars.p + 10,
-                                                                 ke ? s.slots + SLOT_KINETIC : nullptr, seq,
-                                                                 speculative ? s.scalars.p + 8 : nullptr, s.skinSq);
-  }
-  timer_end(tmr);
-  stats_.launches += 1;
 }
 
 // the planned kick has run (its sums, if any, are in the kinetic slot): remember them for Engine::boost
