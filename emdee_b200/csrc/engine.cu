@@ -165,6 +165,12 @@ struct Engine::Impl {
   bool kick_planned = false, kick_done = false, kick_want_ke = false;
   double kick_CP = 0, kick_CF = 0, kick_ke[3] = {0, 0, 0};
   int kick_layer = -1;
+  // deferred kick (Engine::boost): a kick whose kinetic sums need no reduction (predicted by the previous kick, or not
+  // wanted) is not launched but applied by the drift kernel that follows (k_displace<true>); everything else that reads or
+  // writes momenta or forces executes it first (Engine::flush_kick)
+  bool defer_on = false, env_no_defer = false;
+  double defer_CP = 0, defer_CF = 0;
+  int defer_layer = -1;
 
   // host-visible results: pinned slots the last block of a reducing kernel writes; the host spins on the sequence number
   HostSlot* slots = nullptr;
@@ -323,13 +329,14 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.tickets.ensure(4);
   CUDA_CHECK(cudaMemset(s.tickets.p, 0, 4 * sizeof(unsigned int)));
   s.chkPartial.ensure(nblocks(natoms));
-  s.partial.ensure((size_t)nblocks(natoms) * FORCE_PARTIALS);
+  s.partial.ensure((size_t)nblocks(natoms) * 6);
   CUDA_CHECK(cudaMallocHost(&s.h_scalars, 16 * sizeof(double)));
   CUDA_CHECK(cudaHostAlloc(&s.slots, NSLOTS * sizeof(HostSlot), cudaHostAllocMapped | cudaHostAllocPortable));
   std::memset(s.slots, 0, NSLOTS * sizeof(HostSlot));
   s.env_debug = std::getenv("EMDEE_DEBUG") != nullptr;
   s.env_profile = std::getenv("EMDEE_PROFILE") != nullptr;
-  s.env_no_migrate = s.env_no_migrate;
+  s.env_no_migrate = std::getenv("EMDEE_NO_MIGRATE") != nullptr;
+  s.env_no_defer = std::getenv("EMDEE_NO_DEFER_KICK") != nullptr;
   CUDA_CHECK(cudaEventCreate(&s.ev0));
   CUDA_CHECK(cudaEventCreate(&s.ev1));
   CUDA_CHECK(cudaEventCreateWithFlags(&s.check_event, cudaEventDisableTiming));
@@ -465,6 +472,7 @@ void setup_peer_links(Engine::Impl& s) {
 }  // namespace
 
 void Engine::comm_init(int rank, int world, const void* unique_id) {
+  flush_kick();
   Impl& s = *d_;
   if (world <= 1) return;
   ncclUniqueId id;
@@ -813,6 +821,7 @@ double* mapped_alias(const double* host) {
 }  // namespace
 
 void Engine::upload_coordinates(const double* R) {
+  flush_kick();
   Impl& s = *d_;
   if (s.local_io && s.world > 1 && s.owned_valid && !s.all_known) {
     // local I/O: this rank reads only the atoms it owns and its halo atoms, straight from the caller's pinned array.
@@ -844,24 +853,29 @@ void Engine::upload_coordinates(const double* R) {
   }
 }
 void Engine::upload_momenta(const double* P) {
+  flush_kick();
   d_->ke_valid = false;
   CUDA_CHECK(cudaMemcpy(d_->P.p, P, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
   d_->p_partial = false;
 }
 void Engine::upload_forces(int layer0, const double* F) {
+  flush_kick();
   d_->ke_valid = false;
   CUDA_CHECK(cudaMemcpy(d_->F.p + (size_t)layer0 * 3 * d_->N, F, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyHostToDevice));
 }
 void Engine::download_coordinates(double* R) {
+  flush_kick();
   gather_full(*d_, d_->R.p);   // multi-GPU: collective, every rank must call
   d_->halo_fresh = true;
   CUDA_CHECK(cudaMemcpy(R, d_->R.p, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::download_momenta(double* P) {
+  flush_kick();
   gather_full(*d_, d_->P.p);
   CUDA_CHECK(cudaMemcpy(P, d_->P.p, 3 * (size_t)d_->N * sizeof(double), cudaMemcpyDeviceToHost));
 }
 void Engine::download_forces(int layer0, double* F) {
+  flush_kick();
   Impl& s = *d_;
   double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   if (s.local_io && s.world > 1 && s.owned_valid) {
@@ -881,7 +895,8 @@ void Engine::download_forces(int layer0, double* F) {
 }
 void Engine::io_bytes(long long& h2d, long long& d2h) { h2d = d_->io_h2d; d2h = d_->io_d2h; }
 int Engine::comm_mode() { return d_->world <= 1 ? 0 : (d_->peer_ok ? 2 : 1); }
-void Engine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
+void Engine::synchronize() {
+  flush_kick(); CUDA_CHECK(cudaStreamSynchronize(d_->stream)); }
 void Engine::tune(const char* knob, int value) {
   if (std::strcmp(knob, "force_variant") == 0) d_->tune_variant = value;
   else if (std::strcmp(knob, "carveout") == 0) d_->tune_carveout = value;
@@ -898,7 +913,7 @@ namespace {
 template <int PK, int PM, int CK, int CM, bool SINGLE, bool NEED_INVR, int UNROLL = 2, int THREADS = TPB, int MINBLOCKS = 1>
 void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem, cudaStream_t st) {
   const int grid = nblocks(a.Next, THREADS);
-  partial.ensure((size_t)grid * FORCE_PARTIALS);
+  partial.ensure((size_t)grid * 5);
   a.partial = partial.p;
   if (compute) k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, true, UNROLL, THREADS, MINBLOCKS><<<grid, THREADS, smem, st>>>(a);
   else k_pair_forces<PK, PM, CK, CM, SINGLE, NEED_INVR, false, UNROLL, THREADS, MINBLOCKS><<<grid, THREADS, smem, st>>>(a);
@@ -928,7 +943,7 @@ void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
 #define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
       const int grid = nblocks(a.Next, TH);                                                                                \
-      s.partial.ensure((size_t)grid * FORCE_PARTIALS);                                                                               \
+      s.partial.ensure((size_t)grid * 5);                                                                                  \
       a.partial = s.partial.p;                                                                                             \
       auto kt = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, true, UN, TH, MB, LL, PL, PR, FO>;   \
       auto kf = k_pair_forces<K_PAIR_LJ_CUT, M_NONE, K_COUL_NONE, M_NONE, true, false, false, UN, TH, MB, LL, PL, PR, FO>;  \
@@ -978,7 +993,7 @@ bool build_typed_table(const LayerTable& lt, std::vector<TypedEntry>& out, int& 
 template <int PM, int CK>
 void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
   const int grid = nblocks(a.Next, 256);
-  partial.ensure((size_t)grid * FORCE_PARTIALS);
+  partial.ensure((size_t)grid * 5);
   a.partial = partial.p;
   const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
   if (a.nt == 2) {
@@ -1092,6 +1107,7 @@ void Engine::kernel_times(double* ms8, long long* n8) {
 }
 
 bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars& out, double& neighbor_seconds) {
+  flush_kick();
   Impl& s = *d_;
   const int N = s.N;
   const LayerTable& lt = s.layers[layer0];
@@ -1388,14 +1404,6 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   a.coul = lt.coul;
   a.F = Fl; a.partial = s.partial.p; a.ticket = s.tickets.p; a.out = s.scalars.p;
   a.crit = !speculative ? nullptr : (s.world > 1 ? s.scalars.p + CRIT_DIST : s.scalars.p + 8);
-  // the planned kick (Engine::plan_kick) rides in the pair kernel's epilogue
-  a.kick = (s.kick_planned && s.kick_layer == layer0) ? 1 : 0;
-  a.kick_ke = (a.kick && s.kick_want_ke) ? 1 : 0;
-  a.kCP = s.kick_CP; a.kCF = s.kick_CF;
-  a.P = s.P.p; a.invMass = s.invMass.p;
-  a.kout = (s.world > 1) ? s.scalars.p + 5 : s.scalars.p + 10;   // several GPUs: contiguous with the force scalars for the reduction
-  a.khs = (s.world > 1 || !a.kick_ke) ? nullptr : s.slots + SLOT_KINETIC;
-  a.kseq = (a.khs != nullptr) ? s.next_seq(SLOT_KINETIC) : 0ull;
   a.skinSq = s.skinSq;
   a.hs = (s.world > 1) ? nullptr : s.slots + SLOT_FORCE;   // several GPUs: the scalars are all-reduced first
   a.seq = s.next_seq(SLOT_FORCE);
@@ -1431,11 +1439,11 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   s.last_force_timer = tmr;
   stats_.launches += 2;
   stats_.force_launches += 1;
+  if (s.kick_planned && s.kick_layer == layer0) launch_planned_kick(speculative);
 }
 
-// A kick that EmDee_boost is about to issue right after the force evaluation it triggers: the pair kernel applies it in its
-// epilogue (the thread that finishes an atom's force updates its momentum; the kinetic sums join the kernel's reduction):
-// no kick kernel, one host wait, and on several GPUs one reduction, for both. Only where the kick can
+// A kick that EmDee_boost is about to issue right after the force evaluation it triggers: compute_forces launches it
+// itself behind the pair kernel (one host wait, and on several GPUs one reduction, for both). Only where the kick can
 // follow the pair kernel directly: free atoms, no bonded / reciprocal-space terms added afterwards (abi.cpp decides).
 void Engine::plan_kick(int layer0, double CP, double CF, bool want_kinetic) {
   Impl& s = *d_;
@@ -1447,6 +1455,27 @@ void Engine::plan_kick(int layer0, double CP, double CF, bool want_kinetic) {
   s.kick_CP = CP;
   s.kick_CF = CF;
   s.kick_want_ke = want_kinetic;
+}
+
+// launches the planned kick behind the pair kernel of the same layer (`speculative`: it checks the criterion like the pair kernel)
+void Engine::launch_planned_kick(bool speculative) {
+  Impl& s = *d_;
+  const double* Fl = s.F.p + (size_t)s.kick_layer * 3 * s.N;
+  const int ke = s.kick_want_ke ? 1 : 0;
+  const int tmr = timer_begin(TIMER_BOOST);
+  if (s.world > 1) {
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.kick_CP, s.kick_CF, s.P.p, Fl,
+                                                                      s.invMass.p, ke, s.partial.p, s.tickets.p + 1, s.scalars.p + 5,
+                                                                      speculative ? s.scalars.p + CRIT_DIST : nullptr, s.skinSq);
+  } else {
+    const unsigned long long seq = ke ? s.next_seq(SLOT_KINETIC) : 0ull;
+    k_boost<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, s.kick_CP, s.kick_CF, s.P.p, Fl, s.invMass.p, nullptr, ke,
+                                                                 s.partial.p, s.tickets.p + 1, s.scalars.p + 10,
+                                                                 ke ? s.slots + SLOT_KINETIC : nullptr, seq,
+                                                                 speculative ? s.scalars.p + 8 : nullptr, s.skinSq);
+  }
+  timer_end(tmr);
+  stats_.launches += 1;
 }
 
 // the planned kick has run (its sums, if any, are in the kinetic slot): remember them for Engine::boost
@@ -1468,6 +1497,26 @@ void Engine::collect_planned_kick() {
   s.kick_done = true;
 }
 
+// executes a deferred kick now (its kinetic sums were already answered): every entry point that reads or writes momenta
+// or forces, other than the drift that absorbs it, starts with this
+void Engine::flush_kick() {
+  Impl& s = *d_;
+  if (!s.defer_on) return;
+  s.defer_on = false;
+  const double* Fl = s.F.p + (size_t)s.defer_layer * 3 * s.N;
+  const int tmr = timer_begin(TIMER_BOOST);
+  if (s.world > 1 && s.owned_valid)
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.defer_CP, s.defer_CF, s.P.p, Fl,
+                                                                      s.invMass.p, 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10,
+                                                                      nullptr, 0.0);
+  else
+    k_boost<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, s.defer_CP, s.defer_CF, s.P.p, Fl, s.invMass.p, nullptr, 0,
+                                                                 s.partial.p, s.tickets.p + 1, s.scalars.p + 10, nullptr, 0ull,
+                                                                 nullptr, 0.0);
+  timer_end(tmr);
+  stats_.launches += 1;
+}
+
 void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke) {
   Impl& s = *d_;
   const double tp0 = wall_now();
@@ -1482,12 +1531,25 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
     fatal("momentum update", "internal: a planned kick does not match the kick requested");
   }
   s.kick_planned = false;
+  flush_kick();
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   const bool dist = s.world > 1 && s.owned_valid;
   // the previous kick predicted this one's sums (same coefficients, same forces, momenta untouched in between)
   const bool predicted = want_kinetic && s.ke_valid && s.ke_layer == layer0 && s.ke_CP == CP && s.ke_CF == CF && !s.exposed;
   const int want = (want_kinetic && !predicted) ? 1 : 0;
   s.ke_valid = false;
+  if (!want && !s.exposed && !s.foreign_R && !s.env_no_defer && (s.world == 1 || dist)) {
+    // nothing to reduce: the drift that follows applies this kick (k_displace<true>); flush_kick otherwise
+    s.defer_on = true;
+    s.defer_layer = layer0;
+    s.defer_CP = CP;
+    s.defer_CF = CF;
+    if (predicted)
+      for (int x = 0; x < 3; ++x) ke.twoKE[x] = s.ke_next[x];
+    s.t_boost += wall_now() - tp0;
+    s.n_boost += 1;
+    return;
+  }
   const int tmr = timer_begin(TIMER_BOOST);
   if (dist) {
     // several GPUs: the kick runs over the compact list of owned atoms (work ~ atoms of this rank, not N)
@@ -1536,12 +1598,20 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
 void Engine::displace(double CR, double CP) {
   Impl& s = *d_;
   const double tp0 = wall_now();
+  const bool kick = s.defer_on;   // the deferred kick rides in the drift kernel
+  const double* Fk = kick ? s.F.p + (size_t)s.defer_layer * 3 * s.N : nullptr;
+  s.defer_on = false;
   if (s.world > 1 && s.owned_valid) {
     // owned atoms only (compact list); phase 1 of the rebuild criterion on the new coordinates lands in miResult[world]
     const int tmr = timer_begin(TIMER_DISPLACE);
-    k_displace_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
-                                                                         s.R0.p, s.miPartial.p, s.tickets.p + 2,
-                                                                         s.miResult.p + s.world);
+    if (kick)
+      k_displace_owned<true><<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
+                                                                                 s.R0.p, s.miPartial.p, s.tickets.p + 2,
+                                                                                 s.miResult.p + s.world, s.defer_CP, s.defer_CF, Fk);
+    else
+      k_displace_owned<false><<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
+                                                                                  s.R0.p, s.miPartial.p, s.tickets.p + 2,
+                                                                                  s.miResult.p + s.world, 0.0, 0.0, nullptr);
     timer_end(tmr);
     stats_.launches += 1;
     s.mi_fresh = true;
@@ -1551,9 +1621,19 @@ void Engine::displace(double CR, double CP) {
   } else {
     // the rebuild criterion of the new coordinates lands in scalars[8] on the device; compute_forces launches the pair
     // kernel speculatively against it instead of waiting for it here
+    if (kick && s.world > 1) {   // several GPUs before the first distributed rebuild: the kick stays a kernel of its own
+      s.defer_on = true;
+      flush_kick();
+    }
     const int tmr = timer_begin(TIMER_DISPLACE);
-    k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p, s.chkPartial.p,
-                                                   s.tickets.p + 2, s.scalars.p + 8);
+    if (kick && s.world == 1)
+      k_displace<true><<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p,
+                                                                             s.chkPartial.p, s.tickets.p + 2, s.scalars.p + 8,
+                                                                             s.defer_CP, s.defer_CF, Fk);
+    else
+      k_displace<false><<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p,
+                                                                              s.chkPartial.p, s.tickets.p + 2, s.scalars.p + 8,
+                                                                              0.0, 0.0, nullptr);
     timer_end(tmr);
     stats_.launches += 1;
     s.check_cached = true;
@@ -1606,6 +1686,7 @@ void Engine::set_bodies(const std::vector<int>& first, const std::vector<int>& a
 }
 
 void Engine::update_body_frames(double Lbox) {
+  flush_kick();
   Impl& s = *d_;
   if (s.nbodies == 0) return;
   if (!s.has_R) fatal("rigid-body update", "coordinates have not been uploaded");
@@ -1622,6 +1703,7 @@ void Engine::update_body_frames(double Lbox) {
 }
 
 void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool rotate, bool want_kinetic, KineticAll& ke) {
+  flush_kick();
   Impl& s = *d_;
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   const bool bodies = s.nbodies != 0;
@@ -1675,14 +1757,15 @@ void Engine::boost_all(int layer0, double CP, double CF, bool translate, bool ro
 }
 
 void Engine::move_all(double CR, double CP, double dt, bool translate, bool rotate, int mode) {
+  flush_kick();
   Impl& s = *d_;
   const bool bodies = s.nbodies != 0;
   const bool dist = s.world > 1 && s.owned_valid;
   if (translate && s.nitems < s.N) {
     // the fused rebuild criterion is not used here: body members move in k_body_move below
     const unsigned char* mask = !bodies ? (dist ? s.owned.p : nullptr) : (dist ? s.ownedFree.p : s.freeMask.p);
-    k_displace<<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, mask, s.R0.p, nullptr,
-                                                                      s.tickets.p + 2, s.scalars.p + 8);
+    k_displace<false><<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, mask, s.R0.p, nullptr,
+                                                                            s.tickets.p + 2, s.scalars.p + 8, 0.0, 0.0, nullptr);
     stats_.launches += 1;
   }
   if (bodies) {   // several GPUs: every rank moves every body (replicated state), so member coordinates stay current everywhere
@@ -1729,6 +1812,7 @@ void Engine::set_bonded(const std::vector<BondedTerm>& terms) {
 }
 
 void Engine::add_bonded(int layer0, double Lbox, bool bonded, bool kspace, BondedScalars& out) {
+  flush_kick();
   Impl& s = *d_;
   out = BondedScalars();
   if (s.nterms == 0) return;
@@ -1777,6 +1861,7 @@ void Engine::set_ewald(const EwaldSetup& e) {
 }
 
 void Engine::add_ewald(int layer0, double Lbox, double& Elong, double& Wbody) {
+  flush_kick();
   Impl& s = *d_;
   Elong = Wbody = 0.0;
   if (!s.ewald_on || s.ew_nvecs == 0) return;
@@ -1813,6 +1898,7 @@ void Engine::add_ewald(int layer0, double Lbox, double& Elong, double& Wbody) {
 // synchronisation), and -- as with the reference -- writing coordinates through the pointer does not invalidate
 // anything by itself; the next EmDee_compute_forces re-evaluates the rebuild criterion on whatever it finds.
 void* Engine::expose(int what, int layer0) {
+  flush_kick();
   Impl& s = *d_;
   if (s.world > 1) fatal("memory address retrieving", "not available on several GPUs (every rank holds a slab)");
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -1827,6 +1913,8 @@ void* Engine::expose(int what, int layer0) {
 
 // `this` gives up its own R, P and rigid-body state for `keep`'s (src/EmDeeCode.f90:259-263)
 void Engine::share_phase_space(Engine& keep) {
+  flush_kick();
+  keep.flush_kick();
   Impl& s = *d_;
   Impl& k = *keep.d_;
   if (s.world > 1 || k.world > 1) fatal("phase space sharing", "not available on several GPUs");
@@ -1845,6 +1933,7 @@ void Engine::share_phase_space(Engine& keep) {
 }
 
 void Engine::refresh_member_momenta() {
+  flush_kick();
   Impl& s = *d_;
   if (s.nbodies == 0) return;
   k_body_momenta<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s), s.delta.p, s.P.p);
@@ -1853,6 +1942,7 @@ void Engine::refresh_member_momenta() {
 
 // kinetic sums of the momenta just uploaded: free atoms (k_free_kinetic) + bodies (k_body_take_momenta = assign_momenta)
 void Engine::take_member_momenta(KineticAll& ke) {
+  flush_kick();
   Impl& s = *d_;
   for (int x = 0; x < 3; ++x) ke.twoKEt[x] = ke.twoKEr[x] = 0.0;
   if (s.nitems < s.N) {
@@ -1896,6 +1986,7 @@ int body_item_offset(int what, int& width) {
 
 // out is body-major (width, nbodies) in the reference's Fortran sense: out[b*width + c]
 void Engine::download_body(int what, double* out) {
+  flush_kick();
   Impl& s = *d_;
   const size_t nb = (size_t)s.nbodies;
   if (nb == 0) return;
@@ -1909,6 +2000,7 @@ void Engine::download_body(int what, double* out) {
 }
 
 void Engine::upload_body(int what, const double* in) {
+  flush_kick();
   Impl& s = *d_;
   const size_t nb = (size_t)s.nbodies;
   if (nb == 0) return;
@@ -1921,6 +2013,7 @@ void Engine::upload_body(int what, const double* in) {
 }
 
 void Engine::derive_quaternion_momenta() {
+  flush_kick();
   Impl& s = *d_;
   if (s.nbodies == 0) return;
   k_body_set_omega<<<nblocks(s.nbodies), TPB, 0, s.stream>>>(body_view(s));
@@ -1928,6 +2021,7 @@ void Engine::derive_quaternion_momenta() {
 }
 
 void Engine::shadow_pre(int layer0, double dt, int mode) {
+  flush_kick();
   Impl& s = *d_;
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   const bool bodies = s.nbodies != 0;
@@ -1951,6 +2045,7 @@ void Engine::shadow_pre(int layer0, double dt, int mode) {
 }
 
 void Engine::shadow_post(int layer0, double dt, int mode, double& Us, double& Ks_t, double& Ks_r) {
+  flush_kick();
   Impl& s = *d_;
   const double* Fl = s.F.p + (size_t)layer0 * 3 * s.N;
   const bool bodies = s.nbodies != 0;

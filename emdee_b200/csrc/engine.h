@@ -96,8 +96,8 @@ class Engine {
 
   // ---- device-resident dynamics for free atoms (reference boost / move / kinetic_energies) --
   void boost(int layer0, double CP, double CF, bool want_kinetic, KineticScalars& ke);
-  // announce the kick that follows the next compute_forces of this layer (EmDee_boost with stale forces): the pair kernel
-  // then applies it in its epilogue and the kinetic sums share its reduction and host wait; boost() afterwards just returns them
+  // announce the kick that follows the next compute_forces of this layer (EmDee_boost with stale forces): it is then
+  // launched behind the pair kernel and shares its host wait / reduction; boost() afterwards just returns its sums
   void plan_kick(int layer0, double CP, double CF, bool want_kinetic);
   void displace(double CR, double CP);
 
@@ -157,6 +157,8 @@ class Engine {
  private:
   void rebuild_list(double Lbox);
   void launch_pair_kernel(int layer0, bool compute, double Lbox, bool speculative);
+  void launch_planned_kick(bool speculative);
+  void flush_kick();   // executes a deferred kick (see boost)
   void collect_planned_kick();
   int timer_begin(int kind);
   void timer_end(int idx);

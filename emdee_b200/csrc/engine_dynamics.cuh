@@ -119,11 +119,16 @@ __global__ void __launch_bounds__(TPB) k_boost(int N, double CP, double CF, doub
 // R = CR*R + CP*P/m, fused with the rebuild criterion on the NEW coordinates (|R - R0|^2 ordered scan).
 // Multi-GPU: only owned atoms move here and the criterion is evaluated by the distributed kernels below
 // (partial == nullptr skips the fused scan).
+// KICK: the kick EmDee_boost issued just before this drift and whose kinetic sums were already known (Engine::boost,
+// "deferred kick") is applied here first, P = kCP*P + kCF*F with the very operations of k_boost, so the momenta make one
+// trip through memory per half step instead of two.
+template <bool KICK>
 __global__ void __launch_bounds__(TPB) k_displace(int N, double CR, double CP, double* __restrict__ R,
-                                                  const double* __restrict__ P, const double* __restrict__ invMass,
+                                                  double* __restrict__ P, const double* __restrict__ invMass,
                                                   const unsigned char* __restrict__ owned,
                                                   const double* __restrict__ R0, MaxNext* __restrict__ partial,
-                                                  unsigned int* __restrict__ ticket, double* __restrict__ result) {
+                                                  unsigned int* __restrict__ ticket, double* __restrict__ result,
+                                                  double kCP, double kCF, const double* __restrict__ F) {
   const long long a0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * APT;
   const int n = (a0 >= N) ? 0 : (int)min((long long)APT, N - a0);
   MaxNext s = mn_identity();
@@ -139,6 +144,18 @@ __global__ void __launch_bounds__(TPB) k_displace(int N, double CR, double CP, d
       double r[3 * APT], p[3 * APT];
       load12(R, a0, n, r);
       load12(P, a0, n, p);
+      if (KICK) {
+        double f[3 * APT];
+        load12(F, a0, n, f);
+#pragma unroll
+        for (int j = 0; j < APT; ++j)
+          if (own[j]) {
+#pragma unroll
+            for (int x = 0; x < 3; ++x) p[3 * j + x] = __dadd_rn(__dmul_rn(kCP, p[3 * j + x]), __dmul_rn(kCF, f[3 * j + x]));
+          }
+        if (owned == nullptr) store12(P, a0, n, p);
+        else store12_own(P, a0, own, p);
+      }
 #pragma unroll
       for (int j = 0; j < APT; ++j) {
         if (own[j]) {

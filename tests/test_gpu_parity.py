@@ -434,6 +434,63 @@ def test_kicks_with_energies_every_step():
     so.finalize()
 
 
+def test_deferred_kick_reaches_every_reader():
+    """A kick whose kinetic sums need no reduction (predicted by the previous kick, or Options.Compute off) is not launched:
+    the drift that follows applies it (Engine::boost / k_displace<true>), and every other call that reads or writes momenta
+    or forces must execute it first (Engine::flush_kick). Same numbers as the oracle whatever comes between kick and drift."""
+    def lj(lib, e, s):
+        return lib.EmDee_pair_lj_cut(e, s)
+    sp, c = cm.lj_sample_system(cm.product(), lj)
+    so, _ = cm.lj_sample_system(cm.oracle(), lj)
+    dt = c["Dt"]
+    for s in (sp, so):
+        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
+        s.md.Options.Compute = True
+
+    def step(s):
+        s.boost(1.0, 0.0, 0.5 * dt)
+        s.displace(1.0, 0.0, dt)
+        s.boost(1.0, 0.0, 0.5 * dt)
+
+    def same():
+        assert cm.rel(sp.md.Kinetic.Total, so.md.Kinetic.Total) < 1e-11
+        assert cm.rel_force_error(sp.download("momenta"), so.download("momenta")) < 1e-10
+        assert np.abs(sp.download("coordinates") - so.download("coordinates")).max() < 1e-10
+
+    for s in (sp, so):
+        step(s)
+        s.boost(1.0, 0.0, 0.5 * dt)        # predicted -> deferred in the product
+    same()                                  # the momentum download comes before any drift
+    for s in (sp, so):
+        s.displace(1.0, 0.0, dt)
+        s.boost(1.0, 0.0, 0.5 * dt)
+        s.boost(1.0, 0.0, 0.5 * dt)        # deferred ...
+        s.boost(1.0, 0.2, 0.3 * dt)        # ... then a kick with other coefficients instead of a drift
+    same()
+    for s in (sp, so):
+        step(s)
+        s.boost(1.0, 0.0, 0.5 * dt)        # deferred ...
+    P = so.download("momenta")
+    for s in (sp, so):
+        s.upload("momenta", 0.9 * P)       # ... then overwritten by an upload
+        step(s)
+    same()
+    for s in (sp, so):                      # sums not wanted: every kick with up-to-date forces is deferred
+        s.md.Options.Compute = False
+        for _ in range(8):
+            step(s)
+        s.boost(1.0, 0.0, 0.5 * dt)        # deferred, then forces of this layer are recomputed with energies
+        s.md.Options.Compute = True
+        s.compute_forces()
+        s.displace(1.0, 0.0, dt)
+        s.boost(1.0, 0.0, 0.5 * dt)
+    same()
+    assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-10
+    assert sp.md.Builds == so.md.Builds
+    sp.finalize()
+    so.finalize()
+
+
 # ---- golden numbers that came from neither C++ restatement (tests/golden/numpy_models.py) -----------------------------
 import golden_cases as gc  # noqa: E402
 

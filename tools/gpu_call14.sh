@@ -22,6 +22,7 @@ timeout 300 ncu --set full --clock-control none -k regex:k_pair_forces_typed -s 
 python tools/ncu_summary.py gpurun_out/r2e_typed.ncu-rep > gpurun_out/r2e_typed.txt 2>&1; cat gpurun_out/r2e_typed.txt
 ncu -i gpurun_out/r2e_typed.ncu-rep --page details 2>/dev/null | grep -E "Achieved Occupancy|Theoretical Occ|Executed Ipc|No Eligible|Issued Warp|FP64|Pipe" | head -20
 rm -f gpurun_out/r2e_typed.ncu-rep
+timeout 200 python -m pytest tests -m gpu -x -q > gpurun_out/tests14.txt 2>&1; tail -3 gpurun_out/tests14.txt
 timeout 300 python bench.py --steps 200 --warmup 30 > gpurun_out/bench14_1gpu.json 2> gpurun_out/bench14_1gpu.err
 python - <<'PY'
 import json
