@@ -165,6 +165,11 @@ struct Engine::Impl {
   bool kick_planned = false, kick_done = false, kick_want_ke = false;
   double kick_CP = 0, kick_CF = 0, kick_ke[3] = {0, 0, 0};
   int kick_layer = -1;
+  // duo path (k_pair_forces_duo): union rows of the entry pairs (2d, 2d+1), merged from the list once per rebuild
+  int cap2 = 0;
+  DBuf<unsigned int> duoNbr;
+  DBuf<int> duoCount;
+  long long list_epoch = 0, duo_epoch = -1;   // list_epoch advances at every rebuild; duo rows belong to duo_epoch
   // deferred kick (Engine::boost): a kick whose kinetic sums need no reduction (predicted by the previous kick, or not
   // wanted) is not launched but applied by the drift kernel that follows (k_displace<true>); everything else that reads or
   // writes momenta or forces executes it first (Engine::flush_kick)
@@ -337,6 +342,7 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.env_profile = std::getenv("EMDEE_PROFILE") != nullptr;
   s.env_no_migrate = std::getenv("EMDEE_NO_MIGRATE") != nullptr;
   s.env_no_defer = std::getenv("EMDEE_NO_DEFER_KICK") != nullptr;
+  if (const char* fv = std::getenv("EMDEE_FORCE_VARIANT")) s.tune_variant = std::atoi(fv);   // developer knob (profiling a lab variant)
   CUDA_CHECK(cudaEventCreate(&s.ev0));
   CUDA_CHECK(cudaEventCreate(&s.ev1));
   CUDA_CHECK(cudaEventCreateWithFlags(&s.check_event, cudaEventDisableTiming));
@@ -936,9 +942,57 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
   X(10, 6, 128, 8, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
   X(11, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)
 
+// duo variants of the plain-LJ kernel: (unroll, threads, min blocks)
+#define EMDEE_DUO_VARIANTS(X) \
+  X(20, 4, 256, 2)            \
+  X(21, 3, 256, 2)            \
+  X(22, 4, 128, 4)            \
+  X(23, 2, 256, 3)            \
+  X(24, 6, 256, 2)            \
+  X(25, 4, 512, 1)
+
+void launch_lj_duo(Engine::Impl& s, ForceArgs& a, bool compute, int v) {
+  const int nduo = (a.Next + 1) / 2;
+  if (s.duo_epoch != s.list_epoch) {   // first launch on this list: merge the rows of consecutive entries
+    const long long dtiles = ((long long)nduo + TILE - 1) / TILE;
+    if (s.cap2 == 0) s.cap2 = (int)(1.45 * s.cap) + 8;
+    s.duoCount.ensure(nduo, 1.1);
+    for (;;) {
+      s.duoNbr.ensure((size_t)dtiles * s.cap2 * TILE, 1.1);
+      CUDA_CHECK(cudaMemsetAsync(s.flags.p + 2, 0, 2 * sizeof(int), s.stream));
+      k_merge_duos<<<nblocks(nduo), TPB, 0, s.stream>>>(a.Next, s.cap, s.cap2, s.nbr.p, s.nbrCount.p, s.duoNbr.p, s.duoCount.p,
+                                                        s.flags.p);
+      int hf[2];
+      CUDA_CHECK(cudaMemcpyAsync(hf, s.flags.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+      CUDA_CHECK(cudaStreamSynchronize(s.stream));
+      if (!hf[1]) break;
+      s.cap2 = (int)(hf[0] * 1.1) + 8;   // overflow: regrow to the observed maximum and redo
+    }
+    s.duo_epoch = s.list_epoch;
+  }
+  switch (v) {
+#define EMDEE_DUO_CASE(ID, UN, TH, MB)                                                                              \
+    case ID: {                                                                                                     \
+      const int grid = nblocks(nduo, TH);                                                                          \
+      s.partial.ensure((size_t)grid * 5);                                                                          \
+      a.partial = s.partial.p;                                                                                     \
+      if (compute) k_pair_forces_duo<true, UN, TH, MB><<<grid, TH, 0, s.stream>>>(a, s.cap2, s.duoNbr.p, s.duoCount.p);  \
+      else k_pair_forces_duo<false, UN, TH, MB><<<grid, TH, 0, s.stream>>>(a, s.cap2, s.duoNbr.p, s.duoCount.p);         \
+      break;                                                                                                       \
+    }
+    EMDEE_DUO_VARIANTS(EMDEE_DUO_CASE)
+#undef EMDEE_DUO_CASE
+    default: fatal("force kernel selection", "unknown force_variant");
+  }
+}
+
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
   const int v = s.tune_variant;
+  if (v >= 20) {
+    launch_lj_duo(s, a, compute, v);
+    return;
+  }
   switch (v) {
 #define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
@@ -991,14 +1045,20 @@ bool build_typed_table(const LayerTable& lt, std::vector<TypedEntry>& out, int& 
 }
 
 template <int PM, int CK>
-void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
-  const int grid = nblocks(a.Next, 256);
+void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st, int shape) {
+  const int threads = shape == 1 ? 128 : 256;   // shape 1 (EmDeeX_tune "force_variant"): 128 x 4 instead of 256 x 2
+  const int grid = nblocks(a.Next, threads);
   partial.ensure((size_t)grid * 5);
   a.partial = partial.p;
   const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
   if (a.nt == 2) {
-    if (compute) k_pair_forces_typed<PM, CK, true, true><<<grid, 256, 0, st>>>(a, ttab);
-    else k_pair_forces_typed<PM, CK, false, true><<<grid, 256, 0, st>>>(a, ttab);
+    if (shape == 1) {
+      if (compute) k_pair_forces_typed<PM, CK, true, true, 128, 4><<<grid, 128, 0, st>>>(a, ttab);
+      else k_pair_forces_typed<PM, CK, false, true, 128, 4><<<grid, 128, 0, st>>>(a, ttab);
+    } else {
+      if (compute) k_pair_forces_typed<PM, CK, true, true><<<grid, 256, 0, st>>>(a, ttab);
+      else k_pair_forces_typed<PM, CK, false, true><<<grid, 256, 0, st>>>(a, ttab);
+    }
   } else {
     if (compute) k_pair_forces_typed<PM, CK, true, false><<<grid, 256, smem, st>>>(a, ttab);
     else k_pair_forces_typed<PM, CK, false, false><<<grid, 256, smem, st>>>(a, ttab);
@@ -1006,15 +1066,15 @@ void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, b
 }
 
 template <int PM>
-bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
+bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st, int shape) {
   using namespace nb;
   switch (ck) {
-    case K_COUL_NONE: launch_typed<PM, K_COUL_NONE>(a, partial, ttab, compute, st); return true;
-    case K_COUL_CUT: launch_typed<PM, K_COUL_CUT>(a, partial, ttab, compute, st); return true;
-    case K_COUL_SF: launch_typed<PM, K_COUL_SF>(a, partial, ttab, compute, st); return true;
-    case K_COUL_DAMPED: launch_typed<PM, K_COUL_DAMPED>(a, partial, ttab, compute, st); return true;
-    case K_COUL_DAMPED_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SMOOTHED>(a, partial, ttab, compute, st); return true;
-    case K_COUL_DAMPED_SQUARE_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SQUARE_SMOOTHED>(a, partial, ttab, compute, st); return true;
+    case K_COUL_NONE: launch_typed<PM, K_COUL_NONE>(a, partial, ttab, compute, st, shape); return true;
+    case K_COUL_CUT: launch_typed<PM, K_COUL_CUT>(a, partial, ttab, compute, st, shape); return true;
+    case K_COUL_SF: launch_typed<PM, K_COUL_SF>(a, partial, ttab, compute, st, shape); return true;
+    case K_COUL_DAMPED: launch_typed<PM, K_COUL_DAMPED>(a, partial, ttab, compute, st, shape); return true;
+    case K_COUL_DAMPED_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SMOOTHED>(a, partial, ttab, compute, st, shape); return true;
+    case K_COUL_DAMPED_SQUARE_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SQUARE_SMOOTHED>(a, partial, ttab, compute, st, shape); return true;
     default: return false;
   }
 }
@@ -1038,8 +1098,8 @@ bool try_typed_path(Engine::Impl& s, int layer0, const LayerTable& lt, int ck, F
     }
   }
   if (s.typedState[layer0] != 1) return false;
-  return s.typedPM[layer0] == nb::M_NONE ? launch_typed_ck<nb::M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream)
-                                         : launch_typed_ck<nb::M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream);
+  return s.typedPM[layer0] == nb::M_NONE ? launch_typed_ck<nb::M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream, s.tune_variant)
+                                         : launch_typed_ck<nb::M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream, s.tune_variant);
 }
 
 // FP32 pre-test band (see k_build_list). Positions are ghost-shifted scaled coordinates, |p| <= pmax.
@@ -1375,6 +1435,7 @@ void Engine::rebuild_list(double Lbox) {
     s.check_cached = true;
     s.mi_fresh = false;   // R0 changed: the distributed criterion state is re-evaluated on the next force call
     s.list_valid = true;
+    s.list_epoch += 1;
     stats_.cells_per_dim = M;
   }
 }

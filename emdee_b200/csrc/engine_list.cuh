@@ -306,6 +306,22 @@ __device__ __forceinline__ double strict_pbc_sq(double a, double b) {
   return __dmul_rn(d, d);
 }
 
+// row append without a branch: if (on) { if (cnt < cap) *p = v; ++cnt; }   (p = the row's slot `cnt`)
+__device__ __forceinline__ void append_if(int* p, int v, bool on, int& cnt, int cap) {
+#if defined(__CUDACC__)
+  asm volatile(
+      "{\n\t.reg .pred q, s;\n\tsetp.ne.s32 q, %3, 0;\n\tsetp.lt.and.s32 s, %0, %4, q;\n\t@s st.global.b32 [%1], %2;\n\t@q add.s32 %0, %0, 1;\n\t}"
+      : "+r"(cnt)
+      : "l"(p), "r"(v), "r"((int)on), "r"(cap)
+      : "memory");
+#else   // tests/cusim emulation build
+  if (on) {
+    if (cnt < cap) *p = v;
+    ++cnt;
+  }
+#endif
+}
+
 // (A flat form -- runs pre-clipped in lock step into shared memory, then ONE predicated loop with a per-lane trip count
 // -- was measured in round 2: 3.4x fewer warp-iterations but ~40 SASS instructions per candidate against ~16 here, and
 // 29 % slower overall (0.847 vs 0.658 ms at LJ-1M, profiles/r2c_force_build_variants.txt); removed.)
@@ -328,6 +344,9 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
     const float slack = 1.0e-5f * w + 4.0e-7f;   // covers FP32 rounding of the clip arithmetic and positions
     const float rc = (float)a.xRcs + slack;
     const float rc2 = rc * rc;
+    const float r2_accept = a.r2_accept, r2_reject = a.r2_reject;
+    const int cap = a.cap;
+    const bool slow_masks = !a.all_interact || x0 < x1;
     for (int dz = -2; dz <= 2; ++dz) {
       const float zlo = (float)(ez + dz - 2 + a.g.z0) * w, zhi = zlo + w;   // local layer -> global coordinate
       const float gz = fmaxf(0.0f, fmaxf(zlo - pf.z, pf.z - zhi) - slack);
@@ -343,27 +362,38 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
         ch = min(ch, ex + 2);
         const int row = Mx * ((ey + dy) + Mx * (ez + dz));
         const int f0 = a.cellStart[row + cl], f1 = a.cellStart[row + ch + 1];
-        for (int f = f0; f < f1; ++f) {
-          const float4 qf = __ldg(&a.sPosF[f]);
+        // Straight-line candidate test: in a warp some lane accepts at almost every iteration, so a branch around the
+        // accept path costs every lane both paths. The common case (FP32 decides, no exclusion row, every type pair
+        // interacts) runs without a branch -- predicated store, count += ok -- and one rare branch covers the rest.
+        const float4* qp = a.sPosF + f0;
+        for (int f = f0; f < f1; ++f, ++qp) {
+          const float4 qf = __ldg(qp);
           const float dxf = pf.x - qf.x, dyf = pf.y - qf.y, dzf = pf.z - qf.z;
           const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
-          if (r2f > a.r2_reject) continue;
-          if (f == e) continue;
-          if (r2f >= a.r2_accept) {   // inside the FP32 uncertainty band: decide exactly
-            const double4 rj = a.sRs[f];
-            const double r2 = __dadd_rn(__dadd_rn(strict_pbc_sq(ri.x, rj.x), strict_pbc_sq(ri.y, rj.y)),
-                                        strict_pbc_sq(ri.z, rj.z));
-            if (!(r2 < a.xRc2s)) continue;
+          const bool in32 = r2f < r2_accept;
+          const bool other = (f != e) & (__float_as_int(qf.w) != body_i);
+          if ((!in32 & !(r2f > r2_reject)) | (in32 & other & slow_masks)) {   // rare
+            bool ok = other;
+            if (!in32) {   // inside the FP32 uncertainty band: decide exactly
+              const double4 rj = a.sRs[f];
+              const double r2 = __dadd_rn(__dadd_rn(strict_pbc_sq(ri.x, rj.x), strict_pbc_sq(ri.y, rj.y)),
+                                          strict_pbc_sq(ri.z, rj.z));
+              ok = ok && (r2 < a.xRc2s);
+            }
+            if (ok && slow_masks) {   // some type pair does not interact, or this atom has an exclusion row
+              ok = a.all_interact || a.interact[type_i * a.nt + a.sType[f]];
+              if (ok && x0 < x1) {
+                const int atom_j = a.sMeta[f].x;
+                for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
+              }
+            }
+            if (ok) {
+              if (cnt < cap) out[(size_t)cnt * TILE] = f;
+              ++cnt;
+            }
+            continue;
           }
-          bool ok = (__float_as_int(qf.w) != body_i) && (a.all_interact || a.interact[type_i * a.nt + a.sType[f]]);
-          if (ok && x0 < x1) {
-            const int atom_j = a.sMeta[f].x;
-            for (int q = x0; ok && q < x1; ++q) ok = (a.exItem[q] != atom_j);
-          }
-          if (ok) {
-            if (cnt < a.cap) out[(size_t)cnt * TILE] = f;
-            ++cnt;
-          }
+          append_if(out + (size_t)cnt * TILE, f, in32 & other, cnt, cap);
         }
       }
     }
