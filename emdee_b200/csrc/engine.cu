@@ -165,11 +165,6 @@ struct Engine::Impl {
   bool kick_planned = false, kick_done = false, kick_want_ke = false;
   double kick_CP = 0, kick_CF = 0, kick_ke[3] = {0, 0, 0};
   int kick_layer = -1;
-  // duo path (k_pair_forces_duo): union rows of the entry pairs (2d, 2d+1), merged from the list once per rebuild
-  int cap2 = 0;
-  DBuf<unsigned int> duoNbr;
-  DBuf<int> duoCount;
-  long long list_epoch = 0, duo_epoch = -1;   // list_epoch advances at every rebuild; duo rows belong to duo_epoch
   // deferred kick (Engine::boost): a kick whose kinetic sums need no reduction (predicted by the previous kick, or not
   // wanted) is not launched but applied by the drift kernel that follows (k_displace<true>); everything else that reads or
   // writes momenta or forces executes it first (Engine::flush_kick)
@@ -327,7 +322,7 @@ Engine::Engine(int natoms, int ntypes, int nlayers, double Rc, double skin, cons
   s.ttabs.resize(nlayers);
   s.typedState.assign(nlayers, 0);
   s.typedPM.assign(nlayers, 0);
-  s.flags.ensure(4);
+  s.flags.ensure(8);
   s.scalars.ensure(32);
   CUDA_CHECK(cudaMemset(s.scalars.p, 0, 32 * sizeof(double)));
   s.counter.ensure(2);
@@ -942,57 +937,9 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
   X(10, 6, 128, 8, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
   X(11, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)
 
-// duo variants of the plain-LJ kernel: (unroll, threads, min blocks)
-#define EMDEE_DUO_VARIANTS(X) \
-  X(20, 4, 256, 2)            \
-  X(21, 3, 256, 2)            \
-  X(22, 4, 128, 4)            \
-  X(23, 2, 256, 3)            \
-  X(24, 6, 256, 2)            \
-  X(25, 4, 512, 1)
-
-void launch_lj_duo(Engine::Impl& s, ForceArgs& a, bool compute, int v) {
-  const int nduo = (a.Next + 1) / 2;
-  if (s.duo_epoch != s.list_epoch) {   // first launch on this list: merge the rows of consecutive entries
-    const long long dtiles = ((long long)nduo + TILE - 1) / TILE;
-    if (s.cap2 == 0) s.cap2 = (int)(1.45 * s.cap) + 8;
-    s.duoCount.ensure(nduo, 1.1);
-    for (;;) {
-      s.duoNbr.ensure((size_t)dtiles * s.cap2 * TILE, 1.1);
-      CUDA_CHECK(cudaMemsetAsync(s.flags.p + 2, 0, 2 * sizeof(int), s.stream));
-      k_merge_duos<<<nblocks(nduo), TPB, 0, s.stream>>>(a.Next, s.cap, s.cap2, s.nbr.p, s.nbrCount.p, s.duoNbr.p, s.duoCount.p,
-                                                        s.flags.p);
-      int hf[2];
-      CUDA_CHECK(cudaMemcpyAsync(hf, s.flags.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-      CUDA_CHECK(cudaStreamSynchronize(s.stream));
-      if (!hf[1]) break;
-      s.cap2 = (int)(hf[0] * 1.1) + 8;   // overflow: regrow to the observed maximum and redo
-    }
-    s.duo_epoch = s.list_epoch;
-  }
-  switch (v) {
-#define EMDEE_DUO_CASE(ID, UN, TH, MB)                                                                              \
-    case ID: {                                                                                                     \
-      const int grid = nblocks(nduo, TH);                                                                          \
-      s.partial.ensure((size_t)grid * 5);                                                                          \
-      a.partial = s.partial.p;                                                                                     \
-      if (compute) k_pair_forces_duo<true, UN, TH, MB><<<grid, TH, 0, s.stream>>>(a, s.cap2, s.duoNbr.p, s.duoCount.p);  \
-      else k_pair_forces_duo<false, UN, TH, MB><<<grid, TH, 0, s.stream>>>(a, s.cap2, s.duoNbr.p, s.duoCount.p);         \
-      break;                                                                                                       \
-    }
-    EMDEE_DUO_VARIANTS(EMDEE_DUO_CASE)
-#undef EMDEE_DUO_CASE
-    default: fatal("force kernel selection", "unknown force_variant");
-  }
-}
-
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
   const int v = s.tune_variant;
-  if (v >= 20) {
-    launch_lj_duo(s, a, compute, v);
-    return;
-  }
   switch (v) {
 #define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
@@ -1045,36 +992,31 @@ bool build_typed_table(const LayerTable& lt, std::vector<TypedEntry>& out, int& 
 }
 
 template <int PM, int CK>
-void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st, int shape) {
-  const int threads = shape == 1 ? 128 : 256;   // shape 1 (EmDeeX_tune "force_variant"): 128 x 4 instead of 256 x 2
-  const int grid = nblocks(a.Next, threads);
+void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
+  constexpr int THREADS = 128;
+  const int grid = nblocks(a.Next, THREADS);
   partial.ensure((size_t)grid * 5);
   a.partial = partial.p;
   const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
   if (a.nt == 2) {
-    if (shape == 1) {
-      if (compute) k_pair_forces_typed<PM, CK, true, true, 128, 4><<<grid, 128, 0, st>>>(a, ttab);
-      else k_pair_forces_typed<PM, CK, false, true, 128, 4><<<grid, 128, 0, st>>>(a, ttab);
-    } else {
-      if (compute) k_pair_forces_typed<PM, CK, true, true><<<grid, 256, 0, st>>>(a, ttab);
-      else k_pair_forces_typed<PM, CK, false, true><<<grid, 256, 0, st>>>(a, ttab);
-    }
+    if (compute) k_pair_forces_typed<PM, CK, true, true><<<grid, THREADS, 0, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, true><<<grid, THREADS, 0, st>>>(a, ttab);
   } else {
-    if (compute) k_pair_forces_typed<PM, CK, true, false><<<grid, 256, smem, st>>>(a, ttab);
-    else k_pair_forces_typed<PM, CK, false, false><<<grid, 256, smem, st>>>(a, ttab);
+    if (compute) k_pair_forces_typed<PM, CK, true, false><<<grid, THREADS, smem, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, false><<<grid, THREADS, smem, st>>>(a, ttab);
   }
 }
 
 template <int PM>
-bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st, int shape) {
+bool launch_typed_ck(int ck, ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, bool compute, cudaStream_t st) {
   using namespace nb;
   switch (ck) {
-    case K_COUL_NONE: launch_typed<PM, K_COUL_NONE>(a, partial, ttab, compute, st, shape); return true;
-    case K_COUL_CUT: launch_typed<PM, K_COUL_CUT>(a, partial, ttab, compute, st, shape); return true;
-    case K_COUL_SF: launch_typed<PM, K_COUL_SF>(a, partial, ttab, compute, st, shape); return true;
-    case K_COUL_DAMPED: launch_typed<PM, K_COUL_DAMPED>(a, partial, ttab, compute, st, shape); return true;
-    case K_COUL_DAMPED_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SMOOTHED>(a, partial, ttab, compute, st, shape); return true;
-    case K_COUL_DAMPED_SQUARE_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SQUARE_SMOOTHED>(a, partial, ttab, compute, st, shape); return true;
+    case K_COUL_NONE: launch_typed<PM, K_COUL_NONE>(a, partial, ttab, compute, st); return true;
+    case K_COUL_CUT: launch_typed<PM, K_COUL_CUT>(a, partial, ttab, compute, st); return true;
+    case K_COUL_SF: launch_typed<PM, K_COUL_SF>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED: launch_typed<PM, K_COUL_DAMPED>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SMOOTHED>(a, partial, ttab, compute, st); return true;
+    case K_COUL_DAMPED_SQUARE_SMOOTHED: launch_typed<PM, K_COUL_DAMPED_SQUARE_SMOOTHED>(a, partial, ttab, compute, st); return true;
     default: return false;
   }
 }
@@ -1098,8 +1040,8 @@ bool try_typed_path(Engine::Impl& s, int layer0, const LayerTable& lt, int ck, F
     }
   }
   if (s.typedState[layer0] != 1) return false;
-  return s.typedPM[layer0] == nb::M_NONE ? launch_typed_ck<nb::M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream, s.tune_variant)
-                                         : launch_typed_ck<nb::M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream, s.tune_variant);
+  return s.typedPM[layer0] == nb::M_NONE ? launch_typed_ck<nb::M_NONE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream)
+                                         : launch_typed_ck<nb::M_SHIFTED_FORCE>(ck, a, s.partial, s.ttabs[layer0].p, compute, s.stream);
 }
 
 // FP32 pre-test band (see k_build_list). Positions are ghost-shifted scaled coordinates, |p| <= pmax.
@@ -1435,7 +1377,6 @@ void Engine::rebuild_list(double Lbox) {
     s.check_cached = true;
     s.mi_fresh = false;   // R0 changed: the distributed criterion state is re-evaluated on the next force call
     s.list_valid = true;
-    s.list_epoch += 1;
     stats_.cells_per_dim = M;
   }
 }
@@ -1883,13 +1824,21 @@ void Engine::add_bonded(int layer0, double Lbox, bool bonded, bool kspace, Bonde
   ks.on = (kspace && s.ewald_on) ? 1 : 0;
   ks.alpha = s.ew_alpha; ks.beta = s.ew_beta; ks.q = s.q.p; ks.type = s.type.p; ks.tab = s.tabs[layer0].p; ks.nt = s.nt;
   if (!bonded && !ks.on) return;
+  if (dist) CUDA_CHECK(cudaMemsetAsync(s.flags.p + 4, 0, sizeof(int), s.stream));
   k_bonded<<<nblocks(s.N), TPB, 0, s.stream>>>(s.N, s.termFirst.p, s.termRef.p, s.terms.p, s.R.p, Lbox, bonded ? 1 : 0, ks,
                                                dist ? s.owned.p : nullptr, s.F.p + (size_t)layer0 * 3 * s.N, delta, s.bPartial.p,
-                                               s.tickets.p + 3, s.bScalars.p);
+                                               s.tickets.p + 3, s.bScalars.p, s.xRcSq, s.flags.p + 4);
   stats_.launches += 1;
-  if (dist) NCCL_CHECK(nccl().AllReduce(s.bScalars.p, s.bScalars.p, 6, ncclDouble, ncclSum, s.comm, s.stream));
+  int toolong = 0;
+  if (dist) {
+    NCCL_CHECK(nccl().AllReduce(s.bScalars.p, s.bScalars.p, 6, ncclDouble, ncclSum, s.comm, s.stream));
+    NCCL_CHECK(nccl().AllReduce(s.flags.p + 4, s.flags.p + 4, 1, ncclInt, ncclMax, s.comm, s.stream));   // every rank stops, or none
+    CUDA_CHECK(cudaMemcpyAsync(&toolong, s.flags.p + 4, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  }
   CUDA_CHECK(cudaMemcpyAsync(s.h_bscalars, s.bScalars.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
   CUDA_CHECK(cudaStreamSynchronize(s.stream));
+  if (toolong)
+    fatal("bonded force computation", "a bond or angle arm is longer than Rc + skin: on several GPUs its other end lies outside the halo of the atom's rank");
   out.Ebond = s.h_bscalars[0];
   out.Wbond = s.h_bscalars[1];
   out.Eangle = s.h_bscalars[2];

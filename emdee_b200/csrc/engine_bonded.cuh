@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(TPB) k_bonded(int N, const int* __restrict__ f
                                                 int bonded, BondedEwald ks, const unsigned char* __restrict__ owned,
                                                 double* __restrict__ F,
                                                 const double* __restrict__ delta, double* __restrict__ partial,
-                                                unsigned int* __restrict__ ticket, double* __restrict__ out) {
+                                                unsigned int* __restrict__ ticket, double* __restrict__ out,
+                                                double reach2, int* __restrict__ toolong) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (a < N && first[a + 1] > first[a] && (owned == nullptr || owned[a])) {   // several GPUs: each rank finishes the atoms it owns
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(TPB) k_bonded(int N, const int* __restrict__ f
           r2 += d[x] * d[x];
         }
         const double invR2 = (1.0 / (L * L)) / r2;
+        // several GPUs: a partner is current on this rank only while it lies inside the halo, i.e. closer than Rc + skin
+        if (owned != nullptr && !(r2 * (L * L) < reach2)) *toolong = 1;
         double E = 0.0, W = 0.0;
         if (bonded && tm.kind == T_BOND_HARMONIC) {
           const double r = 1.0 / sqrt(invR2), dr = r - tm.p2;
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(TPB) k_bonded(int N, const int* __restrict__ f
           bb += bv[x] * bv[x];
           ab += av[x] * bv[x];
         }
+        if (owned != nullptr && !(aa < reach2 && bb < reach2)) *toolong = 1;
         if (bonded) {
           double Ea = 0.0, Fa = 0.0;
           if (tm.kind == T_ANGLE_HARMONIC) {

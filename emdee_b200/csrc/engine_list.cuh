@@ -347,27 +347,42 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
     const float r2_accept = a.r2_accept, r2_reject = a.r2_reject;
     const int cap = a.cap;
     const bool slow_masks = !a.all_interact || x0 < x1;
-    for (int dz = -2; dz <= 2; ++dz) {
+    // bounds [f0, f1) of the entries of stencil row r = 5*(dz+2) + (dy+2) that can hold a neighbor (empty: f0 = f1)
+    auto run_bounds = [&](int r, int& f0, int& f1) {
+      const int dz = r / 5 - 2, dy = r - 5 * (r / 5) - 2;
       const float zlo = (float)(ez + dz - 2 + a.g.z0) * w, zhi = zlo + w;   // local layer -> global coordinate
       const float gz = fmaxf(0.0f, fmaxf(zlo - pf.z, pf.z - zhi) - slack);
-      for (int dy = -2; dy <= 2; ++dy) {
-        const float ylo = (float)(ey + dy - 2) * w, yhi = ylo + w;
-        const float gy = fmaxf(0.0f, fmaxf(ylo - pf.y, pf.y - yhi) - slack);
-        const float rem = rc2 - gz * gz - gy * gy;
-        if (rem <= 0.0f) continue;
-        const float hx = sqrtf(rem) + slack;
-        int cl = (int)floorf((pf.x - hx) * (float)a.g.M) + 2;   // `slack` (inside hx) exceeds the FP32 rounding here
-        int ch = (int)floorf((pf.x + hx) * (float)a.g.M) + 2;
-        cl = max(cl, ex - 2);
-        ch = min(ch, ex + 2);
-        const int row = Mx * ((ey + dy) + Mx * (ez + dz));
-        const int f0 = a.cellStart[row + cl], f1 = a.cellStart[row + ch + 1];
+      const float ylo = (float)(ey + dy - 2) * w, yhi = ylo + w;
+      const float gy = fmaxf(0.0f, fmaxf(ylo - pf.y, pf.y - yhi) - slack);
+      const float rem = rc2 - gz * gz - gy * gy;
+      f0 = f1 = 0;
+      if (rem <= 0.0f) return;
+      const float hx = sqrtf(rem) + slack;
+      int cl = (int)floorf((pf.x - hx) * (float)a.g.M) + 2;   // `slack` (inside hx) exceeds the FP32 rounding here
+      int ch = (int)floorf((pf.x + hx) * (float)a.g.M) + 2;
+      cl = max(cl, ex - 2);
+      ch = min(ch, ex + 2);
+      const int row = Mx * ((ey + dy) + Mx * (ez + dz));
+      f0 = a.cellStart[row + cl];
+      f1 = a.cellStart[row + ch + 1];
+    };
+    // Software pipeline (the kernel waits on loads, not on issue slots): the bounds of the NEXT row and the NEXT candidate's
+    // position are requested before the current one is examined.
+    int f0, f1;
+    run_bounds(0, f0, f1);
+    for (int r = 0; r < 25; ++r) {
+      int nf0 = 0, nf1 = 0;
+      if (r + 1 < 25) run_bounds(r + 1, nf0, nf1);
+      if (f0 < f1) {
         // Straight-line candidate test: in a warp some lane accepts at almost every iteration, so a branch around the
         // accept path costs every lane both paths. The common case (FP32 decides, no exclusion row, every type pair
         // interacts) runs without a branch -- predicated store, count += ok -- and one rare branch covers the rest.
         const float4* qp = a.sPosF + f0;
-        for (int f = f0; f < f1; ++f, ++qp) {
-          const float4 qf = __ldg(qp);
+        float4 qn = __ldg(qp);
+        for (int f = f0; f < f1; ++f) {
+          const float4 qf = qn;
+          ++qp;
+          if (f + 1 < f1) qn = __ldg(qp);
           const float dxf = pf.x - qf.x, dyf = pf.y - qf.y, dzf = pf.z - qf.z;
           const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
           const bool in32 = r2f < r2_accept;
@@ -396,6 +411,8 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
           append_if(out + (size_t)cnt * TILE, f, in32 & other, cnt, cap);
         }
       }
+      f0 = nf0;
+      f1 = nf1;
     }
     a.nbrCount[e] = min(cnt, a.cap);
   }

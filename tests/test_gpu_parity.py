@@ -491,42 +491,6 @@ def test_deferred_kick_reaches_every_reader():
     so.finalize()
 
 
-@pytest.mark.parametrize("variant", [20, 23])
-def test_duo_kernel_matches_oracle(variant):
-    """k_pair_forces_duo (one thread per pair of consecutive sorted entries, union rows): forces, energy, virial and the
-    trajectory against the oracle, with rebuilds in between (the union rows are re-merged after each)."""
-    def lj(lib, e, s):
-        return lib.EmDee_pair_lj_cut(e, s)
-    lib = cm.product()
-    sp, c = cm.lj_sample_system(lib, lj)
-    so, _ = cm.lj_sample_system(cm.oracle(), lj)
-    lib.EmDeeX_tune(sp.md, b"force_variant", variant)
-    for s in (sp, so):
-        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
-        s.md.Options.Compute = True
-    dt = c["Dt"]
-    for step in range(30):
-        for s in (sp, so):
-            s.boost(1.0, 0.0, 0.5 * dt)
-            s.displace(1.0, 0.0, dt)
-            s.boost(1.0, 0.0, 0.5 * dt)
-        assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-10, step
-        assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-9, step
-        if step % 10 == 0:
-            assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10, step
-    assert sp.md.Builds == so.md.Builds and sp.md.Builds > 1
-    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
-    # virial-only evaluation (Options.Compute off) through the same kernel
-    for s in (sp, so):
-        s.md.Options.Compute = False
-        s.upload("coordinates", so.download("coordinates"))
-        s.compute_forces()
-    assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-9
-    lib.EmDeeX_tune(sp.md, b"force_variant", 0)
-    sp.finalize()
-    so.finalize()
-
-
 # ---- golden numbers that came from neither C++ restatement (tests/golden/numpy_models.py) -----------------------------
 import golden_cases as gc  # noqa: E402
 
