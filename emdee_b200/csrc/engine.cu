@@ -1540,7 +1540,7 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
   const bool predicted = want_kinetic && s.ke_valid && s.ke_layer == layer0 && s.ke_CP == CP && s.ke_CF == CF && !s.exposed;
   const int want = (want_kinetic && !predicted) ? 1 : 0;
   s.ke_valid = false;
-  if (!want && !s.exposed && !s.foreign_R && !s.env_no_defer && (s.world == 1 || dist)) {
+  if (!want && !s.exposed && !s.foreign_R && !s.env_no_defer && s.world == 1) {   // (several GPUs: measured 1 % slower, see k_displace_owned)
     // nothing to reduce: the drift that follows applies this kick (k_displace<true>); flush_kick otherwise
     s.defer_on = true;
     s.defer_layer = layer0;
@@ -1600,20 +1600,16 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
 void Engine::displace(double CR, double CP) {
   Impl& s = *d_;
   const double tp0 = wall_now();
-  const bool kick = s.defer_on;   // the deferred kick rides in the drift kernel
+  if (s.world > 1) flush_kick();   // (a kick is only ever deferred on one GPU)
+  const bool kick = s.defer_on;    // the deferred kick rides in the drift kernel
   const double* Fk = kick ? s.F.p + (size_t)s.defer_layer * 3 * s.N : nullptr;
   s.defer_on = false;
   if (s.world > 1 && s.owned_valid) {
     // owned atoms only (compact list); phase 1 of the rebuild criterion on the new coordinates lands in miResult[world]
     const int tmr = timer_begin(TIMER_DISPLACE);
-    if (kick)
-      k_displace_owned<true><<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
-                                                                                 s.R0.p, s.miPartial.p, s.tickets.p + 2,
-                                                                                 s.miResult.p + s.world, s.defer_CP, s.defer_CF, Fk);
-    else
-      k_displace_owned<false><<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
-                                                                                  s.R0.p, s.miPartial.p, s.tickets.p + 2,
-                                                                                  s.miResult.p + s.world, 0.0, 0.0, nullptr);
+    k_displace_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CR, CP, s.R.p, s.P.p, s.invMass.p,
+                                                                         s.R0.p, s.miPartial.p, s.tickets.p + 2,
+                                                                         s.miResult.p + s.world);
     timer_end(tmr);
     stats_.launches += 1;
     s.mi_fresh = true;
@@ -1623,12 +1619,8 @@ void Engine::displace(double CR, double CP) {
   } else {
     // the rebuild criterion of the new coordinates lands in scalars[8] on the device; compute_forces launches the pair
     // kernel speculatively against it instead of waiting for it here
-    if (kick && s.world > 1) {   // several GPUs before the first distributed rebuild: the kick stays a kernel of its own
-      s.defer_on = true;
-      flush_kick();
-    }
     const int tmr = timer_begin(TIMER_DISPLACE);
-    if (kick && s.world == 1)
+    if (kick)
       k_displace<true><<<nblocks((s.N + APT - 1) / APT), TPB, 0, s.stream>>>(s.N, CR, CP, s.R.p, s.P.p, s.invMass.p, nullptr, s.R0.p,
                                                                              s.chkPartial.p, s.tickets.p + 2, s.scalars.p + 8,
                                                                              s.defer_CP, s.defer_CF, Fk);

@@ -121,14 +121,13 @@ __global__ void __launch_bounds__(TPB) k_boost_owned(int n, const int* __restric
 }
 
 // Drift of the owned atoms fused with phase 1 of the criterion on the NEW coordinates: (max d_i, first index) over the list
-// (KICK: the deferred kick of Engine::boost applied first, as in k_displace)
-template <bool KICK>
+// (no deferred kick here, unlike k_displace: over the owned list the momenta and forces are gathered, and the fused form
+// measured 1 % slower than the two kernels on 2 GPUs, profiles/r2f_bench_2gpu.txt)
 __global__ void __launch_bounds__(TPB) k_displace_owned(int n, const int* __restrict__ list, double CR, double CP,
-                                                        double* __restrict__ R, double* __restrict__ P,
+                                                        double* __restrict__ R, const double* __restrict__ P,
                                                         const double* __restrict__ invMass, const double* __restrict__ R0,
                                                         MaxIdx* __restrict__ partial, unsigned int* __restrict__ ticket,
-                                                        MaxIdx* __restrict__ result, double kCP, double kCF,
-                                                        const double* __restrict__ F) {
+                                                        MaxIdx* __restrict__ result) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   MaxIdx v;
   v.m = -1.0 / 0.0;
@@ -139,12 +138,7 @@ __global__ void __launch_bounds__(TPB) k_displace_owned(int n, const int* __rest
     double r[3];
 #pragma unroll
     for (int x = 0; x < 3; ++x) {
-      double p = P[3 * a + x];
-      if (KICK) {
-        p = __dadd_rn(__dmul_rn(kCP, p), __dmul_rn(kCF, F[3 * a + x]));
-        P[3 * a + x] = p;
-      }
-      r[x] = __dadd_rn(__dmul_rn(CR, R[3 * a + x]), __dmul_rn(__dmul_rn(CP, p), im));
+      r[x] = __dadd_rn(__dmul_rn(CR, R[3 * a + x]), __dmul_rn(__dmul_rn(CP, P[3 * a + x]), im));
       R[3 * a + x] = r[x];
     }
     const double dx = __dsub_rn(r[0], R0[3 * a]), dy = __dsub_rn(r[1], R0[3 * a + 1]), dz = __dsub_rn(r[2], R0[3 * a + 2]);

@@ -24,6 +24,7 @@
 
 // ---- keywords ------------------------------------------------------------------------------------------------
 #define __global__
+#define __constant__ static const
 #define __device__
 #define __host__
 #define __forceinline__ inline
@@ -443,6 +444,8 @@ inline double __hiloint2double(int hi, int lo) {
   return d;
 }
 inline long long __double2ll_rn(double a) { return std::llrint(a); }
+inline int __double2hiint(double a) { unsigned long long u; std::memcpy(&u, &a, 8); return (int)(u >> 32); }
+inline int __double2loint(double a) { unsigned long long u; std::memcpy(&u, &a, 8); return (int)(u & 0xffffffffull); }
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 inline void sincospi(double x, double* s, double* c) { sincos(3.14159265358979323846 * x, s, c); }
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
