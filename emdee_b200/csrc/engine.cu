@@ -998,12 +998,15 @@ void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, b
   partial.ensure((size_t)grid * 5);
   a.partial = partial.p;
   const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
-  if (a.nt == 2) {
-    if (compute) k_pair_forces_typed<PM, CK, true, true><<<grid, THREADS, 0, st>>>(a, ttab);
-    else k_pair_forces_typed<PM, CK, false, true><<<grid, THREADS, 0, st>>>(a, ttab);
+  if (a.nt == 1) {
+    if (compute) k_pair_forces_typed<PM, CK, true, 1><<<grid, THREADS, 0, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, 1><<<grid, THREADS, 0, st>>>(a, ttab);
+  } else if (a.nt == 2) {
+    if (compute) k_pair_forces_typed<PM, CK, true, 2><<<grid, THREADS, 0, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, 2><<<grid, THREADS, 0, st>>>(a, ttab);
   } else {
-    if (compute) k_pair_forces_typed<PM, CK, true, false><<<grid, THREADS, smem, st>>>(a, ttab);
-    else k_pair_forces_typed<PM, CK, false, false><<<grid, THREADS, smem, st>>>(a, ttab);
+    if (compute) k_pair_forces_typed<PM, CK, true, 0><<<grid, THREADS, smem, st>>>(a, ttab);
+    else k_pair_forces_typed<PM, CK, false, 0><<<grid, THREADS, smem, st>>>(a, ttab);
   }
 }
 
@@ -1427,8 +1430,12 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   const bool lj_plain = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_NONE && !a.q4_quirk;
   const bool lj_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_SHIFTED_FORCE && ck == K_COUL_NONE && !a.q4_quirk;
   const bool lj_coul_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_SF && cm == M_NONE;
-  if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && try_typed_path(s, layer0, lt, ck, a, compute)) {
-    // several types, every pair model pair_lj_cut (one modifier) or pair_none: k_pair_forces_typed, launched by try_typed_path
+  // every pair model pair_lj_cut (one modifier: none or shifted_force) or pair_none, Coulomb kind cut / sf / damped family:
+  // k_pair_forces_typed (branch-free pair term). Plain single-type LJ has its own leaner kernel; force_variant 30 (lab) sends
+  // single-type LJ + sf / LJ + coul_sf through the generic kernel with a branch per pair instead.
+  const bool typed_ok = s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && !(s.nt == 1 && (lj_plain || s.tune_variant == 30));
+  if (typed_ok && try_typed_path(s, layer0, lt, ck, a, compute)) {
+    // launched by try_typed_path
   } else if (s.nt == 1 && lj_plain)
     launch_lj_plain(s, a, compute);
   else if (s.nt == 1 && lj_sf)
@@ -1466,7 +1473,7 @@ void Engine::launch_planned_kick(bool speculative) {
   const int ke = s.kick_want_ke ? 1 : 0;
   const int tmr = timer_begin(TIMER_BOOST);
   if (s.world > 1) {
-    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.kick_CP, s.kick_CF, s.P.p, Fl,
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn, TPB * BOOST_EPT)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.kick_CP, s.kick_CF, s.P.p, Fl,
                                                                       s.invMass.p, ke, s.partial.p, s.tickets.p + 1, s.scalars.p + 5,
                                                                       speculative ? s.scalars.p + CRIT_DIST : nullptr, s.skinSq);
   } else {
@@ -1508,7 +1515,7 @@ void Engine::flush_kick() {
   const double* Fl = s.F.p + (size_t)s.defer_layer * 3 * s.N;
   const int tmr = timer_begin(TIMER_BOOST);
   if (s.world > 1 && s.owned_valid)
-    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.defer_CP, s.defer_CF, s.P.p, Fl,
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn, TPB * BOOST_EPT)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, s.defer_CP, s.defer_CF, s.P.p, Fl,
                                                                       s.invMass.p, 0, s.partial.p, s.tickets.p + 1, s.scalars.p + 10,
                                                                       nullptr, 0.0);
   else
@@ -1555,7 +1562,7 @@ void Engine::boost(int layer0, double CP, double CF, bool want_kinetic, KineticS
   const int tmr = timer_begin(TIMER_BOOST);
   if (dist) {
     // several GPUs: the kick runs over the compact list of owned atoms (work ~ atoms of this rank, not N)
-    k_boost_owned<<<std::max(1, nblocks(s.nOwn)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CP, CF, s.P.p, Fl, s.invMass.p, want,
+    k_boost_owned<<<std::max(1, nblocks(s.nOwn, TPB * BOOST_EPT)), TPB, 0, s.stream>>>(s.nOwn, s.ownedList.p, CP, CF, s.P.p, Fl, s.invMass.p, want,
                                                                       s.partial.p, s.tickets.p + 1, s.scalars.p + 10, nullptr, 0.0);
     timer_end(tmr);
     stats_.launches += 1;

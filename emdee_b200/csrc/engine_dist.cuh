@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(TPB) k_check_owned(int n, const int* __restric
 
 // Free-atom kick of the owned atoms (k_boost through the owned list: the work is O(atoms of this rank), not O(N)); the
 // two sets of kinetic sums and the speculative `crit` as in k_boost
+constexpr int BOOST_EPT = 4;
 __global__ void __launch_bounds__(TPB) k_boost_owned(int n, const int* __restrict__ list, double CP, double CF,
                                                      double* __restrict__ P, const double* __restrict__ F,
                                                      const double* __restrict__ invMass, int want_ke,
@@ -87,19 +88,23 @@ __global__ void __launch_bounds__(TPB) k_boost_owned(int n, const int* __restric
                                                      double* __restrict__ out, const double* __restrict__ crit, double skinSq) {
   __shared__ double red[TPB / 32][6];
   if (crit != nullptr && __ldcg(crit) > skinSq) return;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  // BOOST_EPT list entries per thread, a block-stride apart (coalesced): the grid-wide finish folds 4x fewer block partials
   double ke[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (k < n) {
-    const size_t a = (size_t)list[k];
-    const double im = invMass[a];
 #pragma unroll
-    for (int x = 0; x < 3; ++x) {
-      const double f = F[3 * a + x];
-      const double q = __dadd_rn(__dmul_rn(CP, P[3 * a + x]), __dmul_rn(CF, f));
-      P[3 * a + x] = q;
-      ke[x] = __dmul_rn(__dmul_rn(im, q), q);
-      const double q2 = __dadd_rn(__dmul_rn(CP, q), __dmul_rn(CF, f));
-      ke[3 + x] = __dmul_rn(__dmul_rn(im, q2), q2);
+  for (int j = 0; j < BOOST_EPT; ++j) {
+    const int k = blockIdx.x * (blockDim.x * BOOST_EPT) + j * blockDim.x + threadIdx.x;
+    if (k < n) {
+      const size_t a = (size_t)list[k];
+      const double im = invMass[a];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        const double f = F[3 * a + x];
+        const double q = __dadd_rn(__dmul_rn(CP, P[3 * a + x]), __dmul_rn(CF, f));
+        P[3 * a + x] = q;
+        ke[x] += __dmul_rn(__dmul_rn(im, q), q);
+        const double q2 = __dadd_rn(__dmul_rn(CP, q), __dmul_rn(CF, f));
+        ke[3 + x] += __dmul_rn(__dmul_rn(im, q2), q2);
+      }
     }
   }
   if (!want_ke) return;
