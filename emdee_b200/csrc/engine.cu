@@ -998,10 +998,7 @@ void launch_typed(ForceArgs& a, DBuf<double>& partial, const TypedEntry* ttab, b
   partial.ensure((size_t)grid * 5);
   a.partial = partial.p;
   const size_t smem = (size_t)a.nt * a.nt * sizeof(TypedEntry);
-  if (a.nt == 1) {
-    if (compute) k_pair_forces_typed<PM, CK, true, 1><<<grid, THREADS, 0, st>>>(a, ttab);
-    else k_pair_forces_typed<PM, CK, false, 1><<<grid, THREADS, 0, st>>>(a, ttab);
-  } else if (a.nt == 2) {
+  if (a.nt == 2) {
     if (compute) k_pair_forces_typed<PM, CK, true, 2><<<grid, THREADS, 0, st>>>(a, ttab);
     else k_pair_forces_typed<PM, CK, false, 2><<<grid, THREADS, 0, st>>>(a, ttab);
   } else {
@@ -1430,18 +1427,25 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   const bool lj_plain = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_NONE && !a.q4_quirk;
   const bool lj_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_SHIFTED_FORCE && ck == K_COUL_NONE && !a.q4_quirk;
   const bool lj_coul_sf = uniform && pk == K_PAIR_LJ_CUT && pm == M_NONE && ck == K_COUL_SF && cm == M_NONE;
-  // every pair model pair_lj_cut (one modifier: none or shifted_force) or pair_none, Coulomb kind cut / sf / damped family:
-  // k_pair_forces_typed (branch-free pair term). Plain single-type LJ has its own leaner kernel; force_variant 30 (lab) sends
-  // single-type LJ + sf / LJ + coul_sf through the generic kernel with a branch per pair instead.
-  const bool typed_ok = s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && !(s.nt == 1 && (lj_plain || s.tune_variant == 30));
-  if (typed_ok && try_typed_path(s, layer0, lt, ck, a, compute)) {
-    // launched by try_typed_path
+  // several types, every pair model pair_lj_cut (one modifier: none or shifted_force) or pair_none, Coulomb kind cut / sf /
+  // damped family: k_pair_forces_typed (branch-free pair term), launched by try_typed_path. (Single-type LJ + coul_sf through
+  // the same kernel, without type lookups, measured 0.443 ms against 0.385 ms for the generic kernel below at 1M atoms --
+  // 128 registers against 85 -- and stays with the generic kernel; profiles/r2g_coul_sf_typed_vs_generic.txt.)
+  if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && try_typed_path(s, layer0, lt, ck, a, compute)) {
   } else if (s.nt == 1 && lj_plain)
     launch_lj_plain(s, a, compute);
   else if (s.nt == 1 && lj_sf)
     launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
-  else if (s.nt == 1 && lj_coul_sf)
-    launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
+  else if (s.nt == 1 && lj_coul_sf) {
+    switch (s.tune_variant) {   // launch shapes of the LJ + coul_sf kernel (lab: EMDEE_FORCE_VARIANT)
+      case 31: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 6, 512, 2>(a, s.partial, compute, 0, s.stream); break;
+      case 32: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 4, 512, 2>(a, s.partial, compute, 0, s.stream); break;
+      case 33: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 6, 256, 3>(a, s.partial, compute, 0, s.stream); break;
+      case 34: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 3, 256, 4>(a, s.partial, compute, 0, s.stream); break;
+      case 35: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2, 256, 4>(a, s.partial, compute, 0, s.stream); break;
+      default: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
+    }
+  }
   else
     launch_force<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 4, 256, 2>(a, s.partial, compute, smem_dyn, s.stream);
   timer_end(tmr);
