@@ -1436,16 +1436,8 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
     launch_lj_plain(s, a, compute);
   else if (s.nt == 1 && lj_sf)
     launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
-  else if (s.nt == 1 && lj_coul_sf) {
-    switch (s.tune_variant) {   // launch shapes of the LJ + coul_sf kernel (lab: EMDEE_FORCE_VARIANT)
-      case 31: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 6, 512, 2>(a, s.partial, compute, 0, s.stream); break;
-      case 32: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 4, 512, 2>(a, s.partial, compute, 0, s.stream); break;
-      case 33: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 6, 256, 3>(a, s.partial, compute, 0, s.stream); break;
-      case 34: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 3, 256, 4>(a, s.partial, compute, 0, s.stream); break;
-      case 35: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 2, 256, 4>(a, s.partial, compute, 0, s.stream); break;
-      default: launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
-    }
-  }
+  else if (s.nt == 1 && lj_coul_sf)   // unroll 3 / 256 threads / 4 blocks: fastest of six launch shapes (profiles/r2g_coul_sf_typed_vs_generic.txt)
+    launch_force<K_PAIR_LJ_CUT, M_NONE, K_COUL_SF, M_NONE, true, true, 3, 256, 4>(a, s.partial, compute, 0, s.stream);
   else
     launch_force<K_DYNAMIC, M_DYNAMIC, K_DYNAMIC, M_DYNAMIC, false, true, 4, 256, 2>(a, s.partial, compute, smem_dyn, s.stream);
   timer_end(tmr);
