@@ -1134,6 +1134,14 @@ bool Engine::compute_forces(int layer0, bool compute, double Lbox, ForceScalars&
     stats_.launches += 2;
   } else if (s.check_cached && s.list_valid && s.world == 1) {
     speculative = true;
+  } else if (s.list_valid && s.world == 1) {
+    // the coordinates came from an upload (or may have been written through a raw pointer): the criterion is evaluated on the
+    // device and stays there -- the pair kernel is launched speculatively against it, as after a drift; no host wait here
+    k_displacement_check<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p, s.tickets.p + 2, s.scalars.p + 8,
+                                                           nullptr, 0ull);
+    stats_.launches += 1;
+    s.check_cached = true;   // scalars[8] stays valid until the coordinates or R0 change
+    speculative = true;
   } else {
     const unsigned long long seq = s.next_seq(SLOT_CHECK);
     k_displacement_check<<<nblocks(N), TPB, 0, s.stream>>>(s.R.p, s.R0.p, N, s.chkPartial.p, s.tickets.p + 2,
