@@ -595,7 +595,7 @@ void exchange_step(Engine::Impl& s, bool with_criterion) {
     // NVLink peer path: halo coordinates go straight into the neighbors' arrays, the criterion state into every mailbox
     const unsigned long long seq = ++s.xseq;
     const int nUp = halo ? s.haloCount[0] : 0, nDn = halo ? s.haloCount[1] : 0;
-    k_push_step<<<std::max(1, nblocks(nUp + nDn)), TPB, 0, s.stream>>>(nUp, s.haloList[0].p, nDn, s.haloList[1].p, s.R.p, s.peerR[up],
+    k_push_step<<<std::max(1, nblocks(3LL * (nUp + nDn))), TPB, 0, s.stream>>>(nUp, s.haloList[0].p, nDn, s.haloList[1].p, s.R.p, s.peerR[up],
                                                                       s.peerR[dn], halo ? 1 : 0, with_criterion ? 1 : 0,
                                                                       s.miResult.p + s.world, s.peers, s.world, s.rank, up, dn, seq,
                                                                       s.tickets.p + 3);
@@ -1353,7 +1353,8 @@ void Engine::rebuild_list(double Lbox) {
       // write-out was measured 6x slower at LJ-1M -- serial per-atom dependency chains at ~12 warps/SM --
       // and removed)
       const int tmr = timer_begin(1);
-      k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      if (s.tune_variant == 40) k_build_list<2><<<nblocks(Next), TPB, 0, s.stream>>>(b);   // (lab)
+      else k_build_list<1><<<nblocks(Next), TPB, 0, s.stream>>>(b);
       timer_end(tmr);
       stats_.launches += 1;
       stats_.build_launches += 1;

@@ -255,19 +255,23 @@ __global__ void __launch_bounds__(TPB) k_push_step(int nUp, const int* __restric
                                                    int world, int rank, int up, int dn, unsigned long long seq,
                                                    unsigned int* __restrict__ ticket) {
   __shared__ bool last;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (with_halo && k < nUp + nDn) {
+  // one thread per DOUBLE (3 per halo atom): consecutive lanes write consecutive words of the neighbor's array wherever the
+  // halo atoms are consecutive in the atom index, so the peer stores leave the SM as full sectors instead of 8-byte
+  // fragments 24 bytes apart; one system fence per block (by the thread that then takes the ticket) instead of one per thread
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (with_halo && j < 3LL * (nUp + nDn)) {
+    const int k = (int)(j / 3);
+    const int x = (int)(j - 3LL * k);
     const bool isUp = k < nUp;
     const size_t a = (size_t)(isUp ? listUp[k] : listDn[k - nUp]);
     double* dst = isUp ? Rup : Rdn;
-    const double x = R[3 * a], y = R[3 * a + 1], z = R[3 * a + 2];
-    dst[3 * a] = x;
-    dst[3 * a + 1] = y;
-    dst[3 * a + 2] = z;
-    __threadfence_system();
+    dst[3 * a + x] = R[3 * a + x];
   }
   __syncthreads();
-  if (threadIdx.x == 0) last = (take_ticket(ticket) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (take_ticket(ticket) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!last) return;
   __threadfence_system();
