@@ -939,7 +939,7 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
 
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
-  const int v = s.tune_variant;
+  const int v = s.tune_variant >= 40 ? 0 : s.tune_variant;   // (40+: list-build lab variants)
   switch (v) {
 #define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
