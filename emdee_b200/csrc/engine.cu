@@ -165,6 +165,10 @@ struct Engine::Impl {
   bool kick_planned = false, kick_done = false, kick_want_ke = false;
   double kick_CP = 0, kick_CF = 0, kick_ke[3] = {0, 0, 0};
   int kick_layer = -1;
+  // compact-record path (k_pair_forces_rec16): 16-byte fixed-point records refreshed every step + cell-tagged copy of the list
+  DBuf<Rec16> rec16;
+  DBuf<unsigned int> taggedNbr;
+  long long list_epoch = 0, tag_epoch = -1;   // list_epoch advances at every rebuild; the tagged copy belongs to tag_epoch
   // deferred kick (Engine::boost): a kick whose kinetic sums need no reduction (predicted by the previous kick, or not
   // wanted) is not launched but applied by the drift kernel that follows (k_displace<true>); everything else that reads or
   // writes momenta or forces executes it first (Engine::flush_kick)
@@ -921,21 +925,34 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
 }
 
 // Plain single-type Lennard-Jones: the benchmark kernel. Variant 0 is what ships; the others exist for tools/force_lab.py
-// (EmDeeX_tune "force_variant" / "carveout"), which times them back to back on one resident system.
+// (EmDeeX_tune "force_variant" / "carveout"), which times them back to back on one resident system: 1 = the form with a
+// branch per pair, 3 / 4 = the "gathers only" / "arithmetic only" probes. (Launch shapes, unroll depths and cache policies
+// were swept in round 2 -- profiles/r2c_force_build_variants.txt -- and their instantiations removed.)
 //   columns: UNROLL, THREADS, MINBLOCKS, index-stream load, position-gather load, PROBE, FORM
 #define EMDEE_LJ_VARIANTS(X)                                                \
   X(0, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
   X(1, 6, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_DEFAULT)                      \
-  X(2, 6, 512, 2, LD_NO_ALLOCATE, LD_PLAIN, 0, FORM_BRANCHLESS)             \
   X(3, 6, 512, 2, LD_PLAIN, LD_PLAIN, 1, FORM_DEFAULT)                      \
-  X(4, 6, 512, 2, LD_PLAIN, LD_PLAIN, 2, FORM_DEFAULT)                      \
-  X(5, 5, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
-  X(6, 6, 256, 4, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
-  X(7, 7, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                   \
-  X(8, 6, 1024, 1, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
-  X(9, 6, 512, 2, LD_PLAIN, LD_EVICT_LAST, 0, FORM_BRANCHLESS)              \
-  X(10, 6, 128, 8, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)                  \
-  X(11, 4, 512, 2, LD_PLAIN, LD_PLAIN, 0, FORM_BRANCHLESS)
+  X(4, 6, 512, 2, LD_PLAIN, LD_PLAIN, 2, FORM_DEFAULT)
+
+// compact-record variant of the plain-LJ kernel (lab variant 50; single GPU, fewer than 2^23 sorted entries)
+void launch_lj_rec16(Engine::Impl& s, ForceArgs& a, bool compute, double Lbox, bool speculative) {
+  const int Next = a.Next;
+  const long long ntiles = ((long long)Next + TILE - 1) / TILE;
+  if (s.tag_epoch != s.list_epoch) {   // first launch on this list: tagged copy of the rows
+    s.taggedNbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
+    k_tag_list<<<nblocks(Next), TPB, 0, s.stream>>>(Next, s.cap, s.grid.Mx, s.nbr.p, s.nbrCount.p, s.sCell.p, s.taggedNbr.p);
+    s.tag_epoch = s.list_epoch;
+  }
+  s.rec16.ensure(Next, 1.1);
+  k_refresh_rec16<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.grid.M, s.grid.Mx, s.R.p, s.sMeta.p, s.sCell.p, s.rec16.p,
+                                                       speculative ? s.scalars.p + 8 : nullptr, s.skinSq);
+  const int grid = nblocks(Next, 512);
+  s.partial.ensure((size_t)grid * 5);
+  a.partial = s.partial.p;
+  if (compute) k_pair_forces_rec16<true, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
+  else k_pair_forces_rec16<false, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
+}
 
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
@@ -1386,6 +1403,7 @@ void Engine::rebuild_list(double Lbox) {
     s.check_cached = true;
     s.mi_fresh = false;   // R0 changed: the distributed criterion state is re-evaluated on the next force call
     s.list_valid = true;
+    s.list_epoch += 1;
     stats_.cells_per_dim = M;
   }
 }
@@ -1441,7 +1459,9 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   // the same kernel, without type lookups, measured 0.443 ms against 0.385 ms for the generic kernel below at 1M atoms --
   // 128 registers against 85 -- and stays with the generic kernel; profiles/r2g_coul_sf_typed_vs_generic.txt.)
   if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && try_typed_path(s, layer0, lt, ck, a, compute)) {
-  } else if (s.nt == 1 && lj_plain)
+  } else if (s.nt == 1 && lj_plain && s.tune_variant == 50 && s.world == 1 && Next < (1 << REC16_INDEX_BITS))
+    launch_lj_rec16(s, a, compute, Lbox, speculative);
+  else if (s.nt == 1 && lj_plain)
     launch_lj_plain(s, a, compute);
   else if (s.nt == 1 && lj_sf)
     launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);
