@@ -947,11 +947,27 @@ void launch_lj_rec16(Engine::Impl& s, ForceArgs& a, bool compute, double Lbox, b
   s.rec16.ensure(Next, 1.1);
   k_refresh_rec16<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.grid.M, s.grid.Mx, s.R.p, s.sMeta.p, s.sCell.p, s.rec16.p,
                                                        speculative ? s.scalars.p + 8 : nullptr, s.skinSq);
-  const int grid = nblocks(Next, 512);
-  s.partial.ensure((size_t)grid * 5);
-  a.partial = s.partial.p;
-  if (compute) k_pair_forces_rec16<true, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
-  else k_pair_forces_rec16<false, 6, 512, 2><<<grid, 512, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);
+  switch (s.tune_variant) {   // (lab) unroll, threads, min blocks, index prefetch
+#define EMDEE_REC16_CASE(ID, UN, TH, MB, PF)                                                                                     \
+    case ID: {                                                                                                                  \
+      const int grid = nblocks(Next, TH);                                                                                       \
+      s.partial.ensure((size_t)grid * 5);                                                                                       \
+      a.partial = s.partial.p;                                                                                                  \
+      if (compute) k_pair_forces_rec16<true, UN, TH, MB, PF><<<grid, TH, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);  \
+      else k_pair_forces_rec16<false, UN, TH, MB, PF><<<grid, TH, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);         \
+      break;                                                                                                                    \
+    }
+    EMDEE_REC16_CASE(50, 6, 512, 2, false)
+    EMDEE_REC16_CASE(51, 8, 512, 2, false)
+    EMDEE_REC16_CASE(52, 6, 512, 2, true)
+    EMDEE_REC16_CASE(53, 8, 512, 2, true)
+    EMDEE_REC16_CASE(54, 4, 512, 2, true)
+    EMDEE_REC16_CASE(55, 6, 256, 4, true)
+    EMDEE_REC16_CASE(56, 6, 1024, 1, true)
+    EMDEE_REC16_CASE(57, 10, 512, 2, false)
+#undef EMDEE_REC16_CASE
+    default: fatal("force kernel selection", "unknown force_variant");
+  }
 }
 
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
@@ -1459,7 +1475,7 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   // the same kernel, without type lookups, measured 0.443 ms against 0.385 ms for the generic kernel below at 1M atoms --
   // 128 registers against 85 -- and stays with the generic kernel; profiles/r2g_coul_sf_typed_vs_generic.txt.)
   if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && try_typed_path(s, layer0, lt, ck, a, compute)) {
-  } else if (s.nt == 1 && lj_plain && s.tune_variant == 50 && s.world == 1 && Next < (1 << REC16_INDEX_BITS))
+  } else if (s.nt == 1 && lj_plain && s.tune_variant >= 50 && s.tune_variant < 60 && s.world == 1 && Next < (1 << REC16_INDEX_BITS))
     launch_lj_rec16(s, a, compute, Lbox, speculative);
   else if (s.nt == 1 && lj_plain)
     launch_lj_plain(s, a, compute);
