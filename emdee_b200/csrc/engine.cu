@@ -165,10 +165,6 @@ struct Engine::Impl {
   bool kick_planned = false, kick_done = false, kick_want_ke = false;
   double kick_CP = 0, kick_CF = 0, kick_ke[3] = {0, 0, 0};
   int kick_layer = -1;
-  // compact-record path (k_pair_forces_rec16): 16-byte fixed-point records refreshed every step + cell-tagged copy of the list
-  DBuf<Rec16> rec16;
-  DBuf<unsigned int> taggedNbr;
-  long long list_epoch = 0, tag_epoch = -1;   // list_epoch advances at every rebuild; the tagged copy belongs to tag_epoch
   // deferred kick (Engine::boost): a kick whose kinetic sums need no reduction (predicted by the previous kick, or not
   // wanted) is not launched but applied by the drift kernel that follows (k_displace<true>); everything else that reads or
   // writes momenta or forces executes it first (Engine::flush_kick)
@@ -935,44 +931,9 @@ void launch_force(ForceArgs& a, DBuf<double>& partial, bool compute, size_t smem
   X(3, 6, 512, 2, LD_PLAIN, LD_PLAIN, 1, FORM_DEFAULT)                      \
   X(4, 6, 512, 2, LD_PLAIN, LD_PLAIN, 2, FORM_DEFAULT)
 
-// compact-record variant of the plain-LJ kernel (lab variant 50; single GPU, fewer than 2^23 sorted entries)
-void launch_lj_rec16(Engine::Impl& s, ForceArgs& a, bool compute, double Lbox, bool speculative) {
-  const int Next = a.Next;
-  const long long ntiles = ((long long)Next + TILE - 1) / TILE;
-  if (s.tag_epoch != s.list_epoch) {   // first launch on this list: tagged copy of the rows
-    s.taggedNbr.ensure((size_t)ntiles * s.cap * TILE, 1.1);
-    k_tag_list<<<nblocks(Next), TPB, 0, s.stream>>>(Next, s.cap, s.grid.Mx, s.nbr.p, s.nbrCount.p, s.sCell.p, s.taggedNbr.p);
-    s.tag_epoch = s.list_epoch;
-  }
-  s.rec16.ensure(Next, 1.1);
-  k_refresh_rec16<<<nblocks(Next), TPB, 0, s.stream>>>(Next, Lbox, s.grid.M, s.grid.Mx, s.R.p, s.sMeta.p, s.sCell.p, s.rec16.p,
-                                                       speculative ? s.scalars.p + 8 : nullptr, s.skinSq);
-  switch (s.tune_variant) {   // (lab) unroll, threads, min blocks, index prefetch
-#define EMDEE_REC16_CASE(ID, UN, TH, MB, PF)                                                                                     \
-    case ID: {                                                                                                                  \
-      const int grid = nblocks(Next, TH);                                                                                       \
-      s.partial.ensure((size_t)grid * 5);                                                                                       \
-      a.partial = s.partial.p;                                                                                                  \
-      if (compute) k_pair_forces_rec16<true, UN, TH, MB, PF><<<grid, TH, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);  \
-      else k_pair_forces_rec16<false, UN, TH, MB, PF><<<grid, TH, 0, s.stream>>>(a, s.grid.M, s.rec16.p, s.taggedNbr.p);         \
-      break;                                                                                                                    \
-    }
-    EMDEE_REC16_CASE(50, 6, 512, 2, false)
-    EMDEE_REC16_CASE(51, 8, 512, 2, false)
-    EMDEE_REC16_CASE(52, 6, 512, 2, true)
-    EMDEE_REC16_CASE(53, 8, 512, 2, true)
-    EMDEE_REC16_CASE(54, 4, 512, 2, true)
-    EMDEE_REC16_CASE(55, 6, 256, 4, true)
-    EMDEE_REC16_CASE(56, 6, 1024, 1, true)
-    EMDEE_REC16_CASE(57, 10, 512, 2, false)
-#undef EMDEE_REC16_CASE
-    default: fatal("force kernel selection", "unknown force_variant");
-  }
-}
-
 void launch_lj_plain(Engine::Impl& s, ForceArgs& a, bool compute) {
   using namespace nb;
-  const int v = s.tune_variant >= 40 ? 0 : s.tune_variant;   // (40+: list-build lab variants)
+  const int v = s.tune_variant;
   switch (v) {
 #define EMDEE_LJ_CASE(ID, UN, TH, MB, LL, PL, PR, FO)                                                                       \
     case ID: {                                                                                                             \
@@ -1386,8 +1347,7 @@ void Engine::rebuild_list(double Lbox) {
       // write-out was measured 6x slower at LJ-1M -- serial per-atom dependency chains at ~12 warps/SM --
       // and removed)
       const int tmr = timer_begin(1);
-      if (s.tune_variant == 40) k_build_list<2><<<nblocks(Next), TPB, 0, s.stream>>>(b);   // (lab)
-      else k_build_list<1><<<nblocks(Next), TPB, 0, s.stream>>>(b);
+      k_build_list<<<nblocks(Next), TPB, 0, s.stream>>>(b);
       timer_end(tmr);
       stats_.launches += 1;
       stats_.build_launches += 1;
@@ -1419,7 +1379,6 @@ void Engine::rebuild_list(double Lbox) {
     s.check_cached = true;
     s.mi_fresh = false;   // R0 changed: the distributed criterion state is re-evaluated on the next force call
     s.list_valid = true;
-    s.list_epoch += 1;
     stats_.cells_per_dim = M;
   }
 }
@@ -1475,9 +1434,7 @@ void Engine::launch_pair_kernel(int layer0, bool compute, double Lbox, bool spec
   // the same kernel, without type lookups, measured 0.443 ms against 0.385 ms for the generic kernel below at 1M atoms --
   // 128 registers against 85 -- and stays with the generic kernel; profiles/r2g_coul_sf_typed_vs_generic.txt.)
   if (s.nt > 1 && s.nt <= MAX_SMEM_TYPES && !a.q4_quirk && cm == M_NONE && try_typed_path(s, layer0, lt, ck, a, compute)) {
-  } else if (s.nt == 1 && lj_plain && s.tune_variant >= 50 && s.tune_variant < 60 && s.world == 1 && Next < (1 << REC16_INDEX_BITS))
-    launch_lj_rec16(s, a, compute, Lbox, speculative);
-  else if (s.nt == 1 && lj_plain)
+  } else if (s.nt == 1 && lj_plain)
     launch_lj_plain(s, a, compute);
   else if (s.nt == 1 && lj_sf)
     launch_force<K_PAIR_LJ_CUT, M_SHIFTED_FORCE, K_COUL_NONE, M_NONE, true, true, 4, 256, 3>(a, s.partial, compute, 0, s.stream);

@@ -325,7 +325,6 @@ __device__ __forceinline__ void append_if(int* p, int v, bool on, int& cnt, int 
 // (A flat form -- runs pre-clipped in lock step into shared memory, then ONE predicated loop with a per-lane trip count
 // -- was measured in round 2: 3.4x fewer warp-iterations but ~40 SASS instructions per candidate against ~16 here, and
 // 29 % slower overall (0.847 vs 0.658 ms at LJ-1M, profiles/r2c_force_build_variants.txt); removed.)
-template <int WIDE>
 __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ BuildArgs a) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
@@ -406,26 +405,15 @@ __global__ void __launch_bounds__(TPB) k_build_list(const __grid_constant__ Buil
           }
           append_if(out + (size_t)cnt * TILE, f, in32 & other, cnt, cap);
         };
+        // (two candidates per iteration with both positions requested ahead measured the same 0.56 ms at 62 registers
+        // instead of 48 -- GPU call 24 -- and was not kept)
         const float4* qp = a.sPosF + f0;
-        if (WIDE == 2) {   // (lab) two candidates per iteration, the next two positions requested before these are examined
-          float4 qa = __ldg(qp), qb = qa;
-          if (f0 + 1 < f1) qb = __ldg(qp + 1);
-          for (int f = f0; f < f1; f += 2) {
-            const float4 ca = qa, cb = qb;
-            qp += 2;
-            if (f + 2 < f1) qa = __ldg(qp);
-            if (f + 3 < f1) qb = __ldg(qp + 1);
-            examine(ca, f);
-            if (f + 1 < f1) examine(cb, f + 1);
-          }
-        } else {
-          float4 qn = __ldg(qp);
-          for (int f = f0; f < f1; ++f) {
-            const float4 qf = qn;
-            ++qp;
-            if (f + 1 < f1) qn = __ldg(qp);
-            examine(qf, f);
-          }
+        float4 qn = __ldg(qp);
+        for (int f = f0; f < f1; ++f) {
+          const float4 qf = qn;
+          ++qp;
+          if (f + 1 < f1) qn = __ldg(qp);
+          examine(qf, f);
         }
       }
       f0 = nf0;

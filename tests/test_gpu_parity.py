@@ -491,38 +491,6 @@ def test_deferred_kick_reaches_every_reader():
     so.finalize()
 
 
-def test_compact_record_kernel_matches_oracle():
-    """k_pair_forces_rec16 (force_variant 50): 16-byte fixed-point records relative to the build-time cell, cell offsets in
-    the list entries, separations as differences of magic-number doubles. Forces, energy, virial and the trajectory against
-    the oracle over rebuilds (atoms cross cells; the tagged list is rebuilt after each) at the tolerances of the 32-byte kernel."""
-    def lj(lib, e, s):
-        return lib.EmDee_pair_lj_cut(e, s)
-    lib = cm.product()
-    sp, c = cm.lj_sample_system(lib, lj)
-    so, _ = cm.lj_sample_system(cm.oracle(), lj)
-    lib.EmDeeX_tune(sp.md, b"force_variant", 50)
-    for s in (sp, so):
-        s.random_momenta(c["kB"] * c["Temp"], True, c["seed"])
-        s.md.Options.Compute = True
-        s.compute_forces()
-    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
-    dt = c["Dt"]
-    for step in range(30):
-        for s in (sp, so):
-            s.boost(1.0, 0.0, 0.5 * dt)
-            s.displace(1.0, 0.0, dt)
-            s.boost(1.0, 0.0, 0.5 * dt)
-        assert cm.rel(sp.md.Energy.Potential, so.md.Energy.Potential) < 1e-10, step
-        assert cm.rel(sp.md.Virial.Total, so.md.Virial.Total) < 1e-9, step
-        if step % 10 == 0:
-            assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10, step
-    assert sp.md.Builds == so.md.Builds and sp.md.Builds > 1
-    assert cm.rel_force_error(sp.download("forces"), so.download("forces")) < 1e-10
-    lib.EmDeeX_tune(sp.md, b"force_variant", 0)
-    sp.finalize()
-    so.finalize()
-
-
 # ---- golden numbers that came from neither C++ restatement (tests/golden/numpy_models.py) -----------------------------
 import golden_cases as gc  # noqa: E402
 
