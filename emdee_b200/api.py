@@ -131,6 +131,7 @@ ABI_EXT_PRODUCT = {
     "EmDeeX_tune": (None, [tEmDee, C.c_char_p, C.c_int]),
     "EmDeeX_stream": (C.c_void_p, [tEmDee]),
     "EmDeeX_measure_fp64_tflops": (C.c_double, []),
+    "EmDeeX_math_probe": (None, [C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "EmDeeX_comm_unique_id": (None, [C.c_char_p]),
     "EmDeeX_comm_init": (None, [tEmDee, C.c_int, C.c_int, C.c_char_p]),
     "EmDeeX_slab_range": (None, [C.c_int, C.c_int, C.c_int, _ip, _ip]),

@@ -1378,6 +1378,7 @@ void EmDeeX_io_bytes(tEmDee md, long long* h2d, long long* d2h) { sys(md)->engin
 void EmDeeX_tune(tEmDee md, const char* knob, int value) { sys(md)->engine->tune(knob, value); }
 void* EmDeeX_stream(tEmDee md) { return sys(md)->engine->stream_handle(); }
 double EmDeeX_measure_fp64_tflops(void) { return emdee::measure_fp64_fma_tflops(); }
+void EmDeeX_math_probe(int what, int n, const double* in, double* out) { emdee::math_probe(what, n, in, out); }
 void EmDeeX_comm_unique_id(char* out128) { emdee::comm_unique_id(out128); }
 void EmDeeX_comm_init(tEmDee md, int rank, int world, const char* unique_id) {
   System* me = sys(md);

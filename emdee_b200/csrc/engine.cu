@@ -2153,6 +2153,38 @@ void Engine::rdf(double Lbox, int bins, double Rc2_scaled, double bins_by_Rc_sca
   sym.release();
 }
 
+namespace {
+// device arithmetic helpers evaluated on an array of inputs (EmDeeX_math_probe; tests/test_gpu_device_math.py)
+__global__ void k_math_probe(int what, int n, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = in[i];
+  double y;
+  switch (what) {
+    case 0: y = fast_rcp(x); break;                        // plain-LJ pair term
+    case 1: y = nb::rcp(x); break;                         // model bodies
+    case 2: y = exp_nonpos(x); break;                      // typed kernel: exp of a non-positive argument
+    case 3: y = uerfc_c(x, exp_nonpos(-x * x)); break;     // typed kernel: the reference's erfc
+    case 4: y = nb::uerfc(x, exp(-x * x)); break;          // generic kernel: the same formula with the library exp
+    default: y = 0.0;
+  }
+  out[i] = y;
+}
+}  // namespace
+
+void math_probe(int what, int n, const double* in, double* out) {
+  if (n <= 0) return;
+  double *din = nullptr, *dout = nullptr;
+  CUDA_CHECK(cudaMalloc(&din, (size_t)n * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&dout, (size_t)n * sizeof(double)));
+  CUDA_CHECK(cudaMemcpy(din, in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  k_math_probe<<<nblocks(n), TPB>>>(what, n, din, dout);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpy(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaFree(din));
+  CUDA_CHECK(cudaFree(dout));
+}
+
 double measure_fp64_fma_tflops() {
   int dev = 0, sms = 0;
   CUDA_CHECK(cudaGetDevice(&dev));

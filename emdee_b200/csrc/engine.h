@@ -176,4 +176,8 @@ void comm_unique_id(void* out128);
 // DFMA microbenchmark on the current device: sustained FP64 FMA throughput in TFLOP/s.
 double measure_fp64_fma_tflops();
 
+// Evaluates one of the kernels' arithmetic helpers on n host inputs (what: 0 fast_rcp, 1 nb::rcp, 2 exp_nonpos, 3 uerfc_c,
+// 4 nb::uerfc with the library exp); test hook for the device-only code paths.
+void math_probe(int what, int n, const double* in, double* out);
+
 }  // namespace emdee

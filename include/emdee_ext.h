@@ -80,6 +80,11 @@ void* EmDeeX_stream( tEmDee md );
    roofline denominator; MEASURED_PEAKS.json carries only HBM and bf16 figures). */
 double EmDeeX_measure_fp64_tflops( void );
 
+/* Test hook: evaluates one of the kernels' device-only arithmetic helpers on n inputs (what: 0 = reciprocal of the plain-LJ
+   pair term, 1 = reciprocal of the model bodies, 2 = exp of a non-positive argument as the typed kernel computes it,
+   3 = the reference's erfc(x) (src/math.f90:685-691) as the typed kernel computes it, 4 = the same with the library exp). */
+void EmDeeX_math_probe( int what, int n, const double* in, double* out );
+
 /* ---- product-only: multi-GPU (one process per GPU, z-slab decomposition over NCCL) -------------
    Every rank creates the SAME system with the same calls and the same full-size arrays (SPMD). Rank 0
    obtains a 128-byte NCCL id, the launcher broadcasts it (e.g. torch.distributed), and every rank calls

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(path):
     for name in declared_symbols("emdee.h"):
         assert hasattr(dll, name), f"{os.path.basename(path)} lacks {name}"
     ext = declared_symbols("emdee_ext.h")
-    product_only = {"EmDeeX_stats", "EmDeeX_tune", "EmDeeX_set_kernel_timing", "EmDeeX_synchronize", "EmDeeX_kernel_times", "EmDeeX_io_bytes", "EmDeeX_comm_mode", "EmDeeX_stream", "EmDeeX_measure_fp64_tflops",
+    product_only = {"EmDeeX_stats", "EmDeeX_tune", "EmDeeX_set_kernel_timing", "EmDeeX_synchronize", "EmDeeX_kernel_times", "EmDeeX_io_bytes", "EmDeeX_comm_mode", "EmDeeX_stream", "EmDeeX_measure_fp64_tflops", "EmDeeX_math_probe",
                     "EmDeeX_comm_unique_id", "EmDeeX_comm_init", "EmDeeX_slab_range"}
     for name in ext:
         if path == cm.ORACLE_STRICT and name in product_only:
