@@ -631,7 +631,7 @@ void exchange_step(Engine::Impl& s, bool with_criterion) {
 }
 void halo_exchange(Engine::Impl& s) { exchange_step(s, false); }
 
-// rebuild-time migration: see k_mig_flags. Returns with R, P current for every atom this rank may need.
+// rebuild-time migration: see k_mig_flags_listed. Returns with R, P current for every atom this rank may need.
 void migrate(Engine::Impl& s, double Lbox) {
   const int N = s.N;
   s.known.ensure(N);

@@ -378,25 +378,7 @@ __global__ void __launch_bounds__(TPB) k_mask_owned(int N, const unsigned char* 
 // every rank, each rank sends its owned atoms that now sit within three cell layers of a slab face (or just
 // beyond it) to the neighbor on that side, as (id, R, P) records. After that a rank "knows" its previously
 // owned atoms plus what it received -- a superset of its new slab + 2-layer halo, because nothing moves more
-// than skin/2 < one layer between rebuilds -- and re-bins only those.
-__global__ void __launch_bounds__(TPB) k_mig_flags(int N, double L, GridDesc g, const double* __restrict__ R,
-                                                   const unsigned char* __restrict__ owned,
-                                                   unsigned char* __restrict__ fl) {   // 2 flag arrays of N
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  bool up = false, dn = false;
-  if (owned[i]) {
-    const double rs = __ddiv_rn(R[3 * (size_t)i + 2], L);
-    int cz = (int)__dmul_rn((double)g.M, __dsub_rn(rs, floor(rs)));
-    if (cz >= g.M) cz = g.M - 1;
-    const int z1 = g.z0 + g.nzl;
-    up = ((cz - (z1 - 3)) % g.M + g.M) % g.M < 5;     // layers z1-3 .. z1+1 (periodic)
-    dn = (((g.z0 + 2) - cz) % g.M + g.M) % g.M < 5;   // layers z0-2 .. z0+2
-  }
-  fl[i] = up;
-  fl[(size_t)N + i] = dn;
-}
-
+// than skin/2 < one layer between rebuilds -- and re-bins only those (k_mig_flags_listed / k_unpack7_listed below).
 __global__ void __launch_bounds__(TPB) k_pack7(int n, const int* __restrict__ list, const double* __restrict__ R,
                                                const double* __restrict__ P, double* __restrict__ buf) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,19 +391,6 @@ __global__ void __launch_bounds__(TPB) k_pack7(int n, const int* __restrict__ li
     b[1 + x] = R[3 * (size_t)a + x];
     b[4 + x] = P[3 * (size_t)a + x];
   }
-}
-__global__ void __launch_bounds__(TPB) k_unpack7(int n, const double* __restrict__ buf, double* __restrict__ R,
-                                                 double* __restrict__ P, unsigned char* __restrict__ known) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const double* b = buf + 7 * (size_t)k;
-  const int a = (int)b[0];
-#pragma unroll
-  for (int x = 0; x < 3; ++x) {
-    R[3 * (size_t)a + x] = b[1 + x];
-    P[3 * (size_t)a + x] = b[4 + x];
-  }
-  known[a] = 1;
 }
 
 // ---- compact forms: the same decisions over a LIST of atoms (what this rank owned at the last build, plus what it just
