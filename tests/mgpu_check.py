@@ -301,5 +301,47 @@ def main():
     dist.destroy_process_group()
 
 
+def long_bond_scenario():
+    """EMDEE_MGPU_LONG_BOND=1: a harmonic bond longer than Rc + skin on the slab-decomposed path. The partner of an owned atom
+    then lies outside the rank's halo and its coordinates go stale: every rank must stop with the library's message (Error in
+    bonded force computation ...) instead of computing a wrong force. The caller checks exit code and stderr."""
+    rank, world, local = edist.env_rank_world()
+    if os.environ.get("EMDEE_MGPU_EMULATED") == "1":
+        dist.init_process_group("gloo")
+        lib = cm.emulated()
+    else:
+        torch.cuda.set_device(local)
+        os.environ["EMDEE_DEVICE"] = str(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        lib = cm.product()
+    c = cm.load_fixture("NIST_spce_sample")
+    nmol, L = 125, 18.0
+    rng = np.random.default_rng(3)
+    grid = np.array([[i, j, k] for i in range(5) for j in range(5) for k in range(5)], dtype=float) * 3.5 + 0.7
+    mol = np.array([[0.0, 0.0, 0.0], [0.8, 0.58, 0.0], [-0.8, 0.58, 0.0]])
+    R = (grid[:, None, :] + mol[None, :, :]).reshape(-1, 3) + rng.normal(scale=0.05, size=(3 * nmol, 3))
+    types = np.tile(np.array([1, 2, 2], dtype=np.int32), nmol)
+    s = lib.system(2, 1, 5.0, 0.8, 3 * nmol, types, c["mass"], None)
+    edist.init_comm(lib, s)
+    eps = c["epsilon"] / c["mvv2e"]
+    s.set_pair_model(1, 1, lib.EmDee_shifted_force(lib.EmDee_pair_lj_cut(eps[0], c["sigma"][0])), c["kCoul"])
+    s.set_pair_model(2, 2, lib.EmDee_pair_none(), c["kCoul"])
+    s.set_coul_model(lib.EmDee_shifted_force(lib.EmDee_coul_cut()))
+    bond = lib.EmDee_bond_harmonic(0.9, 1.0)
+    for m in range(nmol):
+        o = 3 * m + 1
+        s.lib.EmDee_add_bond(s.md, o, o + 1, bond)
+        s.lib.EmDee_add_bond(s.md, o, o + 2, bond)
+    s.lib.EmDee_add_bond(s.md, 1, 3 * 2 + 1, bond)   # O of molecule 0 - O of molecule 2: 7 A along z > Rc + skin = 5.8 A
+    s.upload("charges", np.tile(np.array([-0.8476, 0.4238, 0.4238]), nmol))
+    s.upload("box", np.array([L]))
+    s.upload("coordinates", R)          # first box + coordinates: forces are computed here -> the library stops
+    s.compute_forces()
+    print("[mgpu] long bond was NOT rejected", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if os.environ.get("EMDEE_MGPU_LONG_BOND") == "1":
+        long_bond_scenario()
+    else:
+        main()

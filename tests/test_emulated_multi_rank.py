@@ -45,3 +45,16 @@ def test_slab_decomposition_on_emulator(world, libs):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "[mgpu] ALL OK" in r.stdout
+
+
+def test_bond_longer_than_the_halo_is_rejected_on_every_rank(libs):
+    """several GPUs: a bonded partner outside the halo would be read with stale coordinates; the library stops instead
+    (Engine::add_bonded, k_bonded `toolong`), on all ranks (the flag is all-reduced), with its usual message format"""
+    env = dict(os.environ, EMDEE_MGPU_EMULATED="1", EMDEE_NCCL_LIB=libs, FAKE_NCCL_TIMEOUT="60", EMDEE_QUIET="1",
+               OMP_NUM_THREADS="1", EMDEE_MGPU_LONG_BOND="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29711", os.path.join(cm.ROOT, "tests", "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode != 0
+    assert "NOT rejected" not in r.stdout
+    assert r.stderr.count("Error in bonded force computation: a bond or angle arm is longer than Rc + skin") >= 1, r.stderr[-3000:]
